@@ -1,0 +1,290 @@
+/*
+ * rbgtopo.h — C ABI of the B200-native topology-aware placement engine for
+ * sgl-project/rbg RoleBasedGroups.
+ *
+ * This is the drop-in boundary. The reference has NO FFI for
+ * this path: its plugin boundary is the Go interface
+ * scheduler.PodGroupManager (pkg/scheduler/podgroup_manager.go:64-78), selected
+ * by --scheduler-name (cmd/rbgs/main.go:148-152) through NewPodGroupManager
+ * (pkg/scheduler/podgroup_manager.go:82-92).  A third PodGroupManager
+ * implementation ("b200-topo") binds the entry points below
+ * through cgo.  Every entry point cites the reference symbol whose output it
+ * consumes or whose call site it plugs into.
+ *
+ * Rules of the ABI
+ *   - plain C: int32_t/int64_t/uint64_t/float pointers + sizes, no C++ types,
+ *     no torch types, no exceptions across the boundary, never abort().
+ *   - every function returns an int32 status: 0 = RBGTOPO_OK, <0 = error; the
+ *     text is available from rbgtopo_last_error().
+ *   - the caller owns every buffer it passes; nothing is retained after return
+ *     (cgo pointer rules).  The opaque rbgtopo_ctx owns all device memory,
+ *     streams and staging buffers.
+ *   - thread-safe: up to --max-concurrent-reconciles goroutines (default 10,
+ *     cmd/rbgs/main.go:140-143) may call into one ctx concurrently; calls take
+ *     a slot (stream + pinned staging + device scratch) from an internal pool.
+ *   - there is NO CPU fallback: without a CUDA device rbgtopo_create fails
+ *     with RBGTOPO_ENODEVICE.  (The Go shim then degrades to "no placement
+ *     hint", the controller's behaviour today.)
+ *
+ * The batch wire format ("blob") is one contiguous int32 array so that a Go
+ * []int32 can be handed over with a single unsafe.Pointer and DMA'd to the GPU
+ * unmodified; the kernels index it directly.  Layout in the BLOB section.
+ */
+#ifndef RBGTOPO_H_
+#define RBGTOPO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBGTOPO_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------ */
+#define RBGTOPO_OK          0
+#define RBGTOPO_EINVAL     -1  /* malformed argument / blob                     */
+#define RBGTOPO_ENODEVICE  -2  /* no CUDA device / wrong arch (needs sm_100)     */
+#define RBGTOPO_ECUDA      -3  /* CUDA runtime error (text in last_error)       */
+#define RBGTOPO_EINEXACT   -4  /* input violates the fp32 exactness contract     */
+#define RBGTOPO_ENOTOPO    -5  /* score/assign called before set_topology        */
+#define RBGTOPO_ELIMIT     -6  /* a documented limit (roles/step, K, N) exceeded */
+#define RBGTOPO_ENOMEM     -7
+
+/* ---- spec constants (frozen) ----------------------------- */
+#define RBGTOPO_F_CAP            8     /* A.2: min(free[m], F)                  */
+#define RBGTOPO_SELF_W           8000  /* A.3: self term = 8 x NVLink weight    */
+#define RBGTOPO_NEED_CAP         16    /* A.2: need_rho is clamped by the host   */
+#define RBGTOPO_MAX_STEP_ROLES   8     /* role rows scored per step             */
+#define RBGTOPO_MAX_STEP_REPLICAS 32   /* = KMAX; bigger levels go in waves     */
+#define RBGTOPO_MAX_GROUP_ROLES  16    /* pair-matrix columns (Q)               */
+#define RBGTOPO_MAX_FREE         32767 /* free[n], consumed amounts             */
+#define RBGTOPO_MAX_EDGE_W       65535
+
+/* step flags */
+#define RBGTOPO_STEP_EXCLUSIVE   1  /* group-exclusive-topology set:
+                                       api/workloads/constants/annotation.go:25,
+                                       pkg/reconciler/pod_reconciler.go:125-137 */
+#define RBGTOPO_STEP_GANG        2  /* group-gang-scheduling == "true":
+                                       api/workloads/constants/annotation.go:37 */
+/* role flags */
+#define RBGTOPO_ROLE_EXCLUSIVE   1  /* role takes part in exclusive topology; 0 =
+                                       role-disable-exclusive opt-out
+                                       (annotation.go:29,60; pod_reconciler.go:127) */
+
+/* per-step result status */
+#define RBGTOPO_PLACED_ALL   0
+#define RBGTOPO_PLACED_PART  1  /* some replicas have no feasible node (-1)     */
+#define RBGTOPO_GANG_FAILED  2  /* gang step: nothing placed, all -1            */
+
+/* ---- BLOB: one batch of placement steps -------------------------------- *
+ * A "step" is one wave of one dependency level of one RoleBasedGroup: the
+ * roles of that level (pkg/dependency/dependency.go:129-205 order) with their
+ * pending replica counts (rolebasedgroup_controller.go:509-518 override by the
+ * coordination target, scaler.go:141-169), at most RBGTOPO_MAX_STEP_REPLICAS
+ * replicas.  All int32 words, little endian:
+ *
+ *   word 0  magic 0x54474252 ("RBGT")      word 1  RBGTOPO_ABI_VERSION
+ *   word 2  n_steps                        word 3  total words in the blob
+ *   word 4  total replicas  (sum of R)     word 5  total role rows (sum of P)
+ *   word 6,7 reserved (0)
+ *   then n_steps step records of RBGTOPO_STEP_WORDS words:
+ *     +0 gid            group id (>=0), compared with domain_owner[]
+ *     +1 flags          RBGTOPO_STEP_*
+ *     +2 fixed_domain   -1, or the domain the group already occupies
+ *     +3 n_roles  P     1..RBGTOPO_MAX_STEP_ROLES
+ *     +4 role_off       word offset of P role records (4 words each:
+ *                       count, demand, need, role_flags)
+ *     +5 q              number of group roles = pair-matrix columns (0..16)
+ *     +6 pair_off       word offset of pair[P][q] (row-major int32)
+ *     +7 n_anchors      pods of this group already placed (sparse anchor[q][n])
+ *     +8 anchor_off     word offset of n_anchors records (node, role q, count)
+ *     +9 n_consumed     nodes whose capacity this group already took in this
+ *                       reconcile and that free[] does not reflect yet
+ *     +10 consumed_off  word offset of n_consumed records (node, amount)
+ *     +11 n_replicas R  = sum of role counts, 1..RBGTOPO_MAX_STEP_REPLICAS
+ *     +12 replica_off   prefix sum of R over earlier steps (row of the dense
+ *                       matrix and index into assign[])
+ *     +13 rolerow_off   prefix sum of P over earlier steps
+ *     +14,15 reserved (0)
+ *   then the variable sections the offsets point at.
+ * Replica order inside a step: role records in the given order (the host
+ * passes them lexicographically, dependency.go:133-137), ordinal ascending
+ * (stateful_instance_set_utils.go:74-76).
+ * ------------------------------------------------------------------------ */
+#define RBGTOPO_BLOB_MAGIC   0x54474252
+#define RBGTOPO_HDR_WORDS    8
+#define RBGTOPO_STEP_WORDS   16
+#define RBGTOPO_ROLE_WORDS   4
+#define RBGTOPO_ANCHOR_WORDS 3
+#define RBGTOPO_CONS_WORDS   2
+
+typedef struct rbgtopo_ctx rbgtopo_ctx;
+
+typedef struct rbgtopo_config {
+  int32_t device;        /* CUDA device ordinal                                */
+  int32_t rank;          /* node-axis shard of this process, 0..world-1        */
+  int32_t world;         /* number of node-axis shards (GPUs), >= 1            */
+  int32_t slots;         /* concurrent in-flight calls, 0 = default (4)        */
+  int32_t emit_matrix;   /* 1 = materialise the dense (replica x node) matrix
+                            (north_star default); 0 = fused select only        */
+  int32_t chunk_nodes;   /* nodes per CTA work item, 0 = default (2048)        */
+  int32_t reserved[2];
+} rbgtopo_config;
+
+/* Per-call device timing, milliseconds from CUDA events on the call's stream. */
+typedef struct rbgtopo_timing {
+  float h2d_ms, base_ms, score_ms, select_ms, d2h_ms, total_ms;
+  int32_t launches;      /* kernels launched by the call                       */
+  int32_t reserved;
+  int64_t scores;        /* (replica x node) scores produced by the call       */
+  int64_t algo_bytes;    /* algorithmic bytes of the score kernel, DESIGN §5   */
+} rbgtopo_timing;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+/* Plug-in construction: called from the b200-topo case added to
+ * NewPodGroupManager (pkg/scheduler/podgroup_manager.go:82-92). */
+int32_t rbgtopo_create(const rbgtopo_config* cfg, rbgtopo_ctx** out);
+int32_t rbgtopo_destroy(rbgtopo_ctx* ctx);
+int32_t rbgtopo_abi_version(void);
+/* Copies the calling thread's last error text for ctx (ctx may be NULL for
+ * create failures); returns the text length. */
+int32_t rbgtopo_last_error(rbgtopo_ctx* ctx, char* buf, int32_t len);
+
+/* ---- cluster snapshot (new input; the reference has no node informer,
+ *      SURVEY.md §8f rank 1).  Called when the Node cache changes. ---------- */
+/* CSR must be symmetric (undirected topology), col_idx strictly ascending per
+ * row, no self loops; edge_w in [0, RBGTOPO_MAX_EDGE_W]; free in
+ * [0, RBGTOPO_MAX_FREE]; domain in [0, n_domains); domain_owner[d] = -1 or gid.
+ * `generation` is echoed by rbgtopo_stats; the device-resident CSR is the cache
+ * keyed by it (SURVEY.md §5 checkpoint row). */
+int32_t rbgtopo_set_topology(rbgtopo_ctx* ctx, int32_t n_nodes, int64_t n_edges,
+                             const int32_t* row_ptr, const int32_t* col_idx,
+                             const int32_t* edge_w, const int32_t* free_slots,
+                             const int32_t* domain, int32_t n_domains,
+                             const int32_t* domain_owner, uint64_t generation);
+/* Capacity / ownership refresh between reconciles (scheduled-pod counts change:
+ * rolebasedgroup_controller.go:1057-1080).  Either pointer may be NULL. */
+int32_t rbgtopo_update_nodes(rbgtopo_ctx* ctx, const int32_t* free_slots,
+                             const int32_t* domain_owner, uint64_t generation);
+
+/* ---- the hot path ------------------------------------------------------- */
+/* Score + select + greedy-assign one batch of steps (host buffers in, host
+ * buffers out; H2D/D2H inside).  Plugs in between step 5 and step 7 of
+ * Reconcile (rolebasedgroup_controller.go:193-207), i.e. from
+ * ReconcilePodGroup (podgroup_manager.go:67-73).
+ *   blob / blob_words  : the batch (layout above)
+ *   assign[total R]    : node per replica in replica order, -1 = unplaced
+ *   status[n_steps]    : RBGTOPO_PLACED_* per step
+ *   domain[n_steps]    : exclusive domain chosen / confirmed, -1 if none
+ * With world > 1 this entry is invalid (use the shard calls below). */
+int32_t rbgtopo_score_assign(rbgtopo_ctx* ctx, const int32_t* blob,
+                             int64_t blob_words, int32_t* assign,
+                             int32_t* status, int32_t* domain);
+
+/* Same computation with the batch kept resident in HBM (bench `value` leg,
+ * CUDA-graph replay): stage once, run many times, fetch results on demand. */
+int32_t rbgtopo_stage(rbgtopo_ctx* ctx, const int32_t* blob, int64_t blob_words,
+                      int32_t* handle);
+int32_t rbgtopo_run_staged(rbgtopo_ctx* ctx, int32_t handle, int32_t iters);
+int32_t rbgtopo_fetch(rbgtopo_ctx* ctx, int32_t handle, int32_t* assign,
+                      int32_t* status, int32_t* domain);
+int32_t rbgtopo_release(rbgtopo_ctx* ctx, int32_t handle);
+
+/* Inspection of a staged+run batch (parity tests): one dense row
+ * scores[n_nodes] of replica `row` (global replica index; local slab only when
+ * world > 1: out has slab length), and the merged top-K keys of one role row. */
+int32_t rbgtopo_read_scores(rbgtopo_ctx* ctx, int32_t handle, int32_t row,
+                            float* out, int32_t out_len);
+int32_t rbgtopo_read_topk(rbgtopo_ctx* ctx, int32_t handle, int32_t rolerow,
+                          uint64_t* out_keys, int32_t k);
+
+/* ---- node-axis sharding over `world` GPUs --------------- *
+ * rank g scores columns [slab_lo, slab_hi) and selects a local top-K; the
+ * caller all-gathers the key lists (NCCL, one collective per pass) and every
+ * rank runs the identical merge + greedy.
+ *   shard_score : run score+select for the local slab of a staged batch;
+ *                 *keys_dev / *keys_bytes = device buffer to all-gather.
+ *   shard_merge : keys_all_dev = world x keys_bytes gathered buffer.  Returns
+ *                 *need_pass2 = 1 when some exclusive step has to reselect
+ *                 inside its chosen domain; then *keys2_dev/*keys2_bytes is
+ *                 the second (small) buffer to all-gather.
+ *   shard_assign: final merge + greedy (keys2_all_dev may be NULL when
+ *                 need_pass2 was 0); results via rbgtopo_fetch. */
+int32_t rbgtopo_shard_score(rbgtopo_ctx* ctx, int32_t handle, void** keys_dev,
+                            int64_t* keys_bytes);
+int32_t rbgtopo_shard_merge(rbgtopo_ctx* ctx, int32_t handle,
+                            const void* keys_all_dev, int32_t* need_pass2,
+                            void** keys2_dev, int64_t* keys2_bytes);
+int32_t rbgtopo_shard_assign(rbgtopo_ctx* ctx, int32_t handle,
+                             const void* keys2_all_dev);
+int32_t rbgtopo_slab(rbgtopo_ctx* ctx, int32_t* lo, int32_t* hi);
+
+/* Use an external CUDA stream (e.g. the one the caller's NCCL runs on) for
+ * every call on this ctx; NULL restores the internal per-slot streams. */
+int32_t rbgtopo_set_stream(rbgtopo_ctx* ctx, void* cuda_stream);
+
+/* ---- stats (SURVEY.md §5 metrics row) ----------------------------------- */
+int32_t rbgtopo_last_timing(rbgtopo_ctx* ctx, rbgtopo_timing* out);
+int32_t rbgtopo_stats(rbgtopo_ctx* ctx, uint64_t* generation, int64_t* calls,
+                      int64_t* scores_total, int64_t* kernel_launches);
+
+/* ======================================================================== *
+ * Host-side plugin arithmetic (reference-pinned).
+ * In production the Go shim calls the controller's own Go functions; these
+ * C mirrors exist so that a C/C++/Python host above the ABI builds the same
+ * steps the Go host would.  All follow the cited Go code exactly.
+ * ======================================================================== */
+
+/* RoleBasedGroup.GetGroupSize, api/workloads/v1alpha2/helper.go:50-65.
+ * lws_size[i] <= 0 means "not a leader-worker role or size unset". */
+int32_t rbgtopo_group_size(int32_t n_roles, const int32_t* replicas,
+                           const int32_t* lws_size);
+
+/* dependencyOrder, pkg/dependency/dependency.go:129-205.  Roles are given in
+ * any order by name; dep_off[n_roles+1]/dep_idx index into the same role list.
+ * Writes level_of[n_roles] and order[n_roles] (role indices sorted by (level,
+ * name)); returns the number of levels, or RBGTOPO_EINVAL on a cycle. */
+int32_t rbgtopo_dependency_levels(int32_t n_roles, const char* const* names,
+                                  const int32_t* dep_off, const int32_t* dep_idx,
+                                  int32_t* level_of, int32_t* order);
+
+/* parsePercentage, pkg/coordination/coordinationscaling/scaler.go:253-270. */
+int32_t rbgtopo_parse_percentage(const char* s, double* out);
+
+/* CoordinationScaler.CalculateTargetReplicas, scaler.go:70-172 (+ progression
+ * gate :192-242).  progression: 0 = OrderScheduled (default), 1 = OrderReady. */
+int32_t rbgtopo_calculate_target_replicas(double max_skew, int32_t progression,
+                                          int32_t n_roles,
+                                          const int32_t* desired,
+                                          const int32_t* current,
+                                          const int32_t* scheduled,
+                                          const int32_t* ready,
+                                          int32_t* target);
+
+/* GetScaledValueFromIntOrPercent,
+ * vendor/k8s.io/apimachinery/pkg/util/intstr/intstr.go:181-197. */
+int32_t rbgtopo_scaled_value(int32_t is_percent, int32_t value, int32_t total,
+                             int32_t round_up);
+
+/* calculateCoordinationUpdatedReplicasBound,
+ * rolebasedgroup_controller.go:1328-1345. */
+int32_t rbgtopo_updated_replicas_bound(int32_t max_skew_percent,
+                                       int32_t ref_updated, int32_t ref_desired,
+                                       int32_t request_desired, int32_t* lower,
+                                       int32_t* upper);
+
+/* calculateNextRollingTarget, rolebasedgroup_controller.go:1223-1263 (with
+ * getFastestAndSlowestRole :1265-1282; ties beyond the reference's comparator
+ * are broken by role index).  rolling_target[n_roles] out. Returns 0, or 1 when
+ * the reference returns nil (fewer than two roles). */
+int32_t rbgtopo_next_rolling_target(int32_t max_skew_percent, int32_t n_roles,
+                                    const int32_t* desired,
+                                    const int32_t* updated,
+                                    const int32_t* ready,
+                                    int32_t* rolling_target);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBGTOPO_H_ */
