@@ -204,10 +204,10 @@ int32_t rbgtopo_read_topk(rbgtopo_ctx* ctx, int32_t handle, int32_t rolerow,
  * caller all-gathers the key lists (NCCL, one collective per pass) and every
  * rank runs the identical merge + greedy.
  *   shard_score : run score+select for the local slab of a staged batch;
- *                 *keys_dev / *keys_bytes = device buffer to all-gather.
+ *                 (keys_dev, keys_bytes) = device buffer to all-gather.
  *   shard_merge : keys_all_dev = world x keys_bytes gathered buffer.  Returns
  *                 *need_pass2 = 1 when some exclusive step has to reselect
- *                 inside its chosen domain; then *keys2_dev/*keys2_bytes is
+ *                 inside its chosen domain; then (keys2_dev, keys2_bytes) is
  *                 the second (small) buffer to all-gather.
  *   shard_assign: final merge + greedy (keys2_all_dev may be NULL when
  *                 need_pass2 was 0); results via rbgtopo_fetch. */
@@ -253,7 +253,8 @@ int32_t rbgtopo_dependency_levels(int32_t n_roles, const char* const* names,
 int32_t rbgtopo_parse_percentage(const char* s, double* out);
 
 /* CoordinationScaler.CalculateTargetReplicas, scaler.go:70-172 (+ progression
- * gate :192-242).  progression: 0 = OrderScheduled (default), 1 = OrderReady. */
+ * gate :192-242).  progression: 0 = unset (the Go switch then gates nothing),
+ * 1 = OrderScheduled, 2 = OrderReady. */
 int32_t rbgtopo_calculate_target_replicas(double max_skew, int32_t progression,
                                           int32_t n_roles,
                                           const int32_t* desired,

@@ -1,0 +1,14 @@
+"""rbg_b200 — B200-native topology-aware placement hot path for sgl-project/rbg.
+
+Only what the path needs lives here:
+  csrc/      sm_100a CUDA kernels + the C-ABI runtime (librbgtopo.so, include/rbgtopo.h)
+  _lib.py    ctypes binding of the C ABI (fails loudly when the .so is missing)
+  engine.py  thin object wrapper over a rbgtopo_ctx
+  blob.py    builder of the batch wire format
+  plugin.py  host-side mirror of the reference plugin surface
+             (scheduler.PodGroupManager, pkg/scheduler/podgroup_manager.go:64-78)
+  synth.py   seeded synthetic topologies / RBG fleets
+There is no CPU fallback anywhere in this package.
+"""
+from .blob import BlobBuilder, Step  # noqa: F401
+from .engine import TopoPlacer, RbgTopoError  # noqa: F401

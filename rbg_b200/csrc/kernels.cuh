@@ -1,0 +1,507 @@
+// kernels.cuh — sm_100a kernels of the placement hot path.
+//
+// Algebra: the spec's score  S_rho = W·A_rho  with
+// A_rho = sum_q pair[rho][q]·anchor[q] + need_rho·min(free,F)  is linear in A, so
+//     S_rho[n] = need_rho · base[n]  +  sum over anchor pods (m,q,c) of
+//                pair[rho][q]·c·W[n][m]
+// with base = W·min(free,F) shared by EVERY step of a snapshot (one CSR pass per
+// snapshot, k_base) and the anchor term sparse (<= (deg+1) entries per pod,
+// scattered into shared memory per work item).  All terms are exact integers
+// below 2^24 (spec §3.4), so this is bit-identical to the oracle's sequential
+// fp32 accumulation.  The dense (replica x node) matrix is then a pure HBM
+// write stream fused with the per-row top-K selection (k_score_select).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rbgtopo.h"
+
+namespace rbgtopo {
+
+constexpr int KS = RBGTOPO_MAX_STEP_REPLICAS;  // list stride (= KMAX = 32)
+constexpr int MAXP = RBGTOPO_MAX_STEP_ROLES;
+constexpr int MAXQ = RBGTOPO_MAX_GROUP_ROLES;
+constexpr int SCORE_THREADS = 256;
+constexpr int SCORE_WARPS = SCORE_THREADS / 32;
+constexpr int BASE_THREADS = 256;
+constexpr int BASE_TILE_ROWS = 256;
+constexpr int BASE_TILE_NNZ = 6144;       // 2 x 24 KB staged by TMA bulk copies
+constexpr int FMIN_SMEM_MAX = 131072;     // nodes whose u8 fmin vector is staged
+constexpr uint32_t FULL = 0xFFFFFFFFu;
+
+struct TopoDev {
+  int n;                 // nodes
+  int slab_lo, slab_hi;  // node-axis shard of this rank
+  int slab_stride;       // floats per matrix row (slab length rounded up to 32)
+  const int* row_ptr;
+  const int* col;
+  const int* w;
+  const int* free_;
+  const int* domain;
+  const int* node_owner;      // owner[domain[n]]
+  const unsigned char* fmin;  // min(free, F) as u8, padded to 16 B
+  const float* base;          // W·fmin, padded to slab_stride past slab_hi
+  const int* dom_ptr;         // nodes grouped by domain (CSR)
+  const int* dom_nodes;
+};
+
+struct BatchDev {
+  const int* blob;
+  int n_steps;
+  int lc;           // chunks per step on this rank
+  int chunk;        // nodes per chunk (multiple of 128)
+  int parts;        // ranks (list parts to merge)
+  int emit_matrix;
+  float* matrix;              // [total R][slab_stride]
+  unsigned long long* lists;  // [rolerows][lc][KS] local per-chunk top-K
+  const unsigned long long* lists_all;  // [parts][rolerows][lc][KS]
+  long long part_stride;                // u64 elements between parts
+  unsigned long long* merged;  // [rolerows][KS]
+  unsigned long long* excl;    // [rolerows][KS] local restricted reselect
+  const unsigned long long* excl_all;  // [parts][rolerows][KS]
+  long long excl_part_stride;
+  int* dstar;    // [n_steps]
+  int* assign;   // [total R]
+  int* status;   // [n_steps]
+  int* domain_out;  // [n_steps]
+};
+
+// ---------------------------------------------------------------- helpers
+__device__ __forceinline__ uint32_t orderable_u32(float x) {
+  uint32_t b = __float_as_uint(x);
+  return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ unsigned long long make_key(float s, int node) {
+  return ((unsigned long long)orderable_u32(s) << 32) |
+         (unsigned long long)(0xFFFFFFFFu - (uint32_t)node);
+}
+__device__ __forceinline__ int key_node(unsigned long long k) {
+  return (int)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+}
+// warp-wide max of a u64 with two REDUX ops (hi word, then lo among the ties)
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long k) {
+  uint32_t hi = (uint32_t)(k >> 32);
+  uint32_t mhi = __reduce_max_sync(FULL, hi);
+  uint32_t lo = (hi == mhi) ? (uint32_t)k : 0u;
+  uint32_t mlo = __reduce_max_sync(FULL, lo);
+  return ((unsigned long long)mhi << 32) | mlo;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+// streaming 128-bit store: the dense matrix is written once and not re-read by
+// this kernel, keep it out of L1 and mark it evict-first in L2.
+__device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// ---- mbarrier + TMA 1-D bulk copy (cp.async.bulk), sm_90+/sm_100a ----------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// Exact top-K (descending, unique u64 keys, 0 = empty) of `len` keys in shared
+// or global memory by one warp.  Two-level threshold select:
+//   1. every lane takes the max of its strided share;
+//   2. the K-th largest lane maximum t is a lower bound of the K-th largest key
+//      (K <= 32), found with K REDUX rounds on one value per lane;
+//   3. only keys >= t can be in the top-K and they all sit in the <= K lanes
+//      whose maximum is >= t, so at most K*ceil(len/32) keys survive; they are
+//      compacted into `scratch` (shared, >= cap entries) with ballots;
+//   4. K "largest key below the previous one" rounds over the survivors.
+// out[0..K) gets the keys (0-padded).  All 32 lanes must call; `out` may be
+// shared or global; returns the number of valid keys.
+__device__ __forceinline__ int warp_topk(const unsigned long long* __restrict__ keys, int len,
+                                         int K, unsigned long long* scratch, int cap,
+                                         unsigned long long* out) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long lmax = 0;
+  for (int i = lane; i < len; i += 32) {
+    unsigned long long k = keys[i];
+    lmax = k > lmax ? k : lmax;
+  }
+  // K-th largest lane maximum
+  unsigned long long thr = 0, cur = lmax;
+  for (int r = 0; r < K; ++r) {
+    unsigned long long m = warp_max_u64(cur);
+    thr = m;
+    if (m == 0) break;
+    if (cur == m) cur = 0;
+  }
+  // compact survivors
+  int cnt = 0;
+  for (int i0 = 0; i0 < len; i0 += 32) {
+    int i = i0 + lane;
+    unsigned long long k = (i < len) ? keys[i] : 0ull;
+    bool keep = (k != 0ull) && (k >= thr);
+    uint32_t b = __ballot_sync(FULL, keep);
+    if (keep) {
+      int pos = cnt + __popc(b & ((1u << lane) - 1u));
+      if (pos < cap) scratch[pos] = k;
+    }
+    cnt += __popc(b);
+  }
+  __syncwarp();
+  if (cnt > cap) cnt = cap;  // cannot happen when cap >= K*ceil(len/32)
+  // final rounds
+  unsigned long long prev = ~0ull;
+  int valid = 0;
+  for (int r = 0; r < K; ++r) {
+    unsigned long long best = 0;
+    for (int i = lane; i < cnt; i += 32) {
+      unsigned long long k = scratch[i];
+      if (k < prev && k > best) best = k;
+    }
+    best = warp_max_u64(best);
+    if (lane == 0) out[r] = best;
+    if (best == 0) {
+      for (int q = r + 1 + lane; q < K; q += 32) out[q] = 0;
+      break;
+    }
+    prev = best;
+    ++valid;
+  }
+  __syncwarp();
+  return valid;
+}
+
+// ============================================================= k_prep / k_base
+// fmin[n] = min(free[n], F) (u8) and node_owner[n] = owner[domain[n]].
+__global__ void k_prep(int n, const int* __restrict__ free_, const int* __restrict__ domain,
+                       const int* __restrict__ owner, unsigned char* __restrict__ fmin,
+                       int* __restrict__ node_owner) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    int f = free_[i];
+    fmin[i] = (unsigned char)(f < RBGTOPO_F_CAP ? f : RBGTOPO_F_CAP);
+    node_owner[i] = owner[domain[i]];
+  }
+}
+
+// base[n] = sum_j w_j * fmin[col_j] + SELF_W * fmin[n]   for the rows of one tile.
+// The tile's contiguous col_idx / edge_w segment and (when it fits) the whole u8
+// fmin vector are staged into shared memory with TMA bulk copies completing on
+// one mbarrier; 8 lanes walk one row (vector of int32 gathers from smem, fp32
+// accumulate), reduced with warp shuffles.  tiles[] = (row0, row1) pairs built on
+// the host so that nnz <= BASE_TILE_NNZ (a single over-long row is its own tile
+// and reads global memory directly).
+__global__ void __launch_bounds__(BASE_THREADS)
+k_base(TopoDev t, const int2* __restrict__ tiles, int fmin_staged, int fmin_bytes,
+       float* __restrict__ base_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  int* s_col = reinterpret_cast<int*>(smem_raw);
+  int* s_w = s_col + (BASE_TILE_NNZ + 8);
+  unsigned char* s_fmin = reinterpret_cast<unsigned char*>(s_w + (BASE_TILE_NNZ + 8));
+
+  const int2 tile = tiles[blockIdx.x];
+  const int r0 = tile.x, r1 = tile.y;
+  const int e0 = t.row_ptr[r0], e1 = t.row_ptr[r1];
+  const int a0 = e0 & ~3;  // 16-byte aligned segment start
+  const int seg = e1 - a0;
+  const bool staged = seg <= BASE_TILE_NNZ + 4;
+  const uint32_t seg_bytes = (uint32_t)(((seg * 4) + 15) & ~15);
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = (staged ? 2u * seg_bytes : 0u) + (fmin_staged ? (uint32_t)fmin_bytes : 0u);
+    mbar_expect_tx(&bar, total);
+    if (staged && seg_bytes) {
+      bulk_g2s(s_col, t.col + a0, seg_bytes, &bar);
+      bulk_g2s(s_w, t.w + a0, seg_bytes, &bar);
+    }
+    if (fmin_staged) bulk_g2s(s_fmin, t.fmin, (uint32_t)fmin_bytes, &bar);
+  }
+  mbar_wait(&bar, 0);
+
+  const unsigned char* fm = fmin_staged ? s_fmin : t.fmin;
+  const int sub = threadIdx.x & 7;
+  const int iters = (r1 - r0 + (BASE_THREADS / 8) - 1) / (BASE_THREADS / 8);
+  for (int it = 0; it < iters; ++it) {
+    const int r = r0 + it * (BASE_THREADS / 8) + (threadIdx.x >> 3);
+    float acc = 0.0f;
+    if (r < r1) {
+      const int rb = t.row_ptr[r], re = t.row_ptr[r + 1];
+      if (staged) {
+        for (int j = rb + sub; j < re; j += 8)
+          acc += (float)s_w[j - a0] * (float)fm[s_col[j - a0]];
+      } else {
+        for (int j = rb + sub; j < re; j += 8) acc += (float)t.w[j] * (float)fm[t.col[j]];
+      }
+    }
+    acc += __shfl_xor_sync(FULL, acc, 4);
+    acc += __shfl_xor_sync(FULL, acc, 2);
+    acc += __shfl_xor_sync(FULL, acc, 1);
+    if (r < r1 && sub == 0) base_out[r] = acc + (float)RBGTOPO_SELF_W * (float)fm[r];
+  }
+}
+
+// ============================================================ k_score_select
+// One work item = (step, chunk of `chunk` nodes of this rank's slab).
+//   1. zero the per-role delta rows in smem, load capacity / ownership
+//   2. scatter the step's anchor pods: walk CSR row m, add pair*c*w to the
+//      delta of every neighbour inside the chunk (+ self term), subtract the
+//      consumed capacity
+//   3. stream: S = need*base + delta, mask infeasible -> -inf, write the
+//      replica rows of the dense matrix with 128-bit streaming stores, keep S in
+//      smem and a per-thread (score, node) maximum per role
+//   4. warp p selects the exact top-K of role row p: the K threads with the
+//      largest maxima hold every top-K element, their
+//      elements are gathered from smem and reduced with warp_topk
+template <int P>
+__device__ __forceinline__ void score_item(const TopoDev& t, const BatchDev& b, const int* hdr,
+                                           int step, int ch, float* sS, int* sAvail,
+                                           uint32_t* sBlk, unsigned long long* sTmax,
+                                           unsigned long long* sScr, const int* sRole,
+                                           const int* sPair) {
+  const int T = b.chunk;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n0 = t.slab_lo + ch * T;
+  const int n1 = min(n0 + T, t.slab_hi);
+  const int gid = hdr[0], flags = hdr[1], fixed_domain = hdr[2];
+  const int Q = hdr[5];
+  const int n_anchors = hdr[7], anchor_off = hdr[8];
+  const int n_cons = hdr[9], cons_off = hdr[10];
+  const int R = hdr[11], rep_off = hdr[12], rolerow_off = hdr[13];
+  const bool excl_step = (flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
+  const int K = min(R, t.n);
+
+  // ---- 1. init
+  for (int i = tid; i < T; i += SCORE_THREADS) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) sS[p * T + i] = 0.0f;
+    int n = n0 + i;
+    int av = -1;
+    bool blk = false;
+    if (n < n1) {
+      av = t.free_[n];
+      if (excl_step) {
+        int o = t.node_owner[n];
+        blk = !(o == -1 || o == gid);
+      }
+    }
+    sAvail[i] = av;
+    uint32_t bm = __ballot_sync(FULL, blk);
+    if (lane == 0) sBlk[i >> 5] = bm;
+  }
+  __syncthreads();
+
+  // ---- 2. anchors (one warp per anchor pod) and consumed capacity
+  const int* anc = b.blob + anchor_off;
+  for (int a = warp; a < n_anchors; a += SCORE_WARPS) {
+    const int m = anc[3 * a], q = anc[3 * a + 1], c = anc[3 * a + 2];
+    int coef[P];
+    bool any = false;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      coef[p] = sPair[p * MAXQ + q] * c;
+      any |= coef[p] != 0;
+    }
+    if (!any) continue;
+    const int rb = t.row_ptr[m], re = t.row_ptr[m + 1];
+    for (int j = rb + lane; j < re; j += 32) {
+      const int nn = t.col[j];
+      if (nn >= n0 && nn < n1) {
+        const int wv = t.w[j];
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+          if (coef[p]) atomicAdd(&sS[p * T + (nn - n0)], (float)(coef[p] * wv));
+      }
+    }
+    if (lane == 0 && m >= n0 && m < n1) {
+#pragma unroll
+      for (int p = 0; p < P; ++p)
+        if (coef[p]) atomicAdd(&sS[p * T + (m - n0)], (float)(coef[p] * RBGTOPO_SELF_W));
+    }
+  }
+  const int* con = b.blob + cons_off;
+  for (int c = tid; c < n_cons; c += SCORE_THREADS) {
+    const int m = con[2 * c];
+    if (m >= n0 && m < n1) atomicSub(&sAvail[m - n0], con[2 * c + 1]);
+  }
+  __syncthreads();
+
+  // ---- 3. stream
+  float bestS[P];
+  int bestN[P];
+  float need[P];
+  int demand[P], rowbase[P], count[P];
+  bool rexcl[P];
+  {
+    int acc = 0;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      count[p] = sRole[4 * p];
+      demand[p] = sRole[4 * p + 1];
+      need[p] = (float)sRole[4 * p + 2];
+      rexcl[p] = excl_step && (sRole[4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE);
+      rowbase[p] = acc;
+      acc += count[p];
+      bestS[p] = -INFINITY;
+      bestN[p] = 0;
+    }
+  }
+  const bool write_rows = b.emit_matrix || (excl_step && fixed_domain < 0);
+  const bool restrict_fixed = excl_step && fixed_domain >= 0;
+  const int groups = T >> 2;
+  for (int g = tid; g < groups; g += SCORE_THREADS) {
+    const int t0 = g << 2;
+    const int n = n0 + t0;
+    if (n >= n1) break;
+    const float4 b4 = *reinterpret_cast<const float4*>(t.base + n);
+    const int4 av4 = *reinterpret_cast<const int4*>(sAvail + t0);
+    const uint32_t blkbits = (sBlk[t0 >> 5] >> (t0 & 31)) & 0xFu;
+    uint32_t dommask = 0xFu;  // lanes allowed for selection under a fixed domain
+    if (restrict_fixed) {
+      dommask = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (n + i < n1 && t.domain[n + i] == fixed_domain) dommask |= 1u << i;
+    }
+    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+    const int av[4] = {av4.x, av4.y, av4.z, av4.w};
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      float4 s4 = *reinterpret_cast<float4*>(sS + p * T + t0);
+      float v[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float x = fmaf(need[p], bb[i], v[i]);
+        bool feas = (av[i] >= demand[p]) && !(rexcl[p] && ((blkbits >> i) & 1u));
+        x = feas ? x : -INFINITY;
+        v[i] = x;
+        float sel = (rexcl[p] && !((dommask >> i) & 1u)) ? -INFINITY : x;
+        if (sel > bestS[p]) {
+          bestS[p] = sel;
+          bestN[p] = n + i;
+        }
+      }
+      float4 o4 = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(sS + p * T + t0) = o4;
+      if (write_rows) {
+        float* rowp = b.matrix + (size_t)(rep_off + rowbase[p]) * t.slab_stride + (n - t.slab_lo);
+        for (int c = 0; c < count[p]; ++c) st_stream_f4(rowp + (size_t)c * t.slab_stride, o4);
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < P; ++p)
+    sTmax[p * SCORE_THREADS + tid] = (bestS[p] == -INFINITY) ? 0ull : make_key(bestS[p], bestN[p]);
+  __syncthreads();
+
+  // ---- 4. select: warp p owns role row p
+  if (warp < P) {
+    const int p = warp;
+    unsigned long long* scr = sScr + warp * (KS * 8 + KS);  // survivors + winners
+    unsigned long long* win = scr + KS * 8;
+    const int nwin = warp_topk(sTmax + p * SCORE_THREADS, SCORE_THREADS, K, scr, KS * 8, win);
+    // gather every element of the winning threads into sTmax[p][..] (reused)
+    unsigned long long* cand = sTmax + p * SCORE_THREADS;
+    const int gpt = (groups + SCORE_THREADS - 1) / SCORE_THREADS;  // float4 groups per thread
+    const int per_thread = gpt << 2;          // elements a thread streamed
+    const int total = nwin * per_thread;      // <= 32 * 8 for T <= 2048
+    const bool rx = excl_step && (sRole[4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE);
+    __syncwarp();
+    for (int i0 = 0; i0 < total; i0 += 32) {
+      int i = i0 + lane;
+      unsigned long long k = 0;
+      if (i < total) {
+        int wi = i / per_thread, e = i % per_thread;
+        int wt = ((key_node(win[wi]) - n0) >> 2) % SCORE_THREADS;  // owning thread
+        int gg = wt + (e >> 2) * SCORE_THREADS;
+        int tt = (gg << 2) + (e & 3);
+        int nn = n0 + tt;
+        if (gg < groups && nn < n1) {
+          float x = sS[p * T + tt];
+          if (rx && restrict_fixed && t.domain[nn] != fixed_domain) x = -INFINITY;
+          if (x != -INFINITY) k = make_key(x, nn);
+        }
+      }
+      cand[i] = k;  // total <= 256 because the host enforces chunk <= 2048
+    }
+    __syncwarp();
+    unsigned long long* out = b.lists + ((size_t)(rolerow_off + p) * b.lc + ch) * KS;
+    int valid = warp_topk(cand, total, K, scr, KS * 8, out);
+    (void)valid;
+    for (int q = K + lane; q < KS; q += 32) out[q] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(SCORE_THREADS)
+k_score_select(TopoDev t, BatchDev b, int items, int PB /* max roles per step in the batch */) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int sHdr[RBGTOPO_STEP_WORDS];
+  __shared__ int sRole[MAXP * 4];
+  __shared__ int sPair[MAXP * MAXQ];
+  const int T = b.chunk;
+  // carve-up (host: score_smem_bytes): sS[PB][T] f32 | sAvail[T] i32 | sBlk[T/32 (+pad)] u32 |
+  //                                    sTmax[PB][256] u64 | sScr[PB][KS*8+KS] u64
+  float* sS = reinterpret_cast<float*>(smem_raw);
+  int* sAvail = reinterpret_cast<int*>(sS + (size_t)PB * T);
+  uint32_t* sBlk = reinterpret_cast<uint32_t*>(sAvail + T);
+  unsigned long long* sTmax =
+      reinterpret_cast<unsigned long long*>(sBlk + (T >> 5) + ((T >> 5) & 1));
+  unsigned long long* sScr = sTmax + (size_t)PB * SCORE_THREADS;
+
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int step = item / b.lc, ch = item % b.lc;
+    __syncthreads();  // previous item's smem is dead
+    const int* hdr_g = b.blob + RBGTOPO_HDR_WORDS + (size_t)step * RBGTOPO_STEP_WORDS;
+    if (threadIdx.x < RBGTOPO_STEP_WORDS) sHdr[threadIdx.x] = hdr_g[threadIdx.x];
+    __syncthreads();
+    const int P = sHdr[3], Q = sHdr[5];
+    if (threadIdx.x < P * 4) sRole[threadIdx.x] = b.blob[sHdr[4] + threadIdx.x];
+    for (int i = threadIdx.x; i < P * MAXQ; i += SCORE_THREADS) {
+      int p = i / MAXQ, q = i % MAXQ;
+      sPair[i] = (q < Q) ? b.blob[sHdr[6] + p * Q + q] : 0;
+    }
+    __syncthreads();
+    switch (P) {
+      case 1: score_item<1>(t, b, sHdr, step, ch, sS, sAvail, sBlk, sTmax, sScr, sRole, sPair); break;
+      case 2: score_item<2>(t, b, sHdr, step, ch, sS, sAvail, sBlk, sTmax, sScr, sRole, sPair); break;
+      case 3: score_item<3>(t, b, sHdr, step, ch, sS, sAvail, sBlk, sTmax, sScr, sRole, sPair); break;
+      case 4: score_item<4>(t, b, sHdr, step, ch, sS, sAvail, sBlk, sTmax, sScr, sRole, sPair); break;
+      case 5: score_item<5>(t, b, sHdr, step, ch, sS, sAvail, sBlk, sTmax, sScr, sRole, sPair); break;
+      case 6: score_item<6>(t, b, sHdr, step, ch, sS, sAvail, sBlk, sTmax, sScr, sRole, sPair); break;
+      case 7: score_item<7>(t, b, sHdr, step, ch, sS, sAvail, sBlk, sTmax, sScr, sRole, sPair); break;
+      default: score_item<8>(t, b, sHdr, step, ch, sS, sAvail, sBlk, sTmax, sScr, sRole, sPair); break;
+    }
+  }
+}
+
+}  // namespace rbgtopo

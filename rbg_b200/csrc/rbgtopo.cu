@@ -1,0 +1,849 @@
+// rbgtopo.cu — host runtime behind the C ABI of include/rbgtopo.h: context,
+// snapshot upload + validation, batch ("blob") validation, slot pool, launches,
+// timing.  Kernels live in kernels.cuh / select.cuh.  No CPU fallback exists:
+// every entry point needs a CUDA device (sm_100).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "select.cuh"
+
+using namespace rbgtopo;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(expr)                                                                      \
+  do {                                                                                \
+    cudaError_t e__ = (expr);                                                         \
+    if (e__ != cudaSuccess)                                                           \
+      return fail(RBGTOPO_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                  __FILE__, __LINE__);                                                \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 4 + 64;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+};
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  ~PinBuf() { if (p) cudaFreeHost(p); }
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 4 + 64;
+    cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+};
+
+struct Topology {
+  bool valid = false;
+  int n = 0, n_domains = 0;
+  long long e = 0;
+  long long wsum_max = 0;  // max over rows of sum_j w_j (exactness bound)
+  uint64_t generation = 0;
+  DevBuf<int> row_ptr, col, w, free_, domain, owner, node_owner, dom_ptr, dom_nodes;
+  DevBuf<unsigned char> fmin;
+  DevBuf<float> base;
+  DevBuf<int2> tiles;
+  int n_tiles = 0;
+  std::vector<int> h_domain;  // kept for update_nodes validation
+  float base_ms = 0.f;
+};
+
+struct BatchMeta {
+  int n_steps = 0, total_r = 0, total_p = 0, max_p = 1, max_k = 1;
+  bool any_excl_unknown = false;
+  long long words = 0;
+  long long scores = 0;      // sum R * N
+  long long algo_bytes = 0;
+};
+
+struct Batch {
+  bool in_use = false;    // reserved by a call or a stage handle
+  bool staged = false;    // holds a staged blob (handle alive)
+  bool ran = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  std::vector<cudaEvent_t> it_ev;  // pairs around k_score_select per iteration
+  BatchMeta m;
+  DevBuf<int> blob;
+  DevBuf<float> matrix;
+  DevBuf<unsigned long long> lists, merged, excl;
+  DevBuf<int> out;  // assign[total_r] | status[n] | domain[n] | dstar[n]
+  PinBuf<int> h_in, h_out;
+  ~Batch() {
+    if (stream) cudaStreamDestroy(stream);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    for (auto& e : it_ev) cudaEventDestroy(e);
+  }
+};
+
+}  // namespace
+
+struct rbgtopo_ctx {
+  rbgtopo_config cfg{};
+  int sm_count = 148;
+  int slab_lo = 0, slab_hi = 0, slab_stride = 0, lc = 1, chunk = 2048;
+  std::shared_mutex topo_mu;  // update = exclusive, score calls = shared
+  std::mutex pool_mu;
+  Topology topo;
+  std::vector<std::unique_ptr<Batch>> batches;
+  cudaStream_t ext_stream = nullptr;
+  bool use_ext_stream = false;
+  std::mutex stat_mu;
+  rbgtopo_timing last{};
+  long long calls = 0, scores_total = 0, launches = 0;
+};
+
+namespace {
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+constexpr size_t kScoreSmemMax = 200 * 1024;  // opt-in dynamic smem of k_score_select
+
+void compute_slab(rbgtopo_ctx* c, int n) {
+  const int W = c->cfg.world, r = c->cfg.rank;
+  auto bound = [&](int g) -> int {
+    if (g <= 0) return 0;
+    if (g >= W) return n;
+    long long b = (long long)g * n / W;
+    return (int)(b / 128 * 128);
+  };
+  c->slab_lo = bound(r);
+  c->slab_hi = bound(r + 1);
+  int max_len = 0;
+  for (int g = 0; g < W; ++g) max_len = std::max(max_len, bound(g + 1) - bound(g));
+  int tcfg = c->cfg.chunk_nodes > 0 ? c->cfg.chunk_nodes : 2048;
+  tcfg = std::min(2048, std::max(128, round_up(tcfg, 128)));
+  c->lc = std::max(1, (max_len + tcfg - 1) / tcfg);
+  c->chunk = std::min(2048, std::max(128, round_up((max_len + c->lc - 1) / c->lc, 128)));
+  c->slab_stride = round_up(std::max(1, c->lc * c->chunk), 32);
+}
+
+TopoDev topo_dev(const rbgtopo_ctx* c) {
+  TopoDev t;
+  const Topology& T = c->topo;
+  t.n = T.n;
+  t.slab_lo = c->slab_lo;
+  t.slab_hi = c->slab_hi;
+  t.slab_stride = c->slab_stride;
+  t.row_ptr = T.row_ptr.p;
+  t.col = T.col.p;
+  t.w = T.w.p;
+  t.free_ = T.free_.p;
+  t.domain = T.domain.p;
+  t.node_owner = T.node_owner.p;
+  t.fmin = T.fmin.p;
+  t.base = T.base.p;
+  t.dom_ptr = T.dom_ptr.p;
+  t.dom_nodes = T.dom_nodes.p;
+  return t;
+}
+
+size_t score_smem_bytes(int PB, int KB, int T) {
+  size_t b = (size_t)PB * T * 4;                 // sS
+  b += (size_t)T * 4;                            // sAvail
+  b += (size_t)((T >> 5) + ((T >> 5) & 1)) * 4;  // sBlk (8-byte aligned end)
+  b += (size_t)PB * SCORE_THREADS * 8;           // sTmax
+  b += (size_t)PB * (KS * 8 + KS) * 8;           // sScr (survivors + winners)
+  (void)KB;
+  return b;
+}
+
+// prep + base kernels on `s`; records base_ms.
+int run_base(rbgtopo_ctx* c, cudaStream_t s) {
+  Topology& T = c->topo;
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  CK(cudaEventRecord(a, s));
+  k_prep<<<(T.n + 255) / 256, 256, 0, s>>>(T.n, T.free_.p, T.domain.p, T.owner.p, T.fmin.p,
+                                           T.node_owner.p);
+  const int fmin_bytes = round_up(T.n, 16);
+  const int staged = T.n <= FMIN_SMEM_MAX ? 1 : 0;
+  size_t smem = (size_t)2 * (BASE_TILE_NNZ + 8) * 4 + (staged ? fmin_bytes : 0);
+  CK(cudaFuncSetAttribute(k_base, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TopoDev td = topo_dev(c);
+  k_base<<<T.n_tiles, BASE_THREADS, smem, s>>>(td, T.tiles.p, staged, fmin_bytes, T.base.p);
+  CK(cudaEventRecord(b, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  CK(cudaEventElapsedTime(&T.base_ms, a, b));
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  std::lock_guard<std::mutex> g(c->stat_mu);
+  c->launches += 2;
+  return RBGTOPO_OK;
+}
+
+// ---- blob validation (host, O(words)) ----------------------------------------
+int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, BatchMeta* m) {
+  const Topology& T = c->topo;
+  if (!blob || words < RBGTOPO_HDR_WORDS) return fail(RBGTOPO_EINVAL, "blob too short");
+  if (blob[0] != RBGTOPO_BLOB_MAGIC) return fail(RBGTOPO_EINVAL, "bad blob magic");
+  if (blob[1] != RBGTOPO_ABI_VERSION) return fail(RBGTOPO_EINVAL, "blob version %d", blob[1]);
+  const int ns = blob[2];
+  if (ns < 0 || blob[3] != words || words > 0x7FFFFFFFLL)
+    return fail(RBGTOPO_EINVAL, "blob header: n_steps=%d words=%d/%lld", ns, blob[3], (long long)words);
+  if ((int64_t)RBGTOPO_HDR_WORDS + (int64_t)ns * RBGTOPO_STEP_WORDS > words)
+    return fail(RBGTOPO_EINVAL, "step table exceeds blob");
+  const long long row_w = T.wsum_max + RBGTOPO_SELF_W;
+  long long racc = 0, pacc = 0;
+  *m = BatchMeta{};
+  auto in = [&](long long off, long long cnt) { return off >= 0 && cnt >= 0 && off + cnt <= words; };
+  for (int s = 0; s < ns; ++s) {
+    const int32_t* st = blob + RBGTOPO_HDR_WORDS + (int64_t)s * RBGTOPO_STEP_WORDS;
+    const int P = st[3], Q = st[5], na = st[7], nc = st[9], R = st[11];
+    if (st[0] < 0) return fail(RBGTOPO_EINVAL, "step %d: gid < 0", s);
+    if (P < 1 || P > RBGTOPO_MAX_STEP_ROLES) return fail(RBGTOPO_ELIMIT, "step %d: %d roles", s, P);
+    if (Q < 0 || Q > RBGTOPO_MAX_GROUP_ROLES) return fail(RBGTOPO_ELIMIT, "step %d: q=%d", s, Q);
+    if (R < 1 || R > RBGTOPO_MAX_STEP_REPLICAS) return fail(RBGTOPO_ELIMIT, "step %d: %d replicas", s, R);
+    if (!in(st[4], 4LL * P) || !in(st[6], (long long)P * Q) || !in(st[8], 3LL * na) || !in(st[10], 2LL * nc))
+      return fail(RBGTOPO_EINVAL, "step %d: section out of bounds", s);
+    if (st[12] != racc || st[13] != pacc) return fail(RBGTOPO_EINVAL, "step %d: bad prefix offsets", s);
+    if (st[2] < -1 || st[2] >= T.n_domains) return fail(RBGTOPO_EINVAL, "step %d: fixed_domain", s);
+    const int32_t* roles = blob + st[4];
+    const int32_t* pair = blob + st[6];
+    const int32_t* anc = blob + st[8];
+    const int32_t* con = blob + st[10];
+    int rsum = 0;
+    for (int p = 0; p < P; ++p) {
+      if (roles[4 * p] < 1 || roles[4 * p + 1] < 0 || roles[4 * p + 1] > RBGTOPO_MAX_FREE ||
+          roles[4 * p + 2] < 0)
+        return fail(RBGTOPO_EINVAL, "step %d role %d: count/demand/need", s, p);
+      rsum += roles[4 * p];
+    }
+    if (rsum != R) return fail(RBGTOPO_EINVAL, "step %d: role counts sum to %d, R=%d", s, rsum, R);
+    for (int i = 0; i < P * Q; ++i)
+      if (pair[i] < 0) return fail(RBGTOPO_EINVAL, "step %d: negative pair weight", s);
+    for (int a = 0; a < na; ++a) {
+      if (anc[3 * a] < 0 || anc[3 * a] >= T.n || anc[3 * a + 1] < 0 || anc[3 * a + 1] >= Q ||
+          anc[3 * a + 2] < 0)
+        return fail(RBGTOPO_EINVAL, "step %d anchor %d out of range", s, a);
+    }
+    for (int i = 0; i < nc; ++i)
+      if (con[2 * i] < 0 || con[2 * i] >= T.n || con[2 * i + 1] < 0 || con[2 * i + 1] > RBGTOPO_MAX_FREE)
+        return fail(RBGTOPO_EINVAL, "step %d consumed %d out of range", s, i);
+    // exactness contract (spec §3.4), conservative: every anchor on one node
+    for (int p = 0; p < P; ++p) {
+      long long amax = (long long)roles[4 * p + 2] * RBGTOPO_F_CAP;
+      for (int a = 0; a < na; ++a) amax += (long long)pair[p * Q + anc[3 * a + 1]] * anc[3 * a + 2];
+      if (amax * row_w >= (1LL << 24))
+        return fail(RBGTOPO_EINEXACT, "step %d role %d: max score bound %lld >= 2^24", s, p, amax * row_w);
+    }
+    racc += R;
+    pacc += P;
+    m->max_p = std::max(m->max_p, P);
+    m->max_k = std::max(m->max_k, R);
+    if ((st[1] & RBGTOPO_STEP_EXCLUSIVE) && st[2] < 0) m->any_excl_unknown = true;
+  }
+  if (blob[4] != racc || blob[5] != pacc) return fail(RBGTOPO_EINVAL, "blob totals mismatch");
+  m->n_steps = ns;
+  m->total_r = (int)racc;
+  m->total_p = (int)pacc;
+  m->words = words;
+  const long long slab = c->slab_hi - c->slab_lo;
+  m->scores = racc * slab;
+  // bytes the score kernel must move for this rank's slab:
+  // matrix write + per-chunk key lists + blob read + per-snapshot vectors once
+  m->algo_bytes = 4LL * racc * slab * (c->cfg.emit_matrix ? 1 : 0) + 8LL * pacc * c->lc * KS +
+                  4LL * words + 12LL * slab;
+  return RBGTOPO_OK;
+}
+
+int acquire_batch(rbgtopo_ctx* c, Batch** out) {
+  std::lock_guard<std::mutex> g(c->pool_mu);
+  for (auto& b : c->batches)
+    if (!b->in_use) {
+      b->in_use = true;
+      *out = b.get();
+      return RBGTOPO_OK;
+    }
+  auto nb = std::make_unique<Batch>();
+  CK(cudaStreamCreateWithFlags(&nb->stream, cudaStreamNonBlocking));
+  for (auto& e : nb->ev) CK(cudaEventCreate(&e));
+  nb->in_use = true;
+  *out = nb.get();
+  c->batches.push_back(std::move(nb));
+  return RBGTOPO_OK;
+}
+void release_batch(rbgtopo_ctx* c, Batch* b) {
+  std::lock_guard<std::mutex> g(c->pool_mu);
+  b->in_use = false;
+  b->staged = false;
+  b->ran = false;
+}
+
+cudaStream_t stream_of(rbgtopo_ctx* c, Batch* b) { return c->use_ext_stream ? c->ext_stream : b->stream; }
+
+// validate + size buffers + H2D.  Caller holds topo_mu shared.
+int stage_into(rbgtopo_ctx* c, Batch* b, const int32_t* blob, int64_t words) {
+  if (!c->topo.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
+  int rc = validate_blob(c, blob, words, &b->m);
+  if (rc) return rc;
+  const BatchMeta& m = b->m;
+  cudaStream_t s = stream_of(c, b);
+  CK(b->blob.reserve((size_t)words));
+  CK(b->h_in.reserve((size_t)words));
+  const bool need_matrix = c->cfg.emit_matrix || m.any_excl_unknown;
+  if (need_matrix) CK(b->matrix.reserve((size_t)std::max(1, m.total_r) * c->slab_stride));
+  CK(b->lists.reserve((size_t)std::max(1, m.total_p) * c->lc * KS));
+  CK(b->merged.reserve((size_t)std::max(1, m.total_p) * KS));
+  CK(b->excl.reserve((size_t)std::max(1, m.total_p) * KS));
+  const size_t out_n = (size_t)m.total_r + 3 * (size_t)m.n_steps + 4;
+  CK(b->out.reserve(out_n));
+  CK(b->h_out.reserve(out_n));
+  CK(cudaEventRecord(b->ev[0], s));
+  memcpy(b->h_in.p, blob, (size_t)words * 4);
+  CK(cudaMemcpyAsync(b->blob.p, b->h_in.p, (size_t)words * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaEventRecord(b->ev[1], s));
+  b->staged = true;
+  b->ran = false;
+  return RBGTOPO_OK;
+}
+
+BatchDev batch_dev(rbgtopo_ctx* c, Batch* b) {
+  BatchDev d;
+  d.blob = b->blob.p;
+  d.n_steps = b->m.n_steps;
+  d.lc = c->lc;
+  d.chunk = c->chunk;
+  d.parts = 1;
+  d.emit_matrix = c->cfg.emit_matrix;
+  d.matrix = b->matrix.p;
+  d.lists = b->lists.p;
+  d.lists_all = b->lists.p;
+  d.part_stride = 0;
+  d.merged = b->merged.p;
+  d.excl = b->excl.p;
+  d.excl_all = b->excl.p;
+  d.excl_part_stride = 0;
+  d.assign = b->out.p;
+  d.status = b->out.p + b->m.total_r;
+  d.domain_out = d.status + b->m.n_steps;
+  d.dstar = d.domain_out + b->m.n_steps;
+  return d;
+}
+
+int launch_score(rbgtopo_ctx* c, Batch* b, cudaStream_t s) {
+  const BatchMeta& m = b->m;
+  if (m.n_steps == 0) return RBGTOPO_OK;
+  const int items = m.n_steps * c->lc;
+  const size_t smem = score_smem_bytes(m.max_p, m.max_k, c->chunk);
+  if (smem > kScoreSmemMax) return fail(RBGTOPO_ELIMIT, "score kernel needs %zu B of shared memory", smem);
+  int occ = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_select, SCORE_THREADS, smem));
+  occ = std::max(1, occ);
+  const int grid = std::min(items, c->sm_count * occ);
+  k_score_select<<<grid, SCORE_THREADS, smem, s>>>(topo_dev(c), batch_dev(c, b), items, m.max_p);
+  return RBGTOPO_OK;
+}
+
+int launch_select(rbgtopo_ctx* c, Batch* b, cudaStream_t s, const BatchDev& d, bool merge,
+                  bool reselect, bool greedy, int* launches) {
+  const int ns = b->m.n_steps;
+  if (ns == 0) return RBGTOPO_OK;
+  const int grid = (ns + SEL_WARPS - 1) / SEL_WARPS;
+  TopoDev td = topo_dev(c);
+  if (merge) { k_merge<<<grid, SEL_THREADS, 0, s>>>(td, d); ++*launches; }
+  if (reselect && b->m.any_excl_unknown) { k_excl_reselect<<<grid, SEL_THREADS, 0, s>>>(td, d); ++*launches; }
+  if (greedy) { k_greedy<<<grid, SEL_THREADS, 0, s>>>(td, d); ++*launches; }
+  return RBGTOPO_OK;
+}
+
+// full single-rank pipeline, `iters` times; leaves results on the device.
+int run_batch(rbgtopo_ctx* c, Batch* b, int iters) {
+  cudaStream_t s = stream_of(c, b);
+  while ((int)b->it_ev.size() < 2 * iters) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    b->it_ev.push_back(e);
+  }
+  int launches = 0;
+  CK(cudaEventRecord(b->ev[2], s));
+  BatchDev d = batch_dev(c, b);
+  for (int it = 0; it < iters; ++it) {
+    CK(cudaEventRecord(b->it_ev[2 * it], s));
+    int rc = launch_score(c, b, s);
+    if (rc) return rc;
+    ++launches;
+    CK(cudaEventRecord(b->it_ev[2 * it + 1], s));
+    rc = launch_select(c, b, s, d, true, true, true, &launches);
+    if (rc) return rc;
+  }
+  CK(cudaEventRecord(b->ev[3], s));
+  CK(cudaGetLastError());
+  b->ran = true;
+  std::lock_guard<std::mutex> g(c->stat_mu);
+  c->launches += launches;
+  c->last.launches = launches;
+  return RBGTOPO_OK;
+}
+
+int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int32_t* domain,
+                int iters) {
+  cudaStream_t s = stream_of(c, b);
+  const BatchMeta& m = b->m;
+  const size_t out_n = (size_t)m.total_r + 2 * (size_t)m.n_steps;
+  CK(cudaEventRecord(b->ev[4], s));
+  if (out_n) CK(cudaMemcpyAsync(b->h_out.p, b->out.p, out_n * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(b->ev[5], s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  if (assign && m.total_r) memcpy(assign, b->h_out.p, (size_t)m.total_r * 4);
+  if (status && m.n_steps) memcpy(status, b->h_out.p + m.total_r, (size_t)m.n_steps * 4);
+  if (domain && m.n_steps) memcpy(domain, b->h_out.p + m.total_r + m.n_steps, (size_t)m.n_steps * 4);
+  // timing
+  rbgtopo_timing tm{};
+  float x = 0.f;
+  if (cudaEventElapsedTime(&x, b->ev[0], b->ev[1]) == cudaSuccess) tm.h2d_ms = x;
+  float score = 0.f;
+  for (int it = 0; it < iters && 2 * it + 1 < (int)b->it_ev.size(); ++it)
+    if (cudaEventElapsedTime(&x, b->it_ev[2 * it], b->it_ev[2 * it + 1]) == cudaSuccess) score += x;
+  tm.score_ms = iters > 0 ? score / iters : 0.f;
+  if (cudaEventElapsedTime(&x, b->ev[2], b->ev[3]) == cudaSuccess)
+    tm.select_ms = iters > 0 ? x / iters - tm.score_ms : 0.f;
+  if (cudaEventElapsedTime(&x, b->ev[4], b->ev[5]) == cudaSuccess) tm.d2h_ms = x;
+  if (cudaEventElapsedTime(&x, b->ev[0], b->ev[5]) == cudaSuccess) tm.total_ms = x;
+  tm.base_ms = c->topo.base_ms;
+  tm.scores = m.scores;
+  tm.algo_bytes = m.algo_bytes;
+  std::lock_guard<std::mutex> g(c->stat_mu);
+  tm.launches = c->last.launches;
+  c->last = tm;
+  c->calls += 1;
+  c->scores_total += m.scores * std::max(1, iters);
+  return RBGTOPO_OK;
+}
+
+Batch* batch_of(rbgtopo_ctx* c, int handle) {
+  std::lock_guard<std::mutex> g(c->pool_mu);
+  if (handle < 0 || handle >= (int)c->batches.size()) return nullptr;
+  Batch* b = c->batches[handle].get();
+  return (b->in_use && b->staged) ? b : nullptr;
+}
+int handle_of(rbgtopo_ctx* c, Batch* b) {
+  std::lock_guard<std::mutex> g(c->pool_mu);
+  for (size_t i = 0; i < c->batches.size(); ++i)
+    if (c->batches[i].get() == b) return (int)i;
+  return -1;
+}
+
+}  // namespace
+
+// ============================================================== C ABI
+extern "C" {
+
+int32_t rbgtopo_abi_version(void) { return RBGTOPO_ABI_VERSION; }
+
+int32_t rbgtopo_last_error(rbgtopo_ctx*, char* buf, int32_t len) {
+  if (buf && len > 0) {
+    int n = (int)std::min<size_t>(g_err.size(), (size_t)len - 1);
+    memcpy(buf, g_err.data(), n);
+    buf[n] = 0;
+  }
+  return (int32_t)g_err.size();
+}
+
+int32_t rbgtopo_create(const rbgtopo_config* cfg, rbgtopo_ctx** out) {
+  if (!cfg || !out) return fail(RBGTOPO_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world)
+    return fail(RBGTOPO_EINVAL, "rank %d / world %d", cfg->rank, cfg->world);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return fail(RBGTOPO_ENODEVICE, "no CUDA device (%s); rbgtopo has no CPU path",
+                e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(RBGTOPO_ENODEVICE, "device %d of %d", cfg->device, ndev);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return fail(RBGTOPO_ENODEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only", cfg->device,
+                prop.major, prop.minor);
+  CK(cudaSetDevice(cfg->device));
+  auto c = std::make_unique<rbgtopo_ctx>();
+  c->cfg = *cfg;
+  if (c->cfg.emit_matrix != 0) c->cfg.emit_matrix = 1;
+  c->sm_count = prop.multiProcessorCount;
+  CK(cudaFuncSetAttribute(k_score_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScoreSmemMax));
+  *out = c.release();
+  return RBGTOPO_OK;
+}
+
+int32_t rbgtopo_destroy(rbgtopo_ctx* c) {
+  if (!c) return RBGTOPO_OK;
+  cudaSetDevice(c->cfg.device);
+  cudaDeviceSynchronize();
+  delete c;
+  return RBGTOPO_OK;
+}
+
+int32_t rbgtopo_set_topology(rbgtopo_ctx* c, int32_t n, int64_t e, const int32_t* row_ptr,
+                             const int32_t* col, const int32_t* w, const int32_t* free_slots,
+                             const int32_t* domain, int32_t n_domains, const int32_t* owner,
+                             uint64_t generation) {
+  if (!c || !row_ptr || !free_slots || !domain || !owner || (e > 0 && (!col || !w)))
+    return fail(RBGTOPO_EINVAL, "null argument");
+  if (n < 1 || e < 0 || e > 0x7FFFFFF0LL || n_domains < 1) return fail(RBGTOPO_EINVAL, "n=%d e=%lld", n, (long long)e);
+  if (row_ptr[0] != 0 || row_ptr[n] != e) return fail(RBGTOPO_EINVAL, "row_ptr ends");
+  // ---- validation (spec §3.1)
+  long long wsum_max = 0;
+  for (int i = 0; i < n; ++i) {
+    if (row_ptr[i + 1] < row_ptr[i]) return fail(RBGTOPO_EINVAL, "row_ptr not monotone at %d", i);
+    if (free_slots[i] < 0 || free_slots[i] > RBGTOPO_MAX_FREE) return fail(RBGTOPO_EINVAL, "free[%d]", i);
+    if (domain[i] < 0 || domain[i] >= n_domains) return fail(RBGTOPO_EINVAL, "domain[%d]", i);
+    long long ws = 0;
+    for (int j = row_ptr[i]; j < row_ptr[i + 1]; ++j) {
+      const int cj = col[j];
+      if (cj < 0 || cj >= n || cj == i) return fail(RBGTOPO_EINVAL, "col_idx[%d]=%d in row %d", j, cj, i);
+      if (j > row_ptr[i] && col[j - 1] >= cj) return fail(RBGTOPO_EINVAL, "row %d not strictly ascending", i);
+      if (w[j] < 0 || w[j] > RBGTOPO_MAX_EDGE_W) return fail(RBGTOPO_EINVAL, "edge_w[%d]", j);
+      ws += w[j];
+      const int32_t* lo = col + row_ptr[cj];
+      const int32_t* hi = col + row_ptr[cj + 1];
+      const int32_t* it = std::lower_bound(lo, hi, i);
+      if (it == hi || *it != i || w[it - col] != w[j])
+        return fail(RBGTOPO_EINVAL, "CSR not symmetric at edge (%d,%d)", i, cj);
+    }
+    wsum_max = std::max(wsum_max, ws);
+  }
+  for (int d = 0; d < n_domains; ++d)
+    if (owner[d] < -1) return fail(RBGTOPO_EINVAL, "domain_owner[%d]", d);
+
+  std::unique_lock<std::shared_mutex> lk(c->topo_mu);
+  CK(cudaSetDevice(c->cfg.device));
+  Topology& T = c->topo;
+  T.valid = false;
+  compute_slab(c, n);
+  // base-kernel tiles
+  std::vector<int2> tiles;
+  for (int r = 0; r < n;) {
+    int r1 = r;
+    const int a0 = row_ptr[r] & ~3;
+    while (r1 < n && r1 - r < BASE_TILE_ROWS && row_ptr[r1 + 1] - a0 <= BASE_TILE_NNZ) ++r1;
+    if (r1 == r) r1 = r + 1;  // over-long row: its own (unstaged) tile
+    tiles.push_back(make_int2(r, r1));
+    r = r1;
+  }
+  // nodes grouped by domain
+  std::vector<int> dom_ptr(n_domains + 1, 0), dom_nodes(n);
+  for (int i = 0; i < n; ++i) dom_ptr[domain[i] + 1]++;
+  for (int d = 0; d < n_domains; ++d) dom_ptr[d + 1] += dom_ptr[d];
+  {
+    std::vector<int> cur(dom_ptr.begin(), dom_ptr.end() - 1);
+    for (int i = 0; i < n; ++i) dom_nodes[cur[domain[i]]++] = i;
+  }
+  const size_t pad = 64;
+  CK(T.row_ptr.reserve(n + 1 + pad));
+  CK(T.col.reserve((size_t)e + pad));
+  CK(T.w.reserve((size_t)e + pad));
+  CK(T.free_.reserve(n + pad));
+  CK(T.domain.reserve(n + pad));
+  CK(T.owner.reserve(n_domains + pad));
+  CK(T.node_owner.reserve(n + pad));
+  CK(T.dom_ptr.reserve(n_domains + 1 + pad));
+  CK(T.dom_nodes.reserve(n + pad));
+  CK(T.fmin.reserve((size_t)round_up(n, 16) + pad));
+  CK(T.base.reserve((size_t)n + 4096));
+  CK(T.tiles.reserve(tiles.size()));
+  CK(cudaMemset(T.col.p, 0, T.col.cap * 4));
+  CK(cudaMemset(T.w.p, 0, T.w.cap * 4));
+  CK(cudaMemset(T.fmin.p, 0, T.fmin.cap));
+  CK(cudaMemset(T.base.p, 0, T.base.cap * 4));
+  CK(cudaMemcpy(T.row_ptr.p, row_ptr, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice));
+  if (e) {
+    CK(cudaMemcpy(T.col.p, col, (size_t)e * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(T.w.p, w, (size_t)e * 4, cudaMemcpyHostToDevice));
+  }
+  CK(cudaMemcpy(T.free_.p, free_slots, (size_t)n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(T.domain.p, domain, (size_t)n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(T.owner.p, owner, (size_t)n_domains * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(T.dom_ptr.p, dom_ptr.data(), (size_t)(n_domains + 1) * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(T.dom_nodes.p, dom_nodes.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(T.tiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  T.n = n;
+  T.e = e;
+  T.n_domains = n_domains;
+  T.n_tiles = (int)tiles.size();
+  T.wsum_max = wsum_max;
+  T.generation = generation;
+  T.h_domain.assign(domain, domain + n);
+  int rc = run_base(c, c->use_ext_stream ? c->ext_stream : (cudaStream_t)0);
+  if (rc) return rc;
+  T.valid = true;
+  return RBGTOPO_OK;
+}
+
+int32_t rbgtopo_update_nodes(rbgtopo_ctx* c, const int32_t* free_slots, const int32_t* owner,
+                             uint64_t generation) {
+  if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
+  std::unique_lock<std::shared_mutex> lk(c->topo_mu);
+  Topology& T = c->topo;
+  if (!T.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
+  CK(cudaSetDevice(c->cfg.device));
+  if (free_slots) {
+    for (int i = 0; i < T.n; ++i)
+      if (free_slots[i] < 0 || free_slots[i] > RBGTOPO_MAX_FREE) return fail(RBGTOPO_EINVAL, "free[%d]", i);
+    CK(cudaMemcpy(T.free_.p, free_slots, (size_t)T.n * 4, cudaMemcpyHostToDevice));
+  }
+  if (owner) {
+    for (int d = 0; d < T.n_domains; ++d)
+      if (owner[d] < -1) return fail(RBGTOPO_EINVAL, "domain_owner[%d]", d);
+    CK(cudaMemcpy(T.owner.p, owner, (size_t)T.n_domains * 4, cudaMemcpyHostToDevice));
+  }
+  T.generation = generation;
+  return run_base(c, c->use_ext_stream ? c->ext_stream : (cudaStream_t)0);
+}
+
+int32_t rbgtopo_score_assign(rbgtopo_ctx* c, const int32_t* blob, int64_t words, int32_t* assign,
+                             int32_t* status, int32_t* domain) {
+  if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
+  if (c->cfg.world != 1) return fail(RBGTOPO_EINVAL, "score_assign needs world == 1; use the shard calls");
+  std::shared_lock<std::shared_mutex> lk(c->topo_mu);
+  CK(cudaSetDevice(c->cfg.device));
+  Batch* b = nullptr;
+  int rc = acquire_batch(c, &b);
+  if (rc) return rc;
+  rc = stage_into(c, b, blob, words);
+  if (!rc) rc = run_batch(c, b, 1);
+  if (!rc) rc = fetch_batch(c, b, assign, status, domain, 1);
+  if (rc) cudaStreamSynchronize(stream_of(c, b));
+  release_batch(c, b);
+  return rc;
+}
+
+int32_t rbgtopo_stage(rbgtopo_ctx* c, const int32_t* blob, int64_t words, int32_t* handle) {
+  if (!c || !handle) return fail(RBGTOPO_EINVAL, "null argument");
+  std::shared_lock<std::shared_mutex> lk(c->topo_mu);
+  CK(cudaSetDevice(c->cfg.device));
+  Batch* b = nullptr;
+  int rc = acquire_batch(c, &b);
+  if (rc) return rc;
+  rc = stage_into(c, b, blob, words);
+  if (rc) {
+    release_batch(c, b);
+    return rc;
+  }
+  CK(cudaStreamSynchronize(stream_of(c, b)));
+  *handle = handle_of(c, b);
+  return RBGTOPO_OK;
+}
+
+int32_t rbgtopo_run_staged(rbgtopo_ctx* c, int32_t handle, int32_t iters) {
+  if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
+  if (c->cfg.world != 1) return fail(RBGTOPO_EINVAL, "run_staged needs world == 1");
+  if (iters < 1 || iters > 4096) return fail(RBGTOPO_EINVAL, "iters");
+  std::shared_lock<std::shared_mutex> lk(c->topo_mu);
+  Batch* b = batch_of(c, handle);
+  if (!b) return fail(RBGTOPO_EINVAL, "bad handle %d", handle);
+  CK(cudaSetDevice(c->cfg.device));
+  int rc = run_batch(c, b, iters);
+  if (rc) return rc;
+  return fetch_batch(c, b, nullptr, nullptr, nullptr, iters);
+}
+
+int32_t rbgtopo_fetch(rbgtopo_ctx* c, int32_t handle, int32_t* assign, int32_t* status, int32_t* domain) {
+  if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
+  Batch* b = batch_of(c, handle);
+  if (!b || !b->ran) return fail(RBGTOPO_EINVAL, "handle %d has no results", handle);
+  CK(cudaSetDevice(c->cfg.device));
+  cudaStream_t s = stream_of(c, b);
+  const BatchMeta& m = b->m;
+  const size_t out_n = (size_t)m.total_r + 2 * (size_t)m.n_steps;
+  if (out_n) CK(cudaMemcpyAsync(b->h_out.p, b->out.p, out_n * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (assign && m.total_r) memcpy(assign, b->h_out.p, (size_t)m.total_r * 4);
+  if (status && m.n_steps) memcpy(status, b->h_out.p + m.total_r, (size_t)m.n_steps * 4);
+  if (domain && m.n_steps) memcpy(domain, b->h_out.p + m.total_r + m.n_steps, (size_t)m.n_steps * 4);
+  return RBGTOPO_OK;
+}
+
+int32_t rbgtopo_release(rbgtopo_ctx* c, int32_t handle) {
+  if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
+  Batch* b = batch_of(c, handle);
+  if (!b) return fail(RBGTOPO_EINVAL, "bad handle %d", handle);
+  cudaSetDevice(c->cfg.device);
+  cudaStreamSynchronize(stream_of(c, b));
+  release_batch(c, b);
+  return RBGTOPO_OK;
+}
+
+int32_t rbgtopo_read_scores(rbgtopo_ctx* c, int32_t handle, int32_t row, float* out, int32_t out_len) {
+  if (!c || !out) return fail(RBGTOPO_EINVAL, "null argument");
+  Batch* b = batch_of(c, handle);
+  if (!b || !b->ran) return fail(RBGTOPO_EINVAL, "handle %d has no results", handle);
+  if (!c->cfg.emit_matrix) return fail(RBGTOPO_EINVAL, "ctx was created with emit_matrix = 0");
+  const int slab = c->slab_hi - c->slab_lo;
+  if (row < 0 || row >= b->m.total_r || out_len < slab) return fail(RBGTOPO_EINVAL, "row/out_len");
+  CK(cudaSetDevice(c->cfg.device));
+  CK(cudaStreamSynchronize(stream_of(c, b)));
+  CK(cudaMemcpy(out, b->matrix.p + (size_t)row * c->slab_stride, (size_t)slab * 4, cudaMemcpyDeviceToHost));
+  return RBGTOPO_OK;
+}
+
+int32_t rbgtopo_read_topk(rbgtopo_ctx* c, int32_t handle, int32_t rolerow, uint64_t* out, int32_t k) {
+  if (!c || !out) return fail(RBGTOPO_EINVAL, "null argument");
+  Batch* b = batch_of(c, handle);
+  if (!b || !b->ran) return fail(RBGTOPO_EINVAL, "handle %d has no results", handle);
+  if (rolerow < 0 || rolerow >= b->m.total_p || k < 1 || k > KS) return fail(RBGTOPO_EINVAL, "rolerow/k");
+  CK(cudaSetDevice(c->cfg.device));
+  CK(cudaStreamSynchronize(stream_of(c, b)));
+  CK(cudaMemcpy(out, b->merged.p + (size_t)rolerow * KS, (size_t)k * 8, cudaMemcpyDeviceToHost));
+  return RBGTOPO_OK;
+}
+
+// ---- node-axis sharding --------------------------------------------------
+int32_t rbgtopo_slab(rbgtopo_ctx* c, int32_t* lo, int32_t* hi) {
+  if (!c || !lo || !hi) return fail(RBGTOPO_EINVAL, "null argument");
+  if (!c->topo.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
+  *lo = c->slab_lo;
+  *hi = c->slab_hi;
+  return RBGTOPO_OK;
+}
+
+int32_t rbgtopo_shard_score(rbgtopo_ctx* c, int32_t handle, void** keys_dev, int64_t* keys_bytes) {
+  if (!c || !keys_dev || !keys_bytes) return fail(RBGTOPO_EINVAL, "null argument");
+  std::shared_lock<std::shared_mutex> lk(c->topo_mu);
+  Batch* b = batch_of(c, handle);
+  if (!b) return fail(RBGTOPO_EINVAL, "bad handle %d", handle);
+  CK(cudaSetDevice(c->cfg.device));
+  cudaStream_t s = stream_of(c, b);
+  while (b->it_ev.size() < 2) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    b->it_ev.push_back(e);
+  }
+  CK(cudaEventRecord(b->ev[2], s));
+  CK(cudaEventRecord(b->it_ev[0], s));
+  int rc = launch_score(c, b, s);
+  if (rc) return rc;
+  CK(cudaEventRecord(b->it_ev[1], s));
+  CK(cudaGetLastError());
+  *keys_dev = b->lists.p;
+  *keys_bytes = (int64_t)std::max(1, b->m.total_p) * c->lc * KS * 8;
+  std::lock_guard<std::mutex> g(c->stat_mu);
+  c->launches += 1;
+  c->last.launches = 1;
+  return RBGTOPO_OK;
+}
+
+int32_t rbgtopo_shard_merge(rbgtopo_ctx* c, int32_t handle, const void* keys_all, int32_t* need_pass2,
+                            void** keys2_dev, int64_t* keys2_bytes) {
+  if (!c || !keys_all || !need_pass2 || !keys2_dev || !keys2_bytes) return fail(RBGTOPO_EINVAL, "null argument");
+  std::shared_lock<std::shared_mutex> lk(c->topo_mu);
+  Batch* b = batch_of(c, handle);
+  if (!b) return fail(RBGTOPO_EINVAL, "bad handle %d", handle);
+  CK(cudaSetDevice(c->cfg.device));
+  cudaStream_t s = stream_of(c, b);
+  BatchDev d = batch_dev(c, b);
+  d.parts = c->cfg.world;
+  d.lists_all = static_cast<const unsigned long long*>(keys_all);
+  d.part_stride = (long long)std::max(1, b->m.total_p) * c->lc * KS;
+  int launches = 0;
+  int rc = launch_select(c, b, s, d, true, true, false, &launches);
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  *need_pass2 = b->m.any_excl_unknown ? 1 : 0;
+  *keys2_dev = b->excl.p;
+  *keys2_bytes = (int64_t)std::max(1, b->m.total_p) * KS * 8;
+  std::lock_guard<std::mutex> g(c->stat_mu);
+  c->launches += launches;
+  c->last.launches += launches;
+  return RBGTOPO_OK;
+}
+
+int32_t rbgtopo_shard_assign(rbgtopo_ctx* c, int32_t handle, const void* keys2_all) {
+  if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
+  std::shared_lock<std::shared_mutex> lk(c->topo_mu);
+  Batch* b = batch_of(c, handle);
+  if (!b) return fail(RBGTOPO_EINVAL, "bad handle %d", handle);
+  if (b->m.any_excl_unknown && !keys2_all) return fail(RBGTOPO_EINVAL, "pass-2 keys required");
+  CK(cudaSetDevice(c->cfg.device));
+  cudaStream_t s = stream_of(c, b);
+  BatchDev d = batch_dev(c, b);
+  d.parts = c->cfg.world;
+  if (keys2_all) {
+    d.excl_all = static_cast<const unsigned long long*>(keys2_all);
+    d.excl_part_stride = (long long)std::max(1, b->m.total_p) * KS;
+  }
+  int launches = 0;
+  int rc = launch_select(c, b, s, d, false, false, true, &launches);
+  if (rc) return rc;
+  CK(cudaEventRecord(b->ev[3], s));
+  CK(cudaGetLastError());
+  b->ran = true;
+  {
+    std::lock_guard<std::mutex> g(c->stat_mu);
+    c->launches += launches;
+    c->last.launches += launches;
+  }
+  return fetch_batch(c, b, nullptr, nullptr, nullptr, 1);
+}
+
+int32_t rbgtopo_set_stream(rbgtopo_ctx* c, void* stream) {
+  if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
+  std::unique_lock<std::shared_mutex> lk(c->topo_mu);
+  c->ext_stream = static_cast<cudaStream_t>(stream);
+  c->use_ext_stream = stream != nullptr;
+  return RBGTOPO_OK;
+}
+
+int32_t rbgtopo_last_timing(rbgtopo_ctx* c, rbgtopo_timing* out) {
+  if (!c || !out) return fail(RBGTOPO_EINVAL, "null argument");
+  std::lock_guard<std::mutex> g(c->stat_mu);
+  *out = c->last;
+  out->base_ms = c->topo.base_ms;
+  return RBGTOPO_OK;
+}
+
+int32_t rbgtopo_stats(rbgtopo_ctx* c, uint64_t* generation, int64_t* calls, int64_t* scores_total,
+                      int64_t* kernel_launches) {
+  if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
+  std::lock_guard<std::mutex> g(c->stat_mu);
+  if (generation) *generation = c->topo.generation;
+  if (calls) *calls = c->calls;
+  if (scores_total) *scores_total = c->scores_total;
+  if (kernel_launches) *kernel_launches = c->launches;
+  return RBGTOPO_OK;
+}
+
+}  // extern "C"

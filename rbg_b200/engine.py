@@ -1,0 +1,152 @@
+"""Object wrapper over one rbgtopo_ctx (C ABI of include/rbgtopo.h)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from .blob import blob_totals
+
+
+class RbgTopoError(RuntimeError):
+    def __init__(self, code: int, text: str):
+        super().__init__(f"rbgtopo error {code}: {text}")
+        self.code = code
+
+
+def _p(a: Optional[np.ndarray], typ=_lib.i32p):
+    return None if a is None else a.ctypes.data_as(typ)
+
+
+def _i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class TopoPlacer:
+    """Device-resident cluster snapshot + placement entry points."""
+
+    def __init__(self, device: int = 0, rank: int = 0, world: int = 1, emit_matrix: bool = True,
+                 chunk_nodes: int = 0):
+        self.lib = _lib.load()
+        cfg = _lib.Config(device=device, rank=rank, world=world, slots=0,
+                          emit_matrix=1 if emit_matrix else 0, chunk_nodes=chunk_nodes)
+        h = C.c_void_p()
+        self._h = None
+        self._check(self.lib.rbgtopo_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self.n_nodes = 0
+        self.world = world
+
+    # -- plumbing
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            buf = C.create_string_buffer(512)
+            self.lib.rbgtopo_last_error(self._h, buf, 512)
+            raise RbgTopoError(rc, buf.value.decode(errors="replace"))
+
+    def close(self) -> None:
+        if self._h is not None:
+            self.lib.rbgtopo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- snapshot
+    def set_topology(self, row_ptr, col_idx, edge_w, free, domain, domain_owner, generation: int = 0) -> None:
+        row_ptr, col_idx, edge_w = _i32(row_ptr), _i32(col_idx), _i32(edge_w)
+        free, domain, owner = _i32(free), _i32(domain), _i32(domain_owner)
+        n = len(row_ptr) - 1
+        self._check(self.lib.rbgtopo_set_topology(self._h, n, len(col_idx), _p(row_ptr), _p(col_idx), _p(edge_w),
+                                                  _p(free), _p(domain), len(owner), _p(owner), generation))
+        self.n_nodes = n
+
+    def update_nodes(self, free=None, domain_owner=None, generation: int = 0) -> None:
+        f = None if free is None else _i32(free)
+        o = None if domain_owner is None else _i32(domain_owner)
+        self._check(self.lib.rbgtopo_update_nodes(self._h, _p(f), _p(o), generation))
+
+    # -- hot path, host buffers in/out
+    def score_assign(self, blob: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        blob = _i32(blob)
+        ns, tr, _ = blob_totals(blob)
+        assign = np.empty(max(tr, 1), dtype=np.int32)
+        status = np.empty(max(ns, 1), dtype=np.int32)
+        domain = np.empty(max(ns, 1), dtype=np.int32)
+        self._check(self.lib.rbgtopo_score_assign(self._h, _p(blob), len(blob), _p(assign), _p(status), _p(domain)))
+        return assign[:tr], status[:ns], domain[:ns]
+
+    # -- staged (device-resident) batches
+    def stage(self, blob: np.ndarray) -> int:
+        blob = _i32(blob)
+        h = C.c_int32(-1)
+        self._check(self.lib.rbgtopo_stage(self._h, _p(blob), len(blob), C.byref(h)))
+        self._staged_totals = getattr(self, "_staged_totals", {})
+        self._staged_totals[h.value] = blob_totals(blob)
+        return h.value
+
+    def run_staged(self, handle: int, iters: int = 1) -> None:
+        self._check(self.lib.rbgtopo_run_staged(self._h, handle, iters))
+
+    def fetch(self, handle: int):
+        ns, tr, _ = self._staged_totals[handle]
+        assign = np.empty(max(tr, 1), dtype=np.int32)
+        status = np.empty(max(ns, 1), dtype=np.int32)
+        domain = np.empty(max(ns, 1), dtype=np.int32)
+        self._check(self.lib.rbgtopo_fetch(self._h, handle, _p(assign), _p(status), _p(domain)))
+        return assign[:tr], status[:ns], domain[:ns]
+
+    def release(self, handle: int) -> None:
+        self._check(self.lib.rbgtopo_release(self._h, handle))
+        self._staged_totals.pop(handle, None)
+
+    def read_scores(self, handle: int, row: int) -> np.ndarray:
+        lo, hi = self.slab()
+        out = np.empty(hi - lo, dtype=np.float32)
+        self._check(self.lib.rbgtopo_read_scores(self._h, handle, row, _p(out, _lib.f32p), len(out)))
+        return out
+
+    def read_topk(self, handle: int, rolerow: int, k: int = 32) -> np.ndarray:
+        out = np.zeros(k, dtype=np.uint64)
+        self._check(self.lib.rbgtopo_read_topk(self._h, handle, rolerow, _p(out, _lib.u64p), k))
+        return out
+
+    # -- node-axis sharding
+    def slab(self) -> Tuple[int, int]:
+        lo, hi = C.c_int32(), C.c_int32()
+        self._check(self.lib.rbgtopo_slab(self._h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def shard_score(self, handle: int) -> Tuple[int, int]:
+        p, nb = C.c_void_p(), C.c_int64()
+        self._check(self.lib.rbgtopo_shard_score(self._h, handle, C.byref(p), C.byref(nb)))
+        return p.value, nb.value
+
+    def shard_merge(self, handle: int, keys_all_ptr: int) -> Tuple[bool, int, int]:
+        need, p, nb = C.c_int32(), C.c_void_p(), C.c_int64()
+        self._check(self.lib.rbgtopo_shard_merge(self._h, handle, C.c_void_p(keys_all_ptr), C.byref(need),
+                                                 C.byref(p), C.byref(nb)))
+        return bool(need.value), p.value, nb.value
+
+    def shard_assign(self, handle: int, keys2_all_ptr: Optional[int]) -> None:
+        self._check(self.lib.rbgtopo_shard_assign(self._h, handle,
+                                                  C.c_void_p(keys2_all_ptr) if keys2_all_ptr else None))
+
+    def set_stream(self, cuda_stream: Optional[int]) -> None:
+        self._check(self.lib.rbgtopo_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    # -- stats
+    def last_timing(self) -> dict:
+        t = _lib.Timing()
+        self._check(self.lib.rbgtopo_last_timing(self._h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in _lib.Timing._fields_ if k != "reserved"}
+
+    def stats(self) -> dict:
+        g, c, s, k = C.c_uint64(), C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self.lib.rbgtopo_stats(self._h, C.byref(g), C.byref(c), C.byref(s), C.byref(k)))
+        return dict(generation=g.value, calls=c.value, scores_total=s.value, kernel_launches=k.value)
