@@ -1,0 +1,455 @@
+#!/usr/bin/env python
+"""bench.py — (replica x node) affinity scores/sec of the placement hot path.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
+line on rank 0.  A "step" = one full placement pass of the whole fleet: every
+RoleBasedGroup of the batch is scored against all nodes and assigned, all
+dependency levels (waves).  Workload at N=1 = BASELINE.json configs[2] (the one
+the metric is quoted on): mooncake 5-role / 7-pod RBGs (examples/mooncake/
+pd-disaggregated-with-mooncake.yaml) on a 10 000-node 4-tier synthetic topology,
+batched `--groups` RBGs per launch (a single RBG is a ~3 MB, ~1 us problem:
+launch-bound, SURVEY.md §0.6 — batching is what makes the roofline meaningful).
+
+  value : scores/s with the wave batches already resident in HBM (kernels only,
+          one stream, CUDA events around the K steps, max over ranks)
+  e2e   : the same metric through the C-ABI plugin call with HOST buffers:
+          rbgtopo_update_nodes(free) + rbgtopo_place_groups(groups blob) per
+          step — H2D of every wave's inputs and D2H of every wave's results,
+          and the host-side wave loop, inside the timed region
+  roofline : k_score_select (dominant kernel): algorithmic bytes / CUDA-event
+          duration of its launches inside the timed region vs the measured HBM
+          peak (MEASURED_PEAKS.json)
+  cpu_baseline : the CPU oracle of OUR spec (kind "port": sgl-project/rbg has no
+          such path and no Go toolchain exists here) on a bounded sample
+
+`--impl reference` times that CPU oracle as the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "replica_x_node_affinity_scores_per_sec"
+UNIT = "scores/s"
+
+
+# ----------------------------------------------------------------- workload
+def build_fleet(n_groups: int, n_nodes: int, seed: int = 0):
+    """cfg3 fleet: mooncake-shaped RBGs; group g already has (g % 4) scheduled
+    pods (partially deployed groups give every group its own anchor term)."""
+    from rbg_b200 import synth
+    from rbg_b200.plugin import RoleBasedGroup, RoleSpec
+    shape = synth.shape_mooncake()
+    rbgs = []
+    for g in range(n_groups):
+        roles = [RoleSpec(r.name, r.replicas, tuple(r.deps), r.demand) for r in shape.roles]
+        placed = [(shape.roles[q].name, node) for node, q, _ in
+                  synth.random_anchors(n_nodes, len(shape.roles), g % 4, seed, g)]
+        rbgs.append(RoleBasedGroup("default", f"rbg{g}", roles, gid=g, policy_rules=shape.policy_rules,
+                                   placed=placed))
+    return rbgs
+
+
+class _RecordingPlacer:
+    """Wraps a placer and records the per-wave step blobs (to stage them)."""
+
+    def __init__(self, inner):
+        self.inner = inner
+        self.n_nodes = inner.n_nodes
+        self.blobs = []
+
+    def score_assign(self, blob):
+        self.blobs.append(np.array(blob, copy=True))
+        return self.inner.score_assign(blob)
+
+
+class _OraclePlacer:
+    """CPU oracle behind the placer interface (cpu_baseline / reference arm only)."""
+
+    def __init__(self, topo, nthreads):
+        from oracle import placer as oracle_placer
+        self.o = oracle_placer
+        self.topo = topo
+        self.n_nodes = topo.n
+        self.nthreads = nthreads
+
+    def score_assign(self, blob):
+        r = self.o.place(self.topo, blob, want_matrix=True, want_topk=False, nthreads=self.nthreads)
+        if r["rc"] != 0:
+            raise RuntimeError(f"oracle rc={r['rc']}")
+        return r["assign"], r["status"], r["domain"]
+
+
+def oracle_wave_blobs(topo, rbgs):
+    """The per-wave step batches of a fleet, derived with the CPU oracle (untimed)."""
+    from oracle import placer as oracle_placer
+    from rbg_b200.plugin import B200TopoPodGroupManager
+    rec = _RecordingPlacer(_OraclePlacer(topo, oracle_placer.max_threads()))
+    B200TopoPodGroupManager(rec).reconcile_pod_groups_by_waves(rbgs)
+    return rec.blobs
+
+
+def oracle_scores_per_sec(topo, blobs, nthreads, min_seconds=6.0, max_reps=1 << 30):
+    """Time ONLY the C oracle (score -> top-K -> greedy, dense matrix emitted) on
+    the wave batches; steps of a batch are spread over `nthreads` OpenMP threads."""
+    from oracle import placer as oracle_placer
+    per_pass = sum(int(b[4]) for b in blobs) * topo.n
+    scores, reps, t0 = 0, 0, time.perf_counter()
+    while True:
+        for b in blobs:
+            r = oracle_placer.place(topo, b, want_matrix=True, want_topk=False, nthreads=nthreads)
+            assert r["rc"] == 0
+        scores += per_pass
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds or reps >= max_reps:
+            break
+    return scores / dt, dt, reps
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class _DevPtr:
+    """Zero-copy view of a library-owned device buffer for torch (plumbing only)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<i8", "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+
+# ------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from rbg_b200 import synth
+    from rbg_b200.engine import TopoPlacer
+    from rbg_b200.plugin import B200TopoPodGroupManager
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    n_nodes = args.nodes * world          # weak scaling on the node axis
+    topo = synth.make_topology(n_nodes, seed=0, tiers=4, samples_per_tier=5)
+    rbgs = build_fleet(args.groups, n_nodes)
+
+    # the wave batches: derive them once on rank-local single-GPU semantics.  The
+    # placement is deterministic, so the wave w+1 batch (which carries wave w's
+    # placements as anchors) is identical every step.
+    if world == 1:
+        eng = TopoPlacer(device=local)
+        eng.set_topology(topo.row_ptr, topo.col_idx, topo.edge_w, topo.free, topo.domain, topo.domain_owner)
+        rec = _RecordingPlacer(eng)
+        B200TopoPodGroupManager(rec).reconcile_pod_groups_by_waves(rbgs)
+        wave_blobs = rec.blobs
+    else:
+        # every rank needs the same wave batches: rank 0 derives them with the CPU-free
+        # single-GPU engine over the full node axis and broadcasts the blobs
+        if rank == 0:
+            e1 = TopoPlacer(device=local)
+            e1.set_topology(topo.row_ptr, topo.col_idx, topo.edge_w, topo.free, topo.domain, topo.domain_owner)
+            rec = _RecordingPlacer(e1)
+            B200TopoPodGroupManager(rec).reconcile_pod_groups_by_waves(rbgs)
+            wave_blobs = rec.blobs
+            e1.close()
+        else:
+            wave_blobs = None
+        box = [wave_blobs]
+        dist.broadcast_object_list(box, src=0)
+        wave_blobs = box[0]
+        eng = TopoPlacer(device=local, rank=rank, world=world)
+        eng.set_topology(topo.row_ptr, topo.col_idx, topo.edge_w, topo.free, topo.domain, topo.domain_owner)
+
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    handles = [eng.stage(b) for b in wave_blobs]
+    total_r = sum(int(b[4]) for b in wave_blobs)
+    lo, hi = eng.slab()
+    scores_per_step_rank = total_r * (hi - lo)
+    gathered = {}
+
+    def device_step():
+        if world == 1:
+            for h in handles:
+                eng.run_staged(h, 1)
+            return
+        with torch.cuda.stream(stream):
+            for h in handles:
+                ptr, nb = eng.shard_score(h)
+                src = torch.as_tensor(_DevPtr(ptr, nb), device="cuda")
+                if h not in gathered:
+                    gathered[h] = torch.empty(world * (nb // 8), dtype=torch.int64, device="cuda")
+                dist.all_gather_into_tensor(gathered[h], src)
+                need2, p2, nb2 = eng.shard_merge(h, gathered[h].data_ptr())
+                g2 = None
+                if need2:
+                    src2 = torch.as_tensor(_DevPtr(p2, nb2), device="cuda")
+                    g2 = torch.empty(world * (nb2 // 8), dtype=torch.int64, device="cuda")
+                    dist.all_gather_into_tensor(g2, src2)
+                eng.shard_assign(h, g2.data_ptr() if g2 is not None else None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: resident inputs, CUDA events on the launching stream
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    for h in handles:
+        eng.fetch(h)            # sync + reset the timing window
+    launches0 = eng.stats()["kernel_launches"]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        device_step()
+    ev1.record(stream)
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.stats()["kernel_launches"] - launches0
+    # per-kernel timing of the timed region (events recorded inside the library
+    # around every k_score_select launch), harvested at fetch
+    score_ms = algo_bytes = 0.0
+    results = []
+    for h in handles:
+        results.append(eng.fetch(h))
+        t = eng.last_timing()
+        score_ms += t["score_ms"]
+        algo_bytes += t["algo_bytes"]
+    t_ms = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    dev_ms = float(t_ms.item())
+    value = scores_per_step_rank * world * args.steps / (dev_ms * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI, H2D + D2H + host wave loop inside
+    eng.set_stream(None)
+    h2d = d2h = 0
+    if world == 1:
+        mgr = B200TopoPodGroupManager(eng)
+        gblob, _ = mgr.groups_blob(rbgs)
+        free = np.ascontiguousarray(topo.free, dtype=np.int32)
+        for _ in range(3):
+            eng.update_nodes(free)
+            eng.place_groups(gblob)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eng.update_nodes(free)
+            a_e2e, s_e2e, d_e2e = eng.place_groups(gblob)
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        h2d = int(free.nbytes + sum(b.nbytes for b in wave_blobs))
+        d2h = int(sum((int(b[4]) + 2 * int(b[2])) * 4 for b in wave_blobs))
+        # the e2e result must equal the staged path's result
+        flat = np.concatenate([r[0] for r in results])
+        assert sorted(flat.tolist()) == sorted(a_e2e.tolist()), "e2e placement differs from the staged path"
+    else:
+        for h in handles:
+            eng.release(h)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            hs = [eng.stage(b) for b in wave_blobs]
+            eng.set_stream(stream.cuda_stream)
+            handles = hs
+            device_step()
+            torch.cuda.synchronize()
+            for h in hs:
+                eng.fetch(h)
+                eng.release(h)
+            eng.set_stream(None)
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        h2d = int(sum(b.nbytes for b in wave_blobs))
+        d2h = int(sum((int(b[4]) + 2 * int(b[2])) * 4 for b in wave_blobs))
+    t_e = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t_e.item())
+    e2e_value = scores_per_step_rank * world * args.steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        achieved = (algo_bytes / 1e9) / (score_ms * 1e-3) if score_ms > 0 else 0.0
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "score_select_dram_bytes.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_step")
+        except Exception:
+            pass
+        # ---- cpu_baseline (bounded sample, N=1 only)
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            from oracle import placer as oracle_placer
+            nt = oracle_placer.max_threads()
+            sample = rbgs[:min(len(rbgs), args.cpu_groups)]
+            sblobs = oracle_wave_blobs(topo, sample)
+            v, dt, reps = oracle_scores_per_sec(topo, sblobs, nt, min_seconds=args.cpu_seconds)
+            s1 = oracle_wave_blobs(topo, sample[:max(8, len(sample) // 8)])
+            v1, dt1, _ = oracle_scores_per_sec(topo, s1, 1, min_seconds=args.cpu_seconds / 2)
+            cpu = {"value": v, "unit": UNIT, "cores": nt, "kind": "port",
+                   "sample": f"{len(sample)} of the {len(rbgs)} RBGs x {reps} passes, same 10 000-node topology, "
+                             f"{dt:.1f} s of wall time on {nt} OpenMP threads; 1 thread: {v1:.3e} scores/s",
+                   "single_thread_value": v1,
+                   "note": "CPU oracle of OUR frozen spec, not sgl-project/rbg code (the reference has no such path)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"cfg3: {args.groups} mooncake RBGs (5 roles / 7 pods, 3 dependency waves) x "
+                            f"{n_nodes}-node NVLink/PCIe/RDMA/VPC topology"
+                            + (f", node axis sharded over {world} GPUs ({args.nodes} nodes per GPU, one all-gather "
+                               f"of per-shard top-K per wave)" if world > 1 else ""),
+                "groups": args.groups, "nodes": n_nodes, "edges": int(topo.e), "replicas_per_step": total_r,
+                "emit_matrix": True,
+                "l2": "dense-matrix write stream per step "
+                      f"({total_r * (hi - lo) * 4 / 1e6:.0f} MB) exceeds the 126 MB L2; inputs are L2-resident by design",
+                "value_leg": "wave batches resident in HBM, base vector resident (recomputed by update_nodes, "
+                             "which is inside the e2e leg)",
+                "e2e_leg": "rbgtopo_update_nodes + rbgtopo_place_groups with host buffers; marshalling RBG "
+                           "objects into the groups blob is the caller's (Go shim) job and is outside",
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "kernel": "k_score_select (3 launches per step, one per wave)",
+                         "peak_source": peak_src, "algo_bytes_per_step": algo_bytes,
+                         "kernel_ms_per_step": score_ms, "frac_of_nominal_8000": achieved / 8000.0},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# -------------------------------------------------------------- reference
+def run_reference(args):
+    """Reference arm: the reference has no implementation of this path and no Go
+    toolchain exists here, so (per the task's tier rules) the arm times the CPU
+    oracle port on all host threads, on the same config and metric."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle import placer as oracle_placer
+    from rbg_b200 import synth
+    n_nodes = args.nodes * args.gpus
+    topo = synth.make_topology(n_nodes, seed=0, tiers=4, samples_per_tier=5)
+    rbgs = build_fleet(args.groups, n_nodes)
+    nt = oracle_placer.max_threads()
+    sample = rbgs[:min(len(rbgs), args.ref_groups)]
+    blobs = oracle_wave_blobs(topo, sample)
+    for _ in range(min(args.warmup, 1)):
+        oracle_scores_per_sec(topo, blobs, nt, min_seconds=0.0, max_reps=1)
+    v, dt, reps = oracle_scores_per_sec(topo, blobs, nt, min_seconds=0.0, max_reps=args.steps)
+    scores = v * dt
+    v = scores / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg3: mooncake RBGs x {n_nodes}-node topology; each step = a bounded sample of "
+                               f"{len(sample)} of the {args.groups} RBGs", "groups": args.groups, "nodes": n_nodes},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": nt, "kind": "port",
+                         "sample": f"{len(sample)} RBGs per step x {args.steps} steps on {nt} OpenMP threads"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--groups", type=int, default=1024)
+    ap.add_argument("--nodes", type=int, default=10000, help="nodes per GPU")
+    ap.add_argument("--cpu-groups", type=int, default=256)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--ref-groups", type=int, default=128)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -182,10 +182,45 @@ int32_t rbgtopo_score_assign(rbgtopo_ctx* ctx, const int32_t* blob,
                              int64_t blob_words, int32_t* assign,
                              int32_t* status, int32_t* domain);
 
+/* ---- GROUPS blob: whole RoleBasedGroups, all dependency levels ------------ *
+ * rbgtopo_place_groups runs the level/wave loop of the plugin on the host side
+ * of the ABI (C++): for every group it forms the steps wave by wave — roles in
+ * the given order (the caller passes them sorted by (level, name), i.e. the
+ * output of rbgtopo_dependency_levels / dependency.go:129-205), a new wave at
+ * every level change and whenever RBGTOPO_MAX_STEP_REPLICAS / _ROLES would be
+ * exceeded — places all groups' wave w in ONE batched launch, feeds the
+ * placements back as anchors / consumed capacity / fixed exclusive domain of
+ * wave w+1 (levels see earlier levels: rolebasedgroup_controller.go:448-476),
+ * and applies gang all-or-nothing over the whole group
+ * (k8s-scheduler-plugin/manager.go:131).  need_rho of a wave is
+ * min(RBGTOPO_NEED_CAP, still-unplaced replicas of the roles q with
+ * pair[rho][q] > 0), DESIGN.md §3.2.
+ *   word 0 magic 0x47474252 ("RBGG")  1 version  2 n_groups  3 total words
+ *   word 4 total pending replicas     5..7 reserved
+ *   n_groups records of RBGTOPO_GROUP_WORDS words:
+ *     +0 gid  +1 flags (RBGTOPO_STEP_*)  +2 fixed_domain (-1 = none yet)
+ *     +3 q = number of roles  +4 role_off (q records of 4 words:
+ *        level, pending replicas, demand, role_flags)
+ *     +5 pair_off (pair[q][q])  +6 n_anchors  +7 anchor_off (node, role, count)
+ *     +8 assign_off (prefix sum of pending over earlier groups)
+ *     +9 n_pending (sum of the roles' pending)  +10,11 reserved
+ * Output: assign[total pending] in (group, role order, ordinal) order,
+ * status[n_groups] (RBGTOPO_PLACED_*), domain[n_groups]. */
+#define RBGTOPO_GROUPS_MAGIC 0x47474252
+#define RBGTOPO_GROUP_WORDS  12
+int32_t rbgtopo_place_groups(rbgtopo_ctx* ctx, const int32_t* groups,
+                             int64_t groups_words, int32_t* assign,
+                             int32_t* status, int32_t* domain);
+
 /* Same computation with the batch kept resident in HBM (bench `value` leg,
  * CUDA-graph replay): stage once, run many times, fetch results on demand. */
 int32_t rbgtopo_stage(rbgtopo_ctx* ctx, const int32_t* blob, int64_t blob_words,
                       int32_t* handle);
+/* run_staged only ENQUEUES `iters` passes on the call's stream (asynchronous);
+ * rbgtopo_fetch synchronises, copies the results of the last pass (any output
+ * pointer may be NULL) and harvests the timing of every pass since the
+ * previous fetch (rbgtopo_last_timing: score_ms = average k_score_select
+ * duration from CUDA events recorded around each launch). */
 int32_t rbgtopo_run_staged(rbgtopo_ctx* ctx, int32_t handle, int32_t iters);
 int32_t rbgtopo_fetch(rbgtopo_ctx* ctx, int32_t handle, int32_t* assign,
                       int32_t* status, int32_t* domain);

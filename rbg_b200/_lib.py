@@ -37,6 +37,7 @@ SIGNATURES = {
                                          i32p, C.c_int32, i32p, C.c_uint64]),
     "rbgtopo_update_nodes": (C.c_int32, [C.c_void_p, i32p, i32p, C.c_uint64]),
     "rbgtopo_score_assign": (C.c_int32, [C.c_void_p, i32p, C.c_int64, i32p, i32p, i32p]),
+    "rbgtopo_place_groups": (C.c_int32, [C.c_void_p, i32p, C.c_int64, i32p, i32p, i32p]),
     "rbgtopo_stage": (C.c_int32, [C.c_void_p, i32p, C.c_int64, i32p]),
     "rbgtopo_run_staged": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
     "rbgtopo_fetch": (C.c_int32, [C.c_void_p, C.c_int32, i32p, i32p, i32p]),

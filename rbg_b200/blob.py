@@ -82,3 +82,78 @@ class BlobBuilder:
 def blob_totals(blob: np.ndarray) -> Tuple[int, int, int]:
     """(n_steps, total replicas, total role rows) of a built blob."""
     return int(blob[2]), int(blob[4]), int(blob[5])
+
+
+GROUPS_MAGIC = 0x47474252
+GROUP_WORDS = 12
+
+
+@dataclass
+class Group:
+    """A whole RoleBasedGroup for rbgtopo_place_groups; roles sorted by (level, name)."""
+    gid: int
+    roles: List[Tuple[int, int, int, int]]          # (level, pending, demand, role_flags)
+    pair: Sequence[Sequence[int]]                    # [Q][Q]
+    anchors: List[Tuple[int, int, int]] = field(default_factory=list)
+    flags: int = 0
+    fixed_domain: int = -1
+
+
+class GroupsBuilder:
+    def __init__(self) -> None:
+        self.groups: List[Group] = []
+
+    def add(self, g: Group) -> "GroupsBuilder":
+        self.groups.append(g)
+        return self
+
+    def build(self) -> np.ndarray:
+        ng = len(self.groups)
+        base = HDR_WORDS + ng * GROUP_WORDS
+        table = np.zeros((ng, GROUP_WORDS), dtype=np.int64)
+        body: List[int] = []
+        pacc = 0
+        for i, g in enumerate(self.groups):
+            q = len(g.roles)
+            role_off = base + len(body)
+            for r in g.roles:
+                body.extend(int(x) for x in r)
+            pair_off = base + len(body)
+            for row in g.pair:
+                assert len(row) == q
+                body.extend(int(x) for x in row)
+            anchor_off = base + len(body)
+            for a in g.anchors:
+                body.extend(int(x) for x in a)
+            pend = sum(r[1] for r in g.roles)
+            table[i] = [g.gid, g.flags, g.fixed_domain, q, role_off, pair_off, len(g.anchors), anchor_off,
+                        pacc, pend, 0, 0]
+            pacc += pend
+        words = base + len(body)
+        out = np.zeros(words, dtype=np.int32)
+        out[0:8] = [GROUPS_MAGIC, VERSION, ng, words, pacc, 0, 0, 0]
+        out[HDR_WORDS:base] = table.reshape(-1)
+        out[base:] = np.asarray(body, dtype=np.int64) if body else []
+        return out
+
+
+def tile_groups_blob(blob: np.ndarray, copies: int, gid_stride: int = 1) -> np.ndarray:
+    """Replicate a 1-group blob `copies` times with gids gid0 + i*gid_stride
+    (vectorised: fleets of identical shapes)."""
+    assert int(blob[2]) == 1
+    rec = blob[HDR_WORDS:HDR_WORDS + GROUP_WORDS].astype(np.int64)
+    body = blob[HDR_WORDS + GROUP_WORDS:].astype(np.int64)
+    nb = len(body)
+    base = HDR_WORDS + copies * GROUP_WORDS
+    table = np.tile(rec, (copies, 1))
+    i = np.arange(copies, dtype=np.int64)
+    shift = (base - (HDR_WORDS + GROUP_WORDS)) + i * nb
+    table[:, 0] = rec[0] + i * gid_stride
+    for col in (4, 5, 7):
+        table[:, col] = rec[col] + shift
+    table[:, 8] = i * rec[9]
+    out = np.zeros(base + copies * nb, dtype=np.int32)
+    out[0:8] = [GROUPS_MAGIC, VERSION, copies, len(out), copies * rec[9], 0, 0, 0]
+    out[HDR_WORDS:base] = table.reshape(-1)
+    out[base:] = np.tile(body, copies)
+    return out

@@ -103,7 +103,9 @@ struct Batch {
   bool ran = false;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {};
-  std::vector<cudaEvent_t> it_ev;  // pairs around k_score_select per iteration
+  std::vector<cudaEvent_t> it_ev;  // triples (before score, after score, after select) per pass
+  int passes = 0, pend_launches = 0, untimed_or_timed_passes = 0;  // since the last harvest
+  bool shard_timed = false;
   BatchMeta m;
   DevBuf<int> blob;
   DevBuf<float> matrix;
@@ -389,37 +391,55 @@ int launch_select(rbgtopo_ctx* c, Batch* b, cudaStream_t s, const BatchDev& d, b
   return RBGTOPO_OK;
 }
 
-// full single-rank pipeline, `iters` times; leaves results on the device.
-int run_batch(rbgtopo_ctx* c, Batch* b, int iters) {
-  cudaStream_t s = stream_of(c, b);
-  while ((int)b->it_ev.size() < 2 * iters) {
+constexpr int kMaxTimedPasses = 512;
+
+int ensure_pass_events(Batch* b, int passes) {
+  while ((int)b->it_ev.size() < 3 * passes) {
     cudaEvent_t e;
     CK(cudaEventCreate(&e));
     b->it_ev.push_back(e);
   }
-  int launches = 0;
-  CK(cudaEventRecord(b->ev[2], s));
-  BatchDev d = batch_dev(c, b);
-  for (int it = 0; it < iters; ++it) {
-    CK(cudaEventRecord(b->it_ev[2 * it], s));
-    int rc = launch_score(c, b, s);
-    if (rc) return rc;
-    ++launches;
-    CK(cudaEventRecord(b->it_ev[2 * it + 1], s));
-    rc = launch_select(c, b, s, d, true, true, true, &launches);
-    if (rc) return rc;
-  }
-  CK(cudaEventRecord(b->ev[3], s));
-  CK(cudaGetLastError());
-  b->ran = true;
-  std::lock_guard<std::mutex> g(c->stat_mu);
-  c->launches += launches;
-  c->last.launches = launches;
   return RBGTOPO_OK;
 }
 
-int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int32_t* domain,
-                int iters) {
+// full single-rank pipeline, `iters` times, ENQUEUE ONLY; results stay on the
+// device.  Every pass gets three events (before score, after score, after
+// select) until kMaxTimedPasses passes are pending harvest.
+int run_batch(rbgtopo_ctx* c, Batch* b, int iters) {
+  cudaStream_t s = stream_of(c, b);
+  int launches = 0;
+  BatchDev d = batch_dev(c, b);
+  for (int it = 0; it < iters; ++it) {
+    const bool timed = b->passes < kMaxTimedPasses;
+    const int e0 = 3 * b->passes;
+    if (timed) {
+      int rc = ensure_pass_events(b, b->passes + 1);
+      if (rc) return rc;
+      CK(cudaEventRecord(b->it_ev[e0], s));
+    }
+    int rc = launch_score(c, b, s);
+    if (rc) return rc;
+    ++launches;
+    if (timed) CK(cudaEventRecord(b->it_ev[e0 + 1], s));
+    rc = launch_select(c, b, s, d, true, true, true, &launches);
+    if (rc) return rc;
+    if (timed) {
+      CK(cudaEventRecord(b->it_ev[e0 + 2], s));
+      b->passes += 1;
+    }
+    b->untimed_or_timed_passes += 1;
+  }
+  CK(cudaGetLastError());
+  b->ran = true;
+  b->pend_launches += launches;
+  std::lock_guard<std::mutex> g(c->stat_mu);
+  c->launches += launches;
+  return RBGTOPO_OK;
+}
+
+// synchronise, copy the last pass's results out, harvest the timing of every
+// pass enqueued since the previous harvest.
+int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int32_t* domain) {
   cudaStream_t s = stream_of(c, b);
   const BatchMeta& m = b->m;
   const size_t out_n = (size_t)m.total_r + 2 * (size_t)m.n_steps;
@@ -431,26 +451,32 @@ int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int3
   if (assign && m.total_r) memcpy(assign, b->h_out.p, (size_t)m.total_r * 4);
   if (status && m.n_steps) memcpy(status, b->h_out.p + m.total_r, (size_t)m.n_steps * 4);
   if (domain && m.n_steps) memcpy(domain, b->h_out.p + m.total_r + m.n_steps, (size_t)m.n_steps * 4);
-  // timing
   rbgtopo_timing tm{};
   float x = 0.f;
   if (cudaEventElapsedTime(&x, b->ev[0], b->ev[1]) == cudaSuccess) tm.h2d_ms = x;
-  float score = 0.f;
-  for (int it = 0; it < iters && 2 * it + 1 < (int)b->it_ev.size(); ++it)
-    if (cudaEventElapsedTime(&x, b->it_ev[2 * it], b->it_ev[2 * it + 1]) == cudaSuccess) score += x;
-  tm.score_ms = iters > 0 ? score / iters : 0.f;
-  if (cudaEventElapsedTime(&x, b->ev[2], b->ev[3]) == cudaSuccess)
-    tm.select_ms = iters > 0 ? x / iters - tm.score_ms : 0.f;
+  float score = 0.f, sel = 0.f;
+  for (int it = 0; it < b->passes; ++it) {
+    if (cudaEventElapsedTime(&x, b->it_ev[3 * it], b->it_ev[3 * it + 1]) == cudaSuccess) score += x;
+    if (cudaEventElapsedTime(&x, b->it_ev[3 * it + 1], b->it_ev[3 * it + 2]) == cudaSuccess) sel += x;
+  }
+  if (b->passes > 0) {
+    tm.score_ms = score / b->passes;
+    tm.select_ms = sel / b->passes;
+  }
   if (cudaEventElapsedTime(&x, b->ev[4], b->ev[5]) == cudaSuccess) tm.d2h_ms = x;
-  if (cudaEventElapsedTime(&x, b->ev[0], b->ev[5]) == cudaSuccess) tm.total_ms = x;
+  tm.total_ms = tm.h2d_ms + score + sel + tm.d2h_ms;
   tm.base_ms = c->topo.base_ms;
   tm.scores = m.scores;
   tm.algo_bytes = m.algo_bytes;
+  tm.launches = b->pend_launches;
+  const int total_passes = b->untimed_or_timed_passes;
+  b->passes = 0;
+  b->pend_launches = 0;
+  b->untimed_or_timed_passes = 0;
   std::lock_guard<std::mutex> g(c->stat_mu);
-  tm.launches = c->last.launches;
   c->last = tm;
   c->calls += 1;
-  c->scores_total += m.scores * std::max(1, iters);
+  c->scores_total += m.scores * std::max(1, total_passes);
   return RBGTOPO_OK;
 }
 
@@ -645,8 +671,211 @@ int32_t rbgtopo_score_assign(rbgtopo_ctx* c, const int32_t* blob, int64_t words,
   if (rc) return rc;
   rc = stage_into(c, b, blob, words);
   if (!rc) rc = run_batch(c, b, 1);
-  if (!rc) rc = fetch_batch(c, b, assign, status, domain, 1);
+  if (!rc) rc = fetch_batch(c, b, assign, status, domain);
   if (rc) cudaStreamSynchronize(stream_of(c, b));
+  release_batch(c, b);
+  return rc;
+}
+
+// ---- whole groups: level/wave loop on the host side of the ABI -------------
+namespace {
+struct GroupRun {
+  const int32_t* rec = nullptr;
+  const int32_t* roles = nullptr;  // q x (level, pending, demand, role_flags)
+  const int32_t* pair = nullptr;   // q x q
+  int q = 0;
+  int cur_role = 0, cur_taken = 0;  // wave cursor
+  int fixed_domain = -1;
+  int status = 0;
+  bool failed = false;
+  std::vector<int> unplaced;        // per role
+  std::vector<int32_t> anchors;     // (node, role, count)*
+  std::vector<int32_t> consumed;    // (node, amount)*
+  // current wave
+  std::vector<int> w_role, w_first, w_count;
+  bool done() const { return failed || cur_role >= q; }
+};
+}  // namespace
+
+int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int32_t* assign,
+                             int32_t* status, int32_t* domain) {
+  if (!c || !gb) return fail(RBGTOPO_EINVAL, "null argument");
+  if (c->cfg.world != 1) return fail(RBGTOPO_EINVAL, "place_groups needs world == 1");
+  if (words < RBGTOPO_HDR_WORDS || gb[0] != RBGTOPO_GROUPS_MAGIC || gb[1] != RBGTOPO_ABI_VERSION ||
+      gb[3] != words)
+    return fail(RBGTOPO_EINVAL, "bad groups blob header");
+  const int ng = gb[2];
+  if (ng < 0 || (int64_t)RBGTOPO_HDR_WORDS + (int64_t)ng * RBGTOPO_GROUP_WORDS > words)
+    return fail(RBGTOPO_EINVAL, "group table exceeds blob");
+  std::shared_lock<std::shared_mutex> lk(c->topo_mu);
+  if (!c->topo.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
+  CK(cudaSetDevice(c->cfg.device));
+  auto in = [&](long long off, long long cnt) { return off >= 0 && cnt >= 0 && off + cnt <= words; };
+  std::vector<GroupRun> runs(ng);
+  long long pacc = 0;
+  for (int g = 0; g < ng; ++g) {
+    const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
+    GroupRun& r = runs[g];
+    r.rec = rec;
+    r.q = rec[3];
+    if (r.q < 1 || r.q > RBGTOPO_MAX_GROUP_ROLES) return fail(RBGTOPO_ELIMIT, "group %d: %d roles", g, r.q);
+    if (!in(rec[4], 4LL * r.q) || !in(rec[5], (long long)r.q * r.q) || !in(rec[7], 3LL * rec[6]))
+      return fail(RBGTOPO_EINVAL, "group %d: section out of bounds", g);
+    r.roles = gb + rec[4];
+    r.pair = gb + rec[5];
+    r.fixed_domain = rec[2];
+    r.unplaced.resize(r.q);
+    long long pend = 0;
+    for (int i = 0; i < r.q; ++i) {
+      if (r.roles[4 * i + 1] < 0 || (i && r.roles[4 * i] < r.roles[4 * (i - 1)]))
+        return fail(RBGTOPO_EINVAL, "group %d role %d: pending < 0 or levels not ascending", g, i);
+      r.unplaced[i] = r.roles[4 * i + 1];
+      pend += r.roles[4 * i + 1];
+    }
+    if (rec[8] != pacc || rec[9] != pend) return fail(RBGTOPO_EINVAL, "group %d: bad assign_off/n_pending", g);
+    pacc += pend;
+    r.anchors.assign(gb + rec[7], gb + rec[7] + 3LL * rec[6]);
+    while (r.cur_role < r.q && r.roles[4 * r.cur_role + 1] == 0) ++r.cur_role;
+  }
+  if (gb[4] != pacc) return fail(RBGTOPO_EINVAL, "total pending mismatch");
+  for (long long i = 0; i < pacc; ++i) assign[i] = -1;
+
+  Batch* b = nullptr;
+  int rc = acquire_batch(c, &b);
+  if (rc) return rc;
+  rbgtopo_timing total{};
+  std::vector<int32_t> blob, w_assign, w_status, w_domain;
+  std::vector<int> active;
+  while (true) {
+    active.clear();
+    for (int g = 0; g < ng; ++g)
+      if (!runs[g].done()) active.push_back(g);
+    if (active.empty()) break;
+    // ---- build this wave's step blob
+    const int ns = (int)active.size();
+    blob.assign((size_t)RBGTOPO_HDR_WORDS + (size_t)ns * RBGTOPO_STEP_WORDS, 0);
+    int racc = 0, rowacc = 0;
+    for (int i = 0; i < ns; ++i) {
+      GroupRun& r = runs[active[i]];
+      r.w_role.clear(); r.w_first.clear(); r.w_count.clear();
+      const int level = r.roles[4 * r.cur_role];
+      int cr = r.cur_role, taken = r.cur_taken, n = 0;
+      while (cr < r.q && r.roles[4 * cr] == level && n < RBGTOPO_MAX_STEP_REPLICAS &&
+             (int)r.w_role.size() < RBGTOPO_MAX_STEP_ROLES) {
+        const int left = r.roles[4 * cr + 1] - taken;
+        if (left <= 0) { ++cr; taken = 0; continue; }
+        const int take = std::min(left, RBGTOPO_MAX_STEP_REPLICAS - n);
+        r.w_role.push_back(cr); r.w_first.push_back(taken); r.w_count.push_back(take);
+        n += take;
+        taken += take;
+        if (taken == r.roles[4 * cr + 1]) { ++cr; taken = 0; }
+      }
+      const int P = (int)r.w_role.size();
+      int32_t st[RBGTOPO_STEP_WORDS] = {0};
+      st[0] = r.rec[0];
+      st[1] = r.rec[1];
+      st[2] = (r.rec[1] & RBGTOPO_STEP_EXCLUSIVE) ? r.fixed_domain : -1;
+      st[3] = P;
+      st[4] = (int32_t)blob.size();
+      for (int p = 0; p < P; ++p) {
+        const int ri = r.w_role[p];
+        int need = 0;
+        for (int q = 0; q < r.q; ++q)
+          if (r.pair[ri * r.q + q] > 0) need += r.unplaced[q];
+        need = std::min(need, RBGTOPO_NEED_CAP);
+        blob.push_back(r.w_count[p]);
+        blob.push_back(r.roles[4 * ri + 2]);
+        blob.push_back(need);
+        blob.push_back(r.roles[4 * ri + 3]);
+      }
+      st[5] = r.q;
+      st[6] = (int32_t)blob.size();
+      for (int p = 0; p < P; ++p)
+        blob.insert(blob.end(), r.pair + r.w_role[p] * r.q, r.pair + (r.w_role[p] + 1) * r.q);
+      st[7] = (int32_t)(r.anchors.size() / 3);
+      st[8] = (int32_t)blob.size();
+      blob.insert(blob.end(), r.anchors.begin(), r.anchors.end());
+      st[9] = (int32_t)(r.consumed.size() / 2);
+      st[10] = (int32_t)blob.size();
+      blob.insert(blob.end(), r.consumed.begin(), r.consumed.end());
+      st[11] = n;
+      st[12] = racc;
+      st[13] = rowacc;
+      racc += n;
+      rowacc += P;
+      memcpy(blob.data() + RBGTOPO_HDR_WORDS + (size_t)i * RBGTOPO_STEP_WORDS, st, sizeof st);
+    }
+    blob[0] = RBGTOPO_BLOB_MAGIC;
+    blob[1] = RBGTOPO_ABI_VERSION;
+    blob[2] = ns;
+    blob[3] = (int32_t)blob.size();
+    blob[4] = racc;
+    blob[5] = rowacc;
+    w_assign.resize(racc);
+    w_status.resize(ns);
+    w_domain.resize(ns);
+    rc = stage_into(c, b, blob.data(), (int64_t)blob.size());
+    if (!rc) rc = run_batch(c, b, 1);
+    if (!rc) rc = fetch_batch(c, b, w_assign.data(), w_status.data(), w_domain.data());
+    if (rc) break;
+    {
+      std::lock_guard<std::mutex> g(c->stat_mu);
+      total.h2d_ms += c->last.h2d_ms; total.score_ms += c->last.score_ms;
+      total.select_ms += c->last.select_ms; total.d2h_ms += c->last.d2h_ms;
+      total.total_ms += c->last.total_ms; total.launches += c->last.launches;
+      total.scores += c->last.scores; total.algo_bytes += c->last.algo_bytes;
+    }
+    // ---- absorb the placements
+    int off = 0;
+    for (int i = 0; i < ns; ++i) {
+      GroupRun& r = runs[active[i]];
+      const bool excl = (r.rec[1] & RBGTOPO_STEP_EXCLUSIVE) != 0;
+      bool any = false;
+      for (size_t p = 0; p < r.w_role.size(); ++p) {
+        const int ri = r.w_role[p];
+        int ord0 = 0;  // index of this role's first replica inside the group's assign range
+        for (int k = 0; k < ri; ++k) ord0 += r.roles[4 * k + 1];
+        for (int k = 0; k < r.w_count[p]; ++k, ++off) {
+          const int node = w_assign[off];
+          assign[r.rec[8] + ord0 + r.w_first[p] + k] = node;
+          if (node >= 0) {
+            any = true;
+            r.anchors.push_back(node); r.anchors.push_back(ri); r.anchors.push_back(1);
+            r.consumed.push_back(node); r.consumed.push_back(r.roles[4 * ri + 2]);
+            r.unplaced[ri] -= 1;
+          }
+        }
+      }
+      if (excl && w_domain[i] >= 0 && any) r.fixed_domain = w_domain[i];
+      r.status = std::max(r.status, w_status[i]);
+      if ((r.rec[1] & RBGTOPO_STEP_GANG) && w_status[i] != RBGTOPO_PLACED_ALL) r.failed = true;
+      // advance the cursor past this wave
+      const int last = (int)r.w_role.size() - 1;
+      r.cur_role = r.w_role[last];
+      r.cur_taken = r.w_first[last] + r.w_count[last];
+      if (r.cur_taken >= r.roles[4 * r.cur_role + 1]) { ++r.cur_role; r.cur_taken = 0; }
+      while (r.cur_role < r.q && r.roles[4 * r.cur_role + 1] == 0) ++r.cur_role;
+    }
+  }
+  if (!rc) {
+    for (int g = 0; g < ng; ++g) {
+      const GroupRun& r = runs[g];
+      const bool excl = (r.rec[1] & RBGTOPO_STEP_EXCLUSIVE) != 0;
+      if (r.failed) {  // gang: nothing of the group is placed
+        for (int k = 0; k < r.rec[9]; ++k) assign[r.rec[8] + k] = -1;
+        if (status) status[g] = RBGTOPO_GANG_FAILED;
+        if (domain) domain[g] = -1;
+      } else {
+        if (status) status[g] = r.status;
+        if (domain) domain[g] = excl ? r.fixed_domain : -1;
+      }
+    }
+    std::lock_guard<std::mutex> g(c->stat_mu);
+    total.base_ms = c->topo.base_ms;
+    c->last = total;
+  } else {
+    cudaStreamSynchronize(stream_of(c, b));
+  }
   release_batch(c, b);
   return rc;
 }
@@ -676,9 +905,7 @@ int32_t rbgtopo_run_staged(rbgtopo_ctx* c, int32_t handle, int32_t iters) {
   Batch* b = batch_of(c, handle);
   if (!b) return fail(RBGTOPO_EINVAL, "bad handle %d", handle);
   CK(cudaSetDevice(c->cfg.device));
-  int rc = run_batch(c, b, iters);
-  if (rc) return rc;
-  return fetch_batch(c, b, nullptr, nullptr, nullptr, iters);
+  return run_batch(c, b, iters);
 }
 
 int32_t rbgtopo_fetch(rbgtopo_ctx* c, int32_t handle, int32_t* assign, int32_t* status, int32_t* domain) {
@@ -686,15 +913,7 @@ int32_t rbgtopo_fetch(rbgtopo_ctx* c, int32_t handle, int32_t* assign, int32_t* 
   Batch* b = batch_of(c, handle);
   if (!b || !b->ran) return fail(RBGTOPO_EINVAL, "handle %d has no results", handle);
   CK(cudaSetDevice(c->cfg.device));
-  cudaStream_t s = stream_of(c, b);
-  const BatchMeta& m = b->m;
-  const size_t out_n = (size_t)m.total_r + 2 * (size_t)m.n_steps;
-  if (out_n) CK(cudaMemcpyAsync(b->h_out.p, b->out.p, out_n * 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
-  if (assign && m.total_r) memcpy(assign, b->h_out.p, (size_t)m.total_r * 4);
-  if (status && m.n_steps) memcpy(status, b->h_out.p + m.total_r, (size_t)m.n_steps * 4);
-  if (domain && m.n_steps) memcpy(domain, b->h_out.p + m.total_r + m.n_steps, (size_t)m.n_steps * 4);
-  return RBGTOPO_OK;
+  return fetch_batch(c, b, assign, status, domain);
 }
 
 int32_t rbgtopo_release(rbgtopo_ctx* c, int32_t handle) {
@@ -747,22 +966,23 @@ int32_t rbgtopo_shard_score(rbgtopo_ctx* c, int32_t handle, void** keys_dev, int
   if (!b) return fail(RBGTOPO_EINVAL, "bad handle %d", handle);
   CK(cudaSetDevice(c->cfg.device));
   cudaStream_t s = stream_of(c, b);
-  while (b->it_ev.size() < 2) {
-    cudaEvent_t e;
-    CK(cudaEventCreate(&e));
-    b->it_ev.push_back(e);
+  const bool timed = b->passes < kMaxTimedPasses;
+  const int e0 = 3 * b->passes;
+  if (timed) {
+    int rc0 = ensure_pass_events(b, b->passes + 1);
+    if (rc0) return rc0;
+    CK(cudaEventRecord(b->it_ev[e0], s));
   }
-  CK(cudaEventRecord(b->ev[2], s));
-  CK(cudaEventRecord(b->it_ev[0], s));
   int rc = launch_score(c, b, s);
   if (rc) return rc;
-  CK(cudaEventRecord(b->it_ev[1], s));
+  if (timed) CK(cudaEventRecord(b->it_ev[e0 + 1], s));
+  b->shard_timed = timed;
+  b->pend_launches += 1;
   CK(cudaGetLastError());
   *keys_dev = b->lists.p;
   *keys_bytes = (int64_t)std::max(1, b->m.total_p) * c->lc * KS * 8;
   std::lock_guard<std::mutex> g(c->stat_mu);
   c->launches += 1;
-  c->last.launches = 1;
   return RBGTOPO_OK;
 }
 
@@ -785,9 +1005,9 @@ int32_t rbgtopo_shard_merge(rbgtopo_ctx* c, int32_t handle, const void* keys_all
   *need_pass2 = b->m.any_excl_unknown ? 1 : 0;
   *keys2_dev = b->excl.p;
   *keys2_bytes = (int64_t)std::max(1, b->m.total_p) * KS * 8;
+  b->pend_launches += launches;
   std::lock_guard<std::mutex> g(c->stat_mu);
   c->launches += launches;
-  c->last.launches += launches;
   return RBGTOPO_OK;
 }
 
@@ -808,15 +1028,18 @@ int32_t rbgtopo_shard_assign(rbgtopo_ctx* c, int32_t handle, const void* keys2_a
   int launches = 0;
   int rc = launch_select(c, b, s, d, false, false, true, &launches);
   if (rc) return rc;
-  CK(cudaEventRecord(b->ev[3], s));
+  if (b->shard_timed) {
+    CK(cudaEventRecord(b->it_ev[3 * b->passes + 2], s));
+    b->passes += 1;
+    b->shard_timed = false;
+  }
+  b->untimed_or_timed_passes += 1;
   CK(cudaGetLastError());
   b->ran = true;
-  {
-    std::lock_guard<std::mutex> g(c->stat_mu);
-    c->launches += launches;
-    c->last.launches += launches;
-  }
-  return fetch_batch(c, b, nullptr, nullptr, nullptr, 1);
+  b->pend_launches += launches;
+  std::lock_guard<std::mutex> g(c->stat_mu);
+  c->launches += launches;
+  return RBGTOPO_OK;
 }
 
 int32_t rbgtopo_set_stream(rbgtopo_ctx* c, void* stream) {

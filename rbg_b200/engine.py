@@ -81,6 +81,16 @@ class TopoPlacer:
         self._check(self.lib.rbgtopo_score_assign(self._h, _p(blob), len(blob), _p(assign), _p(status), _p(domain)))
         return assign[:tr], status[:ns], domain[:ns]
 
+    def place_groups(self, groups_blob: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """Whole groups, all dependency levels (C++ wave loop behind the ABI)."""
+        gb = _i32(groups_blob)
+        ng, tp = int(gb[2]), int(gb[4])
+        assign = np.empty(max(tp, 1), dtype=np.int32)
+        status = np.empty(max(ng, 1), dtype=np.int32)
+        domain = np.empty(max(ng, 1), dtype=np.int32)
+        self._check(self.lib.rbgtopo_place_groups(self._h, _p(gb), len(gb), _p(assign), _p(status), _p(domain)))
+        return assign[:tp], status[:ng], domain[:ng]
+
     # -- staged (device-resident) batches
     def stage(self, blob: np.ndarray) -> int:
         blob = _i32(blob)

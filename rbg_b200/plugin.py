@@ -32,7 +32,7 @@ import numpy as np
 
 from . import _lib
 from .blob import (MAX_STEP_REPLICAS, MAX_STEP_ROLES, NEED_CAP, ROLE_EXCLUSIVE, STEP_EXCLUSIVE, STEP_GANG,
-                   BlobBuilder, Step)
+                   BlobBuilder, Group, GroupsBuilder, Step)
 from .engine import TopoPlacer
 
 RBG_PREFIX = "rbg.workloads.x-k8s.io/"                       # api/workloads/constants
@@ -132,7 +132,7 @@ class _Wave:
 class _GroupRun:
     """Per-group state while its levels/waves are placed."""
 
-    def __init__(self, rbg: RoleBasedGroup, arith: HostArith):
+    def __init__(self, rbg: RoleBasedGroup, arith: HostArith, plan_waves: bool = True):
         self.rbg = rbg
         roles = rbg.roles
         self.Q = len(roles)
@@ -171,7 +171,10 @@ class _GroupRun:
         self.scores = 0
         # waves: levels in order, roles lexicographic inside a level, packed to the ABI limits
         self.waves: List[_Wave] = []
-        for level in arith.dependency_levels(roles):
+        levels = arith.dependency_levels(roles)
+        self.order = [ri for level in levels for ri in level]        # (level, name) order
+        self.level_of = {ri: li for li, level in enumerate(levels) for ri in level}
+        for level in (levels if plan_waves else []):
             cur_roles: List[Tuple[int, int, int]] = []
             cur_n = 0
             for ri in level:
@@ -241,8 +244,44 @@ class B200TopoPodGroupManager:
         return self.reconcile_pod_groups([rbg])[0]
 
     # -- batched form: the concurrent reconciles of one informer snapshot
-    #    (cmd/rbgs/main.go:140-143) coalesced into level-synchronous launches ----
+    #    (cmd/rbgs/main.go:140-143) coalesced into level-synchronous launches.
+    #    The level/wave loop runs behind the ABI (rbgtopo_place_groups, C++).
+    def groups_blob(self, rbgs: Sequence[RoleBasedGroup]):
+        """Marshal RoleBasedGroups into the GROUPS wire format (the Go shim does
+        the same from the typed objects).  Returns (blob, runs)."""
+        runs = [_GroupRun(r, self.arith, plan_waves=False) for r in rbgs]
+        gb = GroupsBuilder()
+        for g in runs:
+            roles = [(g.level_of[ri], g.pending[ri], g.rbg.roles[ri].demand,
+                      ROLE_EXCLUSIVE if g.role_excl[ri] else 0) for ri in g.order]
+            pair = [[int(g.pair[a, b]) for b in g.order] for a in g.order]
+            pos = {ri: k for k, ri in enumerate(g.order)}
+            anchors = [(n, pos[q], c) for (n, q), c in sorted(g.anchors.items())]
+            flags = (STEP_EXCLUSIVE if g.exclusive else 0) | (STEP_GANG if g.gang else 0)
+            gb.add(Group(gid=g.rbg.gid, roles=roles, pair=pair, anchors=anchors, flags=flags,
+                         fixed_domain=g.fixed_domain if g.exclusive else -1))
+        return gb.build(), runs
+
     def reconcile_pod_groups(self, rbgs: Sequence[RoleBasedGroup]) -> List[Placement]:
+        blob, runs = self.groups_blob(rbgs)
+        assign, status, domain = self.placer.place_groups(blob)
+        out, off = [], 0
+        n_nodes = self.placer.n_nodes
+        for i, g in enumerate(runs):
+            nodes: Dict[str, int] = {}
+            for ri in g.order:
+                role = g.rbg.roles[ri]
+                for c in range(g.pending[ri]):
+                    nodes[f"{g.rbg.name}-{role.name}-{g.first_ordinal[ri] + c}"] = int(assign[off])
+                    off += 1
+            p = Placement(int(status[i]), nodes, int(domain[i]), len(nodes) * n_nodes)
+            self._hints[(g.rbg.namespace, g.rbg.name)] = p
+            out.append(p)
+        return out
+
+    # -- the same loop in Python over single-level batches (rbgtopo_score_assign):
+    #    kept as the readable mirror of the C++ loop and for cross-checks.
+    def reconcile_pod_groups_by_waves(self, rbgs: Sequence[RoleBasedGroup]) -> List[Placement]:
         runs = [_GroupRun(r, self.arith) for r in rbgs]
         n_nodes = self.placer.n_nodes
         w = 0
@@ -264,15 +303,16 @@ class B200TopoPodGroupManager:
             w += 1
         out = []
         for g in runs:
+            nodes = {}
+            for wv in g.waves:   # every pending replica, in (level, name, ordinal) order
+                for ri, ordinal, cnt in wv.roles:
+                    for c in range(cnt):
+                        key = f"{g.rbg.name}-{g.rbg.roles[ri].name}-{ordinal + c}"
+                        nodes[key] = -1 if g.failed else g.result_nodes.get(key, -1)
             if g.failed:   # gang: all-or-nothing over GetGroupSize() pods (manager.go:131)
-                nodes = {k: -1 for k in g.result_nodes}
-                for wv in g.waves:
-                    for ri, ordinal, cnt in wv.roles:
-                        for c in range(cnt):
-                            nodes.setdefault(f"{g.rbg.name}-{g.rbg.roles[ri].name}-{ordinal + c}", -1)
                 p = Placement(2, nodes, -1, g.scores)
             else:
-                p = Placement(g.status, dict(g.result_nodes), g.fixed_domain if g.exclusive else -1, g.scores)
+                p = Placement(g.status, nodes, g.fixed_domain if g.exclusive else -1, g.scores)
             self._hints[(g.rbg.namespace, g.rbg.name)] = p
             out.append(p)
         return out
