@@ -189,10 +189,14 @@ static int step_place(const topo_t *t, const int32_t *blob, int64_t words,
   }
   *domain_out = dstar;
 
-  /* A.5 selection: top-K feasible nodes per role row, K = min(n, R) */
-  const int K = R < n ? R : n;
+  /* §3.5 selection: top-K_p feasible nodes per role row, K_p = min(n, replicas of
+   * the step up to and including role p): the replicas placed before role p's
+   * last one can exhaust at most K_p - 1 distinct nodes, so K_p always suffices. */
   uint64_t lists[MAX_STEP_ROLES][KMAX];
+  int kacc = 0;
   for (int p = 0; p < P; ++p) {
+    kacc += roles[4 * p];
+    const int K = kacc < n ? kacc : n;
     const int role_excl = excl_step && (roles[4 * p + 3] & ROLE_EXCLUSIVE);
     const float *S = sc->S + (size_t)p * n;
     int32_t cnt = 0;
@@ -213,7 +217,7 @@ static int step_place(const topo_t *t, const int32_t *blob, int64_t words,
     const int32_t demand = roles[4 * p + 1];
     for (int c = 0; c < roles[4 * p]; ++c, ++r) {
       int32_t pick = -1;
-      for (int k = 0; k < K; ++k) {
+      for (int k = 0; k < KMAX; ++k) { /* K_p keys, then zeros */
         uint64_t key = lists[p][k];
         if (!key) break;
         int32_t node = (int32_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFu));

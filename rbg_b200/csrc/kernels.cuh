@@ -271,237 +271,4 @@ k_base(TopoDev t, const int2* __restrict__ tiles, int fmin_staged, int fmin_byte
   }
 }
 
-// ============================================================ k_score_select
-// One work item = (step, chunk of `chunk` nodes of this rank's slab).
-//   1. zero the per-role delta rows in smem, load capacity / ownership
-//   2. scatter the step's anchor pods: walk CSR row m, add pair*c*w to the
-//      delta of every neighbour inside the chunk (+ self term), subtract the
-//      consumed capacity
-//   3. stream: S = need*base + delta, mask infeasible -> -inf, write the
-//      replica rows of the dense matrix with 128-bit streaming stores, keep S in
-//      smem and a per-thread (score, node) maximum per role
-//   4. warp p selects the exact top-K of role row p: the K threads with the
-//      largest maxima hold every top-K element, their
-//      elements are gathered from smem and reduced with warp_topk
-template <int P>
-__device__ __forceinline__ void score_item(const TopoDev& t, const BatchDev& b, const int* hdr,
-                                           int step, int ch, float* sS, int* sAvail,
-                                           uint32_t* sBlk, unsigned long long* sTmax,
-                                           unsigned long long* sScr, const int* sRole,
-                                           const int* sPair) {
-  const int T = b.chunk;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n0 = t.slab_lo + ch * T;
-  const int n1 = min(n0 + T, t.slab_hi);
-  const int gid = hdr[0], flags = hdr[1], fixed_domain = hdr[2];
-  const int Q = hdr[5];
-  const int n_anchors = hdr[7], anchor_off = hdr[8];
-  const int n_cons = hdr[9], cons_off = hdr[10];
-  const int R = hdr[11], rep_off = hdr[12], rolerow_off = hdr[13];
-  const bool excl_step = (flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
-  const int K = min(R, t.n);
-
-  // ---- 1. init
-  for (int i = tid; i < T; i += SCORE_THREADS) {
-#pragma unroll
-    for (int p = 0; p < P; ++p) sS[p * T + i] = 0.0f;
-    int n = n0 + i;
-    int av = -1;
-    bool blk = false;
-    if (n < n1) {
-      av = t.free_[n];
-      if (excl_step) {
-        int o = t.node_owner[n];
-        blk = !(o == -1 || o == gid);
-      }
-    }
-    sAvail[i] = av;
-    uint32_t bm = __ballot_sync(FULL, blk);
-    if (lane == 0) sBlk[i >> 5] = bm;
-  }
-  __syncthreads();
-
-  // ---- 2. anchors (one warp per anchor pod) and consumed capacity
-  const int* anc = b.blob + anchor_off;
-  for (int a = warp; a < n_anchors; a += SCORE_WARPS) {
-    const int m = anc[3 * a], q = anc[3 * a + 1], c = anc[3 * a + 2];
-    int coef[P];
-    bool any = false;
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-      coef[p] = sPair[p * MAXQ + q] * c;
-      any |= coef[p] != 0;
-    }
-    if (!any) continue;
-    const int rb = t.row_ptr[m], re = t.row_ptr[m + 1];
-    for (int j = rb + lane; j < re; j += 32) {
-      const int nn = t.col[j];
-      if (nn >= n0 && nn < n1) {
-        const int wv = t.w[j];
-#pragma unroll
-        for (int p = 0; p < P; ++p)
-          if (coef[p]) atomicAdd(&sS[p * T + (nn - n0)], (float)(coef[p] * wv));
-      }
-    }
-    if (lane == 0 && m >= n0 && m < n1) {
-#pragma unroll
-      for (int p = 0; p < P; ++p)
-        if (coef[p]) atomicAdd(&sS[p * T + (m - n0)], (float)(coef[p] * RBGTOPO_SELF_W));
-    }
-  }
-  const int* con = b.blob + cons_off;
-  for (int c = tid; c < n_cons; c += SCORE_THREADS) {
-    const int m = con[2 * c];
-    if (m >= n0 && m < n1) atomicSub(&sAvail[m - n0], con[2 * c + 1]);
-  }
-  __syncthreads();
-
-  // ---- 3. stream
-  float bestS[P];
-  int bestN[P];
-  float need[P];
-  int demand[P], rowbase[P], count[P];
-  bool rexcl[P];
-  {
-    int acc = 0;
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-      count[p] = sRole[4 * p];
-      demand[p] = sRole[4 * p + 1];
-      need[p] = (float)sRole[4 * p + 2];
-      rexcl[p] = excl_step && (sRole[4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE);
-      rowbase[p] = acc;
-      acc += count[p];
-      bestS[p] = -INFINITY;
-      bestN[p] = 0;
-    }
-  }
-  const bool write_rows = b.emit_matrix || (excl_step && fixed_domain < 0);
-  const bool restrict_fixed = excl_step && fixed_domain >= 0;
-  const int groups = T >> 2;
-  for (int g = tid; g < groups; g += SCORE_THREADS) {
-    const int t0 = g << 2;
-    const int n = n0 + t0;
-    if (n >= n1) break;
-    const float4 b4 = *reinterpret_cast<const float4*>(t.base + n);
-    const int4 av4 = *reinterpret_cast<const int4*>(sAvail + t0);
-    const uint32_t blkbits = (sBlk[t0 >> 5] >> (t0 & 31)) & 0xFu;
-    uint32_t dommask = 0xFu;  // lanes allowed for selection under a fixed domain
-    if (restrict_fixed) {
-      dommask = 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (n + i < n1 && t.domain[n + i] == fixed_domain) dommask |= 1u << i;
-    }
-    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-    const int av[4] = {av4.x, av4.y, av4.z, av4.w};
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-      float4 s4 = *reinterpret_cast<float4*>(sS + p * T + t0);
-      float v[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float x = fmaf(need[p], bb[i], v[i]);
-        bool feas = (av[i] >= demand[p]) && !(rexcl[p] && ((blkbits >> i) & 1u));
-        x = feas ? x : -INFINITY;
-        v[i] = x;
-        float sel = (rexcl[p] && !((dommask >> i) & 1u)) ? -INFINITY : x;
-        if (sel > bestS[p]) {
-          bestS[p] = sel;
-          bestN[p] = n + i;
-        }
-      }
-      float4 o4 = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(sS + p * T + t0) = o4;
-      if (write_rows) {
-        float* rowp = b.matrix + (size_t)(rep_off + rowbase[p]) * t.slab_stride + (n - t.slab_lo);
-        for (int c = 0; c < count[p]; ++c) st_stream_f4(rowp + (size_t)c * t.slab_stride, o4);
-      }
-    }
-  }
-#pragma unroll
-  for (int p = 0; p < P; ++p)
-    sTmax[p * SCORE_THREADS + tid] = (bestS[p] == -INFINITY) ? 0ull : make_key(bestS[p], bestN[p]);
-  __syncthreads();
-
-  // ---- 4. select: warp p owns role row p
-  if (warp < P) {
-    const int p = warp;
-    unsigned long long* scr = sScr + warp * (KS * 8 + KS);  // survivors + winners
-    unsigned long long* win = scr + KS * 8;
-    const int nwin = warp_topk(sTmax + p * SCORE_THREADS, SCORE_THREADS, K, scr, KS * 8, win);
-    // gather every element of the winning threads into sTmax[p][..] (reused)
-    unsigned long long* cand = sTmax + p * SCORE_THREADS;
-    const int gpt = (groups + SCORE_THREADS - 1) / SCORE_THREADS;  // float4 groups per thread
-    const int per_thread = gpt << 2;          // elements a thread streamed
-    const int total = nwin * per_thread;      // <= 32 * 8 for T <= 2048
-    const bool rx = excl_step && (sRole[4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE);
-    __syncwarp();
-    for (int i0 = 0; i0 < total; i0 += 32) {
-      int i = i0 + lane;
-      unsigned long long k = 0;
-      if (i < total) {
-        int wi = i / per_thread, e = i % per_thread;
-        int wt = ((key_node(win[wi]) - n0) >> 2) % SCORE_THREADS;  // owning thread
-        int gg = wt + (e >> 2) * SCORE_THREADS;
-        int tt = (gg << 2) + (e & 3);
-        int nn = n0 + tt;
-        if (gg < groups && nn < n1) {
-          float x = sS[p * T + tt];
-          if (rx && restrict_fixed && t.domain[nn] != fixed_domain) x = -INFINITY;
-          if (x != -INFINITY) k = make_key(x, nn);
-        }
-      }
-      cand[i] = k;  // total <= 256 because the host enforces chunk <= 2048
-    }
-    __syncwarp();
-    unsigned long long* out = b.lists + ((size_t)(rolerow_off + p) * b.lc + ch) * KS;
-    int valid = warp_topk(cand, total, K, scr, KS * 8, out);
-    (void)valid;
-    for (int q = K + lane; q < KS; q += 32) out[q] = 0;
-  }
-}
-
-__global__ void __launch_bounds__(SCORE_THREADS)
-k_score_select(TopoDev t, BatchDev b, int items, int PB /* max roles per step in the batch */) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int sHdr[RBGTOPO_STEP_WORDS];
-  __shared__ int sRole[MAXP * 4];
-  __shared__ int sPair[MAXP * MAXQ];
-  const int T = b.chunk;
-  // carve-up (host: score_smem_bytes): sS[PB][T] f32 | sAvail[T] i32 | sBlk[T/32 (+pad)] u32 |
-  //                                    sTmax[PB][256] u64 | sScr[PB][KS*8+KS] u64
-  float* sS = reinterpret_cast<float*>(smem_raw);
-  int* sAvail = reinterpret_cast<int*>(sS + (size_t)PB * T);
-  uint32_t* sBlk = reinterpret_cast<uint32_t*>(sAvail + T);
-  unsigned long long* sTmax =
-      reinterpret_cast<unsigned long long*>(sBlk + (T >> 5) + ((T >> 5) & 1));
-  unsigned long long* sScr = sTmax + (size_t)PB * SCORE_THREADS;
-
-  for (int item = blockIdx.x; item < items; item += gridDim.x) {
-    const int step = item / b.lc, ch = item % b.lc;
-    __syncthreads();  // previous item's smem is dead
-    const int* hdr_g = b.blob + RBGTOPO_HDR_WORDS + (size_t)step * RBGTOPO_STEP_WORDS;
-    if (threadIdx.x < RBGTOPO_STEP_WORDS) sHdr[threadIdx.x] = hdr_g[threadIdx.x];
-    __syncthreads();
-    const int P = sHdr[3], Q = sHdr[5];
-    if (threadIdx.x < P * 4) sRole[threadIdx.x] = b.blob[sHdr[4] + threadIdx.x];
-    for (int i = threadIdx.x; i < P * MAXQ; i += SCORE_THREADS) {
-      int p = i / MAXQ, q = i % MAXQ;
-      sPair[i] = (q < Q) ? b.blob[sHdr[6] + p * Q + q] : 0;
-    }
-    __syncthreads();
-    switch (P) {
-      case 1: score_item<1>(t, b, sHdr, step, ch, sS, sAvail, sBlk, sTmax, sScr, sRole, sPair); break;
-      case 2: score_item<2>(t, b, sHdr, step, ch, sS, sAvail, sBlk, sTmax, sScr, sRole, sPair); break;
-      case 3: score_item<3>(t, b, sHdr, step, ch, sS, sAvail, sBlk, sTmax, sScr, sRole, sPair); break;
-      case 4: score_item<4>(t, b, sHdr, step, ch, sS, sAvail, sBlk, sTmax, sScr, sRole, sPair); break;
-      case 5: score_item<5>(t, b, sHdr, step, ch, sS, sAvail, sBlk, sTmax, sScr, sRole, sPair); break;
-      case 6: score_item<6>(t, b, sHdr, step, ch, sS, sAvail, sBlk, sTmax, sScr, sRole, sPair); break;
-      case 7: score_item<7>(t, b, sHdr, step, ch, sS, sAvail, sBlk, sTmax, sScr, sRole, sPair); break;
-      default: score_item<8>(t, b, sHdr, step, ch, sS, sAvail, sBlk, sTmax, sScr, sRole, sPair); break;
-    }
-  }
-}
-
 }  // namespace rbgtopo

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "score.cuh"
 #include "select.cuh"
 
 using namespace rbgtopo;
@@ -184,8 +185,7 @@ size_t score_smem_bytes(int PB, int KB, int T) {
   size_t b = (size_t)PB * T * 4;                 // sS
   b += (size_t)T * 4;                            // sAvail
   b += (size_t)((T >> 5) + ((T >> 5) & 1)) * 4;  // sBlk (8-byte aligned end)
-  b += (size_t)PB * SCORE_THREADS * 8;           // sTmax
-  b += (size_t)PB * (KS * 8 + KS) * 8;           // sScr (survivors + winners)
+  b += (size_t)PB * SCORE_WARPS * KS * 8;        // sWin (per-warp winners)
   (void)KB;
   return b;
 }

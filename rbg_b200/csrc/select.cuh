@@ -31,8 +31,8 @@ __global__ void __launch_bounds__(SEL_THREADS) k_merge(TopoDev t, BatchDev b) {
   if (step >= b.n_steps) return;
   const int* hdr = b.blob + RBGTOPO_HDR_WORDS + (size_t)step * RBGTOPO_STEP_WORDS;
   const int flags = hdr[1], fixed_domain = hdr[2], P = hdr[3], role_off = hdr[4];
-  const int R = hdr[11], rolerow_off = hdr[13];
-  const int K = min(R, t.n);
+  const int rolerow_off = hdr[13];
+  int kacc = 0;
   int dstar = -1;
   bool dstar_set = false;
   const bool excl_step = (flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
@@ -41,6 +41,8 @@ __global__ void __launch_bounds__(SEL_THREADS) k_merge(TopoDev t, BatchDev b) {
     dstar_set = true;
   }
   for (int p = 0; p < P; ++p) {
+    kacc += b.blob[role_off + 4 * p];
+    const int K = min(kacc, t.n);  // spec §3.5: replicas up to and including role p
     unsigned long long* out = b.merged + (size_t)(rolerow_off + p) * KS;
     unsigned long long prev = ~0ull, top = 0;
     int r = 0;
@@ -76,13 +78,14 @@ __global__ void __launch_bounds__(SEL_THREADS) k_excl_reselect(TopoDev t, BatchD
   if (step >= b.n_steps) return;
   const int* hdr = b.blob + RBGTOPO_HDR_WORDS + (size_t)step * RBGTOPO_STEP_WORDS;
   const int flags = hdr[1], fixed_domain = hdr[2], P = hdr[3], role_off = hdr[4];
-  const int R = hdr[11], rep_off = hdr[12], rolerow_off = hdr[13];
+  const int rep_off = hdr[12], rolerow_off = hdr[13];
   if (!(flags & RBGTOPO_STEP_EXCLUSIVE) || fixed_domain >= 0) return;
-  const int K = min(R, t.n);
   const int dstar = b.dstar[step];
-  int rowbase = 0;
+  int rowbase = 0, kacc = 0;
   for (int p = 0; p < P; ++p) {
     const int count = b.blob[role_off + 4 * p];
+    kacc += count;
+    const int K = min(kacc, t.n);
     const bool rexcl = (b.blob[role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE) != 0;
     unsigned long long* out = b.excl + (size_t)(rolerow_off + p) * KS;
     if (rexcl) {
@@ -127,12 +130,14 @@ __global__ void __launch_bounds__(SEL_THREADS) k_greedy(TopoDev t, BatchDev b) {
   const int flags = hdr[1], fixed_domain = hdr[2], P = hdr[3], role_off = hdr[4];
   const int n_cons = hdr[9], cons_off = hdr[10];
   const int R = hdr[11], rep_off = hdr[12], rolerow_off = hdr[13];
-  const int K = min(R, t.n);
   const bool excl_unknown = (flags & RBGTOPO_STEP_EXCLUSIVE) && fixed_domain < 0;
   const int* con = b.blob + cons_off;
 
   // final list per role row
+  int kacc0 = 0;
   for (int p = 0; p < P; ++p) {
+    kacc0 += b.blob[role_off + 4 * p];
+    const int K = min(kacc0, t.n);
     const bool rexcl = (b.blob[role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE) != 0;
     if (excl_unknown && rexcl) {
       // merge the per-rank restricted lists
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_greedy(TopoDev t, BatchDev b) {
     const int count = b.blob[role_off + 4 * p], demand = b.blob[role_off + 4 * p + 1];
     for (int c = 0; c < count; ++c, ++r) {
       int pick = -1;
-      for (int k = 0; k < K; ++k) {
+      for (int k = 0; k < KS; ++k) {  // the list holds K_p keys, then zeros
         const unsigned long long key = sList[warp][p][k];
         if (key == 0) break;
         const int node = key_node(key);
