@@ -94,7 +94,8 @@ extern "C" {
  *     +2 fixed_domain   -1, or the domain the group already occupies
  *     +3 n_roles  P     1..RBGTOPO_MAX_STEP_ROLES
  *     +4 role_off       word offset of P role records (4 words each:
- *                       count, demand, need, role_flags)
+ *                       count, demand, need, role_flags); MUST be a multiple
+ *                       of 4 (the kernels read a record as one 16-byte vector)
  *     +5 q              number of group roles = pair-matrix columns (0..16)
  *     +6 pair_off       word offset of pair[P][q] (row-major int32)
  *     +7 n_anchors      pods of this group already placed (sparse anchor[q][n])
@@ -126,8 +127,8 @@ typedef struct rbgtopo_config {
   int32_t rank;          /* node-axis shard of this process, 0..world-1        */
   int32_t world;         /* number of node-axis shards (GPUs), >= 1            */
   int32_t slots;         /* concurrent in-flight calls, 0 = default (4)        */
-  int32_t emit_matrix;   /* 1 = materialise the dense (replica x node) matrix
-                            (north_star default); 0 = fused select only        */
+  int32_t emit_matrix;   /* reserved: the dense (replica x node) matrix is
+                            always materialised                                */
   int32_t chunk_nodes;   /* nodes per CTA work item, 0 = default (2048)        */
   int32_t reserved[2];
 } rbgtopo_config;

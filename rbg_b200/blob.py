@@ -52,6 +52,8 @@ class BlobBuilder:
         for i, s in enumerate(self.steps):
             P = len(s.roles)
             Q = len(s.pair[0]) if (len(s.pair) and len(s.pair[0])) else 0
+            while (base + len(body)) & 3:      # role records are read as 16-byte vectors
+                body.append(0)
             role_off = base + len(body)
             for r in s.roles:
                 body.extend(int(x) for x in r)

@@ -43,18 +43,23 @@ struct TopoDev {
   const float* base;          // W·fmin, padded to slab_stride past slab_hi
   const int* dom_ptr;         // nodes grouped by domain (CSR)
   const int* dom_nodes;
+  // slab nodes sorted by key(base[n], n) descending (one radix sort per snapshot):
+  // the "background" order every unpatched row shares
+  const unsigned long long* order;
 };
 
 struct BatchDev {
   const int* blob;
   int n_steps;
-  int lc;           // chunks per step on this rank
+  int lc;           // chunks per step on this rank (work items of k_score_emit)
   int chunk;        // nodes per chunk (multiple of 128)
   int parts;        // ranks (list parts to merge)
   int emit_matrix;
   float* matrix;              // [total R][slab_stride]
-  unsigned long long* lists;  // [rolerows][lc][KS] local per-chunk top-K
-  const unsigned long long* lists_all;  // [parts][rolerows][lc][KS]
+  int* cand;                  // per-step scratch: patched slab nodes (select.cuh)
+  const int* poff;            // [n_steps + 1] scratch offsets (host prefix of the caps)
+  unsigned long long* lists;  // [rolerows][KS] rank-local top-K per role row
+  const unsigned long long* lists_all;  // [parts][rolerows][KS]
   long long part_stride;                // u64 elements between parts
   unsigned long long* merged;  // [rolerows][KS]
   unsigned long long* excl;    // [rolerows][KS] local restricted reselect

@@ -3,10 +3,12 @@
 // timing.  Kernels live in kernels.cuh / select.cuh.  No CPU fallback exists:
 // every entry point needs a CUDA device (sm_100).
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -84,6 +86,9 @@ struct Topology {
   DevBuf<int> row_ptr, col, w, free_, domain, owner, node_owner, dom_ptr, dom_nodes;
   DevBuf<unsigned char> fmin;
   DevBuf<float> base;
+  DevBuf<unsigned long long> okeys, order;  // background order of the slab (score.cuh / select.cuh)
+  DevBuf<unsigned char> sort_tmp;
+  std::vector<int> h_degp1;  // deg(n) + 1, for the patch-list capacity of a step
   DevBuf<int2> tiles;
   int n_tiles = 0;
   std::vector<int> h_domain;  // kept for update_nodes validation
@@ -96,6 +101,8 @@ struct BatchMeta {
   long long words = 0;
   long long scores = 0;      // sum R * N
   long long algo_bytes = 0;
+  long long patch_cap = 0;   // sum of the per-step patch-list capacities
+  std::vector<int> poff;     // [n_steps + 1] patch-list offsets
 };
 
 struct Batch {
@@ -111,6 +118,7 @@ struct Batch {
   DevBuf<int> blob;
   DevBuf<float> matrix;
   DevBuf<unsigned long long> lists, merged, excl;
+  DevBuf<int> cand;  // patched-node scratch of the selection kernels
   DevBuf<int> out;  // assign[total_r] | status[n] | domain[n] | dstar[n]
   PinBuf<int> h_in, h_out;
   ~Batch() {
@@ -140,7 +148,6 @@ struct rbgtopo_ctx {
 namespace {
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
-constexpr size_t kScoreSmemMax = 200 * 1024;  // opt-in dynamic smem of k_score_select
 
 void compute_slab(rbgtopo_ctx* c, int n) {
   const int W = c->cfg.world, r = c->cfg.rank;
@@ -178,16 +185,13 @@ TopoDev topo_dev(const rbgtopo_ctx* c) {
   t.base = T.base.p;
   t.dom_ptr = T.dom_ptr.p;
   t.dom_nodes = T.dom_nodes.p;
+  t.order = T.order.p;
   return t;
 }
 
-size_t score_smem_bytes(int PB, int KB, int T) {
-  size_t b = (size_t)PB * T * 4;                 // sS
-  b += (size_t)T * 4;                            // sAvail
-  b += (size_t)((T >> 5) + ((T >> 5) & 1)) * 4;  // sBlk (8-byte aligned end)
-  b += (size_t)PB * SCORE_WARPS * KS * 8;        // sWin (per-warp winners)
-  (void)KB;
-  return b;
+__global__ void k_order_keys(TopoDev t, unsigned long long* keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < t.slab_hi - t.slab_lo) keys[i] = make_key(t.base[t.slab_lo + i], t.slab_lo + i);
 }
 
 // prep + base kernels on `s`; records base_ms.
@@ -205,6 +209,19 @@ int run_base(rbgtopo_ctx* c, cudaStream_t s) {
   CK(cudaFuncSetAttribute(k_base, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   TopoDev td = topo_dev(c);
   k_base<<<T.n_tiles, BASE_THREADS, smem, s>>>(td, T.tiles.p, staged, fmin_bytes, T.base.p);
+  // background order: slab nodes by key(base, node) descending (library radix sort, once per snapshot)
+  const int slab_len = c->slab_hi - c->slab_lo;
+  if (slab_len > 0) {
+    CK(T.okeys.reserve(slab_len));
+    CK(T.order.reserve(slab_len));
+    td = topo_dev(c);
+    k_order_keys<<<(slab_len + 255) / 256, 256, 0, s>>>(td, T.okeys.p);
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp_bytes, T.okeys.p, T.order.p, slab_len, 0, 64, s));
+    CK(T.sort_tmp.reserve(tmp_bytes + 256));
+    tmp_bytes = T.sort_tmp.cap;
+    CK(cub::DeviceRadixSort::SortKeysDescending(T.sort_tmp.p, tmp_bytes, T.okeys.p, T.order.p, slab_len, 0, 64, s));
+  }
   CK(cudaEventRecord(b, s));
   CK(cudaStreamSynchronize(s));
   CK(cudaGetLastError());
@@ -230,6 +247,7 @@ int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, Batc
   const long long row_w = T.wsum_max + RBGTOPO_SELF_W;
   long long racc = 0, pacc = 0;
   *m = BatchMeta{};
+  m->poff.assign((size_t)ns + 1, 0);
   auto in = [&](long long off, long long cnt) { return off >= 0 && cnt >= 0 && off + cnt <= words; };
   for (int s = 0; s < ns; ++s) {
     const int32_t* st = blob + RBGTOPO_HDR_WORDS + (int64_t)s * RBGTOPO_STEP_WORDS;
@@ -271,6 +289,13 @@ int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, Batc
       if (amax * row_w >= (1LL << 24))
         return fail(RBGTOPO_EINEXACT, "step %d role %d: max score bound %lld >= 2^24", s, p, amax * row_w);
     }
+    if (st[4] & 3) return fail(RBGTOPO_EINVAL, "step %d: role_off must be a multiple of 4 words", s);
+    // patched-node scratch: closed neighbourhoods of the anchors + consumed nodes
+    long long pc = nc;
+    for (int a = 0; a < na; ++a) pc += T.h_degp1[anc[3 * a]];
+    if (m->patch_cap + pc > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "patch lists exceed 2^31 entries");
+    m->patch_cap += pc;
+    m->poff[s + 1] = (int)m->patch_cap;
     racc += R;
     pacc += P;
     m->max_p = std::max(m->max_p, P);
@@ -284,10 +309,11 @@ int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, Batc
   m->words = words;
   const long long slab = c->slab_hi - c->slab_lo;
   m->scores = racc * slab;
-  // bytes the score kernel must move for this rank's slab:
-  // matrix write + per-chunk key lists + blob read + per-snapshot vectors once
-  m->algo_bytes = 4LL * racc * slab * (c->cfg.emit_matrix ? 1 : 0) + 8LL * pacc * c->lc * KS +
-                  4LL * words + 12LL * slab;
+  // bytes k_score_emit must move for this rank's slab: the dense
+  // matrix write + the batch blob read + the per-snapshot base/free vectors once
+  // (they are L2-resident across the steps of a launch).  The sparse corrections
+  // (a few dozen 4-byte reductions per step) are deliberately NOT counted.
+  m->algo_bytes = 4LL * racc * slab + 4LL * words + 8LL * slab;
   return RBGTOPO_OK;
 }
 
@@ -323,11 +349,12 @@ int stage_into(rbgtopo_ctx* c, Batch* b, const int32_t* blob, int64_t words) {
   if (rc) return rc;
   const BatchMeta& m = b->m;
   cudaStream_t s = stream_of(c, b);
-  CK(b->blob.reserve((size_t)words));
-  CK(b->h_in.reserve((size_t)words));
-  const bool need_matrix = c->cfg.emit_matrix || m.any_excl_unknown;
-  if (need_matrix) CK(b->matrix.reserve((size_t)std::max(1, m.total_r) * c->slab_stride));
-  CK(b->lists.reserve((size_t)std::max(1, m.total_p) * c->lc * KS));
+  const size_t in_words = (size_t)words + (size_t)m.n_steps + 1;  // blob | poff
+  CK(b->blob.reserve(in_words));
+  CK(b->h_in.reserve(in_words));
+  CK(b->matrix.reserve((size_t)std::max(1, m.total_r) * c->slab_stride));
+  CK(b->cand.reserve((size_t)m.patch_cap + 1));
+  CK(b->lists.reserve((size_t)std::max(1, m.total_p) * KS));
   CK(b->merged.reserve((size_t)std::max(1, m.total_p) * KS));
   CK(b->excl.reserve((size_t)std::max(1, m.total_p) * KS));
   const size_t out_n = (size_t)m.total_r + 3 * (size_t)m.n_steps + 4;
@@ -335,7 +362,8 @@ int stage_into(rbgtopo_ctx* c, Batch* b, const int32_t* blob, int64_t words) {
   CK(b->h_out.reserve(out_n));
   CK(cudaEventRecord(b->ev[0], s));
   memcpy(b->h_in.p, blob, (size_t)words * 4);
-  CK(cudaMemcpyAsync(b->blob.p, b->h_in.p, (size_t)words * 4, cudaMemcpyHostToDevice, s));
+  memcpy(b->h_in.p + words, m.poff.data(), ((size_t)m.n_steps + 1) * 4);
+  CK(cudaMemcpyAsync(b->blob.p, b->h_in.p, in_words * 4, cudaMemcpyHostToDevice, s));
   CK(cudaEventRecord(b->ev[1], s));
   b->staged = true;
   b->ran = false;
@@ -349,8 +377,13 @@ BatchDev batch_dev(rbgtopo_ctx* c, Batch* b) {
   d.lc = c->lc;
   d.chunk = c->chunk;
   d.parts = 1;
-  d.emit_matrix = c->cfg.emit_matrix;
+  {
+    d.emit_matrix = 1;
+
+  }
   d.matrix = b->matrix.p;
+  d.cand = b->cand.p;
+  d.poff = b->blob.p + b->m.words;
   d.lists = b->lists.p;
   d.lists_all = b->lists.p;
   d.part_stride = 0;
@@ -369,25 +402,20 @@ int launch_score(rbgtopo_ctx* c, Batch* b, cudaStream_t s) {
   const BatchMeta& m = b->m;
   if (m.n_steps == 0) return RBGTOPO_OK;
   const int items = m.n_steps * c->lc;
-  const size_t smem = score_smem_bytes(m.max_p, m.max_k, c->chunk);
-  if (smem > kScoreSmemMax) return fail(RBGTOPO_ELIMIT, "score kernel needs %zu B of shared memory", smem);
   int occ = 1;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_select, SCORE_THREADS, smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_emit, SCORE_THREADS, 0));
   occ = std::max(1, occ);
   const int grid = std::min(items, c->sm_count * occ);
-  k_score_select<<<grid, SCORE_THREADS, smem, s>>>(topo_dev(c), batch_dev(c, b), items, m.max_p);
+  k_score_emit<<<grid, SCORE_THREADS, 0, s>>>(topo_dev(c), batch_dev(c, b), items);
   return RBGTOPO_OK;
 }
 
-int launch_select(rbgtopo_ctx* c, Batch* b, cudaStream_t s, const BatchDev& d, bool merge,
-                  bool reselect, bool greedy, int* launches) {
+// world == 1: one fused kernel (select + exclusive domain + greedy), one CTA per step
+int launch_select_assign(rbgtopo_ctx* c, Batch* b, cudaStream_t s, const BatchDev& d, int* launches) {
   const int ns = b->m.n_steps;
   if (ns == 0) return RBGTOPO_OK;
-  const int grid = (ns + SEL_WARPS - 1) / SEL_WARPS;
-  TopoDev td = topo_dev(c);
-  if (merge) { k_merge<<<grid, SEL_THREADS, 0, s>>>(td, d); ++*launches; }
-  if (reselect && b->m.any_excl_unknown) { k_excl_reselect<<<grid, SEL_THREADS, 0, s>>>(td, d); ++*launches; }
-  if (greedy) { k_greedy<<<grid, SEL_THREADS, 0, s>>>(td, d); ++*launches; }
+  k_select_assign<<<ns, 32 * b->m.max_p, 0, s>>>(topo_dev(c), d);
+  ++*launches;
   return RBGTOPO_OK;
 }
 
@@ -421,7 +449,7 @@ int run_batch(rbgtopo_ctx* c, Batch* b, int iters) {
     if (rc) return rc;
     ++launches;
     if (timed) CK(cudaEventRecord(b->it_ev[e0 + 1], s));
-    rc = launch_select(c, b, s, d, true, true, true, &launches);
+    rc = launch_select_assign(c, b, s, d, &launches);
     if (rc) return rc;
     if (timed) {
       CK(cudaEventRecord(b->it_ev[e0 + 2], s));
@@ -528,9 +556,8 @@ int32_t rbgtopo_create(const rbgtopo_config* cfg, rbgtopo_ctx** out) {
   CK(cudaSetDevice(cfg->device));
   auto c = std::make_unique<rbgtopo_ctx>();
   c->cfg = *cfg;
-  if (c->cfg.emit_matrix != 0) c->cfg.emit_matrix = 1;
+  c->cfg.emit_matrix = 1;  // the dense matrix is always materialised (selection reads patched scores back)
   c->sm_count = prop.multiProcessorCount;
-  CK(cudaFuncSetAttribute(k_score_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScoreSmemMax));
   *out = c.release();
   return RBGTOPO_OK;
 }
@@ -633,6 +660,8 @@ int32_t rbgtopo_set_topology(rbgtopo_ctx* c, int32_t n, int64_t e, const int32_t
   T.wsum_max = wsum_max;
   T.generation = generation;
   T.h_domain.assign(domain, domain + n);
+  T.h_degp1.resize(n);
+  for (int i = 0; i < n; ++i) T.h_degp1[i] = row_ptr[i + 1] - row_ptr[i] + 1;
   int rc = run_base(c, c->use_ext_stream ? c->ext_stream : (cudaStream_t)0);
   if (rc) return rc;
   T.valid = true;
@@ -776,6 +805,7 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
       st[1] = r.rec[1];
       st[2] = (r.rec[1] & RBGTOPO_STEP_EXCLUSIVE) ? r.fixed_domain : -1;
       st[3] = P;
+      while (blob.size() & 3) blob.push_back(0);  // role records are read as 16-byte vectors
       st[4] = (int32_t)blob.size();
       for (int p = 0; p < P; ++p) {
         const int ri = r.w_role[p];
@@ -930,7 +960,6 @@ int32_t rbgtopo_read_scores(rbgtopo_ctx* c, int32_t handle, int32_t row, float* 
   if (!c || !out) return fail(RBGTOPO_EINVAL, "null argument");
   Batch* b = batch_of(c, handle);
   if (!b || !b->ran) return fail(RBGTOPO_EINVAL, "handle %d has no results", handle);
-  if (!c->cfg.emit_matrix) return fail(RBGTOPO_EINVAL, "ctx was created with emit_matrix = 0");
   const int slab = c->slab_hi - c->slab_lo;
   if (row < 0 || row >= b->m.total_r || out_len < slab) return fail(RBGTOPO_EINVAL, "row/out_len");
   CK(cudaSetDevice(c->cfg.device));
@@ -977,12 +1006,13 @@ int32_t rbgtopo_shard_score(rbgtopo_ctx* c, int32_t handle, void** keys_dev, int
   if (rc) return rc;
   if (timed) CK(cudaEventRecord(b->it_ev[e0 + 1], s));
   b->shard_timed = timed;
-  b->pend_launches += 1;
+  b->pend_launches += 2;
+  if (b->m.n_steps) k_select<<<b->m.n_steps, 32 * b->m.max_p, 0, s>>>(topo_dev(c), batch_dev(c, b), 0);
   CK(cudaGetLastError());
   *keys_dev = b->lists.p;
-  *keys_bytes = (int64_t)std::max(1, b->m.total_p) * c->lc * KS * 8;
+  *keys_bytes = (int64_t)std::max(1, b->m.total_p) * KS * 8;
   std::lock_guard<std::mutex> g(c->stat_mu);
-  c->launches += 1;
+  c->launches += 2;
   return RBGTOPO_OK;
 }
 
@@ -997,10 +1027,17 @@ int32_t rbgtopo_shard_merge(rbgtopo_ctx* c, int32_t handle, const void* keys_all
   BatchDev d = batch_dev(c, b);
   d.parts = c->cfg.world;
   d.lists_all = static_cast<const unsigned long long*>(keys_all);
-  d.part_stride = (long long)std::max(1, b->m.total_p) * c->lc * KS;
+  d.part_stride = (long long)std::max(1, b->m.total_p) * KS;
   int launches = 0;
-  int rc = launch_select(c, b, s, d, true, true, false, &launches);
-  if (rc) return rc;
+  if (b->m.n_steps) {
+    const int grid = (b->m.n_steps + SEL_WARPS - 1) / SEL_WARPS;
+    k_merge<<<grid, SEL_THREADS, 0, s>>>(topo_dev(c), d);
+    ++launches;
+    if (b->m.any_excl_unknown) {
+      k_select<<<b->m.n_steps, 32 * b->m.max_p, 0, s>>>(topo_dev(c), d, 1);
+      ++launches;
+    }
+  }
   CK(cudaGetLastError());
   *need_pass2 = b->m.any_excl_unknown ? 1 : 0;
   *keys2_dev = b->excl.p;
@@ -1026,8 +1063,11 @@ int32_t rbgtopo_shard_assign(rbgtopo_ctx* c, int32_t handle, const void* keys2_a
     d.excl_part_stride = (long long)std::max(1, b->m.total_p) * KS;
   }
   int launches = 0;
-  int rc = launch_select(c, b, s, d, false, false, true, &launches);
-  if (rc) return rc;
+  if (b->m.n_steps) {
+    const int grid = (b->m.n_steps + SEL_WARPS - 1) / SEL_WARPS;
+    k_greedy<<<grid, SEL_THREADS, 0, s>>>(topo_dev(c), d);
+    ++launches;
+  }
   if (b->shard_timed) {
     CK(cudaEventRecord(b->it_ev[3 * b->passes + 2], s));
     b->passes += 1;

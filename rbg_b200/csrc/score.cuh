@@ -1,240 +1,148 @@
-// score.cuh — k_score_select: the dominant kernel of the path.
+// score.cuh — k_score_emit: the dominant kernel of the path.
 //
-// One work item = (step, chunk of `chunk` <= 2048 nodes of this rank's slab);
-// a persistent grid of 256-thread CTAs strides over the items.
-//   1. load the step record, zero the per-role delta rows in shared memory, load
-//      capacity and (exclusive steps) the domain-ownership mask
-//   2. scatter the step's anchor pods into the deltas: one warp walks CSR row m
-//      (coalesced int32 loads) and adds pair*c*w to the delta of every neighbour
-//      inside the chunk (+ the self term); consumed capacity is subtracted
-//   3. per role row: S = need*base + delta (one FFMA per score, exact), mask
-//      infeasible -> -inf, write the row once per replica of the role with
-//      128-bit streaming stores.  Each thread keeps its <= 8 scores of the role
-//      in registers as 32-bit local keys  (int(S) << 3 | 7 - e)  so that
-//   4. every warp selects the exact top-K of its 256 scores with K REDUX rounds
-//      (warp max of the lane maxima; the winning lane rescans its own registers
-//      for its next best) — no shared memory, no block barrier.
-//   5. after the last role one barrier; warp p merges the 8 per-warp lists of
-//      role p (<= 8*K keys) and writes the chunk's top-K keys to global memory.
-// K of role p = number of replicas of the step up to and including role p
-// (spec §3.5: earlier replicas can exhaust at most that many - 1 nodes).
+// Emits the dense (replica x node) score matrix as a pure HBM write stream.
+// One work item = (step, chunk of `chunk` <= 2048 nodes of this rank's slab); a
+// persistent grid of 256-thread CTAs takes contiguous item ranges, so the chunks
+// of a step run back to back on one SM (its header, roles, anchors and the
+// anchors' CSR rows are L1 hits after the first chunk).  No shared memory.
+//   1. background: every role row is  S = need*base[n]  where the node is feasible
+//      (free >= demand, and for exclusive roles the domain is unowned or ours),
+//      else -inf; written once per replica of the role with 128-bit streaming
+//      stores.  base/free are per-snapshot vectors shared by all steps (L1/L2).
+//   2. only for steps with anchor pods / consumed capacity, after one block
+//      barrier: a warp walks the CSR row of anchor m (coalesced int32 loads) and
+//      adds pair*c*w onto the just-written, L2-hot scores of the neighbours inside
+//      the chunk with fire-and-forget red.global.add.f32 (+ the self term); nodes
+//      whose consumed capacity makes them infeasible are overwritten with -inf.
+//      All addends are exact integers and -inf absorbs adds, so the result is
+//      bit-identical to the oracle's sequential fp32 accumulation in any order.
+// Selection never touches this kernel's data path except for reading back the
+// few patched scores (select.cuh).
 #pragma once
 #include "kernels.cuh"
 
 namespace rbgtopo {
 
 constexpr int GPT = 2;  // float4 groups per thread: chunk <= 256 * 4 * GPT = 2048
-constexpr int EPT = 4 * GPT;
 
-// host mirror: rbgtopo.cu score_smem_bytes()
-//   sD[PB][T] f32 | sAvail[T] i32 | sBlk[T/32 (+pad to 8 B)] u32 | sWin[PB][8][KS] u64
-__global__ void __launch_bounds__(SCORE_THREADS, 4)
-k_score_select(TopoDev t, BatchDev b, int items, int PB /* max roles per step in the batch */) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int sHdr[RBGTOPO_STEP_WORDS];
-  __shared__ int sRole[MAXP * 4];
-  __shared__ int sPair[MAXP * MAXQ];
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(SCORE_THREADS, 6)
+k_score_emit(TopoDev t, BatchDev b, int items) {
   const int T = b.chunk;
-  float* sD = reinterpret_cast<float*>(smem_raw);
-  int* sAvail = reinterpret_cast<int*>(sD + (size_t)PB * T);
-  uint32_t* sBlk = reinterpret_cast<uint32_t*>(sAvail + T);
-  unsigned long long* sWin =
-      reinterpret_cast<unsigned long long*>(sBlk + (T >> 5) + ((T >> 5) & 1));
-
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int groups = T >> 2;
+  const int* __restrict__ blob = b.blob;
+  const size_t stride = (size_t)t.slab_stride;
 
-  for (int item = blockIdx.x; item < items; item += gridDim.x) {
-    const int step = item / b.lc, ch = item - step * b.lc;
+  const int per = (items + gridDim.x - 1) / gridDim.x;
+  int item = blockIdx.x * per;
+  const int item_end = min(items, item + per);
+  if (item >= item_end) return;
+  int step = item / b.lc, ch = item - step * b.lc;
+  for (; item < item_end; ++item) {
     const int n0 = t.slab_lo + ch * T;
     const int n1 = min(n0 + T, t.slab_hi);
-    __syncthreads();  // previous item's shared memory is dead
-    if (tid < RBGTOPO_STEP_WORDS)
-      sHdr[tid] = b.blob[RBGTOPO_HDR_WORDS + (size_t)step * RBGTOPO_STEP_WORDS + tid];
-    __syncthreads();
-    const int gid = sHdr[0], flags = sHdr[1], fixed_domain = sHdr[2], P = sHdr[3];
-    const int Q = sHdr[5];
-    const int n_anchors = sHdr[7], n_cons = sHdr[9];
-    const int rep_off = sHdr[12], rolerow_off = sHdr[13];
-    const bool excl_step = (flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
+    const int* __restrict__ hdr = blob + RBGTOPO_HDR_WORDS + (size_t)step * RBGTOPO_STEP_WORDS;
+    const int4 h0 = __ldg(reinterpret_cast<const int4*>(hdr));      // gid flags fixed P
+    const int4 h1 = __ldg(reinterpret_cast<const int4*>(hdr) + 1);  // role_off Q pair_off n_anchors
+    const int4 h2 = __ldg(reinterpret_cast<const int4*>(hdr) + 2);  // anchor_off n_cons cons_off R
+    const int4 h3 = __ldg(reinterpret_cast<const int4*>(hdr) + 3);  // rep_off rolerow_off - -
+    const int gid = h0.x, P = h0.w;
+    const bool excl_step = (h0.y & RBGTOPO_STEP_EXCLUSIVE) != 0;
+    const int4* __restrict__ roles = reinterpret_cast<const int4*>(blob + h1.x);  // 16-byte aligned (validated)
+    float* const mrow0 = b.matrix + (size_t)h3.x * stride + (n0 - t.slab_lo);
 
-    // ---- 1. step parameters + init (independent, one barrier)
-    if (tid < P * 4) sRole[tid] = b.blob[sHdr[4] + tid];
-    for (int i = tid; i < P * MAXQ; i += SCORE_THREADS) {
-      const int p = i / MAXQ, q = i - p * MAXQ;
-      sPair[i] = (q < Q) ? b.blob[sHdr[6] + p * Q + q] : 0;
-    }
-    {
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int i = tid; i < P * groups; i += SCORE_THREADS) reinterpret_cast<float4*>(sD)[i] = z;
-      // P * groups float4 == the first P rows of sD (rows are T floats = groups float4)
-    }
-    for (int i = tid; i < T; i += SCORE_THREADS) {
-      const int n = n0 + i;
-      int av = -1;
-      bool blk = false;
-      if (n < n1) {
-        av = t.free_[n];
-        if (excl_step) {
-          const int o = t.node_owner[n];
-          blk = !(o == -1 || o == gid);
-        }
-      }
-      sAvail[i] = av;
-      const uint32_t bm = __ballot_sync(FULL, blk);
-      if (lane == 0) sBlk[i >> 5] = bm;
-    }
-    __syncthreads();
-
-    // ---- 2. anchors (one warp per anchor pod) and consumed capacity
-    {
-      const int* anc = b.blob + sHdr[8];
-      for (int a = warp; a < n_anchors; a += SCORE_WARPS) {
-        const int m = anc[3 * a], q = anc[3 * a + 1], c = anc[3 * a + 2];
-        const int rb = t.row_ptr[m], re = t.row_ptr[m + 1];
-        for (int j = rb + lane; j < re; j += 32) {
-          const int nn = t.col[j];
-          if (nn >= n0 && nn < n1) {
-            const int wv = t.w[j] * c;
-            for (int p = 0; p < P; ++p) {
-              const int coef = sPair[p * MAXQ + q];
-              if (coef) atomicAdd(&sD[p * T + (nn - n0)], (float)(coef * wv));
-            }
-          }
-        }
-        if (lane == 0 && m >= n0 && m < n1) {
-          for (int p = 0; p < P; ++p) {
-            const int coef = sPair[p * MAXQ + q] * c;
-            if (coef) atomicAdd(&sD[p * T + (m - n0)], (float)(coef * RBGTOPO_SELF_W));
-          }
-        }
-      }
-      const int* con = b.blob + sHdr[10];
-      for (int c = tid; c < n_cons; c += SCORE_THREADS) {
-        const int m = con[2 * c];
-        if (m >= n0 && m < n1) atomicSub(&sAvail[m - n0], con[2 * c + 1]);
-      }
-    }
-    __syncthreads();
-
-    // ---- 3+4. per role: stream the row, select per warp
-    const bool write_rows = b.emit_matrix || (excl_step && fixed_domain < 0);
-    const bool restrict_fixed = excl_step && fixed_domain >= 0;
-    // thread-invariant per-group data, loaded once for all roles
-    float4 base4[GPT];
-    int4 av4[GPT];
-    uint32_t okbits[GPT];  // bit i: lane valid; bit 4+i: blocked by ownership; bit 8+i: in fixed domain
+    // ---- 1. background rows
 #pragma unroll
     for (int j = 0; j < GPT; ++j) {
       const int g = tid + j * SCORE_THREADS;
       const int n = n0 + (g << 2);
-      okbits[j] = 0;
-      base4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      av4[j] = make_int4(-1, -1, -1, -1);
       if (g < groups && n < n1) {
-        base4[j] = *reinterpret_cast<const float4*>(t.base + n);
-        av4[j] = *reinterpret_cast<const int4*>(sAvail + (g << 2));
-        const uint32_t blk = (sBlk[g >> 3] >> ((g & 7) << 2)) & 0xFu;
-        uint32_t valid = 0, dom = 0xFu;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) valid |= (n + i < n1) ? (1u << i) : 0u;
-        if (restrict_fixed) {
-          dom = 0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (n + i < n1 && t.domain[n + i] == fixed_domain) dom |= 1u << i;
+        const float4 base4 = __ldg(reinterpret_cast<const float4*>(t.base + n));
+        const int4 av = __ldg(reinterpret_cast<const int4*>(t.free_ + n));  // padded past n: safe
+        uint32_t okm = 0xFu;
+        if (n + 4 > n1) okm = (1u << (n1 - n)) - 1u;  // only in the slab's last group
+        uint32_t blk = 0;
+        if (excl_step) {
+          const int4 ow = __ldg(reinterpret_cast<const int4*>(t.node_owner + n));
+          blk = (!(ow.x == -1 || ow.x == gid) ? 1u : 0u) | (!(ow.y == -1 || ow.y == gid) ? 2u : 0u) |
+                (!(ow.z == -1 || ow.z == gid) ? 4u : 0u) | (!(ow.w == -1 || ow.w == gid) ? 8u : 0u);
         }
-        okbits[j] = valid | (blk << 4) | (dom << 8);
+        float* rowp = mrow0 + (g << 2);
+        for (int p = 0; p < P; ++p) {
+          const int4 role = __ldg(roles + p);  // count demand need flags
+          const float need = (float)role.z;
+          const uint32_t bad = (excl_step && (role.w & RBGTOPO_ROLE_EXCLUSIVE)) ? blk : 0u;
+          const uint32_t good = okm & ~bad;
+          float4 o4;
+          o4.x = (av.x >= role.y && (good & 1u)) ? need * base4.x : -INFINITY;
+          o4.y = (av.y >= role.y && (good & 2u)) ? need * base4.y : -INFINITY;
+          o4.z = (av.z >= role.y && (good & 4u)) ? need * base4.z : -INFINITY;
+          o4.w = (av.w >= role.y && (good & 8u)) ? need * base4.w : -INFINITY;
+          for (int c = 0; c < role.x; ++c) {
+            st_stream_f4(rowp, o4);
+            rowp += stride;
+          }
+        }
       }
     }
 
-    int kacc = 0, rowbase = 0;
-    for (int p = 0; p < P; ++p) {
-      const int count = sRole[4 * p], demand = sRole[4 * p + 1];
-      const float need = (float)sRole[4 * p + 2];
-      const bool rexcl = excl_step && (sRole[4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE);
-      kacc += count;
-      const int Kp = min(kacc, t.n);
-      int k32[EPT];
-#pragma unroll
-      for (int j = 0; j < GPT; ++j) {
-        const int g = tid + j * SCORE_THREADS;
-        const uint32_t ok = okbits[j];
-        float v[4];
-        if (ok & 0xFu) {
-          const float4 d4 = *reinterpret_cast<const float4*>(sD + p * T + (g << 2));
-          const float bb[4] = {base4[j].x, base4[j].y, base4[j].z, base4[j].w};
-          const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-          const int av[4] = {av4[j].x, av4[j].y, av4[j].z, av4[j].w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float x = fmaf(need, bb[i], dd[i]);
-            const bool feas = (av[i] >= demand) && ((ok >> i) & 1u) && !(rexcl && ((ok >> (4 + i)) & 1u));
-            v[i] = feas ? x : -INFINITY;
-            const bool sel = feas && !(rexcl && !((ok >> (8 + i)) & 1u));
-            k32[j * 4 + i] = sel ? ((__float2int_rn(x) << 3) | (7 - (j * 4 + i))) : -1;
+    // ---- 2. sparse corrections (steps with anchors / consumed capacity only)
+    if ((h1.w | h2.y) != 0) {
+      __threadfence();
+      __syncthreads();  // the chunk's background scores are written
+      const int* __restrict__ con = blob + h2.z;
+      for (int c = tid; c < h2.y; c += SCORE_THREADS) {  // consumed capacity -> maybe infeasible
+        const int m = __ldg(con + 2 * c);
+        if (m >= n0 && m < n1) {
+          int amt = 0;
+          for (int k = 0; k < h2.y; ++k)
+            if (__ldg(con + 2 * k) == m) amt += __ldg(con + 2 * k + 1);  // duplicates add up
+          const int avail = __ldg(t.free_ + m) - amt;
+          float* rowp = mrow0 + (m - n0);
+          for (int p = 0; p < P; ++p) {
+            const int4 role = __ldg(roles + p);
+            if (avail < role.y)
+              for (int k = 0; k < role.x; ++k) rowp[(size_t)k * stride] = -INFINITY;
+            rowp += (size_t)role.x * stride;
           }
-          if (write_rows) {
-            const float4 o4 = make_float4(v[0], v[1], v[2], v[3]);
-            float* rowp = b.matrix + (size_t)(rep_off + rowbase) * t.slab_stride + (n0 - t.slab_lo) + (g << 2);
-            for (int c = 0; c < count; ++c) st_stream_f4(rowp + (size_t)c * t.slab_stride, o4);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) k32[j * 4 + i] = -1;
         }
       }
-      rowbase += count;
-
-      // ---- per-warp exact top-Kp from registers
-      int cur = k32[0];
-#pragma unroll
-      for (int e = 1; e < EPT; ++e) cur = max(cur, k32[e]);
-      unsigned long long* win = sWin + ((size_t)p * SCORE_WARPS + warp) * KS;
-      int r = 0;
-      for (; r < Kp; ++r) {
-        unsigned long long key = 0;
-        if (cur >= 0) {
-          const int e = 7 - (cur & 7);
-          const int node = n0 + ((tid + (e >> 2) * SCORE_THREADS) << 2) + (e & 3);
-          key = make_key((float)(cur >> 3), node);
-        }
-        const unsigned long long m = warp_max_u64(key);
-        if (m == 0) break;
-        if (lane == 0) win[r] = m;
-        if (key == m) {  // this lane won: its next best is its largest local key below cur
-          int nxt = -1;
-#pragma unroll
-          for (int e = 0; e < EPT; ++e) nxt = (k32[e] < cur) ? max(nxt, k32[e]) : nxt;
-          cur = nxt;
+      const int* __restrict__ anc = blob + h2.x;
+      const int Q = h1.y;
+      for (int a = warp; a < h1.w; a += SCORE_WARPS) {  // one warp per anchor pod
+        const int m = __ldg(anc + 3 * a), q = __ldg(anc + 3 * a + 1), c = __ldg(anc + 3 * a + 2);
+        const int rb = __ldg(t.row_ptr + m), re = __ldg(t.row_ptr + m + 1);
+        for (int j = rb + lane; j <= re; j += 32) {  // j == re stands for the self term
+          int nn, wv;
+          if (j < re) {
+            nn = __ldg(t.col + j);
+            wv = __ldg(t.w + j) * c;
+          } else {
+            nn = m;
+            wv = RBGTOPO_SELF_W * c;
+          }
+          if (nn >= n0 && nn < n1) {
+            float* rowp = mrow0 + (nn - n0);
+            for (int p = 0; p < P; ++p) {
+              const int count = __ldg(blob + h1.x + 4 * p);
+              const int coef = __ldg(blob + h1.z + p * Q + q);
+              if (coef) {
+                const float add = (float)(coef * wv);
+                for (int k = 0; k < count; ++k) red_add_f32(rowp + (size_t)k * stride, add);
+              }
+              rowp += (size_t)count * stride;
+            }
+          }
         }
       }
-      for (int q = r + lane; q < Kp; q += 32) win[q] = 0;
     }
-    __syncthreads();
-
-    // ---- 5. warp p merges the 8 per-warp lists of role p
-    if (warp < P) {
-      const int p = warp;
-      int kp = 0;
-      for (int q = 0; q <= p; ++q) kp += sRole[4 * q];
-      kp = min(kp, t.n);
-      const unsigned long long* src = sWin + (size_t)p * SCORE_WARPS * KS;
-      unsigned long long* out = b.lists + ((size_t)(rolerow_off + p) * b.lc + ch) * KS;
-      unsigned long long prev = ~0ull;
-      int r = 0;
-      for (; r < kp; ++r) {
-        unsigned long long best = 0;
-        for (int i = lane; i < SCORE_WARPS * kp; i += 32) {
-          const unsigned long long k = src[(i / kp) * KS + (i % kp)];
-          if (k < prev && k > best) best = k;
-        }
-        best = warp_max_u64(best);
-        if (best == 0) break;
-        if (lane == 0) out[r] = best;
-        prev = best;
-      }
-      for (int q = r + lane; q < KS; q += 32) out[q] = 0;
+    if (++ch == b.lc) {
+      ch = 0;
+      ++step;
     }
   }
 }

@@ -1,184 +1,189 @@
-// select.cuh — merge of per-chunk / per-rank top-K lists, exclusive-domain
-// reselect and the deterministic greedy assignment.
-// One warp per step; steps are independent (snapshot semantics, spec §3.7).
+// select.cuh — per-role top-K selection, exclusive-domain handling and the
+// deterministic greedy assignment.
+//
+// A role row is  need*base[n]  except at the step's few PATCHED nodes (closed
+// neighbourhoods of its anchor pods, nodes with consumed capacity), so its top-K
+// is the merge of
+//   (a) the top-K of the patched nodes, whose exact scores are read back from the
+//       dense matrix (a few dozen 4-byte reads, L2), and
+//   (b) the first K feasible, unpatched nodes of the per-snapshot background
+//       order (slab nodes sorted by key(base[n], n) descending; for need == 0
+//       every background score is 0 and the order is simply node ascending).
+// One warp per role row; ballots pick the accepted lanes in order, REDUX finds
+// the patch maxima.  Steps are independent (snapshot semantics, spec §3.7).
 #pragma once
 #include "kernels.cuh"
 
 namespace rbgtopo {
 
-constexpr int SEL_WARPS = 4;
-constexpr int SEL_THREADS = SEL_WARPS * 32;
+constexpr int DOM_ANY = -2;   // no domain restriction
+constexpr int DOM_NONE = -1;  // exclusive step without any feasible domain: empty list
 
-// Largest key strictly below `prev` among count lists of K keys each
-// (lists[i*stride + k]); every lane scans a strided share.
-__device__ __forceinline__ unsigned long long next_below(const unsigned long long* base,
-                                                         int nlists, long long stride, int K,
-                                                         unsigned long long prev) {
+struct StepHdr {
+  int gid, flags, fixed_domain, P, role_off, n_anchors, anchor_off, n_cons, cons_off, R, rep_off, rolerow_off;
+};
+__device__ __forceinline__ StepHdr load_hdr(const BatchDev& b, int step) {
+  const int* hdr = b.blob + RBGTOPO_HDR_WORDS + (size_t)step * RBGTOPO_STEP_WORDS;
+  StepHdr h;
+  h.gid = hdr[0]; h.flags = hdr[1]; h.fixed_domain = hdr[2]; h.P = hdr[3]; h.role_off = hdr[4];
+  h.n_anchors = hdr[7]; h.anchor_off = hdr[8];
+  h.n_cons = hdr[9]; h.cons_off = hdr[10]; h.R = hdr[11]; h.rep_off = hdr[12]; h.rolerow_off = hdr[13];
+  return h;
+}
+// K of role row p = replicas of the step up to and including role p (spec §3.5)
+__device__ __forceinline__ int role_k(const BatchDev& b, const StepHdr& h, int p, int n) {
+  int k = 0;
+  for (int q = 0; q <= p; ++q) k += b.blob[h.role_off + 4 * q];
+  return min(k, n);
+}
+__device__ __forceinline__ int role_rowbase(const BatchDev& b, const StepHdr& h, int p) {
+  int k = 0;
+  for (int q = 0; q < p; ++q) k += b.blob[h.role_off + 4 * q];
+  return k;
+}
+
+// The step's patched slab nodes (duplicates allowed) into cand[]; *sCnt counts them.
+// Called by every warp of the CTA; the caller zeroes *sCnt before and syncs after.
+__device__ __forceinline__ void build_candidates(const TopoDev& t, const BatchDev& b, const StepHdr& h,
+                                                 int* cand, int* sCnt) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int* anc = b.blob + h.anchor_off;
+  for (int a = warp; a < h.n_anchors; a += nwarps) {
+    const int m = anc[3 * a];
+    const int rb = t.row_ptr[m], re = t.row_ptr[m + 1];
+    for (int j0 = rb; j0 <= re; j0 += 32) {  // j == re stands for the anchor's own node
+      const int j = j0 + lane;
+      int nn = -1;
+      if (j < re) nn = t.col[j];
+      else if (j == re) nn = m;
+      const bool keep = nn >= t.slab_lo && nn < t.slab_hi;
+      const uint32_t msk = __ballot_sync(FULL, keep);
+      int base = 0;
+      if (lane == 0 && msk) base = atomicAdd(sCnt, __popc(msk));
+      base = __shfl_sync(FULL, base, 0);
+      if (keep) cand[base + __popc(msk & ((1u << lane) - 1u))] = nn;
+    }
+  }
+  const int* con = b.blob + h.cons_off;
+  for (int c = threadIdx.x; c < h.n_cons; c += blockDim.x) {
+    const int m = con[2 * c];
+    if (m >= t.slab_lo && m < t.slab_hi) cand[atomicAdd(sCnt, 1)] = m;
+  }
+}
+
+// Rank-local top-K of role row p of `step` into out[0..KS) (keys descending, then
+// zeros).  sAcc / sPat: per-warp shared scratch of KS keys each.  All 32 lanes call.
+__device__ __forceinline__ void select_role(const TopoDev& t, const BatchDev& b, const StepHdr& h, int p,
+                                            int K, int dom, const int* cand, int cnt,
+                                            unsigned long long* sAcc, unsigned long long* sPat,
+                                            unsigned long long* out) {
   const int lane = threadIdx.x & 31;
-  unsigned long long best = 0;
-  const int total = nlists * K;
-  for (int i = lane; i < total; i += 32) {
-    unsigned long long k = base[(long long)(i / K) * stride + (i % K)];
-    if (k < prev && k > best) best = k;
+  if (dom == DOM_NONE || K <= 0) {
+    out[lane] = 0;
+    return;
   }
-  return warp_max_u64(best);
-}
+  const int demand = b.blob[h.role_off + 4 * p + 1];
+  const int need_i = b.blob[h.role_off + 4 * p + 2];
+  const bool rexcl = (h.flags & RBGTOPO_STEP_EXCLUSIVE) && (b.blob[h.role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE);
+  const float* __restrict__ row =
+      b.matrix + (size_t)(h.rep_off + role_rowbase(b, h, p)) * t.slab_stride - t.slab_lo;  // row[node]
 
-// ---- B1: merged[rolerow][KS] = top-K over parts x lc chunk lists; D* ----------
-__global__ void __launch_bounds__(SEL_THREADS) k_merge(TopoDev t, BatchDev b) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int step = blockIdx.x * SEL_WARPS + warp;
-  if (step >= b.n_steps) return;
-  const int* hdr = b.blob + RBGTOPO_HDR_WORDS + (size_t)step * RBGTOPO_STEP_WORDS;
-  const int flags = hdr[1], fixed_domain = hdr[2], P = hdr[3], role_off = hdr[4];
-  const int rolerow_off = hdr[13];
-  int kacc = 0;
-  int dstar = -1;
-  bool dstar_set = false;
-  const bool excl_step = (flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
-  if (excl_step && fixed_domain >= 0) {
-    dstar = fixed_domain;
-    dstar_set = true;
-  }
-  for (int p = 0; p < P; ++p) {
-    kacc += b.blob[role_off + 4 * p];
-    const int K = min(kacc, t.n);  // spec §3.5: replicas up to and including role p
-    unsigned long long* out = b.merged + (size_t)(rolerow_off + p) * KS;
-    unsigned long long prev = ~0ull, top = 0;
-    int r = 0;
-    for (; r < K; ++r) {
+  // ---- (a) top-K of the patched nodes (exact scores from the matrix)
+  int npat = 0;
+  {
+    unsigned long long prev = ~0ull;
+    for (; npat < K; ++npat) {
       unsigned long long best = 0;
-      for (int g = 0; g < b.parts; ++g) {
-        const unsigned long long* src =
-            b.lists_all + (long long)g * b.part_stride + (size_t)(rolerow_off + p) * b.lc * KS;
-        unsigned long long m = next_below(src, b.lc, KS, K, prev);
-        best = m > best ? m : best;
-      }
-      if (best == 0) break;
-      if (lane == 0) out[r] = best;
-      if (r == 0) top = best;
-      prev = best;
-    }
-    for (int q = r + lane; q < KS; q += 32) out[q] = 0;  // zero padding after the r valid keys
-    if (excl_step && !dstar_set && (b.blob[role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE)) {
-      // the FIRST participating role decides (spec §3.5)
-      dstar = top ? t.domain[key_node(top)] : -1;
-      dstar_set = true;
-    }
-  }
-  if (lane == 0) b.dstar[step] = excl_step ? dstar : -1;
-}
-
-// ---- B2: restricted reselect inside D* for exclusive steps without a fixed
-// domain: scan the nodes of D* that fall into this rank's slab, read the scores
-// back from the dense matrix (just written, L2-resident), top-K per role row.
-__global__ void __launch_bounds__(SEL_THREADS) k_excl_reselect(TopoDev t, BatchDev b) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int step = blockIdx.x * SEL_WARPS + warp;
-  if (step >= b.n_steps) return;
-  const int* hdr = b.blob + RBGTOPO_HDR_WORDS + (size_t)step * RBGTOPO_STEP_WORDS;
-  const int flags = hdr[1], fixed_domain = hdr[2], P = hdr[3], role_off = hdr[4];
-  const int rep_off = hdr[12], rolerow_off = hdr[13];
-  if (!(flags & RBGTOPO_STEP_EXCLUSIVE) || fixed_domain >= 0) return;
-  const int dstar = b.dstar[step];
-  int rowbase = 0, kacc = 0;
-  for (int p = 0; p < P; ++p) {
-    const int count = b.blob[role_off + 4 * p];
-    kacc += count;
-    const int K = min(kacc, t.n);
-    const bool rexcl = (b.blob[role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE) != 0;
-    unsigned long long* out = b.excl + (size_t)(rolerow_off + p) * KS;
-    if (rexcl) {
-      int r = 0;
-      if (dstar >= 0) {
-        const int d0 = t.dom_ptr[dstar], d1 = t.dom_ptr[dstar + 1];
-        const float* row = b.matrix + (size_t)(rep_off + rowbase) * t.slab_stride;
-        unsigned long long prev = ~0ull;
-        for (; r < K; ++r) {
-          unsigned long long best = 0;
-          for (int i = d0 + lane; i < d1; i += 32) {
-            const int n = t.dom_nodes[i];
-            if (n >= t.slab_lo && n < t.slab_hi) {
-              const float x = row[n - t.slab_lo];
-              if (x != -INFINITY) {
-                unsigned long long k = make_key(x, n);
-                if (k < prev && k > best) best = k;
-              }
-            }
-          }
-          best = warp_max_u64(best);
-          if (best == 0) break;
-          if (lane == 0) out[r] = best;
-          prev = best;
-        }
-      }
-      for (int q = r + lane; q < KS; q += 32) out[q] = 0;
-    }
-    rowbase += count;
-  }
-}
-
-// ---- B3: final lists + greedy in replica order (spec §3.6) --------------------
-__global__ void __launch_bounds__(SEL_THREADS) k_greedy(TopoDev t, BatchDev b) {
-  __shared__ unsigned long long sList[SEL_WARPS][MAXP][KS];
-  __shared__ int sTakenNode[SEL_WARPS][KS];
-  __shared__ int sTakenAmt[SEL_WARPS][KS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int step = blockIdx.x * SEL_WARPS + warp;
-  if (step >= b.n_steps) return;
-  const int* hdr = b.blob + RBGTOPO_HDR_WORDS + (size_t)step * RBGTOPO_STEP_WORDS;
-  const int flags = hdr[1], fixed_domain = hdr[2], P = hdr[3], role_off = hdr[4];
-  const int n_cons = hdr[9], cons_off = hdr[10];
-  const int R = hdr[11], rep_off = hdr[12], rolerow_off = hdr[13];
-  const bool excl_unknown = (flags & RBGTOPO_STEP_EXCLUSIVE) && fixed_domain < 0;
-  const int* con = b.blob + cons_off;
-
-  // final list per role row
-  int kacc0 = 0;
-  for (int p = 0; p < P; ++p) {
-    kacc0 += b.blob[role_off + 4 * p];
-    const int K = min(kacc0, t.n);
-    const bool rexcl = (b.blob[role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE) != 0;
-    if (excl_unknown && rexcl) {
-      // merge the per-rank restricted lists
-      unsigned long long prev = ~0ull;
-      int r = 0;
-      for (; r < K; ++r) {
-        unsigned long long best = 0;
-        for (int g = lane; g < b.parts * K; g += 32) {
-          unsigned long long k =
-              b.excl_all[(long long)(g / K) * b.excl_part_stride + (size_t)(rolerow_off + p) * KS + (g % K)];
+      for (int i = lane; i < cnt; i += 32) {
+        const int node = cand[i];
+        const float x = row[node];
+        if (x != -INFINITY && (dom == DOM_ANY || t.domain[node] == dom)) {
+          const unsigned long long k = make_key(x, node);
           if (k < prev && k > best) best = k;
         }
-        best = warp_max_u64(best);
-        if (best == 0) break;
-        if (lane == 0) sList[warp][p][r] = best;
-        prev = best;
       }
-      for (int q = r + lane; q < KS; q += 32) sList[warp][p][q] = 0;
-      // publish the final list for inspection (rbgtopo_read_topk)
-      __syncwarp();
-      b.merged[(size_t)(rolerow_off + p) * KS + lane] = sList[warp][p][lane];
-    } else {
-      sList[warp][p][lane] = b.merged[(size_t)(rolerow_off + p) * KS + lane];
+      best = warp_max_u64(best);
+      if (best == 0) break;
+      if (lane == 0) sPat[npat] = best;
+      prev = best;
+    }
+  }
+
+  // ---- (b) walk the background order
+  const int slab_len = t.slab_hi - t.slab_lo;
+  const float need = (float)need_i;
+  int acc = 0;
+  for (int pos = 0; pos < slab_len && acc < K; pos += 32) {
+    const int i = pos + lane;
+    int node = -1;
+    unsigned long long key = 0;
+    bool ok = false;
+    if (i < slab_len) {
+      if (need_i > 0) {
+        const unsigned long long ob = t.order[i];
+        node = key_node(ob);
+        const float base = __uint_as_float((uint32_t)(ob >> 32) ^ 0x80000000u);  // base >= 0
+        key = make_key(need * base, node);
+      } else {
+        node = t.slab_lo + i;
+        key = make_key(0.0f, node);
+      }
+      ok = t.free_[node] >= demand;
+      if (ok && rexcl) {
+        const int o = t.node_owner[node];
+        ok = (o == -1 || o == h.gid);
+      }
+      if (ok && dom != DOM_ANY) ok = t.domain[node] == dom;
+    }
+    if (__any_sync(FULL, ok)) {
+      // patched nodes are not background: their exact key is in (a)
+      for (int e = 0; e < cnt; ++e)
+        if (cand[e] == node) ok = false;
+    }
+    const uint32_t m = __ballot_sync(FULL, ok);
+    const int idx = acc + __popc(m & ((1u << lane) - 1u));
+    if (ok && idx < K) sAcc[idx] = key;
+    acc += __popc(m);
+  }
+  acc = min(acc, K);
+  __syncwarp();
+
+  // ---- merge the two descending lists
+  if (lane == 0) {
+    int ia = 0, ip = 0;
+    for (int r = 0; r < KS; ++r) {
+      unsigned long long v = 0;
+      if (r < K) {
+        const unsigned long long a = ia < acc ? sAcc[ia] : 0ull;
+        const unsigned long long c = ip < npat ? sPat[ip] : 0ull;
+        if (a > c) { v = a; ++ia; } else if (c) { v = c; ++ip; }
+      }
+      out[r] = v;
     }
   }
   __syncwarp();
+}
 
+// Greedy in replica order on the step's final lists (spec §3.6).  One warp.
+__device__ __forceinline__ void greedy_step(const TopoDev& t, const BatchDev& b, int step, const StepHdr& h,
+                                            const unsigned long long (*sList)[KS], int* sTakenNode,
+                                            int* sTakenAmt, int dstar) {
+  const int lane = threadIdx.x & 31;
+  const int* con = b.blob + h.cons_off;
   int ntaken = 0, unplaced = 0, r = 0;
-  for (int p = 0; p < P; ++p) {
-    const int count = b.blob[role_off + 4 * p], demand = b.blob[role_off + 4 * p + 1];
+  for (int p = 0; p < h.P; ++p) {
+    const int count = b.blob[h.role_off + 4 * p], demand = b.blob[h.role_off + 4 * p + 1];
     for (int c = 0; c < count; ++c, ++r) {
       int pick = -1;
       for (int k = 0; k < KS; ++k) {  // the list holds K_p keys, then zeros
-        const unsigned long long key = sList[warp][p][k];
+        const unsigned long long key = sList[p][k];
         if (key == 0) break;
         const int node = key_node(key);
         int used = 0;
-        for (int i = lane; i < n_cons; i += 32)
+        for (int i = lane; i < h.n_cons; i += 32)
           if (con[2 * i] == node) used += con[2 * i + 1];
         for (int i = lane; i < ntaken; i += 32)
-          if (sTakenNode[warp][i] == node) used += sTakenAmt[warp][i];
+          if (sTakenNode[i] == node) used += sTakenAmt[i];
         used = __reduce_add_sync(FULL, used);
         if (t.free_[node] - used >= demand) {
           pick = node;
@@ -187,27 +192,177 @@ __global__ void __launch_bounds__(SEL_THREADS) k_greedy(TopoDev t, BatchDev b) {
       }
       if (pick >= 0) {
         if (lane == 0) {
-          sTakenNode[warp][ntaken] = pick;
-          sTakenAmt[warp][ntaken] = demand;
+          sTakenNode[ntaken] = pick;
+          sTakenAmt[ntaken] = demand;
         }
         ++ntaken;
         __syncwarp();
       } else {
         ++unplaced;
       }
-      if (lane == 0) b.assign[rep_off + r] = pick;
+      if (lane == 0) b.assign[h.rep_off + r] = pick;
     }
   }
   __syncwarp();
   int status = unplaced ? RBGTOPO_PLACED_PART : RBGTOPO_PLACED_ALL;
-  if (unplaced && (flags & RBGTOPO_STEP_GANG)) {
+  if (unplaced && (h.flags & RBGTOPO_STEP_GANG)) {
     status = RBGTOPO_GANG_FAILED;
-    for (int i = lane; i < R; i += 32) b.assign[rep_off + i] = -1;
+    for (int i = lane; i < h.R; i += 32) b.assign[h.rep_off + i] = -1;
   }
   if (lane == 0) {
     b.status[step] = status;
-    b.domain_out[step] = b.dstar[step];
+    b.domain_out[step] = dstar;
+    b.dstar[step] = dstar;
   }
+}
+
+// ---- world == 1: select + exclusive domain + greedy fused, one CTA per step,
+// warp p selects role row p, warp 0 runs the greedy.  blockDim = 32 * PB.
+__global__ void __launch_bounds__(32 * MAXP) k_select_assign(TopoDev t, BatchDev b) {
+  __shared__ unsigned long long sList[MAXP][KS];
+  __shared__ unsigned long long sAcc[MAXP][KS];
+  __shared__ unsigned long long sPat[MAXP][KS];
+  __shared__ int sTakenNode[KS], sTakenAmt[KS];
+  __shared__ int sDstar, sCnt;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int step = blockIdx.x;
+  const StepHdr h = load_hdr(b, step);
+  const bool excl_step = (h.flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
+  int* cand = b.cand + b.poff[step];
+  if (threadIdx.x == 0) sCnt = 0;
+  __syncthreads();
+  build_candidates(t, b, h, cand, &sCnt);
+  __syncthreads();
+  const int cnt = sCnt;
+  int dstar = excl_step ? h.fixed_domain : -1;
+  if (excl_step && h.fixed_domain < 0) {
+    // D* = domain of the best feasible node of the FIRST participating role (spec §3.5)
+    int pstar = -1;
+    for (int p = 0; p < h.P; ++p)
+      if (b.blob[h.role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE) { pstar = p; break; }
+    if (warp == 0) {
+      int d = -1;
+      if (pstar >= 0) {
+        select_role(t, b, h, pstar, 1, DOM_ANY, cand, cnt, sAcc[0], sPat[0], sList[0]);
+        const unsigned long long top = sList[0][0];
+        d = top ? t.domain[key_node(top)] : -1;
+      }
+      if (lane == 0) sDstar = d;
+    }
+    __syncthreads();
+    dstar = sDstar;
+  }
+  if (warp < h.P) {
+    const int p = warp;
+    const bool rexcl = excl_step && (b.blob[h.role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE);
+    const int dom = rexcl ? (dstar >= 0 ? dstar : DOM_NONE) : DOM_ANY;
+    select_role(t, b, h, p, role_k(b, h, p, t.n), dom, cand, cnt, sAcc[p], sPat[p], sList[p]);
+    b.merged[(size_t)(h.rolerow_off + p) * KS + lane] = sList[p][lane];
+  }
+  __syncthreads();
+  if (warp == 0) greedy_step(t, b, step, h, sList, sTakenNode, sTakenAmt, dstar);
+}
+
+// ---- world > 1, pass 1 (pass2 == 0): rank-local lists of every role row; roles
+// of exclusive steps WITHOUT a fixed domain are selected unrestricted (their top-1
+// decides D* after the all-gather).  Pass 2 (pass2 == 1): those roles again,
+// restricted to D*, into b.excl.
+__global__ void __launch_bounds__(32 * MAXP) k_select(TopoDev t, BatchDev b, int pass2) {
+  __shared__ unsigned long long sAcc[MAXP][KS];
+  __shared__ unsigned long long sPat[MAXP][KS];
+  __shared__ int sCnt;
+  const int warp = threadIdx.x >> 5;
+  const int step = blockIdx.x;
+  const StepHdr h = load_hdr(b, step);
+  const bool excl_step = (h.flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
+  const bool unknown = excl_step && h.fixed_domain < 0;
+  if (pass2 && !unknown) return;  // CTA-uniform
+  int* cand = b.cand + b.poff[step];
+  if (threadIdx.x == 0) sCnt = 0;
+  __syncthreads();
+  build_candidates(t, b, h, cand, &sCnt);
+  __syncthreads();
+  const int cnt = sCnt;
+  if (warp >= h.P) return;
+  const int p = warp;
+  const bool rexcl = excl_step && (b.blob[h.role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE);
+  const int K = role_k(b, h, p, t.n);
+  if (!pass2) {
+    const int dom = (rexcl && !unknown) ? h.fixed_domain : DOM_ANY;
+    select_role(t, b, h, p, K, dom, cand, cnt, sAcc[p], sPat[p], b.lists + (size_t)(h.rolerow_off + p) * KS);
+  } else if (rexcl) {
+    const int d = b.dstar[step];
+    select_role(t, b, h, p, K, d >= 0 ? d : DOM_NONE, cand, cnt, sAcc[p], sPat[p],
+                b.excl + (size_t)(h.rolerow_off + p) * KS);
+  }
+}
+
+constexpr int SEL_WARPS = 4;
+constexpr int SEL_THREADS = SEL_WARPS * 32;
+
+// Top-K of `parts` descending lists of K keys each (src + g*stride), by one warp.
+__device__ __forceinline__ int merge_parts(const unsigned long long* src, long long stride, int parts, int K,
+                                           unsigned long long* out /* [KS] */) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long prev = ~0ull;
+  int r = 0;
+  for (; r < K; ++r) {
+    unsigned long long best = 0;
+    for (int i = lane; i < parts * K; i += 32) {
+      const unsigned long long k = src[(long long)(i / K) * stride + (i % K)];
+      if (k < prev && k > best) best = k;
+    }
+    best = warp_max_u64(best);
+    if (best == 0) break;
+    if (lane == 0) out[r] = best;
+    prev = best;
+  }
+  for (int q = r + lane; q < KS; q += 32) out[q] = 0;
+  __syncwarp();
+  return r;
+}
+
+// ---- world > 1: merged[rolerow] = top-K over the ranks' lists; D* per step
+__global__ void __launch_bounds__(SEL_THREADS) k_merge(TopoDev t, BatchDev b) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int step = blockIdx.x * SEL_WARPS + warp;
+  if (step >= b.n_steps) return;
+  const StepHdr h = load_hdr(b, step);
+  const bool excl_step = (h.flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
+  int dstar = excl_step ? h.fixed_domain : -1;
+  bool dstar_set = !excl_step || h.fixed_domain >= 0;
+  for (int p = 0; p < h.P; ++p) {
+    unsigned long long* out = b.merged + (size_t)(h.rolerow_off + p) * KS;
+    merge_parts(b.lists_all + (size_t)(h.rolerow_off + p) * KS, b.part_stride, b.parts, role_k(b, h, p, t.n), out);
+    if (!dstar_set && (b.blob[h.role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE)) {
+      const unsigned long long top = out[0];  // the FIRST participating role decides
+      dstar = top ? t.domain[key_node(top)] : -1;
+      dstar_set = true;
+    }
+  }
+  if (lane == 0) b.dstar[step] = dstar;
+}
+
+// ---- world > 1: final lists (restricted ones merged over the ranks) + greedy
+__global__ void __launch_bounds__(SEL_THREADS) k_greedy(TopoDev t, BatchDev b) {
+  __shared__ unsigned long long sList[SEL_WARPS][MAXP][KS];
+  __shared__ int sTakenNode[SEL_WARPS][KS];
+  __shared__ int sTakenAmt[SEL_WARPS][KS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int step = blockIdx.x * SEL_WARPS + warp;
+  if (step >= b.n_steps) return;
+  const StepHdr h = load_hdr(b, step);
+  const bool unknown = (h.flags & RBGTOPO_STEP_EXCLUSIVE) && h.fixed_domain < 0;
+  for (int p = 0; p < h.P; ++p) {
+    const bool rexcl = (b.blob[h.role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE) != 0;
+    unsigned long long* mg = b.merged + (size_t)(h.rolerow_off + p) * KS;
+    if (unknown && rexcl)  // publish the final (restricted) list for rbgtopo_read_topk too
+      merge_parts(b.excl_all + (size_t)(h.rolerow_off + p) * KS, b.excl_part_stride, b.parts,
+                  role_k(b, h, p, t.n), mg);
+    sList[warp][p][lane] = mg[lane];
+  }
+  __syncwarp();
+  greedy_step(t, b, step, h, sList[warp], sTakenNode[warp], sTakenAmt[warp], b.dstar[step]);
 }
 
 }  // namespace rbgtopo
