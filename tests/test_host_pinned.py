@@ -1,0 +1,139 @@
+"""The product's host-side mirrors of the reference-pinned arithmetic (C, exported
+through the ABI: rbgtopo_* in include/rbgtopo.h) against the reference's golden
+tables and, on sweeps, against oracle/refpinned.py."""
+import ctypes as C
+import math
+
+import pytest
+
+from oracle import refpinned as rp
+from rbg_b200 import _lib
+from rbg_b200.plugin import HostArith, RoleSpec
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return _lib.load()
+
+
+def _arr(v):
+    return (C.c_int32 * len(v))(*v)
+
+
+PROG = {"": 0, None: 0, "OrderScheduled": 1, "OrderReady": 2}
+
+
+def _ctr(lib, max_skew, prog, states, order):
+    n = len(order)
+    tgt = (C.c_int32 * n)()
+    rc = lib.rbgtopo_calculate_target_replicas(max_skew, PROG[prog], n, _arr([states[r][0] for r in order]),
+                                               _arr([states[r][1] for r in order]), _arr([states[r][2] for r in order]),
+                                               _arr([states[r][3] for r in order]), tgt)
+    return rc, dict(zip(order, tgt))
+
+
+def test_calculate_target_replicas_golden(lib, golden):
+    # pkg/coordination/coordinationscaling/scaler_test.go:100-518, :599-759
+    for table in ("calculate_target_replicas", "progression_strategy"):
+        for c in golden[table]["cases"]:
+            out = C.c_double()
+            assert lib.rbgtopo_parse_percentage(c["maxSkew"].encode(), C.byref(out)) == 0
+            if c.get("wantErr"):
+                assert _ctr(lib, out.value, "", {}, [])[0] != 0
+                continue
+            for order in (sorted(c["states"]), sorted(c["states"], reverse=True)):
+                rc, got = _ctr(lib, out.value, c.get("progression", ""), c["states"], order)
+                assert rc == 0 and got == c["want"], c["name"]
+
+
+def test_parse_percentage_golden(lib, golden):
+    # scaler_test.go:520-597
+    for c in golden["parse_percentage"]["cases"]:
+        out = C.c_double()
+        rc = lib.rbgtopo_parse_percentage(c["in"].encode(), C.byref(out))
+        if c.get("wantErr"):
+            assert rc != 0, c["in"]
+        else:
+            assert rc == 0 and out.value == c["want"], c["in"]
+
+
+def test_updated_replicas_bound_golden(lib, golden):
+    # rolebasedgroup_controller_test.go:1283-1377
+    for c in golden["updated_replicas_bound"]["cases"]:
+        lo, hi = C.c_int32(), C.c_int32()
+        s = int(c["maxSkew"].rstrip("%"))
+        assert lib.rbgtopo_updated_replicas_bound(s, c["refUpdated"], c["refDesired"], c["requestDesired"],
+                                                  C.byref(lo), C.byref(hi)) == 0
+        assert (lo.value, hi.value) == (c["lower"], c["upper"]), c["name"]
+
+
+def test_scaled_value_matches_intstr(lib):
+    # vendor/k8s.io/apimachinery/pkg/util/intstr/intstr.go:181-197
+    for pct in (0, 1, 5, 10, 33, 50, 99, 100, 150):
+        for total in (0, 1, 2, 3, 7, 10, 99, 100, 1000):
+            for up in (0, 1):
+                assert lib.rbgtopo_scaled_value(1, pct, total, up) == \
+                    rp.get_scaled_value_from_int_or_percent(f"{pct}%", total, bool(up))
+    assert lib.rbgtopo_scaled_value(0, 7, 100, 1) == 7
+
+
+def _roll(lib, s_pct, desired, updated):
+    """Test_CalculateNextRollingTarget loop (rolebasedgroup_controller_test.go:207-250) via the C mirror,
+    cross-checked step by step against oracle/refpinned.py."""
+    names = sorted(desired)
+    d = [desired[k] for k in names]
+    u = [updated[k] for k in names]
+    bias = max(int(math.ceil(10000.0 / x)) for x in d)
+    max_bp = max(1, int(math.ceil(s_pct * 10000 / 100)))
+    for _ in range(100000):
+        tgt = (C.c_int32 * len(d))()
+        rc = lib.rbgtopo_next_rolling_target(s_pct, len(d), _arr(d), _arr(u), _arr(d), tgt)
+        ref = rp.calculate_next_rolling_target(f"{s_pct}%", names, dict(zip(names, d)), dict(zip(names, u)),
+                                               dict(zip(names, d)))
+        assert rc == 0 and list(tgt) == [ref[k] for k in names], (d, u, list(tgt), ref)
+        u = list(tgt)
+        ratios = [u[i] / d[i] for i in range(len(d))]
+        assert int(math.ceil(10000.0 * (max(ratios) - min(ratios)))) <= bias + max_bp, (d, u)
+        if all(u[i] >= d[i] for i in range(len(d))):
+            return
+    raise AssertionError("did not terminate")
+
+
+def test_next_rolling_target(lib, golden):
+    # rolebasedgroup_controller_test.go:54-332 (seeds + thinned sweeps; full sweeps in test_refpinned_golden)
+    for c in golden["next_rolling_target_seeds"]["cases"]:
+        _roll(lib, int(c["maxSkew"].rstrip("%")), c["desired"], c["updated"])
+    for p in range(1, 100, 7):
+        for d in range(1, 100, 5):
+            _roll(lib, 1, {"prefill": p, "decode": d}, {"prefill": 0, "decode": 0})
+
+
+def test_dependency_levels_and_group_size(golden):
+    # pkg/dependency/dependency_test.go:37-121; api/workloads/v1alpha2/helper.go:50-65
+    ha = HostArith()
+    for c in golden["dependency_order"]["cases"]:
+        roles = [RoleSpec(n, 1, tuple(deps)) for n, deps in c["deps"].items()]
+        if c.get("wantErr"):
+            with pytest.raises(ValueError):
+                ha.dependency_levels(roles)
+        else:
+            got = [[roles[i].name for i in lvl] for lvl in ha.dependency_levels(roles)]
+            assert got == c["want"], c["name"]
+    for c in golden["group_size"]["cases"]:
+        roles = [RoleSpec(f"r{i}", r["replicas"], lws_size=(r.get("lws_size") or 0) if r.get("lws") else 0)
+                 for i, r in enumerate(c["roles"])]
+        assert ha.group_size(roles) == c["want"]
+
+
+def test_dependency_levels_random_vs_oracle():
+    import random
+    ha = HostArith()
+    rnd = random.Random(5)
+    for _ in range(200):
+        n = rnd.randint(1, 9)
+        names = [f"role{rnd.randint(0, 99):02d}x{i}" for i in range(n)]
+        deps = {nm: [names[j] for j in range(n) if j < i and rnd.random() < 0.3] for i, nm in enumerate(names)}
+        roles = [RoleSpec(nm, 1, tuple(deps[nm])) for nm in names]
+        rnd.shuffle(roles)
+        got = [[roles[i].name for i in lvl] for lvl in ha.dependency_levels(roles)]
+        assert got == rp.dependency_order(deps)
