@@ -414,7 +414,7 @@ int launch_score(rbgtopo_ctx* c, Batch* b, cudaStream_t s) {
 int launch_select_assign(rbgtopo_ctx* c, Batch* b, cudaStream_t s, const BatchDev& d, int* launches) {
   const int ns = b->m.n_steps;
   if (ns == 0) return RBGTOPO_OK;
-  k_select_assign<<<ns, 32 * b->m.max_p, 0, s>>>(topo_dev(c), d);
+  k_select_assign<<<ns, 32 * b->m.max_p, select_smem_bytes(b->m.max_p), s>>>(topo_dev(c), d);
   ++*launches;
   return RBGTOPO_OK;
 }
@@ -1007,7 +1007,8 @@ int32_t rbgtopo_shard_score(rbgtopo_ctx* c, int32_t handle, void** keys_dev, int
   if (timed) CK(cudaEventRecord(b->it_ev[e0 + 1], s));
   b->shard_timed = timed;
   b->pend_launches += 2;
-  if (b->m.n_steps) k_select<<<b->m.n_steps, 32 * b->m.max_p, 0, s>>>(topo_dev(c), batch_dev(c, b), 0);
+  if (b->m.n_steps)
+    k_select<<<b->m.n_steps, 32 * b->m.max_p, select_smem_bytes(b->m.max_p), s>>>(topo_dev(c), batch_dev(c, b), 0);
   CK(cudaGetLastError());
   *keys_dev = b->lists.p;
   *keys_bytes = (int64_t)std::max(1, b->m.total_p) * KS * 8;
@@ -1034,7 +1035,7 @@ int32_t rbgtopo_shard_merge(rbgtopo_ctx* c, int32_t handle, const void* keys_all
     k_merge<<<grid, SEL_THREADS, 0, s>>>(topo_dev(c), d);
     ++launches;
     if (b->m.any_excl_unknown) {
-      k_select<<<b->m.n_steps, 32 * b->m.max_p, 0, s>>>(topo_dev(c), d, 1);
+      k_select<<<b->m.n_steps, 32 * b->m.max_p, select_smem_bytes(b->m.max_p), s>>>(topo_dev(c), d, 1);
       ++launches;
     }
   }

@@ -73,8 +73,11 @@ __device__ __forceinline__ void build_candidates(const TopoDev& t, const BatchDe
 
 // Rank-local top-K of role row p of `step` into out[0..KS) (keys descending, then
 // zeros).  sAcc / sPat: per-warp shared scratch of KS keys each.  All 32 lanes call.
+// cand/cnt: the step's patched nodes (shared memory when they fit, else the global
+// scratch); kcache: per-warp shared array of >= min(cnt, kcap) keys (may be null).
 __device__ __forceinline__ void select_role(const TopoDev& t, const BatchDev& b, const StepHdr& h, int p,
                                             int K, int dom, const int* cand, int cnt,
+                                            unsigned long long* kcache, int kcap,
                                             unsigned long long* sAcc, unsigned long long* sPat,
                                             unsigned long long* out) {
   const int lane = threadIdx.x & 31;
@@ -88,18 +91,36 @@ __device__ __forceinline__ void select_role(const TopoDev& t, const BatchDev& b,
   const float* __restrict__ row =
       b.matrix + (size_t)(h.rep_off + role_rowbase(b, h, p)) * t.slab_stride - t.slab_lo;  // row[node]
 
-  // ---- (a) top-K of the patched nodes (exact scores from the matrix)
+  // ---- (a) top-K of the patched nodes (exact scores read back from the matrix,
+  // once, into the shared key cache; duplicates of a node give equal keys, which
+  // the strictly-below rounds skip)
   int npat = 0;
   {
-    unsigned long long prev = ~0ull;
-    for (; npat < K; ++npat) {
-      unsigned long long best = 0;
+    const bool cached = kcache != nullptr && cnt <= kcap;
+    if (cached) {
       for (int i = lane; i < cnt; i += 32) {
         const int node = cand[i];
         const float x = row[node];
-        if (x != -INFINITY && (dom == DOM_ANY || t.domain[node] == dom)) {
-          const unsigned long long k = make_key(x, node);
+        kcache[i] = (x != -INFINITY && (dom == DOM_ANY || t.domain[node] == dom)) ? make_key(x, node) : 0ull;
+      }
+      __syncwarp();
+    }
+    unsigned long long prev = ~0ull;
+    for (; npat < K; ++npat) {
+      unsigned long long best = 0;
+      if (cached) {
+        for (int i = lane; i < cnt; i += 32) {
+          const unsigned long long k = kcache[i];
           if (k < prev && k > best) best = k;
+        }
+      } else {
+        for (int i = lane; i < cnt; i += 32) {
+          const int node = cand[i];
+          const float x = row[node];
+          if (x != -INFINITY && (dom == DOM_ANY || t.domain[node] == dom)) {
+            const unsigned long long k = make_key(x, node);
+            if (k < prev && k > best) best = k;
+          }
         }
       }
       best = warp_max_u64(best);
@@ -218,7 +239,31 @@ __device__ __forceinline__ void greedy_step(const TopoDev& t, const BatchDev& b,
 
 // ---- world == 1: select + exclusive domain + greedy fused, one CTA per step,
 // warp p selects role row p, warp 0 runs the greedy.  blockDim = 32 * PB.
+// dynamic shared memory of the selection kernels: cand[CAND_CAP] i32 | keys[PB][CAND_CAP] u64
+constexpr int CAND_CAP = 512;
+__host__ __device__ inline size_t select_smem_bytes(int PB) { return (size_t)CAND_CAP * 4 + (size_t)PB * CAND_CAP * 8; }
+
+// Builds the patched-node list in shared memory when it fits (the host-computed
+// capacity poff[step+1]-poff[step] is an upper bound), else in the global scratch.
+struct CandRef { const int* p; int cnt; };
+__device__ __forceinline__ CandRef stage_candidates(const TopoDev& t, const BatchDev& b, int step, const StepHdr& h,
+                                                    int* sCand, int* sCnt) {
+  const int cap = b.poff[step + 1] - b.poff[step];
+  int* dst = cap <= CAND_CAP ? sCand : b.cand + b.poff[step];
+  if (threadIdx.x == 0) *sCnt = 0;
+  __syncthreads();
+  build_candidates(t, b, h, dst, sCnt);
+  __syncthreads();
+  CandRef r;
+  r.p = dst;
+  r.cnt = *sCnt;
+  return r;
+}
+
 __global__ void __launch_bounds__(32 * MAXP) k_select_assign(TopoDev t, BatchDev b) {
+  extern __shared__ __align__(16) unsigned char sel_smem[];
+  int* sCand = reinterpret_cast<int*>(sel_smem);
+  unsigned long long* sKeys = reinterpret_cast<unsigned long long*>(sel_smem + (size_t)CAND_CAP * 4);
   __shared__ unsigned long long sList[MAXP][KS];
   __shared__ unsigned long long sAcc[MAXP][KS];
   __shared__ unsigned long long sPat[MAXP][KS];
@@ -228,12 +273,9 @@ __global__ void __launch_bounds__(32 * MAXP) k_select_assign(TopoDev t, BatchDev
   const int step = blockIdx.x;
   const StepHdr h = load_hdr(b, step);
   const bool excl_step = (h.flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
-  int* cand = b.cand + b.poff[step];
-  if (threadIdx.x == 0) sCnt = 0;
-  __syncthreads();
-  build_candidates(t, b, h, cand, &sCnt);
-  __syncthreads();
-  const int cnt = sCnt;
+  const CandRef cr = stage_candidates(t, b, step, h, sCand, &sCnt);
+  const int* cand = cr.p;
+  const int cnt = cr.cnt;
   int dstar = excl_step ? h.fixed_domain : -1;
   if (excl_step && h.fixed_domain < 0) {
     // D* = domain of the best feasible node of the FIRST participating role (spec §3.5)
@@ -243,7 +285,7 @@ __global__ void __launch_bounds__(32 * MAXP) k_select_assign(TopoDev t, BatchDev
     if (warp == 0) {
       int d = -1;
       if (pstar >= 0) {
-        select_role(t, b, h, pstar, 1, DOM_ANY, cand, cnt, sAcc[0], sPat[0], sList[0]);
+        select_role(t, b, h, pstar, 1, DOM_ANY, cand, cnt, sKeys, CAND_CAP, sAcc[0], sPat[0], sList[0]);
         const unsigned long long top = sList[0][0];
         d = top ? t.domain[key_node(top)] : -1;
       }
@@ -256,7 +298,8 @@ __global__ void __launch_bounds__(32 * MAXP) k_select_assign(TopoDev t, BatchDev
     const int p = warp;
     const bool rexcl = excl_step && (b.blob[h.role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE);
     const int dom = rexcl ? (dstar >= 0 ? dstar : DOM_NONE) : DOM_ANY;
-    select_role(t, b, h, p, role_k(b, h, p, t.n), dom, cand, cnt, sAcc[p], sPat[p], sList[p]);
+    select_role(t, b, h, p, role_k(b, h, p, t.n), dom, cand, cnt, sKeys + (size_t)p * CAND_CAP, CAND_CAP, sAcc[p],
+                sPat[p], sList[p]);
     b.merged[(size_t)(h.rolerow_off + p) * KS + lane] = sList[p][lane];
   }
   __syncthreads();
@@ -268,6 +311,9 @@ __global__ void __launch_bounds__(32 * MAXP) k_select_assign(TopoDev t, BatchDev
 // decides D* after the all-gather).  Pass 2 (pass2 == 1): those roles again,
 // restricted to D*, into b.excl.
 __global__ void __launch_bounds__(32 * MAXP) k_select(TopoDev t, BatchDev b, int pass2) {
+  extern __shared__ __align__(16) unsigned char sel_smem[];
+  int* sCand = reinterpret_cast<int*>(sel_smem);
+  unsigned long long* sKeys = reinterpret_cast<unsigned long long*>(sel_smem + (size_t)CAND_CAP * 4);
   __shared__ unsigned long long sAcc[MAXP][KS];
   __shared__ unsigned long long sPat[MAXP][KS];
   __shared__ int sCnt;
@@ -277,23 +323,21 @@ __global__ void __launch_bounds__(32 * MAXP) k_select(TopoDev t, BatchDev b, int
   const bool excl_step = (h.flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
   const bool unknown = excl_step && h.fixed_domain < 0;
   if (pass2 && !unknown) return;  // CTA-uniform
-  int* cand = b.cand + b.poff[step];
-  if (threadIdx.x == 0) sCnt = 0;
-  __syncthreads();
-  build_candidates(t, b, h, cand, &sCnt);
-  __syncthreads();
-  const int cnt = sCnt;
+  const CandRef cr = stage_candidates(t, b, step, h, sCand, &sCnt);
+  const int* cand = cr.p;
+  const int cnt = cr.cnt;
   if (warp >= h.P) return;
   const int p = warp;
   const bool rexcl = excl_step && (b.blob[h.role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE);
   const int K = role_k(b, h, p, t.n);
   if (!pass2) {
     const int dom = (rexcl && !unknown) ? h.fixed_domain : DOM_ANY;
-    select_role(t, b, h, p, K, dom, cand, cnt, sAcc[p], sPat[p], b.lists + (size_t)(h.rolerow_off + p) * KS);
+    select_role(t, b, h, p, K, dom, cand, cnt, sKeys + (size_t)p * CAND_CAP, CAND_CAP, sAcc[p], sPat[p],
+                b.lists + (size_t)(h.rolerow_off + p) * KS);
   } else if (rexcl) {
     const int d = b.dstar[step];
-    select_role(t, b, h, p, K, d >= 0 ? d : DOM_NONE, cand, cnt, sAcc[p], sPat[p],
-                b.excl + (size_t)(h.rolerow_off + p) * KS);
+    select_role(t, b, h, p, K, d >= 0 ? d : DOM_NONE, cand, cnt, sKeys + (size_t)p * CAND_CAP, CAND_CAP, sAcc[p],
+                sPat[p], b.excl + (size_t)(h.rolerow_off + p) * KS);
   }
 }
 

@@ -1,0 +1,74 @@
+"""Multi-GPU node-axis sharding through the C ABI (rbgtopo_shard_*), one process
+per GPU over NCCL.  Needs >= 2 GPUs; launched by the test with torch.distributed.run."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["RBG_ROOT"]); sys.path.insert(0, os.path.join(os.environ["RBG_ROOT"], "tests"))
+from oracle import placer as oracle_placer
+from rbg_b200 import synth
+from rbg_b200.engine import TopoPlacer
+from test_gpu_parity import _random_steps
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+class DevPtr:
+    def __init__(self, p, nb):
+        self.__cuda_array_interface__ = {"shape": (nb // 8,), "typestr": "<i8", "data": (p, False), "version": 3, "strides": None}
+for n, seed, excl in [(4096, 1, False), (10000, 2, True), (3000, 3, True)]:
+    topo = synth.make_topology(n, seed=seed, tiers=4, owned_frac=0.25 if excl else 0.0)
+    blob = _random_steps(topo, 50 + seed, 24, excl=excl, gang=True)
+    ref = oracle_placer.place(topo, blob)
+    eng = TopoPlacer(device=local, rank=rank, world=world)
+    eng.set_topology(topo.row_ptr, topo.col_idx, topo.edge_w, topo.free, topo.domain, topo.domain_owner)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    h = eng.stage(blob)
+    p, nb = eng.shard_score(h)
+    src = torch.as_tensor(DevPtr(p, nb), device="cuda")
+    allk = torch.empty(world * (nb // 8), dtype=torch.int64, device="cuda")
+    dist.all_gather_into_tensor(allk, src)
+    need2, p2, nb2 = eng.shard_merge(h, allk.data_ptr())
+    all2 = None
+    if need2:
+        src2 = torch.as_tensor(DevPtr(p2, nb2), device="cuda")
+        all2 = torch.empty(world * (nb2 // 8), dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(all2, src2)
+    eng.shard_assign(h, all2.data_ptr() if all2 is not None else None)
+    assign, status, domain = eng.fetch(h)
+    assert np.array_equal(assign, ref["assign"]), (rank, n, assign[:16], ref["assign"][:16])
+    assert np.array_equal(status, ref["status"]) and np.array_equal(domain, ref["domain"])
+    lo, hi = eng.slab()
+    for row in range(0, ref["matrix"].shape[0], 7):          # this rank's column slab of the dense matrix
+        got = eng.read_scores(h, row)
+        assert np.array_equal(got.view(np.uint32), ref["matrix"][row, lo:hi].view(np.uint32)), (rank, row)
+    for rr in range(ref["topk"].shape[0]):
+        assert np.array_equal(eng.read_topk(h, rr, 32), ref["topk"][rr]), (rank, rr)
+    eng.release(h); eng.close()
+dist.barrier()
+if rank == 0: print("SHARD_OK", world)
+dist.destroy_process_group()
+'''
+
+
+def test_node_axis_sharding_matches_oracle(tmp_path):
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    world = 2 if ngpu < 4 else 4
+    script = tmp_path / "shard_worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, RBG_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SHARD_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
