@@ -257,7 +257,8 @@ int32_t rbgtopo_shard_assign(rbgtopo_ctx* ctx, int32_t handle,
 int32_t rbgtopo_slab(rbgtopo_ctx* ctx, int32_t* lo, int32_t* hi);
 
 /* Use an external CUDA stream (e.g. the one the caller's NCCL runs on) for
- * every call on this ctx; NULL restores the internal per-slot streams. */
+ * every call on this ctx; NULL restores the internal per-slot streams (pass
+ * cudaStreamLegacy, (void*)0x1, to select the legacy default stream). */
 int32_t rbgtopo_set_stream(rbgtopo_ctx* ctx, void* cuda_stream);
 
 /* ---- stats (SURVEY.md §5 metrics row) ----------------------------------- */

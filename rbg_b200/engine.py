@@ -148,7 +148,12 @@ class TopoPlacer:
                                                   C.c_void_p(keys2_all_ptr) if keys2_all_ptr else None))
 
     def set_stream(self, cuda_stream: Optional[int]) -> None:
-        self._check(self.lib.rbgtopo_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+        """None restores the internal per-call streams.  A torch default stream has
+        handle 0 (the legacy NULL stream): it is passed as cudaStreamLegacy (0x1)."""
+        if cuda_stream is None:
+            self._check(self.lib.rbgtopo_set_stream(self._h, None))
+        else:
+            self._check(self.lib.rbgtopo_set_stream(self._h, C.c_void_p(cuda_stream if cuda_stream else 1)))
 
     # -- stats
     def last_timing(self) -> dict:

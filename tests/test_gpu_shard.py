@@ -29,7 +29,8 @@ for n, seed, excl in [(4096, 1, False), (10000, 2, True), (3000, 3, True)]:
     ref = oracle_placer.place(topo, blob)
     eng = TopoPlacer(device=local, rank=rank, world=world)
     eng.set_topology(topo.row_ptr, topo.col_idx, topo.edge_w, topo.free, topo.domain, topo.domain_owner)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()                 # kernels and NCCL ordered on one stream
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     h = eng.stage(blob)
     p, nb = eng.shard_score(h)
