@@ -137,7 +137,7 @@ typedef struct rbgtopo_config {
 typedef struct rbgtopo_timing {
   float h2d_ms, base_ms, score_ms, select_ms, d2h_ms, total_ms;
   int32_t launches;      /* kernels launched by the call                       */
-  int32_t reserved;
+  int32_t h2d_words;     /* int32 words uploaded for the batch (blob + offsets)    */
   int64_t scores;        /* (replica x node) scores produced by the call       */
   int64_t algo_bytes;    /* algorithmic bytes of the score kernel, DESIGN §5   */
 } rbgtopo_timing;
@@ -212,6 +212,17 @@ int32_t rbgtopo_score_assign(rbgtopo_ctx* ctx, const int32_t* blob,
 int32_t rbgtopo_place_groups(rbgtopo_ctx* ctx, const int32_t* groups,
                              int64_t groups_words, int32_t* assign,
                              int32_t* status, int32_t* domain);
+
+/* rbgtopo_place_groups pipeline, staged: the groups are compiled into a
+ * device-resident multi-wave plan (one step blob, wave-major; later waves' anchor /
+ * consumed records are filled in on the device by the wave that places them), so
+ * rbgtopo_run_staged runs ONE score launch for the dense rows of every wave plus
+ * one select/assign launch per wave with no host round trip.  rbgtopo_fetch then
+ * returns group-order results like place_groups (groups the plan could not finish
+ * exactly — non-gang groups with an unplaced replica — keep status 1; place_groups
+ * itself re-runs those through the host-driven loop). */
+int32_t rbgtopo_stage_groups(rbgtopo_ctx* ctx, const int32_t* groups,
+                             int64_t groups_words, int32_t* handle);
 
 /* Same computation with the batch kept resident in HBM (bench `value` leg,
  * CUDA-graph replay): stage once, run many times, fetch results on demand. */

@@ -23,7 +23,7 @@ class Config(C.Structure):
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("base_ms", C.c_float), ("score_ms", C.c_float),
                 ("select_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
-                ("launches", C.c_int32), ("reserved", C.c_int32), ("scores", C.c_int64),
+                ("launches", C.c_int32), ("h2d_words", C.c_int32), ("scores", C.c_int64),
                 ("algo_bytes", C.c_int64)]
 
 
@@ -38,6 +38,7 @@ SIGNATURES = {
     "rbgtopo_update_nodes": (C.c_int32, [C.c_void_p, i32p, i32p, C.c_uint64]),
     "rbgtopo_score_assign": (C.c_int32, [C.c_void_p, i32p, C.c_int64, i32p, i32p, i32p]),
     "rbgtopo_place_groups": (C.c_int32, [C.c_void_p, i32p, C.c_int64, i32p, i32p, i32p]),
+    "rbgtopo_stage_groups": (C.c_int32, [C.c_void_p, i32p, C.c_int64, i32p]),
     "rbgtopo_stage": (C.c_int32, [C.c_void_p, i32p, C.c_int64, i32p]),
     "rbgtopo_run_staged": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
     "rbgtopo_fetch": (C.c_int32, [C.c_void_p, C.c_int32, i32p, i32p, i32p]),

@@ -89,6 +89,7 @@ struct Topology {
   DevBuf<unsigned long long> okeys, order;  // background order of the slab (score.cuh / select.cuh)
   DevBuf<unsigned char> sort_tmp;
   std::vector<int> h_degp1;  // deg(n) + 1, for the patch-list capacity of a step
+  int max_degp1 = 1;
   DevBuf<int2> tiles;
   int n_tiles = 0;
   std::vector<int> h_domain;  // kept for update_nodes validation
@@ -119,6 +120,12 @@ struct Batch {
   DevBuf<float> matrix;
   DevBuf<unsigned long long> lists, merged, excl;
   DevBuf<int> cand;  // patched-node scratch of the selection kernels
+  // device-resident multi-wave plan (rbgtopo_stage_groups / place_groups): steps are
+  // wave-major; wave w = steps [wave_begin[w], wave_begin[w + 1])
+  std::vector<int> wave_begin, wave_maxp;
+  std::vector<int> out_index;    // plan replica -> position in the group-order assign array
+  std::vector<int> step_group;   // plan step -> group
+  std::vector<int> grp_flags, grp_assign_off, grp_pending;
   DevBuf<int> out;  // assign[total_r] | status[n] | domain[n] | dstar[n]
   PinBuf<int> h_in, h_out;
   ~Batch() {
@@ -291,8 +298,10 @@ int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, Batc
     }
     if (st[4] & 3) return fail(RBGTOPO_EINVAL, "step %d: role_off must be a multiple of 4 words", s);
     // patched-node scratch: closed neighbourhoods of the anchors + consumed nodes
-    long long pc = nc;
-    for (int a = 0; a < na; ++a) pc += T.h_degp1[anc[3 * a]];
+    if (st[15] < 0 || st[15] > na || (st[14] != 0 && (st[14] <= s || st[14] >= ns)))
+      return fail(RBGTOPO_EINVAL, "step %d: bad wave links", s);
+    long long pc = nc;  // records of earlier waves (the last st[15]) are filled on the device: any node
+    for (int a = 0; a < na; ++a) pc += a < na - st[15] ? T.h_degp1[anc[3 * a]] : T.max_degp1;
     if (m->patch_cap + pc > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "patch lists exceed 2^31 entries");
     m->patch_cap += pc;
     m->poff[s + 1] = (int)m->patch_cap;
@@ -335,6 +344,7 @@ int acquire_batch(rbgtopo_ctx* c, Batch** out) {
 }
 void release_batch(rbgtopo_ctx* c, Batch* b) {
   std::lock_guard<std::mutex> g(c->pool_mu);
+  b->wave_begin.clear();
   b->in_use = false;
   b->staged = false;
   b->ran = false;
@@ -378,7 +388,7 @@ BatchDev batch_dev(rbgtopo_ctx* c, Batch* b) {
   d.chunk = c->chunk;
   d.parts = 1;
   {
-    d.emit_matrix = 1;
+    d.emit_matrix = b->wave_begin.empty() ? 1 : 3;  // plans: background only, corrections per wave
 
   }
   d.matrix = b->matrix.p;
@@ -414,8 +424,20 @@ int launch_score(rbgtopo_ctx* c, Batch* b, cudaStream_t s) {
 int launch_select_assign(rbgtopo_ctx* c, Batch* b, cudaStream_t s, const BatchDev& d, int* launches) {
   const int ns = b->m.n_steps;
   if (ns == 0) return RBGTOPO_OK;
-  k_select_assign<<<ns, 32 * b->m.max_p, select_smem_bytes(b->m.max_p), s>>>(topo_dev(c), d);
-  ++*launches;
+  if (b->wave_begin.empty()) {
+    k_select_assign<<<ns, 32 * b->m.max_p, select_smem_bytes(b->m.max_p), s>>>(topo_dev(c), d, 0, 0);
+    ++*launches;
+    return RBGTOPO_OK;
+  }
+  // multi-wave plan: the emit kernel wrote the background rows of every wave; each
+  // wave applies its sparse corrections, selects, assigns and chains into the next
+  for (size_t w = 0; w + 1 < b->wave_begin.size(); ++w) {
+    const int n = b->wave_begin[w + 1] - b->wave_begin[w];
+    if (n <= 0) continue;
+    k_select_assign<<<n, 32 * b->wave_maxp[w], select_smem_bytes(b->wave_maxp[w]), s>>>(
+        topo_dev(c), d, b->wave_begin[w], SEL_CORRECT | SEL_CHAIN);
+    ++*launches;
+  }
   return RBGTOPO_OK;
 }
 
@@ -497,6 +519,7 @@ int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int3
   tm.scores = m.scores;
   tm.algo_bytes = m.algo_bytes;
   tm.launches = b->pend_launches;
+  tm.h2d_words = (int32_t)(m.words + m.n_steps + 1);
   const int total_passes = b->untimed_or_timed_passes;
   b->passes = 0;
   b->pend_launches = 0;
@@ -661,7 +684,11 @@ int32_t rbgtopo_set_topology(rbgtopo_ctx* c, int32_t n, int64_t e, const int32_t
   T.generation = generation;
   T.h_domain.assign(domain, domain + n);
   T.h_degp1.resize(n);
-  for (int i = 0; i < n; ++i) T.h_degp1[i] = row_ptr[i + 1] - row_ptr[i] + 1;
+  T.max_degp1 = 1;
+  for (int i = 0; i < n; ++i) {
+    T.h_degp1[i] = row_ptr[i + 1] - row_ptr[i] + 1;
+    T.max_degp1 = std::max(T.max_degp1, T.h_degp1[i]);
+  }
   int rc = run_base(c, c->use_ext_stream ? c->ext_stream : (cudaStream_t)0);
   if (rc) return rc;
   T.valid = true;
@@ -726,8 +753,11 @@ struct GroupRun {
 };
 }  // namespace
 
-int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int32_t* assign,
-                             int32_t* status, int32_t* domain) {
+// The host-driven wave loop: one batched launch pair per wave, placements fed back
+// through the host.  Exact for every case; used for the groups the device-resident
+// plan cannot finish (`only` != null: just those groups) and as its reference.
+static int32_t place_groups_slow(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int32_t* assign,
+                                 int32_t* status, int32_t* domain, const std::vector<char>* only) {
   if (!c || !gb) return fail(RBGTOPO_EINVAL, "null argument");
   if (c->cfg.world != 1) return fail(RBGTOPO_EINVAL, "place_groups needs world == 1");
   if (words < RBGTOPO_HDR_WORDS || gb[0] != RBGTOPO_GROUPS_MAGIC || gb[1] != RBGTOPO_ABI_VERSION ||
@@ -767,7 +797,13 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
     while (r.cur_role < r.q && r.roles[4 * r.cur_role + 1] == 0) ++r.cur_role;
   }
   if (gb[4] != pacc) return fail(RBGTOPO_EINVAL, "total pending mismatch");
-  for (long long i = 0; i < pacc; ++i) assign[i] = -1;
+  for (int g = 0; g < ng; ++g) {
+    if (only && !(*only)[g]) {
+      runs[g].cur_role = runs[g].q;  // not ours: done from the start, results untouched
+      continue;
+    }
+    for (int k = 0; k < runs[g].rec[9]; ++k) assign[runs[g].rec[8] + k] = -1;
+  }
 
   Batch* b = nullptr;
   int rc = acquire_batch(c, &b);
@@ -854,6 +890,7 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
       total.select_ms += c->last.select_ms; total.d2h_ms += c->last.d2h_ms;
       total.total_ms += c->last.total_ms; total.launches += c->last.launches;
       total.scores += c->last.scores; total.algo_bytes += c->last.algo_bytes;
+      total.h2d_words += c->last.h2d_words;
     }
     // ---- absorb the placements
     int off = 0;
@@ -889,6 +926,7 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
   }
   if (!rc) {
     for (int g = 0; g < ng; ++g) {
+      if (only && !(*only)[g]) continue;
       const GroupRun& r = runs[g];
       const bool excl = (r.rec[1] & RBGTOPO_STEP_EXCLUSIVE) != 0;
       if (r.failed) {  // gang: nothing of the group is placed
@@ -908,6 +946,249 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
   }
   release_batch(c, b);
   return rc;
+}
+
+// ---- device-resident multi-wave plan ------------------------------------------
+// All waves of all groups as ONE step blob, wave-major.  The wave structure is
+// static (it depends only on levels and pending counts), so every step's records
+// can be laid out up front: its anchor list = the group's scheduled pods + one
+// record per replica of the earlier waves (filled in on the device by the wave
+// that places it), its consumed list likewise, `need` predicted under the
+// assumption that earlier replicas get placed.  Groups for which that assumption
+// fails (non-gang groups with an unplaced replica) are re-run through the
+// host-driven loop afterwards (place_groups_slow) — rare, and exact either way.
+namespace {
+struct PlanWave { std::vector<int> role, first, count; };
+
+int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, std::vector<int32_t>* blob, Batch* b) {
+  if (words < RBGTOPO_HDR_WORDS || gb[0] != RBGTOPO_GROUPS_MAGIC || gb[1] != RBGTOPO_ABI_VERSION || gb[3] != words)
+    return fail(RBGTOPO_EINVAL, "bad groups blob header");
+  const int ng = gb[2];
+  if (ng < 0 || (int64_t)RBGTOPO_HDR_WORDS + (int64_t)ng * RBGTOPO_GROUP_WORDS > words)
+    return fail(RBGTOPO_EINVAL, "group table exceeds blob");
+  auto in = [&](long long off, long long cnt) { return off >= 0 && cnt >= 0 && off + cnt <= words; };
+  std::vector<std::vector<PlanWave>> waves(ng);
+  size_t W = 0;
+  long long pacc = 0;
+  b->grp_flags.assign(ng, 0);
+  b->grp_assign_off.assign(ng, 0);
+  b->grp_pending.assign(ng, 0);
+  for (int g = 0; g < ng; ++g) {
+    const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
+    const int q = rec[3];
+    if (q < 1 || q > RBGTOPO_MAX_GROUP_ROLES) return fail(RBGTOPO_ELIMIT, "group %d: %d roles", g, q);
+    if (!in(rec[4], 4LL * q) || !in(rec[5], (long long)q * q) || !in(rec[7], 3LL * rec[6]))
+      return fail(RBGTOPO_EINVAL, "group %d: section out of bounds", g);
+    const int32_t* roles = gb + rec[4];
+    long long pend = 0;
+    for (int i = 0; i < q; ++i) {
+      if (roles[4 * i + 1] < 0 || (i && roles[4 * i] < roles[4 * (i - 1)]))
+        return fail(RBGTOPO_EINVAL, "group %d role %d: pending < 0 or levels not ascending", g, i);
+      pend += roles[4 * i + 1];
+    }
+    if (rec[8] != pacc || rec[9] != pend) return fail(RBGTOPO_EINVAL, "group %d: bad assign_off/n_pending", g);
+    b->grp_flags[g] = rec[1];
+    b->grp_assign_off[g] = (int)pacc;
+    b->grp_pending[g] = (int)pend;
+    pacc += pend;
+    // static wave structure: same rule as the host loop / plugin.py
+    int cr = 0, taken = 0;
+    while (cr < q) {
+      if (roles[4 * cr + 1] - taken <= 0) { ++cr; taken = 0; continue; }
+      PlanWave w;
+      const int level = roles[4 * cr];
+      int n = 0;
+      while (cr < q && roles[4 * cr] == level && n < RBGTOPO_MAX_STEP_REPLICAS &&
+             (int)w.role.size() < RBGTOPO_MAX_STEP_ROLES) {
+        const int left = roles[4 * cr + 1] - taken;
+        if (left <= 0) { ++cr; taken = 0; continue; }
+        const int take = std::min(left, RBGTOPO_MAX_STEP_REPLICAS - n);
+        w.role.push_back(cr); w.first.push_back(taken); w.count.push_back(take);
+        n += take;
+        taken += take;
+        if (taken == roles[4 * cr + 1]) { ++cr; taken = 0; }
+      }
+      waves[g].push_back(std::move(w));
+    }
+    W = std::max(W, waves[g].size());
+  }
+  if (gb[4] != pacc) return fail(RBGTOPO_EINVAL, "total pending mismatch");
+
+  // step numbering, wave-major
+  std::vector<std::vector<int>> step_of(ng);
+  int ns = 0;
+  b->wave_begin.assign(1, 0);
+  b->wave_maxp.clear();
+  b->step_group.clear();
+  for (size_t w = 0; w < W; ++w) {
+    int mp = 1;
+    for (int g = 0; g < ng; ++g)
+      if (w < waves[g].size()) {
+        step_of[g].push_back(ns++);
+        b->step_group.push_back(g);
+        mp = std::max(mp, (int)waves[g][w].role.size());
+      }
+    b->wave_begin.push_back(ns);
+    b->wave_maxp.push_back(mp);
+  }
+  blob->assign((size_t)RBGTOPO_HDR_WORDS + (size_t)ns * RBGTOPO_STEP_WORDS, 0);
+  b->out_index.clear();
+  int racc = 0, rowacc = 0;
+  std::vector<int> placed_before;  // per role, replicas in earlier waves
+  for (size_t w = 0; w < W; ++w)
+    for (int g = 0; g < ng; ++g) {
+      if (w >= waves[g].size()) continue;
+      const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
+      const int q = rec[3];
+      const int32_t* roles = gb + rec[4];
+      const int32_t* pair = gb + rec[5];
+      placed_before.assign(q, 0);
+      int i0 = 0;
+      for (size_t w2 = 0; w2 < w; ++w2)
+        for (size_t k = 0; k < waves[g][w2].role.size(); ++k) {
+          placed_before[waves[g][w2].role[k]] += waves[g][w2].count[k];
+          i0 += waves[g][w2].count[k];
+        }
+      const PlanWave& pw = waves[g][w];
+      const int P = (int)pw.role.size();
+      int32_t st[RBGTOPO_STEP_WORDS] = {0};
+      st[0] = rec[0];
+      st[1] = rec[1] & (RBGTOPO_STEP_EXCLUSIVE | RBGTOPO_STEP_GANG);
+      st[2] = (rec[1] & RBGTOPO_STEP_EXCLUSIVE) ? rec[2] : -1;
+      st[3] = P;
+      while (blob->size() & 3) blob->push_back(0);
+      st[4] = (int32_t)blob->size();
+      int n = 0;
+      for (int p = 0; p < P; ++p) {
+        const int ri = pw.role[p];
+        int need = 0;
+        for (int k = 0; k < q; ++k)
+          if (pair[ri * q + k] > 0) need += roles[4 * k + 1] - placed_before[k];
+        need = std::min(need, RBGTOPO_NEED_CAP);
+        blob->push_back(pw.count[p]);
+        blob->push_back(roles[4 * ri + 2]);
+        blob->push_back(need);
+        blob->push_back((roles[4 * ri + 3] & 0xFF) | (ri << 8));
+        n += pw.count[p];
+        int ord0 = 0;
+        for (int k = 0; k < ri; ++k) ord0 += roles[4 * k + 1];
+        for (int k = 0; k < pw.count[p]; ++k) b->out_index.push_back(rec[8] + ord0 + pw.first[p] + k);
+      }
+      st[5] = q;
+      st[6] = (int32_t)blob->size();
+      for (int p = 0; p < P; ++p) blob->insert(blob->end(), pair + pw.role[p] * q, pair + (pw.role[p] + 1) * q);
+      st[7] = rec[6] + i0;
+      st[8] = (int32_t)blob->size();
+      blob->insert(blob->end(), gb + rec[7], gb + rec[7] + 3LL * rec[6]);
+      for (size_t w2 = 0; w2 < w; ++w2)  // one record per replica of the earlier waves, filled on the device
+        for (size_t k = 0; k < waves[g][w2].role.size(); ++k)
+          for (int r = 0; r < waves[g][w2].count[k]; ++r) {
+            blob->push_back(0);
+            blob->push_back(waves[g][w2].role[k]);
+            blob->push_back(1);  // counted by the exactness bound; the device writes 0 for unplaced replicas
+          }
+      st[9] = i0;
+      st[10] = (int32_t)blob->size();
+      blob->insert(blob->end(), (size_t)2 * i0, 0);
+      st[11] = n;
+      st[12] = racc;
+      st[13] = rowacc;
+      st[14] = (w + 1 < waves[g].size()) ? step_of[g][w + 1] : 0;
+      st[15] = i0;
+      racc += n;
+      rowacc += P;
+      memcpy(blob->data() + RBGTOPO_HDR_WORDS + (size_t)step_of[g][w] * RBGTOPO_STEP_WORDS, st, sizeof st);
+    }
+  (*blob)[0] = RBGTOPO_BLOB_MAGIC;
+  (*blob)[1] = RBGTOPO_ABI_VERSION;
+  (*blob)[2] = ns;
+  (*blob)[3] = (int32_t)blob->size();
+  (*blob)[4] = racc;
+  (*blob)[5] = rowacc;
+  (void)c;
+  return RBGTOPO_OK;
+}
+
+// Step-order results of a plan batch (already in b->h_out) -> group order.  Returns
+// the groups the plan could not finish exactly (dirty) in *dirty.
+void plan_results(const Batch* b, int32_t* assign, int32_t* status, int32_t* domain, std::vector<char>* dirty) {
+  const BatchMeta& m = b->m;
+  const int32_t* a = b->h_out.p;
+  const int32_t* st = a + m.total_r;
+  const int32_t* dm = st + m.n_steps;
+  const int ng = (int)b->grp_flags.size();
+  for (int i = 0; i < m.total_r; ++i)
+    if (assign) assign[b->out_index[i]] = a[i];
+  std::vector<int> gstat(ng, 0), gdom(ng, -1);
+  for (int s = 0; s < m.n_steps; ++s) {
+    const int g = b->step_group[s];
+    gstat[g] = std::max(gstat[g], st[s]);
+    if (dm[s] >= 0) gdom[g] = dm[s];
+  }
+  dirty->assign(ng, 0);
+  for (int g = 0; g < ng; ++g) {
+    const bool gang = (b->grp_flags[g] & RBGTOPO_STEP_GANG) != 0;
+    if (gstat[g] == RBGTOPO_GANG_FAILED || (gang && gstat[g] != RBGTOPO_PLACED_ALL)) {
+      if (assign)
+        for (int k = 0; k < b->grp_pending[g]; ++k) assign[b->grp_assign_off[g] + k] = -1;
+      gstat[g] = RBGTOPO_GANG_FAILED;
+      gdom[g] = -1;
+    } else if (gstat[g] == RBGTOPO_PLACED_PART) {
+      (*dirty)[g] = 1;  // `need` of the later waves was predicted with every replica placed
+    }
+    if (status) status[g] = gstat[g];
+    if (domain) domain[g] = (b->grp_flags[g] & RBGTOPO_STEP_EXCLUSIVE) ? gdom[g] : -1;
+  }
+}
+}  // namespace
+
+int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int32_t* assign,
+                             int32_t* status, int32_t* domain) {
+  if (!c || !gb || !assign) return fail(RBGTOPO_EINVAL, "null argument");
+  if (c->cfg.world != 1) return fail(RBGTOPO_EINVAL, "place_groups needs world == 1");
+  std::vector<char> dirty;
+  {
+    std::shared_lock<std::shared_mutex> lk(c->topo_mu);
+    if (!c->topo.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
+    CK(cudaSetDevice(c->cfg.device));
+    Batch* b = nullptr;
+    int rc = acquire_batch(c, &b);
+    if (rc) return rc;
+    std::vector<int32_t> blob;
+    rc = build_plan(c, gb, words, &blob, b);
+    if (!rc) rc = stage_into(c, b, blob.data(), (int64_t)blob.size());
+    if (!rc) rc = run_batch(c, b, 1);
+    if (!rc) rc = fetch_batch(c, b, nullptr, nullptr, nullptr);
+    if (!rc) plan_results(b, assign, status, domain, &dirty);
+    if (rc) cudaStreamSynchronize(stream_of(c, b));
+    release_batch(c, b);
+    if (rc) return rc;
+  }
+  bool any = false;
+  for (char d : dirty) any |= d != 0;
+  if (!any) return RBGTOPO_OK;
+  return place_groups_slow(c, gb, words, assign, status, domain, &dirty);
+}
+
+int32_t rbgtopo_stage_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int32_t* handle) {
+  if (!c || !gb || !handle) return fail(RBGTOPO_EINVAL, "null argument");
+  if (c->cfg.world != 1) return fail(RBGTOPO_EINVAL, "stage_groups needs world == 1");
+  std::shared_lock<std::shared_mutex> lk(c->topo_mu);
+  if (!c->topo.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
+  CK(cudaSetDevice(c->cfg.device));
+  Batch* b = nullptr;
+  int rc = acquire_batch(c, &b);
+  if (rc) return rc;
+  std::vector<int32_t> blob;
+  rc = build_plan(c, gb, words, &blob, b);
+  if (!rc) rc = stage_into(c, b, blob.data(), (int64_t)blob.size());
+  if (rc) {
+    release_batch(c, b);
+    return rc;
+  }
+  CK(cudaStreamSynchronize(stream_of(c, b)));
+  *handle = handle_of(c, b);
+  return RBGTOPO_OK;
 }
 
 int32_t rbgtopo_stage(rbgtopo_ctx* c, const int32_t* blob, int64_t words, int32_t* handle) {
@@ -943,7 +1224,12 @@ int32_t rbgtopo_fetch(rbgtopo_ctx* c, int32_t handle, int32_t* assign, int32_t* 
   Batch* b = batch_of(c, handle);
   if (!b || !b->ran) return fail(RBGTOPO_EINVAL, "handle %d has no results", handle);
   CK(cudaSetDevice(c->cfg.device));
-  return fetch_batch(c, b, assign, status, domain);
+  if (b->wave_begin.empty()) return fetch_batch(c, b, assign, status, domain);
+  int rc = fetch_batch(c, b, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  std::vector<char> dirty;  // plan batches report in group order; unfinished groups keep status 1
+  plan_results(b, assign, status, domain, &dirty);
+  return RBGTOPO_OK;
 }
 
 int32_t rbgtopo_release(rbgtopo_ctx* c, int32_t handle) {

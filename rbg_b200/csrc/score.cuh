@@ -54,7 +54,7 @@ k_score_emit(TopoDev t, BatchDev b, int items) {
     const int rep_off = __ldg(hdr + 12);
     const int gid = h0.x, P = h0.w;
     const bool excl_step = (h0.y & RBGTOPO_STEP_EXCLUSIVE) != 0;
-    const bool sparse = (h1.w | h2.y) != 0;
+    const bool sparse = (h1.w | h2.y) != 0 && !(b.emit_matrix & 2);  // bit 1: background only (plans)
     const int4* __restrict__ roles = reinterpret_cast<const int4*>(blob + h1.x);  // 16-byte aligned (validated)
     const int ch_end = min(b.lc, ch + (item_end - item));
     item += ch_end - ch;

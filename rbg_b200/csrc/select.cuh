@@ -19,15 +19,21 @@ namespace rbgtopo {
 constexpr int DOM_ANY = -2;   // no domain restriction
 constexpr int DOM_NONE = -1;  // exclusive step without any feasible domain: empty list
 
+constexpr int STEP_SKIP = 4;     // internal step flag: an earlier wave of the gang group failed
+constexpr int SEL_CORRECT = 1;   // k_select_assign mode bits: apply the sparse corrections here
+constexpr int SEL_CHAIN = 2;     //   and chain the placements into the group's later waves
+
 struct StepHdr {
-  int gid, flags, fixed_domain, P, role_off, n_anchors, anchor_off, n_cons, cons_off, R, rep_off, rolerow_off;
+  int gid, flags, fixed_domain, P, role_off, Q, pair_off, n_anchors, anchor_off, n_cons, cons_off, R, rep_off,
+      rolerow_off, next_step, i0;
 };
 __device__ __forceinline__ StepHdr load_hdr(const BatchDev& b, int step) {
   const int* hdr = b.blob + RBGTOPO_HDR_WORDS + (size_t)step * RBGTOPO_STEP_WORDS;
   StepHdr h;
   h.gid = hdr[0]; h.flags = hdr[1]; h.fixed_domain = hdr[2]; h.P = hdr[3]; h.role_off = hdr[4];
-  h.n_anchors = hdr[7]; h.anchor_off = hdr[8];
+  h.Q = hdr[5]; h.pair_off = hdr[6]; h.n_anchors = hdr[7]; h.anchor_off = hdr[8];
   h.n_cons = hdr[9]; h.cons_off = hdr[10]; h.R = hdr[11]; h.rep_off = hdr[12]; h.rolerow_off = hdr[13];
+  h.next_step = hdr[14]; h.i0 = hdr[15];
   return h;
 }
 // K of role row p = replicas of the step up to and including role p (spec §3.5)
@@ -68,6 +74,65 @@ __device__ __forceinline__ void build_candidates(const TopoDev& t, const BatchDe
   for (int c = threadIdx.x; c < h.n_cons; c += blockDim.x) {
     const int m = con[2 * c];
     if (m >= t.slab_lo && m < t.slab_hi) cand[atomicAdd(sCnt, 1)] = m;
+  }
+}
+
+__device__ __forceinline__ void sel_red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// The sparse corrections of one step over this rank's whole slab (the same ones
+// k_score_emit applies per chunk, score.cuh): -inf where consumed capacity makes a
+// node infeasible, pair*c*w reductions for the anchors' closed neighbourhoods.
+// Called by every warp of the CTA after the background rows exist in memory.
+__device__ __forceinline__ void correct_step(const TopoDev& t, const BatchDev& b, const StepHdr& h) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const size_t stride = (size_t)t.slab_stride;
+  float* const mrow0 = b.matrix + (size_t)h.rep_off * stride - t.slab_lo;  // mrow0[node]
+  const int* con = b.blob + h.cons_off;
+  for (int c = threadIdx.x; c < h.n_cons; c += blockDim.x) {
+    const int m = con[2 * c];
+    if (m >= t.slab_lo && m < t.slab_hi && con[2 * c + 1] > 0) {
+      int amt = 0;
+      for (int k = 0; k < h.n_cons; ++k)
+        if (con[2 * k] == m) amt += con[2 * k + 1];
+      const int avail = t.free_[m] - amt;
+      float* rowp = mrow0 + m;
+      for (int p = 0; p < h.P; ++p) {
+        const int count = b.blob[h.role_off + 4 * p], demand = b.blob[h.role_off + 4 * p + 1];
+        if (avail < demand)
+          for (int k = 0; k < count; ++k) rowp[(size_t)k * stride] = -INFINITY;
+        rowp += (size_t)count * stride;
+      }
+    }
+  }
+  const int* anc = b.blob + h.anchor_off;
+  for (int a = warp; a < h.n_anchors; a += nwarps) {
+    const int m = anc[3 * a], q = anc[3 * a + 1], c = anc[3 * a + 2];
+    if (c == 0) continue;
+    const int rb = t.row_ptr[m], re = t.row_ptr[m + 1];
+    for (int j = rb + lane; j <= re; j += 32) {  // j == re stands for the self term
+      int nn, wv;
+      if (j < re) {
+        nn = t.col[j];
+        wv = t.w[j] * c;
+      } else {
+        nn = m;
+        wv = RBGTOPO_SELF_W * c;
+      }
+      if (nn >= t.slab_lo && nn < t.slab_hi) {
+        float* rowp = mrow0 + nn;
+        for (int p = 0; p < h.P; ++p) {
+          const int count = b.blob[h.role_off + 4 * p];
+          const int coef = b.blob[h.pair_off + p * h.Q + q];
+          if (coef) {
+            const float add = (float)(coef * wv);
+            for (int k = 0; k < count; ++k) sel_red_add_f32(rowp + (size_t)k * stride, add);
+          }
+          rowp += (size_t)count * stride;
+        }
+      }
+    }
   }
 }
 
@@ -186,9 +251,13 @@ __device__ __forceinline__ void select_role(const TopoDev& t, const BatchDev& b,
 }
 
 // Greedy in replica order on the step's final lists (spec §3.6).  One warp.
+// With `chain` the placements are written into the later waves of the same group
+// (device-resident multi-wave plans, rbgtopo.cu build_plan): anchor record
+// n_static + i and consumed record i of every later step, the exclusive domain,
+// and the SKIP flag when a gang group failed.
 __device__ __forceinline__ void greedy_step(const TopoDev& t, const BatchDev& b, int step, const StepHdr& h,
                                             const unsigned long long (*sList)[KS], int* sTakenNode,
-                                            int* sTakenAmt, int dstar) {
+                                            int* sTakenAmt, int dstar, bool chain = false) {
   const int lane = threadIdx.x & 31;
   const int* con = b.blob + h.cons_off;
   int ntaken = 0, unplaced = 0, r = 0;
@@ -235,6 +304,41 @@ __device__ __forceinline__ void greedy_step(const TopoDev& t, const BatchDev& b,
     b.domain_out[step] = dstar;
     b.dstar[step] = dstar;
   }
+  if (chain && h.next_step > 0) {
+    __syncwarp();
+    int* wb = const_cast<int*>(b.blob);
+    const bool excl = (h.flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
+    const bool dead = status == RBGTOPO_GANG_FAILED;
+    bool any = false;
+    for (int i = 0; i < h.R; ++i) any |= b.assign[h.rep_off + i] >= 0;
+    const int fixed = excl ? ((dstar >= 0 && any) ? dstar : h.fixed_domain) : -1;
+    for (int s2 = h.next_step; s2 > 0;) {
+      int* hd = wb + RBGTOPO_HDR_WORDS + (size_t)s2 * RBGTOPO_STEP_WORDS;
+      const int n_static = hd[7] - hd[15];  // n_anchors - replicas of the earlier waves
+      int rr = 0;
+      for (int p = 0; p < h.P; ++p) {
+        const int count = b.blob[h.role_off + 4 * p], demand = b.blob[h.role_off + 4 * p + 1];
+        const int q = (b.blob[h.role_off + 4 * p + 3] >> 8) & 0xFF;
+        for (int c = lane; c < count; c += 32) {
+          const int node = b.assign[h.rep_off + rr + c];
+          int* ar = wb + hd[8] + 3 * (n_static + h.i0 + rr + c);
+          int* cr = wb + hd[10] + 2 * (h.i0 + rr + c);
+          ar[0] = node >= 0 ? node : 0;
+          ar[1] = q;
+          ar[2] = node >= 0 ? 1 : 0;
+          cr[0] = node >= 0 ? node : 0;
+          cr[1] = node >= 0 ? demand : 0;
+        }
+        rr += count;
+      }
+      const int nxt = hd[14];
+      if (lane == 0) {
+        hd[2] = fixed;
+        hd[1] = dead ? (hd[1] | STEP_SKIP) : (hd[1] & ~STEP_SKIP);
+      }
+      s2 = nxt;
+    }
+  }
 }
 
 // ---- world == 1: select + exclusive domain + greedy fused, one CTA per step,
@@ -260,7 +364,7 @@ __device__ __forceinline__ CandRef stage_candidates(const TopoDev& t, const Batc
   return r;
 }
 
-__global__ void __launch_bounds__(32 * MAXP) k_select_assign(TopoDev t, BatchDev b) {
+__global__ void __launch_bounds__(32 * MAXP) k_select_assign(TopoDev t, BatchDev b, int step_begin, int mode) {
   extern __shared__ __align__(16) unsigned char sel_smem[];
   int* sCand = reinterpret_cast<int*>(sel_smem);
   unsigned long long* sKeys = reinterpret_cast<unsigned long long*>(sel_smem + (size_t)CAND_CAP * 4);
@@ -270,9 +374,24 @@ __global__ void __launch_bounds__(32 * MAXP) k_select_assign(TopoDev t, BatchDev
   __shared__ int sTakenNode[KS], sTakenAmt[KS];
   __shared__ int sDstar, sCnt;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int step = blockIdx.x;
+  const int step = step_begin + blockIdx.x;
   const StepHdr h = load_hdr(b, step);
   const bool excl_step = (h.flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
+  if (h.flags & STEP_SKIP) {  // an earlier wave of this gang group failed: nothing is placed
+    if (warp == 0) {
+      for (int i = lane; i < h.R; i += 32) b.assign[h.rep_off + i] = -1;
+      if (lane == 0) {
+        b.status[step] = RBGTOPO_GANG_FAILED;
+        b.domain_out[step] = -1;
+        b.dstar[step] = -1;
+      }
+    }
+    return;
+  }
+  if (mode & SEL_CORRECT) {
+    correct_step(t, b, h);
+    __threadfence();  // the reductions have landed before any read-back below
+  }
   const CandRef cr = stage_candidates(t, b, step, h, sCand, &sCnt);
   const int* cand = cr.p;
   const int cnt = cr.cnt;
@@ -303,7 +422,7 @@ __global__ void __launch_bounds__(32 * MAXP) k_select_assign(TopoDev t, BatchDev
     b.merged[(size_t)(h.rolerow_off + p) * KS + lane] = sList[p][lane];
   }
   __syncthreads();
-  if (warp == 0) greedy_step(t, b, step, h, sList, sTakenNode, sTakenAmt, dstar);
+  if (warp == 0) greedy_step(t, b, step, h, sList, sTakenNode, sTakenAmt, dstar, (mode & SEL_CHAIN) != 0);
 }
 
 // ---- world > 1, pass 1 (pass2 == 0): rank-local lists of every role row; roles

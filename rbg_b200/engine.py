@@ -100,6 +100,15 @@ class TopoPlacer:
         self._staged_totals[h.value] = blob_totals(blob)
         return h.value
 
+    def stage_groups(self, groups_blob: np.ndarray) -> int:
+        """Compile whole groups into a device-resident multi-wave plan (see rbgtopo.h)."""
+        gb = _i32(groups_blob)
+        h = C.c_int32(-1)
+        self._check(self.lib.rbgtopo_stage_groups(self._h, _p(gb), len(gb), C.byref(h)))
+        self._staged_totals = getattr(self, "_staged_totals", {})
+        self._staged_totals[h.value] = (int(gb[2]), int(gb[4]), 0)   # fetch: per group / per pending replica
+        return h.value
+
     def run_staged(self, handle: int, iters: int = 1) -> None:
         self._check(self.lib.rbgtopo_run_staged(self._h, handle, iters))
 
@@ -159,7 +168,7 @@ class TopoPlacer:
     def last_timing(self) -> dict:
         t = _lib.Timing()
         self._check(self.lib.rbgtopo_last_timing(self._h, C.byref(t)))
-        return {k: getattr(t, k) for k, _ in _lib.Timing._fields_ if k != "reserved"}
+        return {k: getattr(t, k) for k, _ in _lib.Timing._fields_}
 
     def stats(self) -> dict:
         g, c, s, k = C.c_uint64(), C.c_int64(), C.c_int64(), C.c_int64()
