@@ -6,6 +6,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -958,7 +959,12 @@ static int32_t place_groups_slow(rbgtopo_ctx* c, const int32_t* gb, int64_t word
 // fails (non-gang groups with an unplaced replica) are re-run through the
 // host-driven loop afterwards (place_groups_slow) — rare, and exact either way.
 namespace {
-struct PlanWave { std::vector<int> role, first, count; };
+struct PlanWave {  // <= RBGTOPO_MAX_STEP_ROLES entries, no heap
+  int n = 0;
+  int role[RBGTOPO_MAX_STEP_ROLES], first[RBGTOPO_MAX_STEP_ROLES], count[RBGTOPO_MAX_STEP_ROLES];
+  void push(int r, int f, int c) { role[n] = r; first[n] = f; count[n] = c; ++n; }
+  int size() const { return n; }
+};
 
 int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, std::vector<int32_t>* blob, Batch* b) {
   if (words < RBGTOPO_HDR_WORDS || gb[0] != RBGTOPO_GROUPS_MAGIC || gb[1] != RBGTOPO_ABI_VERSION || gb[3] != words)
@@ -967,7 +973,11 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, std::vector<int
   if (ng < 0 || (int64_t)RBGTOPO_HDR_WORDS + (int64_t)ng * RBGTOPO_GROUP_WORDS > words)
     return fail(RBGTOPO_EINVAL, "group table exceeds blob");
   auto in = [&](long long off, long long cnt) { return off >= 0 && cnt >= 0 && off + cnt <= words; };
-  std::vector<std::vector<PlanWave>> waves(ng);
+  // flat wave table (thread-local scratch keeps its capacity across calls)
+  static thread_local std::vector<PlanWave> wv;
+  static thread_local std::vector<int> wv_off, step_flat;
+  wv.clear();
+  wv_off.assign((size_t)ng + 1, 0);
   size_t W = 0;
   long long pacc = 0;
   b->grp_flags.assign(ng, 0);
@@ -998,24 +1008,27 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, std::vector<int
       PlanWave w;
       const int level = roles[4 * cr];
       int n = 0;
-      while (cr < q && roles[4 * cr] == level && n < RBGTOPO_MAX_STEP_REPLICAS &&
-             (int)w.role.size() < RBGTOPO_MAX_STEP_ROLES) {
+      while (cr < q && roles[4 * cr] == level && n < RBGTOPO_MAX_STEP_REPLICAS && w.size() < RBGTOPO_MAX_STEP_ROLES) {
         const int left = roles[4 * cr + 1] - taken;
         if (left <= 0) { ++cr; taken = 0; continue; }
         const int take = std::min(left, RBGTOPO_MAX_STEP_REPLICAS - n);
-        w.role.push_back(cr); w.first.push_back(taken); w.count.push_back(take);
+        w.push(cr, taken, take);
         n += take;
         taken += take;
         if (taken == roles[4 * cr + 1]) { ++cr; taken = 0; }
       }
-      waves[g].push_back(std::move(w));
+      wv.push_back(w);
     }
-    W = std::max(W, waves[g].size());
+    wv_off[g + 1] = (int)wv.size();
+    W = std::max(W, (size_t)(wv_off[g + 1] - wv_off[g]));
   }
+  auto nwaves = [&](int g) { return (size_t)(wv_off[g + 1] - wv_off[g]); };
+  auto wave = [&](int g, size_t w) -> const PlanWave& { return wv[wv_off[g] + w]; };
   if (gb[4] != pacc) return fail(RBGTOPO_EINVAL, "total pending mismatch");
 
-  // step numbering, wave-major
-  std::vector<std::vector<int>> step_of(ng);
+  // step numbering, wave-major: step_flat[wv_off[g] + w]
+  step_flat.assign(wv.size(), 0);
+  auto step_of = [&](int g, size_t w) -> int& { return step_flat[wv_off[g] + w]; };
   int ns = 0;
   b->wave_begin.assign(1, 0);
   b->wave_maxp.clear();
@@ -1023,82 +1036,111 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, std::vector<int
   for (size_t w = 0; w < W; ++w) {
     int mp = 1;
     for (int g = 0; g < ng; ++g)
-      if (w < waves[g].size()) {
-        step_of[g].push_back(ns++);
+      if (w < nwaves(g)) {
+        step_of(g, w) = ns++;
         b->step_group.push_back(g);
-        mp = std::max(mp, (int)waves[g][w].role.size());
+        mp = std::max(mp, wave(g, w).size());
       }
     b->wave_begin.push_back(ns);
     b->wave_maxp.push_back(mp);
   }
-  blob->assign((size_t)RBGTOPO_HDR_WORDS + (size_t)ns * RBGTOPO_STEP_WORDS, 0);
-  b->out_index.clear();
-  int racc = 0, rowacc = 0;
-  std::vector<int> placed_before;  // per role, replicas in earlier waves
-  for (size_t w = 0; w < W; ++w)
-    for (int g = 0; g < ng; ++g) {
-      if (w >= waves[g].size()) continue;
-      const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
-      const int q = rec[3];
-      const int32_t* roles = gb + rec[4];
-      const int32_t* pair = gb + rec[5];
-      placed_before.assign(q, 0);
-      int i0 = 0;
-      for (size_t w2 = 0; w2 < w; ++w2)
-        for (size_t k = 0; k < waves[g][w2].role.size(); ++k) {
-          placed_before[waves[g][w2].role[k]] += waves[g][w2].count[k];
-          i0 += waves[g][w2].count[k];
-        }
-      const PlanWave& pw = waves[g][w];
-      const int P = (int)pw.role.size();
-      int32_t st[RBGTOPO_STEP_WORDS] = {0};
+  // pass 1 (step order): section sizes -> offsets, replica / role-row prefixes
+  static thread_local std::vector<int> sec_off, rep_off, row_off;
+  sec_off.assign((size_t)ns + 1, 0);
+  rep_off.assign((size_t)ns + 1, 0);
+  row_off.assign((size_t)ns + 1, 0);
+  {
+    long long off = (long long)RBGTOPO_HDR_WORDS + (long long)ns * RBGTOPO_STEP_WORDS;  // multiple of 4
+    int s = 0;
+    static thread_local std::vector<int> i0_of;  // per group, replicas before the current wave
+    i0_of.assign(ng, 0);
+    for (size_t w = 0; w < W; ++w)
+      for (int g = 0; g < ng; ++g) {
+        if (w >= nwaves(g)) continue;
+        const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
+        const PlanWave& pw = wave(g, w);
+        int n = 0;
+        for (int k = 0; k < pw.size(); ++k) n += pw.count[k];
+        const int i0 = i0_of[g];
+        long long sz = 4LL * pw.size() + (long long)pw.size() * rec[3] + 3LL * (rec[6] + i0) + 2LL * i0;
+        sz = (sz + 3) & ~3LL;  // keeps every role section 16-byte aligned
+        sec_off[s] = (int)off;
+        off += sz;
+        rep_off[s + 1] = rep_off[s] + n;
+        row_off[s + 1] = row_off[s] + pw.size();
+        i0_of[g] = i0 + n;
+        ++s;
+      }
+    if (off > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "plan blob exceeds 2^31 words");
+    sec_off[ns] = (int)off;
+  }
+  blob->assign((size_t)sec_off[ns], 0);
+  b->out_index.assign((size_t)pacc, 0);
+  int32_t* const out = blob->data();
+  // pass 2 (group order): fill every step of a group while walking its waves once
+  for (int g = 0; g < ng; ++g) {
+    const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
+    const int q = rec[3], na = rec[6];
+    const int32_t* roles = gb + rec[4];
+    const int32_t* pair = gb + rec[5];
+    int placed_before[RBGTOPO_MAX_GROUP_ROLES] = {0};
+    int ord0[RBGTOPO_MAX_GROUP_ROLES];
+    for (int k = 0, acc = 0; k < q; ++k) { ord0[k] = acc; acc += roles[4 * k + 1]; }
+    int i0 = 0;
+    for (size_t w = 0; w < nwaves(g); ++w) {
+      const PlanWave& pw = wave(g, w);
+      const int P = pw.size();
+      const int s = step_of(g, w);
+      int32_t* st = out + RBGTOPO_HDR_WORDS + (size_t)s * RBGTOPO_STEP_WORDS;
+      int32_t* p = out + sec_off[s];
       st[0] = rec[0];
       st[1] = rec[1] & (RBGTOPO_STEP_EXCLUSIVE | RBGTOPO_STEP_GANG);
       st[2] = (rec[1] & RBGTOPO_STEP_EXCLUSIVE) ? rec[2] : -1;
       st[3] = P;
-      while (blob->size() & 3) blob->push_back(0);
-      st[4] = (int32_t)blob->size();
+      st[4] = (int32_t)(p - out);
       int n = 0;
-      for (int p = 0; p < P; ++p) {
-        const int ri = pw.role[p];
+      int* oi = b->out_index.data() + rep_off[s];
+      for (int k = 0; k < P; ++k) {
+        const int ri = pw.role[k];
         int need = 0;
-        for (int k = 0; k < q; ++k)
-          if (pair[ri * q + k] > 0) need += roles[4 * k + 1] - placed_before[k];
-        need = std::min(need, RBGTOPO_NEED_CAP);
-        blob->push_back(pw.count[p]);
-        blob->push_back(roles[4 * ri + 2]);
-        blob->push_back(need);
-        blob->push_back((roles[4 * ri + 3] & 0xFF) | (ri << 8));
-        n += pw.count[p];
-        int ord0 = 0;
-        for (int k = 0; k < ri; ++k) ord0 += roles[4 * k + 1];
-        for (int k = 0; k < pw.count[p]; ++k) b->out_index.push_back(rec[8] + ord0 + pw.first[p] + k);
+        for (int j = 0; j < q; ++j)
+          if (pair[ri * q + j] > 0) need += roles[4 * j + 1] - placed_before[j];
+        *p++ = pw.count[k];
+        *p++ = roles[4 * ri + 2];
+        *p++ = std::min(need, RBGTOPO_NEED_CAP);
+        *p++ = (roles[4 * ri + 3] & 0xFF) | (ri << 8);
+        for (int c2 = 0; c2 < pw.count[k]; ++c2) *oi++ = rec[8] + ord0[ri] + pw.first[k] + c2;
+        n += pw.count[k];
       }
       st[5] = q;
-      st[6] = (int32_t)blob->size();
-      for (int p = 0; p < P; ++p) blob->insert(blob->end(), pair + pw.role[p] * q, pair + (pw.role[p] + 1) * q);
-      st[7] = rec[6] + i0;
-      st[8] = (int32_t)blob->size();
-      blob->insert(blob->end(), gb + rec[7], gb + rec[7] + 3LL * rec[6]);
+      st[6] = (int32_t)(p - out);
+      for (int k = 0; k < P; ++k) {
+        memcpy(p, pair + pw.role[k] * q, (size_t)q * 4);
+        p += q;
+      }
+      st[7] = na + i0;
+      st[8] = (int32_t)(p - out);
+      memcpy(p, gb + rec[7], (size_t)na * 12);
+      p += 3 * na;
       for (size_t w2 = 0; w2 < w; ++w2)  // one record per replica of the earlier waves, filled on the device
-        for (size_t k = 0; k < waves[g][w2].role.size(); ++k)
-          for (int r = 0; r < waves[g][w2].count[k]; ++r) {
-            blob->push_back(0);
-            blob->push_back(waves[g][w2].role[k]);
-            blob->push_back(1);  // counted by the exactness bound; the device writes 0 for unplaced replicas
+        for (int k = 0; k < wave(g, w2).size(); ++k)
+          for (int r = 0; r < wave(g, w2).count[k]; ++r) {
+            *p++ = 0;
+            *p++ = wave(g, w2).role[k];
+            *p++ = 1;  // counted by the exactness bound; the device writes 0 for unplaced replicas
           }
       st[9] = i0;
-      st[10] = (int32_t)blob->size();
-      blob->insert(blob->end(), (size_t)2 * i0, 0);
+      st[10] = (int32_t)(p - out);  // consumed records stay zero until the device fills them
       st[11] = n;
-      st[12] = racc;
-      st[13] = rowacc;
-      st[14] = (w + 1 < waves[g].size()) ? step_of[g][w + 1] : 0;
+      st[12] = rep_off[s];
+      st[13] = row_off[s];
+      st[14] = (w + 1 < nwaves(g)) ? step_of(g, w + 1) : 0;
       st[15] = i0;
-      racc += n;
-      rowacc += P;
-      memcpy(blob->data() + RBGTOPO_HDR_WORDS + (size_t)step_of[g][w] * RBGTOPO_STEP_WORDS, st, sizeof st);
+      for (int k = 0; k < P; ++k) placed_before[pw.role[k]] += pw.count[k];
+      i0 += n;
     }
+  }
+  const int racc = rep_off[ns], rowacc = row_off[ns];
   (*blob)[0] = RBGTOPO_BLOB_MAGIC;
   (*blob)[1] = RBGTOPO_ABI_VERSION;
   (*blob)[2] = ns;
@@ -1154,12 +1196,24 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
     Batch* b = nullptr;
     int rc = acquire_batch(c, &b);
     if (rc) return rc;
-    std::vector<int32_t> blob;
+    static thread_local std::vector<int32_t> blob;
+    static const bool prof = getenv("RBGTOPO_PROFILE_HOST") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t0 = now();
     rc = build_plan(c, gb, words, &blob, b);
+    auto t1 = now();
     if (!rc) rc = stage_into(c, b, blob.data(), (int64_t)blob.size());
+    auto t2 = now();
     if (!rc) rc = run_batch(c, b, 1);
+    auto t3 = now();
     if (!rc) rc = fetch_batch(c, b, nullptr, nullptr, nullptr);
+    auto t4 = now();
     if (!rc) plan_results(b, assign, status, domain, &dirty);
+    if (prof) {
+      auto us = [](auto a, auto b2) { return std::chrono::duration<double, std::micro>(b2 - a).count(); };
+      fprintf(stderr, "[rbgtopo host] build %.0f us, validate+stage %.0f us, enqueue %.0f us, wait+fetch %.0f us, results %.0f us\n",
+              us(t0, t1), us(t1, t2), us(t2, t3), us(t3, t4), us(t4, now()));
+    }
     if (rc) cudaStreamSynchronize(stream_of(c, b));
     release_batch(c, b);
     if (rc) return rc;
