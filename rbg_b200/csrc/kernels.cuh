@@ -58,6 +58,7 @@ struct BatchDev {
   float* matrix;              // [total R][slab_stride]
   int* cand;                  // per-step scratch: patched slab nodes (select.cuh)
   const int* poff;            // [n_steps + 1] scratch offsets (host prefix of the caps)
+  const int* cta_item;        // [grid + 1] byte-balanced (step, chunk) item ranges of k_score_emit
   unsigned long long* lists;  // [rolerows][KS] rank-local top-K per role row
   const unsigned long long* lists_all;  // [parts][rolerows][KS]
   long long part_stride;                // u64 elements between parts

@@ -105,6 +105,7 @@ struct BatchMeta {
   long long algo_bytes = 0;
   long long patch_cap = 0;   // sum of the per-step patch-list capacities
   std::vector<int> poff;     // [n_steps + 1] patch-list offsets
+  std::vector<int> cta_item; // [emit_grid + 1] byte-balanced item ranges of k_score_emit
 };
 
 struct Batch {
@@ -142,6 +143,7 @@ struct rbgtopo_ctx {
   rbgtopo_config cfg{};
   int sm_count = 148;
   int slab_lo = 0, slab_hi = 0, slab_stride = 0, lc = 1, chunk = 2048;
+  int emit_grid = 148;  // persistent CTAs of k_score_emit (SMs x occupancy)
   std::shared_mutex topo_mu;  // update = exclusive, score calls = shared
   std::mutex pool_mu;
   Topology topo;
@@ -313,6 +315,28 @@ int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, Batc
     if ((st[1] & RBGTOPO_STEP_EXCLUSIVE) && st[2] < 0) m->any_excl_unknown = true;
   }
   if (blob[4] != racc || blob[5] != pacc) return fail(RBGTOPO_EINVAL, "blob totals mismatch");
+  // byte-balanced work split of k_score_emit: an item (step, chunk) weighs R_step rows
+  {
+    const int G = std::max(1, c->emit_grid), lc = c->lc;
+    const long long total_w = racc * lc;
+    m->cta_item.assign((size_t)G + 1, ns * lc);
+    int s = 0;
+    for (int g = 0; g < G; ++g) {
+      const long long target = total_w * g / G;
+      while (s < ns) {  // advance to the step containing `target`
+        const int32_t* st = blob + RBGTOPO_HDR_WORDS + (int64_t)s * RBGTOPO_STEP_WORDS;
+        if ((long long)(st[12] + st[11]) * lc > target) break;
+        ++s;
+      }
+      if (s >= ns) break;
+      const int32_t* st = blob + RBGTOPO_HDR_WORDS + (int64_t)s * RBGTOPO_STEP_WORDS;
+      const long long before = (long long)st[12] * lc;
+      int ch = (int)((target - before + st[11] - 1) / st[11]);  // first chunk at or past the target
+      if (target <= before) ch = 0;
+      m->cta_item[g] = s * lc + std::min(ch, lc);
+    }
+    m->cta_item[0] = 0;
+  }
   m->n_steps = ns;
   m->total_r = (int)racc;
   m->total_p = (int)pacc;
@@ -360,7 +384,7 @@ int stage_into(rbgtopo_ctx* c, Batch* b, const int32_t* blob, int64_t words) {
   if (rc) return rc;
   const BatchMeta& m = b->m;
   cudaStream_t s = stream_of(c, b);
-  const size_t in_words = (size_t)words + (size_t)m.n_steps + 1;  // blob | poff
+  const size_t in_words = (size_t)words + (size_t)m.n_steps + 1 + m.cta_item.size();  // blob | poff | cta_item
   CK(b->blob.reserve(in_words));
   CK(b->h_in.reserve(in_words));
   CK(b->matrix.reserve((size_t)std::max(1, m.total_r) * c->slab_stride));
@@ -374,6 +398,7 @@ int stage_into(rbgtopo_ctx* c, Batch* b, const int32_t* blob, int64_t words) {
   CK(cudaEventRecord(b->ev[0], s));
   memcpy(b->h_in.p, blob, (size_t)words * 4);
   memcpy(b->h_in.p + words, m.poff.data(), ((size_t)m.n_steps + 1) * 4);
+  memcpy(b->h_in.p + words + m.n_steps + 1, m.cta_item.data(), m.cta_item.size() * 4);
   CK(cudaMemcpyAsync(b->blob.p, b->h_in.p, in_words * 4, cudaMemcpyHostToDevice, s));
   CK(cudaEventRecord(b->ev[1], s));
   b->staged = true;
@@ -395,6 +420,7 @@ BatchDev batch_dev(rbgtopo_ctx* c, Batch* b) {
   d.matrix = b->matrix.p;
   d.cand = b->cand.p;
   d.poff = b->blob.p + b->m.words;
+  d.cta_item = d.poff + b->m.n_steps + 1;
   d.lists = b->lists.p;
   d.lists_all = b->lists.p;
   d.part_stride = 0;
@@ -413,10 +439,7 @@ int launch_score(rbgtopo_ctx* c, Batch* b, cudaStream_t s) {
   const BatchMeta& m = b->m;
   if (m.n_steps == 0) return RBGTOPO_OK;
   const int items = m.n_steps * c->lc;
-  int occ = 1;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_emit, SCORE_THREADS, 0));
-  occ = std::max(1, occ);
-  const int grid = std::min(items, c->sm_count * occ);
+  const int grid = c->emit_grid;
   k_score_emit<<<grid, SCORE_THREADS, 0, s>>>(topo_dev(c), batch_dev(c, b), items);
   return RBGTOPO_OK;
 }
@@ -582,6 +605,11 @@ int32_t rbgtopo_create(const rbgtopo_config* cfg, rbgtopo_ctx** out) {
   c->cfg = *cfg;
   c->cfg.emit_matrix = 1;  // the dense matrix is always materialised (selection reads patched scores back)
   c->sm_count = prop.multiProcessorCount;
+  {
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_emit, SCORE_THREADS, 0));
+    c->emit_grid = c->sm_count * std::max(1, occ);
+  }
   *out = c.release();
   return RBGTOPO_OK;
 }

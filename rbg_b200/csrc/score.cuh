@@ -28,66 +28,43 @@ namespace rbgtopo {
 
 constexpr int GPT = 2;  // float4 groups per thread: chunk <= 256 * 4 * GPT = 2048
 
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
 __global__ void __launch_bounds__(SCORE_THREADS, 6)
 k_score_emit(TopoDev t, BatchDev b, int items) {
-  const int T = b.chunk;
+  const int T = b.chunk, lc = b.lc;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int groups = T >> 2;
   const int* __restrict__ blob = b.blob;
   const size_t stride = (size_t)t.slab_stride;
+  const bool background_only = (b.emit_matrix & 2) != 0;  // plans: corrections are applied per wave
 
-  const int per = (items + gridDim.x - 1) / gridDim.x;
-  const int item0 = blockIdx.x * per;
-  const int item_end = min(items, item0 + per);
+  // contiguous, byte-balanced item ranges (host: validate_blob): an item weighs the
+  // replica rows of its step, so every CTA writes the same number of bytes
+  const int item0 = __ldg(b.cta_item + blockIdx.x);
+  const int item_end = min(items, __ldg(b.cta_item + blockIdx.x + 1));
   if (item0 >= item_end) return;
-  int step = item0 / b.lc, ch = item0 - step * b.lc;
-  for (int item = item0; item < item_end; ++step, ch = 0) {
-    // ---- step-level state, shared by the step's chunks
-    const int* __restrict__ hdr = blob + RBGTOPO_HDR_WORDS + (size_t)step * RBGTOPO_STEP_WORDS;
-    const int4 h0 = __ldg(reinterpret_cast<const int4*>(hdr));      // gid flags fixed P
-    const int4 h1 = __ldg(reinterpret_cast<const int4*>(hdr) + 1);  // role_off Q pair_off n_anchors
-    const int4 h2 = __ldg(reinterpret_cast<const int4*>(hdr) + 2);  // anchor_off n_cons cons_off R
-    const int rep_off = __ldg(hdr + 12);
-    const int gid = h0.x, P = h0.w;
-    const bool excl_step = (h0.y & RBGTOPO_STEP_EXCLUSIVE) != 0;
-    const bool sparse = (h1.w | h2.y) != 0 && !(b.emit_matrix & 2);  // bit 1: background only (plans)
-    const int4* __restrict__ roles = reinterpret_cast<const int4*>(blob + h1.x);  // 16-byte aligned (validated)
-    const int ch_end = min(b.lc, ch + (item_end - item));
-    item += ch_end - ch;
-
-    // register double buffer: the next chunk's base/free vectors are requested
-    // before the current chunk is streamed, so their latency hides behind the stores
-    float4 nb4[GPT];
-    int4 nav[GPT];
-    auto prefetch = [&](int chn) {
-      const int m0 = t.slab_lo + chn * T;
-#pragma unroll
-      for (int j = 0; j < GPT; ++j) {
-        const int g = tid + j * SCORE_THREADS;
-        const int n = m0 + (g << 2);
-        if (g < groups && n < t.slab_hi) {
-          nb4[j] = __ldg(reinterpret_cast<const float4*>(t.base + n));
-          nav[j] = __ldg(reinterpret_cast<const int4*>(t.free_ + n));  // padded past n: safe
-        }
-      }
-    };
-    prefetch(ch);
-    for (; ch < ch_end; ++ch) {
+  int step = item0 / lc, ch = item0 - step * lc;
+  for (int item = item0; item < item_end; ++item) {
+    {
+      const int* __restrict__ hdr = blob + RBGTOPO_HDR_WORDS + (size_t)step * RBGTOPO_STEP_WORDS;
+      const int4 h0 = __ldg(reinterpret_cast<const int4*>(hdr));      // gid flags fixed P
+      const int4 h1 = __ldg(reinterpret_cast<const int4*>(hdr) + 1);  // role_off Q pair_off n_anchors
+      const int4 h2 = __ldg(reinterpret_cast<const int4*>(hdr) + 2);  // anchor_off n_cons cons_off R
+      const int rep_off = __ldg(hdr + 12);
+      const int gid = h0.x, P = h0.w;
+      const bool excl_step = (h0.y & RBGTOPO_STEP_EXCLUSIVE) != 0;
+      const bool sparse = (h1.w | h2.y) != 0 && !background_only;
+      const int4* __restrict__ roles = reinterpret_cast<const int4*>(blob + h1.x);  // 16-byte aligned (validated)
       const int n0 = t.slab_lo + ch * T;
       const int n1 = min(n0 + T, t.slab_hi);
       float* const mrow0 = b.matrix + (size_t)rep_off * stride + (n0 - t.slab_lo);
-      float4 cb4[GPT];
-      int4 cav[GPT];
-#pragma unroll
-      for (int j = 0; j < GPT; ++j) {
-        cb4[j] = nb4[j];
-        cav[j] = nav[j];
-      }
-      if (ch + 1 < ch_end) prefetch(ch + 1);
 
       // ---- 1. background rows
 #pragma unroll
@@ -95,8 +72,8 @@ k_score_emit(TopoDev t, BatchDev b, int items) {
         const int g = tid + j * SCORE_THREADS;
         const int n = n0 + (g << 2);
         if (g < groups && n < n1) {
-          const float4 base4 = cb4[j];
-          int4 av = cav[j];
+          const float4 base4 = __ldg(reinterpret_cast<const float4*>(t.base + n));
+          int4 av = __ldg(reinterpret_cast<const int4*>(t.free_ + n));  // padded past n: safe
           if (n + 4 > n1) {  // only in the slab's last group: lanes past the slab are infeasible
             if (n + 1 >= n1) av.y = -1;
             if (n + 2 >= n1) av.z = -1;
@@ -182,6 +159,10 @@ k_score_emit(TopoDev t, BatchDev b, int items) {
           }
         }
       }
+    }
+    if (++ch == lc) {
+      ch = 0;
+      ++step;
     }
   }
 }
