@@ -20,6 +20,7 @@
 #include "kernels.cuh"
 #include "score.cuh"
 #include "select.cuh"
+#include "select_fast.cuh"
 
 using namespace rbgtopo;
 
@@ -104,6 +105,7 @@ struct BatchMeta {
   long long scores = 0;      // sum R * N
   long long algo_bytes = 0;
   long long patch_cap = 0;   // sum of the per-step patch-list capacities
+  int max_cap = 0;           // largest per-step capacity (sizes the shared-memory hash table)
   std::vector<int> poff;     // [n_steps + 1] patch-list offsets
   std::vector<int> cta_item; // [emit_grid + 1] byte-balanced item ranges of k_score_emit
 };
@@ -158,6 +160,7 @@ struct rbgtopo_ctx {
 namespace {
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+constexpr size_t kFastSmemMax = 96 * 1024;  // opt-in dynamic smem of k_select_assign_fast
 
 void compute_slab(rbgtopo_ctx* c, int n) {
   const int W = c->cfg.world, r = c->cfg.rank;
@@ -307,6 +310,7 @@ int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, Batc
     for (int a = 0; a < na; ++a) pc += a < na - st[15] ? T.h_degp1[anc[3 * a]] : T.max_degp1;
     if (m->patch_cap + pc > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "patch lists exceed 2^31 entries");
     m->patch_cap += pc;
+    m->max_cap = (int)std::max<long long>(m->max_cap, std::min<long long>(pc, 1 << 30));
     m->poff[s + 1] = (int)m->patch_cap;
     racc += R;
     pacc += P;
@@ -448,8 +452,24 @@ int launch_score(rbgtopo_ctx* c, Batch* b, cudaStream_t s) {
 int launch_select_assign(rbgtopo_ctx* c, Batch* b, cudaStream_t s, const BatchDev& d, int* launches) {
   const int ns = b->m.n_steps;
   if (ns == 0) return RBGTOPO_OK;
+  // shared-memory hash table for the patched nodes of a step: power of two >= 1.5 x the
+  // largest capacity among the launch's steps; >= 4 warps per CTA for the table passes
+  auto table = [&](int s0, int s1, int* CAP, int* HT) {
+    int mc = 0;
+    for (int s2 = s0; s2 < s1; ++s2) mc = std::max(mc, b->m.poff[s2 + 1] - b->m.poff[s2]);
+    *CAP = std::max(32, round_up(mc, 32));
+    *HT = 64;
+    while (2 * *HT < 3 * *CAP && *HT < (1 << 20)) *HT <<= 1;
+  };
+  int CAP, HT;
+  table(0, ns, &CAP, &HT);
+  const bool fast = fast_smem_bytes(b->m.max_p, HT, CAP) <= kFastSmemMax;
   if (b->wave_begin.empty()) {
-    k_select_assign<<<ns, 32 * b->m.max_p, select_smem_bytes(b->m.max_p), s>>>(topo_dev(c), d, 0, 0);
+    const int nth = std::max(128, 32 * b->m.max_p);
+    if (fast)
+      k_select_assign_fast<<<ns, nth, fast_smem_bytes(nth / 32, HT, CAP), s>>>(topo_dev(c), d, 0, 0, HT, CAP);
+    else
+      k_select_assign<<<ns, 32 * b->m.max_p, select_smem_bytes(b->m.max_p), s>>>(topo_dev(c), d, 0, 0);
     ++*launches;
     return RBGTOPO_OK;
   }
@@ -458,8 +478,14 @@ int launch_select_assign(rbgtopo_ctx* c, Batch* b, cudaStream_t s, const BatchDe
   for (size_t w = 0; w + 1 < b->wave_begin.size(); ++w) {
     const int n = b->wave_begin[w + 1] - b->wave_begin[w];
     if (n <= 0) continue;
-    k_select_assign<<<n, 32 * b->wave_maxp[w], select_smem_bytes(b->wave_maxp[w]), s>>>(
-        topo_dev(c), d, b->wave_begin[w], SEL_CORRECT | SEL_CHAIN);
+    if (fast) {
+      const int nth = std::max(128, 32 * b->wave_maxp[w]);
+      table(b->wave_begin[w], b->wave_begin[w + 1], &CAP, &HT);
+      k_select_assign_fast<<<n, nth, fast_smem_bytes(nth / 32, HT, CAP), s>>>(
+          topo_dev(c), d, b->wave_begin[w], SEL_CORRECT | SEL_CHAIN, HT, CAP);
+    } else
+      k_select_assign<<<n, 32 * b->wave_maxp[w], select_smem_bytes(b->wave_maxp[w]), s>>>(
+          topo_dev(c), d, b->wave_begin[w], SEL_CORRECT | SEL_CHAIN);
     ++*launches;
   }
   return RBGTOPO_OK;
@@ -605,6 +631,7 @@ int32_t rbgtopo_create(const rbgtopo_config* cfg, rbgtopo_ctx** out) {
   c->cfg = *cfg;
   c->cfg.emit_matrix = 1;  // the dense matrix is always materialised (selection reads patched scores back)
   c->sm_count = prop.multiProcessorCount;
+  CK(cudaFuncSetAttribute(k_select_assign_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
   {
     int occ = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_emit, SCORE_THREADS, 0));

@@ -250,6 +250,47 @@ __device__ __forceinline__ void select_role(const TopoDev& t, const BatchDev& b,
   __syncwarp();
 }
 
+// Multi-wave plans (rbgtopo.cu build_plan): write this step's placements into the
+// later waves of the same group — anchor record n_static + i and consumed record i
+// of every later step, the exclusive domain, and the SKIP flag when a gang group
+// failed.  One warp, after the step's assign[] is final.
+__device__ __forceinline__ void chain_step(const BatchDev& b, const StepHdr& h, int status, int dstar) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  int* wb = const_cast<int*>(b.blob);
+  const bool excl = (h.flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
+  const bool dead = status == RBGTOPO_GANG_FAILED;
+  bool any = false;
+  for (int i = 0; i < h.R; ++i) any |= b.assign[h.rep_off + i] >= 0;
+  const int fixed = excl ? ((dstar >= 0 && any) ? dstar : h.fixed_domain) : -1;
+  for (int s2 = h.next_step; s2 > 0;) {
+    int* hd = wb + RBGTOPO_HDR_WORDS + (size_t)s2 * RBGTOPO_STEP_WORDS;
+    const int n_static = hd[7] - hd[15];  // n_anchors - replicas of the earlier waves
+    int rr = 0;
+    for (int p = 0; p < h.P; ++p) {
+      const int count = b.blob[h.role_off + 4 * p], demand = b.blob[h.role_off + 4 * p + 1];
+      const int q = (b.blob[h.role_off + 4 * p + 3] >> 8) & 0xFF;
+      for (int c = lane; c < count; c += 32) {
+        const int node = b.assign[h.rep_off + rr + c];
+        int* ar = wb + hd[8] + 3 * (n_static + h.i0 + rr + c);
+        int* cr = wb + hd[10] + 2 * (h.i0 + rr + c);
+        ar[0] = node >= 0 ? node : 0;
+        ar[1] = q;
+        ar[2] = node >= 0 ? 1 : 0;
+        cr[0] = node >= 0 ? node : 0;
+        cr[1] = node >= 0 ? demand : 0;
+      }
+      rr += count;
+    }
+    const int nxt = hd[14];
+    if (lane == 0) {
+      hd[2] = fixed;
+      hd[1] = dead ? (hd[1] | STEP_SKIP) : (hd[1] & ~STEP_SKIP);
+    }
+    s2 = nxt;
+  }
+}
+
 // Greedy in replica order on the step's final lists (spec §3.6).  One warp.
 // With `chain` the placements are written into the later waves of the same group
 // (device-resident multi-wave plans, rbgtopo.cu build_plan): anchor record
@@ -304,41 +345,7 @@ __device__ __forceinline__ void greedy_step(const TopoDev& t, const BatchDev& b,
     b.domain_out[step] = dstar;
     b.dstar[step] = dstar;
   }
-  if (chain && h.next_step > 0) {
-    __syncwarp();
-    int* wb = const_cast<int*>(b.blob);
-    const bool excl = (h.flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
-    const bool dead = status == RBGTOPO_GANG_FAILED;
-    bool any = false;
-    for (int i = 0; i < h.R; ++i) any |= b.assign[h.rep_off + i] >= 0;
-    const int fixed = excl ? ((dstar >= 0 && any) ? dstar : h.fixed_domain) : -1;
-    for (int s2 = h.next_step; s2 > 0;) {
-      int* hd = wb + RBGTOPO_HDR_WORDS + (size_t)s2 * RBGTOPO_STEP_WORDS;
-      const int n_static = hd[7] - hd[15];  // n_anchors - replicas of the earlier waves
-      int rr = 0;
-      for (int p = 0; p < h.P; ++p) {
-        const int count = b.blob[h.role_off + 4 * p], demand = b.blob[h.role_off + 4 * p + 1];
-        const int q = (b.blob[h.role_off + 4 * p + 3] >> 8) & 0xFF;
-        for (int c = lane; c < count; c += 32) {
-          const int node = b.assign[h.rep_off + rr + c];
-          int* ar = wb + hd[8] + 3 * (n_static + h.i0 + rr + c);
-          int* cr = wb + hd[10] + 2 * (h.i0 + rr + c);
-          ar[0] = node >= 0 ? node : 0;
-          ar[1] = q;
-          ar[2] = node >= 0 ? 1 : 0;
-          cr[0] = node >= 0 ? node : 0;
-          cr[1] = node >= 0 ? demand : 0;
-        }
-        rr += count;
-      }
-      const int nxt = hd[14];
-      if (lane == 0) {
-        hd[2] = fixed;
-        hd[1] = dead ? (hd[1] | STEP_SKIP) : (hd[1] & ~STEP_SKIP);
-      }
-      s2 = nxt;
-    }
-  }
+  if (chain && h.next_step > 0) chain_step(b, h, status, dstar);
 }
 
 // ---- world == 1: select + exclusive domain + greedy fused, one CTA per step,

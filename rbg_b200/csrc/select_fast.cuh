@@ -1,0 +1,356 @@
+// select_fast.cuh — k_select_assign_fast: the world == 1 selection / assignment
+// kernel with the step's patched nodes held in a shared-memory hash table
+// (DESIGN.md §4.3).  One CTA per step, warp p = role row p.
+//
+//   1. one pass over the anchors' CSR rows (warp per anchor, coalesced int32 loads)
+//      inserts every slab neighbour into the table and accumulates pair*c*w into
+//      the per-role delta of its slot (shared-memory float atomics: exact
+//      integers, order-free); the same pass issues the fire-and-forget
+//      red.global.add.f32 corrections onto the dense matrix when the emit kernel
+//      left them to us (multi-wave plans).  Consumed capacity lands in the slot too.
+//   2. the slots learn base / free / domain / ownership of their node (one gather);
+//      the matrix gets -inf where consumed capacity made a node infeasible.
+//   3. warp p: top-K of the patched slots (score = need*base + delta computed
+//      in shared memory — no matrix read-back, nothing to wait for), then the walk
+//      of the per-snapshot background order with an O(1) table probe as the
+//      "is patched" test; ballots pick accepted lanes in order; merge.
+//   4. warp 0: greedy from shared memory (every list entry carries its capacity),
+//      then the chaining writes for multi-wave plans.
+// Falls back to k_select_assign (select.cuh) when a step's patched set does not fit.
+#pragma once
+#include "select.cuh"
+
+namespace rbgtopo {
+
+struct PatchTab {
+  int* node;     // [HT] key, -1 = empty
+  int* cons;     // [HT] consumed capacity of the slot's node
+  float* delta;  // [PB][HT] per-role score delta of the slot's node
+  int mask;      // HT - 1
+  // dense view of the occupied slots (built once after the insert pass): rounds
+  // iterate cnt entries, not HT slots
+  int* dSlot;    // [CAP]
+  float* dBase;  // [CAP]
+  int* dAvail;   // [CAP] free - consumed
+  int* dDom;     // [CAP] domain, bit 31 set = domain owned by another group
+  int cnt;
+};
+__host__ __device__ inline size_t fast_smem_bytes(int PB, int HT, int CAP) {
+  return (size_t)HT * 4 * (2 + PB) + (size_t)CAP * 16;
+}
+
+__device__ __forceinline__ int tab_hash(int n, int mask) { return (int)(((uint32_t)n * 2654435761u) >> 12) & mask; }
+__device__ __forceinline__ int tab_insert(const PatchTab& T, int n) {
+  int h = tab_hash(n, T.mask);
+  while (true) {
+    const int old = atomicCAS(&T.node[h], -1, n);
+    if (old == -1 || old == n) return h;
+    h = (h + 1) & T.mask;
+  }
+}
+__device__ __forceinline__ int tab_find(const PatchTab& T, int n) {
+  int h = tab_hash(n, T.mask);
+  while (true) {
+    const int k = T.node[h];
+    if (k == n) return h;
+    if (k == -1) return -1;
+    h = (h + 1) & T.mask;
+  }
+}
+
+// top-K of role row p into out[0..KS) (+ the capacity of every listed node in
+// outAvail); same contract as select_role (select.cuh).
+__device__ __forceinline__ void select_role_fast(const TopoDev& t, const BatchDev& b, const StepHdr& h, int p, int K,
+                                                 int dom, const PatchTab& T, unsigned long long* sAcc, int* sAccAv,
+                                                 unsigned long long* sPat, int* sPatAv, unsigned long long* out,
+                                                 int* outAvail) {
+  const int lane = threadIdx.x & 31;
+  if (dom == DOM_NONE || K <= 0) {
+    out[lane] = 0;
+    return;
+  }
+  const int demand = b.blob[h.role_off + 4 * p + 1];
+  const int need_i = b.blob[h.role_off + 4 * p + 2];
+  const float need = (float)need_i;
+  const bool rexcl = (h.flags & RBGTOPO_STEP_EXCLUSIVE) && (b.blob[h.role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE);
+  const float* delta = T.delta + (size_t)p * (T.mask + 1);
+
+  // ---- (a) patched slots: keys from shared memory, K strictly-descending rounds
+  int npat = 0;
+  {
+    unsigned long long prev = ~0ull;
+    for (; npat < K; ++npat) {
+      unsigned long long best = 0;
+      int bav = 0;
+      for (int i = lane; i < T.cnt; i += 32) {
+        const int av = T.dAvail[i], dd = T.dDom[i];
+        if (av >= demand && !(rexcl && dd < 0) && (dom == DOM_ANY || (dd & 0x7FFFFFFF) == dom)) {
+          const int slot = T.dSlot[i];
+          const unsigned long long k = make_key(fmaf(need, T.dBase[i], delta[slot]), T.node[slot]);
+          if (k < prev && k > best) { best = k; bav = av; }
+        }
+      }
+      const unsigned long long m = warp_max_u64(best);
+      if (m == 0) break;
+      const uint32_t who = __ballot_sync(FULL, best == m);
+      bav = __shfl_sync(FULL, bav, __ffs(who) - 1);
+      if (lane == 0) { sPat[npat] = m; sPatAv[npat] = bav; }
+      prev = m;
+    }
+  }
+
+  // ---- (b) walk the background order; patched nodes are skipped by a table probe
+  const int slab_len = t.slab_hi - t.slab_lo;
+  int acc = 0;
+  for (int pos = 0; pos < slab_len && acc < K; pos += 32) {
+    const int i = pos + lane;
+    int av = 0;
+    unsigned long long key = 0;
+    bool ok = false;
+    if (i < slab_len) {
+      int node;
+      if (need_i > 0) {
+        const unsigned long long ob = t.order[i];
+        node = key_node(ob);
+        const float base = __uint_as_float((uint32_t)(ob >> 32) ^ 0x80000000u);  // base >= 0
+        key = make_key(need * base, node);
+      } else {
+        node = t.slab_lo + i;
+        key = make_key(0.0f, node);
+      }
+      av = t.free_[node];
+      ok = av >= demand;
+      if (ok && rexcl) {
+        const int o = t.node_owner[node];
+        ok = (o == -1 || o == h.gid);
+      }
+      if (ok && dom != DOM_ANY) ok = t.domain[node] == dom;
+      if (ok) ok = tab_find(T, node) < 0;
+    }
+    const uint32_t m = __ballot_sync(FULL, ok);
+    const int idx = acc + __popc(m & ((1u << lane) - 1u));
+    if (ok && idx < K) { sAcc[idx] = key; sAccAv[idx] = av; }
+    acc += __popc(m);
+  }
+  acc = min(acc, K);
+  __syncwarp();
+
+  // ---- merge the two descending lists
+  if (lane == 0) {
+    int ia = 0, ip = 0;
+    for (int r = 0; r < KS; ++r) {
+      unsigned long long v = 0;
+      int av = 0;
+      if (r < K) {
+        const unsigned long long a = ia < acc ? sAcc[ia] : 0ull;
+        const unsigned long long c = ip < npat ? sPat[ip] : 0ull;
+        if (a > c) { v = a; av = sAccAv[ia]; ++ia; } else if (c) { v = c; av = sPatAv[ip]; ++ip; }
+      }
+      out[r] = v;
+      outAvail[r] = av;
+    }
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * MAXP)
+k_select_assign_fast(TopoDev t, BatchDev b, int step_begin, int mode, int HT, int CAP) {
+  extern __shared__ __align__(16) unsigned char fs_smem[];
+  __shared__ unsigned long long sList[MAXP][KS], sAcc[MAXP][KS], sPat[MAXP][KS];
+  __shared__ int sListAv[MAXP][KS], sAccAv[MAXP][KS], sPatAv[MAXP][KS];
+  __shared__ int sTakenNode[KS], sTakenAmt[KS];
+  __shared__ int sDstar, sCnt;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthreads = blockDim.x, nwarps = nthreads >> 5;
+  const int PB = nwarps;
+  PatchTab T;
+  T.node = reinterpret_cast<int*>(fs_smem);
+  T.cons = T.node + HT;
+  T.delta = reinterpret_cast<float*>(T.cons + HT);
+  T.mask = HT - 1;
+  T.dSlot = reinterpret_cast<int*>(T.delta + (size_t)PB * HT);
+  T.dBase = reinterpret_cast<float*>(T.dSlot + CAP);
+  T.dAvail = reinterpret_cast<int*>(T.dBase + CAP);
+  T.dDom = T.dAvail + CAP;
+  T.cnt = 0;
+
+  const int step = step_begin + blockIdx.x;
+  const StepHdr h = load_hdr(b, step);
+  const bool excl_step = (h.flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
+  if (h.flags & STEP_SKIP) {  // an earlier wave of this gang group failed: nothing is placed
+    if (warp == 0) {
+      for (int i = lane; i < h.R; i += 32) b.assign[h.rep_off + i] = -1;
+      if (lane == 0) {
+        b.status[step] = RBGTOPO_GANG_FAILED;
+        b.domain_out[step] = -1;
+        b.dstar[step] = -1;
+      }
+    }
+    return;
+  }
+
+  // ---- 0. empty table
+  for (int i = tid; i < HT; i += nthreads) {
+    T.node[i] = -1;
+    T.cons[i] = 0;
+  }
+  for (int i = tid; i < PB * HT; i += nthreads) T.delta[i] = 0.0f;
+  if (tid == 0) sCnt = 0;
+  __syncthreads();
+
+  // ---- 1. anchors -> slots (+ matrix corrections when asked), consumed capacity
+  const size_t stride = (size_t)t.slab_stride;
+  float* const mrow0 = b.matrix + (size_t)h.rep_off * stride - t.slab_lo;  // mrow0[node]
+  const bool correct = (mode & SEL_CORRECT) != 0;
+  {
+    const int* anc = b.blob + h.anchor_off;
+    for (int a = warp; a < h.n_anchors; a += nwarps) {
+      const int m = anc[3 * a], q = anc[3 * a + 1], c = anc[3 * a + 2];
+      const int rb = t.row_ptr[m], re = t.row_ptr[m + 1];
+      for (int j = rb + lane; j <= re; j += 32) {  // j == re stands for the anchor's own node
+        int nn, wv;
+        if (j < re) {
+          nn = t.col[j];
+          wv = t.w[j] * c;
+        } else {
+          nn = m;
+          wv = RBGTOPO_SELF_W * c;
+        }
+        if (nn >= t.slab_lo && nn < t.slab_hi) {
+          const int slot = tab_insert(T, nn);
+          if (c) {
+            float* rowp = mrow0 + nn;
+            for (int p = 0; p < h.P; ++p) {
+              const int count = b.blob[h.role_off + 4 * p];
+              const int coef = b.blob[h.pair_off + p * h.Q + q];
+              if (coef) {
+                const float add = (float)(coef * wv);
+                atomicAdd(&T.delta[(size_t)p * HT + slot], add);
+                if (correct)
+                  for (int k = 0; k < count; ++k) sel_red_add_f32(rowp + (size_t)k * stride, add);
+              }
+              rowp += (size_t)count * stride;
+            }
+          }
+        }
+      }
+    }
+    const int* con = b.blob + h.cons_off;
+    for (int c = tid; c < h.n_cons; c += nthreads) {
+      const int m = con[2 * c], amt = con[2 * c + 1];
+      if (m >= t.slab_lo && m < t.slab_hi) atomicAdd(&T.cons[tab_insert(T, m)], amt);
+    }
+  }
+  __syncthreads();
+
+  // ---- 2. dense view + node attributes; -inf where consumed capacity made a node infeasible
+  for (int i0 = 0; i0 < HT; i0 += nthreads) {
+    const int i = i0 + tid;
+    const int node = i < HT ? T.node[i] : -1;
+    const bool occ = node >= 0;
+    const uint32_t msk = __ballot_sync(FULL, occ);
+    int basei = 0;
+    if (lane == 0 && msk) basei = atomicAdd(&sCnt, __popc(msk));
+    basei = __shfl_sync(FULL, basei, 0);
+    if (occ) {
+      const int d = basei + __popc(msk & ((1u << lane) - 1u));
+      const int av = t.free_[node] - T.cons[i];
+      int dd = t.domain[node];
+      if (excl_step) {
+        const int o = t.node_owner[node];
+        if (!(o == -1 || o == h.gid)) dd |= 0x80000000;
+      }
+      T.dSlot[d] = i;
+      T.dBase[d] = t.base[node];
+      T.dAvail[d] = av;
+      T.dDom[d] = dd;
+      if (correct && T.cons[i] > 0) {
+        float* rowp = mrow0 + node;
+        for (int p = 0; p < h.P; ++p) {
+          const int count = b.blob[h.role_off + 4 * p], demand = b.blob[h.role_off + 4 * p + 1];
+          if (av < demand)
+            for (int k = 0; k < count; ++k) rowp[(size_t)k * stride] = -INFINITY;
+          rowp += (size_t)count * stride;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  T.cnt = sCnt;
+
+  // ---- 3. exclusive domain, selection
+  int dstar = excl_step ? h.fixed_domain : -1;
+  if (excl_step && h.fixed_domain < 0) {
+    int pstar = -1;
+    for (int p = 0; p < h.P; ++p)
+      if (b.blob[h.role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE) { pstar = p; break; }
+    if (warp == 0) {
+      int d = -1;
+      if (pstar >= 0) {
+        select_role_fast(t, b, h, pstar, 1, DOM_ANY, T, sAcc[0], sAccAv[0], sPat[0], sPatAv[0], sList[0], sListAv[0]);
+        const unsigned long long top = sList[0][0];
+        d = top ? t.domain[key_node(top)] : -1;
+      }
+      if (lane == 0) sDstar = d;
+    }
+    __syncthreads();
+    dstar = sDstar;
+  }
+  if (warp < h.P) {
+    const int p = warp;
+    const bool rexcl = excl_step && (b.blob[h.role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE);
+    const int dom = rexcl ? (dstar >= 0 ? dstar : DOM_NONE) : DOM_ANY;
+    select_role_fast(t, b, h, p, role_k(b, h, p, t.n), dom, T, sAcc[p], sAccAv[p], sPat[p], sPatAv[p], sList[p],
+                     sListAv[p]);
+    b.merged[(size_t)(h.rolerow_off + p) * KS + lane] = sList[p][lane];
+  }
+  __syncthreads();
+
+  // ---- 4. greedy from shared memory (+ chaining for multi-wave plans)
+  if (warp == 0) {
+    int ntaken = 0, unplaced = 0, r = 0;
+    for (int p = 0; p < h.P; ++p) {
+      const int count = b.blob[h.role_off + 4 * p], demand = b.blob[h.role_off + 4 * p + 1];
+      for (int c = 0; c < count; ++c, ++r) {
+        int pick = -1;
+        for (int k = 0; k < KS; ++k) {
+          const unsigned long long key = sList[p][k];
+          if (key == 0) break;
+          const int node = key_node(key);
+          int used = 0;
+          for (int i = lane; i < ntaken; i += 32)
+            if (sTakenNode[i] == node) used += sTakenAmt[i];
+          used = __reduce_add_sync(FULL, used);
+          if (sListAv[p][k] - used >= demand) {
+            pick = node;
+            break;
+          }
+        }
+        if (pick >= 0) {
+          if (lane == 0) {
+            sTakenNode[ntaken] = pick;
+            sTakenAmt[ntaken] = demand;
+          }
+          ++ntaken;
+          __syncwarp();
+        } else {
+          ++unplaced;
+        }
+        if (lane == 0) b.assign[h.rep_off + r] = pick;
+      }
+    }
+    __syncwarp();
+    int status = unplaced ? RBGTOPO_PLACED_PART : RBGTOPO_PLACED_ALL;
+    if (unplaced && (h.flags & RBGTOPO_STEP_GANG)) {
+      status = RBGTOPO_GANG_FAILED;
+      for (int i = lane; i < h.R; i += 32) b.assign[h.rep_off + i] = -1;
+    }
+    if (lane == 0) {
+      b.status[step] = status;
+      b.domain_out[step] = dstar;
+      b.dstar[step] = dstar;
+    }
+    if ((mode & SEL_CHAIN) && h.next_step > 0) chain_step(b, h, status, dstar);
+  }
+}
+
+}  // namespace rbgtopo
