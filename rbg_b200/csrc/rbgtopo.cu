@@ -115,6 +115,8 @@ struct Batch {
   bool staged = false;    // holds a staged blob (handle alive)
   bool ran = false;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // wave kernels of a plan run here, concurrently with k_score_emit
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> it_ev;  // triples (before score, after score, after select) per pass
   int passes = 0, pend_launches = 0, untimed_or_timed_passes = 0;  // since the last harvest
@@ -134,6 +136,9 @@ struct Batch {
   PinBuf<int> h_in, h_out;
   ~Batch() {
     if (stream) cudaStreamDestroy(stream);
+    if (stream2) cudaStreamDestroy(stream2);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : it_ev) cudaEventDestroy(e);
   }
@@ -160,7 +165,12 @@ struct rbgtopo_ctx {
 namespace {
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
-constexpr size_t kFastSmemMax = 96 * 1024;  // opt-in dynamic smem of k_select_assign_fast
+constexpr size_t kFastSmemMax = 96 * 1024;
+// Experiment switch (profiles/README.md "two-stream plan"): run the wave kernels on a second
+// stream concurrently with k_score_emit.  Measured no gain (the latency-bound wave kernels
+// slow down behind the saturated memory system), so the serial pipeline is the default.
+const bool kSerialPlan = getenv("RBGTOPO_CONCURRENT_PLAN") == nullptr;
+const int kEmitOcc = getenv("RBGTOPO_EMIT_OCC") ? atoi(getenv("RBGTOPO_EMIT_OCC")) : 6;  // opt-in dynamic smem of k_select_assign_fast
 
 void compute_slab(rbgtopo_ctx* c, int n) {
   const int W = c->cfg.world, r = c->cfg.rank;
@@ -200,6 +210,14 @@ TopoDev topo_dev(const rbgtopo_ctx* c) {
   t.dom_nodes = T.dom_nodes.p;
   t.order = T.order.p;
   return t;
+}
+
+// Sparse corrections of every step of a multi-wave plan, after the wave kernels have
+// chained all placements: one CTA per step (select.cuh correct_step).
+__global__ void __launch_bounds__(128) k_correct_all(TopoDev t, BatchDev b) {
+  const StepHdr h = load_hdr(b, blockIdx.x);
+  if (h.flags & STEP_SKIP) return;
+  correct_step(t, b, h);
 }
 
 __global__ void k_order_keys(TopoDev t, unsigned long long* keys) {
@@ -365,6 +383,13 @@ int acquire_batch(rbgtopo_ctx* c, Batch** out) {
     }
   auto nb = std::make_unique<Batch>();
   CK(cudaStreamCreateWithFlags(&nb->stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = highest priority
+    CK(cudaStreamCreateWithPriority(&nb->stream2, cudaStreamNonBlocking, hi));
+    CK(cudaEventCreateWithFlags(&nb->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&nb->ev_join, cudaEventDisableTiming));
+  }
   for (auto& e : nb->ev) CK(cudaEventCreate(&e));
   nb->in_use = true;
   *out = nb.get();
@@ -473,19 +498,31 @@ int launch_select_assign(rbgtopo_ctx* c, Batch* b, cudaStream_t s, const BatchDe
     ++*launches;
     return RBGTOPO_OK;
   }
-  // multi-wave plan: the emit kernel wrote the background rows of every wave; each
-  // wave applies its sparse corrections, selects, assigns and chains into the next
+  // multi-wave plan: the wave kernels (select, assign, chain) do not read the matrix, so
+  // they run on a second, high-priority stream CONCURRENTLY with k_score_emit (which the
+  // caller has already enqueued on `s`); the sparse corrections of all steps are applied
+  // afterwards by one launch, when both are done.
+  const bool concurrent = b->stream2 != nullptr && !kSerialPlan;
+  cudaStream_t sw = concurrent ? b->stream2 : s;
+  if (concurrent) CK(cudaStreamWaitEvent(sw, b->ev_fork, 0));
+  const int wave_mode = concurrent ? SEL_CHAIN : (SEL_CORRECT | SEL_CHAIN);
   for (size_t w = 0; w + 1 < b->wave_begin.size(); ++w) {
     const int n = b->wave_begin[w + 1] - b->wave_begin[w];
     if (n <= 0) continue;
     if (fast) {
       const int nth = std::max(128, 32 * b->wave_maxp[w]);
       table(b->wave_begin[w], b->wave_begin[w + 1], &CAP, &HT);
-      k_select_assign_fast<<<n, nth, fast_smem_bytes(nth / 32, HT, CAP), s>>>(
-          topo_dev(c), d, b->wave_begin[w], SEL_CORRECT | SEL_CHAIN, HT, CAP);
+      k_select_assign_fast<<<n, nth, fast_smem_bytes(nth / 32, HT, CAP), sw>>>(
+          topo_dev(c), d, b->wave_begin[w], wave_mode, HT, CAP);
     } else
-      k_select_assign<<<n, 32 * b->wave_maxp[w], select_smem_bytes(b->wave_maxp[w]), s>>>(
-          topo_dev(c), d, b->wave_begin[w], SEL_CORRECT | SEL_CHAIN);
+      k_select_assign<<<n, 32 * b->wave_maxp[w], select_smem_bytes(b->wave_maxp[w]), sw>>>(
+          topo_dev(c), d, b->wave_begin[w], wave_mode);
+    ++*launches;
+  }
+  if (concurrent) {
+    CK(cudaEventRecord(b->ev_join, sw));
+    CK(cudaStreamWaitEvent(s, b->ev_join, 0));
+    k_correct_all<<<ns, 128, 0, s>>>(topo_dev(c), d);
     ++*launches;
   }
   return RBGTOPO_OK;
@@ -517,6 +554,7 @@ int run_batch(rbgtopo_ctx* c, Batch* b, int iters) {
       if (rc) return rc;
       CK(cudaEventRecord(b->it_ev[e0], s));
     }
+    if (!b->wave_begin.empty()) CK(cudaEventRecord(b->ev_fork, s));  // inputs of this pass are ready
     int rc = launch_score(c, b, s);
     if (rc) return rc;
     ++launches;
@@ -635,7 +673,7 @@ int32_t rbgtopo_create(const rbgtopo_config* cfg, rbgtopo_ctx** out) {
   {
     int occ = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_emit, SCORE_THREADS, 0));
-    c->emit_grid = c->sm_count * std::max(1, occ);
+    c->emit_grid = c->sm_count * std::max(1, std::min(occ, kEmitOcc));  // leave room for the wave kernels
   }
   *out = c.release();
   return RBGTOPO_OK;
