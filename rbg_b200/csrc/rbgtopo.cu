@@ -608,6 +608,7 @@ int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int3
   tm.algo_bytes = m.algo_bytes;
   tm.launches = b->pend_launches;
   tm.h2d_words = (int32_t)(m.words + m.n_steps + 1);
+  (void)cudaGetLastError();  // events recorded under stream capture have no timestamps: not an error here
   const int total_passes = b->untimed_or_timed_passes;
   b->passes = 0;
   b->pend_launches = 0;
