@@ -202,40 +202,18 @@ def run_ours(args):
     # the wave batches: derive them once on rank-local single-GPU semantics.  The
     # placement is deterministic, so the wave w+1 batch (which carries wave w's
     # placements as anchors) is identical every step.
-    gblob = None
-    if world == 1:
-        eng = TopoPlacer(device=local)
-        eng.set_topology(topo.row_ptr, topo.col_idx, topo.edge_w, topo.free, topo.domain, topo.domain_owner)
-        gblob, _ = B200TopoPodGroupManager(eng).groups_blob(rbgs)
-        wave_blobs = []
-    else:
-        # every rank needs the same wave batches: rank 0 derives them with the CPU-free
-        # single-GPU engine over the full node axis and broadcasts the blobs
-        if rank == 0:
-            e1 = TopoPlacer(device=local)
-            e1.set_topology(topo.row_ptr, topo.col_idx, topo.edge_w, topo.free, topo.domain, topo.domain_owner)
-            rec = _RecordingPlacer(e1)
-            B200TopoPodGroupManager(rec).reconcile_pod_groups_by_waves(rbgs)
-            wave_blobs = rec.blobs
-            e1.close()
-        else:
-            wave_blobs = None
-        box = [wave_blobs]
-        dist.broadcast_object_list(box, src=0)
-        wave_blobs = box[0]
-        eng = TopoPlacer(device=local, rank=rank, world=world)
-        eng.set_topology(topo.row_ptr, topo.col_idx, topo.edge_w, topo.free, topo.domain, topo.domain_owner)
+    eng = TopoPlacer(device=local, rank=rank, world=world)
+    eng.set_topology(topo.row_ptr, topo.col_idx, topo.edge_w, topo.free, topo.domain, topo.domain_owner)
+    gblob, _ = B200TopoPodGroupManager(eng).groups_blob(rbgs)   # host-side marshalling, identical on every rank
+    wave_blobs = []
 
     stream = torch.cuda.Stream()
     eng.set_stream(stream.cuda_stream)
-    if world == 1:
-        # device-resident multi-wave plan: ONE k_score_emit launch for the dense rows of all
-        # waves, then one select/assign launch per wave chained on the device
-        handles = [eng.stage_groups(gblob)]
-        total_r = int(gblob[4])
-    else:
-        handles = [eng.stage(b) for b in wave_blobs]
-        total_r = sum(int(b[4]) for b in wave_blobs)
+    # device-resident multi-wave plan: ONE k_score_emit launch per rank for the dense rows of all
+    # waves; per wave: select (+ all-gather + merge when sharded) + assign, chained on the device
+    handles = [eng.stage_groups(gblob)]
+    total_r = int(gblob[4])
+    n_waves = eng.shard_waves(handles[0])
     lo, hi = eng.slab()
     scores_per_step_rank = total_r * (hi - lo)
     gathered = {}
@@ -247,21 +225,22 @@ def run_ours(args):
             return
         with torch.cuda.stream(stream):
             for h in handles:
-                ptr, nb = eng.shard_score(h)
-                if (h, ptr) not in gathered:   # library buffers are stable per staged batch: wrap them once
-                    gathered[(h, ptr)] = (torch.as_tensor(_DevPtr(ptr, nb), device="cuda"),
-                                          torch.empty(world * (nb // 8), dtype=torch.int64, device="cuda"))
-                src, allk = gathered[(h, ptr)]
-                dist.all_gather_into_tensor(allk, src)
-                need2, p2, nb2 = eng.shard_merge(h, allk.data_ptr())
-                g2 = None
-                if need2:
-                    if (h, p2, 2) not in gathered:
-                        gathered[(h, p2, 2)] = (torch.as_tensor(_DevPtr(p2, nb2), device="cuda"),
-                                                torch.empty(world * (nb2 // 8), dtype=torch.int64, device="cuda"))
-                    src2, g2 = gathered[(h, p2, 2)]
-                    dist.all_gather_into_tensor(g2, src2)
-                eng.shard_assign(h, g2.data_ptr() if g2 is not None else None)
+                for w in range(n_waves):
+                    ptr, nb = eng.shard_wave_score(h, w)
+                    if (h, ptr) not in gathered:   # library buffers are stable per staged batch: wrap them once
+                        gathered[(h, ptr)] = (torch.as_tensor(_DevPtr(ptr, nb), device="cuda"),
+                                              torch.empty(world * (nb // 8), dtype=torch.int64, device="cuda"))
+                    src, allk = gathered[(h, ptr)]
+                    dist.all_gather_into_tensor(allk, src)
+                    need2, p2, nb2 = eng.shard_wave_merge(h, w, allk.data_ptr())
+                    g2 = None
+                    if need2:
+                        if (h, p2, 2) not in gathered:
+                            gathered[(h, p2, 2)] = (torch.as_tensor(_DevPtr(p2, nb2), device="cuda"),
+                                                    torch.empty(world * (nb2 // 8), dtype=torch.int64, device="cuda"))
+                        src2, g2 = gathered[(h, p2, 2)]
+                        dist.all_gather_into_tensor(g2, src2)
+                    eng.shard_wave_assign(h, w, g2.data_ptr() if g2 is not None else None)
 
     def barrier():
         if world > 1:
@@ -369,7 +348,7 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            hs = [eng.stage(b) for b in wave_blobs]
+            hs = [eng.stage_groups(gblob)]
             eng.set_stream(stream.cuda_stream)
             handles = hs
             eager_step()
@@ -379,8 +358,8 @@ def run_ours(args):
                 eng.release(h)
             eng.set_stream(None)
         e2e_ms = (time.perf_counter() - t0) * 1e3
-        h2d = int(sum(b.nbytes for b in wave_blobs))
-        d2h = int(sum((int(b[4]) + 2 * int(b[2])) * 4 for b in wave_blobs))
+        h2d = int(4 * h2d_words)
+        d2h = int(4 * (total_r + 2 * 3 * args.groups))
     t_e = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)

@@ -258,6 +258,21 @@ int32_t rbgtopo_read_topk(rbgtopo_ctx* ctx, int32_t handle, int32_t rolerow,
  *                 the second (small) buffer to all-gather.
  *   shard_assign: final merge + greedy (keys2_all_dev may be NULL when
  *                 need_pass2 was 0); results via rbgtopo_fetch. */
+/* Wave-ranged forms.  A staged step batch has 1 wave; a staged GROUPS plan
+ * (rbgtopo_stage_groups, also valid with world > 1) has W = rbgtopo_shard_waves
+ * waves that must be run in order 0..W-1, each as score -> all-gather -> merge
+ * [-> all-gather -> ] assign.  Wave 0's score call also enqueues the single
+ * k_score_emit launch for the rows of every wave on this rank's slab; the
+ * placements are chained into later waves on every rank identically. */
+int32_t rbgtopo_shard_waves(rbgtopo_ctx* ctx, int32_t handle, int32_t* n_waves);
+int32_t rbgtopo_shard_wave_score(rbgtopo_ctx* ctx, int32_t handle, int32_t wave,
+                                 void** keys_dev, int64_t* keys_bytes);
+int32_t rbgtopo_shard_wave_merge(rbgtopo_ctx* ctx, int32_t handle, int32_t wave,
+                                 const void* keys_all_dev, int32_t* need_pass2,
+                                 void** keys2_dev, int64_t* keys2_bytes);
+int32_t rbgtopo_shard_wave_assign(rbgtopo_ctx* ctx, int32_t handle, int32_t wave,
+                                  const void* keys2_all_dev);
+/* single-wave forms (wave 0 of a step batch) */
 int32_t rbgtopo_shard_score(rbgtopo_ctx* ctx, int32_t handle, void** keys_dev,
                             int64_t* keys_bytes);
 int32_t rbgtopo_shard_merge(rbgtopo_ctx* ctx, int32_t handle,

@@ -157,6 +157,12 @@ struct rbgtopo_ctx {
   std::vector<std::unique_ptr<Batch>> batches;
   cudaStream_t ext_stream = nullptr;
   bool use_ext_stream = false;
+  // snapshot refresh pipeline: update_nodes enqueues on topo_stream and returns; every batch
+  // stream waits on topo_ready before it touches the snapshot
+  cudaStream_t topo_stream = nullptr;
+  cudaEvent_t topo_ready = nullptr, ev_base_a = nullptr, ev_base_b = nullptr;
+  bool base_timing_pending = false;
+  PinBuf<int> h_free, h_owner;
   std::mutex stat_mu;
   rbgtopo_timing last{};
   long long calls = 0, scores_total = 0, launches = 0;
@@ -165,7 +171,7 @@ struct rbgtopo_ctx {
 namespace {
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
-constexpr size_t kFastSmemMax = 96 * 1024;
+constexpr size_t kFastSmemMax = 200 * 1024;
 // Experiment switch (profiles/README.md "two-stream plan"): run the wave kernels on a second
 // stream concurrently with k_score_emit.  Measured no gain (the latency-bound wave kernels
 // slow down behind the saturated memory system), so the serial pipeline is the default.
@@ -226,12 +232,20 @@ __global__ void k_order_keys(TopoDev t, unsigned long long* keys) {
 }
 
 // prep + base kernels on `s`; records base_ms.
-int run_base(rbgtopo_ctx* c, cudaStream_t s) {
+void harvest_base_ms(rbgtopo_ctx* c) {
+  if (!c->base_timing_pending) return;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, c->ev_base_a, c->ev_base_b) == cudaSuccess) {
+    c->topo.base_ms = ms;
+    c->base_timing_pending = false;
+  } else {
+    (void)cudaGetLastError();  // not finished yet
+  }
+}
+
+int run_base(rbgtopo_ctx* c, cudaStream_t s, bool sync) {
   Topology& T = c->topo;
-  cudaEvent_t a, b;
-  CK(cudaEventCreate(&a));
-  CK(cudaEventCreate(&b));
-  CK(cudaEventRecord(a, s));
+  CK(cudaEventRecord(c->ev_base_a, s));
   k_prep<<<(T.n + 255) / 256, 256, 0, s>>>(T.n, T.free_.p, T.domain.p, T.owner.p, T.fmin.p,
                                            T.node_owner.p);
   const int fmin_bytes = round_up(T.n, 16);
@@ -253,19 +267,23 @@ int run_base(rbgtopo_ctx* c, cudaStream_t s) {
     tmp_bytes = T.sort_tmp.cap;
     CK(cub::DeviceRadixSort::SortKeysDescending(T.sort_tmp.p, tmp_bytes, T.okeys.p, T.order.p, slab_len, 0, 64, s));
   }
-  CK(cudaEventRecord(b, s));
-  CK(cudaStreamSynchronize(s));
+  CK(cudaEventRecord(c->ev_base_b, s));
+  CK(cudaEventRecord(c->topo_ready, s));
+  c->base_timing_pending = true;
   CK(cudaGetLastError());
-  CK(cudaEventElapsedTime(&T.base_ms, a, b));
-  cudaEventDestroy(a);
-  cudaEventDestroy(b);
+  if (sync) {
+    CK(cudaStreamSynchronize(s));
+    harvest_base_ms(c);
+  }
   std::lock_guard<std::mutex> g(c->stat_mu);
-  c->launches += 2;
+  c->launches += 3;
   return RBGTOPO_OK;
 }
 
 // ---- blob validation (host, O(words)) ----------------------------------------
-int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, BatchMeta* m) {
+// `trusted`: the blob was built by build_plan from an already validated GROUPS blob — the
+// per-record range checks are skipped, the derived metadata and the exactness bound are not.
+int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, BatchMeta* m, bool trusted = false) {
   const Topology& T = c->topo;
   if (!blob || words < RBGTOPO_HDR_WORDS) return fail(RBGTOPO_EINVAL, "blob too short");
   if (blob[0] != RBGTOPO_BLOB_MAGIC) return fail(RBGTOPO_EINVAL, "bad blob magic");
@@ -303,16 +321,18 @@ int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, Batc
       rsum += roles[4 * p];
     }
     if (rsum != R) return fail(RBGTOPO_EINVAL, "step %d: role counts sum to %d, R=%d", s, rsum, R);
-    for (int i = 0; i < P * Q; ++i)
-      if (pair[i] < 0) return fail(RBGTOPO_EINVAL, "step %d: negative pair weight", s);
-    for (int a = 0; a < na; ++a) {
-      if (anc[3 * a] < 0 || anc[3 * a] >= T.n || anc[3 * a + 1] < 0 || anc[3 * a + 1] >= Q ||
-          anc[3 * a + 2] < 0)
-        return fail(RBGTOPO_EINVAL, "step %d anchor %d out of range", s, a);
+    if (!trusted) {
+      for (int i = 0; i < P * Q; ++i)
+        if (pair[i] < 0) return fail(RBGTOPO_EINVAL, "step %d: negative pair weight", s);
+      for (int a = 0; a < na; ++a) {
+        if (anc[3 * a] < 0 || anc[3 * a] >= T.n || anc[3 * a + 1] < 0 || anc[3 * a + 1] >= Q ||
+            anc[3 * a + 2] < 0)
+          return fail(RBGTOPO_EINVAL, "step %d anchor %d out of range", s, a);
+      }
+      for (int i = 0; i < nc; ++i)
+        if (con[2 * i] < 0 || con[2 * i] >= T.n || con[2 * i + 1] < 0 || con[2 * i + 1] > RBGTOPO_MAX_FREE)
+          return fail(RBGTOPO_EINVAL, "step %d consumed %d out of range", s, i);
     }
-    for (int i = 0; i < nc; ++i)
-      if (con[2 * i] < 0 || con[2 * i] >= T.n || con[2 * i + 1] < 0 || con[2 * i + 1] > RBGTOPO_MAX_FREE)
-        return fail(RBGTOPO_EINVAL, "step %d consumed %d out of range", s, i);
     // exactness contract (spec §3.4), conservative: every anchor on one node
     for (int p = 0; p < P; ++p) {
       long long amax = (long long)roles[4 * p + 2] * RBGTOPO_F_CAP;
@@ -407,15 +427,21 @@ void release_batch(rbgtopo_ctx* c, Batch* b) {
 cudaStream_t stream_of(rbgtopo_ctx* c, Batch* b) { return c->use_ext_stream ? c->ext_stream : b->stream; }
 
 // validate + size buffers + H2D.  Caller holds topo_mu shared.
+// blob == b->h_in.p: the (trusted) plan was built in place in the pinned staging buffer.
 int stage_into(rbgtopo_ctx* c, Batch* b, const int32_t* blob, int64_t words) {
   if (!c->topo.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
-  int rc = validate_blob(c, blob, words, &b->m);
+  const bool in_place = blob == b->h_in.p;
+  int rc = validate_blob(c, blob, words, &b->m, in_place);
   if (rc) return rc;
   const BatchMeta& m = b->m;
   cudaStream_t s = stream_of(c, b);
   const size_t in_words = (size_t)words + (size_t)m.n_steps + 1 + m.cta_item.size();  // blob | poff | cta_item
   CK(b->blob.reserve(in_words));
-  CK(b->h_in.reserve(in_words));
+  if (in_place) {
+    if (b->h_in.cap < in_words) return fail(RBGTOPO_EINVAL, "internal: in-place plan without tail room");
+  } else {
+    CK(b->h_in.reserve(in_words));
+  }
   CK(b->matrix.reserve((size_t)std::max(1, m.total_r) * c->slab_stride));
   CK(b->cand.reserve((size_t)m.patch_cap + 1));
   CK(b->lists.reserve((size_t)std::max(1, m.total_p) * KS));
@@ -424,8 +450,9 @@ int stage_into(rbgtopo_ctx* c, Batch* b, const int32_t* blob, int64_t words) {
   const size_t out_n = (size_t)m.total_r + 3 * (size_t)m.n_steps + 4;
   CK(b->out.reserve(out_n));
   CK(b->h_out.reserve(out_n));
+  CK(cudaStreamWaitEvent(s, c->topo_ready, 0));  // the snapshot refresh (if any) is complete
   CK(cudaEventRecord(b->ev[0], s));
-  memcpy(b->h_in.p, blob, (size_t)words * 4);
+  if (!in_place) memcpy(b->h_in.p, blob, (size_t)words * 4);
   memcpy(b->h_in.p + words, m.poff.data(), ((size_t)m.n_steps + 1) * 4);
   memcpy(b->h_in.p + words + m.n_steps + 1, m.cta_item.data(), m.cta_item.size() * 4);
   CK(cudaMemcpyAsync(b->blob.p, b->h_in.p, in_words * 4, cudaMemcpyHostToDevice, s));
@@ -544,6 +571,7 @@ int ensure_pass_events(Batch* b, int passes) {
 // select) until kMaxTimedPasses passes are pending harvest.
 int run_batch(rbgtopo_ctx* c, Batch* b, int iters) {
   cudaStream_t s = stream_of(c, b);
+  CK(cudaStreamWaitEvent(s, c->topo_ready, 0));  // a pending snapshot refresh finishes first
   int launches = 0;
   BatchDev d = batch_dev(c, b);
   for (int it = 0; it < iters; ++it) {
@@ -603,6 +631,7 @@ int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int3
   }
   if (cudaEventElapsedTime(&x, b->ev[4], b->ev[5]) == cudaSuccess) tm.d2h_ms = x;
   tm.total_ms = tm.h2d_ms + score + sel + tm.d2h_ms;
+  harvest_base_ms(c);
   tm.base_ms = c->topo.base_ms;
   tm.scores = m.scores;
   tm.algo_bytes = m.algo_bytes;
@@ -670,7 +699,12 @@ int32_t rbgtopo_create(const rbgtopo_config* cfg, rbgtopo_ctx** out) {
   c->cfg = *cfg;
   c->cfg.emit_matrix = 1;  // the dense matrix is always materialised (selection reads patched scores back)
   c->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&c->topo_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->topo_ready, cudaEventDisableTiming));
+  CK(cudaEventCreate(&c->ev_base_a));
+  CK(cudaEventCreate(&c->ev_base_b));
   CK(cudaFuncSetAttribute(k_select_assign_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
+  CK(cudaFuncSetAttribute(k_shard_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
   {
     int occ = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_emit, SCORE_THREADS, 0));
@@ -684,6 +718,10 @@ int32_t rbgtopo_destroy(rbgtopo_ctx* c) {
   if (!c) return RBGTOPO_OK;
   cudaSetDevice(c->cfg.device);
   cudaDeviceSynchronize();
+  if (c->topo_stream) cudaStreamDestroy(c->topo_stream);
+  if (c->topo_ready) cudaEventDestroy(c->topo_ready);
+  if (c->ev_base_a) cudaEventDestroy(c->ev_base_a);
+  if (c->ev_base_b) cudaEventDestroy(c->ev_base_b);
   delete c;
   return RBGTOPO_OK;
 }
@@ -784,7 +822,7 @@ int32_t rbgtopo_set_topology(rbgtopo_ctx* c, int32_t n, int64_t e, const int32_t
     T.h_degp1[i] = row_ptr[i + 1] - row_ptr[i] + 1;
     T.max_degp1 = std::max(T.max_degp1, T.h_degp1[i]);
   }
-  int rc = run_base(c, c->use_ext_stream ? c->ext_stream : (cudaStream_t)0);
+  int rc = run_base(c, c->topo_stream, true);
   if (rc) return rc;
   T.valid = true;
   return RBGTOPO_OK;
@@ -793,22 +831,30 @@ int32_t rbgtopo_set_topology(rbgtopo_ctx* c, int32_t n, int64_t e, const int32_t
 int32_t rbgtopo_update_nodes(rbgtopo_ctx* c, const int32_t* free_slots, const int32_t* owner,
                              uint64_t generation) {
   if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
-  std::unique_lock<std::shared_mutex> lk(c->topo_mu);
+  std::unique_lock<std::shared_mutex> lk(c->topo_mu);  // no batch is in flight while we hold it
   Topology& T = c->topo;
   if (!T.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
   CK(cudaSetDevice(c->cfg.device));
+  cudaStream_t s = c->topo_stream;
+  CK(cudaStreamSynchronize(s));  // the previous refresh no longer reads the pinned staging
   if (free_slots) {
     for (int i = 0; i < T.n; ++i)
       if (free_slots[i] < 0 || free_slots[i] > RBGTOPO_MAX_FREE) return fail(RBGTOPO_EINVAL, "free[%d]", i);
-    CK(cudaMemcpy(T.free_.p, free_slots, (size_t)T.n * 4, cudaMemcpyHostToDevice));
+    CK(c->h_free.reserve((size_t)T.n));
+    memcpy(c->h_free.p, free_slots, (size_t)T.n * 4);
+    CK(cudaMemcpyAsync(T.free_.p, c->h_free.p, (size_t)T.n * 4, cudaMemcpyHostToDevice, s));
   }
   if (owner) {
     for (int d = 0; d < T.n_domains; ++d)
       if (owner[d] < -1) return fail(RBGTOPO_EINVAL, "domain_owner[%d]", d);
-    CK(cudaMemcpy(T.owner.p, owner, (size_t)T.n_domains * 4, cudaMemcpyHostToDevice));
+    CK(c->h_owner.reserve((size_t)T.n_domains));
+    memcpy(c->h_owner.p, owner, (size_t)T.n_domains * 4);
+    CK(cudaMemcpyAsync(T.owner.p, c->h_owner.p, (size_t)T.n_domains * 4, cudaMemcpyHostToDevice, s));
   }
   T.generation = generation;
-  return run_base(c, c->use_ext_stream ? c->ext_stream : (cudaStream_t)0);
+  // asynchronous: the refresh (prep, base SpMV, order sort) overlaps the caller's next host
+  // work; every batch stream waits on topo_ready before reading the snapshot
+  return run_base(c, s, false);
 }
 
 int32_t rbgtopo_score_assign(rbgtopo_ctx* c, const int32_t* blob, int64_t words, int32_t* assign,
@@ -1060,7 +1106,9 @@ struct PlanWave {  // <= RBGTOPO_MAX_STEP_ROLES entries, no heap
   int size() const { return n; }
 };
 
-int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, std::vector<int32_t>* blob, Batch* b) {
+// Builds the plan IN PLACE in b->h_in (pinned); *plan_words = its size.  The GROUPS blob is
+// fully validated here (ranges of every user-provided value), so staging may trust the plan.
+int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_words, Batch* b) {
   if (words < RBGTOPO_HDR_WORDS || gb[0] != RBGTOPO_GROUPS_MAGIC || gb[1] != RBGTOPO_ABI_VERSION || gb[3] != words)
     return fail(RBGTOPO_EINVAL, "bad groups blob header");
   const int ng = gb[2];
@@ -1088,7 +1136,17 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, std::vector<int
     for (int i = 0; i < q; ++i) {
       if (roles[4 * i + 1] < 0 || (i && roles[4 * i] < roles[4 * (i - 1)]))
         return fail(RBGTOPO_EINVAL, "group %d role %d: pending < 0 or levels not ascending", g, i);
+      if (roles[4 * i + 2] < 0 || roles[4 * i + 2] > RBGTOPO_MAX_FREE)
+        return fail(RBGTOPO_EINVAL, "group %d role %d: demand", g, i);
       pend += roles[4 * i + 1];
+    }
+    if (rec[0] < 0 || rec[2] < -1 || rec[2] >= c->topo.n_domains) return fail(RBGTOPO_EINVAL, "group %d: gid / fixed_domain", g);
+    for (int i = 0; i < q * q; ++i)
+      if (gb[rec[5] + i] < 0) return fail(RBGTOPO_EINVAL, "group %d: negative pair weight", g);
+    for (int a = 0; a < rec[6]; ++a) {
+      const int32_t* an = gb + rec[7] + 3 * a;
+      if (an[0] < 0 || an[0] >= c->topo.n || an[1] < 0 || an[1] >= q || an[2] < 0)
+        return fail(RBGTOPO_EINVAL, "group %d anchor %d out of range", g, a);
     }
     if (rec[8] != pacc || rec[9] != pend) return fail(RBGTOPO_EINVAL, "group %d: bad assign_off/n_pending", g);
     b->grp_flags[g] = rec[1];
@@ -1168,9 +1226,13 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, std::vector<int
     if (off > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "plan blob exceeds 2^31 words");
     sec_off[ns] = (int)off;
   }
-  blob->assign((size_t)sec_off[ns], 0);
+  {
+    const size_t total = (size_t)sec_off[ns] + (size_t)ns + 1 + (size_t)c->emit_grid + 1 + 64;  // + poff + cta_item
+    CK(b->h_in.reserve(total));
+    memset(b->h_in.p, 0, (size_t)sec_off[ns] * 4);
+  }
   b->out_index.assign((size_t)pacc, 0);
-  int32_t* const out = blob->data();
+  int32_t* const out = b->h_in.p;
   // pass 2 (group order): fill every step of a group while walking its waves once
   for (int g = 0; g < ng; ++g) {
     const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
@@ -1235,13 +1297,13 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, std::vector<int
     }
   }
   const int racc = rep_off[ns], rowacc = row_off[ns];
-  (*blob)[0] = RBGTOPO_BLOB_MAGIC;
-  (*blob)[1] = RBGTOPO_ABI_VERSION;
-  (*blob)[2] = ns;
-  (*blob)[3] = (int32_t)blob->size();
-  (*blob)[4] = racc;
-  (*blob)[5] = rowacc;
-  (void)c;
+  out[0] = RBGTOPO_BLOB_MAGIC;
+  out[1] = RBGTOPO_ABI_VERSION;
+  out[2] = ns;
+  out[3] = sec_off[ns];
+  out[4] = racc;
+  out[5] = rowacc;
+  *plan_words = sec_off[ns];
   return RBGTOPO_OK;
 }
 
@@ -1290,13 +1352,13 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
     Batch* b = nullptr;
     int rc = acquire_batch(c, &b);
     if (rc) return rc;
-    static thread_local std::vector<int32_t> blob;
+    int64_t plan_words = 0;
     static const bool prof = getenv("RBGTOPO_PROFILE_HOST") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto t0 = now();
-    rc = build_plan(c, gb, words, &blob, b);
+    rc = build_plan(c, gb, words, &plan_words, b);
     auto t1 = now();
-    if (!rc) rc = stage_into(c, b, blob.data(), (int64_t)blob.size());
+    if (!rc) rc = stage_into(c, b, b->h_in.p, plan_words);
     auto t2 = now();
     if (!rc) rc = run_batch(c, b, 1);
     auto t3 = now();
@@ -1320,16 +1382,15 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
 
 int32_t rbgtopo_stage_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int32_t* handle) {
   if (!c || !gb || !handle) return fail(RBGTOPO_EINVAL, "null argument");
-  if (c->cfg.world != 1) return fail(RBGTOPO_EINVAL, "stage_groups needs world == 1");
   std::shared_lock<std::shared_mutex> lk(c->topo_mu);
   if (!c->topo.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
   CK(cudaSetDevice(c->cfg.device));
   Batch* b = nullptr;
   int rc = acquire_batch(c, &b);
   if (rc) return rc;
-  std::vector<int32_t> blob;
-  rc = build_plan(c, gb, words, &blob, b);
-  if (!rc) rc = stage_into(c, b, blob.data(), (int64_t)blob.size());
+  int64_t plan_words = 0;
+  rc = build_plan(c, gb, words, &plan_words, b);
+  if (!rc) rc = stage_into(c, b, b->h_in.p, plan_words);
   if (rc) {
     release_batch(c, b);
     return rc;
@@ -1422,99 +1483,199 @@ int32_t rbgtopo_slab(rbgtopo_ctx* c, int32_t* lo, int32_t* hi) {
   return RBGTOPO_OK;
 }
 
-int32_t rbgtopo_shard_score(rbgtopo_ctx* c, int32_t handle, void** keys_dev, int64_t* keys_bytes) {
+// ---- wave-ranged sharded pipeline.  A step batch (rbgtopo_stage) is one wave; a plan
+// (rbgtopo_stage_groups) has W waves: wave 0's score call also enqueues the ONE
+// k_score_emit launch that writes the background rows of every wave on this rank's slab.
+namespace {
+struct WaveRange { int s0, s1, rr0, rr1, maxp; };
+int wave_range(rbgtopo_ctx* c, Batch* b, int wave, WaveRange* w) {
+  const BatchMeta& m = b->m;
+  if (b->wave_begin.empty()) {
+    if (wave != 0) return fail(RBGTOPO_EINVAL, "wave %d of a single-wave batch", wave);
+    *w = WaveRange{0, m.n_steps, 0, m.total_p, m.max_p};
+    return RBGTOPO_OK;
+  }
+  if (wave < 0 || wave + 1 >= (int)b->wave_begin.size()) return fail(RBGTOPO_EINVAL, "wave %d", wave);
+  w->s0 = b->wave_begin[wave];
+  w->s1 = b->wave_begin[wave + 1];
+  w->maxp = b->wave_maxp[wave];
+  const int32_t* blob = b->h_in.p;  // host copy of the uploaded plan
+  w->rr0 = w->s0 < m.n_steps ? blob[RBGTOPO_HDR_WORDS + (size_t)w->s0 * RBGTOPO_STEP_WORDS + 13] : m.total_p;
+  w->rr1 = w->s1 < m.n_steps ? blob[RBGTOPO_HDR_WORDS + (size_t)w->s1 * RBGTOPO_STEP_WORDS + 13] : m.total_p;
+  (void)c;
+  return RBGTOPO_OK;
+}
+void wave_table(Batch* b, const WaveRange& w, int* CAP, int* HT) {
+  int mc = 0;
+  for (int s = w.s0; s < w.s1; ++s) mc = std::max(mc, b->m.poff[s + 1] - b->m.poff[s]);
+  *CAP = std::max(32, round_up(mc, 32));
+  *HT = 64;
+  while (2 * *HT < 3 * *CAP && *HT < (1 << 20)) *HT <<= 1;
+}
+}  // namespace
+
+int32_t rbgtopo_shard_waves(rbgtopo_ctx* c, int32_t handle, int32_t* n_waves) {
+  if (!c || !n_waves) return fail(RBGTOPO_EINVAL, "null argument");
+  Batch* b = batch_of(c, handle);
+  if (!b) return fail(RBGTOPO_EINVAL, "bad handle %d", handle);
+  *n_waves = b->wave_begin.empty() ? 1 : (int)b->wave_begin.size() - 1;
+  return RBGTOPO_OK;
+}
+
+int32_t rbgtopo_shard_wave_score(rbgtopo_ctx* c, int32_t handle, int32_t wave, void** keys_dev, int64_t* keys_bytes) {
   if (!c || !keys_dev || !keys_bytes) return fail(RBGTOPO_EINVAL, "null argument");
   std::shared_lock<std::shared_mutex> lk(c->topo_mu);
   Batch* b = batch_of(c, handle);
   if (!b) return fail(RBGTOPO_EINVAL, "bad handle %d", handle);
+  WaveRange w;
+  int rc = wave_range(c, b, wave, &w);
+  if (rc) return rc;
   CK(cudaSetDevice(c->cfg.device));
   cudaStream_t s = stream_of(c, b);
-  const bool timed = b->passes < kMaxTimedPasses;
-  const int e0 = 3 * b->passes;
-  if (timed) {
-    int rc0 = ensure_pass_events(b, b->passes + 1);
-    if (rc0) return rc0;
-    CK(cudaEventRecord(b->it_ev[e0], s));
+  int launches = 0;
+  const bool plan = !b->wave_begin.empty();
+  BatchDev d = batch_dev(c, b);
+  if (wave == 0) {
+    CK(cudaStreamWaitEvent(s, c->topo_ready, 0));
+    const bool timed = b->passes < kMaxTimedPasses;
+    const int e0 = 3 * b->passes;
+    if (timed) {
+      int rc0 = ensure_pass_events(b, b->passes + 1);
+      if (rc0) return rc0;
+      CK(cudaEventRecord(b->it_ev[e0], s));
+    }
+    rc = launch_score(c, b, s);  // step batch: its rows + corrections; plan: background of every wave
+    if (rc) return rc;
+    ++launches;
+    if (timed) CK(cudaEventRecord(b->it_ev[e0 + 1], s));
+    b->shard_timed = timed;
   }
-  int rc = launch_score(c, b, s);
-  if (rc) return rc;
-  if (timed) CK(cudaEventRecord(b->it_ev[e0 + 1], s));
-  b->shard_timed = timed;
-  b->pend_launches += 2;
-  if (b->m.n_steps)
-    k_select<<<b->m.n_steps, 32 * b->m.max_p, select_smem_bytes(b->m.max_p), s>>>(topo_dev(c), batch_dev(c, b), 0);
+  const int n = w.s1 - w.s0;
+  if (n > 0) {
+    int CAP, HT;
+    wave_table(b, w, &CAP, &HT);
+    const int nth = std::max(128, 32 * w.maxp);
+    if (fast_smem_bytes(nth / 32, HT, CAP) <= kFastSmemMax) {
+      k_shard_select<<<n, nth, fast_smem_bytes(nth / 32, HT, CAP), s>>>(topo_dev(c), d, w.s0, 0, plan ? SEL_CORRECT : 0, HT, CAP);
+    } else {
+      if (plan) return fail(RBGTOPO_ELIMIT, "plan step with more than %d patched nodes on the sharded path", CAP);
+      k_select<<<n, 32 * w.maxp, select_smem_bytes(w.maxp), s>>>(topo_dev(c), d, 0);
+    }
+    ++launches;
+  }
   CK(cudaGetLastError());
-  *keys_dev = b->lists.p;
-  *keys_bytes = (int64_t)std::max(1, b->m.total_p) * KS * 8;
+  *keys_dev = b->lists.p + (size_t)w.rr0 * KS;
+  *keys_bytes = (int64_t)std::max(1, w.rr1 - w.rr0) * KS * 8;
+  b->pend_launches += launches;
   std::lock_guard<std::mutex> g(c->stat_mu);
-  c->launches += 2;
+  c->launches += launches;
   return RBGTOPO_OK;
 }
 
-int32_t rbgtopo_shard_merge(rbgtopo_ctx* c, int32_t handle, const void* keys_all, int32_t* need_pass2,
-                            void** keys2_dev, int64_t* keys2_bytes) {
+int32_t rbgtopo_shard_wave_merge(rbgtopo_ctx* c, int32_t handle, int32_t wave, const void* keys_all,
+                                 int32_t* need_pass2, void** keys2_dev, int64_t* keys2_bytes) {
   if (!c || !keys_all || !need_pass2 || !keys2_dev || !keys2_bytes) return fail(RBGTOPO_EINVAL, "null argument");
   std::shared_lock<std::shared_mutex> lk(c->topo_mu);
   Batch* b = batch_of(c, handle);
   if (!b) return fail(RBGTOPO_EINVAL, "bad handle %d", handle);
+  WaveRange w;
+  int rc = wave_range(c, b, wave, &w);
+  if (rc) return rc;
   CK(cudaSetDevice(c->cfg.device));
   cudaStream_t s = stream_of(c, b);
   BatchDev d = batch_dev(c, b);
+  const long long rows = std::max(1, w.rr1 - w.rr0);
   d.parts = c->cfg.world;
-  d.lists_all = static_cast<const unsigned long long*>(keys_all);
-  d.part_stride = (long long)std::max(1, b->m.total_p) * KS;
+  d.part_stride = rows * KS;
+  d.lists_all = static_cast<const unsigned long long*>(keys_all) - (long long)w.rr0 * KS;  // indexed by global role row
   int launches = 0;
-  if (b->m.n_steps) {
-    const int grid = (b->m.n_steps + SEL_WARPS - 1) / SEL_WARPS;
-    k_merge<<<grid, SEL_THREADS, 0, s>>>(topo_dev(c), d);
+  const int n = w.s1 - w.s0;
+  // an exclusive group's D* can also appear in a later wave (first placed replica), so plans
+  // take the second pass whenever the GROUP is exclusive and the step has no fixed domain yet;
+  // that is only known on the device -> conservatively: any exclusive step in the wave
+  bool excl_unknown = b->m.any_excl_unknown;
+  if (!b->wave_begin.empty()) {
+    excl_unknown = false;
+    for (int s2 = w.s0; s2 < w.s1 && !excl_unknown; ++s2)
+      excl_unknown = (b->h_in.p[RBGTOPO_HDR_WORDS + (size_t)s2 * RBGTOPO_STEP_WORDS + 1] & RBGTOPO_STEP_EXCLUSIVE) != 0;
+  }
+  if (n > 0) {
+    k_merge<<<(n + SEL_WARPS - 1) / SEL_WARPS, SEL_THREADS, 0, s>>>(topo_dev(c), d, w.s0, n);
     ++launches;
-    if (b->m.any_excl_unknown) {
-      k_select<<<b->m.n_steps, 32 * b->m.max_p, select_smem_bytes(b->m.max_p), s>>>(topo_dev(c), d, 1);
+    if (excl_unknown) {
+      int CAP, HT;
+      wave_table(b, w, &CAP, &HT);
+      const int nth = std::max(128, 32 * w.maxp);
+      if (fast_smem_bytes(nth / 32, HT, CAP) <= kFastSmemMax)
+        k_shard_select<<<n, nth, fast_smem_bytes(nth / 32, HT, CAP), s>>>(topo_dev(c), d, w.s0, 1, 0, HT, CAP);
+      else
+        k_select<<<n, 32 * w.maxp, select_smem_bytes(w.maxp), s>>>(topo_dev(c), d, 1);
       ++launches;
     }
   }
   CK(cudaGetLastError());
-  *need_pass2 = b->m.any_excl_unknown ? 1 : 0;
-  *keys2_dev = b->excl.p;
-  *keys2_bytes = (int64_t)std::max(1, b->m.total_p) * KS * 8;
+  *need_pass2 = excl_unknown ? 1 : 0;
+  *keys2_dev = b->excl.p + (size_t)w.rr0 * KS;
+  *keys2_bytes = (int64_t)rows * KS * 8;
   b->pend_launches += launches;
   std::lock_guard<std::mutex> g(c->stat_mu);
   c->launches += launches;
   return RBGTOPO_OK;
 }
 
-int32_t rbgtopo_shard_assign(rbgtopo_ctx* c, int32_t handle, const void* keys2_all) {
+int32_t rbgtopo_shard_wave_assign(rbgtopo_ctx* c, int32_t handle, int32_t wave, const void* keys2_all) {
   if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
   std::shared_lock<std::shared_mutex> lk(c->topo_mu);
   Batch* b = batch_of(c, handle);
   if (!b) return fail(RBGTOPO_EINVAL, "bad handle %d", handle);
-  if (b->m.any_excl_unknown && !keys2_all) return fail(RBGTOPO_EINVAL, "pass-2 keys required");
+  WaveRange w;
+  int rc = wave_range(c, b, wave, &w);
+  if (rc) return rc;
   CK(cudaSetDevice(c->cfg.device));
   cudaStream_t s = stream_of(c, b);
   BatchDev d = batch_dev(c, b);
   d.parts = c->cfg.world;
+  const long long rows = std::max(1, w.rr1 - w.rr0);
   if (keys2_all) {
-    d.excl_all = static_cast<const unsigned long long*>(keys2_all);
-    d.excl_part_stride = (long long)std::max(1, b->m.total_p) * KS;
+    d.excl_all = static_cast<const unsigned long long*>(keys2_all) - (long long)w.rr0 * KS;
+    d.excl_part_stride = rows * KS;
+  } else {
+    d.parts = 1;  // no second pass: k_greedy never reads excl_all for steps with a fixed / no domain
   }
   int launches = 0;
-  if (b->m.n_steps) {
-    const int grid = (b->m.n_steps + SEL_WARPS - 1) / SEL_WARPS;
-    k_greedy<<<grid, SEL_THREADS, 0, s>>>(topo_dev(c), d);
+  const int n = w.s1 - w.s0;
+  const bool plan = !b->wave_begin.empty();
+  if (n > 0) {
+    k_greedy<<<(n + SEL_WARPS - 1) / SEL_WARPS, SEL_THREADS, 0, s>>>(topo_dev(c), d, w.s0, n, plan ? 1 : 0);
     ++launches;
   }
-  if (b->shard_timed) {
-    CK(cudaEventRecord(b->it_ev[3 * b->passes + 2], s));
-    b->passes += 1;
-    b->shard_timed = false;
+  const bool last = !plan || wave + 2 == (int)b->wave_begin.size();
+  if (last) {
+    if (b->shard_timed) {
+      CK(cudaEventRecord(b->it_ev[3 * b->passes + 2], s));
+      b->passes += 1;
+      b->shard_timed = false;
+    }
+    b->untimed_or_timed_passes += 1;
+    b->ran = true;
   }
-  b->untimed_or_timed_passes += 1;
   CK(cudaGetLastError());
-  b->ran = true;
   b->pend_launches += launches;
   std::lock_guard<std::mutex> g(c->stat_mu);
   c->launches += launches;
   return RBGTOPO_OK;
+}
+
+// single-wave forms (step batches)
+int32_t rbgtopo_shard_score(rbgtopo_ctx* c, int32_t handle, void** keys_dev, int64_t* keys_bytes) {
+  return rbgtopo_shard_wave_score(c, handle, 0, keys_dev, keys_bytes);
+}
+int32_t rbgtopo_shard_merge(rbgtopo_ctx* c, int32_t handle, const void* keys_all, int32_t* need_pass2,
+                            void** keys2_dev, int64_t* keys2_bytes) {
+  return rbgtopo_shard_wave_merge(c, handle, 0, keys_all, need_pass2, keys2_dev, keys2_bytes);
+}
+int32_t rbgtopo_shard_assign(rbgtopo_ctx* c, int32_t handle, const void* keys2_all) {
+  return rbgtopo_shard_wave_assign(c, handle, 0, keys2_all);
 }
 
 int32_t rbgtopo_set_stream(rbgtopo_ctx* c, void* stream) {

@@ -493,10 +493,11 @@ __device__ __forceinline__ int merge_parts(const unsigned long long* src, long l
 }
 
 // ---- world > 1: merged[rolerow] = top-K over the ranks' lists; D* per step
-__global__ void __launch_bounds__(SEL_THREADS) k_merge(TopoDev t, BatchDev b) {
+__global__ void __launch_bounds__(SEL_THREADS) k_merge(TopoDev t, BatchDev b, int step_begin, int count) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int step = blockIdx.x * SEL_WARPS + warp;
-  if (step >= b.n_steps) return;
+  const int idx = blockIdx.x * SEL_WARPS + warp;
+  if (idx >= count) return;
+  const int step = step_begin + idx;
   const StepHdr h = load_hdr(b, step);
   const bool excl_step = (h.flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
   int dstar = excl_step ? h.fixed_domain : -1;
@@ -514,14 +515,23 @@ __global__ void __launch_bounds__(SEL_THREADS) k_merge(TopoDev t, BatchDev b) {
 }
 
 // ---- world > 1: final lists (restricted ones merged over the ranks) + greedy
-__global__ void __launch_bounds__(SEL_THREADS) k_greedy(TopoDev t, BatchDev b) {
+__global__ void __launch_bounds__(SEL_THREADS) k_greedy(TopoDev t, BatchDev b, int step_begin, int count, int chain) {
   __shared__ unsigned long long sList[SEL_WARPS][MAXP][KS];
   __shared__ int sTakenNode[SEL_WARPS][KS];
   __shared__ int sTakenAmt[SEL_WARPS][KS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int step = blockIdx.x * SEL_WARPS + warp;
-  if (step >= b.n_steps) return;
+  const int idx = blockIdx.x * SEL_WARPS + warp;
+  if (idx >= count) return;
+  const int step = step_begin + idx;
   const StepHdr h = load_hdr(b, step);
+  if (h.flags & STEP_SKIP) {  // an earlier wave of this gang group failed
+    for (int i = lane; i < h.R; i += 32) b.assign[h.rep_off + i] = -1;
+    if (lane == 0) {
+      b.status[step] = RBGTOPO_GANG_FAILED;
+      b.domain_out[step] = -1;
+    }
+    return;
+  }
   const bool unknown = (h.flags & RBGTOPO_STEP_EXCLUSIVE) && h.fixed_domain < 0;
   for (int p = 0; p < h.P; ++p) {
     const bool rexcl = (b.blob[h.role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE) != 0;
@@ -532,7 +542,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_greedy(TopoDev t, BatchDev b) {
     sList[warp][p][lane] = mg[lane];
   }
   __syncwarp();
-  greedy_step(t, b, step, h, sList[warp], sTakenNode[warp], sTakenAmt[warp], b.dstar[step]);
+  greedy_step(t, b, step, h, sList[warp], sTakenNode[warp], sTakenAmt[warp], b.dstar[step], chain != 0);
 }
 
 }  // namespace rbgtopo

@@ -153,41 +153,13 @@ __device__ __forceinline__ void select_role_fast(const TopoDev& t, const BatchDe
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(32 * MAXP)
-k_select_assign_fast(TopoDev t, BatchDev b, int step_begin, int mode, int HT, int CAP) {
-  extern __shared__ __align__(16) unsigned char fs_smem[];
-  __shared__ unsigned long long sList[MAXP][KS], sAcc[MAXP][KS], sPat[MAXP][KS];
-  __shared__ int sListAv[MAXP][KS], sAccAv[MAXP][KS], sPatAv[MAXP][KS];
-  __shared__ int sTakenNode[KS], sTakenAmt[KS];
-  __shared__ int sDstar, sCnt;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthreads = blockDim.x, nwarps = nthreads >> 5;
-  const int PB = nwarps;
-  PatchTab T;
-  T.node = reinterpret_cast<int*>(fs_smem);
-  T.cons = T.node + HT;
-  T.delta = reinterpret_cast<float*>(T.cons + HT);
-  T.mask = HT - 1;
-  T.dSlot = reinterpret_cast<int*>(T.delta + (size_t)PB * HT);
-  T.dBase = reinterpret_cast<float*>(T.dSlot + CAP);
-  T.dAvail = reinterpret_cast<int*>(T.dBase + CAP);
-  T.dDom = T.dAvail + CAP;
-  T.cnt = 0;
-
-  const int step = step_begin + blockIdx.x;
-  const StepHdr h = load_hdr(b, step);
+// Steps 0-2 of the kernels below: fill the shared-memory table of the step's patched
+// nodes (+ the dense view), optionally issuing the matrix corrections.  Whole CTA.
+__device__ __forceinline__ void build_table(const TopoDev& t, const BatchDev& b, const StepHdr& h, PatchTab& T, int HT,
+                                            int PB, bool correct, int* sCntp) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
   const bool excl_step = (h.flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
-  if (h.flags & STEP_SKIP) {  // an earlier wave of this gang group failed: nothing is placed
-    if (warp == 0) {
-      for (int i = lane; i < h.R; i += 32) b.assign[h.rep_off + i] = -1;
-      if (lane == 0) {
-        b.status[step] = RBGTOPO_GANG_FAILED;
-        b.domain_out[step] = -1;
-        b.dstar[step] = -1;
-      }
-    }
-    return;
-  }
-
+  int& sCnt = *sCntp;
   // ---- 0. empty table
   for (int i = tid; i < HT; i += nthreads) {
     T.node[i] = -1;
@@ -200,7 +172,6 @@ k_select_assign_fast(TopoDev t, BatchDev b, int step_begin, int mode, int HT, in
   // ---- 1. anchors -> slots (+ matrix corrections when asked), consumed capacity
   const size_t stride = (size_t)t.slab_stride;
   float* const mrow0 = b.matrix + (size_t)h.rep_off * stride - t.slab_lo;  // mrow0[node]
-  const bool correct = (mode & SEL_CORRECT) != 0;
   {
     const int* anc = b.blob + h.anchor_off;
     for (int a = warp; a < h.n_anchors; a += nwarps) {
@@ -277,6 +248,45 @@ k_select_assign_fast(TopoDev t, BatchDev b, int step_begin, int mode, int HT, in
   __syncthreads();
   T.cnt = sCnt;
 
+}
+
+__global__ void __launch_bounds__(32 * MAXP)
+k_select_assign_fast(TopoDev t, BatchDev b, int step_begin, int mode, int HT, int CAP) {
+  extern __shared__ __align__(16) unsigned char fs_smem[];
+  __shared__ unsigned long long sList[MAXP][KS], sAcc[MAXP][KS], sPat[MAXP][KS];
+  __shared__ int sListAv[MAXP][KS], sAccAv[MAXP][KS], sPatAv[MAXP][KS];
+  __shared__ int sTakenNode[KS], sTakenAmt[KS];
+  __shared__ int sDstar, sCnt;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthreads = blockDim.x, nwarps = nthreads >> 5;
+  const int PB = nwarps;
+  PatchTab T;
+  T.node = reinterpret_cast<int*>(fs_smem);
+  T.cons = T.node + HT;
+  T.delta = reinterpret_cast<float*>(T.cons + HT);
+  T.mask = HT - 1;
+  T.dSlot = reinterpret_cast<int*>(T.delta + (size_t)PB * HT);
+  T.dBase = reinterpret_cast<float*>(T.dSlot + CAP);
+  T.dAvail = reinterpret_cast<int*>(T.dBase + CAP);
+  T.dDom = T.dAvail + CAP;
+  T.cnt = 0;
+
+  const int step = step_begin + blockIdx.x;
+  const StepHdr h = load_hdr(b, step);
+  const bool excl_step = (h.flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
+  if (h.flags & STEP_SKIP) {  // an earlier wave of this gang group failed: nothing is placed
+    if (warp == 0) {
+      for (int i = lane; i < h.R; i += 32) b.assign[h.rep_off + i] = -1;
+      if (lane == 0) {
+        b.status[step] = RBGTOPO_GANG_FAILED;
+        b.domain_out[step] = -1;
+        b.dstar[step] = -1;
+      }
+    }
+    return;
+  }
+
+  build_table(t, b, h, T, HT, PB, (mode & SEL_CORRECT) != 0, &sCnt);
+
   // ---- 3. exclusive domain, selection
   int dstar = excl_step ? h.fixed_domain : -1;
   if (excl_step && h.fixed_domain < 0) {
@@ -350,6 +360,52 @@ k_select_assign_fast(TopoDev t, BatchDev b, int step_begin, int mode, int HT, in
       b.dstar[step] = dstar;
     }
     if ((mode & SEL_CHAIN) && h.next_step > 0) chain_step(b, h, status, dstar);
+  }
+}
+
+// ---- world > 1: rank-local lists of the steps [step_begin, step_begin + gridDim.x).
+// pass2 == 0: every role row (exclusive roles of steps WITHOUT a fixed domain are selected
+// unrestricted: their top-1 decides D* after the all-gather) into b.lists; the matrix
+// corrections of multi-wave plans are issued here (mode & SEL_CORRECT).
+// pass2 == 1: those exclusive roles again, restricted to D*, into b.excl.
+__global__ void __launch_bounds__(32 * MAXP)
+k_shard_select(TopoDev t, BatchDev b, int step_begin, int pass2, int mode, int HT, int CAP) {
+  extern __shared__ __align__(16) unsigned char fs_smem[];
+  __shared__ unsigned long long sAcc[MAXP][KS], sPat[MAXP][KS], sOut[MAXP][KS];
+  __shared__ int sAccAv[MAXP][KS], sPatAv[MAXP][KS], sOutAv[MAXP][KS];
+  __shared__ int sCnt;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, PB = blockDim.x >> 5;
+  PatchTab T;
+  T.node = reinterpret_cast<int*>(fs_smem);
+  T.cons = T.node + HT;
+  T.delta = reinterpret_cast<float*>(T.cons + HT);
+  T.mask = HT - 1;
+  T.dSlot = reinterpret_cast<int*>(T.delta + (size_t)PB * HT);
+  T.dBase = reinterpret_cast<float*>(T.dSlot + CAP);
+  T.dAvail = reinterpret_cast<int*>(T.dBase + CAP);
+  T.dDom = T.dAvail + CAP;
+  T.cnt = 0;
+  const int step = step_begin + blockIdx.x;
+  const StepHdr h = load_hdr(b, step);
+  const bool excl_step = (h.flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
+  const bool unknown = excl_step && h.fixed_domain < 0;
+  if ((h.flags & STEP_SKIP) || (pass2 && !unknown)) {  // CTA-uniform
+    if (!pass2 && warp < h.P) b.lists[(size_t)(h.rolerow_off + warp) * KS + lane] = 0;
+    return;
+  }
+  build_table(t, b, h, T, HT, PB, !pass2 && (mode & SEL_CORRECT) != 0, &sCnt);
+  if (warp >= h.P) return;
+  const int p = warp;
+  const bool rexcl = excl_step && (b.blob[h.role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE);
+  const int K = role_k(b, h, p, t.n);
+  if (!pass2) {
+    const int dom = (rexcl && !unknown) ? h.fixed_domain : DOM_ANY;
+    select_role_fast(t, b, h, p, K, dom, T, sAcc[p], sAccAv[p], sPat[p], sPatAv[p], sOut[p], sOutAv[p]);
+    b.lists[(size_t)(h.rolerow_off + p) * KS + lane] = sOut[p][lane];
+  } else if (rexcl) {
+    const int d = b.dstar[step];
+    select_role_fast(t, b, h, p, K, d >= 0 ? d : DOM_NONE, T, sAcc[p], sAccAv[p], sPat[p], sPatAv[p], sOut[p], sOutAv[p]);
+    b.excl[(size_t)(h.rolerow_off + p) * KS + lane] = sOut[p][lane];
   }
 }
 

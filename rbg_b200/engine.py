@@ -141,6 +141,26 @@ class TopoPlacer:
         self._check(self.lib.rbgtopo_slab(self._h, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
 
+    def shard_waves(self, handle: int) -> int:
+        n = C.c_int32()
+        self._check(self.lib.rbgtopo_shard_waves(self._h, handle, C.byref(n)))
+        return n.value
+
+    def shard_wave_score(self, handle: int, wave: int) -> Tuple[int, int]:
+        p, nb = C.c_void_p(), C.c_int64()
+        self._check(self.lib.rbgtopo_shard_wave_score(self._h, handle, wave, C.byref(p), C.byref(nb)))
+        return p.value, nb.value
+
+    def shard_wave_merge(self, handle: int, wave: int, keys_all_ptr: int) -> Tuple[bool, int, int]:
+        need, p, nb = C.c_int32(), C.c_void_p(), C.c_int64()
+        self._check(self.lib.rbgtopo_shard_wave_merge(self._h, handle, wave, C.c_void_p(keys_all_ptr), C.byref(need),
+                                                      C.byref(p), C.byref(nb)))
+        return bool(need.value), p.value, nb.value
+
+    def shard_wave_assign(self, handle: int, wave: int, keys2_all_ptr: Optional[int]) -> None:
+        self._check(self.lib.rbgtopo_shard_wave_assign(self._h, handle, wave,
+                                                       C.c_void_p(keys2_all_ptr) if keys2_all_ptr else None))
+
     def shard_score(self, handle: int) -> Tuple[int, int]:
         p, nb = C.c_void_p(), C.c_int64()
         self._check(self.lib.rbgtopo_shard_score(self._h, handle, C.byref(p), C.byref(nb)))

@@ -54,6 +54,44 @@ for n, seed, excl in [(4096, 1, False), (10000, 2, True), (3000, 3, True)]:
     for rr in range(ref["topk"].shape[0]):
         assert np.array_equal(eng.read_topk(h, rr, 32), ref["topk"][rr]), (rank, rr)
     eng.release(h); eng.close()
+# ---- whole groups through the sharded multi-wave plan (one emit launch per rank, per-wave
+#      select -> all-gather -> merge -> assign, placements chained on every rank)
+from rbg_b200.plugin import B200TopoPodGroupManager
+from test_gpu_groups import _fleet
+from test_plugin_host import OraclePlacer
+for n, kw in [(8000, {}), (6000, dict(excl_every=3, gang_every=4)), (5000, dict(big_every=5))]:
+    topo = synth.make_topology(n, seed=n, tiers=4, owned_frac=0.2 if kw.get("excl_every") else 0.0)
+    rbgs = _fleet(n, 24, seed=9, **kw)
+    ref = B200TopoPodGroupManager(OraclePlacer(topo)).reconcile_pod_groups_by_waves(rbgs)
+    eng = TopoPlacer(device=local, rank=rank, world=world)
+    eng.set_topology(topo.row_ptr, topo.col_idx, topo.edge_w, topo.free, topo.domain, topo.domain_owner)
+    eng.set_stream(stream.cuda_stream)
+    gblob, runs = B200TopoPodGroupManager(eng).groups_blob(rbgs)
+    h = eng.stage_groups(gblob)
+    for w in range(eng.shard_waves(h)):
+        p, nb = eng.shard_wave_score(h, w)
+        src = torch.as_tensor(DevPtr(p, nb), device="cuda")
+        allk = torch.empty(world * (nb // 8), dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(allk, src)
+        need2, p2, nb2 = eng.shard_wave_merge(h, w, allk.data_ptr())
+        all2 = None
+        if need2:
+            src2 = torch.as_tensor(DevPtr(p2, nb2), device="cuda")
+            all2 = torch.empty(world * (nb2 // 8), dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(all2, src2)
+        eng.shard_wave_assign(h, w, all2.data_ptr() if all2 is not None else None)
+    assign, status, domain = eng.fetch(h)
+    off = 0
+    for i, (g, r) in enumerate(zip(runs, ref)):
+        want = list(r.nodes.values())
+        got = assign[off:off + len(want)].tolist()
+        off += len(want)
+        if r.status == 1:      # plan leaves non-gang partial groups to the host loop: only the status is checked
+            assert status[i] == 1, (rank, n, i)
+            continue
+        assert got == want, (rank, n, i, got, want)
+        assert status[i] == r.status and domain[i] == r.domain, (rank, n, i, status[i], r.status, domain[i], r.domain)
+    eng.release(h); eng.close()
 dist.barrier()
 if rank == 0: print("SHARD_OK", world)
 dist.destroy_process_group()
