@@ -176,6 +176,7 @@ constexpr size_t kFastSmemMax = 200 * 1024;
 // stream concurrently with k_score_emit.  Measured no gain (the latency-bound wave kernels
 // slow down behind the saturated memory system), so the serial pipeline is the default.
 const bool kSerialPlan = getenv("RBGTOPO_CONCURRENT_PLAN") == nullptr;
+const int kHostThreads = getenv("RBGTOPO_HOST_THREADS") ? std::max(1, atoi(getenv("RBGTOPO_HOST_THREADS"))) : 4;
 const int kEmitOcc = getenv("RBGTOPO_EMIT_OCC") ? atoi(getenv("RBGTOPO_EMIT_OCC")) : 6;  // opt-in dynamic smem of k_select_assign_fast
 
 void compute_slab(rbgtopo_ctx* c, int n) {
@@ -297,18 +298,21 @@ int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, Batc
   long long racc = 0, pacc = 0;
   *m = BatchMeta{};
   m->poff.assign((size_t)ns + 1, 0);
+  int* const pcs = m->poff.data() + 1;  // per-step patch capacity first, prefix-summed below
   auto in = [&](long long off, long long cnt) { return off >= 0 && cnt >= 0 && off + cnt <= words; };
-  for (int s = 0; s < ns; ++s) {
+#define STEP_FAIL(code, ...) return report ? fail(code, __VA_ARGS__) : (int)(code)
+  // Everything about step s that does not depend on the steps before it.  report=false: code only
+  // (called from worker threads); report=true: also formats the message.
+  auto check_step = [&](int s, bool report) -> int {
     const int32_t* st = blob + RBGTOPO_HDR_WORDS + (int64_t)s * RBGTOPO_STEP_WORDS;
     const int P = st[3], Q = st[5], na = st[7], nc = st[9], R = st[11];
-    if (st[0] < 0) return fail(RBGTOPO_EINVAL, "step %d: gid < 0", s);
-    if (P < 1 || P > RBGTOPO_MAX_STEP_ROLES) return fail(RBGTOPO_ELIMIT, "step %d: %d roles", s, P);
-    if (Q < 0 || Q > RBGTOPO_MAX_GROUP_ROLES) return fail(RBGTOPO_ELIMIT, "step %d: q=%d", s, Q);
-    if (R < 1 || R > RBGTOPO_MAX_STEP_REPLICAS) return fail(RBGTOPO_ELIMIT, "step %d: %d replicas", s, R);
+    if (st[0] < 0) STEP_FAIL(RBGTOPO_EINVAL, "step %d: gid < 0", s);
+    if (P < 1 || P > RBGTOPO_MAX_STEP_ROLES) STEP_FAIL(RBGTOPO_ELIMIT, "step %d: %d roles", s, P);
+    if (Q < 0 || Q > RBGTOPO_MAX_GROUP_ROLES) STEP_FAIL(RBGTOPO_ELIMIT, "step %d: q=%d", s, Q);
+    if (R < 1 || R > RBGTOPO_MAX_STEP_REPLICAS) STEP_FAIL(RBGTOPO_ELIMIT, "step %d: %d replicas", s, R);
     if (!in(st[4], 4LL * P) || !in(st[6], (long long)P * Q) || !in(st[8], 3LL * na) || !in(st[10], 2LL * nc))
-      return fail(RBGTOPO_EINVAL, "step %d: section out of bounds", s);
-    if (st[12] != racc || st[13] != pacc) return fail(RBGTOPO_EINVAL, "step %d: bad prefix offsets", s);
-    if (st[2] < -1 || st[2] >= T.n_domains) return fail(RBGTOPO_EINVAL, "step %d: fixed_domain", s);
+      STEP_FAIL(RBGTOPO_EINVAL, "step %d: section out of bounds", s);
+    if (st[2] < -1 || st[2] >= T.n_domains) STEP_FAIL(RBGTOPO_EINVAL, "step %d: fixed_domain", s);
     const int32_t* roles = blob + st[4];
     const int32_t* pair = blob + st[6];
     const int32_t* anc = blob + st[8];
@@ -317,43 +321,58 @@ int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, Batc
     for (int p = 0; p < P; ++p) {
       if (roles[4 * p] < 1 || roles[4 * p + 1] < 0 || roles[4 * p + 1] > RBGTOPO_MAX_FREE ||
           roles[4 * p + 2] < 0)
-        return fail(RBGTOPO_EINVAL, "step %d role %d: count/demand/need", s, p);
+        STEP_FAIL(RBGTOPO_EINVAL, "step %d role %d: count/demand/need", s, p);
       rsum += roles[4 * p];
     }
-    if (rsum != R) return fail(RBGTOPO_EINVAL, "step %d: role counts sum to %d, R=%d", s, rsum, R);
+    if (rsum != R) STEP_FAIL(RBGTOPO_EINVAL, "step %d: role counts sum to %d, R=%d", s, rsum, R);
     if (!trusted) {
       for (int i = 0; i < P * Q; ++i)
-        if (pair[i] < 0) return fail(RBGTOPO_EINVAL, "step %d: negative pair weight", s);
+        if (pair[i] < 0) STEP_FAIL(RBGTOPO_EINVAL, "step %d: negative pair weight", s);
       for (int a = 0; a < na; ++a) {
         if (anc[3 * a] < 0 || anc[3 * a] >= T.n || anc[3 * a + 1] < 0 || anc[3 * a + 1] >= Q ||
             anc[3 * a + 2] < 0)
-          return fail(RBGTOPO_EINVAL, "step %d anchor %d out of range", s, a);
+          STEP_FAIL(RBGTOPO_EINVAL, "step %d anchor %d out of range", s, a);
       }
       for (int i = 0; i < nc; ++i)
         if (con[2 * i] < 0 || con[2 * i] >= T.n || con[2 * i + 1] < 0 || con[2 * i + 1] > RBGTOPO_MAX_FREE)
-          return fail(RBGTOPO_EINVAL, "step %d consumed %d out of range", s, i);
+          STEP_FAIL(RBGTOPO_EINVAL, "step %d consumed %d out of range", s, i);
     }
     // exactness contract (spec §3.4), conservative: every anchor on one node
     for (int p = 0; p < P; ++p) {
       long long amax = (long long)roles[4 * p + 2] * RBGTOPO_F_CAP;
       for (int a = 0; a < na; ++a) amax += (long long)pair[p * Q + anc[3 * a + 1]] * anc[3 * a + 2];
       if (amax * row_w >= (1LL << 24))
-        return fail(RBGTOPO_EINEXACT, "step %d role %d: max score bound %lld >= 2^24", s, p, amax * row_w);
+        STEP_FAIL(RBGTOPO_EINEXACT, "step %d role %d: max score bound %lld >= 2^24", s, p, amax * row_w);
     }
-    if (st[4] & 3) return fail(RBGTOPO_EINVAL, "step %d: role_off must be a multiple of 4 words", s);
-    // patched-node scratch: closed neighbourhoods of the anchors + consumed nodes
+    if (st[4] & 3) STEP_FAIL(RBGTOPO_EINVAL, "step %d: role_off must be a multiple of 4 words", s);
     if (st[15] < 0 || st[15] > na || (st[14] != 0 && (st[14] <= s || st[14] >= ns)))
-      return fail(RBGTOPO_EINVAL, "step %d: bad wave links", s);
-    long long pc = nc;  // records of earlier waves (the last st[15]) are filled on the device: any node
+      STEP_FAIL(RBGTOPO_EINVAL, "step %d: bad wave links", s);
+    // patched-node scratch: closed neighbourhoods of the anchors + consumed nodes.  Records of
+    // earlier waves (the last st[15]) are filled on the device: any node.
+    long long pc = nc;
     for (int a = 0; a < na; ++a) pc += a < na - st[15] ? T.h_degp1[anc[3 * a]] : T.max_degp1;
+    if (pc > 0x7FFFFFF0LL) STEP_FAIL(RBGTOPO_ELIMIT, "step %d: patch list exceeds 2^31 entries", s);
+    pcs[s] = (int)pc;
+    return RBGTOPO_OK;
+  };
+#undef STEP_FAIL
+  int first_bad = ns;
+#pragma omp parallel for schedule(static) num_threads(kHostThreads) reduction(min : first_bad) if (ns >= 256 && kHostThreads > 1)
+  for (int s = 0; s < ns; ++s)
+    if (check_step(s, false) != RBGTOPO_OK) first_bad = std::min(first_bad, s);
+  if (first_bad < ns) return check_step(first_bad, true);
+  for (int s = 0; s < ns; ++s) {  // the prefix-dependent part
+    const int32_t* st = blob + RBGTOPO_HDR_WORDS + (int64_t)s * RBGTOPO_STEP_WORDS;
+    if (st[12] != racc || st[13] != pacc) return fail(RBGTOPO_EINVAL, "step %d: bad prefix offsets", s);
+    const long long pc = pcs[s];
     if (m->patch_cap + pc > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "patch lists exceed 2^31 entries");
     m->patch_cap += pc;
     m->max_cap = (int)std::max<long long>(m->max_cap, std::min<long long>(pc, 1 << 30));
-    m->poff[s + 1] = (int)m->patch_cap;
-    racc += R;
-    pacc += P;
-    m->max_p = std::max(m->max_p, P);
-    m->max_k = std::max(m->max_k, R);
+    pcs[s] = (int)m->patch_cap;
+    racc += st[11];
+    pacc += st[3];
+    m->max_p = std::max(m->max_p, st[3]);
+    m->max_k = std::max(m->max_k, st[11]);
     if ((st[1] & RBGTOPO_STEP_EXCLUSIVE) && st[2] < 0) m->any_excl_unknown = true;
   }
   if (blob[4] != racc || blob[5] != pacc) return fail(RBGTOPO_EINVAL, "blob totals mismatch");
@@ -1115,46 +1134,20 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
   if (ng < 0 || (int64_t)RBGTOPO_HDR_WORDS + (int64_t)ng * RBGTOPO_GROUP_WORDS > words)
     return fail(RBGTOPO_EINVAL, "group table exceeds blob");
   auto in = [&](long long off, long long cnt) { return off >= 0 && cnt >= 0 && off + cnt <= words; };
+  static const bool prof = getenv("RBGTOPO_PROFILE_HOST") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto us = [](auto a, auto b2) { return (long)std::chrono::duration_cast<std::chrono::microseconds>(b2 - a).count(); };
+  const auto p0 = now();
   // flat wave table (thread-local scratch keeps its capacity across calls)
   static thread_local std::vector<PlanWave> wv;
   static thread_local std::vector<int> wv_off, step_flat;
-  wv.clear();
   wv_off.assign((size_t)ng + 1, 0);
-  size_t W = 0;
-  long long pacc = 0;
-  b->grp_flags.assign(ng, 0);
-  b->grp_assign_off.assign(ng, 0);
-  b->grp_pending.assign(ng, 0);
-  for (int g = 0; g < ng; ++g) {
-    const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
-    const int q = rec[3];
-    if (q < 1 || q > RBGTOPO_MAX_GROUP_ROLES) return fail(RBGTOPO_ELIMIT, "group %d: %d roles", g, q);
-    if (!in(rec[4], 4LL * q) || !in(rec[5], (long long)q * q) || !in(rec[7], 3LL * rec[6]))
-      return fail(RBGTOPO_EINVAL, "group %d: section out of bounds", g);
-    const int32_t* roles = gb + rec[4];
-    long long pend = 0;
-    for (int i = 0; i < q; ++i) {
-      if (roles[4 * i + 1] < 0 || (i && roles[4 * i] < roles[4 * (i - 1)]))
-        return fail(RBGTOPO_EINVAL, "group %d role %d: pending < 0 or levels not ascending", g, i);
-      if (roles[4 * i + 2] < 0 || roles[4 * i + 2] > RBGTOPO_MAX_FREE)
-        return fail(RBGTOPO_EINVAL, "group %d role %d: demand", g, i);
-      pend += roles[4 * i + 1];
-    }
-    if (rec[0] < 0 || rec[2] < -1 || rec[2] >= c->topo.n_domains) return fail(RBGTOPO_EINVAL, "group %d: gid / fixed_domain", g);
-    for (int i = 0; i < q * q; ++i)
-      if (gb[rec[5] + i] < 0) return fail(RBGTOPO_EINVAL, "group %d: negative pair weight", g);
-    for (int a = 0; a < rec[6]; ++a) {
-      const int32_t* an = gb + rec[7] + 3 * a;
-      if (an[0] < 0 || an[0] >= c->topo.n || an[1] < 0 || an[1] >= q || an[2] < 0)
-        return fail(RBGTOPO_EINVAL, "group %d anchor %d out of range", g, a);
-    }
-    if (rec[8] != pacc || rec[9] != pend) return fail(RBGTOPO_EINVAL, "group %d: bad assign_off/n_pending", g);
-    b->grp_flags[g] = rec[1];
-    b->grp_assign_off[g] = (int)pacc;
-    b->grp_pending[g] = (int)pend;
-    pacc += pend;
-    // static wave structure: same rule as the host loop / plugin.py
-    int cr = 0, taken = 0;
+  b->grp_flags.resize(ng);
+  b->grp_assign_off.resize(ng);
+  b->grp_pending.resize(ng);
+  // static wave structure: same rule as the host loop / plugin.py.  out == nullptr: count only.
+  auto gen_waves = [](const int32_t* roles, int q, PlanWave* out) -> int {
+    int cr = 0, taken = 0, nw = 0;
     while (cr < q) {
       if (roles[4 * cr + 1] - taken <= 0) { ++cr; taken = 0; continue; }
       PlanWave w;
@@ -1169,71 +1162,150 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
         taken += take;
         if (taken == roles[4 * cr + 1]) { ++cr; taken = 0; }
       }
-      wv.push_back(w);
+      if (out) out[nw] = w;
+      ++nw;
     }
-    wv_off[g + 1] = (int)wv.size();
-    W = std::max(W, (size_t)(wv_off[g + 1] - wv_off[g]));
+    return nw;
+  };
+#define GROUP_FAIL(code, ...) return report ? fail(code, __VA_ARGS__) : (int)(code)
+  int* const g_pend = b->grp_pending.data();
+  int* const g_nw = wv_off.data() + 1;  // per-group wave count first, prefix-summed below
+  const int n_nodes = c->topo.n, n_domains = c->topo.n_domains;
+  auto check_group = [&](int g, bool report) -> int {
+    const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
+    const int q = rec[3];
+    if (q < 1 || q > RBGTOPO_MAX_GROUP_ROLES) GROUP_FAIL(RBGTOPO_ELIMIT, "group %d: %d roles", g, q);
+    if (!in(rec[4], 4LL * q) || !in(rec[5], (long long)q * q) || !in(rec[7], 3LL * rec[6]))
+      GROUP_FAIL(RBGTOPO_EINVAL, "group %d: section out of bounds", g);
+    const int32_t* roles = gb + rec[4];
+    long long pend = 0;
+    for (int i = 0; i < q; ++i) {
+      if (roles[4 * i + 1] < 0 || (i && roles[4 * i] < roles[4 * (i - 1)]))
+        GROUP_FAIL(RBGTOPO_EINVAL, "group %d role %d: pending < 0 or levels not ascending", g, i);
+      if (roles[4 * i + 2] < 0 || roles[4 * i + 2] > RBGTOPO_MAX_FREE)
+        GROUP_FAIL(RBGTOPO_EINVAL, "group %d role %d: demand", g, i);
+      pend += roles[4 * i + 1];
+    }
+    if (pend > 0x3FFFFFFFLL) GROUP_FAIL(RBGTOPO_ELIMIT, "group %d: pending replicas", g);
+    if (rec[0] < 0 || rec[2] < -1 || rec[2] >= n_domains) GROUP_FAIL(RBGTOPO_EINVAL, "group %d: gid / fixed_domain", g);
+    for (int i = 0; i < q * q; ++i)
+      if (gb[rec[5] + i] < 0) GROUP_FAIL(RBGTOPO_EINVAL, "group %d: negative pair weight", g);
+    for (int a = 0; a < rec[6]; ++a) {
+      const int32_t* an = gb + rec[7] + 3 * a;
+      if (an[0] < 0 || an[0] >= n_nodes || an[1] < 0 || an[1] >= q || an[2] < 0)
+        GROUP_FAIL(RBGTOPO_EINVAL, "group %d anchor %d out of range", g, a);
+    }
+    g_pend[g] = (int)pend;
+    g_nw[g] = gen_waves(roles, q, nullptr);
+    return RBGTOPO_OK;
+  };
+#undef GROUP_FAIL
+  int first_bad = ng;
+#pragma omp parallel for schedule(static) num_threads(kHostThreads) reduction(min : first_bad) if (ng >= 64 && kHostThreads > 1)
+  for (int g = 0; g < ng; ++g)
+    if (check_group(g, false) != RBGTOPO_OK) first_bad = std::min(first_bad, g);
+  if (first_bad < ng) return check_group(first_bad, true);
+  size_t W = 0;
+  long long pacc = 0;
+  for (int g = 0; g < ng; ++g) {  // prefixes
+    const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
+    if (rec[8] != pacc || rec[9] != g_pend[g]) return fail(RBGTOPO_EINVAL, "group %d: bad assign_off/n_pending", g);
+    b->grp_flags[g] = rec[1];
+    b->grp_assign_off[g] = (int)pacc;
+    pacc += g_pend[g];
+    if (pacc > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "pending replicas exceed 2^31");
+    W = std::max(W, (size_t)g_nw[g]);
+    wv_off[g + 1] = wv_off[g] + g_nw[g];
   }
-  auto nwaves = [&](int g) { return (size_t)(wv_off[g + 1] - wv_off[g]); };
-  auto wave = [&](int g, size_t w) -> const PlanWave& { return wv[wv_off[g] + w]; };
   if (gb[4] != pacc) return fail(RBGTOPO_EINVAL, "total pending mismatch");
+  wv.resize((size_t)wv_off[ng]);
+  {
+    PlanWave* const wout = wv.data();
+    const int* const wo = wv_off.data();
+#pragma omp parallel for schedule(static) num_threads(kHostThreads) if (ng >= 64 && kHostThreads > 1)
+    for (int g = 0; g < ng; ++g) {
+      const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
+      gen_waves(gb + rec[4], rec[3], wout + wo[g]);
+    }
+  }
+  const auto p1 = now();
 
-  // step numbering, wave-major: step_flat[wv_off[g] + w]
-  step_flat.assign(wv.size(), 0);
-  auto step_of = [&](int g, size_t w) -> int& { return step_flat[wv_off[g] + w]; };
-  int ns = 0;
+  // step numbering (wave-major) fused with pass 1 (step order): section sizes -> offsets,
+  // replica / role-row prefixes
+  const int ns = wv_off[ng];
+  step_flat.resize((size_t)ns);
+  static thread_local std::vector<int> sec_off, rep_off, row_off, i0_of;
+  sec_off.resize((size_t)ns + 1);
+  rep_off.resize((size_t)ns + 1);
+  row_off.resize((size_t)ns + 1);
+  i0_of.assign(ng, 0);
   b->wave_begin.assign(1, 0);
   b->wave_maxp.clear();
-  b->step_group.clear();
-  for (size_t w = 0; w < W; ++w) {
-    int mp = 1;
-    for (int g = 0; g < ng; ++g)
-      if (w < nwaves(g)) {
-        step_of(g, w) = ns++;
-        b->step_group.push_back(g);
-        mp = std::max(mp, wave(g, w).size());
-      }
-    b->wave_begin.push_back(ns);
-    b->wave_maxp.push_back(mp);
-  }
-  // pass 1 (step order): section sizes -> offsets, replica / role-row prefixes
-  static thread_local std::vector<int> sec_off, rep_off, row_off;
-  sec_off.assign((size_t)ns + 1, 0);
-  rep_off.assign((size_t)ns + 1, 0);
-  row_off.assign((size_t)ns + 1, 0);
+  b->step_group.resize((size_t)ns);
   {
+    const PlanWave* const wvp0 = wv.data();
+    const int* const wo = wv_off.data();
+    int* const stf0 = step_flat.data();
+    int* const sg = b->step_group.data();
+    int* const so = sec_off.data();
+    int* const ro = rep_off.data();
+    int* const wo2 = row_off.data();
+    int* const i0p = i0_of.data();
     long long off = (long long)RBGTOPO_HDR_WORDS + (long long)ns * RBGTOPO_STEP_WORDS;  // multiple of 4
     int s = 0;
-    static thread_local std::vector<int> i0_of;  // per group, replicas before the current wave
-    i0_of.assign(ng, 0);
-    for (size_t w = 0; w < W; ++w)
+    ro[0] = 0;
+    wo2[0] = 0;
+    for (size_t w = 0; w < W; ++w) {
+      int mp = 1;
       for (int g = 0; g < ng; ++g) {
-        if (w >= nwaves(g)) continue;
+        if (w >= (size_t)(wo[g + 1] - wo[g])) continue;
         const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
-        const PlanWave& pw = wave(g, w);
+        const PlanWave& pw = wvp0[wo[g] + w];
+        stf0[wo[g] + w] = s;
+        sg[s] = g;
+        mp = std::max(mp, pw.size());
         int n = 0;
         for (int k = 0; k < pw.size(); ++k) n += pw.count[k];
-        const int i0 = i0_of[g];
+        const int i0 = i0p[g];
         long long sz = 4LL * pw.size() + (long long)pw.size() * rec[3] + 3LL * (rec[6] + i0) + 2LL * i0;
         sz = (sz + 3) & ~3LL;  // keeps every role section 16-byte aligned
-        sec_off[s] = (int)off;
+        so[s] = (int)std::min<long long>(off, 0x7FFFFFF0LL);
         off += sz;
-        rep_off[s + 1] = rep_off[s] + n;
-        row_off[s + 1] = row_off[s] + pw.size();
-        i0_of[g] = i0 + n;
+        ro[s + 1] = ro[s] + n;
+        wo2[s + 1] = wo2[s] + pw.size();
+        i0p[g] = i0 + n;
         ++s;
       }
+      b->wave_begin.push_back(s);
+      b->wave_maxp.push_back(mp);
+    }
     if (off > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "plan blob exceeds 2^31 words");
-    sec_off[ns] = (int)off;
+    so[ns] = (int)off;
   }
+  const auto p2 = now();
+  const auto p3 = now();
   {
     const size_t total = (size_t)sec_off[ns] + (size_t)ns + 1 + (size_t)c->emit_grid + 1 + 64;  // + poff + cta_item
-    CK(b->h_in.reserve(total));
-    memset(b->h_in.p, 0, (size_t)sec_off[ns] * 4);
+    CK(b->h_in.reserve(total));  // no clear: pass 2 writes every word of the plan
   }
-  b->out_index.assign((size_t)pacc, 0);
+  b->out_index.resize((size_t)pacc);
   int32_t* const out = b->h_in.p;
-  // pass 2 (group order): fill every step of a group while walking its waves once
+  const auto p4 = now();
+  // pass 2 (group order): fill every step of a group while walking its waves once.  Groups
+  // write disjoint regions, so the loop is spread over a few host threads (OpenMP keeps its
+  // pool between calls).  thread_local scratch is reached through plain pointers: a worker
+  // thread would otherwise see its own (empty) instance.
+  const PlanWave* const wvp = wv.data();
+  const int* const wvo = wv_off.data();
+  const int* const stf = step_flat.data();
+  const int* const seco = sec_off.data();
+  const int* const repo = rep_off.data();
+  const int* const rowo = row_off.data();
+  int* const oidx = b->out_index.data();
+  auto nwaves2 = [wvo](int g) { return (size_t)(wvo[g + 1] - wvo[g]); };
+  auto wave2 = [wvp, wvo](int g, size_t w) -> const PlanWave& { return wvp[wvo[g] + w]; };
+  auto step2 = [stf, wvo](int g, size_t w) { return stf[wvo[g] + w]; };
+#pragma omp parallel for schedule(static) num_threads(kHostThreads) if (ng >= 64 && kHostThreads > 1)
   for (int g = 0; g < ng; ++g) {
     const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
     const int q = rec[3], na = rec[6];
@@ -1243,19 +1315,19 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
     int ord0[RBGTOPO_MAX_GROUP_ROLES];
     for (int k = 0, acc = 0; k < q; ++k) { ord0[k] = acc; acc += roles[4 * k + 1]; }
     int i0 = 0;
-    for (size_t w = 0; w < nwaves(g); ++w) {
-      const PlanWave& pw = wave(g, w);
+    for (size_t w = 0; w < nwaves2(g); ++w) {
+      const PlanWave& pw = wave2(g, w);
       const int P = pw.size();
-      const int s = step_of(g, w);
+      const int s = step2(g, w);
       int32_t* st = out + RBGTOPO_HDR_WORDS + (size_t)s * RBGTOPO_STEP_WORDS;
-      int32_t* p = out + sec_off[s];
+      int32_t* p = out + seco[s];
       st[0] = rec[0];
       st[1] = rec[1] & (RBGTOPO_STEP_EXCLUSIVE | RBGTOPO_STEP_GANG);
       st[2] = (rec[1] & RBGTOPO_STEP_EXCLUSIVE) ? rec[2] : -1;
       st[3] = P;
       st[4] = (int32_t)(p - out);
       int n = 0;
-      int* oi = b->out_index.data() + rep_off[s];
+      int* oi = oidx + repo[s];
       for (int k = 0; k < P; ++k) {
         const int ri = pw.role[k];
         int need = 0;
@@ -1279,18 +1351,19 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
       memcpy(p, gb + rec[7], (size_t)na * 12);
       p += 3 * na;
       for (size_t w2 = 0; w2 < w; ++w2)  // one record per replica of the earlier waves, filled on the device
-        for (int k = 0; k < wave(g, w2).size(); ++k)
-          for (int r = 0; r < wave(g, w2).count[k]; ++r) {
+        for (int k = 0; k < wave2(g, w2).size(); ++k)
+          for (int r = 0; r < wave2(g, w2).count[k]; ++r) {
             *p++ = 0;
-            *p++ = wave(g, w2).role[k];
+            *p++ = wave2(g, w2).role[k];
             *p++ = 1;  // counted by the exactness bound; the device writes 0 for unplaced replicas
           }
       st[9] = i0;
-      st[10] = (int32_t)(p - out);  // consumed records stay zero until the device fills them
+      st[10] = (int32_t)(p - out);  // consumed records (and the pad) are zero until the device fills them
+      for (int32_t* const end = out + seco[s + 1]; p < end;) *p++ = 0;
       st[11] = n;
-      st[12] = rep_off[s];
-      st[13] = row_off[s];
-      st[14] = (w + 1 < nwaves(g)) ? step_of(g, w + 1) : 0;
+      st[12] = repo[s];
+      st[13] = rowo[s];
+      st[14] = (w + 1 < nwaves2(g)) ? step2(g, w + 1) : 0;
       st[15] = i0;
       for (int k = 0; k < P; ++k) placed_before[pw.role[k]] += pw.count[k];
       i0 += n;
@@ -1303,7 +1376,11 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
   out[3] = sec_off[ns];
   out[4] = racc;
   out[5] = rowacc;
+  out[6] = out[7] = 0;
   *plan_words = sec_off[ns];
+  if (prof)
+    fprintf(stderr, "[rbgtopo plan] validate+waves %ld us, numbering %ld us, offsets %ld us, clear %ld us, fill %ld us\n",
+            us(p0, p1), us(p1, p2), us(p2, p3), us(p3, p4), us(p4, now()));
   return RBGTOPO_OK;
 }
 
