@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "plan.cuh"
 #include "score.cuh"
 #include "select.cuh"
 #include "select_fast.cuh"
@@ -102,6 +103,7 @@ struct BatchMeta {
   int n_steps = 0, total_r = 0, total_p = 0, max_p = 1, max_k = 1;
   bool any_excl_unknown = false;
   long long words = 0;
+  long long h2d_words = 0;   // what staging actually uploaded
   long long scores = 0;      // sum R * N
   long long algo_bytes = 0;
   long long patch_cap = 0;   // sum of the per-step patch-list capacities
@@ -129,8 +131,12 @@ struct Batch {
   // device-resident multi-wave plan (rbgtopo_stage_groups / place_groups): steps are
   // wave-major; wave w = steps [wave_begin[w], wave_begin[w + 1])
   std::vector<int> wave_begin, wave_maxp;
-  std::vector<int> out_index;    // plan replica -> position in the group-order assign array
+  std::vector<int> out_index;    // plan replica -> position in the group-order assign array (host-built plans)
   std::vector<int> step_group;   // plan step -> group
+  std::vector<int> step_row;     // [n_steps + 1] role-row prefix
+  // device-expanded plans: the staging buffer (GROUPS blob | per-step geometry | poff | cta_item)
+  DevBuf<int> gsrc;
+  long long aux_off = -1;        // word offset of the per-step geometry in h_in; -1: host-built plan
   std::vector<int> grp_flags, grp_assign_off, grp_pending;
   DevBuf<int> out;  // assign[total_r] | status[n] | domain[n] | dstar[n]
   PinBuf<int> h_in, h_out;
@@ -176,6 +182,7 @@ constexpr size_t kFastSmemMax = 200 * 1024;
 // stream concurrently with k_score_emit.  Measured no gain (the latency-bound wave kernels
 // slow down behind the saturated memory system), so the serial pipeline is the default.
 const bool kSerialPlan = getenv("RBGTOPO_CONCURRENT_PLAN") == nullptr;
+const bool kVerifyPlan = getenv("RBGTOPO_VERIFY_PLAN") != nullptr;  // self-check: device-expanded plan == host-built plan
 const int kHostThreads = getenv("RBGTOPO_HOST_THREADS") ? std::max(1, atoi(getenv("RBGTOPO_HOST_THREADS"))) : 4;
 const int kEmitOcc = getenv("RBGTOPO_EMIT_OCC") ? atoi(getenv("RBGTOPO_EMIT_OCC")) : 6;  // opt-in dynamic smem of k_select_assign_fast
 
@@ -284,6 +291,30 @@ int run_base(rbgtopo_ctx* c, cudaStream_t s, bool sync) {
 // ---- blob validation (host, O(words)) ----------------------------------------
 // `trusted`: the blob was built by build_plan from an already validated GROUPS blob — the
 // per-record range checks are skipped, the derived metadata and the exactness bound are not.
+// Byte-balanced work split of k_score_emit: an item (step, chunk) weighs R_step rows.
+// rows(s, &first_row, &R) describes step s.
+template <class F>
+void balance_emit_items(const rbgtopo_ctx* c, BatchMeta* m, int ns, long long racc, F&& rows) {
+  const int G = std::max(1, c->emit_grid), lc = c->lc;
+  const long long total_w = racc * lc;
+  m->cta_item.assign((size_t)G + 1, ns * lc);
+  int s = 0, rep0 = 0, R = 1;
+  for (int g = 0; g < G; ++g) {
+    const long long target = total_w * g / G;
+    while (s < ns) {  // advance to the step containing `target`
+      rows(s, &rep0, &R);
+      if ((long long)(rep0 + R) * lc > target) break;
+      ++s;
+    }
+    if (s >= ns) break;
+    const long long before = (long long)rep0 * lc;
+    int ch = (int)((target - before + R - 1) / R);  // first chunk at or past the target
+    if (target <= before) ch = 0;
+    m->cta_item[g] = s * lc + std::min(ch, lc);
+  }
+  m->cta_item[0] = 0;
+}
+
 int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, BatchMeta* m, bool trusted = false) {
   const Topology& T = c->topo;
   if (!blob || words < RBGTOPO_HDR_WORDS) return fail(RBGTOPO_EINVAL, "blob too short");
@@ -376,28 +407,11 @@ int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, Batc
     if ((st[1] & RBGTOPO_STEP_EXCLUSIVE) && st[2] < 0) m->any_excl_unknown = true;
   }
   if (blob[4] != racc || blob[5] != pacc) return fail(RBGTOPO_EINVAL, "blob totals mismatch");
-  // byte-balanced work split of k_score_emit: an item (step, chunk) weighs R_step rows
-  {
-    const int G = std::max(1, c->emit_grid), lc = c->lc;
-    const long long total_w = racc * lc;
-    m->cta_item.assign((size_t)G + 1, ns * lc);
-    int s = 0;
-    for (int g = 0; g < G; ++g) {
-      const long long target = total_w * g / G;
-      while (s < ns) {  // advance to the step containing `target`
-        const int32_t* st = blob + RBGTOPO_HDR_WORDS + (int64_t)s * RBGTOPO_STEP_WORDS;
-        if ((long long)(st[12] + st[11]) * lc > target) break;
-        ++s;
-      }
-      if (s >= ns) break;
-      const int32_t* st = blob + RBGTOPO_HDR_WORDS + (int64_t)s * RBGTOPO_STEP_WORDS;
-      const long long before = (long long)st[12] * lc;
-      int ch = (int)((target - before + st[11] - 1) / st[11]);  // first chunk at or past the target
-      if (target <= before) ch = 0;
-      m->cta_item[g] = s * lc + std::min(ch, lc);
-    }
-    m->cta_item[0] = 0;
-  }
+  balance_emit_items(c, m, ns, racc, [&](int s, int* rep0, int* R) {
+    const int32_t* st = blob + RBGTOPO_HDR_WORDS + (int64_t)s * RBGTOPO_STEP_WORDS;
+    *rep0 = st[12];
+    *R = st[11];
+  });
   m->n_steps = ns;
   m->total_r = (int)racc;
   m->total_p = (int)pacc;
@@ -445,6 +459,20 @@ void release_batch(rbgtopo_ctx* c, Batch* b) {
 
 cudaStream_t stream_of(rbgtopo_ctx* c, Batch* b) { return c->use_ext_stream ? c->ext_stream : b->stream; }
 
+// device scratch + result buffers sized from b->m
+int reserve_batch_buffers(rbgtopo_ctx* c, Batch* b) {
+  const BatchMeta& m = b->m;
+  CK(b->matrix.reserve((size_t)std::max(1, m.total_r) * c->slab_stride));
+  CK(b->cand.reserve((size_t)m.patch_cap + 1));
+  CK(b->lists.reserve((size_t)std::max(1, m.total_p) * KS));
+  CK(b->merged.reserve((size_t)std::max(1, m.total_p) * KS));
+  CK(b->excl.reserve((size_t)std::max(1, m.total_p) * KS));
+  const size_t out_n = (size_t)m.total_r + 3 * (size_t)m.n_steps + 4;
+  CK(b->out.reserve(out_n));
+  CK(b->h_out.reserve(out_n));
+  return RBGTOPO_OK;
+}
+
 // validate + size buffers + H2D.  Caller holds topo_mu shared.
 // blob == b->h_in.p: the (trusted) plan was built in place in the pinned staging buffer.
 int stage_into(rbgtopo_ctx* c, Batch* b, const int32_t* blob, int64_t words) {
@@ -461,14 +489,9 @@ int stage_into(rbgtopo_ctx* c, Batch* b, const int32_t* blob, int64_t words) {
   } else {
     CK(b->h_in.reserve(in_words));
   }
-  CK(b->matrix.reserve((size_t)std::max(1, m.total_r) * c->slab_stride));
-  CK(b->cand.reserve((size_t)m.patch_cap + 1));
-  CK(b->lists.reserve((size_t)std::max(1, m.total_p) * KS));
-  CK(b->merged.reserve((size_t)std::max(1, m.total_p) * KS));
-  CK(b->excl.reserve((size_t)std::max(1, m.total_p) * KS));
-  const size_t out_n = (size_t)m.total_r + 3 * (size_t)m.n_steps + 4;
-  CK(b->out.reserve(out_n));
-  CK(b->h_out.reserve(out_n));
+  rc = reserve_batch_buffers(c, b);
+  if (rc) return rc;
+  b->m.h2d_words = (long long)in_words;
   CK(cudaStreamWaitEvent(s, c->topo_ready, 0));  // the snapshot refresh (if any) is complete
   CK(cudaEventRecord(b->ev[0], s));
   if (!in_place) memcpy(b->h_in.p, blob, (size_t)words * 4);
@@ -655,7 +678,7 @@ int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int3
   tm.scores = m.scores;
   tm.algo_bytes = m.algo_bytes;
   tm.launches = b->pend_launches;
-  tm.h2d_words = (int32_t)(m.words + m.n_steps + 1);
+  tm.h2d_words = (int32_t)m.h2d_words;
   (void)cudaGetLastError();  // events recorded under stream capture have no timestamps: not an error here
   const int total_passes = b->untimed_or_timed_passes;
   b->passes = 0;
@@ -1125,6 +1148,36 @@ struct PlanWave {  // <= RBGTOPO_MAX_STEP_ROLES entries, no heap
   int size() const { return n; }
 };
 
+// Static wave structure of a group: same rule as the host loop / plugin.py (a wave = the next
+// <= 32 replicas of <= 8 roles of one level).  Calls f(index, wave) per wave, returns the count.
+extern "C++" {
+template <class F>
+int walk_waves(const int32_t* roles, int q, F&& f) {
+  int cr = 0, taken = 0, nw = 0;
+  while (cr < q) {
+    if (roles[4 * cr + 1] - taken <= 0) { ++cr; taken = 0; continue; }
+    PlanWave w;
+    const int level = roles[4 * cr];
+    int n = 0;
+    while (cr < q && roles[4 * cr] == level && n < RBGTOPO_MAX_STEP_REPLICAS && w.size() < RBGTOPO_MAX_STEP_ROLES) {
+      const int left = roles[4 * cr + 1] - taken;
+      if (left <= 0) { ++cr; taken = 0; continue; }
+      const int take = std::min(left, RBGTOPO_MAX_STEP_REPLICAS - n);
+      w.push(cr, taken, take);
+      n += take;
+      taken += take;
+      if (taken == roles[4 * cr + 1]) { ++cr; taken = 0; }
+    }
+    f(nw, w);
+    ++nw;
+  }
+  return nw;
+}
+}  // extern "C++"
+int gen_waves(const int32_t* roles, int q, PlanWave* out) {  // out == nullptr: count only
+  return walk_waves(roles, q, [out](int i, const PlanWave& w) { if (out) out[i] = w; });
+}
+
 // Builds the plan IN PLACE in b->h_in (pinned); *plan_words = its size.  The GROUPS blob is
 // fully validated here (ranges of every user-provided value), so staging may trust the plan.
 int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_words, Batch* b) {
@@ -1145,28 +1198,6 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
   b->grp_flags.resize(ng);
   b->grp_assign_off.resize(ng);
   b->grp_pending.resize(ng);
-  // static wave structure: same rule as the host loop / plugin.py.  out == nullptr: count only.
-  auto gen_waves = [](const int32_t* roles, int q, PlanWave* out) -> int {
-    int cr = 0, taken = 0, nw = 0;
-    while (cr < q) {
-      if (roles[4 * cr + 1] - taken <= 0) { ++cr; taken = 0; continue; }
-      PlanWave w;
-      const int level = roles[4 * cr];
-      int n = 0;
-      while (cr < q && roles[4 * cr] == level && n < RBGTOPO_MAX_STEP_REPLICAS && w.size() < RBGTOPO_MAX_STEP_ROLES) {
-        const int left = roles[4 * cr + 1] - taken;
-        if (left <= 0) { ++cr; taken = 0; continue; }
-        const int take = std::min(left, RBGTOPO_MAX_STEP_REPLICAS - n);
-        w.push(cr, taken, take);
-        n += take;
-        taken += take;
-        if (taken == roles[4 * cr + 1]) { ++cr; taken = 0; }
-      }
-      if (out) out[nw] = w;
-      ++nw;
-    }
-    return nw;
-  };
 #define GROUP_FAIL(code, ...) return report ? fail(code, __VA_ARGS__) : (int)(code)
   int* const g_pend = b->grp_pending.data();
   int* const g_nw = wv_off.data() + 1;  // per-group wave count first, prefix-summed below
@@ -1384,6 +1415,318 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
   return RBGTOPO_OK;
 }
 
+// Device-expanded plan: validates the GROUPS blob, computes the per-step GEOMETRY on the host
+// (numbering, section offsets, prefixes, patch capacities, exactness bound, emit work split),
+// uploads GROUPS blob + geometry and lets k_expand_plan (plan.cuh) write the step blob in HBM.
+// Equivalent to build_plan + stage_into, without the step blob ever existing on the host.
+// Caller holds topo_mu shared.
+int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
+  const Topology& T = c->topo;
+  if (!T.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
+  if (words < RBGTOPO_HDR_WORDS || gb[0] != RBGTOPO_GROUPS_MAGIC || gb[1] != RBGTOPO_ABI_VERSION || gb[3] != words)
+    return fail(RBGTOPO_EINVAL, "bad groups blob header");
+  const int ng = gb[2];
+  if (ng < 0 || (int64_t)RBGTOPO_HDR_WORDS + (int64_t)ng * RBGTOPO_GROUP_WORDS > words)
+    return fail(RBGTOPO_EINVAL, "group table exceeds blob");
+  if (words > 0x3FFFFFFFLL) return fail(RBGTOPO_ELIMIT, "groups blob too large");
+  auto in = [&](long long off, long long cnt) { return off >= 0 && cnt >= 0 && off + cnt <= words; };
+  static const bool prof = getenv("RBGTOPO_PROFILE_HOST") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto us = [](auto t0, auto t1) { return (long)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count(); };
+  const auto p0 = now();
+  static thread_local std::vector<int> wv_off, g_pc, g_first, ctr;
+  wv_off.assign((size_t)ng + 1, 0);
+  g_pc.resize((size_t)ng);
+  g_first.resize((size_t)ng);
+  b->grp_flags.resize(ng);
+  b->grp_assign_off.resize(ng);
+  b->grp_pending.resize(ng);
+  int* const g_pend = b->grp_pending.data();
+  int* const g_nw = wv_off.data() + 1;  // per-group wave count first, prefix-summed below
+  int* const g_pcp = g_pc.data();
+  const int n_nodes = T.n, n_domains = T.n_domains;
+  const int* const degp1 = T.h_degp1.data();
+#define GROUP_FAIL(code, ...) return report ? fail(code, __VA_ARGS__) : (int)(code)
+  // everything about group g that does not depend on the groups before it
+  auto check_group = [&](int g, bool report) -> int {
+    const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
+    const int q = rec[3];
+    if (q < 1 || q > RBGTOPO_MAX_GROUP_ROLES) GROUP_FAIL(RBGTOPO_ELIMIT, "group %d: %d roles", g, q);
+    if (!in(rec[4], 4LL * q) || !in(rec[5], (long long)q * q) || !in(rec[7], 3LL * rec[6]))
+      GROUP_FAIL(RBGTOPO_EINVAL, "group %d: section out of bounds", g);
+    const int32_t* roles = gb + rec[4];
+    long long pend = 0;
+    for (int i = 0; i < q; ++i) {
+      if (roles[4 * i + 1] < 0 || (i && roles[4 * i] < roles[4 * (i - 1)]))
+        GROUP_FAIL(RBGTOPO_EINVAL, "group %d role %d: pending < 0 or levels not ascending", g, i);
+      if (roles[4 * i + 2] < 0 || roles[4 * i + 2] > RBGTOPO_MAX_FREE)
+        GROUP_FAIL(RBGTOPO_EINVAL, "group %d role %d: demand", g, i);
+      pend += roles[4 * i + 1];
+    }
+    if (pend > 0x3FFFFFFFLL) GROUP_FAIL(RBGTOPO_ELIMIT, "group %d: pending replicas", g);
+    if (rec[0] < 0 || rec[2] < -1 || rec[2] >= n_domains) GROUP_FAIL(RBGTOPO_EINVAL, "group %d: gid / fixed_domain", g);
+    for (int i = 0; i < q * q; ++i)
+      if (gb[rec[5] + i] < 0) GROUP_FAIL(RBGTOPO_EINVAL, "group %d: negative pair weight", g);
+    long long pc = 0;  // closed neighbourhoods of the scheduled pods
+    for (int a = 0; a < rec[6]; ++a) {
+      const int32_t* an = gb + rec[7] + 3 * a;
+      if (an[0] < 0 || an[0] >= n_nodes || an[1] < 0 || an[1] >= q || an[2] < 0)
+        GROUP_FAIL(RBGTOPO_EINVAL, "group %d anchor %d out of range", g, a);
+      pc += degp1[an[0]];
+    }
+    if (pc > 0x3FFFFFFFLL) GROUP_FAIL(RBGTOPO_ELIMIT, "group %d: patch list exceeds 2^30 entries", g);
+    g_pend[g] = (int)pend;
+    g_pcp[g] = (int)pc;
+    g_nw[g] = gen_waves(roles, q, nullptr);
+    return RBGTOPO_OK;
+  };
+  int first_bad = ng;
+#pragma omp parallel for schedule(static) num_threads(kHostThreads) reduction(min : first_bad) if (ng >= 64 && kHostThreads > 1)
+  for (int g = 0; g < ng; ++g)
+    if (check_group(g, false) != RBGTOPO_OK) first_bad = std::min(first_bad, g);
+  if (first_bad < ng) return check_group(first_bad, true);
+
+  const auto p1 = now();
+  // prefixes over groups, wave sizes, step numbering (wave-major)
+  BatchMeta& m = b->m;
+  m = BatchMeta{};
+  int W = 0;
+  long long pacc = 0;
+  for (int g = 0; g < ng; ++g) {
+    const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
+    if (rec[8] != pacc || rec[9] != g_pend[g]) return fail(RBGTOPO_EINVAL, "group %d: bad assign_off/n_pending", g);
+    b->grp_flags[g] = rec[1];
+    b->grp_assign_off[g] = (int)pacc;
+    pacc += g_pend[g];
+    if (pacc > 0x3FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "pending replicas exceed 2^30");
+    if ((rec[1] & RBGTOPO_STEP_EXCLUSIVE) && rec[2] < 0 && g_nw[g] > 0) m.any_excl_unknown = true;
+    W = std::max(W, g_nw[g]);
+    wv_off[g + 1] = wv_off[g] + g_nw[g];
+    if (wv_off[g + 1] > 0x03FFFFFF) return fail(RBGTOPO_ELIMIT, "plan has more than 2^26 steps");
+  }
+  if (gb[4] != pacc) return fail(RBGTOPO_EINVAL, "total pending mismatch");
+  const int ns = wv_off[ng];
+  const int* const wvo = wv_off.data();  // g_nw[] now holds prefixes: wave count of g = wvo[g + 1] - wvo[g]
+  b->wave_begin.assign((size_t)W + 1, 0);
+  b->wave_maxp.assign((size_t)W, 1);
+  for (int g = 0; g < ng; ++g)  // [k] = groups with exactly k waves (k >= 1)
+    if (wvo[g + 1] > wvo[g]) b->wave_begin[wvo[g + 1] - wvo[g]] += 1;
+  {
+    // steps in wave w = groups with > w waves = sum_{k > w} exact[k]
+    int more = 0;
+    std::vector<int>& wb = b->wave_begin;
+    static thread_local std::vector<int> cnt;
+    cnt.assign((size_t)W + 1, 0);
+    for (int k = W; k >= 1; --k) { more += wb[k]; cnt[k - 1] = more; }
+    wb[0] = 0;
+    for (int w = 0; w < W; ++w) wb[w + 1] = wb[w] + cnt[w];
+  }
+  // staging layout: GROUPS blob | pad | geometry (8 ints per step) | poff | cta_item
+  const size_t G1 = (size_t)std::max(1, c->emit_grid) + 1;
+  const size_t aux_off = ((size_t)words + 3) & ~(size_t)3;
+  const size_t tail_off = aux_off + (size_t)ns * PLAN_AUX_WORDS;
+  const size_t tail_words = (size_t)ns + 1 + G1;
+  const size_t src_words = tail_off + tail_words;
+  if (src_words > 0x7FFFFFF0ULL) return fail(RBGTOPO_ELIMIT, "plan staging exceeds 2^31 words");
+  CK(b->h_in.reserve(src_words));
+  int32_t* const hin = b->h_in.p;
+  int32_t* const aux = hin + aux_off;
+  b->step_group.resize((size_t)ns);
+  {
+    ctr.assign((size_t)W, 0);
+    int* const sg = b->step_group.data();
+    const int* const wb = b->wave_begin.data();
+    for (int g = 0; g < ng; ++g) {
+      int prev = -1;
+      for (int w = 0; w < wvo[g + 1] - wvo[g]; ++w) {
+        const int s = wb[w] + ctr[w]++;
+        if (w == 0) g_first[g] = s;
+        sg[s] = g;
+        aux[(size_t)s * PLAN_AUX_WORDS + 0] = g;
+        aux[(size_t)s * PLAN_AUX_WORDS + 1] = w;
+        aux[(size_t)s * PLAN_AUX_WORDS + 6] = 0;
+        if (prev >= 0) aux[(size_t)prev * PLAN_AUX_WORDS + 6] = s;  // next step of the group
+        prev = s;
+      }
+    }
+  }
+  const auto p2 = now();
+  // per-step sizes, patch capacity, exactness bound (per group, all its waves)
+  const long long row_w = T.wsum_max + RBGTOPO_SELF_W;
+  const int max_degp1 = T.max_degp1;
+  const int* const first_of = g_first.data();
+  auto size_group = [&](int g, bool report) -> int {
+    const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
+    const int q = rec[3], na = rec[6];
+    const int32_t* roles = gb + rec[4];
+    const int32_t* pair = gb + rec[5];
+    long long anch_w[RBGTOPO_MAX_GROUP_ROLES];  // sum over scheduled pods of pair[ri][role]·count
+    for (int ri = 0; ri < q; ++ri) {
+      long long acc = 0;
+      for (int a = 0; a < na; ++a) acc += (long long)pair[ri * q + gb[rec[7] + 3 * a + 1]] * gb[rec[7] + 3 * a + 2];
+      anch_w[ri] = acc;
+    }
+    int placed[RBGTOPO_MAX_GROUP_ROLES] = {0};
+    int i0 = 0, s = -1, rc = RBGTOPO_OK;
+    // the group's steps in wave order: follow the `next` links from its first step
+    walk_waves(roles, q, [&](int w, const PlanWave& pw) {
+      if (rc) return;
+      s = (w == 0) ? first_of[g] : aux[(size_t)s * PLAN_AUX_WORDS + 6];
+      const int P = pw.size();
+      int n = 0;
+      for (int k = 0; k < P; ++k) {
+        const int ri = pw.role[k];
+        int need = 0;
+        long long amax = anch_w[ri];
+        for (int j = 0; j < q; ++j) {
+          if (pair[ri * q + j] > 0) need += roles[4 * j + 1] - placed[j];
+          amax += (long long)pair[ri * q + j] * placed[j];
+        }
+        amax += (long long)std::min(need, RBGTOPO_NEED_CAP) * RBGTOPO_F_CAP;
+        if (amax * row_w >= (1LL << 24)) {
+          rc = report ? fail(RBGTOPO_EINEXACT, "group %d wave %d role %d: max score bound %lld >= 2^24", g, w, ri, amax * row_w)
+                      : (int)RBGTOPO_EINEXACT;
+          return;
+        }
+        n += pw.count[k];
+      }
+      long long sz = 4LL * P + (long long)P * q + 3LL * (na + i0) + 2LL * i0;
+      sz = (sz + 3) & ~3LL;  // keeps every role section 16-byte aligned
+      const long long pc = (long long)i0 + g_pcp[g] + (long long)i0 * max_degp1;
+      if (sz > 0x3FFFFFFFLL || pc > 0x3FFFFFFFLL) {
+        rc = report ? fail(RBGTOPO_ELIMIT, "group %d wave %d: step too large", g, w) : (int)RBGTOPO_ELIMIT;
+        return;
+      }
+      int32_t* a = aux + (size_t)s * PLAN_AUX_WORDS;
+      a[2] = (int)sz;  // -> sec_off
+      a[3] = (int)pc;  // -> sec_end (after the prefix pass took the capacity)
+      a[4] = n;        // -> rep_off
+      a[5] = P;        // -> row_off
+      a[7] = i0;
+      for (int k = 0; k < P; ++k) placed[pw.role[k]] += pw.count[k];
+      i0 += n;
+    });
+    return rc;
+  };
+  first_bad = ng;
+#pragma omp parallel for schedule(static) num_threads(kHostThreads) reduction(min : first_bad) if (ng >= 64 && kHostThreads > 1)
+  for (int g = 0; g < ng; ++g)
+    if (size_group(g, false) != RBGTOPO_OK) first_bad = std::min(first_bad, g);
+  if (first_bad < ng) return size_group(first_bad, true);
+
+  const auto p3 = now();
+  // prefixes over steps
+  int32_t* const poff = hin + tail_off;
+  b->step_row.resize((size_t)ns + 1);
+  long long off = (long long)RBGTOPO_HDR_WORDS + (long long)ns * RBGTOPO_STEP_WORDS;  // multiple of 4
+  long long racc = 0, rowacc = 0;
+  poff[0] = 0;
+  {
+    int w = 0;
+    for (int s = 0; s < ns; ++s) {
+      while (s >= b->wave_begin[w + 1]) ++w;
+      int32_t* a = aux + (size_t)s * PLAN_AUX_WORDS;
+      const int sz = a[2], pc = a[3], n = a[4], P = a[5];
+      if (off + sz > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "plan blob exceeds 2^31 words");
+      if (m.patch_cap + pc > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "patch lists exceed 2^31 entries");
+      a[2] = (int)off;
+      off += sz;
+      a[3] = (int)off;
+      a[4] = (int)racc;
+      a[5] = (int)rowacc;
+      b->step_row[s] = (int)rowacc;
+      racc += n;
+      rowacc += P;
+      m.patch_cap += pc;
+      m.max_cap = std::max(m.max_cap, pc);
+      poff[s + 1] = (int)m.patch_cap;
+      m.max_p = std::max(m.max_p, P);
+      m.max_k = std::max(m.max_k, n);
+      b->wave_maxp[w] = std::max(b->wave_maxp[w], P);
+    }
+    b->step_row[ns] = (int)rowacc;
+  }
+  const long long plan_words = off;
+  m.poff.assign(poff, poff + ns + 1);
+  balance_emit_items(c, &m, ns, racc, [&](int s, int* rep0, int* R) {
+    const int32_t* a = aux + (size_t)s * PLAN_AUX_WORDS;
+    *rep0 = a[4];
+    *R = (s + 1 < ns ? a[PLAN_AUX_WORDS + 4] : (int)racc) - a[4];
+  });
+  memcpy(poff + ns + 1, m.cta_item.data(), G1 * 4);
+  const auto p4 = now();
+  memcpy(hin, gb, (size_t)words * 4);
+  for (size_t i = (size_t)words; i < aux_off; ++i) hin[i] = 0;
+  m.n_steps = ns;
+  m.total_r = (int)racc;
+  m.total_p = (int)rowacc;
+  m.words = plan_words;
+  m.h2d_words = (long long)src_words;
+  const long long slab = c->slab_hi - c->slab_lo;
+  m.scores = racc * slab;
+  m.algo_bytes = 4LL * racc * slab + 4LL * plan_words + 8LL * slab;  // as validate_blob
+  b->aux_off = (long long)aux_off;
+
+  const auto p5 = now();
+  cudaStream_t s = stream_of(c, b);
+  CK(b->gsrc.reserve(src_words));
+  CK(b->blob.reserve((size_t)plan_words + tail_words));
+  int rc = reserve_batch_buffers(c, b);
+  if (rc) return rc;
+  CK(cudaStreamWaitEvent(s, c->topo_ready, 0));  // the snapshot refresh (if any) is complete
+  CK(cudaEventRecord(b->ev[0], s));
+  CK(cudaMemcpyAsync(b->gsrc.p, hin, src_words * 4, cudaMemcpyHostToDevice, s));
+  {
+    const long long warps = (long long)ns + ((long long)tail_words + 1 + 31) / 32;  // a warp per step + tail words
+    k_expand_plan<<<(unsigned)((warps + PLAN_WARPS - 1) / PLAN_WARPS), 32 * PLAN_WARPS, 0, s>>>(b->gsrc.p, b->blob.p, ns, (int)plan_words,
+                                                                   (int)aux_off, (int)tail_off, (int)tail_words,
+                                                                   (int)racc, (int)rowacc);
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(b->ev[1], s));  // h2d_ms = upload + expansion
+  b->pend_launches += 1;
+  b->staged = true;
+  b->ran = false;
+  if (prof)
+    fprintf(stderr, "[rbgtopo plan] check %ld us, numbering %ld us, sizes %ld us, prefixes+split %ld us, copy %ld us, enqueue %ld us\n",
+            us(p0, p1), us(p1, p2), us(p2, p3), us(p3, p4), us(p4, p5), us(p5, now()));
+  return RBGTOPO_OK;
+}
+
+// RBGTOPO_VERIFY_PLAN self-check: the plan k_expand_plan wrote (and the geometry plan_stage
+// computed) must equal, word for word, what the host builder + validator produce.
+int verify_plan(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
+  cudaStream_t s = stream_of(c, b);
+  const BatchMeta& m = b->m;
+  const size_t dev_words = (size_t)m.words + (size_t)m.n_steps + 1 + m.cta_item.size();
+  std::vector<int32_t> got(dev_words);
+  CK(cudaStreamSynchronize(s));
+  CK(cudaMemcpy(got.data(), b->blob.p, dev_words * 4, cudaMemcpyDeviceToHost));
+  Batch ref;  // never staged: only its host vectors and pinned buffer are used
+  int64_t plan_words = 0;
+  int rc = build_plan(c, gb, words, &plan_words, &ref);
+  if (rc) return rc;
+  rc = validate_blob(c, ref.h_in.p, plan_words, &ref.m, true);
+  if (rc) return rc;
+  if (plan_words != m.words) return fail(RBGTOPO_ECUDA, "verify_plan: %lld plan words, host builder %lld", m.words, (long long)plan_words);
+  for (int64_t i = 0; i < plan_words; ++i)
+    if (got[i] != ref.h_in.p[i])
+      return fail(RBGTOPO_ECUDA, "verify_plan: word %lld differs: device %d, host %d", (long long)i, got[i], ref.h_in.p[i]);
+  if (ref.m.poff != m.poff || ref.m.cta_item != m.cta_item)
+    return fail(RBGTOPO_ECUDA, "verify_plan: poff / cta_item differ");
+  for (size_t i = 0; i < m.poff.size(); ++i)
+    if (got[plan_words + i] != m.poff[i]) return fail(RBGTOPO_ECUDA, "verify_plan: device poff[%zu]", i);
+  for (size_t i = 0; i < m.cta_item.size(); ++i)
+    if (got[plan_words + m.poff.size() + i] != m.cta_item[i]) return fail(RBGTOPO_ECUDA, "verify_plan: device cta_item[%zu]", i);
+  if (ref.m.n_steps != m.n_steps || ref.m.total_r != m.total_r || ref.m.total_p != m.total_p || ref.m.max_p != m.max_p ||
+      ref.m.max_k != m.max_k || ref.m.patch_cap != m.patch_cap || ref.m.max_cap != m.max_cap ||
+      ref.m.any_excl_unknown != m.any_excl_unknown || ref.m.scores != m.scores || ref.m.algo_bytes != m.algo_bytes)
+    return fail(RBGTOPO_ECUDA, "verify_plan: batch meta differs");
+  if (ref.wave_begin != b->wave_begin || ref.wave_maxp != b->wave_maxp || ref.step_group != b->step_group)
+    return fail(RBGTOPO_ECUDA, "verify_plan: wave tables differ");
+  return RBGTOPO_OK;
+}
+
 // Step-order results of a plan batch (already in b->h_out) -> group order.  Returns
 // the groups the plan could not finish exactly (dirty) in *dirty.
 void plan_results(const Batch* b, int32_t* assign, int32_t* status, int32_t* domain, std::vector<char>* dirty) {
@@ -1392,8 +1735,14 @@ void plan_results(const Batch* b, int32_t* assign, int32_t* status, int32_t* dom
   const int32_t* st = a + m.total_r;
   const int32_t* dm = st + m.n_steps;
   const int ng = (int)b->grp_flags.size();
-  for (int i = 0; i < m.total_r; ++i)
-    if (assign) assign[b->out_index[i]] = a[i];
+  // a wave's replicas are consecutive in group order: step s covers [i0, i0 + R) of its group
+  const int32_t* aux = b->h_in.p + b->aux_off;
+  if (assign)
+    for (int s = 0; s < m.n_steps; ++s) {
+      const int32_t* x = aux + (size_t)s * PLAN_AUX_WORDS;
+      const int R = (s + 1 < m.n_steps ? x[PLAN_AUX_WORDS + 4] : m.total_r) - x[4];
+      memcpy(assign + b->grp_assign_off[x[0]] + x[7], a + x[4], (size_t)R * 4);
+    }
   std::vector<int> gstat(ng, 0), gdom(ng, -1);
   for (int s = 0; s < m.n_steps; ++s) {
     const int g = b->step_group[s];
@@ -1429,13 +1778,12 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
     Batch* b = nullptr;
     int rc = acquire_batch(c, &b);
     if (rc) return rc;
-    int64_t plan_words = 0;
     static const bool prof = getenv("RBGTOPO_PROFILE_HOST") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto t0 = now();
-    rc = build_plan(c, gb, words, &plan_words, b);
+    rc = plan_stage(c, b, gb, words);
     auto t1 = now();
-    if (!rc) rc = stage_into(c, b, b->h_in.p, plan_words);
+    if (!rc && kVerifyPlan) rc = verify_plan(c, b, gb, words);
     auto t2 = now();
     if (!rc) rc = run_batch(c, b, 1);
     auto t3 = now();
@@ -1444,7 +1792,7 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
     if (!rc) plan_results(b, assign, status, domain, &dirty);
     if (prof) {
       auto us = [](auto a, auto b2) { return std::chrono::duration<double, std::micro>(b2 - a).count(); };
-      fprintf(stderr, "[rbgtopo host] build %.0f us, validate+stage %.0f us, enqueue %.0f us, wait+fetch %.0f us, results %.0f us\n",
+      fprintf(stderr, "[rbgtopo host] plan+stage %.0f us, verify %.0f us, enqueue %.0f us, wait+fetch %.0f us, results %.0f us\n",
               us(t0, t1), us(t1, t2), us(t2, t3), us(t3, t4), us(t4, now()));
     }
     if (rc) cudaStreamSynchronize(stream_of(c, b));
@@ -1465,9 +1813,8 @@ int32_t rbgtopo_stage_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
   Batch* b = nullptr;
   int rc = acquire_batch(c, &b);
   if (rc) return rc;
-  int64_t plan_words = 0;
-  rc = build_plan(c, gb, words, &plan_words, b);
-  if (!rc) rc = stage_into(c, b, b->h_in.p, plan_words);
+  rc = plan_stage(c, b, gb, words);
+  if (!rc && kVerifyPlan) rc = verify_plan(c, b, gb, words);
   if (rc) {
     release_batch(c, b);
     return rc;
@@ -1576,9 +1923,8 @@ int wave_range(rbgtopo_ctx* c, Batch* b, int wave, WaveRange* w) {
   w->s0 = b->wave_begin[wave];
   w->s1 = b->wave_begin[wave + 1];
   w->maxp = b->wave_maxp[wave];
-  const int32_t* blob = b->h_in.p;  // host copy of the uploaded plan
-  w->rr0 = w->s0 < m.n_steps ? blob[RBGTOPO_HDR_WORDS + (size_t)w->s0 * RBGTOPO_STEP_WORDS + 13] : m.total_p;
-  w->rr1 = w->s1 < m.n_steps ? blob[RBGTOPO_HDR_WORDS + (size_t)w->s1 * RBGTOPO_STEP_WORDS + 13] : m.total_p;
+  w->rr0 = b->step_row[w->s0];
+  w->rr1 = b->step_row[w->s1];
   (void)c;
   return RBGTOPO_OK;
 }
@@ -1674,7 +2020,7 @@ int32_t rbgtopo_shard_wave_merge(rbgtopo_ctx* c, int32_t handle, int32_t wave, c
   if (!b->wave_begin.empty()) {
     excl_unknown = false;
     for (int s2 = w.s0; s2 < w.s1 && !excl_unknown; ++s2)
-      excl_unknown = (b->h_in.p[RBGTOPO_HDR_WORDS + (size_t)s2 * RBGTOPO_STEP_WORDS + 1] & RBGTOPO_STEP_EXCLUSIVE) != 0;
+      excl_unknown = (b->grp_flags[b->step_group[s2]] & RBGTOPO_STEP_EXCLUSIVE) != 0;
   }
   if (n > 0) {
     k_merge<<<(n + SEL_WARPS - 1) / SEL_WARPS, SEL_THREADS, 0, s>>>(topo_dev(c), d, w.s0, n);

@@ -93,3 +93,22 @@ def test_concurrent_callers_share_one_context():
     for g, w in zip(got, want):
         assert all(np.array_equal(x, y) for x, y in zip(g, w))
     eng.close()
+
+
+@pytest.mark.gpu
+def test_device_expanded_plan_equals_host_builder():
+    """RBGTOPO_VERIFY_PLAN makes every place_groups / stage_groups call compare the plan that
+    k_expand_plan wrote in HBM (and the host-side geometry) word for word with the host plan
+    builder; the variable is read when the library loads, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RBGTOPO_VERIFY_PLAN="1")
+    this = "tests/test_gpu_groups.py"
+    r = subprocess.run(
+        [sys.executable, "-m", "pytest", this, "-q", "-m", "gpu", "-x", "-k", "not device_expanded"],
+        cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout
