@@ -22,6 +22,7 @@
 #include "score.cuh"
 #include "select.cuh"
 #include "select_fast.cuh"
+#include "plan_group.cuh"
 
 using namespace rbgtopo;
 
@@ -100,7 +101,7 @@ struct Topology {
 };
 
 struct BatchMeta {
-  int n_steps = 0, total_r = 0, total_p = 0, max_p = 1, max_k = 1;
+  int n_steps = 0, total_r = 0, total_p = 0, max_p = 1, max_k = 1, max_q = 1;
   bool any_excl_unknown = false;
   long long words = 0;
   long long h2d_words = 0;   // what staging actually uploaded
@@ -117,8 +118,6 @@ struct Batch {
   bool staged = false;    // holds a staged blob (handle alive)
   bool ran = false;
   cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;  // wave kernels of a plan run here, concurrently with k_score_emit
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> it_ev;  // triples (before score, after score, after select) per pass
   int passes = 0, pend_launches = 0, untimed_or_timed_passes = 0;  // since the last harvest
@@ -142,9 +141,6 @@ struct Batch {
   PinBuf<int> h_in, h_out;
   ~Batch() {
     if (stream) cudaStreamDestroy(stream);
-    if (stream2) cudaStreamDestroy(stream2);
-    if (ev_fork) cudaEventDestroy(ev_fork);
-    if (ev_join) cudaEventDestroy(ev_join);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : it_ev) cudaEventDestroy(e);
   }
@@ -181,7 +177,7 @@ constexpr size_t kFastSmemMax = 200 * 1024;
 // Experiment switch (profiles/README.md "two-stream plan"): run the wave kernels on a second
 // stream concurrently with k_score_emit.  Measured no gain (the latency-bound wave kernels
 // slow down behind the saturated memory system), so the serial pipeline is the default.
-const bool kSerialPlan = getenv("RBGTOPO_CONCURRENT_PLAN") == nullptr;
+const bool kPerWavePlan = getenv("RBGTOPO_PER_WAVE_PLAN") != nullptr;  // one launch per wave instead of k_plan_group
 const bool kVerifyPlan = getenv("RBGTOPO_VERIFY_PLAN") != nullptr;  // self-check: device-expanded plan == host-built plan
 const int kHostThreads = getenv("RBGTOPO_HOST_THREADS") ? std::max(1, atoi(getenv("RBGTOPO_HOST_THREADS"))) : 4;
 const int kEmitOcc = getenv("RBGTOPO_EMIT_OCC") ? atoi(getenv("RBGTOPO_EMIT_OCC")) : 6;  // opt-in dynamic smem of k_select_assign_fast
@@ -224,14 +220,6 @@ TopoDev topo_dev(const rbgtopo_ctx* c) {
   t.dom_nodes = T.dom_nodes.p;
   t.order = T.order.p;
   return t;
-}
-
-// Sparse corrections of every step of a multi-wave plan, after the wave kernels have
-// chained all placements: one CTA per step (select.cuh correct_step).
-__global__ void __launch_bounds__(128) k_correct_all(TopoDev t, BatchDev b) {
-  const StepHdr h = load_hdr(b, blockIdx.x);
-  if (h.flags & STEP_SKIP) return;
-  correct_step(t, b, h);
 }
 
 __global__ void k_order_keys(TopoDev t, unsigned long long* keys) {
@@ -404,6 +392,7 @@ int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, Batc
     pacc += st[3];
     m->max_p = std::max(m->max_p, st[3]);
     m->max_k = std::max(m->max_k, st[11]);
+    m->max_q = std::max(m->max_q, st[5]);
     if ((st[1] & RBGTOPO_STEP_EXCLUSIVE) && st[2] < 0) m->any_excl_unknown = true;
   }
   if (blob[4] != racc || blob[5] != pacc) return fail(RBGTOPO_EINVAL, "blob totals mismatch");
@@ -436,13 +425,6 @@ int acquire_batch(rbgtopo_ctx* c, Batch** out) {
     }
   auto nb = std::make_unique<Batch>();
   CK(cudaStreamCreateWithFlags(&nb->stream, cudaStreamNonBlocking));
-  {
-    int lo = 0, hi = 0;
-    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = highest priority
-    CK(cudaStreamCreateWithPriority(&nb->stream2, cudaStreamNonBlocking, hi));
-    CK(cudaEventCreateWithFlags(&nb->ev_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&nb->ev_join, cudaEventDisableTiming));
-  }
   for (auto& e : nb->ev) CK(cudaEventCreate(&e));
   nb->in_use = true;
   *out = nb.get();
@@ -567,31 +549,35 @@ int launch_select_assign(rbgtopo_ctx* c, Batch* b, cudaStream_t s, const BatchDe
     ++*launches;
     return RBGTOPO_OK;
   }
-  // multi-wave plan: the wave kernels (select, assign, chain) do not read the matrix, so
-  // they run on a second, high-priority stream CONCURRENTLY with k_score_emit (which the
-  // caller has already enqueued on `s`); the sparse corrections of all steps are applied
-  // afterwards by one launch, when both are done.
-  const bool concurrent = b->stream2 != nullptr && !kSerialPlan;
-  cudaStream_t sw = concurrent ? b->stream2 : s;
-  if (concurrent) CK(cudaStreamWaitEvent(sw, b->ev_fork, 0));
-  const int wave_mode = concurrent ? SEL_CHAIN : (SEL_CORRECT | SEL_CHAIN);
+  // multi-wave plan, preferred: every wave of a group in one CTA of ONE launch (plan_group.cuh)
+  if (!kPerWavePlan) {
+    const int nth = std::max(128, 32 * b->m.max_p);
+    const int gCAP = std::max(32, round_up(b->m.max_cap, 32));
+    int gHT = 64;
+    while (gHT <= gCAP && gHT < (1 << 20)) gHT <<= 1;  // > CAP: probes always meet an empty slot
+    const size_t smem = group_smem_bytes(b->m.max_q, nth / 32, gHT, gCAP);
+    const int n0 = b->wave_begin.size() > 1 ? b->wave_begin[1] : 0;  // groups with pending replicas
+    if (smem <= kFastSmemMax) {
+      if (n0 > 0) {
+        k_plan_group<<<n0, nth, smem, s>>>(topo_dev(c), d, b->m.max_q, gHT, gCAP);
+        ++*launches;
+      }
+      return RBGTOPO_OK;
+    }
+  }
+  // fallback: one launch per wave, placements chained through the plan blob in HBM
+  const int wave_mode = SEL_CORRECT | SEL_CHAIN;
   for (size_t w = 0; w + 1 < b->wave_begin.size(); ++w) {
     const int n = b->wave_begin[w + 1] - b->wave_begin[w];
     if (n <= 0) continue;
     if (fast) {
       const int nth = std::max(128, 32 * b->wave_maxp[w]);
       table(b->wave_begin[w], b->wave_begin[w + 1], &CAP, &HT);
-      k_select_assign_fast<<<n, nth, fast_smem_bytes(nth / 32, HT, CAP), sw>>>(
+      k_select_assign_fast<<<n, nth, fast_smem_bytes(nth / 32, HT, CAP), s>>>(
           topo_dev(c), d, b->wave_begin[w], wave_mode, HT, CAP);
     } else
-      k_select_assign<<<n, 32 * b->wave_maxp[w], select_smem_bytes(b->wave_maxp[w]), sw>>>(
+      k_select_assign<<<n, 32 * b->wave_maxp[w], select_smem_bytes(b->wave_maxp[w]), s>>>(
           topo_dev(c), d, b->wave_begin[w], wave_mode);
-    ++*launches;
-  }
-  if (concurrent) {
-    CK(cudaEventRecord(b->ev_join, sw));
-    CK(cudaStreamWaitEvent(s, b->ev_join, 0));
-    k_correct_all<<<ns, 128, 0, s>>>(topo_dev(c), d);
     ++*launches;
   }
   return RBGTOPO_OK;
@@ -624,7 +610,6 @@ int run_batch(rbgtopo_ctx* c, Batch* b, int iters) {
       if (rc) return rc;
       CK(cudaEventRecord(b->it_ev[e0], s));
     }
-    if (!b->wave_begin.empty()) CK(cudaEventRecord(b->ev_fork, s));  // inputs of this pass are ready
     int rc = launch_score(c, b, s);
     if (rc) return rc;
     ++launches;
@@ -747,6 +732,7 @@ int32_t rbgtopo_create(const rbgtopo_config* cfg, rbgtopo_ctx** out) {
   CK(cudaEventCreate(&c->ev_base_b));
   CK(cudaFuncSetAttribute(k_select_assign_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
   CK(cudaFuncSetAttribute(k_shard_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
+  CK(cudaFuncSetAttribute(k_plan_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
   {
     int occ = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_emit, SCORE_THREADS, 0));
@@ -1500,6 +1486,7 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
     pacc += g_pend[g];
     if (pacc > 0x3FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "pending replicas exceed 2^30");
     if ((rec[1] & RBGTOPO_STEP_EXCLUSIVE) && rec[2] < 0 && g_nw[g] > 0) m.any_excl_unknown = true;
+    if (g_nw[g] > 0) m.max_q = std::max(m.max_q, rec[3]);
     W = std::max(W, g_nw[g]);
     wv_off[g + 1] = wv_off[g] + g_nw[g];
     if (wv_off[g + 1] > 0x03FFFFFF) return fail(RBGTOPO_ELIMIT, "plan has more than 2^26 steps");
@@ -1719,7 +1706,7 @@ int verify_plan(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
   for (size_t i = 0; i < m.cta_item.size(); ++i)
     if (got[plan_words + m.poff.size() + i] != m.cta_item[i]) return fail(RBGTOPO_ECUDA, "verify_plan: device cta_item[%zu]", i);
   if (ref.m.n_steps != m.n_steps || ref.m.total_r != m.total_r || ref.m.total_p != m.total_p || ref.m.max_p != m.max_p ||
-      ref.m.max_k != m.max_k || ref.m.patch_cap != m.patch_cap || ref.m.max_cap != m.max_cap ||
+      ref.m.max_k != m.max_k || ref.m.max_q != m.max_q || ref.m.patch_cap != m.patch_cap || ref.m.max_cap != m.max_cap ||
       ref.m.any_excl_unknown != m.any_excl_unknown || ref.m.scores != m.scores || ref.m.algo_bytes != m.algo_bytes)
     return fail(RBGTOPO_ECUDA, "verify_plan: batch meta differs");
   if (ref.wave_begin != b->wave_begin || ref.wave_maxp != b->wave_maxp || ref.step_group != b->step_group)

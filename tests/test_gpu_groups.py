@@ -95,20 +95,69 @@ def test_concurrent_callers_share_one_context():
     eng.close()
 
 
-@pytest.mark.gpu
-def test_device_expanded_plan_equals_host_builder():
-    """RBGTOPO_VERIFY_PLAN makes every place_groups / stage_groups call compare the plan that
-    k_expand_plan wrote in HBM (and the host-side geometry) word for word with the host plan
-    builder; the variable is read when the library loads, hence the subprocess."""
+def test_plan_dense_matrix_and_lists_match_oracle_per_wave():
+    """A staged multi-wave plan leaves the same dense matrix rows and top-K lists in HBM as
+    the wave-by-wave oracle run (rows: wave-major, groups in order)."""
+    from gpu_util import new_engine
+    from oracle import placer as oracle_placer
+    from rbg_b200.blob import BlobBuilder
+    from rbg_b200.plugin import _GroupRun
+    n = 3000
+    topo = synth.make_topology(n, seed=11, tiers=4, owned_frac=0.2)
+    rbgs = _fleet(n, 24, seed=5, excl_every=3, big_every=5)
+    eng = new_engine(topo)
+    mgr = B200TopoPodGroupManager(eng)
+    gblob, _ = mgr.groups_blob(rbgs)
+    h = eng.stage_groups(gblob)
+    eng.run_staged(h, 1)
+    eng.fetch(h)
+    runs = [_GroupRun(r, mgr.arith) for r in rbgs]
+    row = rr = w = 0
+    while True:
+        active = [g for g in runs if w < len(g.waves)]
+        if not active:
+            break
+        bb = BlobBuilder()
+        for g in active:
+            bb.add(g.step(w))
+        ref = oracle_placer.place(topo, bb.build(), want_matrix=True, want_topk=True)
+        assert ref["rc"] == 0 and (ref["status"] == 0).all()     # nobody fails: rows stay aligned with the plan
+        for i in range(ref["matrix"].shape[0]):
+            got = eng.read_scores(h, row + i)
+            exp = ref["matrix"][i]
+            bad = np.nonzero(got.view(np.uint32) != exp.view(np.uint32))[0]
+            assert len(bad) == 0, (w, i, len(bad), int(bad[0]), float(got[bad[0]]), float(exp[bad[0]]))
+        for i in range(ref["topk"].shape[0]):
+            assert np.array_equal(eng.read_topk(h, rr + i, 32), ref["topk"][i]), (w, i)
+        off = 0
+        for i, g in enumerate(active):
+            cnt = sum(c for _, _, c in g.waves[w].roles)
+            g.absorb(w, ref["assign"][off:off + cnt], int(ref["status"][i]), int(ref["domain"][i]), n)
+            off += cnt
+        row += ref["matrix"].shape[0]
+        rr += ref["topk"].shape[0]
+        w += 1
+    assert w >= 3
+    eng.release(h)
+    eng.close()
+
+
+@pytest.mark.parametrize("var", ["RBGTOPO_VERIFY_PLAN", "RBGTOPO_PER_WAVE_PLAN"])
+def test_plan_variants_in_a_subprocess(var):
+    """The library reads its switches when it loads, hence the subprocess.
+    RBGTOPO_VERIFY_PLAN: every place_groups / stage_groups call compares the plan k_expand_plan
+    wrote in HBM (and the host-side geometry) word for word with the host plan builder.
+    RBGTOPO_PER_WAVE_PLAN: the fallback that runs one launch per wave and chains placements
+    through the plan blob (what groups too large for k_plan_group's shared memory take)."""
     import os
     import subprocess
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, RBGTOPO_VERIFY_PLAN="1")
-    this = "tests/test_gpu_groups.py"
+    env = dict(os.environ)
+    env[var] = "1"
     r = subprocess.run(
-        [sys.executable, "-m", "pytest", this, "-q", "-m", "gpu", "-x", "-k", "not device_expanded"],
+        [sys.executable, "-m", "pytest", "tests/test_gpu_groups.py", "-q", "-m", "gpu", "-x", "-k", "not subprocess"],
         cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "passed" in r.stdout
