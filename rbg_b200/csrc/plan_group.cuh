@@ -27,9 +27,9 @@ struct GroupTab {
   int* node;        // [HT] key, -1 = empty
   int* cons;        // [HT] capacity consumed on the slot's node by earlier waves
   float* aw;        // [QB][HT] anchor weight per group role
-  uint32_t* dense;  // [HT / 32] bit = slot already has a dense entry
   int mask, HT;
-  int* dSlot;       // [CAP] dense view of the occupied slots
+  int* cnt;         // occupied slots; the thread whose CAS claims a slot appends it to dSlot
+  int* dSlot;       // [CAP] dense view of the occupied slots (insertion order)
   float* dBase;     // [CAP]
   int* dFree;       // [CAP] free capacity of the node in the snapshot
   int* dAvail;      // [CAP] dFree - cons, refreshed per wave
@@ -40,7 +40,7 @@ struct GroupRole {  // role row of the current wave, staged in shared memory
 };
 
 __host__ __device__ inline size_t group_smem_bytes(int QB, int PB, int HT, int CAP) {
-  return (size_t)HT * 4 * (2 + QB) + (size_t)(HT / 32) * 4 + (size_t)CAP * 20 +  // table + dense view
+  return (size_t)HT * 4 * (2 + QB) + (size_t)CAP * 20 +                          // table + dense view
          (size_t)PB * KS * (3 * 8 + 3 * 4) +                                      // per-role key lists + capacities
          (size_t)MAXP * 16 + (size_t)MAXP * RBGTOPO_MAX_GROUP_ROLES * 4;          // staged roles + pair rows
 }
@@ -49,6 +49,7 @@ __device__ __forceinline__ int gtab_insert(const GroupTab& T, int n) {
   int h = tab_hash(n, T.mask);
   while (true) {
     const int old = atomicCAS(&T.node[h], -1, n);
+    if (old == -1) T.dSlot[atomicAdd(T.cnt, 1)] = h;  // claimed: the capacity bound keeps this below CAP
     if (old == -1 || old == n) return h;
     h = (h + 1) & T.mask;
   }
@@ -62,16 +63,17 @@ __device__ __forceinline__ bool gtab_has(const GroupTab& T, int n) {
     h = (h + 1) & T.mask;
   }
 }
-__device__ __forceinline__ float gtab_delta(const GroupTab& T, const int* pair_row, int Q, int slot) {
+__device__ __forceinline__ float gtab_delta(const GroupTab& T, const float* pair_row, int Q, int slot) {
   float d = 0.0f;
-  for (int q = 0; q < Q; ++q) d = fmaf((float)pair_row[q], T.aw[(size_t)q * T.HT + slot], d);
+  const float* aw = T.aw + slot;
+  for (int q = 0; q < Q; ++q, aw += T.HT) d = fmaf(pair_row[q], *aw, d);
   return d;
 }
 
 // top-K of a role row into out[0..KS) (+ capacities): select_role_fast with the
 // delta evaluated from the per-group-role planes.  One warp.
 __device__ __forceinline__ void select_role_group(const TopoDev& t, int gid, bool excl_step, const GroupRole& role,
-                                                  const int* pair_row, int Q, int K, int dom, const GroupTab& T,
+                                                  const float* pair_row, int Q, int K, int dom, const GroupTab& T,
                                                   int cnt, unsigned long long* sAcc, int* sAccAv,
                                                   unsigned long long* sPat, int* sPatAv, unsigned long long* out,
                                                   int* outAvail) {
@@ -86,29 +88,44 @@ __device__ __forceinline__ void select_role_group(const TopoDev& t, int gid, boo
   const float need = (float)role.need;
   const bool rexcl = excl_step && (role.flags & RBGTOPO_ROLE_EXCLUSIVE);
 
-  // ---- (a) patched slots, K strictly-descending rounds
+  // ---- (a) patched slots, K strictly-descending rounds.  The keys of the first 32 * EREG
+  //      entries are evaluated once and stay in registers; entries past that are re-evaluated
+  //      per round.
+  constexpr int EREG = 8;
+  auto entry_key = [&](int i) -> unsigned long long {
+    const int av = T.dAvail[i], dd = T.dDom[i];
+    if (av >= demand && !(rexcl && dd < 0) && (dom == DOM_ANY || (dd & 0x7FFFFFFF) == dom)) {
+      const int slot = T.dSlot[i];
+      return make_key(fmaf(need, T.dBase[i], gtab_delta(T, pair_row, Q, slot)), T.node[slot]);
+    }
+    return 0ull;
+  };
+  unsigned long long kreg[EREG];
+#pragma unroll
+  for (int j = 0; j < EREG; ++j) {
+    const int i = lane + 32 * j;
+    kreg[j] = i < cnt ? entry_key(i) : 0ull;
+  }
   int npat = 0;
   {
     unsigned long long prev = ~0ull;
     for (; npat < K; ++npat) {
       unsigned long long best = 0;
-      int bav = 0;
-      for (int i = lane; i < cnt; i += 32) {
-        const int av = T.dAvail[i], dd = T.dDom[i];
-        if (av >= demand && !(rexcl && dd < 0) && (dom == DOM_ANY || (dd & 0x7FFFFFFF) == dom)) {
-          const int slot = T.dSlot[i];
-          const unsigned long long k = make_key(fmaf(need, T.dBase[i], gtab_delta(T, pair_row, Q, slot)), T.node[slot]);
-          if (k < prev && k > best) { best = k; bav = av; }
-        }
+      int bi = 0;
+#pragma unroll
+      for (int j = 0; j < EREG; ++j)
+        if (kreg[j] < prev && kreg[j] > best) { best = kreg[j]; bi = lane + 32 * j; }
+      for (int i = lane + 32 * EREG; i < cnt; i += 32) {
+        const unsigned long long k = entry_key(i);
+        if (k < prev && k > best) { best = k; bi = i; }
       }
       const unsigned long long m = warp_max_u64(best);
       if (m == 0) break;
-      const uint32_t who = __ballot_sync(FULL, best == m);
-      bav = __shfl_sync(FULL, bav, __ffs(who) - 1);
-      if (lane == 0) { sPat[npat] = m; sPatAv[npat] = bav; }
+      if (best == m) { sPat[npat] = m; sPatAv[npat] = T.dAvail[bi]; }  // keys are unique: one lane
       prev = m;
     }
   }
+  __syncwarp();
 
   // ---- (b) walk the background order; patched nodes are skipped by a table probe
   const int slab_len = t.slab_hi - t.slab_lo;
@@ -146,22 +163,7 @@ __device__ __forceinline__ void select_role_group(const TopoDev& t, int gid, boo
   acc = min(acc, K);
   __syncwarp();
 
-  // ---- merge the two descending lists
-  if (lane == 0) {
-    int ia = 0, ip = 0;
-    for (int r = 0; r < KS; ++r) {
-      unsigned long long v = 0;
-      int av = 0;
-      if (r < K) {
-        const unsigned long long a = ia < acc ? sAcc[ia] : 0ull;
-        const unsigned long long c = ip < npat ? sPat[ip] : 0ull;
-        if (a > c) { v = a; av = sAccAv[ia]; ++ia; } else if (c) { v = c; av = sPatAv[ip]; ++ip; }
-      }
-      out[r] = v;
-      outAvail[r] = av;
-    }
-  }
-  __syncwarp();
+  merge_lists(sAcc, sAccAv, acc, sPat, sPatAv, npat, K, out, outAvail);
 }
 
 // Inserts the closed neighbourhood of anchor pod(s) (node m, group role q, count c) and the
@@ -186,7 +188,7 @@ __device__ __forceinline__ void gtab_add_anchor(const TopoDev& t, const GroupTab
 
 // grid = groups with at least one pending replica = the steps of wave 0; CTA g starts at step g.
 // QB = largest role count of a group in the batch, PB = warps per CTA (>= roles of any wave).
-__global__ void __launch_bounds__(32 * MAXP) k_plan_group(TopoDev t, BatchDev b, int QB, int HT, int CAP) {
+__global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev b, int QB, int HT, int CAP) {
   extern __shared__ __align__(16) unsigned char pg_smem[];
   __shared__ int sTakenNode[KS], sTakenAmt[KS], sTakenRole[KS];
   __shared__ int sDstar, sCnt, sNew, sStatus, sAny;
@@ -196,10 +198,10 @@ __global__ void __launch_bounds__(32 * MAXP) k_plan_group(TopoDev t, BatchDev b,
   T.node = reinterpret_cast<int*>(pg_smem);
   T.cons = T.node + HT;
   T.aw = reinterpret_cast<float*>(T.cons + HT);
-  T.dense = reinterpret_cast<uint32_t*>(T.aw + (size_t)QB * HT);
   T.mask = HT - 1;
   T.HT = HT;
-  T.dSlot = reinterpret_cast<int*>(T.dense + HT / 32);
+  T.cnt = &sCnt;
+  T.dSlot = reinterpret_cast<int*>(T.aw + (size_t)QB * HT);
   T.dBase = reinterpret_cast<float*>(T.dSlot + CAP);
   T.dFree = reinterpret_cast<int*>(T.dBase + CAP);
   T.dAvail = T.dFree + CAP;
@@ -212,14 +214,13 @@ __global__ void __launch_bounds__(32 * MAXP) k_plan_group(TopoDev t, BatchDev b,
   int* sAccAv = sListAv + (size_t)PB * KS;
   int* sPatAv = sAccAv + (size_t)PB * KS;
   GroupRole* sRole = reinterpret_cast<GroupRole*>(sPatAv + (size_t)PB * KS);
-  int* sPair = reinterpret_cast<int*>(sRole + MAXP);  // [MAXP][RBGTOPO_MAX_GROUP_ROLES]
+  float* sPair = reinterpret_cast<float*>(sRole + MAXP);  // [MAXP][RBGTOPO_MAX_GROUP_ROLES]
 
   for (int i = tid; i < HT; i += nthreads) {
     T.node[i] = -1;
     T.cons[i] = 0;
   }
   for (int i = tid; i < QB * HT; i += nthreads) T.aw[i] = 0.0f;
-  for (int i = tid; i < HT / 32; i += nthreads) T.dense[i] = 0u;
   if (tid == 0) sCnt = 0;
 
   int step = blockIdx.x;
@@ -236,7 +237,8 @@ __global__ void __launch_bounds__(32 * MAXP) k_plan_group(TopoDev t, BatchDev b,
     const int* anc = b.blob + h.anchor_off;
     for (int a = warp; a < h.n_anchors - h.i0; a += nwarps) gtab_add_anchor(t, T, anc[3 * a], anc[3 * a + 1], anc[3 * a + 2], 0);
   }
-  int n_new = 0;  // replicas placed by the previous wave: sTaken*[0, n_new)
+  int n_new = 0;     // replicas placed by the previous wave: sTaken*[0, n_new)
+  int cnt_done = 0;  // dense entries whose node attributes are loaded
 
   while (true) {
     // ---- A. closed neighbourhoods + consumption of the previous wave's placements; this wave's roles
@@ -246,34 +248,24 @@ __global__ void __launch_bounds__(32 * MAXP) k_plan_group(TopoDev t, BatchDev b,
       sRole[tid] = GroupRole{r.x, r.y, r.z, r.w};
     }
     for (int i = tid; i < h.P * Q; i += nthreads)
-      sPair[(i / Q) * RBGTOPO_MAX_GROUP_ROLES + i % Q] = b.blob[h.pair_off + i];
+      sPair[(i / Q) * RBGTOPO_MAX_GROUP_ROLES + i % Q] = (float)b.blob[h.pair_off + i];
     __syncthreads();
 
-    // ---- B. dense entries for the new slots, capacities of all
-    for (int i0 = 0; i0 < HT; i0 += nthreads) {
-      const int i = i0 + tid;
-      const int node = i < HT ? T.node[i] : -1;
-      const bool fresh = node >= 0 && !((T.dense[i >> 5] >> (i & 31)) & 1u);
-      const uint32_t msk = __ballot_sync(FULL, fresh);
-      int basei = 0;
-      if (lane == 0 && msk) basei = atomicAdd(&sCnt, __popc(msk));
-      basei = __shfl_sync(FULL, basei, 0);
-      if (fresh) {
-        const int d = basei + __popc(msk & ((1u << lane) - 1u));
-        int dd = t.domain[node];
-        if (excl_step) {
-          const int o = t.node_owner[node];
-          if (!(o == -1 || o == gid)) dd |= 0x80000000;
-        }
-        T.dSlot[d] = i;
-        T.dBase[d] = t.base[node];
-        T.dFree[d] = t.free_[node];
-        T.dDom[d] = dd;
-      }
-      if (lane == 0 && msk) T.dense[i >> 5] |= msk;  // i >> 5 is the same word for the whole warp (nthreads % 32 == 0)
-    }
-    __syncthreads();
+    // ---- B. node attributes of the slots claimed since the last wave, capacities of all
     const int cnt = sCnt;
+    for (int d = cnt_done + tid; d < cnt; d += nthreads) {
+      const int node = T.node[T.dSlot[d]];
+      int dd = t.domain[node];
+      if (excl_step) {
+        const int o = t.node_owner[node];
+        if (!(o == -1 || o == gid)) dd |= 0x80000000;
+      }
+      T.dBase[d] = t.base[node];
+      T.dFree[d] = t.free_[node];
+      T.dDom[d] = dd;
+    }
+    cnt_done = cnt;
+    __syncthreads();
     for (int d = tid; d < cnt; d += nthreads) T.dAvail[d] = T.dFree[d] - T.cons[T.dSlot[d]];
     __syncthreads();
 

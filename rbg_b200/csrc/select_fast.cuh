@@ -58,6 +58,31 @@ __device__ __forceinline__ int tab_find(const PatchTab& T, int n) {
   }
 }
 
+// Merge of two strictly descending key lists (disjoint: a patched node never appears in the
+// background walk) into the first K entries of out[0..KS), zero-padded; capacities follow
+// their keys.  Rank = own index + entries of the other list that are larger.  One warp.
+__device__ __forceinline__ void merge_lists(const unsigned long long* sAcc, const int* sAccAv, int acc,
+                                            const unsigned long long* sPat, const int* sPatAv, int npat, int K,
+                                            unsigned long long* out, int* outAvail) {
+  const int lane = threadIdx.x & 31;
+  out[lane] = 0;
+  outAvail[lane] = 0;
+  __syncwarp();
+  if (lane < acc) {
+    const unsigned long long a = sAcc[lane];
+    int r = lane;
+    for (int j = 0; j < npat; ++j) r += sPat[j] > a;
+    if (r < K) { out[r] = a; outAvail[r] = sAccAv[lane]; }
+  }
+  if (lane < npat) {
+    const unsigned long long c = sPat[lane];
+    int r = lane;
+    for (int j = 0; j < acc; ++j) r += sAcc[j] > c;
+    if (r < K) { out[r] = c; outAvail[r] = sPatAv[lane]; }
+  }
+  __syncwarp();
+}
+
 // top-K of role row p into out[0..KS) (+ the capacity of every listed node in
 // outAvail); same contract as select_role (select.cuh).
 __device__ __forceinline__ void select_role_fast(const TopoDev& t, const BatchDev& b, const StepHdr& h, int p, int K,
@@ -135,22 +160,7 @@ __device__ __forceinline__ void select_role_fast(const TopoDev& t, const BatchDe
   acc = min(acc, K);
   __syncwarp();
 
-  // ---- merge the two descending lists
-  if (lane == 0) {
-    int ia = 0, ip = 0;
-    for (int r = 0; r < KS; ++r) {
-      unsigned long long v = 0;
-      int av = 0;
-      if (r < K) {
-        const unsigned long long a = ia < acc ? sAcc[ia] : 0ull;
-        const unsigned long long c = ip < npat ? sPat[ip] : 0ull;
-        if (a > c) { v = a; av = sAccAv[ia]; ++ia; } else if (c) { v = c; av = sPatAv[ip]; ++ip; }
-      }
-      out[r] = v;
-      outAvail[r] = av;
-    }
-  }
-  __syncwarp();
+  merge_lists(sAcc, sAccAv, acc, sPat, sPatAv, npat, K, out, outAvail);
 }
 
 // Steps 0-2 of the kernels below: fill the shared-memory table of the step's patched
