@@ -70,11 +70,51 @@ __device__ __forceinline__ float gtab_delta(const GroupTab& T, const float* pair
   return d;
 }
 
+#ifdef RBGTOPO_PHASE_CLOCKS  // one-off instrumentation (profiles/README.md): per-CTA phase timestamps
+__device__ long long g_phase_clk[2048 * 32];
+__device__ int g_dbg_skip;  // timing experiments only: bit 0 = no corrections, bit 1 = no patched-slot pass
+#define PCLK(k) do { if (tid == 0 && blockIdx.x < 2048 && (k) < 32) g_phase_clk[blockIdx.x * 32 + (k)] = clock64(); } while (0)
+#define PCLKL(k) do { if ((k) >= 0 && (threadIdx.x & 31) == 0 && blockIdx.x < 2048 && (k) < 32) g_phase_clk[blockIdx.x * 32 + (k)] = clock64(); } while (0)
+#else
+#define PCLK(k) do {} while (0)
+#define PCLKL(k) do {} while (0)
+#endif
+
+// Lane `lane`'s candidate at position pos + lane of the background order (spec §3.3: for
+// need == 0 every background score is 0, so the order is node-ascending), with the node
+// attributes selection filters on.  Loaded early (before the table passes of a wave) for
+// pos == 0 so that the two dependent round trips are off the critical path.
+struct BgCand {
+  unsigned long long ob;  // order entry (need > 0) — key(base, node)
+  int node, free_, owner, dom;
+};
+// second half of a candidate load: `ob` = t.order[i] is already in a register
+__device__ __forceinline__ BgCand bg_attrs(const TopoDev& t, int need_i, int i, int slab_len, unsigned long long ob) {
+  BgCand c;
+  c.ob = ob;
+  c.node = -1;
+  c.free_ = 0;
+  c.owner = -1;
+  c.dom = -1;
+  if (i < slab_len) {
+    c.node = need_i > 0 ? key_node(ob) : t.slab_lo + i;
+    c.free_ = t.free_[c.node];
+    c.owner = t.node_owner[c.node];
+    c.dom = t.domain[c.node];
+  }
+  return c;
+}
+__device__ __forceinline__ BgCand bg_load(const TopoDev& t, int need_i, int i, int slab_len) {
+  return bg_attrs(t, need_i, i, slab_len, (i < slab_len && need_i > 0) ? t.order[i] : 0ull);
+}
+
 // top-K of a role row into out[0..KS) (+ capacities): select_role_fast with the
-// delta evaluated from the per-group-role planes.  One warp.
+// delta evaluated from the per-group-role planes.  `first` = bg_load(..., lane, ...) when
+// have_first.  One warp.
 __device__ __forceinline__ void select_role_group(const TopoDev& t, int gid, bool excl_step, const GroupRole& role,
                                                   const float* pair_row, int Q, int K, int dom, const GroupTab& T,
-                                                  int cnt, unsigned long long* sAcc, int* sAccAv,
+                                                  int cnt, bool have_first, const BgCand& first, int dbg,
+                                                  unsigned long long* sAcc, int* sAccAv,
                                                   unsigned long long* sPat, int* sPatAv, unsigned long long* out,
                                                   int* outAvail) {
   const int lane = threadIdx.x & 31;
@@ -101,10 +141,16 @@ __device__ __forceinline__ void select_role_group(const TopoDev& t, int gid, boo
     return 0ull;
   };
   unsigned long long kreg[EREG];
+#ifdef RBGTOPO_PHASE_CLOCKS
+  if (g_dbg_skip & 2) cnt = 0;
+#endif
 #pragma unroll
   for (int j = 0; j < EREG; ++j) {
-    const int i = lane + 32 * j;
-    kreg[j] = i < cnt ? entry_key(i) : 0ull;
+    kreg[j] = 0ull;
+    if (32 * j < cnt) {  // warp-uniform: small tables skip the tail of the unrolled body
+      const int i = lane + 32 * j;
+      if (i < cnt) kreg[j] = entry_key(i);
+    }
   }
   int npat = 0;
   {
@@ -114,7 +160,7 @@ __device__ __forceinline__ void select_role_group(const TopoDev& t, int gid, boo
       int bi = 0;
 #pragma unroll
       for (int j = 0; j < EREG; ++j)
-        if (kreg[j] < prev && kreg[j] > best) { best = kreg[j]; bi = lane + 32 * j; }
+        if (32 * j < cnt && kreg[j] < prev && kreg[j] > best) { best = kreg[j]; bi = lane + 32 * j; }
       for (int i = lane + 32 * EREG; i < cnt; i += 32) {
         const unsigned long long k = entry_key(i);
         if (k < prev && k > best) { best = k; bi = i; }
@@ -126,42 +172,30 @@ __device__ __forceinline__ void select_role_group(const TopoDev& t, int gid, boo
     }
   }
   __syncwarp();
+  PCLKL(dbg);
 
   // ---- (b) walk the background order; patched nodes are skipped by a table probe
   const int slab_len = t.slab_hi - t.slab_lo;
   int acc = 0;
   for (int pos = 0; pos < slab_len && acc < K; pos += 32) {
-    const int i = pos + lane;
-    int av = 0;
-    unsigned long long key = 0;
-    bool ok = false;
-    if (i < slab_len) {
-      int node;
-      if (role.need > 0) {
-        const unsigned long long ob = t.order[i];
-        node = key_node(ob);
-        const float base = __uint_as_float((uint32_t)(ob >> 32) ^ 0x80000000u);  // base >= 0
-        key = make_key(need * base, node);
-      } else {
-        node = t.slab_lo + i;
-        key = make_key(0.0f, node);
-      }
-      av = t.free_[node];
-      ok = av >= demand;
-      if (ok && rexcl) {
-        const int o = t.node_owner[node];
-        ok = (o == -1 || o == gid);
-      }
-      if (ok && dom != DOM_ANY) ok = t.domain[node] == dom;
-      if (ok) ok = !gtab_has(T, node);
-    }
+    const BgCand c = (pos == 0 && have_first) ? first : bg_load(t, role.need, pos + lane, slab_len);
+    bool ok = c.node >= 0 && c.free_ >= demand;
+    if (ok && rexcl) ok = (c.owner == -1 || c.owner == gid);
+    if (ok && dom != DOM_ANY) ok = c.dom == dom;
+    if (ok) ok = !gtab_has(T, c.node);
     const uint32_t m = __ballot_sync(FULL, ok);
     const int idx = acc + __popc(m & ((1u << lane) - 1u));
-    if (ok && idx < K) { sAcc[idx] = key; sAccAv[idx] = av; }
+    if (ok && idx < K) {
+      // need > 0: base >= 0 is the high word of the order entry
+      const float base = __uint_as_float((uint32_t)(c.ob >> 32) ^ 0x80000000u);
+      sAcc[idx] = role.need > 0 ? make_key(need * base, c.node) : make_key(0.0f, c.node);
+      sAccAv[idx] = c.free_;
+    }
     acc += __popc(m);
   }
   acc = min(acc, K);
   __syncwarp();
+  PCLKL(dbg < 0 ? -1 : dbg + 1);
 
   merge_lists(sAcc, sAccAv, acc, sPat, sPatAv, npat, K, out, outAvail);
 }
@@ -190,7 +224,7 @@ __device__ __forceinline__ void gtab_add_anchor(const TopoDev& t, const GroupTab
 // QB = largest role count of a group in the batch, PB = warps per CTA (>= roles of any wave).
 __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev b, int QB, int HT, int CAP) {
   extern __shared__ __align__(16) unsigned char pg_smem[];
-  __shared__ int sTakenNode[KS], sTakenAmt[KS], sTakenRole[KS];
+  __shared__ int sTakenNode[KS], sTakenAmt[KS], sTakenRole[KS], sRowB[KS], sRowN[KS];
   __shared__ int sDstar, sCnt, sNew, sStatus, sAny;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthreads = blockDim.x, nwarps = nthreads >> 5;
   const int PB = nwarps;
@@ -216,20 +250,22 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
   GroupRole* sRole = reinterpret_cast<GroupRole*>(sPatAv + (size_t)PB * KS);
   float* sPair = reinterpret_cast<float*>(sRole + MAXP);  // [MAXP][RBGTOPO_MAX_GROUP_ROLES]
 
+  PCLK(30);
+  int wave_i = 0;
+  int step = blockIdx.x;
+  StepHdr h = load_hdr(b, step);  // in flight while the table is cleared
   for (int i = tid; i < HT; i += nthreads) {
     T.node[i] = -1;
     T.cons[i] = 0;
   }
   for (int i = tid; i < QB * HT; i += nthreads) T.aw[i] = 0.0f;
   if (tid == 0) sCnt = 0;
-
-  int step = blockIdx.x;
-  StepHdr h = load_hdr(b, step);
   const bool excl_step = (h.flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
   const bool gang = (h.flags & RBGTOPO_STEP_GANG) != 0;
   const int gid = h.gid, Q = h.Q;
   int fixed = excl_step ? h.fixed_domain : -1;
   const size_t stride = (size_t)t.slab_stride;
+  const int slab_len = t.slab_hi - t.slab_lo;
   __syncthreads();
 
   // the group's scheduled pods (anchor records of its first step)
@@ -241,15 +277,49 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
   int cnt_done = 0;  // dense entries whose node attributes are loaded
 
   while (true) {
-    // ---- A. closed neighbourhoods + consumption of the previous wave's placements; this wave's roles
-    for (int a = warp; a < n_new; a += nwarps) gtab_add_anchor(t, T, sTakenNode[a], sTakenRole[a], 1, sTakenAmt[a]);
+    PCLK(wave_i * 8 + 0);
+    // head of the background order for this warp's candidates: in flight during A (used when need > 0)
+    const unsigned long long ob0 = lane < slab_len ? t.order[lane] : 0ull;
+    // ---- A. this wave's roles; consumption + CSR row bounds of the previous wave's placements
     if (tid < h.P) {
       const int4 r = *reinterpret_cast<const int4*>(b.blob + h.role_off + 4 * tid);
       sRole[tid] = GroupRole{r.x, r.y, r.z, r.w};
     }
     for (int i = tid; i < h.P * Q; i += nthreads)
       sPair[(i / Q) * RBGTOPO_MAX_GROUP_ROLES + i % Q] = (float)b.blob[h.pair_off + i];
+    if (tid < n_new) {
+      const int m = sTakenNode[tid];
+      const int rb = t.row_ptr[m], re = t.row_ptr[m + 1];
+      sRowB[tid] = rb;
+      sRowN[tid] = re - rb + 1;  // + the node itself
+      if (m >= t.slab_lo && m < t.slab_hi) atomicAdd(&T.cons[gtab_insert(T, m)], sTakenAmt[tid]);
+    }
     __syncthreads();
+    // background candidates of this warp's role: two dependent round trips, consumed in D
+    BgCand first;
+    const bool have_first = warp < h.P;
+    if (have_first) first = bg_attrs(t, sRole[warp].need, lane, slab_len, ob0);
+    // closed neighbourhoods of the placements: one flat pass over all their CSR entries
+    {
+      int total = 0;
+      for (int a = 0; a < n_new; ++a) total += sRowN[a];
+      for (int e = tid; e < total; e += nthreads) {
+        int a = 0, off = e;
+        while (off >= sRowN[a]) off -= sRowN[a++];
+        const int m = sTakenNode[a], q = sTakenRole[a];
+        int nn, wv;
+        if (off < sRowN[a] - 1) {
+          nn = t.col[sRowB[a] + off];
+          wv = t.w[sRowB[a] + off];
+        } else {
+          nn = m;
+          wv = RBGTOPO_SELF_W;
+        }
+        if (nn >= t.slab_lo && nn < t.slab_hi) atomicAdd(&T.aw[(size_t)q * HT + gtab_insert(T, nn)], (float)wv);
+      }
+    }
+    __syncthreads();
+    PCLK(wave_i * 8 + 1);
 
     // ---- B. node attributes of the slots claimed since the last wave, capacities of all
     const int cnt = sCnt;
@@ -268,11 +338,51 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
     __syncthreads();
     for (int d = tid; d < cnt; d += nthreads) T.dAvail[d] = T.dFree[d] - T.cons[T.dSlot[d]];
     __syncthreads();
+    PCLK(wave_i * 8 + 2);
 
-    // ---- C. sparse corrections of this step's matrix rows (fire and forget)
-    {
+    PCLK(wave_i * 8 + 3);
+    // ---- D. exclusive domain, selection (warp p = role row p)
+    int dstar = excl_step ? fixed : -1;
+    if (excl_step && fixed < 0) {
+      int pstar = -1;
+      for (int p = 0; p < h.P; ++p)
+        if (sRole[p].flags & RBGTOPO_ROLE_EXCLUSIVE) { pstar = p; break; }
+      if (warp == 0) {
+        int d = -1;
+        if (pstar >= 0) {
+          select_role_group(t, gid, excl_step, sRole[pstar], sPair + pstar * RBGTOPO_MAX_GROUP_ROLES, Q, 1, DOM_ANY, T,
+                            cnt, pstar == 0, first, 29, sAcc, sAccAv, sPat, sPatAv, sList, sListAv);
+          const unsigned long long top = sList[0];
+          d = top ? t.domain[key_node(top)] : -1;
+        }
+        if (lane == 0) sDstar = d;
+      }
+      __syncthreads();
+      dstar = sDstar;
+    }
+    if (warp < h.P) {
+      const int p = warp;
+      const bool rexcl = excl_step && (sRole[p].flags & RBGTOPO_ROLE_EXCLUSIVE);
+      const int dom = rexcl ? (dstar >= 0 ? dstar : DOM_NONE) : DOM_ANY;
+      int K = 0;
+      for (int q = 0; q <= p; ++q) K += sRole[q].count;
+      K = min(K, t.n);
+      select_role_group(t, gid, excl_step, sRole[p], sPair + p * RBGTOPO_MAX_GROUP_ROLES, Q, K, dom, T, cnt, true, first, warp == 0 ? wave_i * 8 + 6 : -1,
+                        sAcc + p * KS, sAccAv + p * KS, sPat + p * KS, sPatAv + p * KS, sList + p * KS,
+                        sListAv + p * KS);
+      b.merged[(size_t)(h.rolerow_off + p) * KS + lane] = sList[p * KS + lane];
+    }
+    __syncthreads();
+    PCLK(wave_i * 8 + 4);
+
+    // ---- C. sparse corrections of this step's matrix rows (fire and forget), by the warps the
+    //         greedy does not use (nwarps >= 4)
+#ifdef RBGTOPO_PHASE_CLOCKS
+    if (!(g_dbg_skip & 1))
+#endif
+    if (warp != 0) {
       float* const mrow0 = b.matrix + (size_t)h.rep_off * stride - t.slab_lo;  // mrow0[node]
-      for (int d = tid; d < cnt; d += nthreads) {
+      for (int d = tid - 32; d < cnt; d += nthreads - 32) {
         const int slot = T.dSlot[d];
         const int av = T.dAvail[d];
         const bool consumed = T.cons[slot] > 0;
@@ -291,80 +401,44 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
       }
     }
 
-    // ---- D. exclusive domain, selection (warp p = role row p)
-    int dstar = excl_step ? fixed : -1;
-    if (excl_step && fixed < 0) {
-      int pstar = -1;
-      for (int p = 0; p < h.P; ++p)
-        if (sRole[p].flags & RBGTOPO_ROLE_EXCLUSIVE) { pstar = p; break; }
-      if (warp == 0) {
-        int d = -1;
-        if (pstar >= 0) {
-          select_role_group(t, gid, excl_step, sRole[pstar], sPair + pstar * RBGTOPO_MAX_GROUP_ROLES, Q, 1, DOM_ANY, T,
-                            cnt, sAcc, sAccAv, sPat, sPatAv, sList, sListAv);
-          const unsigned long long top = sList[0];
-          d = top ? t.domain[key_node(top)] : -1;
-        }
-        if (lane == 0) sDstar = d;
-      }
-      __syncthreads();
-      dstar = sDstar;
-    }
-    if (warp < h.P) {
-      const int p = warp;
-      const bool rexcl = excl_step && (sRole[p].flags & RBGTOPO_ROLE_EXCLUSIVE);
-      const int dom = rexcl ? (dstar >= 0 ? dstar : DOM_NONE) : DOM_ANY;
-      int K = 0;
-      for (int q = 0; q <= p; ++q) K += sRole[q].count;
-      K = min(K, t.n);
-      select_role_group(t, gid, excl_step, sRole[p], sPair + p * RBGTOPO_MAX_GROUP_ROLES, Q, K, dom, T, cnt,
-                        sAcc + p * KS, sAccAv + p * KS, sPat + p * KS, sPatAv + p * KS, sList + p * KS,
-                        sListAv + p * KS);
-      b.merged[(size_t)(h.rolerow_off + p) * KS + lane] = sList[p * KS + lane];
-    }
-    __syncthreads();
-
-    // ---- E. greedy from shared memory (spec §3.6); the placements stay in sTaken* for the next wave
+    // ---- E. greedy (spec §3.6), candidates across lanes: lane k judges list entry k, lane i keeps
+    //         placement i; the placements stay in sTaken* for the next wave
     if (warp == 0) {
+      int tnode = -1, tamt = 0, trole = 0;
       int ntaken = 0, unplaced = 0, r = 0;
       for (int p = 0; p < h.P; ++p) {
         const int count = sRole[p].count, demand = sRole[p].demand;
         const int grole = (sRole[p].flags >> 8) & 0xFF;
+        const unsigned long long key = sList[p * KS + lane];  // descending, zero-padded
+        const int node = key ? key_node(key) : -1;
+        const int av = sListAv[p * KS + lane];
         for (int c = 0; c < count; ++c, ++r) {
-          int pick = -1;
-          for (int k = 0; k < KS; ++k) {
-            const unsigned long long key = sList[p * KS + k];
-            if (key == 0) break;
-            const int node = key_node(key);
-            int used = 0;
-            for (int i = lane; i < ntaken; i += 32)
-              if (sTakenNode[i] == node) used += sTakenAmt[i];
-            used = __reduce_add_sync(FULL, used);
-            if (sListAv[p * KS + k] - used >= demand) {
-              pick = node;
-              break;
-            }
+          int used = 0;
+          for (int i = 0; i < ntaken; ++i) {
+            const int n_i = __shfl_sync(FULL, tnode, i), a_i = __shfl_sync(FULL, tamt, i);
+            used += n_i == node ? a_i : 0;
           }
+          const uint32_t okm = __ballot_sync(FULL, key != 0 && av - used >= demand);
+          const int pick = okm ? __shfl_sync(FULL, node, __ffs(okm) - 1) : -1;
           if (pick >= 0) {
-            if (lane == 0) {
-              sTakenNode[ntaken] = pick;
-              sTakenAmt[ntaken] = demand;
-              sTakenRole[ntaken] = grole;
-            }
+            if (lane == ntaken) { tnode = pick; tamt = demand; trole = grole; }
             ++ntaken;
-            __syncwarp();
           } else {
             ++unplaced;
           }
           if (lane == 0) b.assign[h.rep_off + r] = pick;
         }
       }
-      __syncwarp();
       int status = unplaced ? RBGTOPO_PLACED_PART : RBGTOPO_PLACED_ALL;
       if (unplaced && gang) {
         status = RBGTOPO_GANG_FAILED;
         for (int i = lane; i < h.R; i += 32) b.assign[h.rep_off + i] = -1;
         ntaken = 0;
+      }
+      if (lane < ntaken) {
+        sTakenNode[lane] = tnode;
+        sTakenAmt[lane] = tamt;
+        sTakenRole[lane] = trole;
       }
       if (lane == 0) {
         b.status[step] = status;
@@ -376,6 +450,8 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
       }
     }
     __syncthreads();
+    PCLK(wave_i * 8 + 5);
+    ++wave_i;
     if (h.next_step <= 0) break;
     n_new = sNew;
     if (excl_step && dstar >= 0 && sAny) fixed = dstar;
@@ -395,8 +471,8 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
     }
     step = h.next_step;
     h = load_hdr(b, step);
-    __syncthreads();  // sTaken*/sNew are read in A after every warp left E
   }
+  PCLK(31);
 }
 
 }  // namespace rbgtopo

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <climits>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -644,6 +645,36 @@ int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int3
   if (assign && m.total_r) memcpy(assign, b->h_out.p, (size_t)m.total_r * 4);
   if (status && m.n_steps) memcpy(status, b->h_out.p + m.total_r, (size_t)m.n_steps * 4);
   if (domain && m.n_steps) memcpy(domain, b->h_out.p + m.total_r + m.n_steps, (size_t)m.n_steps * 4);
+#ifdef RBGTOPO_PHASE_CLOCKS
+  if (!b->wave_begin.empty() && b->wave_begin.size() > 1) {
+    const int n0 = std::min(2048, b->wave_begin[1]);
+    std::vector<long long> clk((size_t)2048 * 32);
+    if (cudaMemcpyFromSymbol(clk.data(), g_phase_clk, clk.size() * 8) == cudaSuccess) {
+      const char* names[6] = {"start", "A anchors", "B attrs", "C corrections", "D select", "E greedy"};
+      double tot = 0;
+      long long t0min = LLONG_MAX, t1max = 0;
+      for (int g = 0; g < n0; ++g) { tot += (double)(clk[g * 32 + 31] - clk[g * 32 + 30]); t0min = std::min(t0min, clk[g * 32 + 30]); t1max = std::max(t1max, clk[g * 32 + 31]); }
+      fprintf(stderr, "[phase clocks] CTA lifetime avg %.0f cycles; first start -> last end %lld cycles\n", tot / n0, t1max - t0min);
+      for (int w = 0; w < 3; ++w) {
+        double d[6] = {0};
+        for (int g = 0; g < n0; ++g) {
+          const long long* c0 = &clk[g * 32 + w * 8];
+          d[0] += (double)(c0[0] - (w ? clk[g * 32 + (w - 1) * 8 + 5] : clk[g * 32 + 30]));
+          for (int k = 1; k < 6; ++k) d[k] += (double)(c0[k] - c0[k - 1]);
+        }
+        double da = 0, db = 0, dm = 0;
+        for (int g = 0; g < n0; ++g) {
+          const long long* c0 = &clk[g * 32 + w * 8];
+          da += (double)(c0[6] - c0[3]); db += (double)(c0[7] - c0[6]); dm += (double)(c0[4] - c0[7]);
+        }
+        fprintf(stderr, "[phase clocks] wave %d:", w);
+        for (int k = 0; k < 6; ++k) fprintf(stderr, " %s %.0f", names[k], d[k] / n0);
+        fprintf(stderr, " | D: patched %.0f, background %.0f, merge+sync %.0f", da / n0, db / n0, dm / n0);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
+#endif
   rbgtopo_timing tm{};
   float x = 0.f;
   if (cudaEventElapsedTime(&x, b->ev[0], b->ev[1]) == cudaSuccess) tm.h2d_ms = x;
@@ -733,6 +764,12 @@ int32_t rbgtopo_create(const rbgtopo_config* cfg, rbgtopo_ctx** out) {
   CK(cudaFuncSetAttribute(k_select_assign_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
   CK(cudaFuncSetAttribute(k_shard_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
   CK(cudaFuncSetAttribute(k_plan_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
+#ifdef RBGTOPO_PHASE_CLOCKS
+  {
+    const int skip = getenv("RBGTOPO_DBG_SKIP") ? atoi(getenv("RBGTOPO_DBG_SKIP")) : 0;
+    CK(cudaMemcpyToSymbol(g_dbg_skip, &skip, sizeof skip));
+  }
+#endif
   {
     int occ = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_emit, SCORE_THREADS, 0));
