@@ -205,7 +205,7 @@ def run_ours(args):
     eng = TopoPlacer(device=local, rank=rank, world=world)
     eng.set_topology(topo.row_ptr, topo.col_idx, topo.edge_w, topo.free, topo.domain, topo.domain_owner)
     gblob, _ = B200TopoPodGroupManager(eng).groups_blob(rbgs)   # host-side marshalling, identical on every rank
-    wave_blobs = []
+    replicated = world == 1 or args.shard_mode == "replicated"
 
     stream = torch.cuda.Stream()
     eng.set_stream(stream.cuda_stream)
@@ -219,7 +219,7 @@ def run_ours(args):
     gathered = {}
 
     def device_step():
-        if world == 1:
+        if replicated:
             for h in handles:
                 eng.run_staged(h, 1)
             return
@@ -252,7 +252,7 @@ def run_ours(args):
     # and replay it — "CUDA streams and graphs instead of a tracing compiler".
     eager_step = device_step
     graph_note = "eager"
-    if world > 1 and args.graph:
+    if world > 1 and args.graph and not replicated:
         try:
             for _ in range(3):
                 eager_step()
@@ -325,7 +325,7 @@ def run_ours(args):
     # ---- e2e: host buffers through the C ABI, H2D + D2H + host wave loop inside
     eng.set_stream(None)
     h2d = d2h = 0
-    if world == 1:
+    if replicated:
         free = np.ascontiguousarray(topo.free, dtype=np.int32)
         for _ in range(3):
             eng.update_nodes(free)
@@ -397,9 +397,13 @@ def run_ours(args):
             "config": {
                 "workload": f"cfg3: {args.groups} mooncake RBGs (5 roles / 7 pods, 3 dependency waves) x "
                             f"{n_nodes}-node NVLink/PCIe/RDMA/VPC topology"
-                            + (f", node axis sharded over {world} GPUs ({args.nodes} nodes per GPU, one all-gather "
-                               f"of per-shard top-K per wave)" if world > 1 else ""),
-                "launch": graph_note if world > 1 else "eager (1 emit + 3 wave launches per step)",
+                            + ("" if world == 1 else
+                               f", node axis sharded over {world} GPUs ({args.nodes} nodes per GPU): "
+                               + ("dense matrix column-sharded, selection replicated on every rank over all nodes "
+                                  "(identical placements, no per-step collective)" if replicated else
+                                  "one NCCL all-gather of per-shard top-K lists per wave")),
+                "parallelism": "single GPU" if world == 1 else f"node-axis x{world}, " + args.shard_mode,
+                "launch": "eager (k_score_emit + k_plan_group per step)" if replicated else graph_note,
                 "groups": args.groups, "nodes": n_nodes, "edges": int(topo.e), "replicas_per_step": total_r,
                 "emit_matrix": True,
                 "l2": "dense-matrix write stream per step "
@@ -415,7 +419,7 @@ def run_ours(args):
             "clocks": dict(clocks, window="clock soak (--soak s of identical untimed steps) + timed region"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
-                         "kernel": "k_score_emit (world=1: one launch per step emits the dense rows of all 3 waves)",
+                         "kernel": "k_score_emit (one launch per step and rank emits the dense rows of all 3 waves)",
                          "peak_source": peak_src, "algo_bytes_per_step": algo_bytes,
                          "kernel_ms_per_step": score_ms, "frac_of_nominal_8000": achieved / 8000.0},
             "cpu_baseline": cpu,
@@ -472,6 +476,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--ref-groups", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--shard-mode", default="replicated", choices=["replicated", "allgather"],
+                    help="N > 1: 'replicated' = dense matrix column-sharded, selection replicated on every rank, "
+                         "no per-step collective; 'allgather' = per-shard top-K lists all-gathered (NCCL) per wave")
     ap.add_argument("--graph", action="store_true",
                     help="world > 1: capture the step into a CUDA graph (experimental: hung with NCCL on this stack)")
     ap.add_argument("--soak", type=float, default=0.6, help="seconds of untimed identical steps before the timed region")

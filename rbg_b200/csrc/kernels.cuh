@@ -46,6 +46,7 @@ struct TopoDev {
   // slab nodes sorted by key(base[n], n) descending (one radix sort per snapshot):
   // the "background" order every unpatched row shares
   const unsigned long long* order;
+  const unsigned long long* order_all;  // the same over ALL nodes (== order when world == 1)
 };
 
 struct BatchDev {

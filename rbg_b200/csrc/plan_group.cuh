@@ -14,6 +14,11 @@
 //   * the dense matrix gets its sparse corrections per wave from the table: one
 //     red.global.add.f32 per (patched node, replica row) with the summed delta,
 //     -inf where consumed capacity made the node infeasible.
+// Node-axis sharding (world > 1): selection is REPLICATED — it is O(K + patches) per role,
+// independent of the node count, so every rank runs it over ALL nodes (table, background
+// order `order_all`, greedy) and reaches the identical placement without exchanging
+// anything; only the HBM-bound dense matrix is sharded, and a rank applies the
+// corrections that fall into its column slab.  No collective on the step path.
 // Selection (patched slots merged with the walk of the background order) and the
 // greedy are the ones of select_fast.cuh.  Steps are read from the expanded plan
 // blob; the chained anchor / consumed records of later steps are neither written
@@ -89,23 +94,23 @@ struct BgCand {
   int node, free_, owner, dom;
 };
 // second half of a candidate load: `ob` = t.order[i] is already in a register
-__device__ __forceinline__ BgCand bg_attrs(const TopoDev& t, int need_i, int i, int slab_len, unsigned long long ob) {
+__device__ __forceinline__ BgCand bg_attrs(const TopoDev& t, int need_i, int i, int n_sel, unsigned long long ob) {
   BgCand c;
   c.ob = ob;
   c.node = -1;
   c.free_ = 0;
   c.owner = -1;
   c.dom = -1;
-  if (i < slab_len) {
-    c.node = need_i > 0 ? key_node(ob) : t.slab_lo + i;
+  if (i < n_sel) {
+    c.node = need_i > 0 ? key_node(ob) : i;
     c.free_ = t.free_[c.node];
     c.owner = t.node_owner[c.node];
     c.dom = t.domain[c.node];
   }
   return c;
 }
-__device__ __forceinline__ BgCand bg_load(const TopoDev& t, int need_i, int i, int slab_len) {
-  return bg_attrs(t, need_i, i, slab_len, (i < slab_len && need_i > 0) ? t.order[i] : 0ull);
+__device__ __forceinline__ BgCand bg_load(const TopoDev& t, int need_i, int i, int n_sel) {
+  return bg_attrs(t, need_i, i, n_sel, (i < n_sel && need_i > 0) ? t.order_all[i] : 0ull);
 }
 
 // top-K of a role row into out[0..KS) (+ capacities): select_role_fast with the
@@ -175,10 +180,9 @@ __device__ __forceinline__ void select_role_group(const TopoDev& t, int gid, boo
   PCLKL(dbg);
 
   // ---- (b) walk the background order; patched nodes are skipped by a table probe
-  const int slab_len = t.slab_hi - t.slab_lo;
   int acc = 0;
-  for (int pos = 0; pos < slab_len && acc < K; pos += 32) {
-    const BgCand c = (pos == 0 && have_first) ? first : bg_load(t, role.need, pos + lane, slab_len);
+  for (int pos = 0; pos < t.n && acc < K; pos += 32) {
+    const BgCand c = (pos == 0 && have_first) ? first : bg_load(t, role.need, pos + lane, t.n);
     bool ok = c.node >= 0 && c.free_ >= demand;
     if (ok && rexcl) ok = (c.owner == -1 || c.owner == gid);
     if (ok && dom != DOM_ANY) ok = c.dom == dom;
@@ -204,7 +208,7 @@ __device__ __forceinline__ void select_role_group(const TopoDev& t, int gid, boo
 // capacity `dem` consumed on m.  One warp.
 __device__ __forceinline__ void gtab_add_anchor(const TopoDev& t, const GroupTab& T, int m, int q, int c, int dem) {
   const int lane = threadIdx.x & 31;
-  if (lane == 0 && dem > 0 && m >= t.slab_lo && m < t.slab_hi) atomicAdd(&T.cons[gtab_insert(T, m)], dem);
+  if (lane == 0 && dem > 0) atomicAdd(&T.cons[gtab_insert(T, m)], dem);
   if (c <= 0) return;
   const int rb = t.row_ptr[m], re = t.row_ptr[m + 1];
   for (int j = rb + lane; j <= re; j += 32) {  // j == re stands for the anchor's own node
@@ -216,7 +220,7 @@ __device__ __forceinline__ void gtab_add_anchor(const TopoDev& t, const GroupTab
       nn = m;
       wv = RBGTOPO_SELF_W * c;
     }
-    if (nn >= t.slab_lo && nn < t.slab_hi) atomicAdd(&T.aw[(size_t)q * T.HT + gtab_insert(T, nn)], (float)wv);
+    atomicAdd(&T.aw[(size_t)q * T.HT + gtab_insert(T, nn)], (float)wv);
   }
 }
 
@@ -265,7 +269,6 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
   const int gid = h.gid, Q = h.Q;
   int fixed = excl_step ? h.fixed_domain : -1;
   const size_t stride = (size_t)t.slab_stride;
-  const int slab_len = t.slab_hi - t.slab_lo;
   __syncthreads();
 
   // the group's scheduled pods (anchor records of its first step)
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
   while (true) {
     PCLK(wave_i * 8 + 0);
     // head of the background order for this warp's candidates: in flight during A (used when need > 0)
-    const unsigned long long ob0 = lane < slab_len ? t.order[lane] : 0ull;
+    const unsigned long long ob0 = lane < t.n ? t.order_all[lane] : 0ull;
     // ---- A. this wave's roles; consumption + CSR row bounds of the previous wave's placements
     if (tid < h.P) {
       const int4 r = *reinterpret_cast<const int4*>(b.blob + h.role_off + 4 * tid);
@@ -292,13 +295,13 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
       const int rb = t.row_ptr[m], re = t.row_ptr[m + 1];
       sRowB[tid] = rb;
       sRowN[tid] = re - rb + 1;  // + the node itself
-      if (m >= t.slab_lo && m < t.slab_hi) atomicAdd(&T.cons[gtab_insert(T, m)], sTakenAmt[tid]);
+      atomicAdd(&T.cons[gtab_insert(T, m)], sTakenAmt[tid]);
     }
     __syncthreads();
     // background candidates of this warp's role: two dependent round trips, consumed in D
     BgCand first;
     const bool have_first = warp < h.P;
-    if (have_first) first = bg_attrs(t, sRole[warp].need, lane, slab_len, ob0);
+    if (have_first) first = bg_attrs(t, sRole[warp].need, lane, t.n, ob0);
     // closed neighbourhoods of the placements: one flat pass over all their CSR entries
     {
       int total = 0;
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
           nn = m;
           wv = RBGTOPO_SELF_W;
         }
-        if (nn >= t.slab_lo && nn < t.slab_hi) atomicAdd(&T.aw[(size_t)q * HT + gtab_insert(T, nn)], (float)wv);
+        atomicAdd(&T.aw[(size_t)q * HT + gtab_insert(T, nn)], (float)wv);
       }
     }
     __syncthreads();
@@ -384,9 +387,11 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
       float* const mrow0 = b.matrix + (size_t)h.rep_off * stride - t.slab_lo;  // mrow0[node]
       for (int d = tid - 32; d < cnt; d += nthreads - 32) {
         const int slot = T.dSlot[d];
+        const int node = T.node[slot];
+        if (node < t.slab_lo || node >= t.slab_hi) continue;  // another rank's columns
         const int av = T.dAvail[d];
         const bool consumed = T.cons[slot] > 0;
-        float* rowp = mrow0 + T.node[slot];
+        float* rowp = mrow0 + node;
         for (int p = 0; p < h.P; ++p) {
           const int count = sRole[p].count;
           if (consumed && av < sRole[p].demand) {

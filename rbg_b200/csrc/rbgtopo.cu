@@ -92,6 +92,7 @@ struct Topology {
   DevBuf<unsigned char> fmin;
   DevBuf<float> base;
   DevBuf<unsigned long long> okeys, order;  // background order of the slab (score.cuh / select.cuh)
+  DevBuf<unsigned long long> okeys_all, order_all;  // world > 1: the order over all nodes (plan_group.cuh)
   DevBuf<unsigned char> sort_tmp;
   std::vector<int> h_degp1;  // deg(n) + 1, for the patch-list capacity of a step
   int max_degp1 = 1;
@@ -220,12 +221,13 @@ TopoDev topo_dev(const rbgtopo_ctx* c) {
   t.dom_ptr = T.dom_ptr.p;
   t.dom_nodes = T.dom_nodes.p;
   t.order = T.order.p;
+  t.order_all = c->cfg.world > 1 ? T.order_all.p : T.order.p;
   return t;
 }
 
-__global__ void k_order_keys(TopoDev t, unsigned long long* keys) {
+__global__ void k_order_keys(TopoDev t, int lo, int hi, unsigned long long* keys) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < t.slab_hi - t.slab_lo) keys[i] = make_key(t.base[t.slab_lo + i], t.slab_lo + i);
+  if (i < hi - lo) keys[i] = make_key(t.base[lo + i], lo + i);
 }
 
 // prep + base kernels on `s`; records base_ms.
@@ -257,12 +259,23 @@ int run_base(rbgtopo_ctx* c, cudaStream_t s, bool sync) {
     CK(T.okeys.reserve(slab_len));
     CK(T.order.reserve(slab_len));
     td = topo_dev(c);
-    k_order_keys<<<(slab_len + 255) / 256, 256, 0, s>>>(td, T.okeys.p);
+    k_order_keys<<<(slab_len + 255) / 256, 256, 0, s>>>(td, c->slab_lo, c->slab_hi, T.okeys.p);
     size_t tmp_bytes = 0;
     CK(cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp_bytes, T.okeys.p, T.order.p, slab_len, 0, 64, s));
     CK(T.sort_tmp.reserve(tmp_bytes + 256));
     tmp_bytes = T.sort_tmp.cap;
     CK(cub::DeviceRadixSort::SortKeysDescending(T.sort_tmp.p, tmp_bytes, T.okeys.p, T.order.p, slab_len, 0, 64, s));
+  }
+  if (c->cfg.world > 1 && T.n > 0) {  // replicated selection (plan_group.cuh) walks the order of ALL nodes
+    CK(T.okeys_all.reserve(T.n));
+    CK(T.order_all.reserve(T.n));
+    td = topo_dev(c);
+    k_order_keys<<<(T.n + 255) / 256, 256, 0, s>>>(td, 0, T.n, T.okeys_all.p);
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp_bytes, T.okeys_all.p, T.order_all.p, T.n, 0, 64, s));
+    CK(T.sort_tmp.reserve(tmp_bytes + 256));
+    tmp_bytes = T.sort_tmp.cap;
+    CK(cub::DeviceRadixSort::SortKeysDescending(T.sort_tmp.p, tmp_bytes, T.okeys_all.p, T.order_all.p, T.n, 0, 64, s));
   }
   CK(cudaEventRecord(c->ev_base_b, s));
   CK(cudaEventRecord(c->topo_ready, s));
@@ -566,6 +579,8 @@ int launch_select_assign(rbgtopo_ctx* c, Batch* b, cudaStream_t s, const BatchDe
       return RBGTOPO_OK;
     }
   }
+  if (c->cfg.world != 1)
+    return fail(RBGTOPO_ELIMIT, "plan does not fit k_plan_group's shared memory: world > 1 must use the shard_wave calls");
   // fallback: one launch per wave, placements chained through the plan blob in HBM
   const int wave_mode = SEL_CORRECT | SEL_CHAIN;
   for (size_t w = 0; w + 1 < b->wave_begin.size(); ++w) {
@@ -1793,7 +1808,6 @@ void plan_results(const Batch* b, int32_t* assign, int32_t* status, int32_t* dom
 int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int32_t* assign,
                              int32_t* status, int32_t* domain) {
   if (!c || !gb || !assign) return fail(RBGTOPO_EINVAL, "null argument");
-  if (c->cfg.world != 1) return fail(RBGTOPO_EINVAL, "place_groups needs world == 1");
   std::vector<char> dirty;
   {
     std::shared_lock<std::shared_mutex> lk(c->topo_mu);
@@ -1826,6 +1840,8 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
   bool any = false;
   for (char d : dirty) any |= d != 0;
   if (!any) return RBGTOPO_OK;
+  if (c->cfg.world != 1)
+    return fail(RBGTOPO_ELIMIT, "a non-gang group was placed only partially: the exact host-driven loop needs world == 1");
   return place_groups_slow(c, gb, words, assign, status, domain, &dirty);
 }
 
@@ -1867,7 +1883,10 @@ int32_t rbgtopo_stage(rbgtopo_ctx* c, const int32_t* blob, int64_t words, int32_
 
 int32_t rbgtopo_run_staged(rbgtopo_ctx* c, int32_t handle, int32_t iters) {
   if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
-  if (c->cfg.world != 1) return fail(RBGTOPO_EINVAL, "run_staged needs world == 1");
+  if (c->cfg.world != 1) {
+    Batch* pb = batch_of(c, handle);  // world > 1: only multi-wave plans run without the shard calls
+    if (pb && pb->wave_begin.empty()) return fail(RBGTOPO_EINVAL, "run_staged of a step batch needs world == 1; use the shard calls");
+  }
   if (iters < 1 || iters > 4096) return fail(RBGTOPO_EINVAL, "iters");
   std::shared_lock<std::shared_mutex> lk(c->topo_mu);
   Batch* b = batch_of(c, handle);

@@ -91,6 +91,39 @@ for n, kw in [(8000, {}), (6000, dict(excl_every=3, gang_every=4)), (5000, dict(
             continue
         assert got == want, (rank, n, i, got, want)
         assert status[i] == r.status and domain[i] == r.domain, (rank, n, i, status[i], r.status, domain[i], r.domain)
+    eng.release(h)
+    # ---- the same plan with REPLICATED selection (k_plan_group over all nodes on every rank, the
+    #      dense matrix still column-sharded): no collective at all, identical placements on every rank
+    h = eng.stage_groups(gblob)
+    eng.run_staged(h, 1)
+    assign2, status2, domain2 = eng.fetch(h)
+    assert np.array_equal(assign2, assign) and np.array_equal(status2, status) and np.array_equal(domain2, domain), (rank, n)
+    if not kw:      # nobody fails in this fleet: the plan's rows line up with the wave-by-wave oracle run
+        from oracle import placer as oracle_placer
+        from rbg_b200.blob import BlobBuilder
+        from rbg_b200.plugin import _GroupRun
+        gruns = [_GroupRun(r, B200TopoPodGroupManager(eng).arith) for r in rbgs]
+        lo, hi = eng.slab()
+        row = w = 0
+        while True:
+            active = [g for g in gruns if w < len(g.waves)]
+            if not active:
+                break
+            bb = BlobBuilder()
+            for g in active:
+                bb.add(g.step(w))
+            oref = oracle_placer.place(topo, bb.build(), want_matrix=True, want_topk=False)
+            assert oref["rc"] == 0 and (oref["status"] == 0).all()
+            for i in range(0, oref["matrix"].shape[0], 3):
+                got = eng.read_scores(h, row + i)
+                assert np.array_equal(got.view(np.uint32), oref["matrix"][i, lo:hi].view(np.uint32)), (rank, w, i)
+            off = 0
+            for i, g in enumerate(active):
+                cnt = sum(c for _, _, c in g.waves[w].roles)
+                g.absorb(w, oref["assign"][off:off + cnt], int(oref["status"][i]), int(oref["domain"][i]), n)
+                off += cnt
+            row += oref["matrix"].shape[0]
+            w += 1
     eng.release(h); eng.close()
 dist.barrier()
 if rank == 0: print("SHARD_OK", world)
