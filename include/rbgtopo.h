@@ -189,11 +189,14 @@ int32_t rbgtopo_score_assign(rbgtopo_ctx* ctx, const int32_t* blob,
  * the given order (the caller passes them sorted by (level, name), i.e. the
  * output of rbgtopo_dependency_levels / dependency.go:129-205), a new wave at
  * every level change and whenever RBGTOPO_MAX_STEP_REPLICAS / _ROLES would be
- * exceeded — places all groups' wave w in ONE batched launch, feeds the
- * placements back as anchors / consumed capacity / fixed exclusive domain of
- * wave w+1 (levels see earlier levels: rolebasedgroup_controller.go:448-476),
- * and applies gang all-or-nothing over the whole group
- * (k8s-scheduler-plugin/manager.go:131).  need_rho of a wave is
+ * exceeded — feeds the placements of wave w back as anchors / consumed
+ * capacity / fixed exclusive domain of wave w+1 (levels see earlier levels:
+ * rolebasedgroup_controller.go:448-476), and applies gang all-or-nothing over
+ * the whole group (k8s-scheduler-plugin/manager.go:131).  On the device this is
+ * a multi-wave plan: the GROUPS blob is expanded into one step blob in HBM, one
+ * launch scores the dense rows of every wave, one launch runs every group's
+ * waves back to back.  With world > 1 every rank calls it with
+ * the same blob and gets the same result (replicated selection).  need_rho of a wave is
  * min(RBGTOPO_NEED_CAP, still-unplaced replicas of the roles q with
  * pair[rho][q] > 0), DESIGN.md §3.2.
  *   word 0 magic 0x47474252 ("RBGG")  1 version  2 n_groups  3 total words
@@ -214,10 +217,11 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* ctx, const int32_t* groups,
                              int32_t* status, int32_t* domain);
 
 /* rbgtopo_place_groups pipeline, staged: the groups are compiled into a
- * device-resident multi-wave plan (one step blob, wave-major; later waves' anchor /
- * consumed records are filled in on the device by the wave that places them), so
- * rbgtopo_run_staged runs ONE score launch for the dense rows of every wave plus
- * one select/assign launch per wave with no host round trip.  rbgtopo_fetch then
+ * device-resident multi-wave plan (one step blob, wave-major, expanded on the
+ * device), so rbgtopo_run_staged runs ONE score launch for the dense rows of every
+ * wave plus one launch that walks every group's waves (or one launch per wave when
+ * a group's table does not fit shared memory) with no host round trip; valid for
+ * any world.  rbgtopo_fetch then
  * returns group-order results like place_groups (groups the plan could not finish
  * exactly — non-gang groups with an unplaced replica — keep status 1; place_groups
  * itself re-runs those through the host-driven loop). */
@@ -231,8 +235,9 @@ int32_t rbgtopo_stage(rbgtopo_ctx* ctx, const int32_t* blob, int64_t blob_words,
 /* run_staged only ENQUEUES `iters` passes on the call's stream (asynchronous);
  * rbgtopo_fetch synchronises, copies the results of the last pass (any output
  * pointer may be NULL) and harvests the timing of every pass since the
- * previous fetch (rbgtopo_last_timing: score_ms = average k_score_select
- * duration from CUDA events recorded around each launch). */
+ * previous fetch (rbgtopo_last_timing: score_ms = average k_score_emit
+ * duration from CUDA events recorded around each launch).  With world > 1
+ * run_staged accepts multi-wave plans only (step batches use the shard calls). */
 int32_t rbgtopo_run_staged(rbgtopo_ctx* ctx, int32_t handle, int32_t iters);
 int32_t rbgtopo_fetch(rbgtopo_ctx* ctx, int32_t handle, int32_t* assign,
                       int32_t* status, int32_t* domain);

@@ -1,15 +1,18 @@
-// kernels.cuh — sm_100a kernels of the placement hot path.
+// kernels.cuh — shared device types and helpers + the per-snapshot kernels of the
+// placement hot path.
 //
 // Algebra: the spec's score  S_rho = W·A_rho  with
 // A_rho = sum_q pair[rho][q]·anchor[q] + need_rho·min(free,F)  is linear in A, so
 //     S_rho[n] = need_rho · base[n]  +  sum over anchor pods (m,q,c) of
 //                pair[rho][q]·c·W[n][m]
 // with base = W·min(free,F) shared by EVERY step of a snapshot (one CSR pass per
-// snapshot, k_base) and the anchor term sparse (<= (deg+1) entries per pod,
-// scattered into shared memory per work item).  All terms are exact integers
-// below 2^24 (spec §3.4), so this is bit-identical to the oracle's sequential
-// fp32 accumulation.  The dense (replica x node) matrix is then a pure HBM
-// write stream fused with the per-row top-K selection (k_score_select).
+// snapshot, k_base below: TMA-staged SpMV) and the anchor term sparse (<= deg+1
+// entries per pod).  All terms are exact integers below 2^24 (spec §3.4), so
+// this is bit-identical to the oracle's sequential fp32 accumulation.  The dense
+// (replica x node) matrix is then a pure HBM write stream (score.cuh) plus
+// sparse red.global.add.f32 corrections; selection works from `base`, the
+// per-snapshot sorted `order` and the few patched nodes (select_fast.cuh,
+// plan_group.cuh) and never scans the matrix.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -136,71 +139,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
           "r"(smem_u32(dst_smem)),
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
-}
-
-// Exact top-K (descending, unique u64 keys, 0 = empty) of `len` keys in shared
-// or global memory by one warp.  Two-level threshold select:
-//   1. every lane takes the max of its strided share;
-//   2. the K-th largest lane maximum t is a lower bound of the K-th largest key
-//      (K <= 32), found with K REDUX rounds on one value per lane;
-//   3. only keys >= t can be in the top-K and they all sit in the <= K lanes
-//      whose maximum is >= t, so at most K*ceil(len/32) keys survive; they are
-//      compacted into `scratch` (shared, >= cap entries) with ballots;
-//   4. K "largest key below the previous one" rounds over the survivors.
-// out[0..K) gets the keys (0-padded).  All 32 lanes must call; `out` may be
-// shared or global; returns the number of valid keys.
-__device__ __forceinline__ int warp_topk(const unsigned long long* __restrict__ keys, int len,
-                                         int K, unsigned long long* scratch, int cap,
-                                         unsigned long long* out) {
-  const int lane = threadIdx.x & 31;
-  unsigned long long lmax = 0;
-  for (int i = lane; i < len; i += 32) {
-    unsigned long long k = keys[i];
-    lmax = k > lmax ? k : lmax;
-  }
-  // K-th largest lane maximum
-  unsigned long long thr = 0, cur = lmax;
-  for (int r = 0; r < K; ++r) {
-    unsigned long long m = warp_max_u64(cur);
-    thr = m;
-    if (m == 0) break;
-    if (cur == m) cur = 0;
-  }
-  // compact survivors
-  int cnt = 0;
-  for (int i0 = 0; i0 < len; i0 += 32) {
-    int i = i0 + lane;
-    unsigned long long k = (i < len) ? keys[i] : 0ull;
-    bool keep = (k != 0ull) && (k >= thr);
-    uint32_t b = __ballot_sync(FULL, keep);
-    if (keep) {
-      int pos = cnt + __popc(b & ((1u << lane) - 1u));
-      if (pos < cap) scratch[pos] = k;
-    }
-    cnt += __popc(b);
-  }
-  __syncwarp();
-  if (cnt > cap) cnt = cap;  // cannot happen when cap >= K*ceil(len/32)
-  // final rounds
-  unsigned long long prev = ~0ull;
-  int valid = 0;
-  for (int r = 0; r < K; ++r) {
-    unsigned long long best = 0;
-    for (int i = lane; i < cnt; i += 32) {
-      unsigned long long k = scratch[i];
-      if (k < prev && k > best) best = k;
-    }
-    best = warp_max_u64(best);
-    if (lane == 0) out[r] = best;
-    if (best == 0) {
-      for (int q = r + 1 + lane; q < K; q += 32) out[q] = 0;
-      break;
-    }
-    prev = best;
-    ++valid;
-  }
-  __syncwarp();
-  return valid;
 }
 
 // ============================================================= k_prep / k_base

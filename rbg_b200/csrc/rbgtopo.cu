@@ -1,7 +1,9 @@
 // rbgtopo.cu — host runtime behind the C ABI of include/rbgtopo.h: context,
-// snapshot upload + validation, batch ("blob") validation, slot pool, launches,
-// timing.  Kernels live in kernels.cuh / select.cuh.  No CPU fallback exists:
-// every entry point needs a CUDA device (sm_100).
+// snapshot upload + validation + refresh pipeline, batch ("blob") validation,
+// multi-wave plan geometry (the plan itself is expanded on the device: plan.cuh),
+// slot pool, launches, timing.  Kernels: kernels.cuh (snapshot), score.cuh (dense
+// matrix), plan_group.cuh / select_fast.cuh / select.cuh (selection + greedy).
+// No CPU fallback exists: every entry point needs a CUDA device (sm_100).
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 

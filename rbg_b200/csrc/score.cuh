@@ -1,36 +1,33 @@
 // score.cuh — k_score_emit: the dominant kernel of the path.
 //
 // Emits the dense (replica x node) score matrix as a pure HBM write stream.
-// One work item = (step, chunk of `chunk` <= 2048 nodes of this rank's slab); a
-// persistent grid of 256-thread CTAs takes contiguous item ranges, so the chunks
-// of a step run back to back on one SM (its header, roles, anchors and the
-// anchors' CSR rows are L1 hits after the first chunk).  No shared memory, no
-// block barrier: every warp owns two 128-node segments of the chunk.
+// One work item = (step, chunk of `chunk` <= 2048 nodes of this rank's slab).  A
+// persistent grid (SMs x 6 CTAs of 256 threads, 40 registers, no shared memory)
+// takes contiguous item ranges that the host balanced by BYTES (an item weighs the
+// replica rows of its step: cta_item[], rbgtopo.cu balance_emit_items), so the
+// chunks of a step run back to back on one SM (header / role records are L1 hits
+// after the first chunk) and every CTA writes the same amount.
 //   1. background: every role row is  S = need*base[n]  where the node is feasible
 //      (free >= demand, and for exclusive roles the domain is unowned or ours),
 //      else -inf; written once per replica of the role with 128-bit streaming
-//      stores.  base/free are per-snapshot vectors shared by all steps (L1/L2).
-//   2. only for steps with anchor pods / consumed capacity: the warp walks the CSR
-//      row of every anchor m (coalesced int32 loads, L1-hot) and, for the
-//      neighbours inside ITS OWN segments, adds pair*c*w onto the scores it has
-//      just written with fire-and-forget red.global.add.f32 (+ the self term);
-//      nodes whose consumed capacity makes them infeasible are overwritten with
-//      -inf.  Stores and reductions of one warp to one address stay ordered
-//      (__syncwarp), so no fence or block barrier is needed.  All addends are
-//      exact integers and -inf absorbs adds, so the result is bit-identical to
-//      the oracle's sequential fp32 accumulation in any order.
-// Selection never touches this kernel's data path except for reading back the
-// few patched scores (select.cuh).
+//      stores (st.global.cs.v4).  base/free are per-snapshot vectors shared by all
+//      steps (L1/L2).  Multi-wave plans stop here: their sparse corrections are
+//      applied by the kernel that knows the placements (plan_group.cuh).
+//   2. step-level batches with anchor pods / consumed capacity: pair*c*w is added
+//      onto the just-written, L2-hot scores with fire-and-forget
+//      red.global.add.f32 (+ the self term); nodes whose consumed capacity makes
+//      them infeasible are overwritten with -inf.  With <= 2 records every warp
+//      scans them and applies those inside its own segments (ordered by
+//      __syncwarp alone); otherwise one block barrier, then the records are spread
+//      over the warps.  All addends are exact integers and -inf absorbs adds, so
+//      the result is bit-identical to the oracle's sequential fp32 accumulation
+//      in any order.
 #pragma once
 #include "kernels.cuh"
 
 namespace rbgtopo {
 
 constexpr int GPT = 2;  // float4 groups per thread: chunk <= 256 * 4 * GPT = 2048
-
-__device__ __forceinline__ void prefetch_l1(const void* p) {
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-}
 
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
