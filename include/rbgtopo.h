@@ -178,7 +178,9 @@ int32_t rbgtopo_update_nodes(rbgtopo_ctx* ctx, const int32_t* free_slots,
  *   assign[total R]    : node per replica in replica order, -1 = unplaced
  *   status[n_steps]    : RBGTOPO_PLACED_* per step
  *   domain[n_steps]    : exclusive domain chosen / confirmed, -1 if none
- * With world > 1 this entry is invalid (use the shard calls below). */
+ * With world > 1 every rank calls it with the same blob: each scores its column
+ * slab of the matrix and computes the identical assignment (replicated selection,
+ * DESIGN.md §7). */
 int32_t rbgtopo_score_assign(rbgtopo_ctx* ctx, const int32_t* blob,
                              int64_t blob_words, int32_t* assign,
                              int32_t* status, int32_t* domain);
@@ -236,8 +238,8 @@ int32_t rbgtopo_stage(rbgtopo_ctx* ctx, const int32_t* blob, int64_t blob_words,
  * rbgtopo_fetch synchronises, copies the results of the last pass (any output
  * pointer may be NULL) and harvests the timing of every pass since the
  * previous fetch (rbgtopo_last_timing: score_ms = average k_score_emit
- * duration from CUDA events recorded around each launch).  With world > 1
- * run_staged accepts multi-wave plans only (step batches use the shard calls). */
+ * duration from CUDA events recorded around each launch).  Valid for any world
+ * (replicated selection); the shard calls below are the all-gather alternative. */
 int32_t rbgtopo_run_staged(rbgtopo_ctx* ctx, int32_t handle, int32_t iters);
 int32_t rbgtopo_fetch(rbgtopo_ctx* ctx, int32_t handle, int32_t* assign,
                       int32_t* status, int32_t* domain);

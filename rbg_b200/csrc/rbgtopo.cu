@@ -560,6 +560,8 @@ int launch_select_assign(rbgtopo_ctx* c, Batch* b, cudaStream_t s, const BatchDe
     const int nth = std::max(128, 32 * b->m.max_p);
     if (fast)
       k_select_assign_fast<<<ns, nth, fast_smem_bytes(nth / 32, HT, CAP), s>>>(topo_dev(c), d, 0, 0, HT, CAP);
+    else if (c->cfg.world != 1)
+      return fail(RBGTOPO_ELIMIT, "a step's patched set exceeds shared memory: world > 1 must use the shard calls");
     else
       k_select_assign<<<ns, 32 * b->m.max_p, select_smem_bytes(b->m.max_p), s>>>(topo_dev(c), d, 0, 0);
     ++*launches;
@@ -942,7 +944,7 @@ int32_t rbgtopo_update_nodes(rbgtopo_ctx* c, const int32_t* free_slots, const in
 int32_t rbgtopo_score_assign(rbgtopo_ctx* c, const int32_t* blob, int64_t words, int32_t* assign,
                              int32_t* status, int32_t* domain) {
   if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
-  if (c->cfg.world != 1) return fail(RBGTOPO_EINVAL, "score_assign needs world == 1; use the shard calls");
+
   std::shared_lock<std::shared_mutex> lk(c->topo_mu);
   CK(cudaSetDevice(c->cfg.device));
   Batch* b = nullptr;
@@ -982,7 +984,6 @@ struct GroupRun {
 static int32_t place_groups_slow(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int32_t* assign,
                                  int32_t* status, int32_t* domain, const std::vector<char>* only) {
   if (!c || !gb) return fail(RBGTOPO_EINVAL, "null argument");
-  if (c->cfg.world != 1) return fail(RBGTOPO_EINVAL, "place_groups needs world == 1");
   if (words < RBGTOPO_HDR_WORDS || gb[0] != RBGTOPO_GROUPS_MAGIC || gb[1] != RBGTOPO_ABI_VERSION ||
       gb[3] != words)
     return fail(RBGTOPO_EINVAL, "bad groups blob header");
@@ -1842,8 +1843,6 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
   bool any = false;
   for (char d : dirty) any |= d != 0;
   if (!any) return RBGTOPO_OK;
-  if (c->cfg.world != 1)
-    return fail(RBGTOPO_ELIMIT, "a non-gang group was placed only partially: the exact host-driven loop needs world == 1");
   return place_groups_slow(c, gb, words, assign, status, domain, &dirty);
 }
 
@@ -1885,10 +1884,7 @@ int32_t rbgtopo_stage(rbgtopo_ctx* c, const int32_t* blob, int64_t words, int32_
 
 int32_t rbgtopo_run_staged(rbgtopo_ctx* c, int32_t handle, int32_t iters) {
   if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
-  if (c->cfg.world != 1) {
-    Batch* pb = batch_of(c, handle);  // world > 1: only multi-wave plans run without the shard calls
-    if (pb && pb->wave_begin.empty()) return fail(RBGTOPO_EINVAL, "run_staged of a step batch needs world == 1; use the shard calls");
-  }
+
   if (iters < 1 || iters > 4096) return fail(RBGTOPO_EINVAL, "iters");
   std::shared_lock<std::shared_mutex> lk(c->topo_mu);
   Batch* b = batch_of(c, handle);

@@ -1,6 +1,8 @@
-// select_fast.cuh — k_select_assign_fast: the world == 1 selection / assignment
-// kernel with the step's patched nodes held in a shared-memory hash table
-// (DESIGN.md §4.3).  One CTA per step, warp p = role row p.
+// select_fast.cuh — k_select_assign_fast: the selection / assignment kernel of
+// step-level batches with the step's patched nodes held in a shared-memory hash
+// table.  One CTA per step, warp p = role row p.  Selection
+// ranges over ALL nodes on every rank (replicated selection); the
+// matrix corrections a rank issues are those of its own column slab.
 //
 //   1. one pass over the anchors' CSR rows (warp per anchor, coalesced int32 loads)
 //      inserts every slab neighbour into the table and accumulates pair*c*w into
@@ -34,6 +36,10 @@ struct PatchTab {
   int* dAvail;   // [CAP] free - consumed
   int* dDom;     // [CAP] domain, bit 31 set = domain owned by another group
   int cnt;
+  // nodes selection ranges over: the rank's slab (all-gather scheme, k_shard_select) or all
+  // nodes (replicated selection, k_select_assign_fast: identical results on every rank)
+  int sel_lo, sel_hi;
+  const unsigned long long* sel_order;  // background order of [sel_lo, sel_hi)
 };
 __host__ __device__ inline size_t fast_smem_bytes(int PB, int HT, int CAP) {
   return (size_t)HT * 4 * (2 + PB) + (size_t)CAP * 16;
@@ -125,7 +131,7 @@ __device__ __forceinline__ void select_role_fast(const TopoDev& t, const BatchDe
   }
 
   // ---- (b) walk the background order; patched nodes are skipped by a table probe
-  const int slab_len = t.slab_hi - t.slab_lo;
+  const int slab_len = T.sel_hi - T.sel_lo;
   int acc = 0;
   for (int pos = 0; pos < slab_len && acc < K; pos += 32) {
     const int i = pos + lane;
@@ -135,12 +141,12 @@ __device__ __forceinline__ void select_role_fast(const TopoDev& t, const BatchDe
     if (i < slab_len) {
       int node;
       if (need_i > 0) {
-        const unsigned long long ob = t.order[i];
+        const unsigned long long ob = T.sel_order[i];
         node = key_node(ob);
         const float base = __uint_as_float((uint32_t)(ob >> 32) ^ 0x80000000u);  // base >= 0
         key = make_key(need * base, node);
       } else {
-        node = t.slab_lo + i;
+        node = T.sel_lo + i;
         key = make_key(0.0f, node);
       }
       av = t.free_[node];
@@ -196,8 +202,9 @@ __device__ __forceinline__ void build_table(const TopoDev& t, const BatchDev& b,
           nn = m;
           wv = RBGTOPO_SELF_W * c;
         }
-        if (nn >= t.slab_lo && nn < t.slab_hi) {
+        if (nn >= T.sel_lo && nn < T.sel_hi) {
           const int slot = tab_insert(T, nn);
+          const bool mine = correct && nn >= t.slab_lo && nn < t.slab_hi;  // this rank's matrix columns
           if (c) {
             float* rowp = mrow0 + nn;
             for (int p = 0; p < h.P; ++p) {
@@ -206,7 +213,7 @@ __device__ __forceinline__ void build_table(const TopoDev& t, const BatchDev& b,
               if (coef) {
                 const float add = (float)(coef * wv);
                 atomicAdd(&T.delta[(size_t)p * HT + slot], add);
-                if (correct)
+                if (mine)
                   for (int k = 0; k < count; ++k) sel_red_add_f32(rowp + (size_t)k * stride, add);
               }
               rowp += (size_t)count * stride;
@@ -218,7 +225,7 @@ __device__ __forceinline__ void build_table(const TopoDev& t, const BatchDev& b,
     const int* con = b.blob + h.cons_off;
     for (int c = tid; c < h.n_cons; c += nthreads) {
       const int m = con[2 * c], amt = con[2 * c + 1];
-      if (m >= t.slab_lo && m < t.slab_hi) atomicAdd(&T.cons[tab_insert(T, m)], amt);
+      if (m >= T.sel_lo && m < T.sel_hi) atomicAdd(&T.cons[tab_insert(T, m)], amt);
     }
   }
   __syncthreads();
@@ -244,7 +251,7 @@ __device__ __forceinline__ void build_table(const TopoDev& t, const BatchDev& b,
       T.dBase[d] = t.base[node];
       T.dAvail[d] = av;
       T.dDom[d] = dd;
-      if (correct && T.cons[i] > 0) {
+      if (correct && T.cons[i] > 0 && node >= t.slab_lo && node < t.slab_hi) {
         float* rowp = mrow0 + node;
         for (int p = 0; p < h.P; ++p) {
           const int count = b.blob[h.role_off + 4 * p], demand = b.blob[h.role_off + 4 * p + 1];
@@ -279,6 +286,9 @@ k_select_assign_fast(TopoDev t, BatchDev b, int step_begin, int mode, int HT, in
   T.dAvail = reinterpret_cast<int*>(T.dBase + CAP);
   T.dDom = T.dAvail + CAP;
   T.cnt = 0;
+  T.sel_lo = 0;  // replicated selection: all nodes (== the slab when world == 1)
+  T.sel_hi = t.n;
+  T.sel_order = t.order_all;
 
   const int step = step_begin + blockIdx.x;
   const StepHdr h = load_hdr(b, step);
@@ -395,6 +405,9 @@ k_shard_select(TopoDev t, BatchDev b, int step_begin, int pass2, int mode, int H
   T.dAvail = reinterpret_cast<int*>(T.dBase + CAP);
   T.dDom = T.dAvail + CAP;
   T.cnt = 0;
+  T.sel_lo = t.slab_lo;  // all-gather scheme: rank-local lists
+  T.sel_hi = t.slab_hi;
+  T.sel_order = t.order;
   const int step = step_begin + blockIdx.x;
   const StepHdr h = load_hdr(b, step);
   const bool excl_step = (h.flags & RBGTOPO_STEP_EXCLUSIVE) != 0;

@@ -95,6 +95,33 @@ def test_concurrent_callers_share_one_context():
     eng.close()
 
 
+def test_churn_reconcile_matches_oracle():
+    """BASELINE.json configs[4]: continuous reconcile under churn — every step 10 % of the nodes
+    leave (capacity 0) or come back, the snapshot is refreshed asynchronously
+    (rbgtopo_update_nodes) and the whole fleet is re-placed; each step equals the oracle run
+    on that step's snapshot."""
+    from gpu_util import new_engine
+    n = 4000
+    topo = synth.make_topology(n, seed=21, tiers=4)
+    free0 = topo.free.copy()
+    rbgs = _fleet(n, 32, seed=8, gang_every=5)
+    eng = new_engine(topo)
+    mgr = B200TopoPodGroupManager(eng)
+    rng = np.random.default_rng(5)
+    gone = np.zeros(n, dtype=bool)
+    for step in range(4):
+        flip = rng.choice(n, size=n // 10, replace=False)
+        gone[flip] = ~gone[flip]
+        topo.free = np.where(gone, 0, free0).astype(np.int32)
+        eng.update_nodes(topo.free, None, generation=10 + step)
+        got = mgr.reconcile_pod_groups(rbgs)
+        ref = _oracle_manager(topo).reconcile_pod_groups_by_waves(rbgs)
+        for a, c in zip(got, ref):
+            assert a.nodes == c.nodes and a.status == c.status and a.domain == c.domain, step
+        assert not any(gone[v] for p in got for v in p.nodes.values() if v >= 0)   # nobody lands on a removed node
+    eng.close()
+
+
 def test_plan_dense_matrix_and_lists_match_oracle_per_wave():
     """A staged multi-wave plan leaves the same dense matrix rows and top-K lists in HBM as
     the wave-by-wave oracle run (rows: wave-major, groups in order)."""

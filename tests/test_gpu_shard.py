@@ -53,7 +53,21 @@ for n, seed, excl in [(4096, 1, False), (10000, 2, True), (3000, 3, True)]:
         assert np.array_equal(got.view(np.uint32), ref["matrix"][row, lo:hi].view(np.uint32)), (rank, row)
     for rr in range(ref["topk"].shape[0]):
         assert np.array_equal(eng.read_topk(h, rr, 32), ref["topk"][rr]), (rank, rr)
-    eng.release(h); eng.close()
+    eng.release(h)
+    # the same batch with replicated selection: no collective, plain run_staged / score_assign on every rank
+    h = eng.stage(blob)
+    eng.run_staged(h, 1)
+    a2, s2, d2 = eng.fetch(h)
+    assert np.array_equal(a2, ref["assign"]) and np.array_equal(s2, ref["status"]) and np.array_equal(d2, ref["domain"]), (rank, n)
+    for row in range(0, ref["matrix"].shape[0], 5):
+        got = eng.read_scores(h, row)
+        assert np.array_equal(got.view(np.uint32), ref["matrix"][row, lo:hi].view(np.uint32)), (rank, row, "replicated")
+    for rr in range(ref["topk"].shape[0]):
+        assert np.array_equal(eng.read_topk(h, rr, 32), ref["topk"][rr]), (rank, rr, "replicated")
+    eng.release(h)
+    a3, s3, d3 = eng.score_assign(blob)
+    assert np.array_equal(a3, ref["assign"]) and np.array_equal(s3, ref["status"]), (rank, n)
+    eng.close()
 # ---- whole groups through the sharded multi-wave plan (one emit launch per rank, per-wave
 #      select -> all-gather -> merge -> assign, placements chained on every rank)
 from rbg_b200.plugin import B200TopoPodGroupManager
@@ -98,6 +112,12 @@ for n, kw in [(8000, {}), (6000, dict(excl_every=3, gang_every=4)), (5000, dict(
     eng.run_staged(h, 1)
     assign2, status2, domain2 = eng.fetch(h)
     assert np.array_equal(assign2, assign) and np.array_equal(status2, status) and np.array_equal(domain2, domain), (rank, n)
+    a4, s4, d4 = eng.place_groups(gblob)     # plan + exact host loop for partially placed groups
+    off = 0
+    for i, r in enumerate(ref):
+        want = list(r.nodes.values())
+        assert a4[off:off + len(want)].tolist() == want and s4[i] == r.status and d4[i] == r.domain, (rank, n, i)
+        off += len(want)
     if not kw:      # nobody fails in this fleet: the plan's rows line up with the wave-by-wave oracle run
         from oracle import placer as oracle_placer
         from rbg_b200.blob import BlobBuilder
