@@ -115,6 +115,7 @@ struct BatchMeta {
   int max_cap = 0;           // largest per-step capacity (sizes the shared-memory hash table)
   std::vector<int> poff;     // [n_steps + 1] patch-list offsets
   std::vector<int> cta_item; // [emit_grid + 1] byte-balanced item ranges of k_score_emit
+  int emit_grid = 1;         // persistent CTAs the ranges were cut for
 };
 
 struct Batch {
@@ -156,7 +157,8 @@ struct rbgtopo_ctx {
   rbgtopo_config cfg{};
   int sm_count = 148;
   int slab_lo = 0, slab_hi = 0, slab_stride = 0, lc = 1, chunk = 2048;
-  int emit_grid = 148;  // persistent CTAs of k_score_emit (SMs x occupancy)
+  int emit_grid = 148;     // persistent CTAs of k_score_emit<true> (SMs x occupancy): step batches
+  int emit_grid_bg = 148;  // ... of k_score_emit<false> (background only): multi-wave plans
   std::shared_mutex topo_mu;  // update = exclusive, score calls = shared
   std::mutex pool_mu;
   Topology topo;
@@ -298,8 +300,9 @@ int run_base(rbgtopo_ctx* c, cudaStream_t s, bool sync) {
 // Byte-balanced work split of k_score_emit: an item (step, chunk) weighs R_step rows.
 // rows(s, &first_row, &R) describes step s.
 template <class F>
-void balance_emit_items(const rbgtopo_ctx* c, BatchMeta* m, int ns, long long racc, F&& rows) {
-  const int G = std::max(1, c->emit_grid), lc = c->lc;
+void balance_emit_items(const rbgtopo_ctx* c, BatchMeta* m, int ns, long long racc, int grid, F&& rows) {
+  const int G = std::max(1, grid), lc = c->lc;
+  m->emit_grid = G;
   const long long total_w = racc * lc;
   m->cta_item.assign((size_t)G + 1, ns * lc);
   int s = 0, rep0 = 0, R = 1;
@@ -319,7 +322,8 @@ void balance_emit_items(const rbgtopo_ctx* c, BatchMeta* m, int ns, long long ra
   m->cta_item[0] = 0;
 }
 
-int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, BatchMeta* m, bool trusted = false) {
+int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, BatchMeta* m, bool trusted = false,
+                  bool plan = false) {
   const Topology& T = c->topo;
   if (!blob || words < RBGTOPO_HDR_WORDS) return fail(RBGTOPO_EINVAL, "blob too short");
   if (blob[0] != RBGTOPO_BLOB_MAGIC) return fail(RBGTOPO_EINVAL, "bad blob magic");
@@ -412,7 +416,7 @@ int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, Batc
     if ((st[1] & RBGTOPO_STEP_EXCLUSIVE) && st[2] < 0) m->any_excl_unknown = true;
   }
   if (blob[4] != racc || blob[5] != pacc) return fail(RBGTOPO_EINVAL, "blob totals mismatch");
-  balance_emit_items(c, m, ns, racc, [&](int s, int* rep0, int* R) {
+  balance_emit_items(c, m, ns, racc, plan ? c->emit_grid_bg : c->emit_grid, [&](int s, int* rep0, int* R) {
     const int32_t* st = blob + RBGTOPO_HDR_WORDS + (int64_t)s * RBGTOPO_STEP_WORDS;
     *rep0 = st[12];
     *R = st[11];
@@ -535,8 +539,10 @@ int launch_score(rbgtopo_ctx* c, Batch* b, cudaStream_t s) {
   const BatchMeta& m = b->m;
   if (m.n_steps == 0) return RBGTOPO_OK;
   const int items = m.n_steps * c->lc;
-  const int grid = c->emit_grid;
-  k_score_emit<<<grid, SCORE_THREADS, 0, s>>>(topo_dev(c), batch_dev(c, b), items);
+  if (b->wave_begin.empty())  // step batch: rows + sparse corrections
+    k_score_emit<true><<<m.emit_grid, SCORE_THREADS, 0, s>>>(topo_dev(c), batch_dev(c, b), items);
+  else                        // multi-wave plan: background rows; corrections come from the selection kernels
+    k_score_emit<false><<<m.emit_grid, SCORE_THREADS, 0, s>>>(topo_dev(c), batch_dev(c, b), items);
   return RBGTOPO_OK;
 }
 
@@ -791,8 +797,10 @@ int32_t rbgtopo_create(const rbgtopo_config* cfg, rbgtopo_ctx** out) {
 #endif
   {
     int occ = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_emit, SCORE_THREADS, 0));
-    c->emit_grid = c->sm_count * std::max(1, std::min(occ, kEmitOcc));  // leave room for the wave kernels
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_emit<true>, SCORE_THREADS, 0));
+    c->emit_grid = c->sm_count * std::max(1, std::min(occ, kEmitOcc));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_emit<false>, SCORE_THREADS, 0));
+    c->emit_grid_bg = c->sm_count * std::max(1, std::min(occ, kEmitOcc));
   }
   *out = c.release();
   return RBGTOPO_OK;
@@ -1357,7 +1365,7 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
   const auto p2 = now();
   const auto p3 = now();
   {
-    const size_t total = (size_t)sec_off[ns] + (size_t)ns + 1 + (size_t)c->emit_grid + 1 + 64;  // + poff + cta_item
+    const size_t total = (size_t)sec_off[ns] + (size_t)ns + 1 + (size_t)c->emit_grid_bg + 1 + 64;  // + poff + cta_item
     CK(b->h_in.reserve(total));  // no clear: pass 2 writes every word of the plan
   }
   b->out_index.resize((size_t)pacc);
@@ -1564,7 +1572,7 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
     for (int w = 0; w < W; ++w) wb[w + 1] = wb[w] + cnt[w];
   }
   // staging layout: GROUPS blob | pad | geometry (8 ints per step) | poff | cta_item
-  const size_t G1 = (size_t)std::max(1, c->emit_grid) + 1;
+  const size_t G1 = (size_t)std::max(1, c->emit_grid_bg) + 1;
   const size_t aux_off = ((size_t)words + 3) & ~(size_t)3;
   const size_t tail_off = aux_off + (size_t)ns * PLAN_AUX_WORDS;
   const size_t tail_words = (size_t)ns + 1 + G1;
@@ -1690,7 +1698,7 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
   }
   const long long plan_words = off;
   m.poff.assign(poff, poff + ns + 1);
-  balance_emit_items(c, &m, ns, racc, [&](int s, int* rep0, int* R) {
+  balance_emit_items(c, &m, ns, racc, c->emit_grid_bg, [&](int s, int* rep0, int* R) {
     const int32_t* a = aux + (size_t)s * PLAN_AUX_WORDS;
     *rep0 = a[4];
     *R = (s + 1 < ns ? a[PLAN_AUX_WORDS + 4] : (int)racc) - a[4];
@@ -1748,7 +1756,7 @@ int verify_plan(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
   int64_t plan_words = 0;
   int rc = build_plan(c, gb, words, &plan_words, &ref);
   if (rc) return rc;
-  rc = validate_blob(c, ref.h_in.p, plan_words, &ref.m, true);
+  rc = validate_blob(c, ref.h_in.p, plan_words, &ref.m, true, true);
   if (rc) return rc;
   if (plan_words != m.words) return fail(RBGTOPO_ECUDA, "verify_plan: %lld plan words, host builder %lld", m.words, (long long)plan_words);
   for (int64_t i = 0; i < plan_words; ++i)

@@ -33,14 +33,19 @@ __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(SCORE_THREADS, 6)
+// SPARSE = false: background rows only (multi-wave plans).  More than 6 resident CTAs per SM
+// do not pay: measured 0.68 of peak at 6 and 7 per SM, 0.65 at 8 (32 registers, small spills).
+#ifndef EMIT_MIN_CTAS_BG
+#define EMIT_MIN_CTAS_BG 6
+#endif
+template <bool SPARSE>
+__global__ void __launch_bounds__(SCORE_THREADS, SPARSE ? 6 : EMIT_MIN_CTAS_BG)
 k_score_emit(TopoDev t, BatchDev b, int items) {
   const int T = b.chunk, lc = b.lc;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int groups = T >> 2;
   const int* __restrict__ blob = b.blob;
   const size_t stride = (size_t)t.slab_stride;
-  const bool background_only = (b.emit_matrix & 2) != 0;  // plans: corrections are applied per wave
 
   // contiguous, byte-balanced item ranges (host: validate_blob): an item weighs the
   // replica rows of its step, so every CTA writes the same number of bytes
@@ -57,7 +62,7 @@ k_score_emit(TopoDev t, BatchDev b, int items) {
       const int rep_off = __ldg(hdr + 12);
       const int gid = h0.x, P = h0.w;
       const bool excl_step = (h0.y & RBGTOPO_STEP_EXCLUSIVE) != 0;
-      const bool sparse = (h1.w | h2.y) != 0 && !background_only;
+      const bool sparse = SPARSE && (h1.w | h2.y) != 0;
       const int4* __restrict__ roles = reinterpret_cast<const int4*>(blob + h1.x);  // 16-byte aligned (validated)
       const int n0 = t.slab_lo + ch * T;
       const int n1 = min(n0 + T, t.slab_hi);
