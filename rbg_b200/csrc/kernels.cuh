@@ -58,11 +58,11 @@ struct BatchDev {
   int lc;           // chunks per step on this rank (work items of k_score_emit)
   int chunk;        // nodes per chunk (multiple of 128)
   int parts;        // ranks (list parts to merge)
+  int bsteps;       // steps per block of k_score_emit's work order (score.cuh)
   int emit_matrix;
   float* matrix;              // [total R][slab_stride]
   int* cand;                  // per-step scratch: patched slab nodes (select.cuh)
   const int* poff;            // [n_steps + 1] scratch offsets (host prefix of the caps)
-  const int* cta_item;        // [grid + 1] byte-balanced (step, chunk) item ranges of k_score_emit
   unsigned long long* lists;  // [rolerows][KS] rank-local top-K per role row
   const unsigned long long* lists_all;  // [parts][rolerows][KS]
   long long part_stride;                // u64 elements between parts

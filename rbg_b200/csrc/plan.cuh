@@ -8,7 +8,7 @@
 // Staging buffer (device copy of what the host wrote into pinned memory):
 //   [0, gwords)               GROUPS blob exactly as the caller passed it (include/rbgtopo.h)
 //   [aux_off, +8*ns)          per step: group, wave, sec_off, sec_end, rep_off, row_off, next_step, i0
-//   [tail_off, +tail_words)   poff[ns + 1] | cta_item[grid + 1], copied behind the plan
+//   [tail_off, +tail_words)   poff[ns + 1], copied behind the plan
 //
 // The wave rule is the one of plugin.py / place_groups_slow (a wave = the next
 // <= 32 replicas of <= 8 roles of one dependency level); it is replayed per step

@@ -114,8 +114,6 @@ struct BatchMeta {
   long long patch_cap = 0;   // sum of the per-step patch-list capacities
   int max_cap = 0;           // largest per-step capacity (sizes the shared-memory hash table)
   std::vector<int> poff;     // [n_steps + 1] patch-list offsets
-  std::vector<int> cta_item; // [emit_grid + 1] byte-balanced item ranges of k_score_emit
-  int emit_grid = 1;         // persistent CTAs the ranges were cut for
 };
 
 struct Batch {
@@ -138,7 +136,7 @@ struct Batch {
   std::vector<int> out_index;    // plan replica -> position in the group-order assign array (host-built plans)
   std::vector<int> step_group;   // plan step -> group
   std::vector<int> step_row;     // [n_steps + 1] role-row prefix
-  // device-expanded plans: the staging buffer (GROUPS blob | per-step geometry | poff | cta_item)
+  // device-expanded plans: the staging buffer (GROUPS blob | per-step geometry | poff)
   DevBuf<int> gsrc;
   long long aux_off = -1;        // word offset of the per-step geometry in h_in; -1: host-built plan
   std::vector<int> grp_flags, grp_assign_off, grp_pending;
@@ -157,8 +155,6 @@ struct rbgtopo_ctx {
   rbgtopo_config cfg{};
   int sm_count = 148;
   int slab_lo = 0, slab_hi = 0, slab_stride = 0, lc = 1, chunk = 2048;
-  int emit_grid = 148;     // persistent CTAs of k_score_emit<true> (SMs x occupancy): step batches
-  int emit_grid_bg = 148;  // ... of k_score_emit<false> (background only): multi-wave plans
   std::shared_mutex topo_mu;  // update = exclusive, score calls = shared
   std::mutex pool_mu;
   Topology topo;
@@ -184,9 +180,10 @@ constexpr size_t kFastSmemMax = 200 * 1024;
 // stream concurrently with k_score_emit.  Measured no gain (the latency-bound wave kernels
 // slow down behind the saturated memory system), so the serial pipeline is the default.
 const bool kPerWavePlan = getenv("RBGTOPO_PER_WAVE_PLAN") != nullptr;  // one launch per wave instead of k_plan_group
+const int kEmitBlockSteps = getenv("RBGTOPO_EMIT_BLOCK") ? std::max(1, atoi(getenv("RBGTOPO_EMIT_BLOCK"))) : 4;
 const bool kVerifyPlan = getenv("RBGTOPO_VERIFY_PLAN") != nullptr;  // self-check: device-expanded plan == host-built plan
 const int kHostThreads = getenv("RBGTOPO_HOST_THREADS") ? std::max(1, atoi(getenv("RBGTOPO_HOST_THREADS"))) : 4;
-const int kEmitOcc = getenv("RBGTOPO_EMIT_OCC") ? atoi(getenv("RBGTOPO_EMIT_OCC")) : 6;  // opt-in dynamic smem of k_select_assign_fast
+  // opt-in dynamic smem of k_select_assign_fast
 
 void compute_slab(rbgtopo_ctx* c, int n) {
   const int W = c->cfg.world, r = c->cfg.rank;
@@ -297,33 +294,13 @@ int run_base(rbgtopo_ctx* c, cudaStream_t s, bool sync) {
 // ---- blob validation (host, O(words)) ----------------------------------------
 // `trusted`: the blob was built by build_plan from an already validated GROUPS blob — the
 // per-record range checks are skipped, the derived metadata and the exactness bound are not.
-// Byte-balanced work split of k_score_emit: an item (step, chunk) weighs R_step rows.
-// rows(s, &first_row, &R) describes step s.
-template <class F>
-void balance_emit_items(const rbgtopo_ctx* c, BatchMeta* m, int ns, long long racc, int grid, F&& rows) {
-  const int G = std::max(1, grid), lc = c->lc;
-  m->emit_grid = G;
-  const long long total_w = racc * lc;
-  m->cta_item.assign((size_t)G + 1, ns * lc);
-  int s = 0, rep0 = 0, R = 1;
-  for (int g = 0; g < G; ++g) {
-    const long long target = total_w * g / G;
-    while (s < ns) {  // advance to the step containing `target`
-      rows(s, &rep0, &R);
-      if ((long long)(rep0 + R) * lc > target) break;
-      ++s;
-    }
-    if (s >= ns) break;
-    const long long before = (long long)rep0 * lc;
-    int ch = (int)((target - before + R - 1) / R);  // first chunk at or past the target
-    if (target <= before) ch = 0;
-    m->cta_item[g] = s * lc + std::min(ch, lc);
-  }
-  m->cta_item[0] = 0;
+// Work items of k_score_emit (score.cuh): idx = (block * lc + chunk) * bsteps + step_in_block;
+// one CTA per (block, chunk) segment, scheduled by the hardware.
+inline long long emit_items(int ns, int lc) {
+  return (long long)((ns + kEmitBlockSteps - 1) / kEmitBlockSteps) * lc * kEmitBlockSteps;
 }
 
-int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, BatchMeta* m, bool trusted = false,
-                  bool plan = false) {
+int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, BatchMeta* m, bool trusted = false) {
   const Topology& T = c->topo;
   if (!blob || words < RBGTOPO_HDR_WORDS) return fail(RBGTOPO_EINVAL, "blob too short");
   if (blob[0] != RBGTOPO_BLOB_MAGIC) return fail(RBGTOPO_EINVAL, "bad blob magic");
@@ -416,11 +393,7 @@ int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, Batc
     if ((st[1] & RBGTOPO_STEP_EXCLUSIVE) && st[2] < 0) m->any_excl_unknown = true;
   }
   if (blob[4] != racc || blob[5] != pacc) return fail(RBGTOPO_EINVAL, "blob totals mismatch");
-  balance_emit_items(c, m, ns, racc, plan ? c->emit_grid_bg : c->emit_grid, [&](int s, int* rep0, int* R) {
-    const int32_t* st = blob + RBGTOPO_HDR_WORDS + (int64_t)s * RBGTOPO_STEP_WORDS;
-    *rep0 = st[12];
-    *R = st[11];
-  });
+  if (emit_items(ns, c->lc) > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "steps x chunks exceed 2^31 work items");
   m->n_steps = ns;
   m->total_r = (int)racc;
   m->total_p = (int)pacc;
@@ -484,7 +457,7 @@ int stage_into(rbgtopo_ctx* c, Batch* b, const int32_t* blob, int64_t words) {
   if (rc) return rc;
   const BatchMeta& m = b->m;
   cudaStream_t s = stream_of(c, b);
-  const size_t in_words = (size_t)words + (size_t)m.n_steps + 1 + m.cta_item.size();  // blob | poff | cta_item
+  const size_t in_words = (size_t)words + (size_t)m.n_steps + 1;  // blob | poff
   CK(b->blob.reserve(in_words));
   if (in_place) {
     if (b->h_in.cap < in_words) return fail(RBGTOPO_EINVAL, "internal: in-place plan without tail room");
@@ -498,7 +471,6 @@ int stage_into(rbgtopo_ctx* c, Batch* b, const int32_t* blob, int64_t words) {
   CK(cudaEventRecord(b->ev[0], s));
   if (!in_place) memcpy(b->h_in.p, blob, (size_t)words * 4);
   memcpy(b->h_in.p + words, m.poff.data(), ((size_t)m.n_steps + 1) * 4);
-  memcpy(b->h_in.p + words + m.n_steps + 1, m.cta_item.data(), m.cta_item.size() * 4);
   CK(cudaMemcpyAsync(b->blob.p, b->h_in.p, in_words * 4, cudaMemcpyHostToDevice, s));
   CK(cudaEventRecord(b->ev[1], s));
   b->staged = true;
@@ -520,7 +492,7 @@ BatchDev batch_dev(rbgtopo_ctx* c, Batch* b) {
   d.matrix = b->matrix.p;
   d.cand = b->cand.p;
   d.poff = b->blob.p + b->m.words;
-  d.cta_item = d.poff + b->m.n_steps + 1;
+  d.bsteps = kEmitBlockSteps;
   d.lists = b->lists.p;
   d.lists_all = b->lists.p;
   d.part_stride = 0;
@@ -538,11 +510,12 @@ BatchDev batch_dev(rbgtopo_ctx* c, Batch* b) {
 int launch_score(rbgtopo_ctx* c, Batch* b, cudaStream_t s) {
   const BatchMeta& m = b->m;
   if (m.n_steps == 0) return RBGTOPO_OK;
-  const int items = m.n_steps * c->lc;
+  const int items = (int)emit_items(m.n_steps, c->lc);
+  const int grid = items / kEmitBlockSteps;  // one CTA per (block of steps, chunk of nodes)
   if (b->wave_begin.empty())  // step batch: rows + sparse corrections
-    k_score_emit<true><<<m.emit_grid, SCORE_THREADS, 0, s>>>(topo_dev(c), batch_dev(c, b), items);
+    k_score_emit<true><<<grid, SCORE_THREADS, 0, s>>>(topo_dev(c), batch_dev(c, b), items);
   else                        // multi-wave plan: background rows; corrections come from the selection kernels
-    k_score_emit<false><<<m.emit_grid, SCORE_THREADS, 0, s>>>(topo_dev(c), batch_dev(c, b), items);
+    k_score_emit<false><<<grid, SCORE_THREADS, 0, s>>>(topo_dev(c), batch_dev(c, b), items);
   return RBGTOPO_OK;
 }
 
@@ -795,13 +768,6 @@ int32_t rbgtopo_create(const rbgtopo_config* cfg, rbgtopo_ctx** out) {
     CK(cudaMemcpyToSymbol(g_dbg_skip, &skip, sizeof skip));
   }
 #endif
-  {
-    int occ = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_emit<true>, SCORE_THREADS, 0));
-    c->emit_grid = c->sm_count * std::max(1, std::min(occ, kEmitOcc));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_emit<false>, SCORE_THREADS, 0));
-    c->emit_grid_bg = c->sm_count * std::max(1, std::min(occ, kEmitOcc));
-  }
   *out = c.release();
   return RBGTOPO_OK;
 }
@@ -1365,7 +1331,7 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
   const auto p2 = now();
   const auto p3 = now();
   {
-    const size_t total = (size_t)sec_off[ns] + (size_t)ns + 1 + (size_t)c->emit_grid_bg + 1 + 64;  // + poff + cta_item
+    const size_t total = (size_t)sec_off[ns] + (size_t)ns + 1 + 64;  // + poff
     CK(b->h_in.reserve(total));  // no clear: pass 2 writes every word of the plan
   }
   b->out_index.resize((size_t)pacc);
@@ -1571,11 +1537,10 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
     wb[0] = 0;
     for (int w = 0; w < W; ++w) wb[w + 1] = wb[w] + cnt[w];
   }
-  // staging layout: GROUPS blob | pad | geometry (8 ints per step) | poff | cta_item
-  const size_t G1 = (size_t)std::max(1, c->emit_grid_bg) + 1;
+  // staging layout: GROUPS blob | pad | geometry (8 ints per step) | poff
   const size_t aux_off = ((size_t)words + 3) & ~(size_t)3;
   const size_t tail_off = aux_off + (size_t)ns * PLAN_AUX_WORDS;
-  const size_t tail_words = (size_t)ns + 1 + G1;
+  const size_t tail_words = (size_t)ns + 1;
   const size_t src_words = tail_off + tail_words;
   if (src_words > 0x7FFFFFF0ULL) return fail(RBGTOPO_ELIMIT, "plan staging exceeds 2^31 words");
   CK(b->h_in.reserve(src_words));
@@ -1697,13 +1662,8 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
     b->step_row[ns] = (int)rowacc;
   }
   const long long plan_words = off;
+  if (emit_items(ns, c->lc) > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "steps x chunks exceed 2^31 work items");
   m.poff.assign(poff, poff + ns + 1);
-  balance_emit_items(c, &m, ns, racc, c->emit_grid_bg, [&](int s, int* rep0, int* R) {
-    const int32_t* a = aux + (size_t)s * PLAN_AUX_WORDS;
-    *rep0 = a[4];
-    *R = (s + 1 < ns ? a[PLAN_AUX_WORDS + 4] : (int)racc) - a[4];
-  });
-  memcpy(poff + ns + 1, m.cta_item.data(), G1 * 4);
   const auto p4 = now();
   memcpy(hin, gb, (size_t)words * 4);
   for (size_t i = (size_t)words; i < aux_off; ++i) hin[i] = 0;
@@ -1738,7 +1698,7 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
   b->staged = true;
   b->ran = false;
   if (prof)
-    fprintf(stderr, "[rbgtopo plan] check %ld us, numbering %ld us, sizes %ld us, prefixes+split %ld us, copy %ld us, enqueue %ld us\n",
+    fprintf(stderr, "[rbgtopo plan] check %ld us, numbering %ld us, sizes %ld us, prefixes %ld us, copy %ld us, enqueue %ld us\n",
             us(p0, p1), us(p1, p2), us(p2, p3), us(p3, p4), us(p4, p5), us(p5, now()));
   return RBGTOPO_OK;
 }
@@ -1748,7 +1708,7 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
 int verify_plan(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
   cudaStream_t s = stream_of(c, b);
   const BatchMeta& m = b->m;
-  const size_t dev_words = (size_t)m.words + (size_t)m.n_steps + 1 + m.cta_item.size();
+  const size_t dev_words = (size_t)m.words + (size_t)m.n_steps + 1;
   std::vector<int32_t> got(dev_words);
   CK(cudaStreamSynchronize(s));
   CK(cudaMemcpy(got.data(), b->blob.p, dev_words * 4, cudaMemcpyDeviceToHost));
@@ -1756,18 +1716,15 @@ int verify_plan(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
   int64_t plan_words = 0;
   int rc = build_plan(c, gb, words, &plan_words, &ref);
   if (rc) return rc;
-  rc = validate_blob(c, ref.h_in.p, plan_words, &ref.m, true, true);
+  rc = validate_blob(c, ref.h_in.p, plan_words, &ref.m, true);
   if (rc) return rc;
   if (plan_words != m.words) return fail(RBGTOPO_ECUDA, "verify_plan: %lld plan words, host builder %lld", m.words, (long long)plan_words);
   for (int64_t i = 0; i < plan_words; ++i)
     if (got[i] != ref.h_in.p[i])
       return fail(RBGTOPO_ECUDA, "verify_plan: word %lld differs: device %d, host %d", (long long)i, got[i], ref.h_in.p[i]);
-  if (ref.m.poff != m.poff || ref.m.cta_item != m.cta_item)
-    return fail(RBGTOPO_ECUDA, "verify_plan: poff / cta_item differ");
+  if (ref.m.poff != m.poff) return fail(RBGTOPO_ECUDA, "verify_plan: poff differs");
   for (size_t i = 0; i < m.poff.size(); ++i)
     if (got[plan_words + i] != m.poff[i]) return fail(RBGTOPO_ECUDA, "verify_plan: device poff[%zu]", i);
-  for (size_t i = 0; i < m.cta_item.size(); ++i)
-    if (got[plan_words + m.poff.size() + i] != m.cta_item[i]) return fail(RBGTOPO_ECUDA, "verify_plan: device cta_item[%zu]", i);
   if (ref.m.n_steps != m.n_steps || ref.m.total_r != m.total_r || ref.m.total_p != m.total_p || ref.m.max_p != m.max_p ||
       ref.m.max_k != m.max_k || ref.m.max_q != m.max_q || ref.m.patch_cap != m.patch_cap || ref.m.max_cap != m.max_cap ||
       ref.m.any_excl_unknown != m.any_excl_unknown || ref.m.scores != m.scores || ref.m.algo_bytes != m.algo_bytes)

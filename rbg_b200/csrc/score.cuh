@@ -1,18 +1,18 @@
 // score.cuh — k_score_emit: the dominant kernel of the path.
 //
 // Emits the dense (replica x node) score matrix as a pure HBM write stream.
-// One work item = (step, chunk of `chunk` <= 2048 nodes of this rank's slab).  A
-// persistent grid (SMs x 6 CTAs of 256 threads, 40 registers, no shared memory)
-// takes contiguous item ranges that the host balanced by BYTES (an item weighs the
-// replica rows of its step: cta_item[], rbgtopo.cu balance_emit_items), so the
-// chunks of a step run back to back on one SM (header / role records are L1 hits
-// after the first chunk) and every CTA writes the same amount.
+// One CTA (256 threads, no shared memory) = one SEGMENT: a chunk of <= 2048 nodes
+// of this rank's slab x a block of `bsteps` consecutive steps.  A thread loads the
+// per-node operands of its two float4 groups (base, free: step independent) once
+// and then only the per-step part repeats: header, role records, 12 ALU ops and
+// the 128-bit streaming stores (st.global.cs.v4) per role.  The grid is simply
+// all segments: the hardware scheduler balances them (a persistent grid with
+// statically byte-balanced ranges was 18 % slower: the slowest SM sets the time).
 //   1. background: every role row is  S = need*base[n]  where the node is feasible
 //      (free >= demand, and for exclusive roles the domain is unowned or ours),
-//      else -inf; written once per replica of the role with 128-bit streaming
-//      stores (st.global.cs.v4).  base/free are per-snapshot vectors shared by all
-//      steps (L1/L2).  Multi-wave plans stop here: their sparse corrections are
-//      applied by the kernel that knows the placements (plan_group.cuh).
+//      else -inf; written once per replica of the role.  Multi-wave plans stop
+//      here (SPARSE = false): their sparse corrections are applied by the kernel
+//      that knows the placements (plan_group.cuh).
 //   2. step-level batches with anchor pods / consumed capacity: pair*c*w is added
 //      onto the just-written, L2-hot scores with fire-and-forget
 //      red.global.add.f32 (+ the self term); nodes whose consumed capacity makes
@@ -33,11 +33,16 @@ __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
-// SPARSE = false: background rows only (multi-wave plans).  More than 6 resident CTAs per SM
-// do not pay: measured 0.68 of peak at 6 and 7 per SM, 0.65 at 8 (32 registers, small spills).
+// Why the loop nest is (chunk outer, steps inner): with one (step, chunk) item per iteration a
+// single-replica step cost ~117 instructions per 512-byte warp store (SASS count: node operands,
+// tail fix-up and header decode per store); here they are amortised over the block's steps.
+//
+// SPARSE = false: background rows only (multi-wave plans).  Register cap: 6 CTAs/SM (40 registers,
+// 36 bytes of spills) measured best — 0.845 of peak vs 0.826 at 5/SM (no spills), 0.79 at 4 or 8.
 #ifndef EMIT_MIN_CTAS_BG
 #define EMIT_MIN_CTAS_BG 6
 #endif
+
 template <bool SPARSE>
 __global__ void __launch_bounds__(SCORE_THREADS, SPARSE ? 6 : EMIT_MIN_CTAS_BG)
 k_score_emit(TopoDev t, BatchDev b, int items) {
@@ -46,63 +51,72 @@ k_score_emit(TopoDev t, BatchDev b, int items) {
   const int groups = T >> 2;
   const int* __restrict__ blob = b.blob;
   const size_t stride = (size_t)t.slab_stride;
+  (void)lane; (void)warp;
 
-  // contiguous, byte-balanced item ranges (host: validate_blob): an item weighs the
-  // replica rows of its step, so every CTA writes the same number of bytes
-  const int item0 = __ldg(b.cta_item + blockIdx.x);
-  const int item_end = min(items, __ldg(b.cta_item + blockIdx.x + 1));
-  if (item0 >= item_end) return;
-  int step = item0 / lc, ch = item0 - step * lc;
-  for (int item = item0; item < item_end; ++item) {
-    {
+  // segment = blockIdx.x = block * lc + chunk;  `items` = segments * bsteps (host: emit_items)
+  const int BS = b.bsteps;
+  const int seg = blockIdx.x;
+  const int blk = seg / lc, ch = seg - blk * lc;
+  if ((seg + 1) * BS > items) return;
+  {
+    // ---- node operands of this thread's groups
+    const int n0 = t.slab_lo + ch * T;
+    const int n1 = min(n0 + T, t.slab_hi);
+    float4 base4[GPT];
+    int4 av[GPT];
+    bool live[GPT];
+#pragma unroll
+    for (int j = 0; j < GPT; ++j) {
+      const int g = tid + j * SCORE_THREADS;
+      const int n = n0 + (g << 2);
+      live[j] = g < groups && n < n1;
+      if (live[j]) {
+        base4[j] = __ldg(reinterpret_cast<const float4*>(t.base + n));
+        av[j] = __ldg(reinterpret_cast<const int4*>(t.free_ + n));  // padded past n: safe
+        if (n + 4 > n1) {  // only in the slab's last group: lanes past the slab are infeasible
+          if (n + 1 >= n1) av[j].y = -1;
+          if (n + 2 >= n1) av[j].z = -1;
+          av[j].w = -1;
+        }
+      }
+    }
+    const int step_end = min(b.n_steps, (blk + 1) * BS);  // the last block may be short
+    for (int step = blk * BS; step < step_end; ++step) {
       const int* __restrict__ hdr = blob + RBGTOPO_HDR_WORDS + (size_t)step * RBGTOPO_STEP_WORDS;
       const int4 h0 = __ldg(reinterpret_cast<const int4*>(hdr));      // gid flags fixed P
-      const int4 h1 = __ldg(reinterpret_cast<const int4*>(hdr) + 1);  // role_off Q pair_off n_anchors
-      const int4 h2 = __ldg(reinterpret_cast<const int4*>(hdr) + 2);  // anchor_off n_cons cons_off R
+      const int role_off = __ldg(hdr + 4);
       const int rep_off = __ldg(hdr + 12);
       const int gid = h0.x, P = h0.w;
       const bool excl_step = (h0.y & RBGTOPO_STEP_EXCLUSIVE) != 0;
-      const bool sparse = SPARSE && (h1.w | h2.y) != 0;
-      const int4* __restrict__ roles = reinterpret_cast<const int4*>(blob + h1.x);  // 16-byte aligned (validated)
-      const int n0 = t.slab_lo + ch * T;
-      const int n1 = min(n0 + T, t.slab_hi);
+      const int4* __restrict__ roles = reinterpret_cast<const int4*>(blob + role_off);  // 16-byte aligned (validated)
       float* const mrow0 = b.matrix + (size_t)rep_off * stride + (n0 - t.slab_lo);
 
       // ---- 1. background rows
 #pragma unroll
       for (int j = 0; j < GPT; ++j) {
+        if (!live[j]) continue;
         const int g = tid + j * SCORE_THREADS;
-        const int n = n0 + (g << 2);
-        if (g < groups && n < n1) {
-          const float4 base4 = __ldg(reinterpret_cast<const float4*>(t.base + n));
-          int4 av = __ldg(reinterpret_cast<const int4*>(t.free_ + n));  // padded past n: safe
-          if (n + 4 > n1) {  // only in the slab's last group: lanes past the slab are infeasible
-            if (n + 1 >= n1) av.y = -1;
-            if (n + 2 >= n1) av.z = -1;
-            av.w = -1;
-          }
-          int4 avx = av;  // capacity as seen by exclusive roles: blocked domains are infeasible
-          if (excl_step) {
-            const int4 ow = __ldg(reinterpret_cast<const int4*>(t.node_owner + n));
-            if (!(ow.x == -1 || ow.x == gid)) avx.x = -1;
-            if (!(ow.y == -1 || ow.y == gid)) avx.y = -1;
-            if (!(ow.z == -1 || ow.z == gid)) avx.z = -1;
-            if (!(ow.w == -1 || ow.w == gid)) avx.w = -1;
-          }
-          float* rowp = mrow0 + (g << 2);
-          for (int p = 0; p < P; ++p) {
-            const int4 role = __ldg(roles + p);  // count demand need flags
-            const float need = (float)role.z;
-            const int4 a = (role.w & RBGTOPO_ROLE_EXCLUSIVE) ? avx : av;
-            float4 o4;
-            o4.x = a.x >= role.y ? need * base4.x : -INFINITY;
-            o4.y = a.y >= role.y ? need * base4.y : -INFINITY;
-            o4.z = a.z >= role.y ? need * base4.z : -INFINITY;
-            o4.w = a.w >= role.y ? need * base4.w : -INFINITY;
-            for (int c = 0; c < role.x; ++c) {
-              st_stream_f4(rowp, o4);
-              rowp += stride;
-            }
+        int4 avx = av[j];  // capacity as seen by exclusive roles: blocked domains are infeasible
+        if (excl_step) {
+          const int4 ow = __ldg(reinterpret_cast<const int4*>(t.node_owner + n0 + (g << 2)));
+          if (!(ow.x == -1 || ow.x == gid)) avx.x = -1;
+          if (!(ow.y == -1 || ow.y == gid)) avx.y = -1;
+          if (!(ow.z == -1 || ow.z == gid)) avx.z = -1;
+          if (!(ow.w == -1 || ow.w == gid)) avx.w = -1;
+        }
+        float* rowp = mrow0 + (g << 2);
+        for (int p = 0; p < P; ++p) {
+          const int4 role = __ldg(roles + p);  // count demand need flags
+          const float need = (float)role.z;
+          const int4 a = (role.w & RBGTOPO_ROLE_EXCLUSIVE) ? avx : av[j];
+          float4 o4;
+          o4.x = a.x >= role.y ? need * base4[j].x : -INFINITY;
+          o4.y = a.y >= role.y ? need * base4[j].y : -INFINITY;
+          o4.z = a.z >= role.y ? need * base4[j].z : -INFINITY;
+          o4.w = a.w >= role.y ? need * base4[j].w : -INFINITY;
+          for (int c = 0; c < role.x; ++c) {
+            st_stream_f4(rowp, o4);
+            rowp += stride;
           }
         }
       }
@@ -110,6 +124,12 @@ k_score_emit(TopoDev t, BatchDev b, int items) {
       // ---- 2. sparse corrections.  Few records: every warp scans them all and
       // applies the ones inside its own segments (ordering by __syncwarp alone).
       // Many records: one block barrier, then the records are spread over warps.
+      int4 h1 = make_int4(0, 0, 0, 0), h2 = make_int4(0, 0, 0, 0);
+      if (SPARSE) {
+        h1 = __ldg(reinterpret_cast<const int4*>(hdr) + 1);  // role_off Q pair_off n_anchors
+        h2 = __ldg(reinterpret_cast<const int4*>(hdr) + 2);  // anchor_off n_cons cons_off R
+      }
+      const bool sparse = SPARSE && (h1.w | h2.y) != 0;
       if (sparse) {
         const bool own = (h1.w + h2.y) <= 2;
         if (own) __syncwarp(); else __syncthreads();  // background stores precede the reductions
@@ -161,10 +181,6 @@ k_score_emit(TopoDev t, BatchDev b, int items) {
           }
         }
       }
-    }
-    if (++ch == lc) {
-      ch = 0;
-      ++step;
     }
   }
 }
