@@ -95,6 +95,24 @@ def test_concurrent_callers_share_one_context():
     eng.close()
 
 
+def test_degenerate_fleets():
+    """No groups, groups with nothing pending, a single one-replica group: the plan machinery
+    (device expansion, zero-sized launches) must cope."""
+    from gpu_util import new_engine
+    topo = synth.make_topology(700, seed=4, tiers=3)
+    eng = new_engine(topo)
+    mgr = B200TopoPodGroupManager(eng)
+    assert mgr.reconcile_pod_groups([]) == []
+    idle = RoleBasedGroup("default", "idle", [RoleSpec("a", 0, (), 1), RoleSpec("b", 0, ("a",), 1)], gid=0)
+    one = RoleBasedGroup("default", "one", [RoleSpec("a", 1, (), 1)], gid=1)
+    for fleet in ([idle], [idle, one, idle], [one]):
+        got = mgr.reconcile_pod_groups(fleet)
+        ref = _oracle_manager(topo).reconcile_pod_groups_by_waves(fleet)
+        for a, c in zip(got, ref):
+            assert a.nodes == c.nodes and a.status == c.status and a.domain == c.domain
+    eng.close()
+
+
 def test_churn_reconcile_matches_oracle():
     """BASELINE.json configs[4]: continuous reconcile under churn — every step 10 % of the nodes
     leave (capacity 0) or come back, the snapshot is refreshed asynchronously
