@@ -180,7 +180,8 @@ constexpr size_t kFastSmemMax = 200 * 1024;
 // stream concurrently with k_score_emit.  Measured no gain (the latency-bound wave kernels
 // slow down behind the saturated memory system), so the serial pipeline is the default.
 const bool kPerWavePlan = getenv("RBGTOPO_PER_WAVE_PLAN") != nullptr;  // one launch per wave instead of k_plan_group
-const int kEmitBlockSteps = getenv("RBGTOPO_EMIT_BLOCK") ? std::max(1, atoi(getenv("RBGTOPO_EMIT_BLOCK"))) : 4;
+const int kEmitBlockSteps =
+    getenv("RBGTOPO_EMIT_BLOCK") ? std::min(EMIT_MAX_BLOCK, std::max(1, atoi(getenv("RBGTOPO_EMIT_BLOCK")))) : 4;
 const bool kVerifyPlan = getenv("RBGTOPO_VERIFY_PLAN") != nullptr;  // self-check: device-expanded plan == host-built plan
 const int kHostThreads = getenv("RBGTOPO_HOST_THREADS") ? std::max(1, atoi(getenv("RBGTOPO_HOST_THREADS"))) : 4;
   // opt-in dynamic smem of k_select_assign_fast

@@ -1,11 +1,12 @@
 // score.cuh — k_score_emit: the dominant kernel of the path.
 //
 // Emits the dense (replica x node) score matrix as a pure HBM write stream.
-// One CTA (256 threads, no shared memory) = one SEGMENT: a chunk of <= 2048 nodes
-// of this rank's slab x a block of `bsteps` consecutive steps.  A thread loads the
-// per-node operands of its two float4 groups (base, free: step independent) once
-// and then only the per-step part repeats: header, role records, 12 ALU ops and
-// the 128-bit streaming stores (st.global.cs.v4) per role.  The grid is simply
+// One CTA (256 threads) = one SEGMENT: a chunk of <= 2048 nodes of this rank's slab
+// x a block of `bsteps` consecutive steps.  The steps' headers and role records
+// are staged in shared memory (two parallel rounds of loads), a thread loads the
+// per-node operands of its two float4 groups (base, free: step independent) once,
+// and then only the per-step part repeats: 12 ALU ops and the 128-bit streaming
+// stores (st.global.cs.v4) per role.  The grid is simply
 // all segments: the hardware scheduler balances them (a persistent grid with
 // statically byte-balanced ranges was 18 % slower: the slowest SM sets the time).
 //   1. background: every role row is  S = need*base[n]  where the node is feasible
@@ -42,6 +43,7 @@ __device__ __forceinline__ void red_add_f32(float* p, float v) {
 #ifndef EMIT_MIN_CTAS_BG
 #define EMIT_MIN_CTAS_BG 6
 #endif
+constexpr int EMIT_MAX_BLOCK = 16;  // upper bound of b.bsteps
 
 template <bool SPARSE>
 __global__ void __launch_bounds__(SCORE_THREADS, SPARSE ? 6 : EMIT_MIN_CTAS_BG)
@@ -58,6 +60,25 @@ k_score_emit(TopoDev t, BatchDev b, int items) {
   const int seg = blockIdx.x;
   const int blk = seg / lc, ch = seg - blk * lc;
   if ((seg + 1) * BS > items) return;
+  const int step0 = blk * BS;
+  const int nst = min(b.n_steps, step0 + BS) - step0;  // the last block may be short
+  // per-step metadata of the segment into shared memory: two parallel rounds of loads instead of a
+  // dependent header -> role chain in front of every step's stores
+  __shared__ int4 sH0[EMIT_MAX_BLOCK];                 // gid flags fixed P
+  __shared__ int sRoleOff[EMIT_MAX_BLOCK], sRepOff[EMIT_MAX_BLOCK];
+  __shared__ int4 sRoles[EMIT_MAX_BLOCK][MAXP];        // count demand need flags
+  if (tid < nst) {
+    const int* __restrict__ hdr = blob + RBGTOPO_HDR_WORDS + (size_t)(step0 + tid) * RBGTOPO_STEP_WORDS;
+    sH0[tid] = __ldg(reinterpret_cast<const int4*>(hdr));
+    sRoleOff[tid] = __ldg(hdr + 4);
+    sRepOff[tid] = __ldg(hdr + 12);
+  }
+  __syncthreads();
+  if (tid < nst * MAXP) {
+    const int s = tid / MAXP, p = tid - s * MAXP;
+    if (p < sH0[s].w) sRoles[s][p] = __ldg(reinterpret_cast<const int4*>(blob + sRoleOff[s]) + p);
+  }
+  __syncthreads();
   {
     // ---- node operands of this thread's groups
     const int n0 = t.slab_lo + ch * T;
@@ -80,16 +101,15 @@ k_score_emit(TopoDev t, BatchDev b, int items) {
         }
       }
     }
-    const int step_end = min(b.n_steps, (blk + 1) * BS);  // the last block may be short
-    for (int step = blk * BS; step < step_end; ++step) {
+    for (int si = 0; si < nst; ++si) {
+      const int step = step0 + si;
       const int* __restrict__ hdr = blob + RBGTOPO_HDR_WORDS + (size_t)step * RBGTOPO_STEP_WORDS;
-      const int4 h0 = __ldg(reinterpret_cast<const int4*>(hdr));      // gid flags fixed P
-      const int role_off = __ldg(hdr + 4);
-      const int rep_off = __ldg(hdr + 12);
+      const int4 h0 = sH0[si];
       const int gid = h0.x, P = h0.w;
       const bool excl_step = (h0.y & RBGTOPO_STEP_EXCLUSIVE) != 0;
-      const int4* __restrict__ roles = reinterpret_cast<const int4*>(blob + role_off);  // 16-byte aligned (validated)
-      float* const mrow0 = b.matrix + (size_t)rep_off * stride + (n0 - t.slab_lo);
+      const int4* roles = sRoles[si];
+      float* const mrow0 = b.matrix + (size_t)sRepOff[si] * stride + (n0 - t.slab_lo);
+      (void)hdr;
 
       // ---- 1. background rows
 #pragma unroll
@@ -106,7 +126,7 @@ k_score_emit(TopoDev t, BatchDev b, int items) {
         }
         float* rowp = mrow0 + (g << 2);
         for (int p = 0; p < P; ++p) {
-          const int4 role = __ldg(roles + p);  // count demand need flags
+          const int4 role = roles[p];  // count demand need flags
           const float need = (float)role.z;
           const int4 a = (role.w & RBGTOPO_ROLE_EXCLUSIVE) ? avx : av[j];
           float4 o4;
@@ -144,7 +164,7 @@ k_score_emit(TopoDev t, BatchDev b, int items) {
             const int avail = __ldg(t.free_ + m) - amt;
             float* rowp = mrow0 + (m - n0);
             for (int p = 0; p < P; ++p) {
-              const int4 role = __ldg(roles + p);
+              const int4 role = roles[p];
               if (avail < role.y)
                 for (int k = 0; k < role.x; ++k) rowp[(size_t)k * stride] = -INFINITY;
               rowp += (size_t)role.x * stride;
