@@ -96,6 +96,8 @@ struct Topology {
   DevBuf<unsigned long long> okeys, order;  // background order of the slab (score.cuh / select.cuh)
   DevBuf<unsigned long long> okeys_all, order_all;  // world > 1: the order over all nodes (plan_group.cuh)
   DevBuf<unsigned char> sort_tmp;
+  cudaGraphExec_t refresh_exec = nullptr;  // captured refresh chain of this topology (run_base)
+  bool refresh_ready = false;              // buffers sized / graph built for the current topology
   std::vector<int> h_degp1;  // deg(n) + 1, for the patch-list capacity of a step
   int max_degp1 = 1;
   DevBuf<int2> tiles;
@@ -182,6 +184,7 @@ constexpr size_t kFastSmemMax = 200 * 1024;
 const bool kPerWavePlan = getenv("RBGTOPO_PER_WAVE_PLAN") != nullptr;  // one launch per wave instead of k_plan_group
 const int kEmitBlockSteps =
     getenv("RBGTOPO_EMIT_BLOCK") ? std::min(EMIT_MAX_BLOCK, std::max(1, atoi(getenv("RBGTOPO_EMIT_BLOCK")))) : 4;
+const bool kRefreshGraph = getenv("RBGTOPO_NO_REFRESH_GRAPH") == nullptr;
 const bool kVerifyPlan = getenv("RBGTOPO_VERIFY_PLAN") != nullptr;  // self-check: device-expanded plan == host-built plan
 const int kHostThreads = getenv("RBGTOPO_HOST_THREADS") ? std::max(1, atoi(getenv("RBGTOPO_HOST_THREADS"))) : 4;
   // opt-in dynamic smem of k_select_assign_fast
@@ -244,40 +247,89 @@ void harvest_base_ms(rbgtopo_ctx* c) {
   }
 }
 
-int run_base(rbgtopo_ctx* c, cudaStream_t s, bool sync) {
+// The snapshot refresh chain (k_prep, k_base, order keys + radix sort[s]): 12-21 launches.
+// prepare_refresh sizes every buffer (allocations are not allowed under stream capture);
+// enqueue_refresh only launches.
+int prepare_refresh(rbgtopo_ctx* c) {
   Topology& T = c->topo;
-  CK(cudaEventRecord(c->ev_base_a, s));
+  const int fmin_bytes = round_up(T.n, 16);
+  const int staged = T.n <= FMIN_SMEM_MAX ? 1 : 0;
+  const size_t smem = (size_t)2 * (BASE_TILE_NNZ + 8) * 4 + (staged ? fmin_bytes : 0);
+  CK(cudaFuncSetAttribute(k_base, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int slab_len = c->slab_hi - c->slab_lo;
+  size_t tmp_bytes = 0, need = 0;
+  if (slab_len > 0) {
+    CK(T.okeys.reserve(slab_len));
+    CK(T.order.reserve(slab_len));
+    CK(cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp_bytes, T.okeys.p, T.order.p, slab_len, 0, 64, nullptr));
+    need = std::max(need, tmp_bytes);
+  }
+  if (c->cfg.world > 1 && T.n > 0) {
+    CK(T.okeys_all.reserve(T.n));
+    CK(T.order_all.reserve(T.n));
+    CK(cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp_bytes, T.okeys_all.p, T.order_all.p, T.n, 0, 64, nullptr));
+    need = std::max(need, tmp_bytes);
+  }
+  CK(T.sort_tmp.reserve(need + 256));
+  return RBGTOPO_OK;
+}
+
+int enqueue_refresh(rbgtopo_ctx* c, cudaStream_t s) {
+  Topology& T = c->topo;
   k_prep<<<(T.n + 255) / 256, 256, 0, s>>>(T.n, T.free_.p, T.domain.p, T.owner.p, T.fmin.p,
                                            T.node_owner.p);
   const int fmin_bytes = round_up(T.n, 16);
   const int staged = T.n <= FMIN_SMEM_MAX ? 1 : 0;
-  size_t smem = (size_t)2 * (BASE_TILE_NNZ + 8) * 4 + (staged ? fmin_bytes : 0);
-  CK(cudaFuncSetAttribute(k_base, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  TopoDev td = topo_dev(c);
+  const size_t smem = (size_t)2 * (BASE_TILE_NNZ + 8) * 4 + (staged ? fmin_bytes : 0);
+  const TopoDev td = topo_dev(c);
   k_base<<<T.n_tiles, BASE_THREADS, smem, s>>>(td, T.tiles.p, staged, fmin_bytes, T.base.p);
   // background order: slab nodes by key(base, node) descending (library radix sort, once per snapshot)
   const int slab_len = c->slab_hi - c->slab_lo;
   if (slab_len > 0) {
-    CK(T.okeys.reserve(slab_len));
-    CK(T.order.reserve(slab_len));
-    td = topo_dev(c);
     k_order_keys<<<(slab_len + 255) / 256, 256, 0, s>>>(td, c->slab_lo, c->slab_hi, T.okeys.p);
-    size_t tmp_bytes = 0;
-    CK(cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp_bytes, T.okeys.p, T.order.p, slab_len, 0, 64, s));
-    CK(T.sort_tmp.reserve(tmp_bytes + 256));
-    tmp_bytes = T.sort_tmp.cap;
+    size_t tmp_bytes = T.sort_tmp.cap;
     CK(cub::DeviceRadixSort::SortKeysDescending(T.sort_tmp.p, tmp_bytes, T.okeys.p, T.order.p, slab_len, 0, 64, s));
   }
   if (c->cfg.world > 1 && T.n > 0) {  // replicated selection (plan_group.cuh) walks the order of ALL nodes
-    CK(T.okeys_all.reserve(T.n));
-    CK(T.order_all.reserve(T.n));
-    td = topo_dev(c);
     k_order_keys<<<(T.n + 255) / 256, 256, 0, s>>>(td, 0, T.n, T.okeys_all.p);
-    size_t tmp_bytes = 0;
-    CK(cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp_bytes, T.okeys_all.p, T.order_all.p, T.n, 0, 64, s));
-    CK(T.sort_tmp.reserve(tmp_bytes + 256));
-    tmp_bytes = T.sort_tmp.cap;
+    size_t tmp_bytes = T.sort_tmp.cap;
     CK(cub::DeviceRadixSort::SortKeysDescending(T.sort_tmp.p, tmp_bytes, T.okeys_all.p, T.order_all.p, T.n, 0, 64, s));
+  }
+  CK(cudaGetLastError());
+  return RBGTOPO_OK;
+}
+
+// Refresh of the per-snapshot vectors on `s`; records base_ms.  The chain is captured once per
+// topology into a CUDA graph and replayed (one launch instead of 12+ from update_nodes);
+// RBGTOPO_NO_REFRESH_GRAPH or a failed capture fall back to the plain launches.
+int run_base(rbgtopo_ctx* c, cudaStream_t s, bool sync) {
+  Topology& T = c->topo;
+  if (!T.refresh_ready) {
+    int rc = prepare_refresh(c);
+    if (rc) return rc;
+    if (T.refresh_exec) {
+      cudaGraphExecDestroy(T.refresh_exec);
+      T.refresh_exec = nullptr;
+    }
+    if (kRefreshGraph && cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      const int erc = enqueue_refresh(c, s);
+      cudaGraph_t g = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(s, &g);
+      if (erc == RBGTOPO_OK && ce == cudaSuccess && g &&
+          cudaGraphInstantiate(&T.refresh_exec, g, 0) != cudaSuccess)
+        T.refresh_exec = nullptr;
+      if (erc != RBGTOPO_OK || ce != cudaSuccess) T.refresh_exec = nullptr;
+      if (g) cudaGraphDestroy(g);
+      (void)cudaGetLastError();
+    }
+    T.refresh_ready = true;
+  }
+  CK(cudaEventRecord(c->ev_base_a, s));
+  if (T.refresh_exec) {
+    CK(cudaGraphLaunch(T.refresh_exec, s));
+  } else {
+    int rc = enqueue_refresh(c, s);
+    if (rc) return rc;
   }
   CK(cudaEventRecord(c->ev_base_b, s));
   CK(cudaEventRecord(c->topo_ready, s));
@@ -777,6 +829,7 @@ int32_t rbgtopo_destroy(rbgtopo_ctx* c) {
   if (!c) return RBGTOPO_OK;
   cudaSetDevice(c->cfg.device);
   cudaDeviceSynchronize();
+  if (c->topo.refresh_exec) cudaGraphExecDestroy(c->topo.refresh_exec);
   if (c->topo_stream) cudaStreamDestroy(c->topo_stream);
   if (c->topo_ready) cudaEventDestroy(c->topo_ready);
   if (c->ev_base_a) cudaEventDestroy(c->ev_base_a);
@@ -881,6 +934,7 @@ int32_t rbgtopo_set_topology(rbgtopo_ctx* c, int32_t n, int64_t e, const int32_t
     T.h_degp1[i] = row_ptr[i + 1] - row_ptr[i] + 1;
     T.max_degp1 = std::max(T.max_degp1, T.h_degp1[i]);
   }
+  T.refresh_ready = false;  // new sizes / pointers: re-capture the refresh chain
   int rc = run_base(c, c->topo_stream, true);
   if (rc) return rc;
   T.valid = true;
