@@ -178,16 +178,13 @@ namespace {
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 constexpr size_t kFastSmemMax = 200 * 1024;
-// Experiment switch (profiles/README.md "two-stream plan"): run the wave kernels on a second
-// stream concurrently with k_score_emit.  Measured no gain (the latency-bound wave kernels
-// slow down behind the saturated memory system), so the serial pipeline is the default.
+// Switches, read once when the library loads.
 const bool kPerWavePlan = getenv("RBGTOPO_PER_WAVE_PLAN") != nullptr;  // one launch per wave instead of k_plan_group
 const int kEmitBlockSteps =
     getenv("RBGTOPO_EMIT_BLOCK") ? std::min(EMIT_MAX_BLOCK, std::max(1, atoi(getenv("RBGTOPO_EMIT_BLOCK")))) : 4;
 const bool kRefreshGraph = getenv("RBGTOPO_NO_REFRESH_GRAPH") == nullptr;
 const bool kVerifyPlan = getenv("RBGTOPO_VERIFY_PLAN") != nullptr;  // self-check: device-expanded plan == host-built plan
 const int kHostThreads = getenv("RBGTOPO_HOST_THREADS") ? std::max(1, atoi(getenv("RBGTOPO_HOST_THREADS"))) : 4;
-  // opt-in dynamic smem of k_select_assign_fast
 
 void compute_slab(rbgtopo_ctx* c, int n) {
   const int W = c->cfg.world, r = c->cfg.rank;
@@ -806,7 +803,7 @@ int32_t rbgtopo_create(const rbgtopo_config* cfg, rbgtopo_ctx** out) {
   CK(cudaSetDevice(cfg->device));
   auto c = std::make_unique<rbgtopo_ctx>();
   c->cfg = *cfg;
-  c->cfg.emit_matrix = 1;  // the dense matrix is always materialised (selection reads patched scores back)
+  c->cfg.emit_matrix = 1;  // the dense matrix is always materialised (it is the product; rbgtopo_read_scores)
   c->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&c->topo_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&c->topo_ready, cudaEventDisableTiming));

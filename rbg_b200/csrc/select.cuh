@@ -1,16 +1,20 @@
-// select.cuh — per-role top-K selection, exclusive-domain handling and the
-// deterministic greedy assignment.
-//
+// select.cuh — step header access, the shared pieces of selection / greedy, and the
+// kernels that work WITHOUT a shared-memory table:
+//   * k_select_assign: fallback of select_fast.cuh when a step's patched set does not
+//     fit a CTA's shared memory — the patched nodes go to a global candidate list and
+//     their exact scores are read back from the dense matrix;
+//   * k_merge / k_greedy (+ chain_step): the all-gather scheme of node-axis sharding
+//      and the per-wave plan fallback: merge of the ranks' lists,
+//     exclusive domain, greedy, and the chaining of placements into the later waves
+//     of a plan through the plan blob.
 // A role row is  need*base[n]  except at the step's few PATCHED nodes (closed
 // neighbourhoods of its anchor pods, nodes with consumed capacity), so its top-K
-// is the merge of
-//   (a) the top-K of the patched nodes, whose exact scores are read back from the
-//       dense matrix (a few dozen 4-byte reads, L2), and
-//   (b) the first K feasible, unpatched nodes of the per-snapshot background
-//       order (slab nodes sorted by key(base[n], n) descending; for need == 0
-//       every background score is 0 and the order is simply node ascending).
-// One warp per role row; ballots pick the accepted lanes in order, REDUX finds
-// the patch maxima.  Steps are independent (snapshot semantics, spec §3.7).
+// is the merge of (a) the top-K of the patched nodes and (b) the first K feasible,
+// unpatched nodes of the per-snapshot background order (slab nodes sorted by
+// key(base[n], n) descending; for need == 0 every background score is 0 and the
+// order is simply node ascending).  One warp per role row; ballots pick the
+// accepted lanes in order, REDUX finds the patch maxima.  Steps are independent
+// (snapshot semantics, spec §3.7).
 #pragma once
 #include "kernels.cuh"
 
