@@ -55,6 +55,27 @@ class RoleSpec:
 
 
 @dataclass
+class ScalingRule:
+    """A CoordinatedPolicyRule with Strategy.Scaling (coordinatedpolicy_types.go:41-45;
+    rolebasedgroup_controller.go:981-994): the roles it paces, MaxSkew and Progression."""
+    roles: Sequence[str]
+    max_skew: str = "100%"
+    progression: str = ""               # "" | "OrderScheduled" | "OrderReady" (scaler.go:141-169)
+
+
+@dataclass
+class RoleStatus:
+    """What CalculateScalingForAllCoordination reads per role: status.roleStatuses[] and the
+    scheduled-pod count of getScheduledReplicas (rolebasedgroup_controller.go:1008-1024, :1057-1080)."""
+    replicas: int = 0
+    ready: int = 0
+    scheduled: int = 0
+
+
+PROGRESSION = {"": 0, None: 0, "OrderScheduled": 1, "OrderReady": 2}
+
+
+@dataclass
 class RoleBasedGroup:
     namespace: str
     name: str
@@ -67,6 +88,10 @@ class RoleBasedGroup:
     current: Dict[str, int] = field(default_factory=dict)    # status.roleStatuses[].replicas
     placed: List[Tuple[str, int]] = field(default_factory=list)  # (role, node) of scheduled pods
     exclusive_domain: int = -1                   # domain the group already occupies, if any
+    # coordination scaling inputs; when `targets` is None and rules exist the targets are computed
+    # here with the reference's own arithmetic (rbgtopo_calculate_target_replicas)
+    scaling_rules: List[ScalingRule] = field(default_factory=list)
+    status: Dict[str, RoleStatus] = field(default_factory=dict)
 
 
 @dataclass
@@ -113,6 +138,30 @@ class HostArith:
             out[level[order[i]]].append(order[i])
         return out
 
+    def parse_percentage(self, s: str) -> float:
+        out = C.c_double()
+        if self.lib.rbgtopo_parse_percentage(s.encode(), C.byref(out)) != 0:
+            raise ValueError(f"invalid maxSkew {s!r}")
+        return out.value
+
+    def scaling_targets(self, rbg: "RoleBasedGroup") -> Optional[Dict[str, int]]:
+        """CalculateScalingForAllCoordination (rolebasedgroup_controller.go:968-1054): one
+        CalculateTargetReplicas per rule with a scaling strategy; a role paced by several rules
+        takes the minimum.  None when the group has no scaling rule."""
+        if not rbg.scaling_rules:
+            return None
+        spec = {r.name: r.replicas for r in rbg.roles}
+        result: Dict[str, int] = {}
+        for rule in rbg.scaling_rules:
+            names = list(rule.roles)
+            st = [rbg.status.get(nm, RoleStatus()) for nm in names]
+            tgt = self.calculate_target_replicas(self.parse_percentage(rule.max_skew), PROGRESSION[rule.progression],
+                                                 [spec.get(nm, 0) for nm in names], [s.replicas for s in st],
+                                                 [s.scheduled for s in st], [s.ready for s in st])
+            for nm, t in zip(names, tgt):
+                result[nm] = min(result[nm], t) if nm in result else t
+        return result
+
     def calculate_target_replicas(self, max_skew: float, progression: int, desired, current, scheduled, ready):
         n = len(desired)
         arr = lambda v: (C.c_int32 * n)(*v)
@@ -153,9 +202,10 @@ class _GroupRun:
         self.role_excl = [r.annotations.get(ROLE_DISABLE_EXCLUSIVE_KEY) != "true" for r in roles]
         # pending replicas: coordination target (or spec) minus current
         self.first_ordinal, self.pending = [], []
+        targets = rbg.targets if rbg.targets is not None else arith.scaling_targets(rbg)
         for r in roles:
-            tgt = r.replicas if rbg.targets is None else rbg.targets.get(r.name, r.replicas)
-            cur = rbg.current.get(r.name, 0)
+            tgt = r.replicas if targets is None else targets.get(r.name, r.replicas)
+            cur = rbg.current.get(r.name, rbg.status[r.name].replicas if r.name in rbg.status else 0)
             self.first_ordinal.append(cur)
             self.pending.append(max(tgt - cur, 0))
         self.unplaced = list(self.pending)
@@ -315,6 +365,49 @@ class B200TopoPodGroupManager:
                 p = Placement(g.status, nodes, g.fixed_domain if g.exclusive else -1, g.scores)
             self._hints[(g.rbg.namespace, g.rbg.name)] = p
             out.append(p)
+        return out
+
+    # -- coordination-aware batching ------------------------
+    def coordination_batches(self, rbg: RoleBasedGroup, max_batches: int = 64) -> List[Dict[str, int]]:
+        """The sequence of scaling targets the controller will go through if every batch it
+        creates gets scheduled and ready: the reference paces a group in MaxSkew-bounded steps
+        (scaler.go:70-172), one step per reconcile.  Returned without touching `rbg`."""
+        st = {r.name: RoleStatus(**vars(rbg.status.get(r.name, RoleStatus()))) for r in rbg.roles}
+        out: List[Dict[str, int]] = []
+        for _ in range(max_batches):
+            probe = RoleBasedGroup(rbg.namespace, rbg.name, rbg.roles, scaling_rules=rbg.scaling_rules, status=st)
+            tgt = self.arith.scaling_targets(probe)
+            if tgt is None or all(tgt.get(nm, s.replicas) <= s.replicas for nm, s in st.items()):
+                break
+            out.append(tgt)
+            for nm, t in tgt.items():
+                st[nm] = RoleStatus(replicas=t, ready=t, scheduled=t)
+        return out
+
+    def reconcile_ahead(self, rbg: RoleBasedGroup, batches: int = 2, by_waves: bool = False) -> List[Placement]:
+        """Place the current coordination batch and pre-place the next `batches - 1` in ONE pass:
+        the group is placed up to the targets of the last of those batches (levels and waves keep
+        the capacity consistent across them), and the result is split by ordinal — replica
+        `ordinal` of a role belongs to the first batch whose target exceeds it — so the hints of
+        the coming batches exist before the controller asks for them."""
+        tg = self.coordination_batches(rbg, batches)
+        if not tg:
+            return []
+        cur = {r.name: rbg.current.get(r.name, rbg.status[r.name].replicas if r.name in rbg.status else 0)
+               for r in rbg.roles}
+        step = RoleBasedGroup(rbg.namespace, rbg.name, rbg.roles, annotations=rbg.annotations, gid=rbg.gid,
+                              policy_rules=rbg.policy_rules, targets=tg[-1], current=cur, placed=rbg.placed,
+                              exclusive_domain=rbg.exclusive_domain)
+        p = (self.reconcile_pod_groups_by_waves if by_waves else self.reconcile_pod_groups)([step])[0]
+        out = [Placement(p.status, {}, p.domain, 0) for _ in tg]
+        names = sorted((r.name for r in rbg.roles), key=len, reverse=True)
+        n_nodes = self.placer.n_nodes
+        for key, node in p.nodes.items():
+            stem, ordinal = key[len(rbg.name) + 1:key.rfind("-")], int(key[key.rfind("-") + 1:])
+            role = next(nm for nm in names if nm == stem)
+            k = next(i for i, t in enumerate(tg) if ordinal < t.get(role, 0))
+            out[k].nodes[key] = node
+            out[k].scores += n_nodes
         return out
 
     # -- InjectPodGroupLabels(rbg, podTemplateSpec) ------------------------------

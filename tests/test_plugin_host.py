@@ -126,3 +126,53 @@ def test_unknown_scheduler_name_is_rejected():
     # NewPodGroupManager, pkg/scheduler/podgroup_manager.go:82-92: unknown name -> error
     with pytest.raises(ValueError):
         new_pod_group_manager("kai", OraclePlacer(synth.make_topology(8, tiers=1)))
+
+
+def test_scaling_rules_compute_the_targets_with_the_reference_arithmetic(golden):
+    """rbg.scaling_rules + rbg.status -> targets exactly as CalculateScalingForAllCoordination
+    (rolebasedgroup_controller.go:968-1054) would: every golden case of scaler_test.go through the
+    plugin mirror, plus the minimum rule for a role paced by two rules."""
+    from rbg_b200.plugin import HostArith, RoleStatus, ScalingRule
+    arith = HostArith()
+    for table in ("calculate_target_replicas", "progression_strategy"):
+        for c in golden[table]["cases"]:
+            if c.get("wantErr"):
+                continue
+            names = sorted(c["states"])
+            rbg = RoleBasedGroup("ns", "g", [RoleSpec(nm, c["states"][nm][0]) for nm in names],
+                                 scaling_rules=[ScalingRule(names, c["maxSkew"], c.get("progression", ""))],
+                                 status={nm: RoleStatus(replicas=c["states"][nm][1], scheduled=c["states"][nm][2],
+                                                        ready=c["states"][nm][3]) for nm in names})
+            assert arith.scaling_targets(rbg) == c["want"], c["name"]
+    rbg = RoleBasedGroup("ns", "g", [RoleSpec("a", 100), RoleSpec("b", 100), RoleSpec("c", 100)],
+                         scaling_rules=[ScalingRule(["a", "b"], "10%"), ScalingRule(["b", "c"], "30%")])
+    t = arith.scaling_targets(rbg)
+    assert t["a"] == t["b"] and t["b"] < t["c"]         # b is paced by the tighter rule
+
+
+def test_coordination_aware_batching_places_the_next_batch_ahead():
+    """the batches the controller will walk through (MaxSkew-bounded steps),
+    the current one placed and the next one pre-placed on top of it."""
+    from rbg_b200.plugin import ScalingRule
+    topo = synth.make_topology(512, seed=2, tiers=2)
+    mgr = B200TopoPodGroupManager(OraclePlacer(topo))
+    rbg = RoleBasedGroup("ns", "pd", [RoleSpec("prefill", 300, (), 1), RoleSpec("decode", 100, (), 1)], gid=1,
+                         scaling_rules=[ScalingRule(["prefill", "decode"], "5%", "OrderScheduled")])
+    batches = mgr.coordination_batches(rbg)
+    assert batches[0] == {"prefill": 15, "decode": 5} and batches[1] == {"prefill": 30, "decode": 10}
+    assert batches[-1] == {"prefill": 300, "decode": 100}
+    assert all(b2[r] >= b1[r] for b1, b2 in zip(batches, batches[1:]) for r in b1)
+    first, second = mgr.reconcile_ahead(rbg, 2, by_waves=True)
+    assert len(first.nodes) == 20 and "pd-prefill-14" in first.nodes and "pd-prefill-15" not in first.nodes
+    assert len(second.nodes) == 20 and sorted(second.nodes)[0] == "pd-decode-5" and "pd-prefill-29" in second.nodes
+    # the pre-placed batch saw the first one: capacity taken by batch 1 is not handed out twice
+    used = {}
+    for p in (first, second):
+        for node in p.nodes.values():
+            if node >= 0:
+                used[node] = used.get(node, 0) + 1
+    assert all(cnt <= topo.free[node] for node, cnt in used.items())
+    # one pass up to the second batch's targets, split by ordinal
+    both = RoleBasedGroup("ns", "pd", rbg.roles, gid=1, targets=batches[1])
+    want = B200TopoPodGroupManager(OraclePlacer(topo)).reconcile_pod_groups_by_waves([both])[0]
+    assert {**first.nodes, **second.nodes} == want.nodes
