@@ -5,8 +5,10 @@
 // records with the predicted `need`, pair rows, anchor records, the placeholder
 // records the waves fill in — never exists on the host and never crosses PCIe.
 //
-// Staging buffer (device copy of what the host wrote into pinned memory):
-//   [0, gwords)               GROUPS blob exactly as the caller passed it (include/rbgtopo.h)
+// `grp` = device copy of the GROUPS blob exactly as the caller passed it (include/rbgtopo.h);
+// it is the head of the staging buffer `src`, or the one an earlier batch of the same call
+// uploaded.  Staging buffer (device copy of what the host wrote into pinned memory):
+//   [0, gwords)               the GROUPS blob (absent when `grp` points elsewhere)
 //   [aux_off, +8*ns)          per step: group, wave, sec_off, sec_end, rep_off, row_off, next_step, i0
 //   [tail_off, +tail_words)   poff[ns + 1], copied behind the plan
 //
@@ -69,9 +71,10 @@ __device__ __forceinline__ void plan_wave_at(PlanScratch* S, int q, int w) {
 
 // One warp per step (+ warps for the tail words and the blob header).  Writes every word of
 // its step's header and section, so the plan buffer needs no clearing.
-__global__ void __launch_bounds__(32 * PLAN_WARPS) k_expand_plan(const int* __restrict__ src, int* __restrict__ out,
-                                                                 int ns, int plan_words, int aux_off, int tail_off,
-                                                                 int tail_words, int racc, int rowacc) {
+__global__ void __launch_bounds__(32 * PLAN_WARPS) k_expand_plan(const int* __restrict__ grp, const int* __restrict__ src,
+                                                                 int* __restrict__ out, int ns, int plan_words,
+                                                                 int aux_off, int tail_off, int tail_words, int racc,
+                                                                 int rowacc) {
   __shared__ PlanScratch scratch[PLAN_WARPS];
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.x * PLAN_WARPS + (threadIdx.x >> 5);
@@ -96,12 +99,12 @@ __global__ void __launch_bounds__(32 * PLAN_WARPS) k_expand_plan(const int* __re
   const int sec = __shfl_sync(0xFFFFFFFFu, av, 2), sec_end = __shfl_sync(0xFFFFFFFFu, av, 3);
   const int rep = __shfl_sync(0xFFFFFFFFu, av, 4), row = __shfl_sync(0xFFFFFFFFu, av, 5);
   const int next = __shfl_sync(0xFFFFFFFFu, av, 6), i0 = __shfl_sync(0xFFFFFFFFu, av, 7);
-  if (lane < RBGTOPO_GROUP_WORDS) S->rec[lane] = src[RBGTOPO_HDR_WORDS + (long long)g * RBGTOPO_GROUP_WORDS + lane];
+  if (lane < RBGTOPO_GROUP_WORDS) S->rec[lane] = grp[RBGTOPO_HDR_WORDS + (long long)g * RBGTOPO_GROUP_WORDS + lane];
   __syncwarp();
   const int gid = S->rec[0], gflags = S->rec[1], gfixed = S->rec[2], q = S->rec[3], na = S->rec[6];
-  const int* g_roles = src + S->rec[4];
-  const int* g_pair = src + S->rec[5];
-  const int* g_anc = src + S->rec[7];
+  const int* g_roles = grp + S->rec[4];
+  const int* g_pair = grp + S->rec[5];
+  const int* g_anc = grp + S->rec[7];
   for (int i = lane; i < 4 * q; i += 32) S->roles[i] = g_roles[i];
   for (int i = lane; i < q * q; i += 32) S->pair[i] = g_pair[i];
   __syncwarp();

@@ -122,6 +122,7 @@ struct Batch {
   bool in_use = false;    // reserved by a call or a stage handle
   bool staged = false;    // holds a staged blob (handle alive)
   bool ran = false;
+  bool d2h_enqueued = false;  // enqueue_d2h ran for the last pass; fetch_batch only has to wait
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> it_ev;  // triples (before score, after score, after select) per pass
@@ -141,6 +142,7 @@ struct Batch {
   // device-expanded plans: the staging buffer (GROUPS blob | per-step geometry | poff)
   DevBuf<int> gsrc;
   long long aux_off = -1;        // word offset of the per-step geometry in h_in; -1: host-built plan
+  int g_lo = 0;                  // first group of the GROUPS blob this plan covers
   std::vector<int> grp_flags, grp_assign_off, grp_pending;
   DevBuf<int> out;  // assign[total_r] | status[n] | domain[n] | dstar[n]
   PinBuf<int> h_in, h_out;
@@ -182,6 +184,11 @@ constexpr size_t kFastSmemMax = 200 * 1024;
 const bool kPerWavePlan = getenv("RBGTOPO_PER_WAVE_PLAN") != nullptr;  // one launch per wave instead of k_plan_group
 const int kEmitBlockSteps =
     getenv("RBGTOPO_EMIT_BLOCK") ? std::min(EMIT_MAX_BLOCK, std::max(1, atoi(getenv("RBGTOPO_EMIT_BLOCK")))) : 4;
+// place_groups can pipeline a fleet as two halves (host geometry of half 2 under the device work of
+// half 1).  Opt-in: at 1 024 groups it does not pay — the step is device-bound and the latency-bound
+// k_plan_group takes as long for half the groups as for all of them (profiles/README.md).
+const int kSplitMinGroups =
+    getenv("RBGTOPO_SPLIT_MIN_GROUPS") ? std::max(2, atoi(getenv("RBGTOPO_SPLIT_MIN_GROUPS"))) : (1 << 30);
 const bool kRefreshGraph = getenv("RBGTOPO_NO_REFRESH_GRAPH") == nullptr;
 const bool kVerifyPlan = getenv("RBGTOPO_VERIFY_PLAN") != nullptr;  // self-check: device-expanded plan == host-built plan
 const int kHostThreads = getenv("RBGTOPO_HOST_THREADS") ? std::max(1, atoi(getenv("RBGTOPO_HOST_THREADS"))) : 4;
@@ -477,6 +484,7 @@ int acquire_batch(rbgtopo_ctx* c, Batch** out) {
 void release_batch(rbgtopo_ctx* c, Batch* b) {
   std::lock_guard<std::mutex> g(c->pool_mu);
   b->wave_begin.clear();
+  b->d2h_enqueued = false;
   b->in_use = false;
   b->staged = false;
   b->ran = false;
@@ -681,13 +689,26 @@ int run_batch(rbgtopo_ctx* c, Batch* b, int iters) {
 
 // synchronise, copy the last pass's results out, harvest the timing of every
 // pass enqueued since the previous harvest.
-int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int32_t* domain) {
+// The D2H half of fetch_batch, enqueue only (place_groups pipelines two batches).
+int enqueue_d2h(rbgtopo_ctx* c, Batch* b) {
   cudaStream_t s = stream_of(c, b);
   const BatchMeta& m = b->m;
   const size_t out_n = (size_t)m.total_r + 2 * (size_t)m.n_steps;
   CK(cudaEventRecord(b->ev[4], s));
   if (out_n) CK(cudaMemcpyAsync(b->h_out.p, b->out.p, out_n * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(b->ev[5], s));
+  b->d2h_enqueued = true;
+  return RBGTOPO_OK;
+}
+
+int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int32_t* domain) {
+  cudaStream_t s = stream_of(c, b);
+  const BatchMeta& m = b->m;
+  if (!b->d2h_enqueued) {
+    int rc = enqueue_d2h(c, b);
+    if (rc) return rc;
+  }
+  b->d2h_enqueued = false;
   CK(cudaStreamSynchronize(s));
   CK(cudaGetLastError());
   if (assign && m.total_r) memcpy(assign, b->h_out.p, (size_t)m.total_r * 4);
@@ -1487,14 +1508,22 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
 // uploads GROUPS blob + geometry and lets k_expand_plan (plan.cuh) write the step blob in HBM.
 // Equivalent to build_plan + stage_into, without the step blob ever existing on the host.
 // Caller holds topo_mu shared.
-int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
+// [g_lo, g_hi): the groups of this batch (place_groups pipelines two halves of a large fleet);
+// pacc0 = pending replicas of the groups before g_lo; dev_groups = device copy of the GROUPS blob
+// uploaded by an earlier batch of the same call (then only the geometry is uploaded), or nullptr.
+int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, int g_lo = 0, int g_hi = -1,
+               long long pacc0 = 0, const int* dev_groups = nullptr, cudaEvent_t dev_groups_ready = nullptr) {
   const Topology& T = c->topo;
   if (!T.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
   if (words < RBGTOPO_HDR_WORDS || gb[0] != RBGTOPO_GROUPS_MAGIC || gb[1] != RBGTOPO_ABI_VERSION || gb[3] != words)
     return fail(RBGTOPO_EINVAL, "bad groups blob header");
-  const int ng = gb[2];
-  if (ng < 0 || (int64_t)RBGTOPO_HDR_WORDS + (int64_t)ng * RBGTOPO_GROUP_WORDS > words)
+  const int ng_all = gb[2];
+  if (ng_all < 0 || (int64_t)RBGTOPO_HDR_WORDS + (int64_t)ng_all * RBGTOPO_GROUP_WORDS > words)
     return fail(RBGTOPO_EINVAL, "group table exceeds blob");
+  if (g_hi < 0) g_hi = ng_all;
+  if (g_lo < 0 || g_lo > g_hi || g_hi > ng_all) return fail(RBGTOPO_EINVAL, "internal: group range");
+  const int ng = g_hi - g_lo;  // below, g is the index inside the range; blob records are g_lo + g
+  b->g_lo = g_lo;
   if (words > 0x3FFFFFFFLL) return fail(RBGTOPO_ELIMIT, "groups blob too large");
   auto in = [&](long long off, long long cnt) { return off >= 0 && cnt >= 0 && off + cnt <= words; };
   static const bool prof = getenv("RBGTOPO_PROFILE_HOST") != nullptr;
@@ -1516,7 +1545,7 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
 #define GROUP_FAIL(code, ...) return report ? fail(code, __VA_ARGS__) : (int)(code)
   // everything about group g that does not depend on the groups before it
   auto check_group = [&](int g, bool report) -> int {
-    const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
+    const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)(g_lo + g) * RBGTOPO_GROUP_WORDS;
     const int q = rec[3];
     if (q < 1 || q > RBGTOPO_MAX_GROUP_ROLES) GROUP_FAIL(RBGTOPO_ELIMIT, "group %d: %d roles", g, q);
     if (!in(rec[4], 4LL * q) || !in(rec[5], (long long)q * q) || !in(rec[7], 3LL * rec[6]))
@@ -1558,9 +1587,9 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
   BatchMeta& m = b->m;
   m = BatchMeta{};
   int W = 0;
-  long long pacc = 0;
+  long long pacc = pacc0;
   for (int g = 0; g < ng; ++g) {
-    const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
+    const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)(g_lo + g) * RBGTOPO_GROUP_WORDS;
     if (rec[8] != pacc || rec[9] != g_pend[g]) return fail(RBGTOPO_EINVAL, "group %d: bad assign_off/n_pending", g);
     b->grp_flags[g] = rec[1];
     b->grp_assign_off[g] = (int)pacc;
@@ -1572,7 +1601,7 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
     wv_off[g + 1] = wv_off[g] + g_nw[g];
     if (wv_off[g + 1] > 0x03FFFFFF) return fail(RBGTOPO_ELIMIT, "plan has more than 2^26 steps");
   }
-  if (gb[4] != pacc) return fail(RBGTOPO_EINVAL, "total pending mismatch");
+  if (g_hi == ng_all && gb[4] != pacc) return fail(RBGTOPO_EINVAL, "total pending mismatch");
   const int ns = wv_off[ng];
   const int* const wvo = wv_off.data();  // g_nw[] now holds prefixes: wave count of g = wvo[g + 1] - wvo[g]
   b->wave_begin.assign((size_t)W + 1, 0);
@@ -1590,7 +1619,7 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
     for (int w = 0; w < W; ++w) wb[w + 1] = wb[w] + cnt[w];
   }
   // staging layout: GROUPS blob | pad | geometry (8 ints per step) | poff
-  const size_t aux_off = ((size_t)words + 3) & ~(size_t)3;
+  const size_t aux_off = dev_groups ? 0 : (((size_t)words + 3) & ~(size_t)3);  // the blob is already on the device
   const size_t tail_off = aux_off + (size_t)ns * PLAN_AUX_WORDS;
   const size_t tail_words = (size_t)ns + 1;
   const size_t src_words = tail_off + tail_words;
@@ -1609,7 +1638,7 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
         const int s = wb[w] + ctr[w]++;
         if (w == 0) g_first[g] = s;
         sg[s] = g;
-        aux[(size_t)s * PLAN_AUX_WORDS + 0] = g;
+        aux[(size_t)s * PLAN_AUX_WORDS + 0] = g_lo + g;
         aux[(size_t)s * PLAN_AUX_WORDS + 1] = w;
         aux[(size_t)s * PLAN_AUX_WORDS + 6] = 0;
         if (prev >= 0) aux[(size_t)prev * PLAN_AUX_WORDS + 6] = s;  // next step of the group
@@ -1623,7 +1652,7 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
   const int max_degp1 = T.max_degp1;
   const int* const first_of = g_first.data();
   auto size_group = [&](int g, bool report) -> int {
-    const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
+    const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)(g_lo + g) * RBGTOPO_GROUP_WORDS;
     const int q = rec[3], na = rec[6];
     const int32_t* roles = gb + rec[4];
     const int32_t* pair = gb + rec[5];
@@ -1717,8 +1746,10 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
   if (emit_items(ns, c->lc) > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "steps x chunks exceed 2^31 work items");
   m.poff.assign(poff, poff + ns + 1);
   const auto p4 = now();
-  memcpy(hin, gb, (size_t)words * 4);
-  for (size_t i = (size_t)words; i < aux_off; ++i) hin[i] = 0;
+  if (!dev_groups) {
+    memcpy(hin, gb, (size_t)words * 4);
+    for (size_t i = (size_t)words; i < aux_off; ++i) hin[i] = 0;
+  }
   m.n_steps = ns;
   m.total_r = (int)racc;
   m.total_p = (int)rowacc;
@@ -1738,9 +1769,10 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
   CK(cudaStreamWaitEvent(s, c->topo_ready, 0));  // the snapshot refresh (if any) is complete
   CK(cudaEventRecord(b->ev[0], s));
   CK(cudaMemcpyAsync(b->gsrc.p, hin, src_words * 4, cudaMemcpyHostToDevice, s));
+  if (dev_groups && dev_groups_ready) CK(cudaStreamWaitEvent(s, dev_groups_ready, 0));
   {
     const long long warps = (long long)ns + ((long long)tail_words + 1 + 31) / 32;  // a warp per step + tail words
-    k_expand_plan<<<(unsigned)((warps + PLAN_WARPS - 1) / PLAN_WARPS), 32 * PLAN_WARPS, 0, s>>>(b->gsrc.p, b->blob.p, ns, (int)plan_words,
+    k_expand_plan<<<(unsigned)((warps + PLAN_WARPS - 1) / PLAN_WARPS), 32 * PLAN_WARPS, 0, s>>>(dev_groups ? dev_groups : b->gsrc.p, b->gsrc.p, b->blob.p, ns, (int)plan_words,
                                                                    (int)aux_off, (int)tail_off, (int)tail_words,
                                                                    (int)racc, (int)rowacc);
     CK(cudaGetLastError());
@@ -1800,7 +1832,7 @@ void plan_results(const Batch* b, int32_t* assign, int32_t* status, int32_t* dom
     for (int s = 0; s < m.n_steps; ++s) {
       const int32_t* x = aux + (size_t)s * PLAN_AUX_WORDS;
       const int R = (s + 1 < m.n_steps ? x[PLAN_AUX_WORDS + 4] : m.total_r) - x[4];
-      memcpy(assign + b->grp_assign_off[x[0]] + x[7], a + x[4], (size_t)R * 4);
+      memcpy(assign + b->grp_assign_off[x[0] - b->g_lo] + x[7], a + x[4], (size_t)R * 4);
     }
   std::vector<int> gstat(ng, 0), gdom(ng, -1);
   for (int s = 0; s < m.n_steps; ++s) {
@@ -1808,8 +1840,10 @@ void plan_results(const Batch* b, int32_t* assign, int32_t* status, int32_t* dom
     gstat[g] = std::max(gstat[g], st[s]);
     if (dm[s] >= 0) gdom[g] = dm[s];
   }
-  dirty->assign(ng, 0);
+  const int g0 = b->g_lo;  // status / domain / dirty are indexed by the group's position in the GROUPS blob
+  if ((int)dirty->size() < g0 + ng) dirty->resize((size_t)g0 + ng, 0);
   for (int g = 0; g < ng; ++g) {
+    (*dirty)[g0 + g] = 0;
     const bool gang = (b->grp_flags[g] & RBGTOPO_STEP_GANG) != 0;
     if (gstat[g] == RBGTOPO_GANG_FAILED || (gang && gstat[g] != RBGTOPO_PLACED_ALL)) {
       if (assign)
@@ -1817,11 +1851,27 @@ void plan_results(const Batch* b, int32_t* assign, int32_t* status, int32_t* dom
       gstat[g] = RBGTOPO_GANG_FAILED;
       gdom[g] = -1;
     } else if (gstat[g] == RBGTOPO_PLACED_PART) {
-      (*dirty)[g] = 1;  // `need` of the later waves was predicted with every replica placed
+      (*dirty)[g0 + g] = 1;  // `need` of the later waves was predicted with every replica placed
     }
-    if (status) status[g] = gstat[g];
-    if (domain) domain[g] = (b->grp_flags[g] & RBGTOPO_STEP_EXCLUSIVE) ? gdom[g] : -1;
+    if (status) status[g0 + g] = gstat[g];
+    if (domain) domain[g0 + g] = (b->grp_flags[g] & RBGTOPO_STEP_EXCLUSIVE) ? gdom[g] : -1;
   }
+}
+}  // namespace
+
+namespace {
+rbgtopo_timing add_timing(const rbgtopo_timing& a, const rbgtopo_timing& b) {
+  rbgtopo_timing t = a;
+  t.h2d_ms += b.h2d_ms;
+  t.score_ms += b.score_ms;
+  t.select_ms += b.select_ms;
+  t.d2h_ms += b.d2h_ms;
+  t.total_ms += b.total_ms;
+  t.launches += b.launches;
+  t.h2d_words += b.h2d_words;
+  t.scores += b.scores;
+  t.algo_bytes += b.algo_bytes;
+  return t;
 }
 }  // namespace
 
@@ -1833,29 +1883,80 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
     std::shared_lock<std::shared_mutex> lk(c->topo_mu);
     if (!c->topo.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
     CK(cudaSetDevice(c->cfg.device));
+    static const bool prof = getenv("RBGTOPO_PROFILE_HOST") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](auto a, auto b2) { return std::chrono::duration<double, std::micro>(b2 - a).count(); };
+    // Optional (RBGTOPO_SPLIT_MIN_GROUPS): two pipelined halves (groups are independent, spec §3.7) —
+    // the host computes the geometry of the second half while the device expands, scores and places
+    // the first, and unpacks the first half's results while the second runs.  The GROUPS blob is
+    // uploaded once.
+    const int ng_all = words >= RBGTOPO_HDR_WORDS ? gb[2] : 0;
+    const bool split = ng_all >= kSplitMinGroups && !kVerifyPlan;
     Batch* b = nullptr;
     int rc = acquire_batch(c, &b);
     if (rc) return rc;
-    static const bool prof = getenv("RBGTOPO_PROFILE_HOST") != nullptr;
-    auto now = [] { return std::chrono::steady_clock::now(); };
-    auto t0 = now();
-    rc = plan_stage(c, b, gb, words);
-    auto t1 = now();
-    if (!rc && kVerifyPlan) rc = verify_plan(c, b, gb, words);
-    auto t2 = now();
-    if (!rc) rc = run_batch(c, b, 1);
-    auto t3 = now();
-    if (!rc) rc = fetch_batch(c, b, nullptr, nullptr, nullptr);
-    auto t4 = now();
-    if (!rc) plan_results(b, assign, status, domain, &dirty);
-    if (prof) {
-      auto us = [](auto a, auto b2) { return std::chrono::duration<double, std::micro>(b2 - a).count(); };
-      fprintf(stderr, "[rbgtopo host] plan+stage %.0f us, verify %.0f us, enqueue %.0f us, wait+fetch %.0f us, results %.0f us\n",
-              us(t0, t1), us(t1, t2), us(t2, t3), us(t3, t4), us(t4, now()));
+    if (!split) {
+      auto t0 = now();
+      rc = plan_stage(c, b, gb, words);
+      auto t1 = now();
+      if (!rc && kVerifyPlan) rc = verify_plan(c, b, gb, words);
+      auto t2 = now();
+      if (!rc) rc = run_batch(c, b, 1);
+      auto t3 = now();
+      if (!rc) rc = fetch_batch(c, b, nullptr, nullptr, nullptr);
+      auto t4 = now();
+      if (!rc) plan_results(b, assign, status, domain, &dirty);
+      if (prof)
+        fprintf(stderr, "[rbgtopo host] plan+stage %.0f us, verify %.0f us, enqueue %.0f us, wait+fetch %.0f us, results %.0f us\n",
+                us(t0, t1), us(t1, t2), us(t2, t3), us(t3, t4), us(t4, now()));
+      if (rc) cudaStreamSynchronize(stream_of(c, b));
+      release_batch(c, b);
+      if (rc) return rc;
+    } else {
+      Batch* b2 = nullptr;
+      rc = acquire_batch(c, &b2);
+      if (rc) {
+        release_batch(c, b);
+        return rc;
+      }
+      const int mid = ng_all / 2;
+      auto t0 = now();
+      rc = plan_stage(c, b, gb, words, 0, mid);
+      if (!rc) rc = run_batch(c, b, 1);
+      if (!rc) rc = enqueue_d2h(c, b);
+      auto t1 = now();
+      if (!rc) rc = plan_stage(c, b2, gb, words, mid, ng_all, b->m.total_r, b->gsrc.p, b->ev[1]);
+      if (!rc) rc = run_batch(c, b2, 1);
+      if (!rc) rc = enqueue_d2h(c, b2);
+      auto t2 = now();
+      rbgtopo_timing first{};
+      if (!rc) rc = fetch_batch(c, b, nullptr, nullptr, nullptr);
+      auto t3 = now();
+      if (!rc) {
+        std::lock_guard<std::mutex> g(c->stat_mu);
+        first = c->last;
+      }
+      if (!rc) plan_results(b, assign, status, domain, &dirty);
+      auto t4 = now();
+      if (!rc) rc = fetch_batch(c, b2, nullptr, nullptr, nullptr);
+      auto t5 = now();
+      if (!rc) plan_results(b2, assign, status, domain, &dirty);
+      if (!rc) {
+        std::lock_guard<std::mutex> g(c->stat_mu);
+        c->last = add_timing(first, c->last);
+      }
+      if (prof)
+        fprintf(stderr, "[rbgtopo host] half 1 plan+enqueue %.0f us, half 2 plan+enqueue %.0f us, wait 1 %.0f us, results 1 %.0f us, "
+                        "wait 2 %.0f us, results 2 %.0f us\n",
+                us(t0, t1), us(t1, t2), us(t2, t3), us(t3, t4), us(t4, t5), us(t5, now()));
+      if (rc) {
+        cudaStreamSynchronize(stream_of(c, b));
+        cudaStreamSynchronize(stream_of(c, b2));
+      }
+      release_batch(c, b2);
+      release_batch(c, b);
+      if (rc) return rc;
     }
-    if (rc) cudaStreamSynchronize(stream_of(c, b));
-    release_batch(c, b);
-    if (rc) return rc;
   }
   bool any = false;
   for (char d : dirty) any |= d != 0;

@@ -187,13 +187,14 @@ def test_plan_dense_matrix_and_lists_match_oracle_per_wave():
     eng.close()
 
 
-@pytest.mark.parametrize("var", ["RBGTOPO_VERIFY_PLAN", "RBGTOPO_PER_WAVE_PLAN"])
+@pytest.mark.parametrize("var", ["RBGTOPO_VERIFY_PLAN", "RBGTOPO_PER_WAVE_PLAN", "RBGTOPO_SPLIT_MIN_GROUPS"])
 def test_plan_variants_in_a_subprocess(var):
     """The library reads its switches when it loads, hence the subprocess.
     RBGTOPO_VERIFY_PLAN: every place_groups / stage_groups call compares the plan k_expand_plan
     wrote in HBM (and the host-side geometry) word for word with the host plan builder.
     RBGTOPO_PER_WAVE_PLAN: the fallback that runs one launch per wave and chains placements
-    through the plan blob (what groups too large for k_plan_group's shared memory take)."""
+    through the plan blob (what groups too large for k_plan_group's shared memory take).
+    RBGTOPO_SPLIT_MIN_GROUPS=1 (-> 2): place_groups pipelines every fleet as two halves (opt-in)."""
     import os
     import subprocess
     import sys
