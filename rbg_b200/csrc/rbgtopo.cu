@@ -96,6 +96,7 @@ struct Topology {
   DevBuf<unsigned long long> okeys, order;  // background order of the slab (score.cuh / select.cuh)
   DevBuf<unsigned long long> okeys_all, order_all;  // world > 1: the order over all nodes (plan_group.cuh)
   DevBuf<unsigned char> sort_tmp;
+  int key_nb = 0, key_bits = 64;           // compact sort key of the background order (prepare_refresh)
   cudaGraphExec_t refresh_exec = nullptr;  // captured refresh chain of this topology (run_base)
   bool refresh_ready = false;              // buffers sized / graph built for the current topology
   std::vector<int> h_degp1;  // deg(n) + 1, for the patch-list capacity of a step
@@ -189,6 +190,7 @@ const int kEmitBlockSteps =
 // k_plan_group takes as long for half the groups as for all of them (profiles/README.md).
 const int kSplitMinGroups =
     getenv("RBGTOPO_SPLIT_MIN_GROUPS") ? std::max(2, atoi(getenv("RBGTOPO_SPLIT_MIN_GROUPS"))) : (1 << 30);
+const bool kCompactSortKey = getenv("RBGTOPO_WIDE_SORT_KEY") == nullptr;
 const bool kRefreshGraph = getenv("RBGTOPO_NO_REFRESH_GRAPH") == nullptr;
 const bool kVerifyPlan = getenv("RBGTOPO_VERIFY_PLAN") != nullptr;  // self-check: device-expanded plan == host-built plan
 const int kHostThreads = getenv("RBGTOPO_HOST_THREADS") ? std::max(1, atoi(getenv("RBGTOPO_HOST_THREADS"))) : 4;
@@ -234,9 +236,26 @@ TopoDev topo_dev(const rbgtopo_ctx* c) {
   return t;
 }
 
-__global__ void k_order_keys(TopoDev t, int lo, int hi, unsigned long long* keys) {
+// Sort keys of the background order.  base is a non-negative integer-valued float (sums of
+// int weights x fmin), so  (int(base) << nb) | (2^nb - 1 - node)  orders exactly like
+// make_key(base, node) and needs only nb + bits(max base) <= ~32 of the 64 key bits: the radix
+// sort runs 4 passes instead of 8.  nb == 0 selects the plain 64-bit key.
+__global__ void k_order_keys(TopoDev t, int lo, int hi, int nb, unsigned long long* keys) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < hi - lo) keys[i] = make_key(t.base[lo + i], lo + i);
+  if (i >= hi - lo) return;
+  const int node = lo + i;
+  if (nb == 0)
+    keys[i] = make_key(t.base[node], node);
+  else
+    keys[i] = ((unsigned long long)(long long)t.base[node] << nb) | (unsigned long long)(((1u << nb) - 1u) - (uint32_t)node);
+}
+// compact sorted keys -> the key(base, node) form the selection kernels read
+__global__ void k_order_expand(unsigned long long* keys, int n, int nb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = keys[i];
+  const uint32_t mask = (1u << nb) - 1u;
+  keys[i] = make_key((float)(long long)(k >> nb), (int)(mask - (uint32_t)(k & mask)));
 }
 
 // prep + base kernels on `s`; records base_ms.
@@ -256,6 +275,18 @@ void harvest_base_ms(rbgtopo_ctx* c) {
 // enqueue_refresh only launches.
 int prepare_refresh(rbgtopo_ctx* c) {
   Topology& T = c->topo;
+  {  // compact sort key: node bits + bits of the largest possible base = (wsum_max + self) * F
+    auto bits = [](unsigned long long v) { int b = 0; while (v) { ++b; v >>= 1; } return std::max(1, b); };
+    const int nb = bits((unsigned long long)std::max(1, T.n - 1));
+    const int bb = bits((unsigned long long)(T.wsum_max + RBGTOPO_SELF_W) * RBGTOPO_F_CAP);
+    if (kCompactSortKey && nb + bb <= 62 && nb <= 31) {
+      T.key_nb = nb;
+      T.key_bits = nb + bb;
+    } else {
+      T.key_nb = 0;
+      T.key_bits = 64;
+    }
+  }
   const int fmin_bytes = round_up(T.n, 16);
   const int staged = T.n <= FMIN_SMEM_MAX ? 1 : 0;
   const size_t smem = (size_t)2 * (BASE_TILE_NNZ + 8) * 4 + (staged ? fmin_bytes : 0);
@@ -290,14 +321,16 @@ int enqueue_refresh(rbgtopo_ctx* c, cudaStream_t s) {
   // background order: slab nodes by key(base, node) descending (library radix sort, once per snapshot)
   const int slab_len = c->slab_hi - c->slab_lo;
   if (slab_len > 0) {
-    k_order_keys<<<(slab_len + 255) / 256, 256, 0, s>>>(td, c->slab_lo, c->slab_hi, T.okeys.p);
+    k_order_keys<<<(slab_len + 255) / 256, 256, 0, s>>>(td, c->slab_lo, c->slab_hi, T.key_nb, T.okeys.p);
     size_t tmp_bytes = T.sort_tmp.cap;
-    CK(cub::DeviceRadixSort::SortKeysDescending(T.sort_tmp.p, tmp_bytes, T.okeys.p, T.order.p, slab_len, 0, 64, s));
+    CK(cub::DeviceRadixSort::SortKeysDescending(T.sort_tmp.p, tmp_bytes, T.okeys.p, T.order.p, slab_len, 0, T.key_bits, s));
+    if (T.key_nb) k_order_expand<<<(slab_len + 255) / 256, 256, 0, s>>>(T.order.p, slab_len, T.key_nb);
   }
   if (c->cfg.world > 1 && T.n > 0) {  // replicated selection (plan_group.cuh) walks the order of ALL nodes
-    k_order_keys<<<(T.n + 255) / 256, 256, 0, s>>>(td, 0, T.n, T.okeys_all.p);
+    k_order_keys<<<(T.n + 255) / 256, 256, 0, s>>>(td, 0, T.n, T.key_nb, T.okeys_all.p);
     size_t tmp_bytes = T.sort_tmp.cap;
-    CK(cub::DeviceRadixSort::SortKeysDescending(T.sort_tmp.p, tmp_bytes, T.okeys_all.p, T.order_all.p, T.n, 0, 64, s));
+    CK(cub::DeviceRadixSort::SortKeysDescending(T.sort_tmp.p, tmp_bytes, T.okeys_all.p, T.order_all.p, T.n, 0, T.key_bits, s));
+    if (T.key_nb) k_order_expand<<<(T.n + 255) / 256, 256, 0, s>>>(T.order_all.p, T.n, T.key_nb);
   }
   CK(cudaGetLastError());
   return RBGTOPO_OK;
