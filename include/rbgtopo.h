@@ -355,6 +355,28 @@ int32_t rbgtopo_next_rolling_target(int32_t max_skew_percent, int32_t n_roles,
                                     const int32_t* ready,
                                     int32_t* rolling_target);
 
+/* ---- host-only inspection of the multi-wave plan (no GPU needed) ----------- *
+ * The step geometry rbgtopo_place_groups / rbgtopo_stage_groups derive from a
+ * GROUPS blob — which wave every pending replica is placed in, how the waves of
+ * all groups are laid out wave-major — computed by the very code path those
+ * calls use, without touching a device (unit tests, capacity planning).
+ *   deg_plus1[n_nodes] = CSR degree + 1 per node (NULL: 1 everywhere), wsum_max =
+ *   largest row sum of edge weights (0: none): they only enter the patch-list
+ *   capacities and the exactness bound (RBGTOPO_EINEXACT).
+ * out_steps receives RBGTOPO_PLAN_STEP_WORDS ints per step, steps in wave-major
+ * order: group index, wave of the group, section offset, section end (words of
+ * the step blob), first replica row, first role row, next step of the group
+ * (0 = last), replicas of the group placed by its earlier waves.  At most
+ * out_cap_steps steps are written; *n_steps / *n_waves / *plan_words report the
+ * totals. */
+#define RBGTOPO_PLAN_STEP_WORDS 8
+int32_t rbgtopo_plan_describe(const int32_t* groups, int64_t groups_words,
+                              int32_t n_nodes, int32_t n_domains,
+                              const int32_t* deg_plus1, int64_t wsum_max,
+                              int32_t* out_steps, int64_t out_cap_steps,
+                              int32_t* n_steps, int32_t* n_waves,
+                              int64_t* plan_words);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,13 +71,24 @@ template <typename T>
 struct PinBuf {
   T* p = nullptr;
   size_t cap = 0;
-  ~PinBuf() { if (p) cudaFreeHost(p); }
-  cudaError_t reserve(size_t n) {
-    if (n <= cap) return cudaSuccess;
-    if (p) cudaFreeHost(p);
+  bool pageable = false;  // host-only inspection (rbgtopo_plan_describe): plain malloc, no CUDA call
+  ~PinBuf() { release(); }
+  void release() {
+    if (!p) return;
+    if (pageable) free(p); else cudaFreeHost(p);
     p = nullptr;
     cap = 0;
+  }
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    release();
     size_t want = n + n / 4 + 64;
+    if (pageable) {
+      p = static_cast<T*>(malloc(want * sizeof(T)));
+      if (!p) return cudaErrorMemoryAllocation;
+      cap = want;
+      return cudaSuccess;
+    }
     cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
     if (e == cudaSuccess) cap = want;
     return e;
@@ -1544,10 +1555,23 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
 // [g_lo, g_hi): the groups of this batch (place_groups pipelines two halves of a large fleet);
 // pacc0 = pending replicas of the groups before g_lo; dev_groups = device copy of the GROUPS blob
 // uploaded by an earlier batch of the same call (then only the geometry is uploaded), or nullptr.
-int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, int g_lo = 0, int g_hi = -1,
-               long long pacc0 = 0, const int* dev_groups = nullptr, cudaEvent_t dev_groups_ready = nullptr) {
-  const Topology& T = c->topo;
-  if (!T.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
+// What the plan geometry needs to know about the snapshot (host side only).
+struct TopoHost {
+  int n = 0, n_domains = 0;
+  const int* degp1 = nullptr;  // [n] deg + 1, or nullptr = all 1
+  int max_degp1 = 1;
+  long long wsum_max = 0;
+};
+struct PlanLayout {  // staging layout of one plan: GROUPS blob | pad | geometry (8 ints per step) | poff
+  size_t aux_off = 0, tail_off = 0, tail_words = 0, src_words = 0;
+  long long plan_words = 0, racc = 0, rowacc = 0;
+  int ns = 0;
+};
+
+// Pure host part of plan_stage (no CUDA call when b->h_in is pageable): validates the groups of
+// [g_lo, g_hi), fills the batch's wave tables, b->m and the staging buffer b->h_in.
+int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_t words, int g_lo, int g_hi,
+                  long long pacc0, bool with_blob, PlanLayout* L) {
   if (words < RBGTOPO_HDR_WORDS || gb[0] != RBGTOPO_GROUPS_MAGIC || gb[1] != RBGTOPO_ABI_VERSION || gb[3] != words)
     return fail(RBGTOPO_EINVAL, "bad groups blob header");
   const int ng_all = gb[2];
@@ -1574,7 +1598,7 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, int g
   int* const g_nw = wv_off.data() + 1;  // per-group wave count first, prefix-summed below
   int* const g_pcp = g_pc.data();
   const int n_nodes = T.n, n_domains = T.n_domains;
-  const int* const degp1 = T.h_degp1.data();
+  const int* const degp1 = T.degp1;
 #define GROUP_FAIL(code, ...) return report ? fail(code, __VA_ARGS__) : (int)(code)
   // everything about group g that does not depend on the groups before it
   auto check_group = [&](int g, bool report) -> int {
@@ -1601,7 +1625,7 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, int g
       const int32_t* an = gb + rec[7] + 3 * a;
       if (an[0] < 0 || an[0] >= n_nodes || an[1] < 0 || an[1] >= q || an[2] < 0)
         GROUP_FAIL(RBGTOPO_EINVAL, "group %d anchor %d out of range", g, a);
-      pc += degp1[an[0]];
+      pc += degp1 ? degp1[an[0]] : 1;
     }
     if (pc > 0x3FFFFFFFLL) GROUP_FAIL(RBGTOPO_ELIMIT, "group %d: patch list exceeds 2^30 entries", g);
     g_pend[g] = (int)pend;
@@ -1652,7 +1676,7 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, int g
     for (int w = 0; w < W; ++w) wb[w + 1] = wb[w] + cnt[w];
   }
   // staging layout: GROUPS blob | pad | geometry (8 ints per step) | poff
-  const size_t aux_off = dev_groups ? 0 : (((size_t)words + 3) & ~(size_t)3);  // the blob is already on the device
+  const size_t aux_off = with_blob ? (((size_t)words + 3) & ~(size_t)3) : 0;  // without: the blob is already on the device
   const size_t tail_off = aux_off + (size_t)ns * PLAN_AUX_WORDS;
   const size_t tail_words = (size_t)ns + 1;
   const size_t src_words = tail_off + tail_words;
@@ -1776,10 +1800,10 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, int g
     b->step_row[ns] = (int)rowacc;
   }
   const long long plan_words = off;
-  if (emit_items(ns, c->lc) > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "steps x chunks exceed 2^31 work items");
+  if (emit_items(ns, lc) > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "steps x chunks exceed 2^31 work items");
   m.poff.assign(poff, poff + ns + 1);
   const auto p4 = now();
-  if (!dev_groups) {
+  if (with_blob) {
     memcpy(hin, gb, (size_t)words * 4);
     for (size_t i = (size_t)words; i < aux_off; ++i) hin[i] = 0;
   }
@@ -1788,16 +1812,46 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, int g
   m.total_p = (int)rowacc;
   m.words = plan_words;
   m.h2d_words = (long long)src_words;
-  const long long slab = c->slab_hi - c->slab_lo;
-  m.scores = racc * slab;
-  m.algo_bytes = 4LL * racc * slab + 4LL * plan_words + 8LL * slab;  // as validate_blob
   b->aux_off = (long long)aux_off;
+  L->aux_off = aux_off;
+  L->tail_off = tail_off;
+  L->tail_words = tail_words;
+  L->src_words = src_words;
+  L->plan_words = plan_words;
+  L->racc = racc;
+  L->rowacc = rowacc;
+  L->ns = ns;
+  if (prof)
+    fprintf(stderr, "[rbgtopo plan] check %ld us, numbering %ld us, sizes %ld us, prefixes %ld us, copy %ld us\n",
+            us(p0, p1), us(p1, p2), us(p2, p3), us(p3, p4), us(p4, now()));
+  return RBGTOPO_OK;
+}
 
-  const auto p5 = now();
+int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, int g_lo = 0, int g_hi = -1,
+               long long pacc0 = 0, const int* dev_groups = nullptr, cudaEvent_t dev_groups_ready = nullptr) {
+  const Topology& T = c->topo;
+  if (!T.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
+  TopoHost th;
+  th.n = T.n;
+  th.n_domains = T.n_domains;
+  th.degp1 = T.h_degp1.data();
+  th.max_degp1 = T.max_degp1;
+  th.wsum_max = T.wsum_max;
+  PlanLayout L;
+  int rc = plan_geometry(th, c->lc, b, gb, words, g_lo, g_hi, pacc0, dev_groups == nullptr, &L);
+  if (rc) return rc;
+  BatchMeta& m = b->m;
+  const long long slab = c->slab_hi - c->slab_lo;
+  m.scores = L.racc * slab;
+  m.algo_bytes = 4LL * L.racc * slab + 4LL * L.plan_words + 8LL * slab;  // as validate_blob
+  const size_t aux_off = L.aux_off, tail_off = L.tail_off, tail_words = L.tail_words, src_words = L.src_words;
+  const long long plan_words = L.plan_words, racc = L.racc, rowacc = L.rowacc;
+  const int ns = L.ns;
+  int32_t* const hin = b->h_in.p;
   cudaStream_t s = stream_of(c, b);
   CK(b->gsrc.reserve(src_words));
   CK(b->blob.reserve((size_t)plan_words + tail_words));
-  int rc = reserve_batch_buffers(c, b);
+  rc = reserve_batch_buffers(c, b);
   if (rc) return rc;
   CK(cudaStreamWaitEvent(s, c->topo_ready, 0));  // the snapshot refresh (if any) is complete
   CK(cudaEventRecord(b->ev[0], s));
@@ -1814,9 +1868,6 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, int g
   b->pend_launches += 1;
   b->staged = true;
   b->ran = false;
-  if (prof)
-    fprintf(stderr, "[rbgtopo plan] check %ld us, numbering %ld us, sizes %ld us, prefixes %ld us, copy %ld us, enqueue %ld us\n",
-            us(p0, p1), us(p1, p2), us(p2, p3), us(p3, p4), us(p4, p5), us(p5, now()));
   return RBGTOPO_OK;
 }
 
@@ -1995,6 +2046,40 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
   for (char d : dirty) any |= d != 0;
   if (!any) return RBGTOPO_OK;
   return place_groups_slow(c, gb, words, assign, status, domain, &dirty);
+}
+
+int32_t rbgtopo_plan_describe(const int32_t* gb, int64_t words, int32_t n_nodes, int32_t n_domains,
+                              const int32_t* deg_plus1, int64_t wsum_max, int32_t* out_steps, int64_t out_cap_steps,
+                              int32_t* n_steps, int32_t* n_waves, int64_t* plan_words) {
+  if (!gb || !n_steps) return fail(RBGTOPO_EINVAL, "null argument");
+  if (n_nodes < 1 || n_domains < 1 || wsum_max < 0) return fail(RBGTOPO_EINVAL, "n_nodes / n_domains / wsum_max");
+  TopoHost th;
+  th.n = n_nodes;
+  th.n_domains = n_domains;
+  th.degp1 = deg_plus1;
+  th.max_degp1 = 1;
+  if (deg_plus1)
+    for (int i = 0; i < n_nodes; ++i) {
+      if (deg_plus1[i] < 1) return fail(RBGTOPO_EINVAL, "deg_plus1[%d]", i);
+      th.max_degp1 = std::max(th.max_degp1, deg_plus1[i]);
+    }
+  th.wsum_max = wsum_max;
+  static thread_local std::unique_ptr<Batch> scratch;  // host vectors + a pageable staging buffer only
+  if (!scratch) {
+    scratch = std::make_unique<Batch>();
+    scratch->h_in.pageable = true;
+  }
+  PlanLayout L;
+  const int lc = (n_nodes + 2047) / 2048;
+  int rc = plan_geometry(th, lc, scratch.get(), gb, words, 0, -1, 0, false, &L);
+  if (rc) return rc;
+  *n_steps = L.ns;
+  if (n_waves) *n_waves = (int)scratch->wave_begin.size() - 1;
+  if (plan_words) *plan_words = L.plan_words;
+  if (out_steps && out_cap_steps > 0)
+    memcpy(out_steps, scratch->h_in.p + L.aux_off,
+           (size_t)std::min<int64_t>(out_cap_steps, L.ns) * RBGTOPO_PLAN_STEP_WORDS * 4);
+  return RBGTOPO_OK;
 }
 
 int32_t rbgtopo_stage_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int32_t* handle) {
