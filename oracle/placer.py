@@ -51,16 +51,30 @@ def check_topology(topo) -> int:
                                         _p(fr), _p(dm), C.c_int32(len(ow)), _p(ow))
 
 
-def place(topo, blob, want_matrix=True, want_topk=True, nthreads=1):
+_MATRIX_CACHE = {}
+
+
+def place(topo, blob, want_matrix=True, want_topk=True, nthreads=1, reuse_matrix=False):
     """Run the oracle on a batch.  Returns dict(rc, assign, status, domain,
-    matrix [total R][N] or None, topk [rolerows][32] or None)."""
+    matrix [total R][N] or None, topk [rolerows][32] or None).
+    reuse_matrix: write the dense matrix into a buffer kept per shape instead of a fresh array
+    (timing runs: a fresh 50 MB array per call is page-fault time, not oracle time); the returned
+    matrix is then only valid until the next call with the same shape."""
     lib = load()
     rp, ci, ew = _i32(topo.row_ptr), _i32(topo.col_idx), _i32(topo.edge_w)
     fr, dm, ow = _i32(topo.free), _i32(topo.domain), _i32(topo.domain_owner)
     blob = _i32(blob)
     n = len(rp) - 1
     ns, tr, tp = int(blob[2]), int(blob[4]), int(blob[5])
-    matrix = np.empty((max(tr, 1), n), dtype=np.float32) if want_matrix else None
+    matrix = None
+    if want_matrix:
+        shape = (max(tr, 1), n)
+        if reuse_matrix:
+            matrix = _MATRIX_CACHE.get(shape)
+            if matrix is None:
+                matrix = _MATRIX_CACHE[shape] = np.empty(shape, dtype=np.float32)
+        else:
+            matrix = np.empty(shape, dtype=np.float32)
     topk = np.zeros((max(tp, 1), KMAX), dtype=np.uint64) if want_topk else None
     assign = np.full(max(tr, 1), -2, dtype=np.int32)
     status = np.full(max(ns, 1), -2, dtype=np.int32)
