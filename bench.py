@@ -352,16 +352,19 @@ def run_ours(args):
     h2d = d2h = 0
     if replicated:
         free = np.ascontiguousarray(topo.free, dtype=np.int32)
-        for _ in range(3):
+        for _ in range(max(args.warmup, 3) + 16):   # the host side (threads, caches) cooled down during the value leg
             eng.update_nodes(free)
             eng.place_groups(gblob)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            eng.update_nodes(free)
-            a_e2e, s_e2e, d_e2e = eng.place_groups(gblob)
-        torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t0) * 1e3
+        rounds = []
+        for _ in range(5):                            # K steps per round; the median round is reported
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                eng.update_nodes(free)
+                a_e2e, s_e2e, d_e2e = eng.place_groups(gblob)
+            torch.cuda.synchronize()
+            rounds.append((time.perf_counter() - t0) * 1e3)
+        e2e_ms = sorted(rounds)[len(rounds) // 2]
         n_plan_steps = eng.last_timing()["h2d_words"]          # blob + offsets words of the compiled plan
         h2d = int(free.nbytes + 4 * n_plan_steps)
         d2h = int(4 * (total_r + 2 * 3 * args.groups))
@@ -436,8 +439,9 @@ def run_ours(args):
                       f"({total_r * (hi - lo) * 4 / 1e6:.0f} MB) exceeds the 126 MB L2; inputs are L2-resident by design",
                 "value_leg": "multi-wave plan resident in HBM (rbgtopo_stage_groups), base vector resident "
                              "(recomputed by update_nodes, which is inside the e2e leg)",
-                "e2e_leg": "rbgtopo_update_nodes + rbgtopo_place_groups with host buffers; marshalling RBG "
-                           "objects into the groups blob is the caller's (Go shim) job and is outside",
+                "e2e_leg": "rbgtopo_update_nodes + rbgtopo_place_groups with host buffers, median of 5 rounds of "
+                           "K steps; marshalling RBG objects into the groups blob is the caller's (Go shim) job "
+                           "and is outside",
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
