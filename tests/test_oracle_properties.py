@@ -11,7 +11,7 @@ from oracle import placer, placer_ref
 from rbg_b200 import synth
 from rbg_b200.blob import ROLE_EXCLUSIVE, STEP_EXCLUSIVE, STEP_GANG, BlobBuilder, Step
 
-CFG = dict(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+CFG = dict(max_examples=200, deadline=None, suppress_health_check=[HealthCheck.too_slow])
 
 
 @st.composite
