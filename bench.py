@@ -45,70 +45,71 @@ UNIT = "scores/s"
 
 
 # ----------------------------------------------------------------- workload
-def build_fleet(n_groups: int, n_nodes: int, seed: int = 0):
-    """cfg3 fleet: mooncake-shaped RBGs; group g already has (g % 4) scheduled
-    pods (partially deployed groups give every group its own anchor term)."""
-    from rbg_b200 import synth
-    from rbg_b200.plugin import RoleBasedGroup, RoleSpec
-    shape = synth.shape_mooncake()
-    rbgs = []
+# A fleet is described by plain dicts (no product or oracle types), so that the two arms build
+# their own objects from the same description: ours -> rbg_b200.plugin.RoleBasedGroup (marshalled
+# by the plugin mirror through the C ABI), reference / checker -> oracle.wave_loop.OGroup.
+CONFIGS = {
+    # BASELINE.json configs[2]: the one the metric is quoted on (default, weak scaling on the node axis)
+    "cfg3": dict(shape="mooncake", groups=1024, nodes=10000, scaling="weak",
+                 what="mooncake RBGs (5 roles / 7 pods, 3 dependency waves)"),
+    # BASELINE.json configs[3]: fleet of 1 000 RBGs x 8 replicas over 50 000 nodes, node axis sharded (strong scaling)
+    "cfg4": dict(shape="fleet8", groups=1000, nodes=50000, scaling="strong",
+                 what="fleet8 RBGs (router 1 / prefill 3 / decode 4 = 8 pods, 1 wave)"),
+    # BASELINE.json configs[4]: continuous reconcile under churn, 10 % node add/remove per step, 10 000 nodes
+    "cfg5": dict(shape="mooncake", groups=1024, nodes=10000, scaling="strong",
+                 what="mooncake RBGs re-placed every step while 10 % of the nodes leave / come back"),
+}
+
+
+def fleet_spec(shape_name: str, n_groups: int, n_nodes: int, seed: int = 0):
+    """Group g of the fleet already has (g % 4) scheduled pods (partially deployed groups give
+    every group its own anchor term)."""
+    from rbg_b200 import synth     # pure numpy generators; loads no native code
+    shape = {"mooncake": synth.shape_mooncake, "fleet8": synth.shape_fleet8, "pd144": synth.shape_pd_144}[shape_name]()
+    out = []
     for g in range(n_groups):
-        roles = [RoleSpec(r.name, r.replicas, tuple(r.deps), r.demand) for r in shape.roles]
         placed = [(shape.roles[q].name, node) for node, q, _ in
                   synth.random_anchors(n_nodes, len(shape.roles), g % 4, seed, g)]
-        rbgs.append(RoleBasedGroup("default", f"rbg{g}", roles, gid=g, policy_rules=shape.policy_rules,
-                                   placed=placed))
-    return rbgs
+        out.append(dict(name=f"rbg{g}", gid=g, roles=[(r.name, r.replicas, tuple(r.deps), r.demand) for r in shape.roles],
+                        rules=[tuple(x) for x in shape.policy_rules], placed=placed))
+    return out
 
 
-class _RecordingPlacer:
-    """Wraps a placer and records the per-wave step blobs (to stage them)."""
-
-    def __init__(self, inner):
-        self.inner = inner
-        self.n_nodes = inner.n_nodes
-        self.blobs = []
-
-    def score_assign(self, blob):
-        self.blobs.append(np.array(blob, copy=True))
-        return self.inner.score_assign(blob)
+def to_plugin(specs):
+    from rbg_b200.plugin import RoleBasedGroup, RoleSpec
+    return [RoleBasedGroup("default", s["name"], [RoleSpec(n, r, d, dm) for n, r, d, dm in s["roles"]], gid=s["gid"],
+                           policy_rules=s["rules"], placed=s["placed"]) for s in specs]
 
 
-class _OraclePlacer:
-    """CPU oracle behind the placer interface (cpu_baseline / reference arm only)."""
-
-    def __init__(self, topo, nthreads):
-        from oracle import placer as oracle_placer
-        self.o = oracle_placer
-        self.topo = topo
-        self.n_nodes = topo.n
-        self.nthreads = nthreads
-
-    def score_assign(self, blob):
-        r = self.o.place(self.topo, blob, want_matrix=True, want_topk=False, nthreads=self.nthreads)
-        if r["rc"] != 0:
-            raise RuntimeError(f"oracle rc={r['rc']}")
-        return r["assign"], r["status"], r["domain"]
+def to_oracle(specs):
+    from oracle.wave_loop import OGroup, ORole
+    return [OGroup(s["name"], s["gid"], [ORole(n, r, d, dm) for n, r, d, dm in s["roles"]], rules=s["rules"],
+                   placed=s["placed"]) for s in specs]
 
 
-def oracle_wave_blobs(topo, rbgs):
-    """The per-wave step batches of a fleet, derived with the CPU oracle (untimed)."""
+def build_fleet(n_groups: int, n_nodes: int, seed: int = 0):   # kept for probes / tests
+    return to_plugin(fleet_spec("mooncake", n_groups, n_nodes, seed))
+
+
+def oracle_wave_blobs(topo, specs):
+    """The per-wave step batches of a fleet, derived with the CPU oracle alone (untimed)."""
     from oracle import placer as oracle_placer
-    from rbg_b200.plugin import B200TopoPodGroupManager
-    rec = _RecordingPlacer(_OraclePlacer(topo, oracle_placer.max_threads()))
-    B200TopoPodGroupManager(rec).reconcile_pod_groups_by_waves(rbgs)
-    return rec.blobs
+    from oracle import wave_loop
+    _, blobs = wave_loop.run_fleet(topo, to_oracle(specs), nthreads=oracle_placer.max_threads())
+    return blobs
 
 
-def oracle_scores_per_sec(topo, blobs, nthreads, min_seconds=6.0, max_reps=1 << 30):
+def oracle_scores_per_sec(topo, blobs, nthreads, min_seconds=6.0, max_reps=1 << 30, fast=False):
     """Time ONLY the C oracle (score -> top-K -> greedy, dense matrix emitted) on
-    the wave batches; steps of a batch are spread over `nthreads` OpenMP threads."""
+    the wave batches; steps of a batch are spread over `nthreads` OpenMP threads.
+    fast=True: the variant with the GPU path's algebra (base + sparse corrections, oracle/placer_fast.c)."""
     from oracle import placer as oracle_placer
+    place = oracle_placer.place_fast if fast else oracle_placer.place
     per_pass = sum(int(b[4]) for b in blobs) * topo.n
     scores, reps, t0 = 0, 0, time.perf_counter()
     while True:
         for b in blobs:
-            r = oracle_placer.place(topo, b, want_matrix=True, want_topk=False, nthreads=nthreads, reuse_matrix=True)
+            r = place(topo, b, want_matrix=True, want_topk=False, nthreads=nthreads, reuse_matrix=True)
             assert r["rc"] == 0
         scores += per_pass
         reps += 1
@@ -133,14 +134,21 @@ def host_thread_candidates():
     return sorted(cand)
 
 
-def best_oracle_threads(topo, blobs, seconds=0.4):
+def best_oracle_threads(topo, blobs, seconds=0.4, fast=False):
     """The thread count at which the oracle is fastest on this host (short calibration passes)."""
     best_nt, best_v = 1, 0.0
     for nt in host_thread_candidates():
-        v, _, _ = oracle_scores_per_sec(topo, blobs, nt, min_seconds=seconds)
+        v, _, _ = oracle_scores_per_sec(topo, blobs, nt, min_seconds=seconds, fast=fast)
         if v > best_v:
             best_nt, best_v = nt, v
     return best_nt
+
+
+def product_so_loaded() -> bool:
+    try:
+        return "librbgtopo" in open("/proc/self/maps").read()
+    except Exception:
+        return False
 
 
 # ------------------------------------------------------------------ clocks
@@ -204,57 +212,149 @@ class _DevPtr:
                                          "version": 3, "strides": None}
 
 
+# ------------------------------------------------------------------ parity
+def parity_check(eng, topo, specs, gblob, handle, fetched, sample, lo, hi, oracle_threads):
+    """The checker: the CPU oracle's level/wave loop on a deterministic sample of the fleet vs the
+    staged multi-wave plan this rank just ran — dense matrix bits on the rank's column slab
+    (every wave, every replica row of the sampled groups), assignment, status, exclusive domain.
+    Groups are independent within a batch (snapshot semantics), so the oracle run
+    of the sample alone equals the sample's part of the fleet run."""
+    from oracle import wave_loop
+    from rbg_b200.engine import plan_steps
+    steps = plan_steps(gblob, topo.n, len(topo.domain_owner))
+    row_of = {(int(st[0]), int(st[1])): int(st[4]) for st in steps}
+    rows = bad_rows = 0
+    first_bad = None
+
+    def on_wave(w, active, blob, r):
+        nonlocal rows, bad_rows, first_bad
+        off = 0
+        for st in active:
+            cnt = sum(c for _, _, c in st.waves[w])
+            row0 = row_of[(sample[st.pos], w)]
+            for k in range(cnt):
+                got = eng.read_scores(handle, row0 + k)
+                exp = r["matrix"][off + k, lo:hi]
+                rows += 1
+                if not np.array_equal(got.view(np.uint32), exp.view(np.uint32)):
+                    bad_rows += 1
+                    if first_bad is None:
+                        j = int(np.nonzero(got.view(np.uint32) != exp.view(np.uint32))[0][0])
+                        first_bad = f"group {sample[st.pos]} wave {w} replica {k} node {lo + j}: gpu {got[j]} oracle {exp[j]}"
+            off += cnt
+
+    og = to_oracle([specs[i] for i in sample])
+    states = [wave_loop.GroupState(g) for g in og]
+    for i, st in enumerate(states):
+        st.pos = i
+    # run_fleet builds its own states: re-use its loop but with ours (same order) to keep `pos`
+    blobs, w = [], 0
+    from oracle import placer as oracle_placer
+    while True:
+        active = [st for st in states if not st.failed and w < len(st.waves)]
+        if not active:
+            break
+        blob = wave_loop.build_blob([st.step(w) for st in active])
+        r = oracle_placer.place(topo, blob, want_matrix=True, want_topk=False, nthreads=oracle_threads)
+        assert r["rc"] == 0, r["rc"]
+        on_wave(w, active, blob, r)
+        off = 0
+        for i, st in enumerate(active):
+            cnt = sum(c for _, _, c in st.waves[w])
+            st.absorb(w, r["assign"][off:off + cnt], int(r["status"][i]), int(r["domain"][i]))
+            off += cnt
+        w += 1
+    assign, status, domain = fetched
+    bad_groups = 0
+    for st in states:
+        g = sample[st.pos]
+        rec = gblob[8 + 12 * g: 8 + 12 * (g + 1)]
+        want = st.assign_in_group_order()
+        res = st.result()
+        got = assign[rec[8]: rec[8] + rec[9]].tolist()
+        if got != want or int(status[g]) != res["status"] or int(domain[g]) != res["domain"]:
+            bad_groups += 1
+            if first_bad is None:
+                first_bad = f"group {g}: gpu {got} status {int(status[g])} domain {int(domain[g])}; oracle {want} {res['status']} {res['domain']}"
+    return {"ok": bad_rows == 0 and bad_groups == 0, "groups_checked": len(sample), "rows_checked": rows,
+            "waves": w, "bad_rows": bad_rows, "bad_groups": bad_groups, "first_bad": first_bad,
+            "checked": "dense matrix bits on this rank's column slab (every wave of the sampled groups), assignment, "
+                       "status, exclusive domain vs the CPU oracle's wave loop"}
+
+
+def placement_parity(topo, specs, sample, gblob, result, oracle_threads):
+    """assign / status / domain of the sampled groups (host-buffer results) vs the oracle."""
+    from oracle import wave_loop
+    states, _ = wave_loop.run_fleet(topo, to_oracle([specs[i] for i in sample]), nthreads=oracle_threads)
+    assign, status, domain = result
+    bad = 0
+    for g, st in zip(sample, states):
+        rec = gblob[8 + 12 * g: 8 + 12 * (g + 1)]
+        res = st.result()
+        if (assign[rec[8]: rec[8] + rec[9]].tolist() != st.assign_in_group_order() or int(status[g]) != res["status"]
+                or int(domain[g]) != res["domain"]):
+            bad += 1
+    return bad
+
+
 # ------------------------------------------------------------------- ours
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from rbg_b200 import synth
-    from rbg_b200.engine import TopoPlacer
-    from rbg_b200.plugin import B200TopoPodGroupManager
+class Dist:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", 0))
+        self.world = int(os.environ.get("WORLD_SIZE", 1))
+        self.local = int(os.environ.get("LOCAL_RANK", 0))
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        assert self.world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={self.world}"
+        self.stream = torch.cuda.Stream()
 
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    n_nodes = args.nodes * world          # weak scaling on the node axis
-    topo = synth.make_topology(n_nodes, seed=0, tiers=4, samples_per_tier=5)
-    rbgs = build_fleet(args.groups, n_nodes)
+    def max_over_ranks(self, x: float) -> float:
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # the wave batches: derive them once on rank-local single-GPU semantics.  The
-    # placement is deterministic, so the wave w+1 batch (which carries wave w's
-    # placements as anchors) is identical every step.
-    eng = TopoPlacer(device=local, rank=rank, world=world)
-    eng.set_topology(topo.row_ptr, topo.col_idx, topo.edge_w, topo.free, topo.domain, topo.domain_owner)
-    gblob, _ = B200TopoPodGroupManager(eng).groups_blob(rbgs)   # host-side marshalling, identical on every rank
-    replicated = world == 1 or args.shard_mode == "replicated"
+    def min_over_ranks(self, x: float) -> float:
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return float(t.item())
 
-    stream = torch.cuda.Stream()
-    eng.set_stream(stream.cuda_stream)
-    # device-resident multi-wave plan: ONE k_score_emit launch per rank for the dense rows of all
-    # waves; per wave: select (+ all-gather + merge when sharded) + assign, chained on the device
-    handles = [eng.stage_groups(gblob)]
-    total_r = int(gblob[4])
-    n_waves = eng.shard_waves(handles[0])
-    lo, hi = eng.slab()
-    scores_per_step_rank = total_r * (hi - lo)
-    gathered = {}
 
-    def device_step():
-        if replicated:
+def make_device_step(D, eng, handles, n_waves, mode):
+    """One placement pass of the staged fleet.  replicated: run_staged (no collective on the step
+    path).  p2p: the in-library all-gather over NVLink peer memory (rbgtopo_run_staged_p2p).
+    allgather: per-wave NCCL all-gather driven from here (north_star's literal scheme)."""
+    torch, dist = D.torch, D.dist
+    if mode == "replicated" or D.world == 1:
+        def step():
             for h in handles:
                 eng.run_staged(h, 1)
-            return
-        with torch.cuda.stream(stream):
+        return step
+    if mode == "p2p":
+        def step():
+            for h in handles:
+                eng.run_staged_p2p(h, 1)
+        return step
+    gathered = {}
+
+    def step():
+        with torch.cuda.stream(D.stream):
             for h in handles:
                 for w in range(n_waves):
                     ptr, nb = eng.shard_wave_score(h, w)
                     if (h, ptr) not in gathered:   # library buffers are stable per staged batch: wrap them once
                         gathered[(h, ptr)] = (torch.as_tensor(_DevPtr(ptr, nb), device="cuda"),
-                                              torch.empty(world * (nb // 8), dtype=torch.int64, device="cuda"))
+                                              torch.empty(D.world * (nb // 8), dtype=torch.int64, device="cuda"))
                     src, allk = gathered[(h, ptr)]
                     dist.all_gather_into_tensor(allk, src)
                     need2, p2, nb2 = eng.shard_wave_merge(h, w, allk.data_ptr())
@@ -262,236 +362,324 @@ def run_ours(args):
                     if need2:
                         if (h, p2, 2) not in gathered:
                             gathered[(h, p2, 2)] = (torch.as_tensor(_DevPtr(p2, nb2), device="cuda"),
-                                                    torch.empty(world * (nb2 // 8), dtype=torch.int64, device="cuda"))
+                                                    torch.empty(D.world * (nb2 // 8), dtype=torch.int64, device="cuda"))
                         src2, g2 = gathered[(h, p2, 2)]
                         dist.all_gather_into_tensor(g2, src2)
                     eng.shard_wave_assign(h, w, g2.data_ptr() if g2 is not None else None)
+    return step
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    # world > 1: a step is ~20 small launches + 3-6 NCCL calls issued from Python; capture it
-    # once into a CUDA graph (kernels of the library and the NCCL all-gathers on one stream)
-    # and replay it — "CUDA streams and graphs instead of a tracing compiler".
-    eager_step = device_step
-    graph_note = "eager"
-    if world > 1 and args.graph and not replicated:
-        try:
-            for _ in range(3):
-                eager_step()
-            torch.cuda.synchronize()
-            # events recorded during capture carry no timestamps: take the per-kernel
-            # CUDA-event timing of the dominant kernel from these eager passes
-            eager_timing = []
-            for h in handles:
-                eng.fetch(h)
-                eager_timing.append(eng.last_timing())
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=stream):
-                eager_step()
-            torch.cuda.synchronize()
+def run_config(D, args, cfg_name, with_clocks):
+    """Stages one configuration, checks it against the oracle, times the resident-plan leg
+    (`value`) and the host-buffer leg (`e2e`).  Returns the pieces of the JSON line."""
+    torch = D.torch
+    from rbg_b200 import synth
+    from rbg_b200.engine import TopoPlacer
+    from rbg_b200.plugin import B200TopoPodGroupManager
+    cfg = CONFIGS[cfg_name]
+    rank, world, local = D.rank, D.world, D.local
+    groups = args.groups if cfg_name == "cfg3" else cfg["groups"]
+    nodes = args.nodes if cfg_name == "cfg3" else cfg["nodes"]
+    n_nodes = nodes * world if cfg["scaling"] == "weak" else nodes
+    topo = synth.make_topology(n_nodes, seed=0, tiers=4, samples_per_tier=5)
+    specs = fleet_spec(cfg["shape"], groups, n_nodes)
+    rbgs = to_plugin(specs)
+    mode = args.shard_mode if world > 1 else "replicated"
+    churn = cfg_name == "cfg5"
 
-            def device_step():   # noqa: F811
-                with torch.cuda.stream(stream):
-                    g.replay()
-            graph_note = "cuda-graph replay of one captured step"
-        except Exception as e:   # capture not possible on this stack: stay eager
-            graph_note = f"eager (graph capture failed: {type(e).__name__})"
-            device_step = eager_step
-            torch.cuda.synchronize()
+    eng = TopoPlacer(device=local, rank=rank, world=world)
+    eng.set_topology(topo.row_ptr, topo.col_idx, topo.edge_w, topo.free, topo.domain, topo.domain_owner)
+    gblob, _ = B200TopoPodGroupManager(eng).groups_blob(rbgs)   # host-side marshalling, identical on every rank
+    if mode == "p2p":
+        eng.p2p_connect(D)
+    eng.set_stream(D.stream.cuda_stream)
+    handles = [eng.stage_groups(gblob)]
+    total_r = int(gblob[4])
+    n_waves = eng.shard_waves(handles[0])
+    lo, hi = eng.slab()
+    scores_rank = total_r * (hi - lo)
+    scores_all = total_r * n_nodes
+    device_step = make_device_step(D, eng, handles, n_waves, mode)
 
-    # ---- value: resident inputs, CUDA events on the launching stream
-    for _ in range(max(args.warmup, 3)):
-        device_step()
-    for h in handles:
-        eng.fetch(h)            # sync + reset the timing window
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    # clock soak: K steps last a few ms, far below nvidia-smi's sampling period, so the
-    # same step is run untimed for ~0.6 s first; the clock samples cover soak + timed region
-    t_soak = time.perf_counter()
-    while time.perf_counter() - t_soak < args.soak:
-        for _ in range(50):
+    # ---- parity first (DESIGN.md §5): a deterministic sample of the fleet, all waves, on every rank
+    from oracle import placer as oracle_placer
+    nt_par = max(1, min(16, oracle_placer.max_threads(), len(os.sched_getaffinity(0)) // max(1, world)))
+    sample = sorted(set(int(i) for i in np.linspace(0, groups - 1, min(groups, args.parity_groups))))
+    device_step()
+    D.torch.cuda.synchronize()
+    fetched = eng.fetch(handles[0])
+    par = parity_check(eng, topo, specs, gblob, handles[0], fetched, sample, lo, hi, nt_par)
+    par["ok"] = bool(D.min_over_ranks(1.0 if par["ok"] else 0.0) > 0.5)
+    par["ranks_checked"] = world
+    if not par["ok"] and not args.keep_going:
+        raise SystemExit(f"PARITY FAILED ({cfg_name}, rank {rank}): {par}")
+
+    out = {"config_name": cfg_name, "parity": par}
+    steps = args.steps
+    if not churn:
+        # ---- value: resident inputs, CUDA events on the launching stream
+        for _ in range(max(args.warmup, 3)):
             device_step()
         for h in handles:
-            eng.fetch(h)
-    launches0 = eng.stats()["kernel_launches"]
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(args.steps):
-        device_step()
-    ev1.record(stream)
-    barrier()
-    dev_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
-    launches = eng.stats()["kernel_launches"] - launches0
-    # per-kernel timing of the timed region (events recorded inside the library
-    # around every k_score_select launch), harvested at fetch
-    score_ms = algo_bytes = 0.0
-    results, h2d_words = [], 0
-    for i, h in enumerate(handles):
-        results.append(eng.fetch(h))
-        t = eng.last_timing()
-        if graph_note.startswith("cuda-graph"):
-            t = eager_timing[i]
-        score_ms += t["score_ms"]
-        algo_bytes += t["algo_bytes"]
-        h2d_words += t["h2d_words"]
-    t_ms = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    dev_ms = float(t_ms.item())
-    value = scores_per_step_rank * world * args.steps / (dev_ms * 1e-3)
-
-    # ---- e2e: host buffers through the C ABI, H2D + D2H + host wave loop inside
-    eng.set_stream(None)
-    h2d = d2h = 0
-    if replicated:
-        free = np.ascontiguousarray(topo.free, dtype=np.int32)
-        for _ in range(max(args.warmup, 3) + 16):   # the host side (threads, caches) cooled down during the value leg
-            eng.update_nodes(free)
-            eng.place_groups(gblob)
-        rounds = []
-        for _ in range(5):                            # K steps per round; the median round is reported
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                eng.update_nodes(free)
-                a_e2e, s_e2e, d_e2e = eng.place_groups(gblob)
-            torch.cuda.synchronize()
-            rounds.append((time.perf_counter() - t0) * 1e3)
-        e2e_ms = sorted(rounds)[len(rounds) // 2]
-        n_plan_steps = eng.last_timing()["h2d_words"]          # blob + offsets words of the compiled plan
-        h2d = int(free.nbytes + 4 * n_plan_steps)
-        d2h = int(4 * (total_r + 2 * 3 * args.groups))
-        # the e2e result must equal the staged path's result
-        assert np.array_equal(results[0][0], a_e2e), "e2e placement differs from the staged path"
-    else:
-        for h in handles:
-            eng.release(h)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            hs = [eng.stage_groups(gblob)]
-            eng.set_stream(stream.cuda_stream)
-            handles = hs
-            eager_step()
-            torch.cuda.synchronize()
-            for h in hs:
+            eng.fetch(h)            # sync + reset the timing window
+        sampler = ClockSampler(local)
+        if rank == 0 and with_clocks:
+            sampler.start()
+        # clock soak: K steps last a few ms, far below nvidia-smi's sampling period, so the
+        # same step is run untimed for ~0.6 s first; the clock samples cover soak + timed region
+        t_soak = time.perf_counter()
+        while time.perf_counter() - t_soak < (args.soak if with_clocks else 0.1):
+            for _ in range(50):
+                device_step()
+            for h in handles:
                 eng.fetch(h)
-                eng.release(h)
-            eng.set_stream(None)
-        e2e_ms = (time.perf_counter() - t0) * 1e3
-        h2d = int(4 * h2d_words)
-        d2h = int(4 * (total_r + 2 * 3 * args.groups))
-    t_e = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t_e.item())
-    e2e_value = scores_per_step_rank * world * args.steps / (e2e_ms * 1e-3)
+        launches0 = eng.stats()["kernel_launches"]
+        D.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(D.stream)
+        for _ in range(steps):
+            device_step()
+        ev1.record(D.stream)
+        D.barrier()
+        dev_ms = ev0.elapsed_time(ev1)
+        clocks = sampler.stop() if (rank == 0 and with_clocks) else None
+        launches = eng.stats()["kernel_launches"] - launches0
+        # per-kernel timing of the timed region (events recorded inside the library around every
+        # launch of the dense-matrix kernel), harvested at fetch
+        score_ms = algo_bytes = 0.0
+        for h in handles:
+            eng.fetch(h)
+            t = eng.last_timing()
+            score_ms += t["score_ms"]
+            algo_bytes += t["algo_bytes"]
+        per_score, per_sel = eng.last_pass_times()
+        dev_ms = D.max_over_ranks(dev_ms)
+        out.update(value=scores_rank * world * steps / (dev_ms * 1e-3) if cfg["scaling"] == "weak"
+                   else scores_all * steps / (dev_ms * 1e-3),
+                   ms_per_step=dev_ms / steps, launches=int(launches), clocks=clocks, score_ms=score_ms,
+                   algo_bytes=algo_bytes,
+                   emit_launch_us={"min": float(per_score.min()) * 1e3, "median": float(np.median(per_score)) * 1e3,
+                                   "max": float(per_score.max()) * 1e3, "n": int(len(per_score))} if len(per_score) else None,
+                   select_launch_us={"min": float(per_sel.min()) * 1e3, "median": float(np.median(per_sel)) * 1e3,
+                                     "n": int(len(per_sel))} if len(per_sel) else None)
 
+    # ---- e2e: host buffers through the C ABI, H2D + D2H inside
+    eng.set_stream(None)
+    free0 = np.ascontiguousarray(topo.free, dtype=np.int32)
+    if churn:
+        # 10 % of the nodes leave (capacity 0) or come back per step: 8 snapshots, cycled
+        rng = np.random.default_rng(5)
+        gone = np.zeros(n_nodes, dtype=bool)
+        frees = []
+        for _ in range(8):
+            flip = rng.choice(n_nodes, size=n_nodes // 10, replace=False)
+            gone[flip] = ~gone[flip]
+            frees.append(np.where(gone, 0, free0).astype(np.int32))
+    else:
+        frees = [free0]
+    if mode == "replicated" or world == 1:
+        def e2e_step(k):
+            eng.update_nodes(frees[k % len(frees)])
+            return eng.place_groups(gblob)
+    else:
+        def e2e_step(k):
+            eng.update_nodes(frees[k % len(frees)])
+            h = eng.stage_groups(gblob)
+            eng.set_stream(D.stream.cuda_stream)
+            make_device_step(D, eng, [h], n_waves, mode)()
+            torch.cuda.synchronize()
+            r = eng.fetch(h)
+            eng.release(h)
+            eng.set_stream(None)
+            return r
+    if churn:   # parity of two churned snapshots (placements only: the host-buffer call keeps no matrix)
+        bad = 0
+        for k in (0, 3):
+            res = e2e_step(k)
+            topo_k = synth.Topology(topo.row_ptr, topo.col_idx, topo.edge_w, frees[k], topo.domain, topo.domain_owner)
+            bad += placement_parity(topo_k, specs, sample, gblob, res, nt_par)
+        out["parity"]["churn_snapshots_checked"] = 2
+        out["parity"]["churn_bad_groups"] = bad
+        out["parity"]["ok"] = bool(out["parity"]["ok"] and D.min_over_ranks(1.0 if bad == 0 else 0.0) > 0.5)
+        if not out["parity"]["ok"] and not args.keep_going:
+            raise SystemExit(f"PARITY FAILED under churn ({cfg_name}, rank {rank})")
+    for k in range(max(args.warmup, 3) + 16):   # the host side (threads, caches) cooled down during the value leg
+        e2e_step(k)
+    rounds = []
+    res = None
+    for _ in range(5):                            # K steps per round; the median round is reported
+        D.barrier()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            res = e2e_step(k)
+        torch.cuda.synchronize()
+        rounds.append((time.perf_counter() - t0) * 1e3)
+    e2e_ms = D.max_over_ranks(sorted(rounds)[len(rounds) // 2])
+    if not churn:
+        assert np.array_equal(fetched[0], res[0]), "e2e placement differs from the staged path"
+    n_plan_words = eng.last_timing()["h2d_words"]          # GROUPS blob + per-step geometry words uploaded
+    out.update(e2e_value=(scores_rank * world if cfg["scaling"] == "weak" else scores_all) * steps / (e2e_ms * 1e-3),
+               e2e_ms=e2e_ms / steps, h2d=int(free0.nbytes + 4 * n_plan_words), d2h=int(4 * (total_r + 2 * 3 * groups)),
+               n_nodes=n_nodes, groups=groups, total_r=total_r, edges=int(topo.e), slab=(lo, hi), mode=mode,
+               topo=topo, specs=specs, what=cfg["what"], scaling=cfg["scaling"])
+    if churn:   # no resident-plan leg: every step re-uploads a changed snapshot, so the step IS the e2e call
+        out.update(value=out["e2e_value"], ms_per_step=out["e2e_ms"], launches=0, clocks=None, score_ms=0.0, algo_bytes=0.0)
+    for h in handles:
+        eng.release(h)
+    eng.close()
+    return out
+
+
+def roofline_of(r, peak, peak_src):
+    achieved = (r["algo_bytes"] / 1e9) / (r["score_ms"] * 1e-3) if r.get("score_ms") else 0.0
+    step_frac = (r["algo_bytes"] / 1e9) / (r["ms_per_step"] * 1e-3) / peak if r.get("ms_per_step") else None
+    traffic = None
+    traffic_src = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "score_select_dram_bytes.json")) as f:
+            j = json.load(f)
+            traffic = j.get("dram_bytes_per_step")
+            traffic_src = "static_from_profile: " + str(j.get("source", "ncu --set full capture kept under profiles/"))
+    except Exception:
+        pass
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
+            "kernel": "k_score_emit (one launch per step and rank emits the dense rows of every wave)",
+            "peak_source": peak_src, "algo_bytes_per_step": r["algo_bytes"], "kernel_ms_per_step": r["score_ms"],
+            "kernel_launch_us": r.get("emit_launch_us"), "select_launch_us": r.get("select_launch_us"),
+            "frac_of_nominal_8000": achieved / 8000.0,
+            "whole_step_frac": step_frac,
+            "whole_step_note": "the same algorithmic bytes over ms_per_step (dense-matrix kernel + selection/greedy kernel)"}
+
+
+def run_ours(args):
+    D = Dist(args)
+    rank, world = D.rank, D.world
+    main = run_config(D, args, args.config, with_clocks=True)
+    alts = {}
+    if args.alt:
+        for name in ("cfg4", "cfg5"):
+            if name != args.config:
+                alts[name] = run_config(D, args, name, with_clocks=False)
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        achieved = (algo_bytes / 1e9) / (score_ms * 1e-3) if score_ms > 0 else 0.0
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "score_select_dram_bytes.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_step")
-        except Exception:
-            pass
+        topo, specs = main["topo"], main["specs"]
+        n_nodes, lo, hi = main["n_nodes"], *main["slab"]
+        replicated = main["mode"] == "replicated"
         # ---- cpu_baseline (bounded sample, N=1 only)
         cpu = None
         if world == 1 and not args.no_cpu:
             from oracle import placer as oracle_placer
-            sample = rbgs[:min(len(rbgs), args.cpu_groups)]
+            sample = specs[:min(len(specs), args.cpu_groups)]
             sblobs = oracle_wave_blobs(topo, sample)
             nt = best_oracle_threads(topo, sblobs)
             v, dt, reps = oracle_scores_per_sec(topo, sblobs, nt, min_seconds=args.cpu_seconds)
             s1 = oracle_wave_blobs(topo, sample[:max(8, len(sample) // 8)])
             v1, dt1, _ = oracle_scores_per_sec(topo, s1, 1, min_seconds=args.cpu_seconds / 2)
             cpu = {"value": v, "unit": UNIT, "cores": nt, "kind": "port",
-                   "sample": f"{len(sample)} of the {len(rbgs)} RBGs x {reps} passes, same 10 000-node topology, "
+                   "sample": f"{len(sample)} of the {len(specs)} RBGs x {reps} passes, same {n_nodes}-node topology, "
                              f"{dt:.1f} s of wall time on {nt} OpenMP threads (the fastest of "
                              f"{host_thread_candidates()}); 1 thread: {v1:.3e} scores/s",
                    "single_thread_value": v1,
                    "note": "CPU oracle of OUR frozen spec, not sgl-project/rbg code (the reference has no such path)"}
+            if hasattr(oracle_placer, "place_fast"):
+                ntf = best_oracle_threads(topo, sblobs, fast=True)
+                vf, dtf, repsf = oracle_scores_per_sec(topo, sblobs, ntf, min_seconds=args.cpu_seconds / 2, fast=True)
+                cpu["same_algebra"] = {"value": vf, "cores": ntf, "kind": "port",
+                                       "note": "CPU variant with the GPU path's algebra (base vector per snapshot + sparse "
+                                               "corrections, partial selection): oracle/placer_fast.c, bit-checked against "
+                                               "the literal oracle in tests/"}
+
+        def alt_line(r):
+            d = {"workload": f"{r['config_name']}: {r['groups']} {r['what']} x {r['n_nodes']}-node topology",
+                 "scaling": r["scaling"], "parity": r["parity"],
+                 "e2e": {"value": r["e2e_value"], "unit": UNIT, "ms_per_step": r["e2e_ms"],
+                         "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]}}
+            if r.get("score_ms"):
+                d.update(value=r["value"], unit=UNIT, ms_per_step=r["ms_per_step"], gpu_launches=r["launches"],
+                         roofline=roofline_of(r, peak, peak_src))
+            return d
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+            "scaling": main["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"cfg3: {args.groups} mooncake RBGs (5 roles / 7 pods, 3 dependency waves) x "
+                "workload": f"{args.config}: {main['groups']} {main['what']} x "
                             f"{n_nodes}-node NVLink/PCIe/RDMA/VPC topology"
                             + ("" if world == 1 else
-                               f", node axis sharded over {world} GPUs ({args.nodes} nodes per GPU): "
+                               f", node axis sharded over {world} GPUs ({(hi - lo)} nodes on rank 0): "
                                + ("dense matrix column-sharded, selection replicated on every rank over all nodes "
                                   "(identical placements, no per-step collective)" if replicated else
-                                  "one NCCL all-gather of per-shard top-K lists per wave")),
-                "parallelism": "single GPU" if world == 1 else f"node-axis x{world}, " + args.shard_mode,
-                "launch": "eager (k_score_emit + k_plan_group per step)" if replicated else graph_note,
-                "groups": args.groups, "nodes": n_nodes, "edges": int(topo.e), "replicas_per_step": total_r,
+                                  ("per-shard top-K lists all-gathered per wave by the library's own kernels over NVLink "
+                                   "peer memory (no NCCL call on the step path)" if main["mode"] == "p2p" else
+                                   "one NCCL all-gather of per-shard top-K lists per wave"))),
+                "parallelism": "single GPU" if world == 1 else f"node-axis x{world}, " + main["mode"],
+                "launch": "eager (k_score_emit || k_plan_select, then k_plan_correct, per step)" if replicated else main["mode"],
+                "groups": main["groups"], "nodes": n_nodes, "edges": main["edges"], "replicas_per_step": main["total_r"],
                 "emit_matrix": True,
                 "l2": "dense-matrix write stream per step "
-                      f"({total_r * (hi - lo) * 4 / 1e6:.0f} MB) exceeds the 126 MB L2; inputs are L2-resident by design",
+                      f"({main['total_r'] * (hi - lo) * 4 / 1e6:.0f} MB) exceeds the 126 MB L2; inputs are L2-resident by design",
                 "value_leg": "multi-wave plan resident in HBM (rbgtopo_stage_groups), base vector resident "
                              "(recomputed by update_nodes, which is inside the e2e leg)",
                 "e2e_leg": "rbgtopo_update_nodes + rbgtopo_place_groups with host buffers, median of 5 rounds of "
                            "K steps; marshalling RBG objects into the groups blob is the caller's (Go shim) job "
                            "and is outside",
             },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": int(launches),
-            "clocks": dict(clocks, window="clock soak (--soak s of identical untimed steps) + timed region"),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": traffic,
-                         "kernel": "k_score_emit (one launch per step and rank emits the dense rows of all 3 waves)",
-                         "peak_source": peak_src, "algo_bytes_per_step": algo_bytes,
-                         "kernel_ms_per_step": score_ms, "frac_of_nominal_8000": achieved / 8000.0},
+            "e2e": {"value": main["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": main["h2d"],
+                    "d2h_bytes_per_step": main["d2h"], "ms_per_step": main["e2e_ms"]},
+            "gpu_launches": main["launches"],
+            "clocks": dict(main["clocks"] or {}, window="clock soak (--soak s of identical untimed steps) + timed region"),
+            "roofline": roofline_of(main, peak, peak_src),
+            "parity": main["parity"],
             "cpu_baseline": cpu,
+            "alt": {k: alt_line(v) for k, v in alts.items()},
         }
         print(json.dumps(line))
-    eng.close()
     if world > 1:
-        dist.destroy_process_group()
+        D.dist.destroy_process_group()
 
 
 # -------------------------------------------------------------- reference
 def run_reference(args):
     """Reference arm: the reference has no implementation of this path and no Go
     toolchain exists here, so (per the task's tier rules) the arm times the CPU
-    oracle port on all host threads, on the same config and metric."""
+    oracle port on all host threads, on the same config and metric.  Inputs are built by
+    oracle-side code only (oracle/wave_loop.py): the product library is never loaded here."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     from oracle import placer as oracle_placer
-    from rbg_b200 import synth
-    n_nodes = args.nodes * args.gpus
+    from rbg_b200 import synth      # pure numpy generators
+    cfg = CONFIGS[args.config]
+    groups = args.groups if args.config == "cfg3" else cfg["groups"]
+    nodes = args.nodes if args.config == "cfg3" else cfg["nodes"]
+    n_nodes = nodes * args.gpus if cfg["scaling"] == "weak" else nodes
     topo = synth.make_topology(n_nodes, seed=0, tiers=4, samples_per_tier=5)
-    rbgs = build_fleet(args.groups, n_nodes)
-    sample = rbgs[:min(len(rbgs), args.ref_groups)]
+    specs = fleet_spec(cfg["shape"], groups, n_nodes)
+    sample = specs[:min(len(specs), args.ref_groups)]
     blobs = oracle_wave_blobs(topo, sample)
     nt = best_oracle_threads(topo, blobs)   # torchrun pins OMP_NUM_THREADS=1: the fastest count within the affinity mask
     for _ in range(min(args.warmup, 1)):
         oracle_scores_per_sec(topo, blobs, nt, min_seconds=0.0, max_reps=1)
     v, dt, reps = oracle_scores_per_sec(topo, blobs, nt, min_seconds=0.0, max_reps=args.steps)
-    scores = v * dt
-    v = scores / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": cfg["scaling"],
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"cfg3: mooncake RBGs x {n_nodes}-node topology; each step = a bounded sample of "
-                               f"{len(sample)} of the {args.groups} RBGs", "groups": args.groups, "nodes": n_nodes},
+        "config": {"workload": f"{args.config}: {cfg['what']} x {n_nodes}-node topology; each step = a bounded sample of "
+                               f"{len(sample)} of the {groups} RBGs (the rate is per score, so the sample size does "
+                               "not enter the comparison)", "groups": groups, "nodes": n_nodes},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": nt, "kind": "port",
                          "sample": f"{len(sample)} RBGs per step x {args.steps} steps on {nt} OpenMP threads "
                                    f"(the fastest of {host_thread_candidates()})"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "product_so_loaded": product_so_loaded(),
     }
+    if hasattr(oracle_placer, "place_fast"):
+        ntf = best_oracle_threads(topo, blobs, fast=True)
+        vf, _, _ = oracle_scores_per_sec(topo, blobs, ntf, min_seconds=0.0, max_reps=args.steps, fast=True)
+        line["cpu_baseline"]["same_algebra"] = {"value": vf, "cores": ntf,
+                                                "note": "oracle/placer_fast.c: base + sparse algebra, partial selection"}
     print(json.dumps(line))
 
 
@@ -501,17 +689,24 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--groups", type=int, default=1024)
-    ap.add_argument("--nodes", type=int, default=10000, help="nodes per GPU")
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS),
+                    help="cfg3 (default, BASELINE.json configs[2]: the metric's config), cfg4 (fleet, 50 000 nodes, "
+                         "strong scaling), cfg5 (continuous reconcile under 10 %% churn)")
+    ap.add_argument("--no-alt", dest="alt", action="store_false",
+                    help="skip the cfg4 / cfg5 measurements reported under `alt`")
+    ap.add_argument("--groups", type=int, default=1024, help="cfg3: RBGs per step")
+    ap.add_argument("--nodes", type=int, default=10000, help="cfg3: nodes per GPU")
+    ap.add_argument("--parity-groups", type=int, default=64, help="groups the oracle re-places before timing")
+    ap.add_argument("--keep-going", action="store_true", help="report a parity failure in the line instead of aborting")
     ap.add_argument("--cpu-groups", type=int, default=256)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--ref-groups", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--shard-mode", default="replicated", choices=["replicated", "allgather"],
+    ap.add_argument("--shard-mode", default="replicated", choices=["replicated", "allgather", "p2p"],
                     help="N > 1: 'replicated' = dense matrix column-sharded, selection replicated on every rank, "
-                         "no per-step collective; 'allgather' = per-shard top-K lists all-gathered (NCCL) per wave")
-    ap.add_argument("--graph", action="store_true",
-                    help="world > 1: capture the step into a CUDA graph (experimental: hung with NCCL on this stack)")
+                         "no per-step collective; 'p2p' = per-shard top-K lists exchanged per wave by the library's "
+                         "own kernels over NVLink peer memory; 'allgather' = the same exchange as NCCL all-gathers "
+                         "driven from Python")
     ap.add_argument("--soak", type=float, default=0.6, help="seconds of untimed identical steps before the timed region")
     args = ap.parse_args()
     if args.impl == "reference":

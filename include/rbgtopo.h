@@ -296,6 +296,12 @@ int32_t rbgtopo_set_stream(rbgtopo_ctx* ctx, void* cuda_stream);
 
 /* ---- stats (SURVEY.md §5 metrics row) ----------------------------------- */
 int32_t rbgtopo_last_timing(rbgtopo_ctx* ctx, rbgtopo_timing* out);
+/* Per-pass CUDA-event durations (ms) of the dense-matrix kernel (k_score_emit) and of the
+ * selection / assignment kernel(s), for every timed pass the last rbgtopo_fetch harvested
+ * (bench.py prints their min / median so that a reported average can be checked).  At most `cap`
+ * entries are written; *n_passes is the number available. */
+int32_t rbgtopo_last_pass_times(rbgtopo_ctx* ctx, float* score_ms, float* select_ms,
+                                int32_t cap, int32_t* n_passes);
 int32_t rbgtopo_stats(rbgtopo_ctx* ctx, uint64_t* generation, int64_t* calls,
                       int64_t* scores_total, int64_t* kernel_launches);
 

@@ -11,4 +11,10 @@ Only what the path needs lives here:
 There is no CPU fallback anywhere in this package.
 """
 from .blob import BlobBuilder, Step  # noqa: F401
-from .engine import TopoPlacer, RbgTopoError  # noqa: F401
+
+
+def __getattr__(name):   # engine (and with it the ctypes binding) only when somebody asks for it:
+    if name in ("TopoPlacer", "RbgTopoError"):   # `import rbg_b200.synth` must stay free of native code
+        from . import engine
+        return getattr(engine, name)
+    raise AttributeError(name)

@@ -31,7 +31,15 @@ using namespace rbgtopo;
 
 namespace {
 
+// Error text.  The failing call stores it for the calling THREAD (g_err) and, thread-agnostic, as
+// the library's most recent error (g_last_err): a cgo caller whose goroutine migrated to another
+// OS thread between the failing call and rbgtopo_last_error still gets the text.  The Go shim
+// fetches it inside the same C helper as the call (go/pkg/scheduler/b200topo/cgo_bridge.go), where
+// no migration can happen; the fallback is for callers that do not.
 thread_local std::string g_err;
+thread_local int g_err_code = 0;
+std::mutex g_last_err_mu;
+std::string g_last_err;
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -40,6 +48,11 @@ int fail(int code, const char* fmt, ...) {
   vsnprintf(buf, sizeof buf, fmt, ap);
   va_end(ap);
   g_err = buf;
+  g_err_code = code;
+  {
+    std::lock_guard<std::mutex> g(g_last_err_mu);
+    g_last_err = buf;
+  }
   return code;
 }
 
@@ -135,6 +148,7 @@ struct Batch {
   bool staged = false;    // holds a staged blob (handle alive)
   bool ran = false;
   bool d2h_enqueued = false;  // enqueue_d2h ran for the last pass; fetch_batch only has to wait
+  uint64_t epoch = 0;         // topology epoch the batch was validated / sized against (set_topology bumps it)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {};
   std::vector<cudaEvent_t> it_ev;  // triples (before score, after score, after select) per pass
@@ -155,7 +169,7 @@ struct Batch {
   DevBuf<int> gsrc;
   long long aux_off = -1;        // word offset of the per-step geometry in h_in; -1: host-built plan
   int g_lo = 0;                  // first group of the GROUPS blob this plan covers
-  std::vector<int> grp_flags, grp_assign_off, grp_pending;
+  std::vector<int> grp_flags, grp_assign_off, grp_pending, grp_fixed;
   DevBuf<int> out;  // assign[total_r] | status[n] | domain[n] | dstar[n]
   PinBuf<int> h_in, h_out;
   ~Batch() {
@@ -172,6 +186,7 @@ struct rbgtopo_ctx {
   int sm_count = 148;
   int slab_lo = 0, slab_hi = 0, slab_stride = 0, lc = 1, chunk = 2048;
   std::shared_mutex topo_mu;  // update = exclusive, score calls = shared
+  uint64_t topo_epoch = 0;    // bumped by set_topology: handles staged against an older topology are stale
   std::mutex pool_mu;
   Topology topo;
   std::vector<std::unique_ptr<Batch>> batches;
@@ -180,11 +195,16 @@ struct rbgtopo_ctx {
   // snapshot refresh pipeline: update_nodes enqueues on topo_stream and returns; every batch
   // stream waits on topo_ready before it touches the snapshot
   cudaStream_t topo_stream = nullptr;
-  cudaEvent_t topo_ready = nullptr, ev_base_a = nullptr, ev_base_b = nullptr;
+  cudaEvent_t topo_ready = nullptr, ev_base_a = nullptr, ev_base_b = nullptr, fence_ev = nullptr;
   bool base_timing_pending = false;
-  PinBuf<int> h_free, h_owner;
+  // update_nodes staging, double buffered: the copy of update k leaves h_free[k & 1]; the host only
+  // waits for update k - 2's H2D (long finished) before overwriting it, not for the refresh chain
+  PinBuf<int> h_free[2], h_owner[2];
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  unsigned stage_idx = 0;
   std::mutex stat_mu;
   rbgtopo_timing last{};
+  std::vector<float> last_score_ms, last_select_ms;  // per pass, harvested by the last fetch (rbgtopo_last_pass_times)
   long long calls = 0, scores_total = 0, launches = 0;
 };
 
@@ -192,6 +212,7 @@ namespace {
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 constexpr size_t kFastSmemMax = 200 * 1024;
+constexpr int kMaxExactTerm = 1 << 24;  // pair weights and anchor counts above this can never satisfy spec §3.4
 // Switches, read once when the library loads.
 const bool kPerWavePlan = getenv("RBGTOPO_PER_WAVE_PLAN") != nullptr;  // one launch per wave instead of k_plan_group
 const int kEmitBlockSteps =
@@ -437,29 +458,37 @@ int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, Batc
     int rsum = 0;
     for (int p = 0; p < P; ++p) {
       if (roles[4 * p] < 1 || roles[4 * p + 1] < 0 || roles[4 * p + 1] > RBGTOPO_MAX_FREE ||
-          roles[4 * p + 2] < 0)
+          roles[4 * p + 2] < 0 || roles[4 * p + 2] > RBGTOPO_NEED_CAP)
         STEP_FAIL(RBGTOPO_EINVAL, "step %d role %d: count/demand/need", s, p);
       rsum += roles[4 * p];
     }
     if (rsum != R) STEP_FAIL(RBGTOPO_EINVAL, "step %d: role counts sum to %d, R=%d", s, rsum, R);
     if (!trusted) {
+      // flag words: only the documented bits (bit 4 of the step flags is the internal STEP_SKIP, bits
+      // 8.. of the role flags carry the group role index in plans); wave links belong to plans only
+      if (st[1] & ~(RBGTOPO_STEP_EXCLUSIVE | RBGTOPO_STEP_GANG)) STEP_FAIL(RBGTOPO_EINVAL, "step %d: unknown step flags 0x%x", s, st[1]);
+      for (int p = 0; p < P; ++p)
+        if (roles[4 * p + 3] & ~RBGTOPO_ROLE_EXCLUSIVE) STEP_FAIL(RBGTOPO_EINVAL, "step %d role %d: unknown role flags", s, p);
+      if (st[14] != 0 || st[15] != 0) STEP_FAIL(RBGTOPO_EINVAL, "step %d: reserved words 14/15 must be 0", s);
       for (int i = 0; i < P * Q; ++i)
-        if (pair[i] < 0) STEP_FAIL(RBGTOPO_EINVAL, "step %d: negative pair weight", s);
+        if (pair[i] < 0 || pair[i] > kMaxExactTerm) STEP_FAIL(RBGTOPO_EINVAL, "step %d: pair weight out of [0, 2^24]", s);
       for (int a = 0; a < na; ++a) {
         if (anc[3 * a] < 0 || anc[3 * a] >= T.n || anc[3 * a + 1] < 0 || anc[3 * a + 1] >= Q ||
-            anc[3 * a + 2] < 0)
+            anc[3 * a + 2] < 0 || anc[3 * a + 2] > kMaxExactTerm)
           STEP_FAIL(RBGTOPO_EINVAL, "step %d anchor %d out of range", s, a);
       }
       for (int i = 0; i < nc; ++i)
         if (con[2 * i] < 0 || con[2 * i] >= T.n || con[2 * i + 1] < 0 || con[2 * i + 1] > RBGTOPO_MAX_FREE)
           STEP_FAIL(RBGTOPO_EINVAL, "step %d consumed %d out of range", s, i);
     }
-    // exactness contract (spec §3.4), conservative: every anchor on one node
+    // exactness contract (spec §3.4), conservative: every anchor on one node.  Terms are bounded by
+    // 2^24 each and the sum saturates as soon as the bound is violated: no signed overflow.
+    const long long amax_limit = ((1LL << 24) + row_w - 1) / row_w;  // amax * row_w >= 2^24  <=>  amax >= limit
     for (int p = 0; p < P; ++p) {
       long long amax = (long long)roles[4 * p + 2] * RBGTOPO_F_CAP;
-      for (int a = 0; a < na; ++a) amax += (long long)pair[p * Q + anc[3 * a + 1]] * anc[3 * a + 2];
-      if (amax * row_w >= (1LL << 24))
-        STEP_FAIL(RBGTOPO_EINEXACT, "step %d role %d: max score bound %lld >= 2^24", s, p, amax * row_w);
+      for (int a = 0; a < na && amax < amax_limit; ++a) amax += (long long)pair[p * Q + anc[3 * a + 1]] * anc[3 * a + 2];
+      if (amax >= amax_limit)
+        STEP_FAIL(RBGTOPO_EINEXACT, "step %d role %d: max score bound >= 2^24 (anchor weight %lld x row weight %lld)", s, p, amax, row_w);
     }
     if (st[4] & 3) STEP_FAIL(RBGTOPO_EINVAL, "step %d: role_off must be a multiple of 4 words", s);
     if (st[15] < 0 || st[15] > na || (st[14] != 0 && (st[14] <= s || st[14] >= ns)))
@@ -569,6 +598,7 @@ int stage_into(rbgtopo_ctx* c, Batch* b, const int32_t* blob, int64_t words) {
   rc = reserve_batch_buffers(c, b);
   if (rc) return rc;
   b->m.h2d_words = (long long)in_words;
+  b->epoch = c->topo_epoch;
   CK(cudaStreamWaitEvent(s, c->topo_ready, 0));  // the snapshot refresh (if any) is complete
   CK(cudaEventRecord(b->ev[0], s));
   if (!in_place) memcpy(b->h_in.p, blob, (size_t)words * 4);
@@ -792,9 +822,10 @@ int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int3
   float x = 0.f;
   if (cudaEventElapsedTime(&x, b->ev[0], b->ev[1]) == cudaSuccess) tm.h2d_ms = x;
   float score = 0.f, sel = 0.f;
+  std::vector<float> pass_score, pass_sel;
   for (int it = 0; it < b->passes; ++it) {
-    if (cudaEventElapsedTime(&x, b->it_ev[3 * it], b->it_ev[3 * it + 1]) == cudaSuccess) score += x;
-    if (cudaEventElapsedTime(&x, b->it_ev[3 * it + 1], b->it_ev[3 * it + 2]) == cudaSuccess) sel += x;
+    if (cudaEventElapsedTime(&x, b->it_ev[3 * it], b->it_ev[3 * it + 1]) == cudaSuccess) { score += x; pass_score.push_back(x); }
+    if (cudaEventElapsedTime(&x, b->it_ev[3 * it + 1], b->it_ev[3 * it + 2]) == cudaSuccess) { sel += x; pass_sel.push_back(x); }
   }
   if (b->passes > 0) {
     tm.score_ms = score / b->passes;
@@ -815,16 +846,47 @@ int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int3
   b->untimed_or_timed_passes = 0;
   std::lock_guard<std::mutex> g(c->stat_mu);
   c->last = tm;
+  c->last_score_ms.swap(pass_score);
+  c->last_select_ms.swap(pass_sel);
   c->calls += 1;
   c->scores_total += m.scores * std::max(1, total_passes);
   return RBGTOPO_OK;
 }
 
-Batch* batch_of(rbgtopo_ctx* c, int handle) {
+// any_epoch: rbgtopo_release only — a handle staged against an older topology can still be released.
+Batch* batch_of(rbgtopo_ctx* c, int handle, bool any_epoch = false) {
   std::lock_guard<std::mutex> g(c->pool_mu);
   if (handle < 0 || handle >= (int)c->batches.size()) return nullptr;
   Batch* b = c->batches[handle].get();
-  return (b->in_use && b->staged) ? b : nullptr;
+  if (!(b->in_use && b->staged)) return nullptr;
+  if (!any_epoch && b->epoch != c->topo_epoch) return nullptr;  // sizes / offsets belong to the old topology
+  return b;
+}
+
+// Orders the snapshot writers behind everything already enqueued on the batch streams: the refresh
+// chain (topo_stream) must not rewrite free / owner / base / order while a batch enqueued by
+// run_staged / shard_* (asynchronous, lock released) still reads them.  Caller holds topo_mu
+// exclusively, so nothing new is enqueued meanwhile.  sync = also wait on the host (set_topology
+// frees and reallocates the buffers).
+int fence_batches(rbgtopo_ctx* c, bool sync) {
+  std::lock_guard<std::mutex> g(c->pool_mu);
+  if (c->use_ext_stream) {
+    if (sync) CK(cudaStreamSynchronize(c->ext_stream));
+    else {
+      CK(cudaEventRecord(c->fence_ev, c->ext_stream));
+      CK(cudaStreamWaitEvent(c->topo_stream, c->fence_ev, 0));
+    }
+  }
+  for (auto& b : c->batches) {
+    if (!b->in_use || !b->stream) continue;
+    if (sync) {
+      CK(cudaStreamSynchronize(b->stream));
+    } else {
+      CK(cudaEventRecord(b->ev[6], b->stream));
+      CK(cudaStreamWaitEvent(c->topo_stream, b->ev[6], 0));
+    }
+  }
+  return RBGTOPO_OK;
 }
 int handle_of(rbgtopo_ctx* c, Batch* b) {
   std::lock_guard<std::mutex> g(c->pool_mu);
@@ -841,12 +903,17 @@ extern "C" {
 int32_t rbgtopo_abi_version(void) { return RBGTOPO_ABI_VERSION; }
 
 int32_t rbgtopo_last_error(rbgtopo_ctx*, char* buf, int32_t len) {
+  std::string text = g_err;
+  if (text.empty()) {  // another OS thread made the failing call (goroutine migration)
+    std::lock_guard<std::mutex> g(g_last_err_mu);
+    text = g_last_err;
+  }
   if (buf && len > 0) {
-    int n = (int)std::min<size_t>(g_err.size(), (size_t)len - 1);
-    memcpy(buf, g_err.data(), n);
+    int n = (int)std::min<size_t>(text.size(), (size_t)len - 1);
+    memcpy(buf, text.data(), n);
     buf[n] = 0;
   }
-  return (int32_t)g_err.size();
+  return (int32_t)text.size();
 }
 
 int32_t rbgtopo_create(const rbgtopo_config* cfg, rbgtopo_ctx** out) {
@@ -874,6 +941,8 @@ int32_t rbgtopo_create(const rbgtopo_config* cfg, rbgtopo_ctx** out) {
   CK(cudaEventCreateWithFlags(&c->topo_ready, cudaEventDisableTiming));
   CK(cudaEventCreate(&c->ev_base_a));
   CK(cudaEventCreate(&c->ev_base_b));
+  CK(cudaEventCreateWithFlags(&c->fence_ev, cudaEventDisableTiming));
+  for (auto& e : c->stage_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CK(cudaFuncSetAttribute(k_select_assign_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
   CK(cudaFuncSetAttribute(k_shard_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
   CK(cudaFuncSetAttribute(k_plan_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
@@ -896,6 +965,8 @@ int32_t rbgtopo_destroy(rbgtopo_ctx* c) {
   if (c->topo_ready) cudaEventDestroy(c->topo_ready);
   if (c->ev_base_a) cudaEventDestroy(c->ev_base_a);
   if (c->ev_base_b) cudaEventDestroy(c->ev_base_b);
+  if (c->fence_ev) cudaEventDestroy(c->fence_ev);
+  for (auto& e : c->stage_ev) if (e) cudaEventDestroy(e);
   delete c;
   return RBGTOPO_OK;
 }
@@ -935,6 +1006,14 @@ int32_t rbgtopo_set_topology(rbgtopo_ctx* c, int32_t n, int64_t e, const int32_t
   std::unique_lock<std::shared_mutex> lk(c->topo_mu);
   CK(cudaSetDevice(c->cfg.device));
   Topology& T = c->topo;
+  // every batch already enqueued finishes before its snapshot buffers are freed / resized, and
+  // the handles staged so far become stale (their sizes and offsets belong to the old topology)
+  {
+    int frc = fence_batches(c, true);
+    if (frc) return frc;
+    CK(cudaStreamSynchronize(c->topo_stream));
+    c->topo_epoch += 1;
+  }
   T.valid = false;
   compute_slab(c, n);
   // base-kernel tiles
@@ -1006,26 +1085,38 @@ int32_t rbgtopo_set_topology(rbgtopo_ctx* c, int32_t n, int64_t e, const int32_t
 int32_t rbgtopo_update_nodes(rbgtopo_ctx* c, const int32_t* free_slots, const int32_t* owner,
                              uint64_t generation) {
   if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
-  std::unique_lock<std::shared_mutex> lk(c->topo_mu);  // no batch is in flight while we hold it
+  std::unique_lock<std::shared_mutex> lk(c->topo_mu);  // no call enqueues while we hold it ...
   Topology& T = c->topo;
   if (!T.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
   CK(cudaSetDevice(c->cfg.device));
   cudaStream_t s = c->topo_stream;
-  CK(cudaStreamSynchronize(s));  // the previous refresh no longer reads the pinned staging
+  {  // ... and what run_staged / shard_* already enqueued (asynchronously) reads the old snapshot first
+    int frc = fence_batches(c, false);
+    if (frc) return frc;
+  }
+  const unsigned sb = c->stage_idx++ & 1u;
+  CK(cudaEventSynchronize(c->stage_ev[sb]));  // the H2D copies of two updates ago have left this staging buffer
   if (free_slots) {
-    for (int i = 0; i < T.n; ++i)
-      if (free_slots[i] < 0 || free_slots[i] > RBGTOPO_MAX_FREE) return fail(RBGTOPO_EINVAL, "free[%d]", i);
-    CK(c->h_free.reserve((size_t)T.n));
-    memcpy(c->h_free.p, free_slots, (size_t)T.n * 4);
-    CK(cudaMemcpyAsync(T.free_.p, c->h_free.p, (size_t)T.n * 4, cudaMemcpyHostToDevice, s));
+    CK(c->h_free[sb].reserve((size_t)T.n));
+    // validate while copying (one pass over the caller's array)
+    int* const dst = c->h_free[sb].p;
+    int bad = -1;
+    for (int i = 0; i < T.n; ++i) {
+      const int f = free_slots[i];
+      dst[i] = f;
+      if ((unsigned)f > (unsigned)RBGTOPO_MAX_FREE && bad < 0) bad = i;
+    }
+    if (bad >= 0) return fail(RBGTOPO_EINVAL, "free[%d]", bad);
   }
   if (owner) {
     for (int d = 0; d < T.n_domains; ++d)
       if (owner[d] < -1) return fail(RBGTOPO_EINVAL, "domain_owner[%d]", d);
-    CK(c->h_owner.reserve((size_t)T.n_domains));
-    memcpy(c->h_owner.p, owner, (size_t)T.n_domains * 4);
-    CK(cudaMemcpyAsync(T.owner.p, c->h_owner.p, (size_t)T.n_domains * 4, cudaMemcpyHostToDevice, s));
+    CK(c->h_owner[sb].reserve((size_t)T.n_domains));
+    memcpy(c->h_owner[sb].p, owner, (size_t)T.n_domains * 4);
   }
+  if (free_slots) CK(cudaMemcpyAsync(T.free_.p, c->h_free[sb].p, (size_t)T.n * 4, cudaMemcpyHostToDevice, s));
+  if (owner) CK(cudaMemcpyAsync(T.owner.p, c->h_owner[sb].p, (size_t)T.n_domains * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaEventRecord(c->stage_ev[sb], s));
   T.generation = generation;
   // asynchronous: the refresh (prep, base SpMV, order sort) overlaps the caller's next host
   // work; every batch stream waits on topo_ready before reading the snapshot
@@ -1153,7 +1244,7 @@ static int32_t place_groups_slow(rbgtopo_ctx* c, const int32_t* gb, int64_t word
       const int P = (int)r.w_role.size();
       int32_t st[RBGTOPO_STEP_WORDS] = {0};
       st[0] = r.rec[0];
-      st[1] = r.rec[1];
+      st[1] = r.rec[1] & (RBGTOPO_STEP_EXCLUSIVE | RBGTOPO_STEP_GANG);  // as build_plan / k_expand_plan
       st[2] = (r.rec[1] & RBGTOPO_STEP_EXCLUSIVE) ? r.fixed_domain : -1;
       st[3] = P;
       while (blob.size() & 3) blob.push_back(0);  // role records are read as 16-byte vectors
@@ -1167,7 +1258,7 @@ static int32_t place_groups_slow(rbgtopo_ctx* c, const int32_t* gb, int64_t word
         blob.push_back(r.w_count[p]);
         blob.push_back(r.roles[4 * ri + 2]);
         blob.push_back(need);
-        blob.push_back(r.roles[4 * ri + 3]);
+        blob.push_back(r.roles[4 * ri + 3] & RBGTOPO_ROLE_EXCLUSIVE);
       }
       st[5] = r.q;
       st[6] = (int32_t)blob.size();
@@ -1328,6 +1419,7 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
   static thread_local std::vector<int> wv_off, step_flat;
   wv_off.assign((size_t)ng + 1, 0);
   b->grp_flags.resize(ng);
+  b->grp_fixed.resize(ng);
   b->grp_assign_off.resize(ng);
   b->grp_pending.resize(ng);
 #define GROUP_FAIL(code, ...) return report ? fail(code, __VA_ARGS__) : (int)(code)
@@ -1351,11 +1443,14 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
     }
     if (pend > 0x3FFFFFFFLL) GROUP_FAIL(RBGTOPO_ELIMIT, "group %d: pending replicas", g);
     if (rec[0] < 0 || rec[2] < -1 || rec[2] >= n_domains) GROUP_FAIL(RBGTOPO_EINVAL, "group %d: gid / fixed_domain", g);
+    if (rec[1] & ~(RBGTOPO_STEP_EXCLUSIVE | RBGTOPO_STEP_GANG)) GROUP_FAIL(RBGTOPO_EINVAL, "group %d: unknown flags 0x%x", g, rec[1]);
+    for (int i = 0; i < q; ++i)
+      if (roles[4 * i + 3] & ~RBGTOPO_ROLE_EXCLUSIVE) GROUP_FAIL(RBGTOPO_EINVAL, "group %d role %d: unknown role flags", g, i);
     for (int i = 0; i < q * q; ++i)
-      if (gb[rec[5] + i] < 0) GROUP_FAIL(RBGTOPO_EINVAL, "group %d: negative pair weight", g);
+      if (gb[rec[5] + i] < 0 || gb[rec[5] + i] > kMaxExactTerm) GROUP_FAIL(RBGTOPO_EINVAL, "group %d: pair weight out of [0, 2^24]", g);
     for (int a = 0; a < rec[6]; ++a) {
       const int32_t* an = gb + rec[7] + 3 * a;
-      if (an[0] < 0 || an[0] >= n_nodes || an[1] < 0 || an[1] >= q || an[2] < 0)
+      if (an[0] < 0 || an[0] >= n_nodes || an[1] < 0 || an[1] >= q || an[2] < 0 || an[2] > kMaxExactTerm)
         GROUP_FAIL(RBGTOPO_EINVAL, "group %d anchor %d out of range", g, a);
     }
     g_pend[g] = (int)pend;
@@ -1374,6 +1469,7 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
     const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
     if (rec[8] != pacc || rec[9] != g_pend[g]) return fail(RBGTOPO_EINVAL, "group %d: bad assign_off/n_pending", g);
     b->grp_flags[g] = rec[1];
+    b->grp_fixed[g] = rec[2];
     b->grp_assign_off[g] = (int)pacc;
     pacc += g_pend[g];
     if (pacc > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "pending replicas exceed 2^31");
@@ -1592,6 +1688,7 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
   g_pc.resize((size_t)ng);
   g_first.resize((size_t)ng);
   b->grp_flags.resize(ng);
+  b->grp_fixed.resize(ng);
   b->grp_assign_off.resize(ng);
   b->grp_pending.resize(ng);
   int* const g_pend = b->grp_pending.data();
@@ -1618,12 +1715,15 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
     }
     if (pend > 0x3FFFFFFFLL) GROUP_FAIL(RBGTOPO_ELIMIT, "group %d: pending replicas", g);
     if (rec[0] < 0 || rec[2] < -1 || rec[2] >= n_domains) GROUP_FAIL(RBGTOPO_EINVAL, "group %d: gid / fixed_domain", g);
+    if (rec[1] & ~(RBGTOPO_STEP_EXCLUSIVE | RBGTOPO_STEP_GANG)) GROUP_FAIL(RBGTOPO_EINVAL, "group %d: unknown flags 0x%x", g, rec[1]);
+    for (int i = 0; i < q; ++i)
+      if (roles[4 * i + 3] & ~RBGTOPO_ROLE_EXCLUSIVE) GROUP_FAIL(RBGTOPO_EINVAL, "group %d role %d: unknown role flags", g, i);
     for (int i = 0; i < q * q; ++i)
-      if (gb[rec[5] + i] < 0) GROUP_FAIL(RBGTOPO_EINVAL, "group %d: negative pair weight", g);
+      if (gb[rec[5] + i] < 0 || gb[rec[5] + i] > kMaxExactTerm) GROUP_FAIL(RBGTOPO_EINVAL, "group %d: pair weight out of [0, 2^24]", g);
     long long pc = 0;  // closed neighbourhoods of the scheduled pods
     for (int a = 0; a < rec[6]; ++a) {
       const int32_t* an = gb + rec[7] + 3 * a;
-      if (an[0] < 0 || an[0] >= n_nodes || an[1] < 0 || an[1] >= q || an[2] < 0)
+      if (an[0] < 0 || an[0] >= n_nodes || an[1] < 0 || an[1] >= q || an[2] < 0 || an[2] > kMaxExactTerm)
         GROUP_FAIL(RBGTOPO_EINVAL, "group %d anchor %d out of range", g, a);
       pc += degp1 ? degp1[an[0]] : 1;
     }
@@ -1649,6 +1749,7 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
     const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)(g_lo + g) * RBGTOPO_GROUP_WORDS;
     if (rec[8] != pacc || rec[9] != g_pend[g]) return fail(RBGTOPO_EINVAL, "group %d: bad assign_off/n_pending", g);
     b->grp_flags[g] = rec[1];
+    b->grp_fixed[g] = rec[2];
     b->grp_assign_off[g] = (int)pacc;
     pacc += g_pend[g];
     if (pacc > 0x3FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "pending replicas exceed 2^30");
@@ -1714,10 +1815,11 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
     const int32_t* roles = gb + rec[4];
     const int32_t* pair = gb + rec[5];
     long long anch_w[RBGTOPO_MAX_GROUP_ROLES];  // sum over scheduled pods of pair[ri][role]·count
+    const long long sat = 1LL << 40;  // far above any admissible bound, far below overflow
     for (int ri = 0; ri < q; ++ri) {
       long long acc = 0;
-      for (int a = 0; a < na; ++a) acc += (long long)pair[ri * q + gb[rec[7] + 3 * a + 1]] * gb[rec[7] + 3 * a + 2];
-      anch_w[ri] = acc;
+      for (int a = 0; a < na && acc < sat; ++a) acc += (long long)pair[ri * q + gb[rec[7] + 3 * a + 1]] * gb[rec[7] + 3 * a + 2];
+      anch_w[ri] = std::min(acc, sat);
     }
     int placed[RBGTOPO_MAX_GROUP_ROLES] = {0};
     int i0 = 0, s = -1, rc = RBGTOPO_OK;
@@ -1732,12 +1834,12 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
         int need = 0;
         long long amax = anch_w[ri];
         for (int j = 0; j < q; ++j) {
-          if (pair[ri * q + j] > 0) need += roles[4 * j + 1] - placed[j];
-          amax += (long long)pair[ri * q + j] * placed[j];
+          if (pair[ri * q + j] > 0) need = (int)std::min<long long>((long long)need + roles[4 * j + 1] - placed[j], 1 << 30);
+          amax = std::min(amax + (long long)pair[ri * q + j] * placed[j], sat);  // each term < 2^24 * 2^30
         }
         amax += (long long)std::min(need, RBGTOPO_NEED_CAP) * RBGTOPO_F_CAP;
-        if (amax * row_w >= (1LL << 24)) {
-          rc = report ? fail(RBGTOPO_EINEXACT, "group %d wave %d role %d: max score bound %lld >= 2^24", g, w, ri, amax * row_w)
+        if (amax >= ((1LL << 24) + row_w - 1) / row_w) {
+          rc = report ? fail(RBGTOPO_EINEXACT, "group %d wave %d role %d: max score bound >= 2^24 (anchor weight %lld x row weight %lld)", g, w, ri, amax, row_w)
                       : (int)RBGTOPO_EINEXACT;
           return;
         }
@@ -1853,6 +1955,7 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, int g
   CK(b->blob.reserve((size_t)plan_words + tail_words));
   rc = reserve_batch_buffers(c, b);
   if (rc) return rc;
+  b->epoch = c->topo_epoch;
   CK(cudaStreamWaitEvent(s, c->topo_ready, 0));  // the snapshot refresh (if any) is complete
   CK(cudaEventRecord(b->ev[0], s));
   CK(cudaMemcpyAsync(b->gsrc.p, hin, src_words * 4, cudaMemcpyHostToDevice, s));
@@ -1919,6 +2022,8 @@ void plan_results(const Batch* b, int32_t* assign, int32_t* status, int32_t* dom
       memcpy(assign + b->grp_assign_off[x[0] - b->g_lo] + x[7], a + x[4], (size_t)R * 4);
     }
   std::vector<int> gstat(ng, 0), gdom(ng, -1);
+  for (int g = 0; g < ng; ++g)  // an exclusive group confirms the domain it already occupies (as the host loop)
+    if (b->grp_flags[g] & RBGTOPO_STEP_EXCLUSIVE) gdom[g] = b->grp_fixed[g];
   for (int s = 0; s < m.n_steps; ++s) {
     const int g = b->step_group[s];
     gstat[g] = std::max(gstat[g], st[s]);
@@ -2124,15 +2229,16 @@ int32_t rbgtopo_run_staged(rbgtopo_ctx* c, int32_t handle, int32_t iters) {
   if (iters < 1 || iters > 4096) return fail(RBGTOPO_EINVAL, "iters");
   std::shared_lock<std::shared_mutex> lk(c->topo_mu);
   Batch* b = batch_of(c, handle);
-  if (!b) return fail(RBGTOPO_EINVAL, "bad handle %d", handle);
+  if (!b) return fail(RBGTOPO_EINVAL, "bad or stale handle %d", handle);
   CK(cudaSetDevice(c->cfg.device));
   return run_batch(c, b, iters);
 }
 
 int32_t rbgtopo_fetch(rbgtopo_ctx* c, int32_t handle, int32_t* assign, int32_t* status, int32_t* domain) {
   if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
+  std::shared_lock<std::shared_mutex> lk(c->topo_mu);
   Batch* b = batch_of(c, handle);
-  if (!b || !b->ran) return fail(RBGTOPO_EINVAL, "handle %d has no results", handle);
+  if (!b || !b->ran) return fail(RBGTOPO_EINVAL, "handle %d has no results (or is stale: the topology changed)", handle);
   CK(cudaSetDevice(c->cfg.device));
   if (b->wave_begin.empty()) return fetch_batch(c, b, assign, status, domain);
   int rc = fetch_batch(c, b, nullptr, nullptr, nullptr);
@@ -2144,8 +2250,9 @@ int32_t rbgtopo_fetch(rbgtopo_ctx* c, int32_t handle, int32_t* assign, int32_t* 
 
 int32_t rbgtopo_release(rbgtopo_ctx* c, int32_t handle) {
   if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
-  Batch* b = batch_of(c, handle);
-  if (!b) return fail(RBGTOPO_EINVAL, "bad handle %d", handle);
+  std::shared_lock<std::shared_mutex> lk(c->topo_mu);
+  Batch* b = batch_of(c, handle, true);
+  if (!b) return fail(RBGTOPO_EINVAL, "bad or stale handle %d", handle);
   cudaSetDevice(c->cfg.device);
   cudaStreamSynchronize(stream_of(c, b));
   release_batch(c, b);
@@ -2154,8 +2261,9 @@ int32_t rbgtopo_release(rbgtopo_ctx* c, int32_t handle) {
 
 int32_t rbgtopo_read_scores(rbgtopo_ctx* c, int32_t handle, int32_t row, float* out, int32_t out_len) {
   if (!c || !out) return fail(RBGTOPO_EINVAL, "null argument");
+  std::shared_lock<std::shared_mutex> lk(c->topo_mu);
   Batch* b = batch_of(c, handle);
-  if (!b || !b->ran) return fail(RBGTOPO_EINVAL, "handle %d has no results", handle);
+  if (!b || !b->ran) return fail(RBGTOPO_EINVAL, "handle %d has no results (or is stale: the topology changed)", handle);
   const int slab = c->slab_hi - c->slab_lo;
   if (row < 0 || row >= b->m.total_r || out_len < slab) return fail(RBGTOPO_EINVAL, "row/out_len");
   CK(cudaSetDevice(c->cfg.device));
@@ -2166,8 +2274,9 @@ int32_t rbgtopo_read_scores(rbgtopo_ctx* c, int32_t handle, int32_t row, float* 
 
 int32_t rbgtopo_read_topk(rbgtopo_ctx* c, int32_t handle, int32_t rolerow, uint64_t* out, int32_t k) {
   if (!c || !out) return fail(RBGTOPO_EINVAL, "null argument");
+  std::shared_lock<std::shared_mutex> lk(c->topo_mu);
   Batch* b = batch_of(c, handle);
-  if (!b || !b->ran) return fail(RBGTOPO_EINVAL, "handle %d has no results", handle);
+  if (!b || !b->ran) return fail(RBGTOPO_EINVAL, "handle %d has no results (or is stale: the topology changed)", handle);
   if (rolerow < 0 || rolerow >= b->m.total_p || k < 1 || k > KS) return fail(RBGTOPO_EINVAL, "rolerow/k");
   CK(cudaSetDevice(c->cfg.device));
   CK(cudaStreamSynchronize(stream_of(c, b)));
@@ -2216,8 +2325,9 @@ void wave_table(Batch* b, const WaveRange& w, int* CAP, int* HT) {
 
 int32_t rbgtopo_shard_waves(rbgtopo_ctx* c, int32_t handle, int32_t* n_waves) {
   if (!c || !n_waves) return fail(RBGTOPO_EINVAL, "null argument");
+  std::shared_lock<std::shared_mutex> lk(c->topo_mu);
   Batch* b = batch_of(c, handle);
-  if (!b) return fail(RBGTOPO_EINVAL, "bad handle %d", handle);
+  if (!b) return fail(RBGTOPO_EINVAL, "bad or stale handle %d", handle);
   *n_waves = b->wave_begin.empty() ? 1 : (int)b->wave_begin.size() - 1;
   return RBGTOPO_OK;
 }
@@ -2226,7 +2336,7 @@ int32_t rbgtopo_shard_wave_score(rbgtopo_ctx* c, int32_t handle, int32_t wave, v
   if (!c || !keys_dev || !keys_bytes) return fail(RBGTOPO_EINVAL, "null argument");
   std::shared_lock<std::shared_mutex> lk(c->topo_mu);
   Batch* b = batch_of(c, handle);
-  if (!b) return fail(RBGTOPO_EINVAL, "bad handle %d", handle);
+  if (!b) return fail(RBGTOPO_EINVAL, "bad or stale handle %d", handle);
   WaveRange w;
   int rc = wave_range(c, b, wave, &w);
   if (rc) return rc;
@@ -2277,7 +2387,7 @@ int32_t rbgtopo_shard_wave_merge(rbgtopo_ctx* c, int32_t handle, int32_t wave, c
   if (!c || !keys_all || !need_pass2 || !keys2_dev || !keys2_bytes) return fail(RBGTOPO_EINVAL, "null argument");
   std::shared_lock<std::shared_mutex> lk(c->topo_mu);
   Batch* b = batch_of(c, handle);
-  if (!b) return fail(RBGTOPO_EINVAL, "bad handle %d", handle);
+  if (!b) return fail(RBGTOPO_EINVAL, "bad or stale handle %d", handle);
   WaveRange w;
   int rc = wave_range(c, b, wave, &w);
   if (rc) return rc;
@@ -2327,7 +2437,7 @@ int32_t rbgtopo_shard_wave_assign(rbgtopo_ctx* c, int32_t handle, int32_t wave, 
   if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
   std::shared_lock<std::shared_mutex> lk(c->topo_mu);
   Batch* b = batch_of(c, handle);
-  if (!b) return fail(RBGTOPO_EINVAL, "bad handle %d", handle);
+  if (!b) return fail(RBGTOPO_EINVAL, "bad or stale handle %d", handle);
   WaveRange w;
   int rc = wave_range(c, b, wave, &w);
   if (rc) return rc;
@@ -2391,6 +2501,18 @@ int32_t rbgtopo_last_timing(rbgtopo_ctx* c, rbgtopo_timing* out) {
   std::lock_guard<std::mutex> g(c->stat_mu);
   *out = c->last;
   out->base_ms = c->topo.base_ms;
+  return RBGTOPO_OK;
+}
+
+int32_t rbgtopo_last_pass_times(rbgtopo_ctx* c, float* score_ms, float* select_ms, int32_t cap, int32_t* n_passes) {
+  if (!c || !n_passes || cap < 0) return fail(RBGTOPO_EINVAL, "null argument");
+  std::lock_guard<std::mutex> g(c->stat_mu);
+  const int n = (int)std::min(c->last_score_ms.size(), c->last_select_ms.size());
+  *n_passes = n;
+  for (int i = 0; i < std::min(n, cap); ++i) {
+    if (score_ms) score_ms[i] = c->last_score_ms[i];
+    if (select_ms) select_ms[i] = c->last_select_ms[i];
+  }
   return RBGTOPO_OK;
 }
 

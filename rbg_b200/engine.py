@@ -10,6 +10,26 @@ from . import _lib
 from .blob import blob_totals
 
 
+def plan_steps(groups_blob, n_nodes: int = 4096, n_domains: int = 1) -> np.ndarray:
+    """Host-only: the step geometry of the multi-wave plan rbgtopo_place_groups / _stage_groups
+    compile from a GROUPS blob (rbgtopo_plan_describe).  One row of 8 ints per step, wave-major:
+    group, wave, section offset, section end, first replica row, first role row, next step, i0."""
+    lib = _lib.load()
+    gb = np.ascontiguousarray(groups_blob, dtype=np.int32)
+    ns, nw, pw = C.c_int32(), C.c_int32(), C.c_int64()
+    i32 = _lib.i32p
+    rc = lib.rbgtopo_plan_describe(gb.ctypes.data_as(i32), len(gb), n_nodes, n_domains, None, 0, None, 0,
+                                   C.byref(ns), C.byref(nw), C.byref(pw))
+    if rc != 0:
+        raise RuntimeError(f"rbgtopo_plan_describe: {rc}")
+    out = np.zeros(max(ns.value, 1) * 8, dtype=np.int32)
+    rc = lib.rbgtopo_plan_describe(gb.ctypes.data_as(i32), len(gb), n_nodes, n_domains, None, 0,
+                                   out.ctypes.data_as(i32), ns.value, C.byref(ns), C.byref(nw), C.byref(pw))
+    if rc != 0:
+        raise RuntimeError(f"rbgtopo_plan_describe: {rc}")
+    return out[:ns.value * 8].reshape(-1, 8)
+
+
 class RbgTopoError(RuntimeError):
     def __init__(self, code: int, text: str):
         super().__init__(f"rbgtopo error {code}: {text}")
@@ -189,6 +209,15 @@ class TopoPlacer:
         t = _lib.Timing()
         self._check(self.lib.rbgtopo_last_timing(self._h, C.byref(t)))
         return {k: getattr(t, k) for k, _ in _lib.Timing._fields_}
+
+    def last_pass_times(self, cap: int = 4096):
+        """(score_ms[], select_ms[]) of the passes the last fetch harvested."""
+        a = np.zeros(cap, dtype=np.float32)
+        b = np.zeros(cap, dtype=np.float32)
+        n = C.c_int32()
+        self._check(self.lib.rbgtopo_last_pass_times(self._h, _p(a, _lib.f32p), _p(b, _lib.f32p), cap, C.byref(n)))
+        k = min(n.value, cap)
+        return a[:k].copy(), b[:k].copy()
 
     def stats(self) -> dict:
         g, c, s, k = C.c_uint64(), C.c_int64(), C.c_int64(), C.c_int64()

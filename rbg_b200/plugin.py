@@ -401,11 +401,14 @@ class B200TopoPodGroupManager:
         p = (self.reconcile_pod_groups_by_waves if by_waves else self.reconcile_pod_groups)([step])[0]
         out = [Placement(p.status, {}, p.domain, 0) for _ in tg]
         names = sorted((r.name for r in rbg.roles), key=len, reverse=True)
+        spec_replicas = {r.name: r.replicas for r in rbg.roles}
         n_nodes = self.placer.n_nodes
         for key, node in p.nodes.items():
             stem, ordinal = key[len(rbg.name) + 1:key.rfind("-")], int(key[key.rfind("-") + 1:])
             role = next(nm for nm in names if nm == stem)
-            k = next(i for i, t in enumerate(tg) if ordinal < t.get(role, 0))
+            # a role no ScalingRule paces is created whole by the current reconcile (its target is the
+            # spec's replica count in every batch): its replicas belong to batch 0
+            k = next((i for i, t in enumerate(tg) if ordinal < t.get(role, spec_replicas[role])), 0)
             out[k].nodes[key] = node
             out[k].scores += n_nodes
         return out

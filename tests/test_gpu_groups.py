@@ -207,3 +207,46 @@ def test_plan_variants_in_a_subprocess(var):
         cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "passed" in r.stdout
+
+
+def test_bench_shape_plan_parity():
+    """The plan bench.py times (cfg3: 1 024 mooncake RBGs x 10 000 nodes, all 3 waves) against the
+    CPU oracle's wave loop: dense matrix bits of every replica row of 128 sampled groups, and the
+    assignment / status / domain of those groups — the checker bench.py itself runs before timing."""
+    import bench
+    from gpu_util import new_engine
+    n, groups = 10000, 1024
+    topo = synth.make_topology(n, seed=0, tiers=4, samples_per_tier=5)
+    specs = bench.fleet_spec("mooncake", groups, n)
+    eng = new_engine(topo)
+    gblob, _ = B200TopoPodGroupManager(eng).groups_blob(bench.to_plugin(specs))
+    h = eng.stage_groups(gblob)
+    eng.run_staged(h, 1)
+    fetched = eng.fetch(h)
+    sample = sorted(set(int(i) for i in np.linspace(0, groups - 1, 128)))
+    par = bench.parity_check(eng, topo, specs, gblob, h, fetched, sample, 0, n, 8)
+    assert par["ok"] and par["rows_checked"] == 128 * 7 and par["waves"] == 3, par
+    # the whole fleet's placements through the host-buffer entry point equal the staged plan's
+    a, s, d = eng.place_groups(gblob)
+    assert np.array_equal(a, fetched[0]) and np.array_equal(s, fetched[1]) and np.array_equal(d, fetched[2])
+    eng.release(h)
+    eng.close()
+
+
+def test_exclusive_group_with_nothing_pending_confirms_its_domain():
+    """plan path and host loop agree on the result contract — an exclusive group that
+    already occupies a domain and has no pending replica reports that domain."""
+    from gpu_util import new_engine
+    topo = synth.make_topology(512, seed=3, tiers=2)
+    eng = new_engine(topo)
+    mgr = B200TopoPodGroupManager(eng)
+    ann = {EXCLUSIVE_TOPOLOGY_KEY: "topology.kubernetes.io/nvlink-domain"}
+    idle = RoleBasedGroup("default", "idle", [RoleSpec("a", 2, (), 1)], annotations=ann, gid=5, current={"a": 2},
+                          placed=[("a", 16), ("a", 17)], exclusive_domain=2)
+    busy = RoleBasedGroup("default", "busy", [RoleSpec("a", 3, (), 1)], annotations=ann, gid=6, current={"a": 1},
+                          placed=[("a", 40)], exclusive_domain=5)
+    got = mgr.reconcile_pod_groups([idle, busy])
+    ref = _oracle_manager(topo).reconcile_pod_groups_by_waves([idle, busy])
+    assert got[0].domain == 2 and got[0].nodes == {} and got[0].status == 0
+    assert got[1].domain == ref[1].domain == 5 and got[1].nodes == ref[1].nodes
+    eng.close()

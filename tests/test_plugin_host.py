@@ -176,3 +176,20 @@ def test_coordination_aware_batching_places_the_next_batch_ahead():
     both = RoleBasedGroup("ns", "pd", rbg.roles, gid=1, targets=batches[1])
     want = B200TopoPodGroupManager(OraclePlacer(topo)).reconcile_pod_groups_by_waves([both])[0]
     assert {**first.nodes, **second.nodes} == want.nodes
+
+
+def test_reconcile_ahead_with_a_role_no_rule_paces():
+    """A role outside every ScalingRule is created whole by the current reconcile (its target is the
+    spec's replica count): its replicas belong to batch 0, the paced roles are split by ordinal."""
+    from rbg_b200.plugin import ScalingRule
+    topo = synth.make_topology(512, seed=5, tiers=2)
+    mgr = B200TopoPodGroupManager(OraclePlacer(topo))
+    rbg = RoleBasedGroup("ns", "pd", [RoleSpec("prefill", 40, (), 1), RoleSpec("decode", 20, (), 1),
+                                      RoleSpec("router", 2, (), 1)], gid=3,
+                         scaling_rules=[ScalingRule(["prefill", "decode"], "25%", "OrderScheduled")])
+    first, second = mgr.reconcile_ahead(rbg, 2, by_waves=True)
+    assert "pd-router-0" in first.nodes and "pd-router-1" in first.nodes
+    assert not any(k.startswith("pd-router-") for k in second.nodes)
+    assert sum(k.startswith("pd-prefill-") for k in first.nodes) == 10
+    assert sum(k.startswith("pd-prefill-") for k in second.nodes) == 10
+    assert len(first.nodes) + len(second.nodes) == 2 + 20 + 10
