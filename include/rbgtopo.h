@@ -361,6 +361,21 @@ int32_t rbgtopo_next_rolling_target(int32_t max_skew_percent, int32_t n_roles,
                                     const int32_t* ready,
                                     int32_t* rolling_target);
 
+/* CalculatePartitionReplicas, pkg/utils/utils.go:139-162.  has_partition = 0: nil partition;
+ * is_percent: the partition is the string "<value>%"; replicas < 0 = nil replicas pointer. */
+int32_t rbgtopo_partition_replicas(int32_t has_partition, int32_t is_percent, int32_t value,
+                                   int32_t replicas, int32_t* out);
+
+/* ParseIntStrAsNonZero, pkg/utils/utils.go:177-185. */
+int32_t rbgtopo_intstr_non_zero(int32_t is_percent, int32_t value, int32_t replicas,
+                                int32_t* out);
+
+/* mergeStrategyRollingUpdate, rolebasedgroup_controller.go:1284-1314, for one role present in
+ * both maps.  Strategy = 6 ints: maxUnavailable (has, is_percent, value), partition (has,
+ * is_percent, value).  out = the merged strategy. */
+int32_t rbgtopo_merge_rolling_update(const int32_t* strategy_a, const int32_t* strategy_b,
+                                     int32_t* out);
+
 /* ---- host-only inspection of the multi-wave plan (no GPU needed) ----------- *
  * The step geometry rbgtopo_place_groups / rbgtopo_stage_groups derive from a
  * GROUPS blob — which wave every pending replica is placed in, how the waves of

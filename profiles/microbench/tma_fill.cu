@@ -58,52 +58,66 @@ __global__ void __launch_bounds__(128) k_tma_fill(float* __restrict__ out, const
   if (tid == 0) bulk_wait_read<0>();
 }
 
-// Per-WARP workers: every warp takes (tile, quarter) items from the queue on its own, keeps a private
-// ring of STAGES x 2 KB in shared memory and issues its own 2 KB bulk stores (lane 0) — no block
-// barrier anywhere, only __syncwarp.  This is the structure the dense-matrix kernel would use.
-template <int STAGES>
-__global__ void __launch_bounds__(256) k_tma_fill_warp(float* __restrict__ out, const float* __restrict__ base, int tiles, int reps,
+// Per-WARP workers, shaped like the dense-matrix kernel: an item = a sub-chunk of SUB nodes x a block
+// of GT role rows ("tiles").  The warp loads the sub-chunk's node operands into registers ONCE
+// (SUB/32 floats per lane), prefetches the index of its next item, then per role row only
+// computes from registers, writes its private 2 KB stage (ring of STAGES), and lane 0 issues `reps`
+// bulk stores.  No block barrier anywhere, only __syncwarp.
+template <int STAGES, int SUB>
+__global__ void __launch_bounds__(512) k_tma_fill_warp(float* __restrict__ out, const float* __restrict__ base, int tiles, int reps,
                                                        int* __restrict__ counter) {
   extern __shared__ __align__(128) float smem[];
-  constexpr int SUB = 512;  // floats per item (2 KB)
+  constexpr int GT = 8;             // role rows per item
+  constexpr int V = SUB / 128;      // float4 per lane
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* ring = smem + (size_t)warp * STAGES * SUB;
-  const int items = tiles * (TILE / SUB);
+  const int subs = TILE / SUB;
+  const int items = (tiles / GT) * subs;
   int it = 0;
-  while (true) {
-    int t = 0;
-    if (lane == 0) {
-      t = atomicAdd(counter, 1);
-      bulk_wait_read<STAGES - 1>();
-    }
-    t = __shfl_sync(0xFFFFFFFFu, t, 0);
-    if (t >= items) break;
-    const int tile = t / (TILE / SUB), q = t % (TILE / SUB);
-    float* st = ring + (size_t)(it % STAGES) * SUB;
-    const float need = (float)(tile & 7);
+  int next = 0;
+  if (lane == 0) next = atomicAdd(counter, 1);
+  next = __shfl_sync(0xFFFFFFFFu, next, 0);
+  while (next < items) {
+    const int t = next;
+    if (lane == 0) next = atomicAdd(counter, 1);  // in flight during this item
+    const int blk = t / subs, q = t % subs;
+    float4 b[V];
 #pragma unroll
-    for (int j = 0; j < SUB / 128; ++j) {
-      const int i = lane + 32 * j;
-      float4 b = __ldg(reinterpret_cast<const float4*>(base) + ((tile & 3) * (TILE / 4) + q * (SUB / 4) + i));
-      b.x *= need; b.y *= need; b.z *= need; b.w *= need;
-      reinterpret_cast<float4*>(st)[i] = b;
+    for (int j = 0; j < V; ++j)
+      b[j] = __ldg(reinterpret_cast<const float4*>(base) + ((blk & 3) * (TILE / 4) + q * (SUB / 4) + lane + 32 * j));
+    for (int g = 0; g < GT; ++g) {
+      const int tile = blk * GT + g;
+      if (lane == 0) bulk_wait_read<STAGES - 1>();
+      __syncwarp();
+      float* st = ring + (size_t)(it % STAGES) * SUB;
+      const float need = (float)(tile & 7);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float4 o;
+        o.x = b[j].x >= 0.f ? need * b[j].x : -1.f;
+        o.y = b[j].y >= 0.f ? need * b[j].y : -1.f;
+        o.z = b[j].z >= 0.f ? need * b[j].z : -1.f;
+        o.w = b[j].w >= 0.f ? need * b[j].w : -1.f;
+        reinterpret_cast<float4*>(st)[lane + 32 * j] = o;
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        float* dst = out + (size_t)tile * reps * TILE + q * SUB;
+        for (int r = 0; r < reps; ++r) bulk_s2g(dst + (size_t)r * TILE, st, SUB * 4);
+        bulk_commit();
+      }
+      ++it;
     }
-    fence_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      float* dst = out + (size_t)tile * reps * TILE + q * SUB;
-      for (int r = 0; r < reps; ++r) bulk_s2g(dst + (size_t)r * TILE, st, SUB * 4);
-      bulk_commit();
-    }
-    ++it;
+    next = __shfl_sync(0xFFFFFFFFu, next, 0);
   }
   if (lane == 0) bulk_wait_read<0>();
 }
 
-template <int STAGES>
+template <int STAGES, int SUB>
 float run_tma_warp(float* out, const float* base, int tiles, int reps, int* ctr, int grid, int threads, int iters) {
-  const int smem = (threads / 32) * STAGES * 2048;
-  cudaFuncSetAttribute(k_tma_fill_warp<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int smem = (threads / 32) * STAGES * SUB * 4;
+  cudaFuncSetAttribute(k_tma_fill_warp<STAGES, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaEvent_t a, b;
   cudaEventCreate(&a);
   cudaEventCreate(&b);
@@ -111,13 +125,14 @@ float run_tma_warp(float* out, const float* base, int tiles, int reps, int* ctr,
   for (int i = 0; i < iters; ++i) {
     cudaMemsetAsync(ctr, 0, 4);
     cudaEventRecord(a);
-    k_tma_fill_warp<STAGES><<<grid, threads, smem>>>(out, base, tiles, reps, ctr);
+    k_tma_fill_warp<STAGES, SUB><<<grid, threads, smem>>>(out, base, tiles, reps, ctr);
     cudaEventRecord(b);
     cudaEventSynchronize(b);
     float ms;
     cudaEventElapsedTime(&ms, a, b);
     if (i >= 2 && ms < best) best = ms;
   }
+  if (cudaGetLastError() != cudaSuccess) return -1.f;
   return best;
 }
 
@@ -203,15 +218,17 @@ int main(int argc, char** argv) {
     }
   }
   for (int reps : {1, 2}) {
-    const int tiles = (int)(bytes / ((size_t)TILE * 4 * reps));
+    const int tiles = (int)(bytes / ((size_t)TILE * 4 * reps)) / 8 * 8;
     const double gb = (double)tiles * reps * TILE * 4 / 1e9;
     for (int warps : {2, 4, 8, 12, 16}) {
-      printf("reps %d  per-warp TMA workers, %2d warps/SM (1 CTA/SM), 2 KB stores:", reps, warps);
-      float t2 = run_tma_warp<2>(out, base, tiles, reps, ctr, sm, warps * 32, 8);
-      float t4 = run_tma_warp<4>(out, base, tiles, reps, ctr, sm, warps * 32, 8);
-      float t6 = run_tma_warp<6>(out, base, tiles, reps, ctr, sm, warps * 32, 8);
-      printf("  2 stages %.1f us %.0f GB/s | 4 stages %.1f us %.0f GB/s | 6 stages %.1f us %.0f GB/s\n", t2 * 1e3, gb / (t2 * 1e-3),
-             t4 * 1e3, gb / (t4 * 1e-3), t6 * 1e3, gb / (t6 * 1e-3));
+      printf("reps %d  per-warp TMA workers, %2d warps/SM (1 CTA/SM):", reps, warps);
+      float a2 = run_tma_warp<2, 512>(out, base, tiles, reps, ctr, sm, warps * 32, 8);
+      float a4 = run_tma_warp<4, 512>(out, base, tiles, reps, ctr, sm, warps * 32, 8);
+      float a8 = warps <= 12 ? run_tma_warp<8, 512>(out, base, tiles, reps, ctr, sm, warps * 32, 8) : -1.f;
+      float b2 = run_tma_warp<2, 1024>(out, base, tiles, reps, ctr, sm, warps * 32, 8);
+      float b4 = warps <= 12 ? run_tma_warp<4, 1024>(out, base, tiles, reps, ctr, sm, warps * 32, 8) : -1.f;
+      printf("  2 KB stores: 2 st %.1f us %.0f | 4 st %.1f us %.0f | 8 st %.1f us %.0f GB/s  ||  4 KB stores: 2 st %.1f us %.0f | 4 st %.1f us %.0f GB/s\n",
+             a2 * 1e3, gb / (a2 * 1e-3), a4 * 1e3, gb / (a4 * 1e-3), a8 * 1e3, gb / (a8 * 1e-3), b2 * 1e3, gb / (b2 * 1e-3), b4 * 1e3, gb / (b4 * 1e-3));
     }
   }
   cudaError_t e = cudaDeviceSynchronize();

@@ -68,6 +68,9 @@ SIGNATURES = {
     "rbgtopo_scaled_value": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "rbgtopo_updated_replicas_bound": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, i32p, i32p]),
     "rbgtopo_next_rolling_target": (C.c_int32, [C.c_int32, C.c_int32, i32p, i32p, i32p, i32p]),
+    "rbgtopo_partition_replicas": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, i32p]),
+    "rbgtopo_intstr_non_zero": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, i32p]),
+    "rbgtopo_merge_rolling_update": (C.c_int32, [i32p, i32p, i32p]),
     "rbgtopo_plan_describe": (C.c_int32, [i32p, C.c_int64, C.c_int32, C.c_int32, i32p, C.c_int64, i32p, C.c_int64,
                                           i32p, i32p, C.POINTER(C.c_int64)]),
 }

@@ -202,4 +202,42 @@ int32_t rbgtopo_next_rolling_target(int32_t s_pct, int32_t n, const int32_t* des
   return RBGTOPO_OK;
 }
 
+// CalculatePartitionReplicas — pkg/utils/utils.go:139-162.  has_partition = 0: nil partition;
+// is_percent: the partition is the string "<value>%"; replicas < 0 stands for a nil replicas pointer (-> 1).
+int32_t rbgtopo_partition_replicas(int32_t has_partition, int32_t is_percent, int32_t value, int32_t replicas,
+                                   int32_t* out) {
+  if (!out) return RBGTOPO_EINVAL;
+  if (!has_partition) { *out = 0; return RBGTOPO_OK; }
+  const int32_t reps = replicas < 0 ? 1 : replicas;
+  // roundUp = true keeps at least one old pod when partition > "0%" and replicas > 0
+  int32_t p = rbgtopo_scaled_value(is_percent, value, reps, 1);
+  // partition < "100%" and replicas >= 1: at least one pod is upgraded
+  if (reps >= 1 && p == reps && is_percent && value != 100) p = reps - 1;
+  *out = std::max(std::min(p, reps), 0);
+  return RBGTOPO_OK;
+}
+
+// ParseIntStrAsNonZero — pkg/utils/utils.go:177-185.
+int32_t rbgtopo_intstr_non_zero(int32_t is_percent, int32_t value, int32_t replicas, int32_t* out) {
+  if (!out) return RBGTOPO_EINVAL;
+  const int32_t v = rbgtopo_scaled_value(is_percent, value, replicas, 1);
+  *out = v < 1 ? 1 : v;
+  return RBGTOPO_OK;
+}
+
+// mergeStrategyRollingUpdate — rolebasedgroup_controller.go:1284-1314, for ONE role present in both
+// maps (a role present in one map only is taken as it is).  A strategy is six ints:
+// maxUnavailable (has, is_percent, value), partition (has, is_percent, value); both fields are
+// compared scaled to 100 with roundUp, a nil field counts as 0 (the Go code drops the error).
+int32_t rbgtopo_merge_rolling_update(const int32_t* a, const int32_t* b, int32_t* out) {
+  if (!a || !b || !out) return RBGTOPO_EINVAL;
+  auto scaled = [](const int32_t* f) { return f[0] ? rbgtopo_scaled_value(f[1], f[2], 100, 1) : 0; };
+  for (int i = 0; i < 6; ++i) out[i] = a[i];
+  if (scaled(a) > scaled(b))
+    for (int i = 0; i < 3; ++i) out[i] = b[i];          // the smaller maxUnavailable wins
+  if (scaled(a + 3) < scaled(b + 3))
+    for (int i = 3; i < 6; ++i) out[i] = b[i];          // the larger partition wins
+  return RBGTOPO_OK;
+}
+
 }  // extern "C"

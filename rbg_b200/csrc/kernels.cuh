@@ -74,6 +74,10 @@ struct BatchDev {
   int* assign;   // [total R]
   int* status;   // [n_steps]
   int* domain_out;  // [n_steps]
+  // correction records of multi-wave plans (plan_group.cuh: k_plan_group(record) -> k_plan_correct)
+  int* corr;      // [patch_cap][corr_w]: node, one value per role row
+  int* corr_cnt;  // [n_steps]
+  int corr_w;     // 1 + largest role count of a step in the batch
 };
 
 // ---------------------------------------------------------------- helpers

@@ -226,10 +226,16 @@ __device__ __forceinline__ void gtab_add_anchor(const TopoDev& t, const GroupTab
 
 // grid = groups with at least one pending replica = the steps of wave 0; CTA g starts at step g.
 // QB = largest role count of a group in the batch, PB = warps per CTA (>= roles of any wave).
-__global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev b, int QB, int HT, int CAP) {
+// record == 0: the sparse corrections of the dense matrix are applied here (the kernel must run
+//   AFTER k_score_emit wrote the background rows: serial pipeline).
+// record == 1: the kernel never touches the matrix — selection and the greedy need only the table —
+//   and leaves, per step, a compact list of corrections (node, one value per role row: the summed
+//   delta, or -inf) in b.corr / b.corr_cnt for k_plan_correct.  It then runs CONCURRENTLY with
+//   k_score_emit on a second stream; the step's critical path becomes max(emit, select) + correct.
+__global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev b, int QB, int HT, int CAP, int record) {
   extern __shared__ __align__(16) unsigned char pg_smem[];
   __shared__ int sTakenNode[KS], sTakenAmt[KS], sTakenRole[KS], sRowB[KS], sRowN[KS];
-  __shared__ int sDstar, sCnt, sNew, sStatus, sAny;
+  __shared__ int sDstar, sCnt, sNew, sStatus, sAny, sCorrN;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthreads = blockDim.x, nwarps = nthreads >> 5;
   const int PB = nwarps;
   GroupTab T;
@@ -288,6 +294,7 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
       const int4 r = *reinterpret_cast<const int4*>(b.blob + h.role_off + 4 * tid);
       sRole[tid] = GroupRole{r.x, r.y, r.z, r.w};
     }
+    if (tid == 0) sCorrN = 0;
     for (int i = tid; i < h.P * Q; i += nthreads)
       sPair[(i / Q) * RBGTOPO_MAX_GROUP_ROLES + i % Q] = (float)b.blob[h.pair_off + i];
     if (tid < n_new) {
@@ -383,7 +390,37 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
 #ifdef RBGTOPO_PHASE_CLOCKS
     if (!(g_dbg_skip & 1))
 #endif
-    if (warp != 0) {
+    if (warp != 0 && record) {
+      // one record per patched node of this rank's slab whose rows differ from the background:
+      // [node, value of role row 0 .. P-1] (the summed delta, or -inf); region of step s =
+      // b.corr + poff[s] * b.corr_w, never more than the step's patch capacity
+      int* const reg = b.corr + (size_t)b.poff[step] * b.corr_w;
+      for (int d = tid - 32; d < cnt; d += nthreads - 32) {
+        const int slot = T.dSlot[d];
+        const int node = T.node[slot];
+        if (node < t.slab_lo || node >= t.slab_hi) continue;  // another rank's columns
+        const int av = T.dAvail[d];
+        const bool consumed = T.cons[slot] > 0;
+        float v[MAXP];
+        bool any = false;
+#pragma unroll
+        for (int p = 0; p < MAXP; ++p) {
+          v[p] = 0.0f;
+          if (p < h.P) {
+            v[p] = (consumed && av < sRole[p].demand) ? -INFINITY
+                                                      : gtab_delta(T, sPair + p * RBGTOPO_MAX_GROUP_ROLES, Q, slot);
+            any |= v[p] != 0.0f;
+          }
+        }
+        if (any) {
+          int* e = reg + (size_t)atomicAdd(&sCorrN, 1) * b.corr_w;
+          e[0] = node;
+#pragma unroll
+          for (int p = 0; p < MAXP; ++p)
+            if (p < h.P) e[1 + p] = __float_as_int(v[p]);
+        }
+      }
+    } else if (warp != 0) {
       float* const mrow0 = b.matrix + (size_t)h.rep_off * stride - t.slab_lo;  // mrow0[node]
       for (int d = tid - 32; d < cnt; d += nthreads - 32) {
         const int slot = T.dSlot[d];
@@ -455,6 +492,7 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
       }
     }
     __syncthreads();
+    if (record && tid == 0) b.corr_cnt[step] = sCorrN;
     PCLK(wave_i * 8 + 5);
     ++wave_i;
     if (h.next_step <= 0) break;
@@ -469,6 +507,7 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
             b.status[s2] = RBGTOPO_GANG_FAILED;
             b.domain_out[s2] = -1;
             b.dstar[s2] = -1;
+            if (record) b.corr_cnt[s2] = 0;
           }
           s2 = h2.next_step;
         }
@@ -478,6 +517,41 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
     h = load_hdr(b, step);
   }
   PCLK(31);
+}
+
+// Applies the correction records k_plan_group(record = 1) left: one warp per step, one lane per
+// record; a value is added onto every replica row of its role with red.global.add.f32 (exact
+// integers, spec §3.4), -inf is stored.  Runs after k_score_emit AND k_plan_group finished.
+constexpr int CORRECT_WARPS = 4;
+__global__ void __launch_bounds__(32 * CORRECT_WARPS) k_plan_correct(TopoDev t, BatchDev b) {
+  const int lane = threadIdx.x & 31;
+  const int step = blockIdx.x * CORRECT_WARPS + (threadIdx.x >> 5);
+  if (step >= b.n_steps) return;
+  const int cnt = b.corr_cnt[step];
+  if (cnt <= 0) return;
+  const int* __restrict__ hdr = b.blob + RBGTOPO_HDR_WORDS + (size_t)step * RBGTOPO_STEP_WORDS;
+  const int P = hdr[3], role_off = hdr[4], rep_off = hdr[12];
+  const int my_count = lane < P ? b.blob[role_off + 4 * lane] : 0;
+  const size_t stride = (size_t)t.slab_stride;
+  float* const mrow0 = b.matrix + (size_t)rep_off * stride - t.slab_lo;  // mrow0[node]
+  const int* const reg = b.corr + (size_t)b.poff[step] * b.corr_w;
+  for (int e0 = 0; e0 < cnt; e0 += 32) {
+    const int e = e0 + lane;
+    const int* rec = reg + (size_t)e * b.corr_w;
+    float* rowp = e < cnt ? mrow0 + rec[0] : nullptr;
+    for (int p = 0; p < P; ++p) {
+      const int count = __shfl_sync(FULL, my_count, p);
+      if (e < cnt) {
+        const float v = __int_as_float(rec[1 + p]);
+        if (v == -INFINITY) {
+          for (int k = 0; k < count; ++k) rowp[(size_t)k * stride] = -INFINITY;
+        } else if (v != 0.0f) {
+          for (int k = 0; k < count; ++k) sel_red_add_f32(rowp + (size_t)k * stride, v);
+        }
+        rowp += (size_t)count * stride;
+      }
+    }
+  }
 }
 
 }  // namespace rbgtopo

@@ -23,6 +23,7 @@
 #include "kernels.cuh"
 #include "plan.cuh"
 #include "score.cuh"
+#include "emit_tma.cuh"
 #include "select.cuh"
 #include "select_fast.cuh"
 #include "plan_group.cuh"
@@ -150,7 +151,8 @@ struct Batch {
   bool d2h_enqueued = false;  // enqueue_d2h ran for the last pass; fetch_batch only has to wait
   uint64_t epoch = 0;         // topology epoch the batch was validated / sized against (set_topology bumps it)
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[8] = {};
+  cudaStream_t stream2 = nullptr;  // selection of multi-wave plans, concurrent with the dense-matrix kernel
+  cudaEvent_t ev[8] = {};          // 0/1 staging, 2/3 fork/join of stream2, 4/5 D2H, 6 snapshot fence
   std::vector<cudaEvent_t> it_ev;  // triples (before score, after score, after select) per pass
   int passes = 0, pend_launches = 0, untimed_or_timed_passes = 0;  // since the last harvest
   bool shard_timed = false;
@@ -159,6 +161,8 @@ struct Batch {
   DevBuf<float> matrix;
   DevBuf<unsigned long long> lists, merged, excl;
   DevBuf<int> cand;  // patched-node scratch of the selection kernels
+  DevBuf<int> etab, emit_ctr;  // emit table of a plan (emit_tma.cuh) and the item queue of k_emit_tma
+  DevBuf<int> corr, corr_cnt;  // correction records of a plan: k_plan_group(record) -> k_plan_correct
   // device-resident multi-wave plan (rbgtopo_stage_groups / place_groups): steps are
   // wave-major; wave w = steps [wave_begin[w], wave_begin[w + 1])
   std::vector<int> wave_begin, wave_maxp;
@@ -174,6 +178,7 @@ struct Batch {
   PinBuf<int> h_in, h_out;
   ~Batch() {
     if (stream) cudaStreamDestroy(stream);
+    if (stream2) cudaStreamDestroy(stream2);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : it_ev) cudaEventDestroy(e);
   }
@@ -215,6 +220,18 @@ constexpr size_t kFastSmemMax = 200 * 1024;
 constexpr int kMaxExactTerm = 1 << 24;  // pair weights and anchor counts above this can never satisfy spec §3.4
 // Switches, read once when the library loads.
 const bool kPerWavePlan = getenv("RBGTOPO_PER_WAVE_PLAN") != nullptr;  // one launch per wave instead of k_plan_group
+// Multi-wave plans: k_plan_group on a second stream, concurrent with k_score_emit, corrections applied
+// afterwards by k_plan_correct (default).  RBGTOPO_SERIAL_PLAN=1: emit, then k_plan_group applying the
+// corrections itself (the round-1 pipeline; kept for A/B measurements).
+const bool kSerialPlan = getenv("RBGTOPO_SERIAL_PLAN") != nullptr;
+const bool kSelectHighPriority = getenv("RBGTOPO_SELECT_LOW_PRIO") == nullptr;
+const bool kSelectFirst = getenv("RBGTOPO_SELECT_FIRST") != nullptr;  // launch order of the two concurrent kernels
+// Dense rows of a plan: k_emit_tma (TMA bulk stores, 8 warps per SM) by default; RBGTOPO_EMIT_ST=1
+// selects k_score_emit<false> (per-thread streaming stores, round 1) for A/B measurements.
+const bool kEmitSt = getenv("RBGTOPO_EMIT_ST") != nullptr;
+const int kEmitTmaBlock = getenv("RBGTOPO_EMIT_TMA_BLOCK")
+                              ? std::min(EMIT_MAX_BSTEPS, std::max(1, atoi(getenv("RBGTOPO_EMIT_TMA_BLOCK")))) : 4;
+const int kEmitCtasPerSm = getenv("RBGTOPO_EMIT_CTAS") ? std::max(1, atoi(getenv("RBGTOPO_EMIT_CTAS"))) : 1;
 const int kEmitBlockSteps =
     getenv("RBGTOPO_EMIT_BLOCK") ? std::min(EMIT_MAX_BLOCK, std::max(1, atoi(getenv("RBGTOPO_EMIT_BLOCK")))) : 4;
 // place_groups can pipeline a fleet as two halves (host geometry of half 2 under the device work of
@@ -548,6 +565,11 @@ int acquire_batch(rbgtopo_ctx* c, Batch** out) {
     }
   auto nb = std::make_unique<Batch>();
   CK(cudaStreamCreateWithFlags(&nb->stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;  // numerically lower = higher priority
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&nb->stream2, cudaStreamNonBlocking, kSelectHighPriority ? hi : lo));
+  }
   for (auto& e : nb->ev) CK(cudaEventCreate(&e));
   nb->in_use = true;
   *out = nb.get();
@@ -573,6 +595,15 @@ int reserve_batch_buffers(rbgtopo_ctx* c, Batch* b) {
   CK(b->lists.reserve((size_t)std::max(1, m.total_p) * KS));
   CK(b->merged.reserve((size_t)std::max(1, m.total_p) * KS));
   CK(b->excl.reserve((size_t)std::max(1, m.total_p) * KS));
+  if (!b->wave_begin.empty()) {
+    CK(b->etab.reserve((size_t)m.n_steps * EMIT_TAB_WORDS + 4));
+    if (!b->emit_ctr.p) {
+      CK(b->emit_ctr.reserve(4));
+      CK(cudaMemset(b->emit_ctr.p, 0, b->emit_ctr.cap * 4));
+    }
+    CK(b->corr.reserve((size_t)m.patch_cap * (size_t)(1 + m.max_p) + 1));
+    CK(b->corr_cnt.reserve((size_t)m.n_steps + 1));
+  }
   const size_t out_n = (size_t)m.total_r + 3 * (size_t)m.n_steps + 4;
   CK(b->out.reserve(out_n));
   CK(b->h_out.reserve(out_n));
@@ -636,6 +667,9 @@ BatchDev batch_dev(rbgtopo_ctx* c, Batch* b) {
   d.status = b->out.p + b->m.total_r;
   d.domain_out = d.status + b->m.n_steps;
   d.dstar = d.domain_out + b->m.n_steps;
+  d.corr = b->corr.p;
+  d.corr_cnt = b->corr_cnt.p;
+  d.corr_w = 1 + b->m.max_p;
   return d;
 }
 
@@ -646,9 +680,34 @@ int launch_score(rbgtopo_ctx* c, Batch* b, cudaStream_t s) {
   const int grid = items / kEmitBlockSteps;  // one CTA per (block of steps, chunk of nodes)
   if (b->wave_begin.empty())  // step batch: rows + sparse corrections
     k_score_emit<true><<<grid, SCORE_THREADS, 0, s>>>(topo_dev(c), batch_dev(c, b), items);
-  else                        // multi-wave plan: background rows; corrections come from the selection kernels
+  else if (kEmitSt)           // multi-wave plan: background rows; corrections come from the selection kernels
     k_score_emit<false><<<grid, SCORE_THREADS, 0, s>>>(topo_dev(c), batch_dev(c, b), items);
+  else {                      // the same rows through TMA bulk stores (emit_tma.cuh), persistent grid
+    BatchDev d = batch_dev(c, b);
+    d.bsteps = kEmitTmaBlock;
+    const int slab = c->slab_hi - c->slab_lo;
+    const int subs = (slab + EMIT_SUB - 1) / EMIT_SUB;
+    const long long n_items = (long long)((m.n_steps + d.bsteps - 1) / d.bsteps) * subs;
+    if (n_items > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "steps x sub-chunks exceed 2^31 work items");
+    if (n_items > 0)
+      k_emit_tma<<<c->sm_count * kEmitCtasPerSm, 32 * EMIT_WARPS, emit_tma_smem_bytes(), s>>>(topo_dev(c), d, b->etab.p, subs, (int)n_items,
+                                                                                             b->emit_ctr.p);
+  }
   return RBGTOPO_OK;
+}
+
+// Launch geometry of k_plan_group for a multi-wave plan; false when the plan has to take the
+// per-wave path (RBGTOPO_PER_WAVE_PLAN, or a group's table exceeds a CTA's shared memory).
+struct PlanGroupCfg { int nth, HT, CAP, n0; size_t smem; };
+bool plan_group_cfg(const Batch* b, PlanGroupCfg* o) {
+  if (b->wave_begin.empty() || kPerWavePlan) return false;
+  o->nth = std::max(128, 32 * b->m.max_p);
+  o->CAP = std::max(32, round_up(b->m.max_cap, 32));
+  o->HT = 64;
+  while (o->HT <= o->CAP && o->HT < (1 << 20)) o->HT <<= 1;  // > CAP: probes always meet an empty slot
+  o->smem = group_smem_bytes(b->m.max_q, o->nth / 32, o->HT, o->CAP);
+  o->n0 = b->wave_begin.size() > 1 ? b->wave_begin[1] : 0;  // groups with pending replicas
+  return o->smem <= kFastSmemMax;
 }
 
 // world == 1: one fused kernel (select + exclusive domain + greedy), one CTA per step
@@ -679,20 +738,13 @@ int launch_select_assign(rbgtopo_ctx* c, Batch* b, cudaStream_t s, const BatchDe
     return RBGTOPO_OK;
   }
   // multi-wave plan, preferred: every wave of a group in one CTA of ONE launch (plan_group.cuh)
-  if (!kPerWavePlan) {
-    const int nth = std::max(128, 32 * b->m.max_p);
-    const int gCAP = std::max(32, round_up(b->m.max_cap, 32));
-    int gHT = 64;
-    while (gHT <= gCAP && gHT < (1 << 20)) gHT <<= 1;  // > CAP: probes always meet an empty slot
-    const size_t smem = group_smem_bytes(b->m.max_q, nth / 32, gHT, gCAP);
-    const int n0 = b->wave_begin.size() > 1 ? b->wave_begin[1] : 0;  // groups with pending replicas
-    if (smem <= kFastSmemMax) {
-      if (n0 > 0) {
-        k_plan_group<<<n0, nth, smem, s>>>(topo_dev(c), d, b->m.max_q, gHT, gCAP);
-        ++*launches;
-      }
-      return RBGTOPO_OK;
+  PlanGroupCfg pg;
+  if (plan_group_cfg(b, &pg)) {
+    if (pg.n0 > 0) {
+      k_plan_group<<<pg.n0, pg.nth, pg.smem, s>>>(topo_dev(c), d, b->m.max_q, pg.HT, pg.CAP, 0);
+      ++*launches;
     }
+    return RBGTOPO_OK;
   }
   if (c->cfg.world != 1)
     return fail(RBGTOPO_ELIMIT, "plan does not fit k_plan_group's shared memory: world > 1 must use the shard_wave calls");
@@ -741,12 +793,34 @@ int run_batch(rbgtopo_ctx* c, Batch* b, int iters) {
       if (rc) return rc;
       CK(cudaEventRecord(b->it_ev[e0], s));
     }
-    int rc = launch_score(c, b, s);
-    if (rc) return rc;
-    ++launches;
-    if (timed) CK(cudaEventRecord(b->it_ev[e0 + 1], s));
-    rc = launch_select_assign(c, b, s, d, &launches);
-    if (rc) return rc;
+    int rc;
+    PlanGroupCfg pg;
+    if (!kSerialPlan && plan_group_cfg(b, &pg)) {
+      // Concurrent pipeline: the selection + greedy of every group (k_plan_group, record mode: it never
+      // touches the matrix) on stream2 beside the dense-matrix kernel on s; the corrections follow both.
+      cudaStream_t s2 = b->stream2;
+      CK(cudaEventRecord(b->ev[2], s));
+      CK(cudaStreamWaitEvent(s2, b->ev[2], 0));  // after the staging / the previous pass's k_plan_correct
+      if (kSelectFirst && pg.n0 > 0) k_plan_group<<<pg.n0, pg.nth, pg.smem, s2>>>(topo_dev(c), d, b->m.max_q, pg.HT, pg.CAP, 1);
+      rc = launch_score(c, b, s);
+      if (rc) return rc;
+      ++launches;
+      if (timed) CK(cudaEventRecord(b->it_ev[e0 + 1], s));
+      if (!kSelectFirst && pg.n0 > 0) k_plan_group<<<pg.n0, pg.nth, pg.smem, s2>>>(topo_dev(c), d, b->m.max_q, pg.HT, pg.CAP, 1);
+      if (pg.n0 > 0) {
+        CK(cudaEventRecord(b->ev[3], s2));
+        CK(cudaStreamWaitEvent(s, b->ev[3], 0));
+        k_plan_correct<<<(b->m.n_steps + CORRECT_WARPS - 1) / CORRECT_WARPS, 32 * CORRECT_WARPS, 0, s>>>(topo_dev(c), d);
+        launches += 2;
+      }
+    } else {
+      rc = launch_score(c, b, s);
+      if (rc) return rc;
+      ++launches;
+      if (timed) CK(cudaEventRecord(b->it_ev[e0 + 1], s));
+      rc = launch_select_assign(c, b, s, d, &launches);
+      if (rc) return rc;
+    }
     if (timed) {
       CK(cudaEventRecord(b->it_ev[e0 + 2], s));
       b->passes += 1;
@@ -881,6 +955,7 @@ int fence_batches(rbgtopo_ctx* c, bool sync) {
     if (!b->in_use || !b->stream) continue;
     if (sync) {
       CK(cudaStreamSynchronize(b->stream));
+      CK(cudaStreamSynchronize(b->stream2));
     } else {
       CK(cudaEventRecord(b->ev[6], b->stream));
       CK(cudaStreamWaitEvent(c->topo_stream, b->ev[6], 0));
@@ -946,6 +1021,7 @@ int32_t rbgtopo_create(const rbgtopo_config* cfg, rbgtopo_ctx** out) {
   CK(cudaFuncSetAttribute(k_select_assign_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
   CK(cudaFuncSetAttribute(k_shard_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
   CK(cudaFuncSetAttribute(k_plan_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
+  CK(cudaFuncSetAttribute(k_emit_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_tma_smem_bytes()));
 #ifdef RBGTOPO_PHASE_CLOCKS
   {
     const int skip = getenv("RBGTOPO_DBG_SKIP") ? atoi(getenv("RBGTOPO_DBG_SKIP")) : 0;
@@ -1967,8 +2043,13 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, int g
                                                                    (int)racc, (int)rowacc);
     CK(cudaGetLastError());
   }
+  if (ns > 0) {
+    k_emit_table<<<(ns + 127) / 128, 128, 0, s>>>(b->blob.p, ns, b->etab.p);
+    CK(cudaMemsetAsync(b->emit_ctr.p, 0, 8, s));  // re-arm the item queue (a failed launch may have left it mid-way)
+    CK(cudaGetLastError());
+  }
   CK(cudaEventRecord(b->ev[1], s));  // h2d_ms = upload + expansion
-  b->pend_launches += 1;
+  b->pend_launches += 2;
   b->staged = true;
   b->ran = false;
   return RBGTOPO_OK;

@@ -137,3 +137,67 @@ def test_dependency_levels_random_vs_oracle():
         rnd.shuffle(roles)
         got = [[roles[i].name for i in lvl] for lvl in ha.dependency_levels(roles)]
         assert got == rp.dependency_order(deps)
+
+
+def _intstr(v):
+    """IntOrString of a golden case -> (has, is_percent, value), or None when the string is one the
+    Go parser rejects (those cases test intstr itself, not the functions above it)."""
+    if v is None:
+        return (0, 0, 0)
+    if isinstance(v, int):
+        return (1, 0, v)
+    s = str(v)
+    if s.endswith("%") and s[:-1].lstrip("-").isdigit():
+        return (1, 1, int(s[:-1]))
+    return None
+
+
+def test_partition_replicas_and_non_zero(lib, golden):
+    # pkg/utils/utils_test.go:342-482 and :484-583, through the C ABI
+    out = C.c_int32()
+    n = 0
+    for c in golden["calculate_partition_replicas"]["cases"]:
+        p = _intstr(c["partition"])
+        if c.get("wantErr") or p is None:
+            continue
+        reps = -1 if c["replicas"] is None else c["replicas"]
+        assert lib.rbgtopo_partition_replicas(p[0], p[1], p[2], reps, C.byref(out)) == 0
+        assert out.value == c["want"], c["name"]
+        assert out.value == rp.calculate_partition_replicas(c["partition"], c["replicas"])
+        n += 1
+    assert n >= 8
+    n = 0
+    for c in golden["parse_intstr_as_non_zero"]["cases"]:
+        p = _intstr(c["in"])
+        if c.get("wantErr") or p is None:
+            continue
+        assert lib.rbgtopo_intstr_non_zero(p[1], p[2], c["replicas"], C.byref(out)) == 0
+        assert out.value == c["want"], c["name"]
+        n += 1
+    assert n >= 5
+
+
+def test_merge_rolling_update(lib, golden):
+    # rolebasedgroup_controller_test.go:1090-1281 (Test_mergeStrategyRollingUpdate), role by role through the C ABI
+    def pack(st):
+        mu, pt = _intstr(st[0]), _intstr(st[1])
+        return None if mu is None or pt is None else list(mu) + list(pt)
+
+    def unpack(v):
+        def one(h, pct, val):
+            return None if not h else (f"{val}%" if pct else val)
+        return [one(*v[0:3]), one(*v[3:6])]
+    n = 0
+    for c in golden["merge_strategy_rolling_update"]["cases"]:
+        for role, want in c["want"].items():
+            if role not in c["a"] or role not in c["b"]:
+                assert want == (c["a"].get(role) or c["b"].get(role))     # present in one map only: taken as it is
+                continue
+            a, b = pack(c["a"][role]), pack(c["b"][role])
+            if a is None or b is None:
+                continue
+            out = (C.c_int32 * 6)()
+            assert lib.rbgtopo_merge_rolling_update((C.c_int32 * 6)(*a), (C.c_int32 * 6)(*b), out) == 0
+            assert unpack(list(out)) == want, c["name"]
+            n += 1
+    assert n >= 3
