@@ -289,6 +289,26 @@ int32_t rbgtopo_shard_assign(rbgtopo_ctx* ctx, int32_t handle,
                              const void* keys2_all_dev);
 int32_t rbgtopo_slab(rbgtopo_ctx* ctx, int32_t* lo, int32_t* hi);
 
+/* ---- the same all-gather done by the library itself over NVLink peer memory (no NCCL call and no
+ * host round trip on the step path).  Setup once per ctx, SPMD:
+ *   rbgtopo_p2p_export : allocates this rank's exchange buffer (rows_cap role rows per wave and
+ *                        source rank, 0 = 16 384) and returns its cudaIpcMemHandle (64 bytes) and /
+ *                        or its device pointer (contexts of ONE process exchange the pointer);
+ *   (caller all-gathers the handles — any transport: torch.distributed, MPI, the shim's gRPC)
+ *   rbgtopo_p2p_import : maps the peers' buffers (handles_all = world x 64 bytes, rank-major) or
+ *                        takes their pointers (peer_ptrs[world]); exactly one of the two.
+ * rbgtopo_run_staged_p2p then enqueues, per pass and wave: k_shard_select -> k_p2p_push (peer stores
+ * of the lists into every rank's buffer + a release flag) -> k_p2p_wait (acquire, bounded spin) ->
+ * k_merge [-> restricted reselect -> push -> wait] -> k_greedy.  Every rank must make the same calls
+ * in the same order.  Results via rbgtopo_fetch; rbgtopo_p2p_stats reports the bytes this rank
+ * stored into peer memory during the last pass and whether a wait timed out (a peer never arrived:
+ * the results of that pass are invalid). */
+int32_t rbgtopo_p2p_export(rbgtopo_ctx* ctx, int32_t rows_cap, void* handle_out,
+                           int32_t handle_len, void** local_ptr);
+int32_t rbgtopo_p2p_import(rbgtopo_ctx* ctx, const void* handles_all, void* const* peer_ptrs);
+int32_t rbgtopo_run_staged_p2p(rbgtopo_ctx* ctx, int32_t handle, int32_t iters);
+int32_t rbgtopo_p2p_stats(rbgtopo_ctx* ctx, int64_t* peer_bytes_last_pass, int32_t* timed_out);
+
 /* Use an external CUDA stream (e.g. the one the caller's NCCL runs on) for
  * every call on this ctx; NULL restores the internal per-slot streams (pass
  * cudaStreamLegacy, (void*)0x1, to select the legacy default stream). */

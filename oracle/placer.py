@@ -27,6 +27,7 @@ def load() -> C.CDLL:
             build()
         _lib = C.CDLL(LIB_PATH)
         _lib.oracle_place.restype = C.c_int
+        _lib.oracle_place_fast.restype = C.c_int
         _lib.oracle_check_topology.restype = C.c_int
         _lib.oracle_max_threads.restype = C.c_int
     return _lib
@@ -54,7 +55,13 @@ def check_topology(topo) -> int:
 _MATRIX_CACHE = {}
 
 
-def place(topo, blob, want_matrix=True, want_topk=True, nthreads=1, reuse_matrix=False):
+def place_fast(topo, blob, want_matrix=True, want_topk=True, nthreads=1, reuse_matrix=False):
+    """The CPU variant with the GPU path's algebra (oracle/placer_fast.c): same contract and, by
+    the exactness contract of the spec, the same bits as place()."""
+    return place(topo, blob, want_matrix, want_topk, nthreads, reuse_matrix, _fn="oracle_place_fast")
+
+
+def place(topo, blob, want_matrix=True, want_topk=True, nthreads=1, reuse_matrix=False, _fn="oracle_place"):
     """Run the oracle on a batch.  Returns dict(rc, assign, status, domain,
     matrix [total R][N] or None, topk [rolerows][32] or None).
     reuse_matrix: write the dense matrix into a buffer kept per shape instead of a fresh array
@@ -79,7 +86,7 @@ def place(topo, blob, want_matrix=True, want_topk=True, nthreads=1, reuse_matrix
     assign = np.full(max(tr, 1), -2, dtype=np.int32)
     status = np.full(max(ns, 1), -2, dtype=np.int32)
     domain = np.full(max(ns, 1), -2, dtype=np.int32)
-    rc = lib.oracle_place(C.c_int32(n), C.c_int64(len(ci)), _p(rp), _p(ci), _p(ew), _p(fr), _p(dm),
+    rc = getattr(lib, _fn)(C.c_int32(n), C.c_int64(len(ci)), _p(rp), _p(ci), _p(ew), _p(fr), _p(dm),
                           C.c_int32(len(ow)), _p(ow), _p(blob), C.c_int64(len(blob)),
                           _p(matrix, C.c_float), _p(topk, C.c_uint64), _p(assign), _p(status), _p(domain),
                           C.c_int32(nthreads))

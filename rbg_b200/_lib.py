@@ -54,6 +54,10 @@ SIGNATURES = {
     "rbgtopo_shard_merge": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, i32p, C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_int64)]),
     "rbgtopo_shard_assign": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "rbgtopo_p2p_export": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "rbgtopo_p2p_import": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "rbgtopo_run_staged_p2p": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
+    "rbgtopo_p2p_stats": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), i32p]),
     "rbgtopo_slab": (C.c_int32, [C.c_void_p, i32p, i32p]),
     "rbgtopo_set_stream": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "rbgtopo_last_timing": (C.c_int32, [C.c_void_p, C.POINTER(Timing)]),

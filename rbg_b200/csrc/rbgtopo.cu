@@ -27,6 +27,7 @@
 #include "select.cuh"
 #include "select_fast.cuh"
 #include "plan_group.cuh"
+#include "p2p.cuh"
 
 using namespace rbgtopo;
 
@@ -161,6 +162,7 @@ struct Batch {
   DevBuf<float> matrix;
   DevBuf<unsigned long long> lists, merged, excl;
   DevBuf<int> cand;  // patched-node scratch of the selection kernels
+  DevBuf<long long> emit_clk;  // RBGTOPO_EMIT_CLOCKS
   DevBuf<int> etab, emit_ctr;  // emit table of a plan (emit_tma.cuh) and the item queue of k_emit_tma
   DevBuf<int> corr, corr_cnt;  // correction records of a plan: k_plan_group(record) -> k_plan_correct
   // device-resident multi-wave plan (rbgtopo_stage_groups / place_groups): steps are
@@ -208,6 +210,15 @@ struct rbgtopo_ctx {
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   unsigned stage_idx = 0;
   std::mutex stat_mu;
+  // in-library all-gather over peer memory (p2p.cuh); SPMD: every rank makes the same calls in the same order
+  DevBuf<unsigned long long> xbuf;
+  DevBuf<int> p2p_ctr;  // [0] = CTA counter of k_p2p_push, [1] = timeout flag of k_p2p_wait
+  P2PDev p2p{};
+  int p2p_rows_cap = 0;
+  bool p2p_ready = false;
+  unsigned long long p2p_seq = 0;
+  long long p2p_bytes_last = 0;  // bytes this rank stored into PEER buffers during the last pass
+  std::vector<void*> p2p_opened;
   rbgtopo_timing last{};
   std::vector<float> last_score_ms, last_select_ms;  // per pass, harvested by the last fetch (rbgtopo_last_pass_times)
   long long calls = 0, scores_total = 0, launches = 0;
@@ -220,18 +231,36 @@ constexpr size_t kFastSmemMax = 200 * 1024;
 constexpr int kMaxExactTerm = 1 << 24;  // pair weights and anchor counts above this can never satisfy spec §3.4
 // Switches, read once when the library loads.
 const bool kPerWavePlan = getenv("RBGTOPO_PER_WAVE_PLAN") != nullptr;  // one launch per wave instead of k_plan_group
-// Multi-wave plans: k_plan_group on a second stream, concurrent with k_score_emit, corrections applied
-// afterwards by k_plan_correct (default).  RBGTOPO_SERIAL_PLAN=1: emit, then k_plan_group applying the
-// corrections itself (the round-1 pipeline; kept for A/B measurements).
-const bool kSerialPlan = getenv("RBGTOPO_SERIAL_PLAN") != nullptr;
+// Multi-wave plans, default: the dense-matrix kernel, then k_plan_group applying the corrections itself.
+// RBGTOPO_CONCURRENT_PLAN=1: k_plan_group (record mode: it never touches the matrix) on a second stream
+// beside the dense-matrix kernel, corrections applied afterwards by k_plan_correct.  Measured SLOWER on
+// B200 in every configuration tried (profiles/README.md round 2: the write stream inflates the latency of
+// the selection's dependent loads 3-4x and the two kernels fight for registers), so it is opt-in.
+const bool kSerialPlan = getenv("RBGTOPO_CONCURRENT_PLAN") == nullptr;
 const bool kSelectHighPriority = getenv("RBGTOPO_SELECT_LOW_PRIO") == nullptr;
 const bool kSelectFirst = getenv("RBGTOPO_SELECT_FIRST") != nullptr;  // launch order of the two concurrent kernels
-// Dense rows of a plan: k_emit_tma (TMA bulk stores, 8 warps per SM) by default; RBGTOPO_EMIT_ST=1
-// selects k_score_emit<false> (per-thread streaming stores, round 1) for A/B measurements.
-const bool kEmitSt = getenv("RBGTOPO_EMIT_ST") != nullptr;
+// Residency cap of k_plan_group beside the dense-matrix kernel: its CTAs REQUEST this much dynamic shared
+// memory (they use ~28 KB), so at most floor(227 KB / request) of them share an SM and the rest of the
+// register file stays with the emit kernel.  0 = no inflation.
+const int kSelectSmemKB = getenv("RBGTOPO_SELECT_SMEM_KB") ? std::max(0, atoi(getenv("RBGTOPO_SELECT_SMEM_KB"))) : 0;
+// Dense rows of a plan: k_score_emit<false> (per-thread streaming stores) by default; RBGTOPO_EMIT_TMA=1
+// selects k_emit_tma (TMA bulk stores from shared memory, 8 warps per SM): bit-identical, a quarter of the
+// footprint, but 58-64 us against 54 us on cfg3 (per-warp latency bound), see profiles/README.md round 2.
+const bool kEmitSt = getenv("RBGTOPO_EMIT_TMA") == nullptr;
 const int kEmitTmaBlock = getenv("RBGTOPO_EMIT_TMA_BLOCK")
                               ? std::min(EMIT_MAX_BSTEPS, std::max(1, atoi(getenv("RBGTOPO_EMIT_TMA_BLOCK")))) : 4;
 const int kEmitCtasPerSm = getenv("RBGTOPO_EMIT_CTAS") ? std::max(1, atoi(getenv("RBGTOPO_EMIT_CTAS"))) : 1;
+const int kEmitStages = getenv("RBGTOPO_EMIT_STAGES") && atoi(getenv("RBGTOPO_EMIT_STAGES")) == 4 ? 4 : 2;
+const bool kEmitNoRegCap = getenv("RBGTOPO_EMIT_NOCAP") != nullptr;  // 96 registers instead of the 64-register cap
+const bool kEmitClocks = getenv("RBGTOPO_EMIT_CLOCKS") != nullptr;   // per-warp phase clocks of k_emit_tma on stderr at fetch
+
+using EmitFn = void (*)(TopoDev, BatchDev, const int*, int, int, int*, long long*);
+EmitFn emit_tma_fn() {
+  if (kEmitClocks) return kEmitStages == 4 ? (kEmitNoRegCap ? k_emit_tma<4, 1, true> : k_emit_tma<4, 4, true>)
+                                           : (kEmitNoRegCap ? k_emit_tma<2, 1, true> : k_emit_tma<2, 4, true>);
+  return kEmitStages == 4 ? (kEmitNoRegCap ? k_emit_tma<4, 1, false> : k_emit_tma<4, 4, false>)
+                          : (kEmitNoRegCap ? k_emit_tma<2, 1, false> : k_emit_tma<2, 4, false>);
+}
 const int kEmitBlockSteps =
     getenv("RBGTOPO_EMIT_BLOCK") ? std::min(EMIT_MAX_BLOCK, std::max(1, atoi(getenv("RBGTOPO_EMIT_BLOCK")))) : 4;
 // place_groups can pipeline a fleet as two halves (host geometry of half 2 under the device work of
@@ -689,9 +718,11 @@ int launch_score(rbgtopo_ctx* c, Batch* b, cudaStream_t s) {
     const int subs = (slab + EMIT_SUB - 1) / EMIT_SUB;
     const long long n_items = (long long)((m.n_steps + d.bsteps - 1) / d.bsteps) * subs;
     if (n_items > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "steps x sub-chunks exceed 2^31 work items");
-    if (n_items > 0)
-      k_emit_tma<<<c->sm_count * kEmitCtasPerSm, 32 * EMIT_WARPS, emit_tma_smem_bytes(), s>>>(topo_dev(c), d, b->etab.p, subs, (int)n_items,
-                                                                                             b->emit_ctr.p);
+    if (n_items > 0) {
+      if (kEmitClocks) CK(b->emit_clk.reserve((size_t)c->sm_count * kEmitCtasPerSm * EMIT_WARPS * 8));
+      emit_tma_fn()<<<c->sm_count * kEmitCtasPerSm, 32 * EMIT_WARPS, emit_tma_smem_bytes(kEmitStages), s>>>(
+          topo_dev(c), d, b->etab.p, subs, (int)n_items, b->emit_ctr.p, b->emit_clk.p);
+    }
   }
   return RBGTOPO_OK;
 }
@@ -801,12 +832,13 @@ int run_batch(rbgtopo_ctx* c, Batch* b, int iters) {
       cudaStream_t s2 = b->stream2;
       CK(cudaEventRecord(b->ev[2], s));
       CK(cudaStreamWaitEvent(s2, b->ev[2], 0));  // after the staging / the previous pass's k_plan_correct
-      if (kSelectFirst && pg.n0 > 0) k_plan_group<<<pg.n0, pg.nth, pg.smem, s2>>>(topo_dev(c), d, b->m.max_q, pg.HT, pg.CAP, 1);
+      const size_t pg_smem = std::min(kFastSmemMax, std::max(pg.smem, (size_t)kSelectSmemKB * 1024));
+      if (kSelectFirst && pg.n0 > 0) k_plan_group<<<pg.n0, pg.nth, pg_smem, s2>>>(topo_dev(c), d, b->m.max_q, pg.HT, pg.CAP, 1);
       rc = launch_score(c, b, s);
       if (rc) return rc;
       ++launches;
       if (timed) CK(cudaEventRecord(b->it_ev[e0 + 1], s));
-      if (!kSelectFirst && pg.n0 > 0) k_plan_group<<<pg.n0, pg.nth, pg.smem, s2>>>(topo_dev(c), d, b->m.max_q, pg.HT, pg.CAP, 1);
+      if (!kSelectFirst && pg.n0 > 0) k_plan_group<<<pg.n0, pg.nth, pg_smem, s2>>>(topo_dev(c), d, b->m.max_q, pg.HT, pg.CAP, 1);
       if (pg.n0 > 0) {
         CK(cudaEventRecord(b->ev[3], s2));
         CK(cudaStreamWaitEvent(s, b->ev[3], 0));
@@ -892,6 +924,18 @@ int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int3
     }
   }
 #endif
+  if (kEmitClocks && b->emit_clk.p && !b->wave_begin.empty()) {
+    const size_t nw = (size_t)c->sm_count * kEmitCtasPerSm * EMIT_WARPS;
+    std::vector<long long> h(nw * 8);
+    if (cudaMemcpy(h.data(), b->emit_clk.p, h.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      double s4[6] = {0};
+      for (size_t w = 0; w < nw; ++w)
+        for (int k = 0; k < 6; ++k) s4[k] += (double)h[w * 8 + k];
+      fprintf(stderr, "[emit clocks] per warp: items %.1f tiles %.1f | cycles: setup %.0f wait %.0f compute %.0f issue %.0f | per item setup %.0f, per tile wait %.0f compute %.0f issue %.0f\n",
+              s4[4] / nw, s4[5] / nw, s4[0] / nw, s4[1] / nw, s4[2] / nw, s4[3] / nw, s4[0] / std::max(1.0, s4[4]), s4[1] / std::max(1.0, s4[5]),
+              s4[2] / std::max(1.0, s4[5]), s4[3] / std::max(1.0, s4[5]));
+    }
+  }
   rbgtopo_timing tm{};
   float x = 0.f;
   if (cudaEventElapsedTime(&x, b->ev[0], b->ev[1]) == cudaSuccess) tm.h2d_ms = x;
@@ -1021,7 +1065,12 @@ int32_t rbgtopo_create(const rbgtopo_config* cfg, rbgtopo_ctx** out) {
   CK(cudaFuncSetAttribute(k_select_assign_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
   CK(cudaFuncSetAttribute(k_shard_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
   CK(cudaFuncSetAttribute(k_plan_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
-  CK(cudaFuncSetAttribute(k_emit_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_tma_smem_bytes()));
+  CK(cudaFuncSetAttribute(emit_tma_fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_tma_smem_bytes(kEmitStages)));
+  // k_emit_tma and k_plan_group are meant to share an SM: both ask for the largest shared-memory carve-out,
+  // otherwise the persistent emit CTA pins the SM at the small carve-out it needs alone and the CTAs of
+  // k_plan_group (28 KB each) cannot be co-scheduled until it exits
+  CK(cudaFuncSetAttribute(emit_tma_fn(), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_plan_group, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 #ifdef RBGTOPO_PHASE_CLOCKS
   {
     const int skip = getenv("RBGTOPO_DBG_SKIP") ? atoi(getenv("RBGTOPO_DBG_SKIP")) : 0;
@@ -1036,6 +1085,7 @@ int32_t rbgtopo_destroy(rbgtopo_ctx* c) {
   if (!c) return RBGTOPO_OK;
   cudaSetDevice(c->cfg.device);
   cudaDeviceSynchronize();
+  for (void* q : c->p2p_opened) cudaIpcCloseMemHandle(q);
   if (c->topo.refresh_exec) cudaGraphExecDestroy(c->topo.refresh_exec);
   if (c->topo_stream) cudaStreamDestroy(c->topo_stream);
   if (c->topo_ready) cudaEventDestroy(c->topo_ready);
@@ -2567,6 +2617,183 @@ int32_t rbgtopo_shard_merge(rbgtopo_ctx* c, int32_t handle, const void* keys_all
 }
 int32_t rbgtopo_shard_assign(rbgtopo_ctx* c, int32_t handle, const void* keys2_all) {
   return rbgtopo_shard_wave_assign(c, handle, 0, keys2_all);
+}
+
+// ---- all-gather over NVLink peer memory, inside the library (p2p.cuh) ------------------------
+int32_t rbgtopo_p2p_export(rbgtopo_ctx* c, int32_t rows_cap, void* handle_out, int32_t handle_len, void** local_ptr) {
+  if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
+  if (c->cfg.world > P2P_MAX_WORLD) return fail(RBGTOPO_ELIMIT, "world %d > %d", c->cfg.world, P2P_MAX_WORLD);
+  if (rows_cap <= 0) rows_cap = 16384;
+  if (handle_out && handle_len < (int32_t)sizeof(cudaIpcMemHandle_t)) return fail(RBGTOPO_EINVAL, "handle buffer < %zu bytes", sizeof(cudaIpcMemHandle_t));
+  std::unique_lock<std::shared_mutex> lk(c->topo_mu);
+  CK(cudaSetDevice(c->cfg.device));
+  const int W = c->cfg.world;
+  const size_t data = (size_t)2 * W * rows_cap * KS;
+  const size_t total = data + (size_t)2 * W * P2P_FLAG_STRIDE + 64;
+  CK(c->xbuf.reserve(total));
+  CK(cudaMemset(c->xbuf.p, 0, c->xbuf.cap * 8));
+  CK(c->p2p_ctr.reserve(4));
+  CK(cudaMemset(c->p2p_ctr.p, 0, c->p2p_ctr.cap * 4));
+  CK(cudaDeviceSynchronize());
+  c->p2p_rows_cap = rows_cap;
+  c->p2p = P2PDev{};
+  c->p2p.world = W;
+  c->p2p.rank = c->cfg.rank;
+  c->p2p.slot_stride = (long long)rows_cap * KS;
+  c->p2p.flags_off = (long long)data;
+  c->p2p.peer[c->cfg.rank] = c->xbuf.p;
+  c->p2p_ready = false;
+  c->p2p_seq = 0;
+  if (handle_out) {
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->xbuf.p));
+    memcpy(handle_out, &h, sizeof h);
+  }
+  if (local_ptr) *local_ptr = c->xbuf.p;
+  return RBGTOPO_OK;
+}
+
+int32_t rbgtopo_p2p_import(rbgtopo_ctx* c, const void* handles_all, void* const* peer_ptrs) {
+  if (!c || (!handles_all && !peer_ptrs)) return fail(RBGTOPO_EINVAL, "null argument");
+  std::unique_lock<std::shared_mutex> lk(c->topo_mu);
+  if (!c->xbuf.p) return fail(RBGTOPO_EINVAL, "rbgtopo_p2p_export has not been called");
+  CK(cudaSetDevice(c->cfg.device));
+  const int W = c->cfg.world;
+  for (int g = 0; g < W; ++g) {
+    if (g == c->cfg.rank) continue;
+    if (peer_ptrs) {  // peers inside this process (several contexts of one process): plain device pointers
+      if (!peer_ptrs[g]) return fail(RBGTOPO_EINVAL, "peer pointer %d is null", g);
+      c->p2p.peer[g] = static_cast<unsigned long long*>(peer_ptrs[g]);
+    } else {          // one process per GPU: map the peer's buffer (enables peer access over NVLink)
+      cudaIpcMemHandle_t h;
+      memcpy(&h, static_cast<const char*>(handles_all) + (size_t)g * sizeof h, sizeof h);
+      void* q = nullptr;
+      CK(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+      c->p2p_opened.push_back(q);
+      c->p2p.peer[g] = static_cast<unsigned long long*>(q);
+    }
+  }
+  c->p2p_ready = true;
+  return RBGTOPO_OK;
+}
+
+namespace {
+// one exchange phase on stream s: push `rows` role rows starting at `src`, wait for every rank's push
+int p2p_exchange(rbgtopo_ctx* c, cudaStream_t s, const unsigned long long* src, long long rows, int* parity_out) {
+  if (rows > c->p2p_rows_cap) return fail(RBGTOPO_ELIMIT, "%lld role rows in one wave exceed the exchange buffer (%d)", rows, c->p2p_rows_cap);
+  const unsigned long long seq = ++c->p2p_seq;
+  const int parity = (int)(seq & 1ull);
+  const long long n_u64 = rows * KS;
+  const int grid = (int)std::min<long long>(std::max<long long>(1, (n_u64 / 2 + 255) / 256), 2 * c->sm_count);
+  k_p2p_push<<<grid, 256, 0, s>>>(c->p2p, src, n_u64, parity, seq, c->p2p_ctr.p);
+  k_p2p_wait<<<1, 32, 0, s>>>(c->p2p, parity, seq, 4000000000LL, c->p2p_ctr.p + 1);
+  CK(cudaGetLastError());
+  c->p2p_bytes_last += n_u64 * 8 * (c->cfg.world - 1);
+  *parity_out = parity;
+  return RBGTOPO_OK;
+}
+}  // namespace
+
+// The sharded pipeline of a staged batch / plan with the exchanges done by the library itself:
+// per wave k_shard_select -> push + wait -> k_merge [-> restricted reselect -> push + wait] -> k_greedy,
+// all enqueued on the call's stream; no NCCL, no host synchronisation.  SPMD: every rank calls it
+// with the same staged batch.
+int32_t rbgtopo_run_staged_p2p(rbgtopo_ctx* c, int32_t handle, int32_t iters) {
+  if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
+  if (iters < 1 || iters > 4096) return fail(RBGTOPO_EINVAL, "iters");
+  std::shared_lock<std::shared_mutex> lk(c->topo_mu);
+  if (c->cfg.world > 1 && !c->p2p_ready) return fail(RBGTOPO_EINVAL, "rbgtopo_p2p_import has not been called");
+  Batch* b = batch_of(c, handle);
+  if (!b) return fail(RBGTOPO_EINVAL, "bad or stale handle %d", handle);
+  if (c->cfg.world == 1) return run_batch(c, b, iters);
+  CK(cudaSetDevice(c->cfg.device));
+  cudaStream_t s = stream_of(c, b);
+  const bool plan = !b->wave_begin.empty();
+  const int n_waves = plan ? (int)b->wave_begin.size() - 1 : 1;
+  std::lock_guard<std::mutex> seq_guard(c->pool_mu);  // one exchange sequence at a time per ctx (the seq counter is SPMD state)
+  CK(cudaStreamWaitEvent(s, c->topo_ready, 0));
+  int launches = 0;
+  for (int it = 0; it < iters; ++it) {
+    c->p2p_bytes_last = 0;
+    const bool timed = b->passes < kMaxTimedPasses;
+    const int e0 = 3 * b->passes;
+    if (timed) {
+      int rc0 = ensure_pass_events(b, b->passes + 1);
+      if (rc0) return rc0;
+      CK(cudaEventRecord(b->it_ev[e0], s));
+    }
+    int rc = launch_score(c, b, s);
+    if (rc) return rc;
+    ++launches;
+    if (timed) CK(cudaEventRecord(b->it_ev[e0 + 1], s));
+    for (int wv = 0; wv < n_waves; ++wv) {
+      WaveRange w;
+      rc = wave_range(c, b, wv, &w);
+      if (rc) return rc;
+      const int n = w.s1 - w.s0;
+      if (n <= 0) continue;
+      BatchDev d = batch_dev(c, b);
+      int CAP, HT;
+      wave_table(b, w, &CAP, &HT);
+      const int nth = std::max(128, 32 * w.maxp);
+      if (fast_smem_bytes(nth / 32, HT, CAP) > kFastSmemMax)
+        return fail(RBGTOPO_ELIMIT, "a step's patched set exceeds shared memory on the sharded path");
+      k_shard_select<<<n, nth, fast_smem_bytes(nth / 32, HT, CAP), s>>>(topo_dev(c), d, w.s0, 0, plan ? SEL_CORRECT : 0, HT, CAP);
+      const long long rows = std::max(1, w.rr1 - w.rr0);
+      int parity = 0;
+      rc = p2p_exchange(c, s, b->lists.p + (size_t)w.rr0 * KS, rows, &parity);
+      if (rc) return rc;
+      d.parts = c->cfg.world;
+      d.part_stride = c->p2p.slot_stride;
+      d.lists_all = c->xbuf.p + (long long)parity * c->cfg.world * c->p2p.slot_stride - (long long)w.rr0 * KS;
+      k_merge<<<(n + SEL_WARPS - 1) / SEL_WARPS, SEL_THREADS, 0, s>>>(topo_dev(c), d, w.s0, n);
+      launches += 4;
+      bool excl_unknown = b->m.any_excl_unknown;
+      if (plan) {
+        excl_unknown = false;
+        for (int s2 = w.s0; s2 < w.s1 && !excl_unknown; ++s2)
+          excl_unknown = (b->grp_flags[b->step_group[s2]] & RBGTOPO_STEP_EXCLUSIVE) != 0;
+      }
+      if (excl_unknown) {
+        k_shard_select<<<n, nth, fast_smem_bytes(nth / 32, HT, CAP), s>>>(topo_dev(c), d, w.s0, 1, 0, HT, CAP);
+        rc = p2p_exchange(c, s, b->excl.p + (size_t)w.rr0 * KS, rows, &parity);
+        if (rc) return rc;
+        d.excl_all = c->xbuf.p + (long long)parity * c->cfg.world * c->p2p.slot_stride - (long long)w.rr0 * KS;
+        d.excl_part_stride = c->p2p.slot_stride;
+        launches += 3;
+      } else {
+        d.parts = 1;  // k_greedy never reads excl_all for steps with a fixed / no domain
+      }
+      k_greedy<<<(n + SEL_WARPS - 1) / SEL_WARPS, SEL_THREADS, 0, s>>>(topo_dev(c), d, w.s0, n, plan ? 1 : 0);
+      ++launches;
+    }
+    if (timed) {
+      CK(cudaEventRecord(b->it_ev[e0 + 2], s));
+      b->passes += 1;
+    }
+    b->untimed_or_timed_passes += 1;
+  }
+  CK(cudaGetLastError());
+  b->ran = true;
+  b->pend_launches += launches;
+  std::lock_guard<std::mutex> g(c->stat_mu);
+  c->launches += launches;
+  return RBGTOPO_OK;
+}
+
+int32_t rbgtopo_p2p_stats(rbgtopo_ctx* c, int64_t* peer_bytes_last_pass, int32_t* timed_out) {
+  if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
+  if (peer_bytes_last_pass) *peer_bytes_last_pass = c->p2p_bytes_last;
+  if (timed_out) {
+    *timed_out = 0;
+    if (c->p2p_ctr.p) {
+      CK(cudaSetDevice(c->cfg.device));
+      int v = 0;
+      CK(cudaMemcpy(&v, c->p2p_ctr.p + 1, 4, cudaMemcpyDeviceToHost));
+      *timed_out = v;
+    }
+  }
+  return RBGTOPO_OK;
 }
 
 int32_t rbgtopo_set_stream(rbgtopo_ctx* c, void* stream) {

@@ -196,6 +196,43 @@ class TopoPlacer:
         self._check(self.lib.rbgtopo_shard_assign(self._h, handle,
                                                   C.c_void_p(keys2_all_ptr) if keys2_all_ptr else None))
 
+    # -- all-gather over NVLink peer memory inside the library
+    def p2p_export(self, rows_cap: int = 0):
+        """(64-byte IPC handle, device pointer) of this rank's exchange buffer."""
+        buf = C.create_string_buffer(64)
+        ptr = C.c_void_p()
+        self._check(self.lib.rbgtopo_p2p_export(self._h, rows_cap, buf, 64, C.byref(ptr)))
+        return bytes(buf.raw), ptr.value
+
+    def p2p_import(self, handles=None, ptrs=None) -> None:
+        """handles: list of `world` 64-byte IPC handles (one process per GPU), or ptrs: list of `world`
+        device pointers (contexts of one process)."""
+        if ptrs is not None:
+            arr = (C.c_void_p * len(ptrs))(*ptrs)
+            self._check(self.lib.rbgtopo_p2p_import(self._h, None, arr))
+        else:
+            blob = b"".join(handles)
+            self._check(self.lib.rbgtopo_p2p_import(self._h, C.c_char_p(blob), None))
+
+    def p2p_connect(self, D) -> None:
+        """One process per GPU: exchange the IPC handles over torch.distributed (plumbing) and map the peers."""
+        import torch
+        h, _ = self.p2p_export()
+        mine = torch.frombuffer(bytearray(h), dtype=torch.uint8).cuda()
+        allh = torch.empty(D.world * 64, dtype=torch.uint8, device="cuda")
+        D.dist.all_gather_into_tensor(allh, mine)
+        raw = bytes(allh.cpu().numpy().tobytes())
+        self.p2p_import(handles=[raw[64 * g: 64 * (g + 1)] for g in range(D.world)])
+        D.barrier()
+
+    def run_staged_p2p(self, handle: int, iters: int = 1) -> None:
+        self._check(self.lib.rbgtopo_run_staged_p2p(self._h, handle, iters))
+
+    def p2p_stats(self):
+        b, t = C.c_int64(), C.c_int32()
+        self._check(self.lib.rbgtopo_p2p_stats(self._h, C.byref(b), C.byref(t)))
+        return dict(peer_bytes_last_pass=b.value, timed_out=bool(t.value))
+
     def set_stream(self, cuda_stream: Optional[int]) -> None:
         """None restores the internal per-call streams.  A torch default stream has
         handle 0 (the legacy NULL stream): it is passed as cudaStreamLegacy (0x1)."""

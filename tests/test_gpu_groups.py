@@ -187,21 +187,25 @@ def test_plan_dense_matrix_and_lists_match_oracle_per_wave():
     eng.close()
 
 
-@pytest.mark.parametrize("var", ["RBGTOPO_VERIFY_PLAN", "RBGTOPO_PER_WAVE_PLAN", "RBGTOPO_SPLIT_MIN_GROUPS"])
+@pytest.mark.parametrize("var", ["RBGTOPO_VERIFY_PLAN", "RBGTOPO_PER_WAVE_PLAN", "RBGTOPO_SPLIT_MIN_GROUPS",
+                                 "RBGTOPO_CONCURRENT_PLAN", "RBGTOPO_EMIT_TMA", "RBGTOPO_CONCURRENT_PLAN+RBGTOPO_EMIT_TMA"])
 def test_plan_variants_in_a_subprocess(var):
     """The library reads its switches when it loads, hence the subprocess.
     RBGTOPO_VERIFY_PLAN: every place_groups / stage_groups call compares the plan k_expand_plan
     wrote in HBM (and the host-side geometry) word for word with the host plan builder.
     RBGTOPO_PER_WAVE_PLAN: the fallback that runs one launch per wave and chains placements
     through the plan blob (what groups too large for k_plan_group's shared memory take).
-    RBGTOPO_SPLIT_MIN_GROUPS=1 (-> 2): place_groups pipelines every fleet as two halves (opt-in)."""
+    RBGTOPO_SPLIT_MIN_GROUPS=1 (-> 2): place_groups pipelines every fleet as two halves (opt-in).
+    RBGTOPO_CONCURRENT_PLAN: k_plan_group in record mode on a second stream + k_plan_correct (opt-in).
+    RBGTOPO_EMIT_TMA: the dense rows of plans through k_emit_tma (TMA bulk stores) instead of k_score_emit."""
     import os
     import subprocess
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ)
-    env[var] = "1"
+    for v in var.split("+"):
+        env[v] = "1"
     r = subprocess.run(
         [sys.executable, "-m", "pytest", "tests/test_gpu_groups.py", "-q", "-m", "gpu", "-x", "-k", "not subprocess"],
         cwd=root, env=env, capture_output=True, text=True, timeout=600)

@@ -163,3 +163,73 @@ def test_group_plans_sharded_on_one_device(world):
             e.release(h)
         for e in engs:
             e.close()
+
+
+def _connect_p2p(engs):
+    """Contexts of one process: exchange the raw device pointers of the exchange buffers."""
+    ptrs = [e.p2p_export(rows_cap=4096)[1] for e in engs]
+    for e in engs:
+        e.p2p_import(ptrs=ptrs)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_p2p_allgather_inside_the_library(world):
+    """rbgtopo_run_staged_p2p: the per-wave exchange of the rank-local lists done by the library's own
+    kernels (peer stores + release/acquire flags), no collective library.  Same results as the oracle
+    (step batches) / as replicated selection (plans), NVLink byte count reported, no timeout."""
+    import torch
+    from oracle import placer as oracle_placer
+    from rbg_b200.plugin import B200TopoPodGroupManager
+    from test_gpu_groups import _fleet
+    from test_gpu_parity import _random_steps
+    from test_plugin_host import OraclePlacer
+    for n, seed, excl in [(4096, 1, False), (6000, 2, True)]:
+        topo = synth.make_topology(n, seed=seed, tiers=4, owned_frac=0.25 if excl else 0.0)
+        blob = _random_steps(topo, 70 + seed, 24, excl=excl, gang=True)
+        ref = oracle_placer.place(topo, blob)
+        engs = _engines(topo, world)
+        _connect_p2p(engs)
+        hs = [e.stage(blob) for e in engs]
+        for rep in range(3):      # the parity / sequence bookkeeping survives repeated passes
+            for e, h in zip(engs, hs):
+                e.run_staged_p2p(h, 1)
+        torch.cuda.synchronize()
+        for r, (e, h) in enumerate(zip(engs, hs)):
+            assign, status, domain = e.fetch(h)
+            st = e.p2p_stats()
+            assert not st["timed_out"] and st["peer_bytes_last_pass"] > 0, (world, r, st)
+            assert np.array_equal(assign, ref["assign"]), (world, r, n)
+            assert np.array_equal(status, ref["status"]) and np.array_equal(domain, ref["domain"]), (world, r, n)
+            lo, hi = e.slab()
+            for row in range(0, ref["matrix"].shape[0], 5):
+                got = e.read_scores(h, row)
+                assert np.array_equal(got.view(np.uint32), ref["matrix"][row, lo:hi].view(np.uint32)), (world, r, row)
+            for rr in range(ref["topk"].shape[0]):
+                assert np.array_equal(e.read_topk(h, rr, 32), ref["topk"][rr]), (world, r, rr)
+            e.release(h)
+        # whole groups: multi-wave plan through the p2p pipeline == replicated selection == oracle wave loop
+        rbgs = _fleet(n, 24, seed=9, excl_every=3 if excl else 0, gang_every=4)
+        oref = B200TopoPodGroupManager(OraclePlacer(topo)).reconcile_pod_groups_by_waves(rbgs)
+        gblob, _ = B200TopoPodGroupManager(engs[0]).groups_blob(rbgs)
+        hs = [e.stage_groups(gblob) for e in engs]
+        for e, h in zip(engs, hs):
+            e.run_staged_p2p(h, 1)
+        torch.cuda.synchronize()
+        res = [e.fetch(h) for e, h in zip(engs, hs)]
+        for r, (e, h) in enumerate(zip(engs, hs)):
+            assert not e.p2p_stats()["timed_out"]
+            e.release(h)
+            h2 = e.stage_groups(gblob)
+            e.run_staged(h2, 1)
+            rep_res = e.fetch(h2)
+            e.release(h2)
+            for x, y in zip(res[r], rep_res):
+                assert np.array_equal(x, y), (world, r, n)
+        off = 0
+        for i, rr in enumerate(oref):
+            want = list(rr.nodes.values())
+            if rr.status != 1:   # non-gang partial groups are finished by the host loop, not by a staged plan
+                assert res[0][0][off:off + len(want)].tolist() == want and res[0][1][i] == rr.status, (world, n, i)
+            off += len(want)
+        for e in engs:
+            e.close()
