@@ -428,11 +428,19 @@ def run_config(D, args, cfg_name, with_clocks):
         # clock soak: K steps last a few ms, far below nvidia-smi's sampling period, so the
         # same step is run untimed for ~0.6 s first; the clock samples cover soak + timed region
         t_soak = time.perf_counter()
-        while time.perf_counter() - t_soak < (args.soak if with_clocks else 0.1):
+        soak_s = args.soak if with_clocks else 0.1
+        while True:   # every rank runs the SAME number of steps (the sharded modes are SPMD): rank 0's clock decides
             for _ in range(50):
                 device_step()
             for h in handles:
                 eng.fetch(h)
+            more = 1.0 if time.perf_counter() - t_soak < soak_s else 0.0
+            if world > 1:
+                t = torch.tensor([more], dtype=torch.float64, device="cuda")
+                D.dist.broadcast(t, src=0)
+                more = float(t.item())
+            if more < 0.5:
+                break
         launches0 = eng.stats()["kernel_launches"]
         D.barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

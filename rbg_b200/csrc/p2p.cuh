@@ -7,12 +7,12 @@
 //     flags [2 parities][world sources] u64 (16 words apart)
 // Phase s of the SPMD call sequence (a wave's lists, or the restricted reselect of its exclusive
 // steps) uses parity s & 1:
-//   k_p2p_push  rank g copies its rows into slot [parity][g] of EVERY rank's buffer (peer stores over
-//               NVLink, 16-byte vectors), fences system-wide, and the last CTA publishes
-//               flags[parity][g] = seq on every rank (st.release.sys);
-//   k_p2p_wait  one warp: lane r spins (ld.acquire.sys) until flags[parity][r] >= seq, bounded by a
-//               clock64 timeout that raises *err instead of hanging the GPU; the consumer (k_merge /
-//               k_greedy) is simply the next kernel of the stream.
+//   push  fused into the producer (k_shard_select, select_fast.cuh): every CTA stores its rows into slot
+//         [parity][g] of EVERY rank's buffer (peer stores over NVLink), fences system-wide, and the last
+//         CTA of the grid publishes flags[parity][g] = seq on every rank (st.release.sys);
+//   wait  fused into the consumer (k_merge / k_greedy, select.cuh): lane r of the CTA's first warp spins
+//         (ld.acquire.sys) until flags[parity][r] >= seq, bounded by a clock64 timeout that raises *err
+//         instead of hanging the GPU (p2p_wait_cta below).
 // Two parities suffice: a rank pushes phase s + 2 only after its own consumer of phase s + 1 ran, which
 // needed every peer's push of s + 1, which those peers issued after their consumers of phase s.
 // No NCCL call, no host round trip on the step path.
@@ -40,43 +40,29 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
   return v;
 }
 
-// src: this rank's rows of the phase (n_u64 = rows * KS elements, 16-byte aligned); done: per-ctx counter.
-__global__ void __launch_bounds__(256) k_p2p_push(P2PDev p, const unsigned long long* __restrict__ src, long long n_u64,
-                                                  int parity, unsigned long long seq, int* __restrict__ done) {
-  const long long slot = ((long long)parity * p.world + p.rank) * p.slot_stride;
-  const long long n2 = n_u64 >> 1;  // KS is even: whole 16-byte vectors
-  const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(src);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
-    const ulonglong2 v = s2[i];
-    for (int g = 0; g < p.world; ++g) reinterpret_cast<ulonglong2*>(p.peer[g] + slot)[i] = v;
+// Prologue of the consuming kernel: lane r < world of warp 0 spins on source r, then the CTA proceeds.
+// world <= 1: nothing to wait for.
+struct P2PWait {
+  const unsigned long long* flags;  // own flag block + parity * world * P2P_FLAG_STRIDE
+  unsigned long long seq;
+  long long timeout_cycles;
+  int* err;
+  int world;
+};
+__device__ __forceinline__ void p2p_wait_cta(const P2PWait& w) {
+  if (w.world <= 1) return;
+  if ((int)threadIdx.x < w.world) {
+    const unsigned long long* f = w.flags + (long long)threadIdx.x * P2P_FLAG_STRIDE;
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u64(f) < w.seq) {
+      if (clock64() - t0 > w.timeout_cycles) {
+        *w.err = 1;
+        break;
+      }
+      __nanosleep(32);
+    }
   }
-  __threadfence_system();  // this CTA's peer stores are visible system-wide before it reports
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const int prev = atomicAdd(done, 1);
-    if (prev == (int)gridDim.x - 1) {  // last CTA: everybody's data is out
-      __threadfence_system();
-      for (int g = 0; g < p.world; ++g)
-        st_release_sys_u64(p.peer[g] + p.flags_off + ((long long)parity * p.world + p.rank) * P2P_FLAG_STRIDE, seq);
-      *done = 0;
-    }
-  }
-}
-
-// One warp; lane r waits for source r.  timeout_cycles bounds the spin (a peer that never arrives must
-// not hang this GPU): on expiry *err = 1 and the stream carries on (rbgtopo_fetch reports the error).
-__global__ void k_p2p_wait(P2PDev p, int parity, unsigned long long seq, long long timeout_cycles, int* __restrict__ err) {
-  const int r = threadIdx.x;
-  if (r >= p.world) return;
-  const unsigned long long* f = p.peer[p.rank] + p.flags_off + ((long long)parity * p.world + r) * P2P_FLAG_STRIDE;
-  const long long t0 = clock64();
-  while (ld_acquire_sys_u64(f) < seq) {
-    if (clock64() - t0 > timeout_cycles) {
-      *err = 1;
-      break;
-    }
-    __nanosleep(64);
-  }
 }
 
 }  // namespace rbgtopo

@@ -2497,7 +2497,7 @@ int32_t rbgtopo_shard_wave_score(rbgtopo_ctx* c, int32_t handle, int32_t wave, v
     wave_table(b, w, &CAP, &HT);
     const int nth = std::max(128, 32 * w.maxp);
     if (fast_smem_bytes(nth / 32, HT, CAP) <= kFastSmemMax) {
-      k_shard_select<<<n, nth, fast_smem_bytes(nth / 32, HT, CAP), s>>>(topo_dev(c), d, w.s0, 0, plan ? SEL_CORRECT : 0, HT, CAP);
+      k_shard_select<<<n, nth, fast_smem_bytes(nth / 32, HT, CAP), s>>>(topo_dev(c), d, w.s0, 0, plan ? SEL_CORRECT : 0, HT, CAP, P2PDev{}, 0, 0, 0ull, nullptr);
     } else {
       if (plan) return fail(RBGTOPO_ELIMIT, "plan step with more than %d patched nodes on the sharded path", CAP);
       k_select<<<n, 32 * w.maxp, select_smem_bytes(w.maxp), s>>>(topo_dev(c), d, 0);
@@ -2541,14 +2541,14 @@ int32_t rbgtopo_shard_wave_merge(rbgtopo_ctx* c, int32_t handle, int32_t wave, c
       excl_unknown = (b->grp_flags[b->step_group[s2]] & RBGTOPO_STEP_EXCLUSIVE) != 0;
   }
   if (n > 0) {
-    k_merge<<<(n + SEL_WARPS - 1) / SEL_WARPS, SEL_THREADS, 0, s>>>(topo_dev(c), d, w.s0, n);
+    k_merge<<<(n + SEL_WARPS - 1) / SEL_WARPS, SEL_THREADS, 0, s>>>(topo_dev(c), d, w.s0, n, P2PWait{});
     ++launches;
     if (excl_unknown) {
       int CAP, HT;
       wave_table(b, w, &CAP, &HT);
       const int nth = std::max(128, 32 * w.maxp);
       if (fast_smem_bytes(nth / 32, HT, CAP) <= kFastSmemMax)
-        k_shard_select<<<n, nth, fast_smem_bytes(nth / 32, HT, CAP), s>>>(topo_dev(c), d, w.s0, 1, 0, HT, CAP);
+        k_shard_select<<<n, nth, fast_smem_bytes(nth / 32, HT, CAP), s>>>(topo_dev(c), d, w.s0, 1, 0, HT, CAP, P2PDev{}, 0, 0, 0ull, nullptr);
       else
         k_select<<<n, 32 * w.maxp, select_smem_bytes(w.maxp), s>>>(topo_dev(c), d, 1);
       ++launches;
@@ -2587,7 +2587,7 @@ int32_t rbgtopo_shard_wave_assign(rbgtopo_ctx* c, int32_t handle, int32_t wave, 
   const int n = w.s1 - w.s0;
   const bool plan = !b->wave_begin.empty();
   if (n > 0) {
-    k_greedy<<<(n + SEL_WARPS - 1) / SEL_WARPS, SEL_THREADS, 0, s>>>(topo_dev(c), d, w.s0, n, plan ? 1 : 0);
+    k_greedy<<<(n + SEL_WARPS - 1) / SEL_WARPS, SEL_THREADS, 0, s>>>(topo_dev(c), d, w.s0, n, plan ? 1 : 0, P2PWait{});
     ++launches;
   }
   const bool last = !plan || wave + 2 == (int)b->wave_begin.size();
@@ -2677,26 +2677,9 @@ int32_t rbgtopo_p2p_import(rbgtopo_ctx* c, const void* handles_all, void* const*
   return RBGTOPO_OK;
 }
 
-namespace {
-// one exchange phase on stream s: push `rows` role rows starting at `src`, wait for every rank's push
-int p2p_exchange(rbgtopo_ctx* c, cudaStream_t s, const unsigned long long* src, long long rows, int* parity_out) {
-  if (rows > c->p2p_rows_cap) return fail(RBGTOPO_ELIMIT, "%lld role rows in one wave exceed the exchange buffer (%d)", rows, c->p2p_rows_cap);
-  const unsigned long long seq = ++c->p2p_seq;
-  const int parity = (int)(seq & 1ull);
-  const long long n_u64 = rows * KS;
-  const int grid = (int)std::min<long long>(std::max<long long>(1, (n_u64 / 2 + 255) / 256), 2 * c->sm_count);
-  k_p2p_push<<<grid, 256, 0, s>>>(c->p2p, src, n_u64, parity, seq, c->p2p_ctr.p);
-  k_p2p_wait<<<1, 32, 0, s>>>(c->p2p, parity, seq, 4000000000LL, c->p2p_ctr.p + 1);
-  CK(cudaGetLastError());
-  c->p2p_bytes_last += n_u64 * 8 * (c->cfg.world - 1);
-  *parity_out = parity;
-  return RBGTOPO_OK;
-}
-}  // namespace
-
 // The sharded pipeline of a staged batch / plan with the exchanges done by the library itself:
-// per wave k_shard_select -> push + wait -> k_merge [-> restricted reselect -> push + wait] -> k_greedy,
-// all enqueued on the call's stream; no NCCL, no host synchronisation.  SPMD: every rank calls it
+// per wave k_shard_select (+ fused push) -> k_merge (waits first) [-> restricted reselect (+ push)] ->
+// k_greedy (waits for it), all enqueued on the call's stream; no NCCL, no host synchronisation.  SPMD: every rank calls it
 // with the same staged batch.
 int32_t rbgtopo_run_staged_p2p(rbgtopo_ctx* c, int32_t handle, int32_t iters) {
   if (!c) return fail(RBGTOPO_EINVAL, "null ctx");
@@ -2738,33 +2721,52 @@ int32_t rbgtopo_run_staged_p2p(rbgtopo_ctx* c, int32_t handle, int32_t iters) {
       const int nth = std::max(128, 32 * w.maxp);
       if (fast_smem_bytes(nth / 32, HT, CAP) > kFastSmemMax)
         return fail(RBGTOPO_ELIMIT, "a step's patched set exceeds shared memory on the sharded path");
-      k_shard_select<<<n, nth, fast_smem_bytes(nth / 32, HT, CAP), s>>>(topo_dev(c), d, w.s0, 0, plan ? SEL_CORRECT : 0, HT, CAP);
       const long long rows = std::max(1, w.rr1 - w.rr0);
-      int parity = 0;
-      rc = p2p_exchange(c, s, b->lists.p + (size_t)w.rr0 * KS, rows, &parity);
-      if (rc) return rc;
-      d.parts = c->cfg.world;
+      if (rows > c->p2p_rows_cap)
+        return fail(RBGTOPO_ELIMIT, "%lld role rows in one wave exceed the exchange buffer (%d)", rows, c->p2p_rows_cap);
+      static const long long timeout_cycles =
+          (getenv("RBGTOPO_P2P_TIMEOUT_MS") ? std::max(1, atoi(getenv("RBGTOPO_P2P_TIMEOUT_MS"))) : 2000) * 2000000LL;  // ~2 GHz
+      const int W = c->cfg.world;
+      auto phase = [&](unsigned long long* seq, int* parity, P2PWait* pw) {  // next exchange phase of the SPMD sequence
+        *seq = ++c->p2p_seq;
+        *parity = (int)(*seq & 1ull);
+        pw->flags = c->xbuf.p + c->p2p.flags_off + (long long)*parity * W * P2P_FLAG_STRIDE;
+        pw->seq = *seq;
+        pw->timeout_cycles = timeout_cycles;
+        pw->err = c->p2p_ctr.p + 1;
+        pw->world = W;
+        c->p2p_bytes_last += rows * KS * 8 * (W - 1);
+      };
+      unsigned long long seq;
+      int parity;
+      P2PWait pw{};
+      phase(&seq, &parity, &pw);
+      // select + fused push (peer stores of every list, release flags by the last CTA)
+      k_shard_select<<<n, nth, fast_smem_bytes(nth / 32, HT, CAP), s>>>(topo_dev(c), d, w.s0, 0, plan ? SEL_CORRECT : 0, HT, CAP,
+                                                                       c->p2p, w.rr0, parity, seq, c->p2p_ctr.p);
+      d.parts = W;
       d.part_stride = c->p2p.slot_stride;
-      d.lists_all = c->xbuf.p + (long long)parity * c->cfg.world * c->p2p.slot_stride - (long long)w.rr0 * KS;
-      k_merge<<<(n + SEL_WARPS - 1) / SEL_WARPS, SEL_THREADS, 0, s>>>(topo_dev(c), d, w.s0, n);
-      launches += 4;
+      d.lists_all = c->xbuf.p + (long long)parity * W * c->p2p.slot_stride - (long long)w.rr0 * KS;
+      k_merge<<<(n + SEL_WARPS - 1) / SEL_WARPS, SEL_THREADS, 0, s>>>(topo_dev(c), d, w.s0, n, pw);  // waits (acquire) first
+      launches += 2;
       bool excl_unknown = b->m.any_excl_unknown;
       if (plan) {
         excl_unknown = false;
         for (int s2 = w.s0; s2 < w.s1 && !excl_unknown; ++s2)
           excl_unknown = (b->grp_flags[b->step_group[s2]] & RBGTOPO_STEP_EXCLUSIVE) != 0;
       }
+      P2PWait pw2{};
       if (excl_unknown) {
-        k_shard_select<<<n, nth, fast_smem_bytes(nth / 32, HT, CAP), s>>>(topo_dev(c), d, w.s0, 1, 0, HT, CAP);
-        rc = p2p_exchange(c, s, b->excl.p + (size_t)w.rr0 * KS, rows, &parity);
-        if (rc) return rc;
-        d.excl_all = c->xbuf.p + (long long)parity * c->cfg.world * c->p2p.slot_stride - (long long)w.rr0 * KS;
+        phase(&seq, &parity, &pw2);
+        k_shard_select<<<n, nth, fast_smem_bytes(nth / 32, HT, CAP), s>>>(topo_dev(c), d, w.s0, 1, 0, HT, CAP, c->p2p, w.rr0, parity, seq,
+                                                                         c->p2p_ctr.p);
+        d.excl_all = c->xbuf.p + (long long)parity * W * c->p2p.slot_stride - (long long)w.rr0 * KS;
         d.excl_part_stride = c->p2p.slot_stride;
-        launches += 3;
+        ++launches;
       } else {
         d.parts = 1;  // k_greedy never reads excl_all for steps with a fixed / no domain
       }
-      k_greedy<<<(n + SEL_WARPS - 1) / SEL_WARPS, SEL_THREADS, 0, s>>>(topo_dev(c), d, w.s0, n, plan ? 1 : 0);
+      k_greedy<<<(n + SEL_WARPS - 1) / SEL_WARPS, SEL_THREADS, 0, s>>>(topo_dev(c), d, w.s0, n, plan ? 1 : 0, pw2);
       ++launches;
     }
     if (timed) {

@@ -17,6 +17,7 @@
 // (snapshot semantics, spec §3.7).
 #pragma once
 #include "kernels.cuh"
+#include "p2p.cuh"
 
 namespace rbgtopo {
 
@@ -497,7 +498,9 @@ __device__ __forceinline__ int merge_parts(const unsigned long long* src, long l
 }
 
 // ---- world > 1: merged[rolerow] = top-K over the ranks' lists; D* per step
-__global__ void __launch_bounds__(SEL_THREADS) k_merge(TopoDev t, BatchDev b, int step_begin, int count) {
+// pw.world > 1: the lists come from the in-library exchange — wait (acquire) for every source first.
+__global__ void __launch_bounds__(SEL_THREADS) k_merge(TopoDev t, BatchDev b, int step_begin, int count, P2PWait pw) {
+  p2p_wait_cta(pw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int idx = blockIdx.x * SEL_WARPS + warp;
   if (idx >= count) return;
@@ -519,7 +522,8 @@ __global__ void __launch_bounds__(SEL_THREADS) k_merge(TopoDev t, BatchDev b, in
 }
 
 // ---- world > 1: final lists (restricted ones merged over the ranks) + greedy
-__global__ void __launch_bounds__(SEL_THREADS) k_greedy(TopoDev t, BatchDev b, int step_begin, int count, int chain) {
+__global__ void __launch_bounds__(SEL_THREADS) k_greedy(TopoDev t, BatchDev b, int step_begin, int count, int chain, P2PWait pw) {
+  p2p_wait_cta(pw);
   __shared__ unsigned long long sList[SEL_WARPS][MAXP][KS];
   __shared__ int sTakenNode[SEL_WARPS][KS];
   __shared__ int sTakenAmt[SEL_WARPS][KS];

@@ -21,6 +21,7 @@
 // Falls back to k_select_assign (select.cuh) when a step's patched set does not fit.
 #pragma once
 #include "select.cuh"
+#include "p2p.cuh"
 
 namespace rbgtopo {
 
@@ -388,8 +389,12 @@ k_select_assign_fast(TopoDev t, BatchDev b, int step_begin, int mode, int HT, in
 // unrestricted: their top-1 decides D* after the all-gather) into b.lists; the matrix
 // corrections of multi-wave plans are issued here (mode & SEL_CORRECT).
 // pass2 == 1: those exclusive roles again, restricted to D*, into b.excl.
+// px.world > 1: the CTA also stores its rows straight into every rank's exchange buffer (p2p.cuh:
+// slot [parity][this rank], row index relative to px_row0) and the last CTA of the grid publishes the
+// release flags — the all-gather is fused into the kernel that produces the lists.
 __global__ void __launch_bounds__(32 * MAXP)
-k_shard_select(TopoDev t, BatchDev b, int step_begin, int pass2, int mode, int HT, int CAP) {
+k_shard_select(TopoDev t, BatchDev b, int step_begin, int pass2, int mode, int HT, int CAP, P2PDev px, int px_row0,
+               int px_parity, unsigned long long px_seq, int* __restrict__ px_done) {
   extern __shared__ __align__(16) unsigned char fs_smem[];
   __shared__ unsigned long long sAcc[MAXP][KS], sPat[MAXP][KS], sOut[MAXP][KS];
   __shared__ int sAccAv[MAXP][KS], sPatAv[MAXP][KS], sOutAv[MAXP][KS];
@@ -412,23 +417,47 @@ k_shard_select(TopoDev t, BatchDev b, int step_begin, int pass2, int mode, int H
   const StepHdr h = load_hdr(b, step);
   const bool excl_step = (h.flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
   const bool unknown = excl_step && h.fixed_domain < 0;
-  if ((h.flags & STEP_SKIP) || (pass2 && !unknown)) {  // CTA-uniform
+  // what this warp's row is worth to the peers: the selected list, or zeros (skipped step, role not reselected)
+  unsigned long long mine = 0ull;
+  const bool idle = (h.flags & STEP_SKIP) || (pass2 && !unknown);  // CTA-uniform
+  if (idle) {
     if (!pass2 && warp < h.P) b.lists[(size_t)(h.rolerow_off + warp) * KS + lane] = 0;
-    return;
+  } else {
+    build_table(t, b, h, T, HT, PB, !pass2 && (mode & SEL_CORRECT) != 0, &sCnt);
+    if (warp < h.P) {
+      const int p = warp;
+      const bool rexcl = excl_step && (b.blob[h.role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE);
+      const int K = role_k(b, h, p, t.n);
+      if (!pass2) {
+        const int dom = (rexcl && !unknown) ? h.fixed_domain : DOM_ANY;
+        select_role_fast(t, b, h, p, K, dom, T, sAcc[p], sAccAv[p], sPat[p], sPatAv[p], sOut[p], sOutAv[p]);
+        mine = sOut[p][lane];
+        b.lists[(size_t)(h.rolerow_off + p) * KS + lane] = mine;
+      } else if (rexcl) {
+        const int d = b.dstar[step];
+        select_role_fast(t, b, h, p, K, d >= 0 ? d : DOM_NONE, T, sAcc[p], sAccAv[p], sPat[p], sPatAv[p], sOut[p], sOutAv[p]);
+        mine = sOut[p][lane];
+        b.excl[(size_t)(h.rolerow_off + p) * KS + lane] = mine;
+      }
+    }
   }
-  build_table(t, b, h, T, HT, PB, !pass2 && (mode & SEL_CORRECT) != 0, &sCnt);
-  if (warp >= h.P) return;
-  const int p = warp;
-  const bool rexcl = excl_step && (b.blob[h.role_off + 4 * p + 3] & RBGTOPO_ROLE_EXCLUSIVE);
-  const int K = role_k(b, h, p, t.n);
-  if (!pass2) {
-    const int dom = (rexcl && !unknown) ? h.fixed_domain : DOM_ANY;
-    select_role_fast(t, b, h, p, K, dom, T, sAcc[p], sAccAv[p], sPat[p], sPatAv[p], sOut[p], sOutAv[p]);
-    b.lists[(size_t)(h.rolerow_off + p) * KS + lane] = sOut[p][lane];
-  } else if (rexcl) {
-    const int d = b.dstar[step];
-    select_role_fast(t, b, h, p, K, d >= 0 ? d : DOM_NONE, T, sAcc[p], sAccAv[p], sPat[p], sPatAv[p], sOut[p], sOutAv[p]);
-    b.excl[(size_t)(h.rolerow_off + p) * KS + lane] = sOut[p][lane];
+  if (px.world > 1) {  // fused all-gather: rows -> every rank's buffer, then the last CTA raises the flags
+    if (warp < h.P) {
+      const long long off = ((long long)px_parity * px.world + px.rank) * px.slot_stride +
+                            (long long)(h.rolerow_off + warp - px_row0) * KS + lane;
+      for (int g = 0; g < px.world; ++g) px.peer[g][off] = mine;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const int prev = atomicAdd(px_done, 1);
+      if (prev == (int)gridDim.x - 1) {
+        __threadfence_system();
+        for (int g = 0; g < px.world; ++g)
+          st_release_sys_u64(px.peer[g] + px.flags_off + ((long long)px_parity * px.world + px.rank) * P2P_FLAG_STRIDE, px_seq);
+        *px_done = 0;
+      }
+    }
   }
 }
 
