@@ -32,33 +32,10 @@ namespace rbgtopo {
 
 constexpr int EMIT_SUB = 512;                 // nodes per item (2 KB per row store)
 constexpr int EMIT_WARPS = 8;                 // warps per CTA (one CTA per SM)
-constexpr int EMIT_TAB_WORDS = 12;            // emit record per step: gid, flags, P, rep_off, 8 packed roles
 constexpr int EMIT_MAX_BSTEPS = 8;
 
 __host__ __device__ inline size_t emit_tma_smem_bytes(int stages) {
   return (size_t)EMIT_WARPS * ((size_t)stages * EMIT_SUB * 4 + EMIT_MAX_BSTEPS * EMIT_TAB_WORDS * 4);
-}
-
-// packed role: count | need << 6 | exclusive << 11 | demand << 12   (count <= 32, need <= 16, demand <= 32767)
-__device__ __forceinline__ int emit_pack_role(int count, int demand, int need, int flags) {
-  return count | (need << 6) | ((flags & RBGTOPO_ROLE_EXCLUSIVE) << 11) | (demand << 12);
-}
-
-// One thread per step: blob -> emit table.  Runs once per staged batch (after the blob / the expanded
-// plan is in HBM); the table depends on nothing the waves change.
-__global__ void k_emit_table(const int* __restrict__ blob, int n_steps, int* __restrict__ etab) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_steps) return;
-  const int* hdr = blob + RBGTOPO_HDR_WORDS + (size_t)s * RBGTOPO_STEP_WORDS;
-  const int P = hdr[3];
-  const int* roles = blob + hdr[4];
-  int* e = etab + (size_t)s * EMIT_TAB_WORDS;
-  e[0] = hdr[0];
-  e[1] = hdr[1];
-  e[2] = P;
-  e[3] = hdr[12];
-  for (int p = 0; p < MAXP; ++p)
-    e[4 + p] = p < P ? emit_pack_role(roles[4 * p], roles[4 * p + 1], roles[4 * p + 2], roles[4 * p + 3]) : 0;
 }
 
 __device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {

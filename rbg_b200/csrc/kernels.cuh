@@ -80,6 +80,16 @@ struct BatchDev {
   int corr_w;     // 1 + largest role count of a step in the batch
 };
 
+// ---- emit table of a multi-wave plan: what the dense-matrix kernels need per step, 12 words —
+// gid, step flags, P, first dense row, 8 packed role rows (count | need << 6 | exclusive << 11 | demand << 12;
+// count <= 32, need <= 16, demand <= 32767).  Written by k_plan_etab (plan.cuh) straight from the GROUPS
+// blob, before the rest of the plan geometry exists, so the matrix can be emitted while the host still
+// computes section offsets and patch capacities.
+constexpr int EMIT_TAB_WORDS = 12;
+__host__ __device__ __forceinline__ int emit_pack_role(int count, int demand, int need, int flags) {
+  return count | (need << 6) | ((flags & RBGTOPO_ROLE_EXCLUSIVE) << 11) | (demand << 12);
+}
+
 // ---------------------------------------------------------------- helpers
 __device__ __forceinline__ uint32_t orderable_u32(float x) {
   uint32_t b = __float_as_uint(x);
@@ -218,6 +228,39 @@ k_base(TopoDev t, const int2* __restrict__ tiles, int fmin_staged, int fmin_byte
     acc += __shfl_xor_sync(FULL, acc, 1);
     if (r < r1 && sub == 0) base_out[r] = acc + (float)RBGTOPO_SELF_W * (float)fm[r];
   }
+}
+
+// ======================================================= background order, small snapshots
+// order[0 .. hi-lo) = the nodes [lo, hi) sorted by key(base[n], n) descending, for slabs of at most
+// ORDER_SMALL_MAX nodes: ONE CTA, bitonic network in shared memory (keys are unique, so the order is the
+// same total order a radix sort gives).  10 000 nodes: ~8 us instead of the ~40 us a 4-pass library radix
+// sort plus its key build / expansion kernels take at this size; larger slabs keep the library sort.
+constexpr int ORDER_SMALL_MAX = 16384;
+constexpr int ORDER_SMALL_THREADS = 1024;
+__global__ void __launch_bounds__(ORDER_SMALL_THREADS) k_order_sort_small(const float* __restrict__ base, int lo, int hi,
+                                                                          unsigned long long* __restrict__ order) {
+  extern __shared__ __align__(16) unsigned long long so_keys[];
+  const int n = hi - lo;
+  int p2 = 32;
+  while (p2 < n) p2 <<= 1;
+  for (int i = threadIdx.x; i < p2; i += ORDER_SMALL_THREADS) so_keys[i] = i < n ? make_key(base[lo + i], lo + i) : 0ull;  // 0 sorts last
+  __syncthreads();
+  for (int k = 2; k <= p2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (p2 >> 1); t += ORDER_SMALL_THREADS) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the t-th pair at distance j
+        const int l = i | j;
+        const unsigned long long a = so_keys[i], b2 = so_keys[l];
+        const bool desc = (i & k) == 0;  // final pass (k == p2): every pair descending
+        if ((a < b2) == desc) {
+          so_keys[i] = b2;
+          so_keys[l] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n; i += ORDER_SMALL_THREADS) order[i] = so_keys[i];
 }
 
 }  // namespace rbgtopo

@@ -19,6 +19,7 @@
 #include <cstdint>
 
 #include "../../include/rbgtopo.h"
+#include "kernels.cuh"
 
 namespace rbgtopo {
 
@@ -67,6 +68,49 @@ __device__ __forceinline__ void plan_wave_at(PlanScratch* S, int q, int w) {
   int acc = 0;
   for (int j = 0; j < RBGTOPO_MAX_GROUP_ROLES; ++j) { S->cum[j] = acc; acc += S->placed[j]; }
   S->cum[RBGTOPO_MAX_GROUP_ROLES] = acc;
+}
+
+// Emit table of the plan (kernels.cuh), one warp per step, from the GROUPS blob and the step numbering
+// alone: sgw = (group, wave) per step.  The role rows (count, demand, predicted need) are those
+// k_expand_plan writes into the step blob later; the first dense row of a step is the group's offset in
+// the batch (assign_off - row_base) plus the replicas of the group's earlier waves — GROUP order, no
+// prefix over steps needed.  Runs right after the first H2D of rbgtopo_place_groups.
+__global__ void __launch_bounds__(32 * PLAN_WARPS) k_plan_etab(const int* __restrict__ grp, const int* __restrict__ sgw, int ns,
+                                                               int row_base, int* __restrict__ etab) {
+  __shared__ PlanScratch scratch[PLAN_WARPS];
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * PLAN_WARPS + (threadIdx.x >> 5);
+  if (s >= ns) return;
+  PlanScratch* S = &scratch[threadIdx.x >> 5];
+  const int g = sgw[2 * s], w = sgw[2 * s + 1];
+  if (lane < RBGTOPO_GROUP_WORDS) S->rec[lane] = grp[RBGTOPO_HDR_WORDS + (long long)g * RBGTOPO_GROUP_WORDS + lane];
+  __syncwarp();
+  const int q = S->rec[3];
+  const int* g_roles = grp + S->rec[4];
+  const int* g_pair = grp + S->rec[5];
+  for (int i = lane; i < 4 * q; i += 32) S->roles[i] = g_roles[i];
+  for (int i = lane; i < q * q; i += 32) S->pair[i] = g_pair[i];
+  __syncwarp();
+  if (lane == 0) plan_wave_at(S, q, w);
+  __syncwarp();
+  const int P = S->n;
+  int* e = etab + (size_t)s * EMIT_TAB_WORDS;
+  if (lane < RBGTOPO_MAX_STEP_ROLES) {
+    int packed = 0;
+    if (lane < P) {
+      const int ri = S->role[lane];
+      int need = 0;
+      for (int j = 0; j < q; ++j)
+        if (S->pair[ri * q + j] > 0) need += S->roles[4 * j + 1] - S->placed[j];
+      packed = emit_pack_role(S->count[lane], S->roles[4 * ri + 2], min(need, RBGTOPO_NEED_CAP), S->roles[4 * ri + 3]);
+    }
+    e[4 + lane] = packed;
+  } else if (lane == 8) {
+    e[0] = S->rec[0];
+    e[1] = S->rec[1] & (RBGTOPO_STEP_EXCLUSIVE | RBGTOPO_STEP_GANG);
+    e[2] = P;
+    e[3] = S->rec[8] - row_base + S->cum[RBGTOPO_MAX_GROUP_ROLES];
+  }
 }
 
 // One warp per step (+ warps for the tail words and the blob header).  Writes every word of

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <shared_mutex>
@@ -123,7 +124,8 @@ struct Topology {
   DevBuf<unsigned long long> okeys_all, order_all;  // world > 1: the order over all nodes (plan_group.cuh)
   DevBuf<unsigned char> sort_tmp;
   int key_nb = 0, key_bits = 64;           // compact sort key of the background order (prepare_refresh)
-  cudaGraphExec_t refresh_exec = nullptr;  // captured refresh chain of this topology (run_base)
+  cudaGraphExec_t refresh_exec = nullptr;  // captured refresh chain of this topology (run_base): k_prep + k_base ...
+  cudaGraphExec_t order_exec = nullptr;    // ... and the order sorts, so that base_ready can be recorded between them
   bool refresh_ready = false;              // buffers sized / graph built for the current topology
   std::vector<int> h_degp1;  // deg(n) + 1, for the patch-list capacity of a step
   int max_degp1 = 1;
@@ -149,6 +151,7 @@ struct Batch {
   bool in_use = false;    // reserved by a call or a stage handle
   bool staged = false;    // holds a staged blob (handle alive)
   bool ran = false;
+  bool early_emit = false;    // plan_stage already enqueued the dense-matrix kernel of the next pass (+ its two events)
   bool d2h_enqueued = false;  // enqueue_d2h ran for the last pass; fetch_batch only has to wait
   uint64_t epoch = 0;         // topology epoch the batch was validated / sized against (set_topology bumps it)
   cudaStream_t stream = nullptr;
@@ -168,7 +171,6 @@ struct Batch {
   // device-resident multi-wave plan (rbgtopo_stage_groups / place_groups): steps are
   // wave-major; wave w = steps [wave_begin[w], wave_begin[w + 1])
   std::vector<int> wave_begin, wave_maxp;
-  std::vector<int> out_index;    // plan replica -> position in the group-order assign array (host-built plans)
   std::vector<int> step_group;   // plan step -> group
   std::vector<int> step_row;     // [n_steps + 1] role-row prefix
   // device-expanded plans: the staging buffer (GROUPS blob | per-step geometry | poff)
@@ -202,6 +204,9 @@ struct rbgtopo_ctx {
   // snapshot refresh pipeline: update_nodes enqueues on topo_stream and returns; every batch
   // stream waits on topo_ready before it touches the snapshot
   cudaStream_t topo_stream = nullptr;
+  // base_ready: free / node_owner / fmin / base of the latest refresh are written (what the dense-matrix kernel
+  // reads); topo_ready: the background order too (what selection reads).  The sort overlaps the emit.
+  cudaEvent_t base_ready = nullptr;
   cudaEvent_t topo_ready = nullptr, ev_base_a = nullptr, ev_base_b = nullptr, fence_ev = nullptr;
   bool base_timing_pending = false;
   // update_nodes staging, double buffered: the copy of update k leaves h_free[k & 1]; the host only
@@ -270,6 +275,9 @@ const int kSplitMinGroups =
     getenv("RBGTOPO_SPLIT_MIN_GROUPS") ? std::max(2, atoi(getenv("RBGTOPO_SPLIT_MIN_GROUPS"))) : (1 << 30);
 const bool kCompactSortKey = getenv("RBGTOPO_WIDE_SORT_KEY") == nullptr;
 const bool kRefreshGraph = getenv("RBGTOPO_NO_REFRESH_GRAPH") == nullptr;
+// RBGTOPO_SMALL_SORT=1: single-CTA bitonic sort of the order for slabs <= 16 384 nodes instead of the library
+// radix sort.  Measured SLOWER (105 barrier rounds: ~150 us vs ~40 us at 10 000 nodes), kept opt-in.
+const bool kSmallSort = getenv("RBGTOPO_SMALL_SORT") != nullptr;
 const bool kVerifyPlan = getenv("RBGTOPO_VERIFY_PLAN") != nullptr;  // self-check: device-expanded plan == host-built plan
 const int kHostThreads = getenv("RBGTOPO_HOST_THREADS") ? std::max(1, atoi(getenv("RBGTOPO_HOST_THREADS"))) : 4;
 
@@ -387,8 +395,10 @@ int prepare_refresh(rbgtopo_ctx* c) {
   return RBGTOPO_OK;
 }
 
-int enqueue_refresh(rbgtopo_ctx* c, cudaStream_t s) {
+// part: 1 = k_prep + k_base, 2 = the background order(s), 3 = both (base_ready recorded in between)
+int enqueue_refresh(rbgtopo_ctx* c, cudaStream_t s, int part) {
   Topology& T = c->topo;
+  if (part & 1) {
   k_prep<<<(T.n + 255) / 256, 256, 0, s>>>(T.n, T.free_.p, T.domain.p, T.owner.p, T.fmin.p,
                                            T.node_owner.p);
   const int fmin_bytes = round_up(T.n, 16);
@@ -396,15 +406,28 @@ int enqueue_refresh(rbgtopo_ctx* c, cudaStream_t s) {
   const size_t smem = (size_t)2 * (BASE_TILE_NNZ + 8) * 4 + (staged ? fmin_bytes : 0);
   const TopoDev td = topo_dev(c);
   k_base<<<T.n_tiles, BASE_THREADS, smem, s>>>(td, T.tiles.p, staged, fmin_bytes, T.base.p);
-  // background order: slab nodes by key(base, node) descending (library radix sort, once per snapshot)
+  }
+  // what the dense-matrix kernel reads is complete here; the order below is only read by selection
+  if (part == 3) CK(cudaEventRecord(c->base_ready, s));
+  if (!(part & 2)) {
+    CK(cudaGetLastError());
+    return RBGTOPO_OK;
+  }
+  const TopoDev td = topo_dev(c);
+  // background order: slab nodes by key(base, node) descending, once per snapshot
   const int slab_len = c->slab_hi - c->slab_lo;
-  if (slab_len > 0) {
+  auto p2_bytes = [](int n) { int p2 = 32; while (p2 < n) p2 <<= 1; return (size_t)p2 * 8; };
+  if (slab_len > 0 && slab_len <= ORDER_SMALL_MAX && kSmallSort) {
+    k_order_sort_small<<<1, ORDER_SMALL_THREADS, p2_bytes(slab_len), s>>>(T.base.p, c->slab_lo, c->slab_hi, T.order.p);
+  } else if (slab_len > 0) {
     k_order_keys<<<(slab_len + 255) / 256, 256, 0, s>>>(td, c->slab_lo, c->slab_hi, T.key_nb, T.okeys.p);
     size_t tmp_bytes = T.sort_tmp.cap;
     CK(cub::DeviceRadixSort::SortKeysDescending(T.sort_tmp.p, tmp_bytes, T.okeys.p, T.order.p, slab_len, 0, T.key_bits, s));
     if (T.key_nb) k_order_expand<<<(slab_len + 255) / 256, 256, 0, s>>>(T.order.p, slab_len, T.key_nb);
   }
-  if (c->cfg.world > 1 && T.n > 0) {  // replicated selection (plan_group.cuh) walks the order of ALL nodes
+  if (c->cfg.world > 1 && T.n > 0 && T.n <= ORDER_SMALL_MAX && kSmallSort) {
+    k_order_sort_small<<<1, ORDER_SMALL_THREADS, p2_bytes(T.n), s>>>(T.base.p, 0, T.n, T.order_all.p);
+  } else if (c->cfg.world > 1 && T.n > 0) {  // replicated selection (plan_group.cuh) walks the order of ALL nodes
     k_order_keys<<<(T.n + 255) / 256, 256, 0, s>>>(td, 0, T.n, T.key_nb, T.okeys_all.p);
     size_t tmp_bytes = T.sort_tmp.cap;
     CK(cub::DeviceRadixSort::SortKeysDescending(T.sort_tmp.p, tmp_bytes, T.okeys_all.p, T.order_all.p, T.n, 0, T.key_bits, s));
@@ -422,28 +445,37 @@ int run_base(rbgtopo_ctx* c, cudaStream_t s, bool sync) {
   if (!T.refresh_ready) {
     int rc = prepare_refresh(c);
     if (rc) return rc;
-    if (T.refresh_exec) {
-      cudaGraphExecDestroy(T.refresh_exec);
-      T.refresh_exec = nullptr;
-    }
-    if (kRefreshGraph && cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-      const int erc = enqueue_refresh(c, s);
+    for (cudaGraphExec_t* e : {&T.refresh_exec, &T.order_exec})
+      if (*e) {
+        cudaGraphExecDestroy(*e);
+        *e = nullptr;
+      }
+    // two graphs — (k_prep, k_base) and the order sorts — so that base_ready can be recorded between them with a
+    // plain cudaEventRecord: the dense-matrix kernel of the next batch then overlaps the sort
+    auto capture = [&](int part, cudaGraphExec_t* out) {
+      if (!kRefreshGraph || cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return;
+      const int erc = enqueue_refresh(c, s, part);
       cudaGraph_t g = nullptr;
       const cudaError_t ce = cudaStreamEndCapture(s, &g);
-      if (erc == RBGTOPO_OK && ce == cudaSuccess && g &&
-          cudaGraphInstantiate(&T.refresh_exec, g, 0) != cudaSuccess)
-        T.refresh_exec = nullptr;
-      if (erc != RBGTOPO_OK || ce != cudaSuccess) T.refresh_exec = nullptr;
+      if (erc != RBGTOPO_OK || ce != cudaSuccess || !g || cudaGraphInstantiate(out, g, 0) != cudaSuccess) *out = nullptr;
       if (g) cudaGraphDestroy(g);
       (void)cudaGetLastError();
+    };
+    capture(1, &T.refresh_exec);
+    if (T.refresh_exec) capture(2, &T.order_exec);
+    if (!T.order_exec && T.refresh_exec) {
+      cudaGraphExecDestroy(T.refresh_exec);
+      T.refresh_exec = nullptr;
     }
     T.refresh_ready = true;
   }
   CK(cudaEventRecord(c->ev_base_a, s));
   if (T.refresh_exec) {
     CK(cudaGraphLaunch(T.refresh_exec, s));
+    CK(cudaEventRecord(c->base_ready, s));
+    CK(cudaGraphLaunch(T.order_exec, s));
   } else {
-    int rc = enqueue_refresh(c, s);
+    int rc = enqueue_refresh(c, s, 3);
     if (rc) return rc;
   }
   CK(cudaEventRecord(c->ev_base_b, s));
@@ -555,7 +587,8 @@ int validate_blob(const rbgtopo_ctx* c, const int32_t* blob, int64_t words, Batc
   if (first_bad < ns) return check_step(first_bad, true);
   for (int s = 0; s < ns; ++s) {  // the prefix-dependent part
     const int32_t* st = blob + RBGTOPO_HDR_WORDS + (int64_t)s * RBGTOPO_STEP_WORDS;
-    if (st[12] != racc || st[13] != pacc) return fail(RBGTOPO_EINVAL, "step %d: bad prefix offsets", s);
+    if ((!trusted && st[12] != racc) || st[13] != pacc) return fail(RBGTOPO_EINVAL, "step %d: bad prefix offsets", s);
+    if (trusted && (st[12] < 0 || st[12] + st[11] > blob[4])) return fail(RBGTOPO_EINVAL, "step %d: replica rows out of range", s);
     const long long pc = pcs[s];
     if (m->patch_cap + pc > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "patch lists exceed 2^31 entries");
     m->patch_cap += pc;
@@ -625,11 +658,6 @@ int reserve_batch_buffers(rbgtopo_ctx* c, Batch* b) {
   CK(b->merged.reserve((size_t)std::max(1, m.total_p) * KS));
   CK(b->excl.reserve((size_t)std::max(1, m.total_p) * KS));
   if (!b->wave_begin.empty()) {
-    CK(b->etab.reserve((size_t)m.n_steps * EMIT_TAB_WORDS + 4));
-    if (!b->emit_ctr.p) {
-      CK(b->emit_ctr.reserve(4));
-      CK(cudaMemset(b->emit_ctr.p, 0, b->emit_ctr.cap * 4));
-    }
     CK(b->corr.reserve((size_t)m.patch_cap * (size_t)(1 + m.max_p) + 1));
     CK(b->corr_cnt.reserve((size_t)m.n_steps + 1));
   }
@@ -659,8 +687,7 @@ int stage_into(rbgtopo_ctx* c, Batch* b, const int32_t* blob, int64_t words) {
   if (rc) return rc;
   b->m.h2d_words = (long long)in_words;
   b->epoch = c->topo_epoch;
-  CK(cudaStreamWaitEvent(s, c->topo_ready, 0));  // the snapshot refresh (if any) is complete
-  CK(cudaEventRecord(b->ev[0], s));
+  CK(cudaEventRecord(b->ev[0], s));  // staging touches the batch's own buffers only; run_batch waits for a pending refresh
   if (!in_place) memcpy(b->h_in.p, blob, (size_t)words * 4);
   memcpy(b->h_in.p + words, m.poff.data(), ((size_t)m.n_steps + 1) * 4);
   CK(cudaMemcpyAsync(b->blob.p, b->h_in.p, in_words * 4, cudaMemcpyHostToDevice, s));
@@ -702,21 +729,24 @@ BatchDev batch_dev(rbgtopo_ctx* c, Batch* b) {
   return d;
 }
 
-int launch_score(rbgtopo_ctx* c, Batch* b, cudaStream_t s) {
-  const BatchMeta& m = b->m;
-  if (m.n_steps == 0) return RBGTOPO_OK;
-  const int items = (int)emit_items(m.n_steps, c->lc);
-  const int grid = items / kEmitBlockSteps;  // one CTA per (block of steps, chunk of nodes)
-  if (b->wave_begin.empty())  // step batch: rows + sparse corrections
-    k_score_emit<true><<<grid, SCORE_THREADS, 0, s>>>(topo_dev(c), batch_dev(c, b), items);
-  else if (kEmitSt)           // multi-wave plan: background rows; corrections come from the selection kernels
-    k_score_emit<false><<<grid, SCORE_THREADS, 0, s>>>(topo_dev(c), batch_dev(c, b), items);
-  else {                      // the same rows through TMA bulk stores (emit_tma.cuh), persistent grid
-    BatchDev d = batch_dev(c, b);
+// Dense rows of a multi-wave plan from its emit table (b->etab): needs neither the expanded plan blob nor
+// b->m, so plan_stage can launch it while the host still computes the rest of the geometry.
+int launch_emit_plan(rbgtopo_ctx* c, Batch* b, cudaStream_t s, int ns) {
+  if (ns <= 0) return RBGTOPO_OK;
+  BatchDev d{};
+  d.n_steps = ns;
+  d.lc = c->lc;
+  d.chunk = c->chunk;
+  d.matrix = b->matrix.p;
+  if (kEmitSt) {
+    d.bsteps = kEmitBlockSteps;
+    const int items = (int)emit_items(ns, c->lc);
+    k_score_emit<false, true><<<items / kEmitBlockSteps, SCORE_THREADS, 0, s>>>(topo_dev(c), d, items, b->etab.p);
+  } else {  // the same rows through TMA bulk stores (emit_tma.cuh), persistent grid
     d.bsteps = kEmitTmaBlock;
     const int slab = c->slab_hi - c->slab_lo;
     const int subs = (slab + EMIT_SUB - 1) / EMIT_SUB;
-    const long long n_items = (long long)((m.n_steps + d.bsteps - 1) / d.bsteps) * subs;
+    const long long n_items = (long long)((ns + d.bsteps - 1) / d.bsteps) * subs;
     if (n_items > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "steps x sub-chunks exceed 2^31 work items");
     if (n_items > 0) {
       if (kEmitClocks) CK(b->emit_clk.reserve((size_t)c->sm_count * kEmitCtasPerSm * EMIT_WARPS * 8));
@@ -724,6 +754,16 @@ int launch_score(rbgtopo_ctx* c, Batch* b, cudaStream_t s) {
           topo_dev(c), d, b->etab.p, subs, (int)n_items, b->emit_ctr.p, b->emit_clk.p);
     }
   }
+  return RBGTOPO_OK;
+}
+
+int launch_score(rbgtopo_ctx* c, Batch* b, cudaStream_t s) {
+  const BatchMeta& m = b->m;
+  if (m.n_steps == 0) return RBGTOPO_OK;
+  if (!b->wave_begin.empty()) return launch_emit_plan(c, b, s, m.n_steps);  // multi-wave plan: background rows from the emit table
+  const int items = (int)emit_items(m.n_steps, c->lc);
+  const int grid = items / kEmitBlockSteps;  // one CTA per (block of steps, chunk of nodes)
+  k_score_emit<true, false><<<grid, SCORE_THREADS, 0, s>>>(topo_dev(c), batch_dev(c, b), items, nullptr);  // step batch: rows + sparse corrections
   return RBGTOPO_OK;
 }
 
@@ -813,19 +853,24 @@ int ensure_pass_events(Batch* b, int passes) {
 // select) until kMaxTimedPasses passes are pending harvest.
 int run_batch(rbgtopo_ctx* c, Batch* b, int iters) {
   cudaStream_t s = stream_of(c, b);
-  CK(cudaStreamWaitEvent(s, c->topo_ready, 0));  // a pending snapshot refresh finishes first
   int launches = 0;
   BatchDev d = batch_dev(c, b);
   for (int it = 0; it < iters; ++it) {
-    const bool timed = b->passes < kMaxTimedPasses;
+    const bool early = b->early_emit;  // the staging enqueued this pass's dense-matrix kernel and its events already
+    b->early_emit = false;
+    const bool timed = early || b->passes < kMaxTimedPasses;
     const int e0 = 3 * b->passes;
-    if (timed) {
+    if (timed && !early) {
       int rc = ensure_pass_events(b, b->passes + 1);
       if (rc) return rc;
       CK(cudaEventRecord(b->it_ev[e0], s));
     }
     int rc;
     PlanGroupCfg pg;
+    if (it == 0) {  // a pending snapshot refresh: the dense-matrix kernel needs base / free, selection also the order
+      if (!early) CK(cudaStreamWaitEvent(s, c->base_ready, 0));
+      if (!kSerialPlan || b->wave_begin.empty()) CK(cudaStreamWaitEvent(s, c->topo_ready, 0));
+    }
     if (!kSerialPlan && plan_group_cfg(b, &pg)) {
       // Concurrent pipeline: the selection + greedy of every group (k_plan_group, record mode: it never
       // touches the matrix) on stream2 beside the dense-matrix kernel on s; the corrections follow both.
@@ -846,10 +891,13 @@ int run_batch(rbgtopo_ctx* c, Batch* b, int iters) {
         launches += 2;
       }
     } else {
-      rc = launch_score(c, b, s);
-      if (rc) return rc;
+      if (!early) {
+        rc = launch_score(c, b, s);
+        if (rc) return rc;
+        if (timed) CK(cudaEventRecord(b->it_ev[e0 + 1], s));
+      }
       ++launches;
-      if (timed) CK(cudaEventRecord(b->it_ev[e0 + 1], s));
+      if (it == 0) CK(cudaStreamWaitEvent(s, c->topo_ready, 0));  // the background order of the refresh
       rc = launch_select_assign(c, b, s, d, &launches);
       if (rc) return rc;
     }
@@ -1058,6 +1106,8 @@ int32_t rbgtopo_create(const rbgtopo_config* cfg, rbgtopo_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&c->topo_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&c->topo_ready, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->base_ready, cudaEventDisableTiming));
+  CK(cudaFuncSetAttribute(k_order_sort_small, cudaFuncAttributeMaxDynamicSharedMemorySize, ORDER_SMALL_MAX * 8));
   CK(cudaEventCreate(&c->ev_base_a));
   CK(cudaEventCreate(&c->ev_base_b));
   CK(cudaEventCreateWithFlags(&c->fence_ev, cudaEventDisableTiming));
@@ -1087,8 +1137,10 @@ int32_t rbgtopo_destroy(rbgtopo_ctx* c) {
   cudaDeviceSynchronize();
   for (void* q : c->p2p_opened) cudaIpcCloseMemHandle(q);
   if (c->topo.refresh_exec) cudaGraphExecDestroy(c->topo.refresh_exec);
+  if (c->topo.order_exec) cudaGraphExecDestroy(c->topo.order_exec);
   if (c->topo_stream) cudaStreamDestroy(c->topo_stream);
   if (c->topo_ready) cudaEventDestroy(c->topo_ready);
+  if (c->base_ready) cudaEventDestroy(c->base_ready);
   if (c->ev_base_a) cudaEventDestroy(c->ev_base_a);
   if (c->ev_base_b) cudaEventDestroy(c->ev_base_b);
   if (c->fence_ev) cudaEventDestroy(c->fence_ev);
@@ -1673,7 +1725,6 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
     const size_t total = (size_t)sec_off[ns] + (size_t)ns + 1 + 64;  // + poff
     CK(b->h_in.reserve(total));  // no clear: pass 2 writes every word of the plan
   }
-  b->out_index.resize((size_t)pacc);
   int32_t* const out = b->h_in.p;
   const auto p4 = now();
   // pass 2 (group order): fill every step of a group while walking its waves once.  Groups
@@ -1686,7 +1737,6 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
   const int* const seco = sec_off.data();
   const int* const repo = rep_off.data();
   const int* const rowo = row_off.data();
-  int* const oidx = b->out_index.data();
   auto nwaves2 = [wvo](int g) { return (size_t)(wvo[g + 1] - wvo[g]); };
   auto wave2 = [wvp, wvo](int g, size_t w) -> const PlanWave& { return wvp[wvo[g] + w]; };
   auto step2 = [stf, wvo](int g, size_t w) { return stf[wvo[g] + w]; };
@@ -1697,8 +1747,6 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
     const int32_t* roles = gb + rec[4];
     const int32_t* pair = gb + rec[5];
     int placed_before[RBGTOPO_MAX_GROUP_ROLES] = {0};
-    int ord0[RBGTOPO_MAX_GROUP_ROLES];
-    for (int k = 0, acc = 0; k < q; ++k) { ord0[k] = acc; acc += roles[4 * k + 1]; }
     int i0 = 0;
     for (size_t w = 0; w < nwaves2(g); ++w) {
       const PlanWave& pw = wave2(g, w);
@@ -1712,7 +1760,6 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
       st[3] = P;
       st[4] = (int32_t)(p - out);
       int n = 0;
-      int* oi = oidx + repo[s];
       for (int k = 0; k < P; ++k) {
         const int ri = pw.role[k];
         int need = 0;
@@ -1722,7 +1769,6 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
         *p++ = roles[4 * ri + 2];
         *p++ = std::min(need, RBGTOPO_NEED_CAP);
         *p++ = (roles[4 * ri + 3] & 0xFF) | (ri << 8);
-        for (int c2 = 0; c2 < pw.count[k]; ++c2) *oi++ = rec[8] + ord0[ri] + pw.first[k] + c2;
         n += pw.count[k];
       }
       st[5] = q;
@@ -1746,7 +1792,7 @@ int build_plan(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int64_t* plan_w
       st[10] = (int32_t)(p - out);  // consumed records (and the pad) are zero until the device fills them
       for (int32_t* const end = out + seco[s + 1]; p < end;) *p++ = 0;
       st[11] = n;
-      st[12] = repo[s];
+      st[12] = rec[8] + i0;  // dense row / assign index of the wave's first replica: GROUP order (a group's waves are consecutive)
       st[13] = rowo[s];
       st[14] = (w + 1 < nwaves2(g)) ? step2(g, w + 1) : 0;
       st[15] = i0;
@@ -1784,16 +1830,20 @@ struct TopoHost {
   int max_degp1 = 1;
   long long wsum_max = 0;
 };
-struct PlanLayout {  // staging layout of one plan: GROUPS blob | pad | geometry (8 ints per step) | poff
-  size_t aux_off = 0, tail_off = 0, tail_words = 0, src_words = 0;
+struct PlanLayout {  // staging layout of one plan: GROUPS blob | pad | (group, wave) per step | geometry (8 ints per step) | poff
+  size_t sgw_off = 0, aux_off = 0, tail_off = 0, tail_words = 0, src_words = 0;
   long long plan_words = 0, racc = 0, rowacc = 0;
   int ns = 0;
 };
+// Called by plan_geometry once the step numbering exists (ns, racc = replicas of the batch, the
+// (group, wave) table in the staging buffer): plan_stage uploads the first part and starts the device on
+// the emit table / the dense matrix while the host goes on with section sizes and prefixes.
+using PlanMidHook = std::function<int(const PlanLayout&)>;
 
 // Pure host part of plan_stage (no CUDA call when b->h_in is pageable): validates the groups of
 // [g_lo, g_hi), fills the batch's wave tables, b->m and the staging buffer b->h_in.
 int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_t words, int g_lo, int g_hi,
-                  long long pacc0, bool with_blob, PlanLayout* L) {
+                  long long pacc0, bool with_blob, PlanLayout* L, const PlanMidHook& mid = nullptr) {
   if (words < RBGTOPO_HDR_WORDS || gb[0] != RBGTOPO_GROUPS_MAGIC || gb[1] != RBGTOPO_ABI_VERSION || gb[3] != words)
     return fail(RBGTOPO_EINVAL, "bad groups blob header");
   const int ng_all = gb[2];
@@ -1902,8 +1952,9 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
     wb[0] = 0;
     for (int w = 0; w < W; ++w) wb[w + 1] = wb[w] + cnt[w];
   }
-  // staging layout: GROUPS blob | pad | geometry (8 ints per step) | poff
-  const size_t aux_off = with_blob ? (((size_t)words + 3) & ~(size_t)3) : 0;  // without: the blob is already on the device
+  // staging layout: GROUPS blob | pad | (group, wave) per step | geometry (8 ints per step) | poff
+  const size_t sgw_off = with_blob ? (((size_t)words + 3) & ~(size_t)3) : 0;  // without: the blob is already on the device
+  const size_t aux_off = sgw_off + (((size_t)2 * ns + 3) & ~(size_t)3);
   const size_t tail_off = aux_off + (size_t)ns * PLAN_AUX_WORDS;
   const size_t tail_words = (size_t)ns + 1;
   const size_t src_words = tail_off + tail_words;
@@ -1911,6 +1962,7 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
   CK(b->h_in.reserve(src_words));
   int32_t* const hin = b->h_in.p;
   int32_t* const aux = hin + aux_off;
+  int32_t* const sgw = hin + sgw_off;
   b->step_group.resize((size_t)ns);
   {
     ctr.assign((size_t)W, 0);
@@ -1922,6 +1974,8 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
         const int s = wb[w] + ctr[w]++;
         if (w == 0) g_first[g] = s;
         sg[s] = g;
+        sgw[2 * (size_t)s] = g_lo + g;
+        sgw[2 * (size_t)s + 1] = w;
         aux[(size_t)s * PLAN_AUX_WORDS + 0] = g_lo + g;
         aux[(size_t)s * PLAN_AUX_WORDS + 1] = w;
         aux[(size_t)s * PLAN_AUX_WORDS + 6] = 0;
@@ -1929,6 +1983,22 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
         prev = s;
       }
     }
+  }
+  if (with_blob) {  // the caller's blob into the pinned staging (the hook uploads it)
+    memcpy(hin, gb, (size_t)words * 4);
+    for (size_t i = (size_t)words; i < sgw_off; ++i) hin[i] = 0;
+  }
+  for (size_t i = sgw_off + 2 * (size_t)ns; i < aux_off; ++i) hin[i] = 0;
+  L->sgw_off = sgw_off;
+  L->aux_off = aux_off;
+  L->tail_off = tail_off;
+  L->tail_words = tail_words;
+  L->src_words = src_words;
+  L->racc = pacc - pacc0;
+  L->ns = ns;
+  if (mid) {
+    const int mrc = mid(*L);
+    if (mrc) return mrc;
   }
   const auto p2 = now();
   // per-step sizes, patch capacity, exactness bound (per group, all its waves)
@@ -2013,7 +2083,10 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
       a[2] = (int)off;
       off += sz;
       a[3] = (int)off;
-      a[4] = (int)racc;
+      // dense-matrix row / assign index of the step's first replica: GROUP order (the group's offset in the
+      // batch + the replicas of its earlier waves), so results need no reordering and the rows of a step
+      // are known without any prefix over steps
+      a[4] = b->grp_assign_off[b->step_group[s]] - (int)pacc0 + a[7];
       a[5] = (int)rowacc;
       b->step_row[s] = (int)rowacc;
       racc += n;
@@ -2031,10 +2104,6 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
   if (emit_items(ns, lc) > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "steps x chunks exceed 2^31 work items");
   m.poff.assign(poff, poff + ns + 1);
   const auto p4 = now();
-  if (with_blob) {
-    memcpy(hin, gb, (size_t)words * 4);
-    for (size_t i = (size_t)words; i < aux_off; ++i) hin[i] = 0;
-  }
   m.n_steps = ns;
   m.total_r = (int)racc;
   m.total_p = (int)rowacc;
@@ -2055,7 +2124,9 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
   return RBGTOPO_OK;
 }
 
-int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, int g_lo = 0, int g_hi = -1,
+// early_emit: also launch the dense-matrix kernel of the FIRST pass from inside the staging (host-buffer
+// entry point: one pass follows at once); run_batch then skips that launch.
+int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, bool early_emit = false, int g_lo = 0, int g_hi = -1,
                long long pacc0 = 0, const int* dev_groups = nullptr, cudaEvent_t dev_groups_ready = nullptr) {
   const Topology& T = c->topo;
   if (!T.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
@@ -2066,7 +2137,45 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, int g
   th.max_degp1 = T.max_degp1;
   th.wsum_max = T.wsum_max;
   PlanLayout L;
-  int rc = plan_geometry(th, c->lc, b, gb, words, g_lo, g_hi, pacc0, dev_groups == nullptr, &L);
+  cudaStream_t s = stream_of(c, b);
+  // Runs inside plan_geometry as soon as the step numbering exists: first upload (GROUPS blob + the
+  // (group, wave) table), emit table on the device and — for the host-buffer entry point — the dense
+  // matrix launch itself, which then overlaps the host's section sizes / prefixes / second upload.
+  auto mid = [&](const PlanLayout& P) -> int {
+    CK(b->gsrc.reserve(P.src_words));
+    CK(b->matrix.reserve((size_t)std::max<long long>(1, P.racc) * c->slab_stride));
+    CK(b->etab.reserve((size_t)P.ns * EMIT_TAB_WORDS + 4));
+    if (!b->emit_ctr.p) {
+      CK(b->emit_ctr.reserve(4));
+      CK(cudaMemset(b->emit_ctr.p, 0, b->emit_ctr.cap * 4));
+    }
+    b->epoch = c->topo_epoch;
+    CK(cudaEventRecord(b->ev[0], s));  // staging touches the batch's own buffers only: no wait for a pending snapshot refresh
+    const size_t lo = dev_groups ? P.sgw_off : 0, hi = P.aux_off;  // blob (unless an earlier batch uploaded it) + (group, wave) table
+    if (hi > lo) CK(cudaMemcpyAsync(b->gsrc.p + lo, b->h_in.p + lo, (hi - lo) * 4, cudaMemcpyHostToDevice, s));
+    if (dev_groups && dev_groups_ready) CK(cudaStreamWaitEvent(s, dev_groups_ready, 0));
+    if (P.ns > 0) {
+      k_plan_etab<<<(P.ns + PLAN_WARPS - 1) / PLAN_WARPS, 32 * PLAN_WARPS, 0, s>>>(dev_groups ? dev_groups : b->gsrc.p, b->gsrc.p + P.sgw_off, P.ns,
+                                                                                 (int)pacc0, b->etab.p);
+      CK(cudaMemsetAsync(b->emit_ctr.p, 0, 8, s));  // re-arm the TMA item queue (a failed launch may have left it mid-way)
+      CK(cudaGetLastError());
+      b->pend_launches += 1;
+      if (early_emit) {  // pass 0 of run_batch starts here
+        int erc = ensure_pass_events(b, b->passes + 1);
+        if (erc) return erc;
+        CK(cudaStreamWaitEvent(s, c->base_ready, 0));  // base / free / node_owner of a pending refresh
+        CK(cudaEventRecord(b->it_ev[3 * b->passes], s));
+        erc = launch_emit_plan(c, b, s, P.ns);
+        if (erc) return erc;
+        CK(cudaEventRecord(b->it_ev[3 * b->passes + 1], s));
+        CK(cudaGetLastError());
+        b->early_emit = true;
+      }
+    }
+    return RBGTOPO_OK;
+  };
+  b->early_emit = false;
+  int rc = plan_geometry(th, c->lc, b, gb, words, g_lo, g_hi, pacc0, dev_groups == nullptr, &L, mid);
   if (rc) return rc;
   BatchMeta& m = b->m;
   const long long slab = c->slab_hi - c->slab_lo;
@@ -2076,16 +2185,10 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, int g
   const long long plan_words = L.plan_words, racc = L.racc, rowacc = L.rowacc;
   const int ns = L.ns;
   int32_t* const hin = b->h_in.p;
-  cudaStream_t s = stream_of(c, b);
-  CK(b->gsrc.reserve(src_words));
   CK(b->blob.reserve((size_t)plan_words + tail_words));
   rc = reserve_batch_buffers(c, b);
   if (rc) return rc;
-  b->epoch = c->topo_epoch;
-  CK(cudaStreamWaitEvent(s, c->topo_ready, 0));  // the snapshot refresh (if any) is complete
-  CK(cudaEventRecord(b->ev[0], s));
-  CK(cudaMemcpyAsync(b->gsrc.p, hin, src_words * 4, cudaMemcpyHostToDevice, s));
-  if (dev_groups && dev_groups_ready) CK(cudaStreamWaitEvent(s, dev_groups_ready, 0));
+  CK(cudaMemcpyAsync(b->gsrc.p + aux_off, hin + aux_off, (src_words - aux_off) * 4, cudaMemcpyHostToDevice, s));  // geometry + poff
   {
     const long long warps = (long long)ns + ((long long)tail_words + 1 + 31) / 32;  // a warp per step + tail words
     k_expand_plan<<<(unsigned)((warps + PLAN_WARPS - 1) / PLAN_WARPS), 32 * PLAN_WARPS, 0, s>>>(dev_groups ? dev_groups : b->gsrc.p, b->gsrc.p, b->blob.p, ns, (int)plan_words,
@@ -2093,13 +2196,8 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, int g
                                                                    (int)racc, (int)rowacc);
     CK(cudaGetLastError());
   }
-  if (ns > 0) {
-    k_emit_table<<<(ns + 127) / 128, 128, 0, s>>>(b->blob.p, ns, b->etab.p);
-    CK(cudaMemsetAsync(b->emit_ctr.p, 0, 8, s));  // re-arm the item queue (a failed launch may have left it mid-way)
-    CK(cudaGetLastError());
-  }
-  CK(cudaEventRecord(b->ev[1], s));  // h2d_ms = upload + expansion
-  b->pend_launches += 2;
+  CK(cudaEventRecord(b->ev[1], s));  // h2d_ms = uploads + emit table + expansion (+ the early emit launch when there is one)
+  b->pend_launches += 1;
   b->staged = true;
   b->ran = false;
   return RBGTOPO_OK;
@@ -2133,6 +2231,19 @@ int verify_plan(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
     return fail(RBGTOPO_ECUDA, "verify_plan: batch meta differs");
   if (ref.wave_begin != b->wave_begin || ref.wave_maxp != b->wave_maxp || ref.step_group != b->step_group)
     return fail(RBGTOPO_ECUDA, "verify_plan: wave tables differ");
+  // the emit table k_plan_etab derived from the GROUPS blob must say what the expanded plan says
+  std::vector<int32_t> etab((size_t)m.n_steps * EMIT_TAB_WORDS);
+  if (m.n_steps) CK(cudaMemcpy(etab.data(), b->etab.p, etab.size() * 4, cudaMemcpyDeviceToHost));
+  for (int st = 0; st < m.n_steps; ++st) {
+    const int32_t* h = ref.h_in.p + RBGTOPO_HDR_WORDS + (size_t)st * RBGTOPO_STEP_WORDS;
+    const int32_t* e = etab.data() + (size_t)st * EMIT_TAB_WORDS;
+    bool ok = e[0] == h[0] && e[1] == h[1] && e[2] == h[3] && e[3] == h[12];
+    for (int p2 = 0; p2 < RBGTOPO_MAX_STEP_ROLES && ok; ++p2) {
+      const int32_t* r = ref.h_in.p + h[4] + 4 * p2;
+      ok = e[4 + p2] == (p2 < h[3] ? emit_pack_role(r[0], r[1], r[2], r[3]) : 0);
+    }
+    if (!ok) return fail(RBGTOPO_ECUDA, "verify_plan: emit table of step %d differs from the plan", st);
+  }
   return RBGTOPO_OK;
 }
 
@@ -2144,14 +2255,8 @@ void plan_results(const Batch* b, int32_t* assign, int32_t* status, int32_t* dom
   const int32_t* st = a + m.total_r;
   const int32_t* dm = st + m.n_steps;
   const int ng = (int)b->grp_flags.size();
-  // a wave's replicas are consecutive in group order: step s covers [i0, i0 + R) of its group
-  const int32_t* aux = b->h_in.p + b->aux_off;
-  if (assign)
-    for (int s = 0; s < m.n_steps; ++s) {
-      const int32_t* x = aux + (size_t)s * PLAN_AUX_WORDS;
-      const int R = (s + 1 < m.n_steps ? x[PLAN_AUX_WORDS + 4] : m.total_r) - x[4];
-      memcpy(assign + b->grp_assign_off[x[0] - b->g_lo] + x[7], a + x[4], (size_t)R * 4);
-    }
+  // the device wrote assign[] in group order already (rep_off of a step = group offset + earlier waves)
+  if (assign && ng > 0 && m.total_r > 0) memcpy(assign + b->grp_assign_off[0], a, (size_t)m.total_r * 4);
   std::vector<int> gstat(ng, 0), gdom(ng, -1);
   for (int g = 0; g < ng; ++g)  // an exclusive group confirms the domain it already occupies (as the host loop)
     if (b->grp_flags[g] & RBGTOPO_STEP_EXCLUSIVE) gdom[g] = b->grp_fixed[g];
@@ -2217,7 +2322,8 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
     if (rc) return rc;
     if (!split) {
       auto t0 = now();
-      rc = plan_stage(c, b, gb, words);
+      static const bool no_early = getenv("RBGTOPO_NO_EARLY_EMIT") != nullptr;  // A/B switch (profiles/README.md)
+      rc = plan_stage(c, b, gb, words, kSerialPlan && !no_early);  // early emit: the dense matrix starts while the host finishes the geometry
       auto t1 = now();
       if (!rc && kVerifyPlan) rc = verify_plan(c, b, gb, words);
       auto t2 = now();
@@ -2241,11 +2347,11 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
       }
       const int mid = ng_all / 2;
       auto t0 = now();
-      rc = plan_stage(c, b, gb, words, 0, mid);
+      rc = plan_stage(c, b, gb, words, false, 0, mid);
       if (!rc) rc = run_batch(c, b, 1);
       if (!rc) rc = enqueue_d2h(c, b);
       auto t1 = now();
-      if (!rc) rc = plan_stage(c, b2, gb, words, mid, ng_all, b->m.total_r, b->gsrc.p, b->ev[1]);
+      if (!rc) rc = plan_stage(c, b2, gb, words, false, mid, ng_all, b->m.total_r, b->gsrc.p, b->ev[1]);
       if (!rc) rc = run_batch(c, b2, 1);
       if (!rc) rc = enqueue_d2h(c, b2);
       auto t2 = now();
@@ -2329,6 +2435,7 @@ int32_t rbgtopo_stage_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
   rc = plan_stage(c, b, gb, words);
   if (!rc && kVerifyPlan) rc = verify_plan(c, b, gb, words);
   if (rc) {
+    cudaStreamSynchronize(stream_of(c, b));  // the first upload / emit table may be in flight
     release_batch(c, b);
     return rc;
   }

@@ -45,9 +45,12 @@ __device__ __forceinline__ void red_add_f32(float* p, float v) {
 #endif
 constexpr int EMIT_MAX_BLOCK = 16;  // upper bound of b.bsteps
 
-template <bool SPARSE>
+// ETAB = true (multi-wave plans, never SPARSE): the per-step metadata comes from the emit table
+// (kernels.cuh: 12 words per step, one round of loads) instead of the step blob — the table exists
+// before the plan has been expanded, so this launch can overlap the host's plan geometry.
+template <bool SPARSE, bool ETAB>
 __global__ void __launch_bounds__(SCORE_THREADS, SPARSE ? 6 : EMIT_MIN_CTAS_BG)
-k_score_emit(TopoDev t, BatchDev b, int items) {
+k_score_emit(TopoDev t, BatchDev b, int items, const int* __restrict__ etab) {
   const int T = b.chunk, lc = b.lc;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int groups = T >> 2;
@@ -67,18 +70,32 @@ k_score_emit(TopoDev t, BatchDev b, int items) {
   __shared__ int4 sH0[EMIT_MAX_BLOCK];                 // gid flags fixed P
   __shared__ int sRoleOff[EMIT_MAX_BLOCK], sRepOff[EMIT_MAX_BLOCK];
   __shared__ int4 sRoles[EMIT_MAX_BLOCK][MAXP];        // count demand need flags
-  if (tid < nst) {
-    const int* __restrict__ hdr = blob + RBGTOPO_HDR_WORDS + (size_t)(step0 + tid) * RBGTOPO_STEP_WORDS;
-    sH0[tid] = __ldg(reinterpret_cast<const int4*>(hdr));
-    sRoleOff[tid] = __ldg(hdr + 4);
-    sRepOff[tid] = __ldg(hdr + 12);
+  if (ETAB) {
+    if (tid < nst) {
+      const int4 e0 = __ldg(reinterpret_cast<const int4*>(etab + (size_t)(step0 + tid) * EMIT_TAB_WORDS));  // gid flags P rep_off
+      sH0[tid] = make_int4(e0.x, e0.y, 0, e0.z);
+      sRepOff[tid] = e0.w;
+    }
+    if (tid >= 32 && tid < 32 + nst * MAXP) {
+      const int s = (tid - 32) / MAXP, p = (tid - 32) - s * MAXP;
+      const int pr = __ldg(etab + (size_t)(step0 + s) * EMIT_TAB_WORDS + 4 + p);
+      sRoles[s][p] = make_int4(pr & 63, pr >> 12, (pr >> 6) & 31, (pr >> 11) & 1);  // count demand need flags
+    }
+    __syncthreads();
+  } else {
+    if (tid < nst) {
+      const int* __restrict__ hdr = blob + RBGTOPO_HDR_WORDS + (size_t)(step0 + tid) * RBGTOPO_STEP_WORDS;
+      sH0[tid] = __ldg(reinterpret_cast<const int4*>(hdr));
+      sRoleOff[tid] = __ldg(hdr + 4);
+      sRepOff[tid] = __ldg(hdr + 12);
+    }
+    __syncthreads();
+    if (tid < nst * MAXP) {
+      const int s = tid / MAXP, p = tid - s * MAXP;
+      if (p < sH0[s].w) sRoles[s][p] = __ldg(reinterpret_cast<const int4*>(blob + sRoleOff[s]) + p);
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  if (tid < nst * MAXP) {
-    const int s = tid / MAXP, p = tid - s * MAXP;
-    if (p < sH0[s].w) sRoles[s][p] = __ldg(reinterpret_cast<const int4*>(blob + sRoleOff[s]) + p);
-  }
-  __syncthreads();
   {
     // ---- node operands of this thread's groups
     const int n0 = t.slab_lo + ch * T;

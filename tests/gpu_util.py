@@ -42,3 +42,10 @@ def check_batch(eng, topo, blob, check_matrix=True, check_topk=True, ref=None):
     a2, s2, d2 = eng.score_assign(blob)
     assert np.array_equal(a2, ref["assign"]) and np.array_equal(s2, ref["status"]) and np.array_equal(d2, ref["domain"])
     return ref
+
+
+def plan_rows(gblob, topo):
+    """(group, wave) -> dense-matrix row of the wave's first replica in a staged multi-wave plan
+    (rows are in GROUP order: a group's waves are consecutive; rbgtopo_plan_describe column 4)."""
+    from rbg_b200.engine import plan_steps
+    return {(int(st[0]), int(st[1])): int(st[4]) for st in plan_steps(gblob, topo.n, len(topo.domain_owner))}

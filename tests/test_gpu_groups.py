@@ -157,7 +157,10 @@ def test_plan_dense_matrix_and_lists_match_oracle_per_wave():
     eng.run_staged(h, 1)
     eng.fetch(h)
     runs = [_GroupRun(r, mgr.arith) for r in rbgs]
-    row = rr = w = 0
+    from gpu_util import plan_rows
+    row_of = plan_rows(gblob, topo)          # dense rows: group order; top-K lists (role rows): wave-major
+    index_of = {id(g): i for i, g in enumerate(runs)}
+    rr = w = 0
     while True:
         active = [g for g in runs if w < len(g.waves)]
         if not active:
@@ -167,11 +170,16 @@ def test_plan_dense_matrix_and_lists_match_oracle_per_wave():
             bb.add(g.step(w))
         ref = oracle_placer.place(topo, bb.build(), want_matrix=True, want_topk=True)
         assert ref["rc"] == 0 and (ref["status"] == 0).all()     # nobody fails: rows stay aligned with the plan
-        for i in range(ref["matrix"].shape[0]):
-            got = eng.read_scores(h, row + i)
-            exp = ref["matrix"][i]
-            bad = np.nonzero(got.view(np.uint32) != exp.view(np.uint32))[0]
-            assert len(bad) == 0, (w, i, len(bad), int(bad[0]), float(got[bad[0]]), float(exp[bad[0]]))
+        off = 0
+        for g in active:
+            cnt = sum(c for _, _, c in g.waves[w].roles)
+            row0 = row_of[(index_of[id(g)], w)]
+            for k in range(cnt):
+                got = eng.read_scores(h, row0 + k)
+                exp = ref["matrix"][off + k]
+                bad = np.nonzero(got.view(np.uint32) != exp.view(np.uint32))[0]
+                assert len(bad) == 0, (w, off + k, len(bad), int(bad[0]), float(got[bad[0]]), float(exp[bad[0]]))
+            off += cnt
         for i in range(ref["topk"].shape[0]):
             assert np.array_equal(eng.read_topk(h, rr + i, 32), ref["topk"][i]), (w, i)
         off = 0
@@ -179,7 +187,6 @@ def test_plan_dense_matrix_and_lists_match_oracle_per_wave():
             cnt = sum(c for _, _, c in g.waves[w].roles)
             g.absorb(w, ref["assign"][off:off + cnt], int(ref["status"][i]), int(ref["domain"][i]), n)
             off += cnt
-        row += ref["matrix"].shape[0]
         rr += ref["topk"].shape[0]
         w += 1
     assert w >= 3

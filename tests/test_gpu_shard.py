@@ -122,9 +122,12 @@ for n, kw in [(8000, {}), (6000, dict(excl_every=3, gang_every=4)), (5000, dict(
         from oracle import placer as oracle_placer
         from rbg_b200.blob import BlobBuilder
         from rbg_b200.plugin import _GroupRun
+        from gpu_util import plan_rows
         gruns = [_GroupRun(r, B200TopoPodGroupManager(eng).arith) for r in rbgs]
+        row_of = plan_rows(gblob, topo)
+        index_of = {id(g): i for i, g in enumerate(gruns)}
         lo, hi = eng.slab()
-        row = w = 0
+        w = 0
         while True:
             active = [g for g in gruns if w < len(g.waves)]
             if not active:
@@ -134,15 +137,15 @@ for n, kw in [(8000, {}), (6000, dict(excl_every=3, gang_every=4)), (5000, dict(
                 bb.add(g.step(w))
             oref = oracle_placer.place(topo, bb.build(), want_matrix=True, want_topk=False)
             assert oref["rc"] == 0 and (oref["status"] == 0).all()
-            for i in range(0, oref["matrix"].shape[0], 3):
-                got = eng.read_scores(h, row + i)
-                assert np.array_equal(got.view(np.uint32), oref["matrix"][i, lo:hi].view(np.uint32)), (rank, w, i)
             off = 0
             for i, g in enumerate(active):
                 cnt = sum(c for _, _, c in g.waves[w].roles)
+                row0 = row_of[(index_of[id(g)], w)]
+                for k in range(0, cnt, 2):
+                    got = eng.read_scores(h, row0 + k)
+                    assert np.array_equal(got.view(np.uint32), oref["matrix"][off + k, lo:hi].view(np.uint32)), (rank, w, i, k)
                 g.absorb(w, oref["assign"][off:off + cnt], int(oref["status"][i]), int(oref["domain"][i]), n)
                 off += cnt
-            row += oref["matrix"].shape[0]
             w += 1
     eng.release(h); eng.close()
 dist.barrier()

@@ -138,9 +138,12 @@ def test_group_plans_sharded_on_one_device(world):
                 assert a4[off:off + len(want)].tolist() == want and s4[i] == rr.status and d4[i] == rr.domain, (world, r, n, i)
                 off += len(want)
             if not kw:   # nobody fails in this fleet: the plan's rows line up with the wave-by-wave oracle run
+                from gpu_util import plan_rows
                 gruns = [_GroupRun(x, B200TopoPodGroupManager(e).arith) for x in rbgs]
+                row_of = plan_rows(gblob, topo)
+                index_of = {id(g): i for i, g in enumerate(gruns)}
                 lo, hi = e.slab()
-                row = w = 0
+                w = 0
                 while True:
                     active = [g for g in gruns if w < len(g.waves)]
                     if not active:
@@ -150,15 +153,15 @@ def test_group_plans_sharded_on_one_device(world):
                         bb.add(g.step(w))
                     oref = oracle_placer.place(topo, bb.build(), want_matrix=True, want_topk=False)
                     assert oref["rc"] == 0 and (oref["status"] == 0).all()
-                    for i in range(0, oref["matrix"].shape[0], 3):
-                        got = e.read_scores(h, row + i)
-                        assert np.array_equal(got.view(np.uint32), oref["matrix"][i, lo:hi].view(np.uint32)), (world, r, w, i)
                     off = 0
                     for i, g in enumerate(active):
                         cnt = sum(c for _, _, c in g.waves[w].roles)
+                        row0 = row_of[(index_of[id(g)], w)]
+                        for k in range(0, cnt, 2):
+                            got = e.read_scores(h, row0 + k)
+                            assert np.array_equal(got.view(np.uint32), oref["matrix"][off + k, lo:hi].view(np.uint32)), (world, r, w, i, k)
                         g.absorb(w, oref["assign"][off:off + cnt], int(oref["status"][i]), int(oref["domain"][i]), n)
                         off += cnt
-                    row += oref["matrix"].shape[0]
                     w += 1
             e.release(h)
         for e in engs:

@@ -64,9 +64,13 @@ def test_plan_geometry_matches_the_plugin_wave_planner(n_groups, seed):
             if w < len(g.waves):
                 exp.append((gi, w))
     assert [(int(s[0]), int(s[1])) for s in steps] == exp
-    rep = row = 0
+    row = 0
     off = 8 + 16 * len(steps)
     first_step = {}
+    group_off, acc = [], 0          # dense rows / assign indices are in GROUP order (the blob's assign_off)
+    for g in runs:
+        group_off.append(acc)
+        acc += sum(g.pending)
     for i, (s, (gi, w)) in enumerate(zip(steps, exp)):
         g = runs[gi]
         wave = g.waves[w]
@@ -74,12 +78,11 @@ def test_plan_geometry_matches_the_plugin_wave_planner(n_groups, seed):
         P = len(wave.roles)
         i0 = sum(c for ww in g.waves[:w] for _, _, c in ww.roles)
         na = len(g.anchors)
-        assert (int(s[4]), int(s[5]), int(s[7])) == (rep, row, i0), (i, gi, w)
+        assert (int(s[4]), int(s[5]), int(s[7])) == (group_off[gi] + i0, row, i0), (i, gi, w)
         size = (4 * P + P * g.Q + 3 * (na + i0) + 2 * i0 + 3) & ~3
         assert (int(s[2]), int(s[3])) == (off, off + size), (i, gi, w)
         nxt = exp.index((gi, w + 1)) if w + 1 < len(g.waves) else 0
         assert int(s[6]) == nxt
-        rep += R
         row += P
         off += size
         first_step.setdefault(gi, i)
