@@ -511,6 +511,48 @@ def run_config(D, args, cfg_name, with_clocks):
         out["parity"]["ok"] = bool(out["parity"]["ok"] and D.min_over_ranks(1.0 if bad == 0 else 0.0) > 0.5)
         if not out["parity"]["ok"] and not args.keep_going:
             raise SystemExit(f"PARITY FAILED under churn ({cfg_name}, rank {rank})")
+    if churn and (mode == "replicated" or world == 1):
+        # the same fleet under SMALL churn: 16 nodes change capacity per step (pods bound / deleted), pushed with
+        # rbgtopo_update_nodes_delta (incremental base + order repair; world > 1: the library refreshes fully)
+        rng = np.random.default_rng(6)
+        cur = free0.copy()
+        deltas = []
+        for _ in range(16):
+            nd = rng.choice(n_nodes, size=16, replace=False).astype(np.int32)
+            vals = rng.integers(0, 9, size=16).astype(np.int32)
+            deltas.append((nd, vals))
+        eng.update_nodes(cur)
+
+        def small_step(k):
+            nd, vals = deltas[k % len(deltas)]
+            eng.update_nodes_delta(nd, vals)
+            return eng.place_groups(gblob)
+        for k in range(4):                                   # parity of the first snapshots of the delta stream
+            res_k = small_step(k)
+            cur[deltas[k][0]] = deltas[k][1]
+            topo_k = synth.Topology(topo.row_ptr, topo.col_idx, topo.edge_w, cur.copy(), topo.domain, topo.domain_owner)
+            if placement_parity(topo_k, specs, sample, gblob, res_k, nt_par):
+                out["parity"]["ok"] = False
+        out["parity"]["ok"] = bool(D.min_over_ranks(1.0 if out["parity"]["ok"] else 0.0) > 0.5)
+        if not out["parity"]["ok"] and not args.keep_going:
+            raise SystemExit(f"PARITY FAILED under small churn ({cfg_name}, rank {rank})")
+        out["parity"]["delta_snapshots_checked"] = 4
+        for k in range(4, 24):
+            small_step(k)
+        rs = []
+        for _ in range(5):
+            D.barrier()
+            t0 = time.perf_counter()
+            for k in range(steps):
+                small_step(k)
+            torch.cuda.synchronize()
+            rs.append((time.perf_counter() - t0) * 1e3)
+        sm = D.max_over_ranks(sorted(rs)[len(rs) // 2])
+        out["small_churn"] = {"value": scores_all * steps / (sm * 1e-3), "unit": UNIT, "ms_per_step": sm / steps,
+                              "nodes_changed_per_step": 16,
+                              "refresh": "rbgtopo_update_nodes_delta: base updated on the changed nodes' closed neighbourhoods, "
+                                         "background order repaired by merge" + ("" if world == 1 else " (world > 1: full refresh)")}
+        eng.update_nodes(frees[0])
     for k in range(max(args.warmup, 3) + 16):   # the host side (threads, caches) cooled down during the value leg
         e2e_step(k)
     rounds = []
@@ -604,6 +646,9 @@ def run_ours(args):
                  "scaling": r["scaling"], "parity": r["parity"],
                  "e2e": {"value": r["e2e_value"], "unit": UNIT, "ms_per_step": r["e2e_ms"],
                          "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]}}
+            if "small_churn" in r:
+                d["small_churn"] = r["small_churn"]
+                d["refresh"] = "10 % of the nodes change per step: rbgtopo_update_nodes (full k_prep + k_base + sort)"
             if r.get("score_ms"):
                 d.update(value=r["value"], unit=UNIT, ms_per_step=r["ms_per_step"], gpu_launches=r["launches"],
                          roofline=roofline_of(r, peak, peak_src))

@@ -169,6 +169,16 @@ int32_t rbgtopo_set_topology(rbgtopo_ctx* ctx, int32_t n_nodes, int64_t n_edges,
 int32_t rbgtopo_update_nodes(rbgtopo_ctx* ctx, const int32_t* free_slots,
                              const int32_t* domain_owner, uint64_t generation);
 
+/* Incremental form: the free capacity of n_changed nodes changed (a pod was
+ * bound / deleted — the reconcile events of rolebasedgroup_controller.go:1347-1430).  The library
+ * updates base = W * min(free, F) on the closed neighbourhoods of those nodes only (exact integer
+ * deltas: bit-identical to a full recomputation) and repairs the background order by taking the
+ * affected entries out and merging them back, instead of the full SpMV + sort of
+ * rbgtopo_update_nodes.  Duplicate nodes: the last value wins.  Falls back to the full refresh when
+ * the neighbourhoods hold more than 2 048 nodes together (e.g. 10 % churn) or with world > 1. */
+int32_t rbgtopo_update_nodes_delta(rbgtopo_ctx* ctx, int32_t n_changed, const int32_t* nodes,
+                                   const int32_t* free_slots, uint64_t generation);
+
 /* ---- the hot path ------------------------------------------------------- */
 /* Score + select + greedy-assign one batch of steps (host buffers in, host
  * buffers out; H2D/D2H inside).  Plugs in between step 5 and step 7 of

@@ -263,4 +263,119 @@ __global__ void __launch_bounds__(ORDER_SMALL_THREADS) k_order_sort_small(const 
   for (int i = threadIdx.x; i < n; i += ORDER_SMALL_THREADS) order[i] = so_keys[i];
 }
 
+// ================================================== incremental snapshot refresh
+// A few nodes changed their free capacity (a pod was bound / deleted).  base = W * min(free, F) is linear in
+// fmin, so  base[n] += w(n, m) * delta_m  over the closed neighbourhood of every changed node m — exact
+// integer arithmetic below 2^24, hence bit-identical to a full recomputation in any order — and the
+// background order is REPAIRED: the affected entries are taken out and merged back at their new rank
+// instead of sorting all N keys again.  pos[node] = the node's position in `order` is kept beside it.
+constexpr int DELTA_MAX_AFFECTED = 2048;  // affected nodes one repair handles (above: full refresh)
+
+// order -> pos (after every full sort)
+__global__ void k_order_pos(const unsigned long long* __restrict__ order, int n, int* __restrict__ pos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pos[key_node(order[i])] = i;
+}
+
+// One warp per changed node: new capacity, delta onto the neighbourhood's base, affected nodes appended once.
+// `changed` = (node, free) pairs, host-deduplicated.  aff[0] = counter, aff[1 ..] = affected nodes.
+__global__ void k_delta_apply(TopoDev t, int* __restrict__ free_w, unsigned char* __restrict__ fmin_w, float* __restrict__ base_w,
+                              const int* __restrict__ changed, int n_changed, int* __restrict__ flag, int* __restrict__ aff) {
+  const int lane = threadIdx.x & 31;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= n_changed) return;
+  const int m = changed[2 * c], f_new = changed[2 * c + 1];
+  const int f_old = free_w[m];
+  const int d = min(f_new, RBGTOPO_F_CAP) - min(f_old, RBGTOPO_F_CAP);
+  if (lane == 0) {
+    free_w[m] = f_new;
+    fmin_w[m] = (unsigned char)min(f_new, RBGTOPO_F_CAP);
+  }
+  if (d == 0) return;  // the scores only see min(free, F): nothing else moves (capacity itself is read live)
+  const int rb = t.row_ptr[m], re = t.row_ptr[m + 1];
+  for (int j = rb + lane; j <= re; j += 32) {  // j == re stands for m itself
+    const int nn = j < re ? t.col[j] : m;
+    const int wv = j < re ? t.w[j] : RBGTOPO_SELF_W;
+    atomicAdd(&base_w[nn], (float)(wv * d));
+    if (atomicExch(&flag[nn], 1) == 0) {
+      const int k = atomicAdd(&aff[0], 1);
+      if (k < DELTA_MAX_AFFECTED) aff[1 + k] = nn;
+    }
+  }
+}
+
+// One CTA: the affected nodes' new keys (descending) and old positions (ascending), both sorted in shared
+// memory by a bitonic network (<= 2048 elements: 66 short rounds); flags cleared for the next delta.
+__global__ void __launch_bounds__(1024) k_delta_sort(const float* __restrict__ base, const int* __restrict__ pos,
+                                                     int* __restrict__ flag, int* __restrict__ aff,
+                                                     unsigned long long* __restrict__ new_keys, int* __restrict__ old_pos) {
+  __shared__ unsigned long long sk[DELTA_MAX_AFFECTED];
+  __shared__ int sp[DELTA_MAX_AFFECTED];
+  const int A = min(aff[0], DELTA_MAX_AFFECTED);
+  int p2 = 32;
+  while (p2 < A) p2 <<= 1;
+  for (int i = threadIdx.x; i < p2; i += blockDim.x) {
+    if (i < A) {
+      const int node = aff[1 + i];
+      sk[i] = make_key(base[node], node);
+      sp[i] = pos[node];
+      flag[node] = 0;
+    } else {
+      sk[i] = 0ull;        // sorts last (descending)
+      sp[i] = 0x7FFFFFFF;  // sorts last (ascending)
+    }
+  }
+  __syncthreads();
+  for (int k = 2; k <= p2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int tt = threadIdx.x; tt < (p2 >> 1); tt += blockDim.x) {
+        const int i = ((tt & ~(j - 1)) << 1) | (tt & (j - 1)), l = i | j;
+        const bool up = (i & k) == 0;
+        const unsigned long long a = sk[i], b2 = sk[l];
+        if ((a < b2) == up) { sk[i] = b2; sk[l] = a; }   // keys: descending
+        const int pa = sp[i], pb = sp[l];
+        if ((pa > pb) == up) { sp[i] = pb; sp[l] = pa; }  // positions: ascending
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < A; i += blockDim.x) {
+    new_keys[i] = sk[i];
+    old_pos[i] = sp[i];
+  }
+}
+
+// Merge: every kept entry of the old order moves by (new keys above it) - (removed entries before it);
+// every affected node is inserted at (its rank among the new keys) + (kept entries above it).
+__global__ void k_delta_merge(const unsigned long long* __restrict__ order_old, int n, const int* __restrict__ aff,
+                              const unsigned long long* __restrict__ new_keys, const int* __restrict__ old_pos,
+                              unsigned long long* __restrict__ order_new, int* __restrict__ pos) {
+  const int A = min(aff[0], DELTA_MAX_AFFECTED);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  auto removed_before = [&](int p) {  // old positions < p that were taken out
+    int lo = 0, hi = A;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (old_pos[mid] < p) lo = mid + 1; else hi = mid; }
+    return lo;
+  };
+  if (i < n) {
+    const unsigned long long key = order_old[i];
+    const int rb = removed_before(i);
+    const bool removed = rb < A && old_pos[rb] == i;
+    if (!removed) {
+      int lo = 0, hi = A;  // new keys greater than key (new_keys is descending)
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (new_keys[mid] > key) lo = mid + 1; else hi = mid; }
+      const int np = i - rb + lo;
+      order_new[np] = key;
+      pos[key_node(key)] = np;
+    }
+  }
+  if (i < A) {
+    const unsigned long long key = new_keys[i];
+    int lo = 0, hi = n;  // old entries greater than key (order_old is descending); the node's own old entry may count: it is removed below
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (order_old[mid] > key) lo = mid + 1; else hi = mid; }
+    const int np = i + lo - removed_before(lo);
+    order_new[np] = key;
+    pos[key_node(key)] = np;
+  }
+}
+
 }  // namespace rbgtopo

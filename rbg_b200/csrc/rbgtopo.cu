@@ -123,6 +123,11 @@ struct Topology {
   DevBuf<unsigned long long> okeys, order;  // background order of the slab (score.cuh / select.cuh)
   DevBuf<unsigned long long> okeys_all, order_all;  // world > 1: the order over all nodes (plan_group.cuh)
   DevBuf<unsigned char> sort_tmp;
+  // incremental refresh (rbgtopo_update_nodes_delta, world == 1): position of every node in `order`, the scratch
+  // of one repair, and whether pos matches order (set by every full refresh)
+  DevBuf<int> pos, flag, aff, old_pos, d_changed;
+  DevBuf<unsigned long long> new_keys, order_alt;
+  bool pos_valid = false;
   int key_nb = 0, key_bits = 64;           // compact sort key of the background order (prepare_refresh)
   cudaGraphExec_t refresh_exec = nullptr;  // captured refresh chain of this topology (run_base): k_prep + k_base ...
   cudaGraphExec_t order_exec = nullptr;    // ... and the order sorts, so that base_ready can be recorded between them
@@ -392,6 +397,15 @@ int prepare_refresh(rbgtopo_ctx* c) {
     need = std::max(need, tmp_bytes);
   }
   CK(T.sort_tmp.reserve(need + 256));
+  if (c->cfg.world == 1) {
+    CK(T.pos.reserve((size_t)T.n));
+    CK(T.flag.reserve((size_t)T.n));
+    CK(cudaMemset(T.flag.p, 0, T.flag.cap * 4));
+    CK(T.aff.reserve(1 + DELTA_MAX_AFFECTED));
+    CK(T.old_pos.reserve(DELTA_MAX_AFFECTED));
+    CK(T.new_keys.reserve(DELTA_MAX_AFFECTED));
+    CK(T.order_alt.reserve((size_t)T.n));
+  }
   return RBGTOPO_OK;
 }
 
@@ -425,6 +439,8 @@ int enqueue_refresh(rbgtopo_ctx* c, cudaStream_t s, int part) {
     CK(cub::DeviceRadixSort::SortKeysDescending(T.sort_tmp.p, tmp_bytes, T.okeys.p, T.order.p, slab_len, 0, T.key_bits, s));
     if (T.key_nb) k_order_expand<<<(slab_len + 255) / 256, 256, 0, s>>>(T.order.p, slab_len, T.key_nb);
   }
+  if (c->cfg.world == 1 && slab_len > 0)  // node -> position, for the incremental repair of the order
+    k_order_pos<<<(slab_len + 255) / 256, 256, 0, s>>>(T.order.p, slab_len, T.pos.p);
   if (c->cfg.world > 1 && T.n > 0 && T.n <= ORDER_SMALL_MAX && kSmallSort) {
     k_order_sort_small<<<1, ORDER_SMALL_THREADS, p2_bytes(T.n), s>>>(T.base.p, 0, T.n, T.order_all.p);
   } else if (c->cfg.world > 1 && T.n > 0) {  // replicated selection (plan_group.cuh) walks the order of ALL nodes
@@ -480,6 +496,7 @@ int run_base(rbgtopo_ctx* c, cudaStream_t s, bool sync) {
   }
   CK(cudaEventRecord(c->ev_base_b, s));
   CK(cudaEventRecord(c->topo_ready, s));
+  T.pos_valid = c->cfg.world == 1;
   c->base_timing_pending = true;
   CK(cudaGetLastError());
   if (sync) {
@@ -1299,6 +1316,81 @@ int32_t rbgtopo_update_nodes(rbgtopo_ctx* c, const int32_t* free_slots, const in
   // asynchronous: the refresh (prep, base SpMV, order sort) overlaps the caller's next host
   // work; every batch stream waits on topo_ready before reading the snapshot
   return run_base(c, s, false);
+}
+
+namespace {
+__global__ void k_delta_scatter(int* __restrict__ free_w, const int* __restrict__ changed, int n_changed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_changed) free_w[changed[2 * i]] = changed[2 * i + 1];
+}
+}  // namespace
+
+// Capacity of a few nodes changed (a pod was bound / deleted; the caller cadence is the reconcile
+// events of rolebasedgroup_controller.go:1347-1430): incremental refresh of base and of the background
+// order (kernels.cuh) instead of the full SpMV + sort.  Falls back to the full refresh when the closed
+// neighbourhoods of the changed nodes hold more than DELTA_MAX_AFFECTED nodes, or with world > 1.
+int32_t rbgtopo_update_nodes_delta(rbgtopo_ctx* c, int32_t n_changed, const int32_t* nodes, const int32_t* free_slots,
+                                   uint64_t generation) {
+  if (!c || n_changed < 0 || (n_changed && (!nodes || !free_slots))) return fail(RBGTOPO_EINVAL, "null argument");
+  std::unique_lock<std::shared_mutex> lk(c->topo_mu);
+  Topology& T = c->topo;
+  if (!T.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
+  CK(cudaSetDevice(c->cfg.device));
+  T.generation = generation;
+  if (n_changed == 0) return RBGTOPO_OK;
+  // validate + deduplicate (the last value of a node wins, as a sequence of single updates would)
+  std::vector<std::pair<int32_t, int32_t>> ch((size_t)n_changed);
+  for (int i = 0; i < n_changed; ++i) {
+    if (nodes[i] < 0 || nodes[i] >= T.n) return fail(RBGTOPO_EINVAL, "nodes[%d] = %d", i, nodes[i]);
+    if (free_slots[i] < 0 || free_slots[i] > RBGTOPO_MAX_FREE) return fail(RBGTOPO_EINVAL, "free[%d]", i);
+    ch[i] = {nodes[i], i};
+  }
+  std::sort(ch.begin(), ch.end());
+  long long est = 0;
+  size_t m = 0;
+  for (size_t i = 0; i < ch.size(); ++i) {
+    if (i + 1 < ch.size() && ch[i + 1].first == ch[i].first) continue;  // a later entry of the same node follows
+    ch[m++] = {ch[i].first, free_slots[ch[i].second]};
+    est += T.h_degp1[ch[i].first];
+  }
+  ch.resize(m);
+  cudaStream_t s = c->topo_stream;
+  {
+    int frc = fence_batches(c, false);  // batches already enqueued read the old snapshot first
+    if (frc) return frc;
+  }
+  const unsigned sb = c->stage_idx++ & 1u;
+  CK(cudaEventSynchronize(c->stage_ev[sb]));
+  CK(c->h_free[sb].reserve(2 * m));
+  for (size_t i = 0; i < m; ++i) {
+    c->h_free[sb].p[2 * i] = ch[i].first;
+    c->h_free[sb].p[2 * i + 1] = ch[i].second;
+  }
+  CK(T.d_changed.reserve(2 * m));
+  CK(cudaMemcpyAsync(T.d_changed.p, c->h_free[sb].p, 2 * m * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaEventRecord(c->stage_ev[sb], s));
+  const bool incremental = c->cfg.world == 1 && T.pos_valid && est <= DELTA_MAX_AFFECTED && getenv("RBGTOPO_NO_DELTA") == nullptr;
+  if (!incremental) {  // scatter the new capacities, then the full refresh
+    k_delta_scatter<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(T.free_.p, T.d_changed.p, (int)m);
+    CK(cudaGetLastError());
+    return run_base(c, s, false);
+  }
+  CK(cudaEventRecord(c->ev_base_a, s));
+  CK(cudaMemsetAsync(T.aff.p, 0, 4, s));
+  const TopoDev td = topo_dev(c);
+  k_delta_apply<<<(unsigned)((m * 32 + 255) / 256), 256, 0, s>>>(td, T.free_.p, T.fmin.p, T.base.p, T.d_changed.p, (int)m, T.flag.p, T.aff.p);
+  CK(cudaEventRecord(c->base_ready, s));  // what the dense-matrix kernel reads is up to date
+  k_delta_sort<<<1, 1024, 0, s>>>(T.base.p, T.pos.p, T.flag.p, T.aff.p, T.new_keys.p, T.old_pos.p);
+  const int n = c->slab_hi - c->slab_lo;  // == T.n (world == 1)
+  k_delta_merge<<<(n + 255) / 256, 256, 0, s>>>(T.order.p, n, T.aff.p, T.new_keys.p, T.old_pos.p, T.order_alt.p, T.pos.p);
+  CK(cudaMemcpyAsync(T.order.p, T.order_alt.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));  // the refresh graph holds T.order.p
+  CK(cudaEventRecord(c->ev_base_b, s));
+  CK(cudaEventRecord(c->topo_ready, s));
+  c->base_timing_pending = true;
+  CK(cudaGetLastError());
+  std::lock_guard<std::mutex> g(c->stat_mu);
+  c->launches += 3;
+  return RBGTOPO_OK;
 }
 
 int32_t rbgtopo_score_assign(rbgtopo_ctx* c, const int32_t* blob, int64_t words, int32_t* assign,

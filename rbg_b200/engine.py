@@ -91,6 +91,12 @@ class TopoPlacer:
         o = None if domain_owner is None else _i32(domain_owner)
         self._check(self.lib.rbgtopo_update_nodes(self._h, _p(f), _p(o), generation))
 
+    def update_nodes_delta(self, nodes, free, generation: int = 0) -> None:
+        """Capacity of a few nodes changed: incremental refresh of base and of the background order."""
+        nd, fr = _i32(nodes), _i32(free)
+        assert len(nd) == len(fr)
+        self._check(self.lib.rbgtopo_update_nodes_delta(self._h, len(nd), _p(nd), _p(fr), generation))
+
     # -- hot path, host buffers in/out
     def score_assign(self, blob: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         blob = _i32(blob)
