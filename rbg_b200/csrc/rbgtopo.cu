@@ -6,6 +6,7 @@
 // No CPU fallback exists: every entry point needs a CUDA device (sm_100).
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <chrono>
@@ -58,6 +59,12 @@ int fail(int code, const char* fmt, ...) {
   }
   return code;
 }
+
+// NVTX range of a host-side phase (SURVEY.md §5 tracing row): visible in nsys / ncu timelines, free otherwise.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 #define CK(expr)                                                                      \
   do {                                                                                \
@@ -457,6 +464,7 @@ int enqueue_refresh(rbgtopo_ctx* c, cudaStream_t s, int part) {
 // topology into a CUDA graph and replayed (one launch instead of 12+ from update_nodes);
 // RBGTOPO_NO_REFRESH_GRAPH or a failed capture fall back to the plain launches.
 int run_base(rbgtopo_ctx* c, cudaStream_t s, bool sync) {
+  NvtxRange nv("rbgtopo:run_base");
   Topology& T = c->topo;
   if (!T.refresh_ready) {
     int rc = prepare_refresh(c);
@@ -687,6 +695,7 @@ int reserve_batch_buffers(rbgtopo_ctx* c, Batch* b) {
 // validate + size buffers + H2D.  Caller holds topo_mu shared.
 // blob == b->h_in.p: the (trusted) plan was built in place in the pinned staging buffer.
 int stage_into(rbgtopo_ctx* c, Batch* b, const int32_t* blob, int64_t words) {
+  NvtxRange nv("rbgtopo:stage_into");
   if (!c->topo.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
   const bool in_place = blob == b->h_in.p;
   int rc = validate_blob(c, blob, words, &b->m, in_place);
@@ -869,6 +878,7 @@ int ensure_pass_events(Batch* b, int passes) {
 // device.  Every pass gets three events (before score, after score, after
 // select) until kMaxTimedPasses passes are pending harvest.
 int run_batch(rbgtopo_ctx* c, Batch* b, int iters) {
+  NvtxRange nv("rbgtopo:run_batch");
   cudaStream_t s = stream_of(c, b);
   int launches = 0;
   BatchDev d = batch_dev(c, b);
@@ -947,6 +957,7 @@ int enqueue_d2h(rbgtopo_ctx* c, Batch* b) {
 }
 
 int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int32_t* domain) {
+  NvtxRange nv("rbgtopo:fetch_batch");
   cudaStream_t s = stream_of(c, b);
   const BatchMeta& m = b->m;
   if (!b->d2h_enqueued) {
@@ -1332,6 +1343,7 @@ __global__ void k_delta_scatter(int* __restrict__ free_w, const int* __restrict_
 int32_t rbgtopo_update_nodes_delta(rbgtopo_ctx* c, int32_t n_changed, const int32_t* nodes, const int32_t* free_slots,
                                    uint64_t generation) {
   if (!c || n_changed < 0 || (n_changed && (!nodes || !free_slots))) return fail(RBGTOPO_EINVAL, "null argument");
+  NvtxRange nv("rbgtopo:update_nodes_delta");
   std::unique_lock<std::shared_mutex> lk(c->topo_mu);
   Topology& T = c->topo;
   if (!T.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
@@ -2220,6 +2232,7 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
 // entry point: one pass follows at once); run_batch then skips that launch.
 int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, bool early_emit = false, int g_lo = 0, int g_hi = -1,
                long long pacc0 = 0, const int* dev_groups = nullptr, cudaEvent_t dev_groups_ready = nullptr) {
+  NvtxRange nv("rbgtopo:plan_stage");
   const Topology& T = c->topo;
   if (!T.valid) return fail(RBGTOPO_ENOTOPO, "set_topology has not been called");
   TopoHost th;
