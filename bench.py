@@ -114,7 +114,7 @@ def oracle_scores_per_sec(topo, blobs, nthreads, min_seconds=6.0, max_reps=1 << 
         scores += per_pass
         reps += 1
         dt = time.perf_counter() - t0
-        if dt >= min_seconds or reps >= max_reps:
+        if reps >= max_reps or (dt >= min_seconds and max_reps >= (1 << 30)):   # a rep count, when given, is exact
             break
     return scores / dt, dt, reps
 
@@ -719,7 +719,7 @@ def run_reference(args):
         oracle_scores_per_sec(topo, blobs, nt, min_seconds=0.0, max_reps=1, fast=True)
     v, dt, reps = oracle_scores_per_sec(topo, blobs, nt, min_seconds=0.0, max_reps=args.steps, fast=True)
     ntl = best_oracle_threads(topo, blobs)
-    vl, _, _ = oracle_scores_per_sec(topo, blobs, ntl, min_seconds=0.0, max_reps=max(1, args.steps // 4))
+    vl, _, _ = oracle_scores_per_sec(topo, blobs, ntl, min_seconds=0.0, max_reps=max(1, args.steps // 10))
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": cfg["scaling"],

@@ -406,6 +406,21 @@ int32_t rbgtopo_intstr_non_zero(int32_t is_percent, int32_t value, int32_t repli
 int32_t rbgtopo_merge_rolling_update(const int32_t* strategy_a, const int32_t* strategy_b,
                                      int32_t* out);
 
+/* GetWorkloadName, api/workloads/v1alpha2/helper.go:68-81 ("{rbg}-{role}", 63 bytes, trailing '-'
+ * trimmed); out_len >= 64; returns the length. */
+int32_t rbgtopo_workload_name(const char* rbg_name, const char* role_name, char* out,
+                              int32_t out_len);
+
+/* GenGroupUniqueKey, helper.go:135-144: hex SHA-1 of "namespace/name" — the value of the
+ * group-unique-hash label the exclusive-topology affinity terms match on
+ * (pkg/reconciler/pod_reconciler.go:172-231); out_len >= 41; returns 40. */
+int32_t rbgtopo_group_unique_key(const char* ns, const char* name, char* out, int32_t out_len);
+
+/* InheritPodGroupAnnotations, pkg/scheduler/common/annotation_inheritance.go:23-43, per key:
+ * 1 when the PodGroup inherits the annotation (the key starts with one of the prefixes). */
+int32_t rbgtopo_inherits_annotation(const char* key, int32_t n_prefixes,
+                                    const char* const* prefixes);
+
 /* ---- host-only inspection of the multi-wave plan (no GPU needed) ----------- *
  * The step geometry rbgtopo_place_groups / rbgtopo_stage_groups derive from a
  * GROUPS blob — which wave every pending replica is placed in, how the waves of

@@ -76,6 +76,9 @@ SIGNATURES = {
     "rbgtopo_partition_replicas": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, i32p]),
     "rbgtopo_intstr_non_zero": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, i32p]),
     "rbgtopo_merge_rolling_update": (C.c_int32, [i32p, i32p, i32p]),
+    "rbgtopo_workload_name": (C.c_int32, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32]),
+    "rbgtopo_group_unique_key": (C.c_int32, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32]),
+    "rbgtopo_inherits_annotation": (C.c_int32, [C.c_char_p, C.c_int32, C.POINTER(C.c_char_p)]),
     "rbgtopo_plan_describe": (C.c_int32, [i32p, C.c_int64, C.c_int32, C.c_int32, i32p, C.c_int64, i32p, C.c_int64,
                                           i32p, i32p, C.POINTER(C.c_int64)]),
 }

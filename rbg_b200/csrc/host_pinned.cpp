@@ -240,4 +240,66 @@ int32_t rbgtopo_merge_rolling_update(const int32_t* a, const int32_t* b, int32_t
   return RBGTOPO_OK;
 }
 
+// GetWorkloadName — api/workloads/v1alpha2/helper.go:68-81: "{rbg}-{role}", cut to 63 bytes, trailing '-' trimmed.
+// Writes the NUL-terminated name (out_len >= 64); returns its length or RBGTOPO_EINVAL.
+int32_t rbgtopo_workload_name(const char* rbg_name, const char* role_name, char* out, int32_t out_len) {
+  if (!rbg_name || !role_name || !out || out_len < 64) return RBGTOPO_EINVAL;
+  std::string name = std::string(rbg_name) + "-" + role_name;
+  if (name.size() > 63) {
+    name.resize(63);
+    while (!name.empty() && name.back() == '-') name.pop_back();
+  }
+  memcpy(out, name.c_str(), name.size() + 1);
+  return (int32_t)name.size();
+}
+
+// GenGroupUniqueKey — helper.go:135-144: lower-case hex SHA-1 of "namespace/name" (40 characters + NUL, out_len >= 41).
+int32_t rbgtopo_group_unique_key(const char* ns, const char* name, char* out, int32_t out_len) {
+  if (!ns || !name || !out || out_len < 41) return RBGTOPO_EINVAL;
+  const std::string msg = std::string(ns) + "/" + name;
+  // SHA-1 (FIPS 180-4), one pass over the padded message
+  uint32_t h[5] = {0x67452301u, 0xEFCDAB89u, 0x98BADCFEu, 0x10325476u, 0xC3D2E1F0u};
+  std::vector<unsigned char> m(msg.begin(), msg.end());
+  const uint64_t bits = (uint64_t)m.size() * 8;
+  m.push_back(0x80);
+  while (m.size() % 64 != 56) m.push_back(0);
+  for (int i = 7; i >= 0; --i) m.push_back((unsigned char)(bits >> (8 * i)));
+  auto rol = [](uint32_t v, int r) { return (v << r) | (v >> (32 - r)); };
+  for (size_t off = 0; off < m.size(); off += 64) {
+    uint32_t w[80];
+    for (int i = 0; i < 16; ++i)
+      w[i] = ((uint32_t)m[off + 4 * i] << 24) | ((uint32_t)m[off + 4 * i + 1] << 16) | ((uint32_t)m[off + 4 * i + 2] << 8) | m[off + 4 * i + 3];
+    for (int i = 16; i < 80; ++i) w[i] = rol(w[i - 3] ^ w[i - 8] ^ w[i - 14] ^ w[i - 16], 1);
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4];
+    for (int i = 0; i < 80; ++i) {
+      uint32_t f, k;
+      if (i < 20) { f = (b & c) | (~b & d); k = 0x5A827999u; }
+      else if (i < 40) { f = b ^ c ^ d; k = 0x6ED9EBA1u; }
+      else if (i < 60) { f = (b & c) | (b & d) | (c & d); k = 0x8F1BBCDCu; }
+      else { f = b ^ c ^ d; k = 0xCA62C1D6u; }
+      const uint32_t t = rol(a, 5) + f + e + k + w[i];
+      e = d; d = c; c = rol(b, 30); b = a; a = t;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e;
+  }
+  static const char* hex = "0123456789abcdef";
+  for (int i = 0; i < 5; ++i)
+    for (int j = 0; j < 8; ++j) out[8 * i + j] = hex[(h[i] >> (28 - 4 * j)) & 15];
+  out[40] = 0;
+  return 40;
+}
+
+// InheritPodGroupAnnotations — pkg/scheduler/common/annotation_inheritance.go:23-43, per key: 1 when the key
+// starts with one of the n_prefixes prefixes (the PodGroup inherits it), else 0.  The map filtering around it is
+// the host language's; an empty result is reported as nil by the reference.
+int32_t rbgtopo_inherits_annotation(const char* key, int32_t n_prefixes, const char* const* prefixes) {
+  if (!key || n_prefixes < 0 || (n_prefixes && !prefixes)) return RBGTOPO_EINVAL;
+  for (int i = 0; i < n_prefixes; ++i) {
+    if (!prefixes[i]) return RBGTOPO_EINVAL;
+    const size_t n = strlen(prefixes[i]);
+    if (strncmp(key, prefixes[i], n) == 0) return 1;
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -965,7 +965,9 @@ int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int3
     if (rc) return rc;
   }
   b->d2h_enqueued = false;
+  const auto f0 = std::chrono::steady_clock::now();
   CK(cudaStreamSynchronize(s));
+  const auto f1 = std::chrono::steady_clock::now();
   CK(cudaGetLastError());
   if (assign && m.total_r) memcpy(assign, b->h_out.p, (size_t)m.total_r * 4);
   if (status && m.n_steps) memcpy(status, b->h_out.p + m.total_r, (size_t)m.n_steps * 4);
@@ -1011,6 +1013,17 @@ int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int3
               s4[4] / nw, s4[5] / nw, s4[0] / nw, s4[1] / nw, s4[2] / nw, s4[3] / nw, s4[0] / std::max(1.0, s4[4]), s4[1] / std::max(1.0, s4[5]),
               s4[2] / std::max(1.0, s4[5]), s4[3] / std::max(1.0, s4[5]));
     }
+  }
+  static const bool prof_dev = getenv("RBGTOPO_PROFILE_HOST") != nullptr;
+  if (prof_dev && b->passes == 1 && !b->wave_begin.empty()) {  // device timeline of a place_groups call, us after the staging began
+    float t[6] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t evs[6] = {b->it_ev[0], b->it_ev[1], b->ev[1], b->it_ev[2], b->ev[4], b->ev[5]};
+    for (int i = 0; i < 6; ++i)
+      if (cudaEventElapsedTime(&t[i], b->ev[0], evs[i]) != cudaSuccess) t[i] = -1.f;
+    fprintf(stderr, "[rbgtopo fetch] stream sync returned after %.0f us\n", std::chrono::duration<double, std::micro>(f1 - f0).count());
+    fprintf(stderr, "[rbgtopo device] us after staging began: emit start %.0f, emit end %.0f, plan expanded %.0f, selection end %.0f, D2H start %.0f, D2H end %.0f\n",
+            t[0] * 1e3, t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3, t[5] * 1e3);
+    (void)cudaGetLastError();
   }
   rbgtopo_timing tm{};
   float x = 0.f;
@@ -2265,6 +2278,7 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, bool 
       CK(cudaMemsetAsync(b->emit_ctr.p, 0, 8, s));  // re-arm the TMA item queue (a failed launch may have left it mid-way)
       CK(cudaGetLastError());
       b->pend_launches += 1;
+      CK(cudaEventRecord(b->ev[2], s));  // GROUPS blob + emit table are on the device: the second half of the staging may follow on stream2
       if (early_emit) {  // pass 0 of run_batch starts here
         int erc = ensure_pass_events(b, b->passes + 1);
         if (erc) return erc;
@@ -2293,15 +2307,24 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, bool 
   CK(b->blob.reserve((size_t)plan_words + tail_words));
   rc = reserve_batch_buffers(c, b);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(b->gsrc.p + aux_off, hin + aux_off, (src_words - aux_off) * 4, cudaMemcpyHostToDevice, s));  // geometry + poff
+  // second half of the staging: geometry + poff up, plan expanded.  With an early emit in flight on s it goes to
+  // stream2 (it needs only the first upload), so the plan is ready when the dense-matrix kernel ends instead of
+  // 20+ us later; s joins before anything reads the plan.
+  cudaStream_t s_exp = (b->early_emit && ns > 0) ? b->stream2 : s;
+  if (s_exp != s) CK(cudaStreamWaitEvent(s_exp, b->ev[2], 0));
+  CK(cudaMemcpyAsync(b->gsrc.p + aux_off, hin + aux_off, (src_words - aux_off) * 4, cudaMemcpyHostToDevice, s_exp));  // geometry + poff
   {
     const long long warps = (long long)ns + ((long long)tail_words + 1 + 31) / 32;  // a warp per step + tail words
-    k_expand_plan<<<(unsigned)((warps + PLAN_WARPS - 1) / PLAN_WARPS), 32 * PLAN_WARPS, 0, s>>>(dev_groups ? dev_groups : b->gsrc.p, b->gsrc.p, b->blob.p, ns, (int)plan_words,
+    k_expand_plan<<<(unsigned)((warps + PLAN_WARPS - 1) / PLAN_WARPS), 32 * PLAN_WARPS, 0, s_exp>>>(dev_groups ? dev_groups : b->gsrc.p, b->gsrc.p, b->blob.p, ns, (int)plan_words,
                                                                    (int)aux_off, (int)tail_off, (int)tail_words,
                                                                    (int)racc, (int)rowacc);
     CK(cudaGetLastError());
   }
-  CK(cudaEventRecord(b->ev[1], s));  // h2d_ms = uploads + emit table + expansion (+ the early emit launch when there is one)
+  if (s_exp != s) {
+    CK(cudaEventRecord(b->ev[3], s_exp));
+    CK(cudaStreamWaitEvent(s, b->ev[3], 0));
+  }
+  CK(cudaEventRecord(b->ev[1], s));  // h2d_ms = uploads + emit table + expansion (+ the early emit when there is one)
   b->pend_launches += 1;
   b->staged = true;
   b->ran = false;

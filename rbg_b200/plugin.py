@@ -41,6 +41,9 @@ ROLE_DISABLE_EXCLUSIVE_KEY = RBG_PREFIX + "role-disable-exclusive"  # annotation
 GANG_SCHEDULING_KEY = RBG_PREFIX + "group-gang-scheduling"          # annotation.go:37
 PLACEMENT_HINT_KEY = RBG_PREFIX + "b200-topo-placement"             # new: RoleID -> node map
 SCHEDULER_PLUGIN_NAME = "b200-topo"                                 # --scheduler-name value
+# what the wrapped gang plugins inject into the pod template when gang scheduling is on
+KUBE_POD_GROUP_LABEL = "pod-group.scheduling.sigs.k8s.io/name"      # k8s-scheduler-plugin/manager.go:49,91-98
+VOLCANO_GROUP_ANNOTATION = "scheduling.k8s.io/group-name"           # volcano/manager.go:85-92
 
 
 @dataclass
@@ -284,9 +287,12 @@ class _GroupRun:
 class B200TopoPodGroupManager:
     """Third ``PodGroupManager`` implementation (plugin type "b200-topo")."""
 
-    def __init__(self, placer: TopoPlacer):
+    def __init__(self, placer: TopoPlacer, inner: Optional[str] = "scheduler-plugins"):
+        """inner: the gang plugin this manager wraps for the PodGroup CR and the pod-group label —
+        "scheduler-plugins" (kube), "volcano" or None (the Go manager takes the implementation object)."""
         self.placer = placer
         self.arith = HostArith()
+        self.inner = inner
         self._hints: Dict[Tuple[str, str], Placement] = {}
 
     # -- ReconcilePodGroup(ctx, rbg, ...) for one group -------------------------
@@ -417,10 +423,16 @@ class B200TopoPodGroupManager:
     def InjectPodGroupLabels(self, rbg: RoleBasedGroup, pod_template: dict) -> None:  # noqa: N802
         """Adds the serialized RoleID -> node map as a pod-template annotation
         (the template is per role, not per replica: SURVEY.md §8b "Injection")."""
+        meta = pod_template.setdefault("metadata", {})
+        if rbg.annotations.get(GANG_SCHEDULING_KEY) == "true":     # the wrapped plugin's injection, unchanged
+            if self.inner == "scheduler-plugins":
+                meta.setdefault("labels", {})[KUBE_POD_GROUP_LABEL] = rbg.name
+            elif self.inner == "volcano":
+                meta.setdefault("annotations", {})[VOLCANO_GROUP_ANNOTATION] = rbg.name
         p = self._hints.get((rbg.namespace, rbg.name))
         if p is None:
             return
-        ann = pod_template.setdefault("metadata", {}).setdefault("annotations", {})
+        ann = meta.setdefault("annotations", {})
         ann[PLACEMENT_HINT_KEY] = json.dumps({k: v for k, v in sorted(p.nodes.items()) if v >= 0},
                                              separators=(",", ":"))
 

@@ -201,3 +201,21 @@ def test_merge_rolling_update(lib, golden):
             assert unpack(list(out)) == want, c["name"]
             n += 1
     assert n >= 3
+
+
+def test_naming_keys_and_annotation_inheritance(lib, golden):
+    # helper.go:68-81 (63-byte cut + TrimRight "-"), :135-144 (sha1), annotation_inheritance_test.go:25-49 — product C functions
+    import hashlib
+    buf = C.create_string_buffer(64)
+    for rbg, role in [("rbg", "prefill"), ("a" * 62, "-x"), ("x" * 40, "y" * 40), ("n", "r")]:
+        n = lib.rbgtopo_workload_name(rbg.encode(), role.encode(), buf, 64)
+        assert buf.value.decode() == rp.get_workload_name(rbg, role) and n == len(buf.value)
+    key = C.create_string_buffer(41)
+    for ns, name in [("default", "test-rbg"), ("ns", "n"), ("a" * 70, "b" * 70), ("", "")]:
+        assert lib.rbgtopo_group_unique_key(ns.encode(), name.encode(), key, 41) == 40
+        assert key.value.decode() == hashlib.sha1(f"{ns}/{name}".encode()).hexdigest() == rp.gen_group_unique_key(ns, name)
+    for c in golden["inherit_pod_group_annotations"]["cases"]:
+        ann, prefixes = c["annotations"] or {}, c["prefixes"]
+        arr = (C.c_char_p * max(len(prefixes), 1))(*[p.encode() for p in prefixes])
+        got = {k: v for k, v in ann.items() if lib.rbgtopo_inherits_annotation(k.encode(), len(prefixes), arr) == 1}
+        assert (got or None) == c["want"]

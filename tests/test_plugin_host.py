@@ -193,3 +193,21 @@ def test_reconcile_ahead_with_a_role_no_rule_paces():
     assert sum(k.startswith("pd-prefill-") for k in first.nodes) == 10
     assert sum(k.startswith("pd-prefill-") for k in second.nodes) == 10
     assert len(first.nodes) + len(second.nodes) == 2 + 20 + 10
+
+
+def test_inject_pod_group_labels_keeps_the_wrapped_plugins_injection():
+    """pkg/scheduler/podgroup_manager_test.go: the kube plugin labels the template, volcano annotates it,
+    only when group-gang-scheduling == "true"; the placement hint rides beside it."""
+    from rbg_b200.plugin import KUBE_POD_GROUP_LABEL, VOLCANO_GROUP_ANNOTATION
+    topo = synth.make_topology(256, seed=1, tiers=2)
+    gang = mooncake("mc", annotations={GANG_SCHEDULING_KEY: "true"})
+    plain = mooncake("mc2", gid=1)
+    for inner, where, key in (("scheduler-plugins", "labels", KUBE_POD_GROUP_LABEL), ("volcano", "annotations", VOLCANO_GROUP_ANNOTATION)):
+        mgr = B200TopoPodGroupManager(OraclePlacer(topo), inner=inner)
+        mgr.reconcile_pod_groups_by_waves([gang, plain])
+        t1, t2 = {}, {}
+        mgr.InjectPodGroupLabels(gang, t1)
+        mgr.InjectPodGroupLabels(plain, t2)
+        assert t1["metadata"][where][key] == "mc"
+        assert key not in t2["metadata"].get(where, {})
+        assert PLACEMENT_HINT_KEY in t1["metadata"]["annotations"] and PLACEMENT_HINT_KEY in t2["metadata"]["annotations"]
