@@ -10,19 +10,29 @@ pd-disaggregated-with-mooncake.yaml) on a 10 000-node 4-tier synthetic topology,
 batched `--groups` RBGs per launch (a single RBG is a ~3 MB, ~1 us problem:
 launch-bound, SURVEY.md §0.6 — batching is what makes the roofline meaningful).
 
-  value : scores/s with the wave batches already resident in HBM (kernels only,
+  parity : BEFORE any timing, on every rank: the CPU oracle's level / wave loop
+          re-places a deterministic sample of 64 groups and the dense matrix bits
+          of this rank's slab, the assignment, status and exclusive domain are
+          compared with the staged plan; a mismatch aborts the run
+  value : scores/s with the multi-wave plan already resident in HBM (kernels only,
           one stream, CUDA events around the K steps, max over ranks)
   e2e   : the same metric through the C-ABI plugin call with HOST buffers:
           rbgtopo_update_nodes(free) + rbgtopo_place_groups(groups blob) per
-          step — H2D of every wave's inputs and D2H of every wave's results,
-          and the host-side wave loop, inside the timed region
-  roofline : k_score_select (dominant kernel): algorithmic bytes / CUDA-event
+          step — H2D of the inputs and D2H of the results inside the timed region
+  roofline : k_score_emit (dominant kernel): algorithmic bytes / CUDA-event
           duration of its launches inside the timed region vs the measured HBM
-          peak (MEASURED_PEAKS.json)
-  cpu_baseline : the CPU oracle of OUR spec (kind "port": sgl-project/rbg has no
-          such path and no Go toolchain exists here) on a bounded sample
+          peak (MEASURED_PEAKS.json); per-launch min / median / max beside it
+  cpu_baseline : a CPU port of OUR spec (kind "port": sgl-project/rbg has no such
+          path and no Go toolchain exists here) on a bounded sample — the variant
+          with the GPU path's algebra (oracle/placer_fast.c), the literal oracle
+          beside it
+  alt   : cfg4 (BASELINE.json configs[3]: 1 000 RBGs x 8 replicas on 50 000 nodes,
+          strong scaling under --gpus N) and cfg5 (configs[4]: continuous reconcile
+          under 10 % node churn per step + a small-churn line through
+          rbgtopo_update_nodes_delta), each with its own parity block
 
-`--impl reference` times that CPU oracle as the reference arm.
+`--impl reference` times the CPU port as the reference arm; its inputs are built by
+oracle-side code only (the product library is never loaded in that process).
 """
 from __future__ import annotations
 

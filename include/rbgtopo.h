@@ -206,8 +206,11 @@ int32_t rbgtopo_score_assign(rbgtopo_ctx* ctx, const int32_t* blob,
  * rolebasedgroup_controller.go:448-476), and applies gang all-or-nothing over
  * the whole group (k8s-scheduler-plugin/manager.go:131).  On the device this is
  * a multi-wave plan: the GROUPS blob is expanded into one step blob in HBM, one
- * launch scores the dense rows of every wave, one launch runs every group's
- * waves back to back.  With world > 1 every rank calls it with
+ * launch scores the dense rows of every wave — it is started from inside the
+ * staging, from an emit table built on the device, while the host still computes
+ * the rest of the plan geometry — and one launch runs every group's waves back to
+ * back.  The dense rows of a plan are in GROUP order: row i is the
+ * i-th pending replica of the blob (assign[] order).  With world > 1 every rank calls it with
  * the same blob and gets the same result (replicated selection).  need_rho of a wave is
  * min(RBGTOPO_NEED_CAP, still-unplaced replicas of the roles q with
  * pair[rho][q] > 0), DESIGN.md §3.2.
@@ -256,8 +259,10 @@ int32_t rbgtopo_fetch(rbgtopo_ctx* ctx, int32_t handle, int32_t* assign,
 int32_t rbgtopo_release(rbgtopo_ctx* ctx, int32_t handle);
 
 /* Inspection of a staged+run batch (parity tests): one dense row
- * scores[n_nodes] of replica `row` (global replica index; local slab only when
- * world > 1: out has slab length), and the merged top-K keys of one role row. */
+ * scores[n_nodes] of replica `row` (global replica index — for a staged GROUPS plan
+ * the index into assign[], i.e. group order; local slab only when world > 1: out
+ * has slab length), and the merged top-K keys of one role row (role rows of a
+ * plan are numbered wave-major, rbgtopo_plan_describe column 5). */
 int32_t rbgtopo_read_scores(rbgtopo_ctx* ctx, int32_t handle, int32_t row,
                             float* out, int32_t out_len);
 int32_t rbgtopo_read_topk(rbgtopo_ctx* ctx, int32_t handle, int32_t rolerow,
@@ -431,8 +436,10 @@ int32_t rbgtopo_inherits_annotation(const char* key, int32_t n_prefixes,
  *   capacities and the exactness bound (RBGTOPO_EINEXACT).
  * out_steps receives RBGTOPO_PLAN_STEP_WORDS ints per step, steps in wave-major
  * order: group index, wave of the group, section offset, section end (words of
- * the step blob), first replica row, first role row, next step of the group
- * (0 = last), replicas of the group placed by its earlier waves.  At most
+ * the step blob), first replica row (= the group's assign_off + the replicas of
+ * its earlier waves: dense rows and assign[] are in GROUP order), first role row
+ * (wave-major prefix), next step of the group (0 = last), replicas of the group
+ * placed by its earlier waves.  At most
  * out_cap_steps steps are written; *n_steps / *n_waves / *plan_words report the
  * totals. */
 #define RBGTOPO_PLAN_STEP_WORDS 8

@@ -2448,9 +2448,9 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
     Batch* b = nullptr;
     int rc = acquire_batch(c, &b);
     if (rc) return rc;
+    static const bool no_early = getenv("RBGTOPO_NO_EARLY_EMIT") != nullptr;  // A/B switch (profiles/README.md)
     if (!split) {
       auto t0 = now();
-      static const bool no_early = getenv("RBGTOPO_NO_EARLY_EMIT") != nullptr;  // A/B switch (profiles/README.md)
       rc = plan_stage(c, b, gb, words, kSerialPlan && !no_early);  // early emit: the dense matrix starts while the host finishes the geometry
       auto t1 = now();
       if (!rc && kVerifyPlan) rc = verify_plan(c, b, gb, words);
@@ -2475,11 +2475,11 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
       }
       const int mid = ng_all / 2;
       auto t0 = now();
-      rc = plan_stage(c, b, gb, words, false, 0, mid);
+      rc = plan_stage(c, b, gb, words, kSerialPlan && !no_early, 0, mid);
       if (!rc) rc = run_batch(c, b, 1);
       if (!rc) rc = enqueue_d2h(c, b);
       auto t1 = now();
-      if (!rc) rc = plan_stage(c, b2, gb, words, false, mid, ng_all, b->m.total_r, b->gsrc.p, b->ev[1]);
+      if (!rc) rc = plan_stage(c, b2, gb, words, kSerialPlan && !no_early, mid, ng_all, b->m.total_r, b->gsrc.p, b->ev[2]);  // ev[2]: the blob is up
       if (!rc) rc = run_batch(c, b2, 1);
       if (!rc) rc = enqueue_d2h(c, b2);
       auto t2 = now();
