@@ -637,8 +637,9 @@ def run_ours(args):
             nt = best_oracle_threads(topo, sblobs, fast=True)
             v, dt, reps = oracle_scores_per_sec(topo, sblobs, nt, min_seconds=args.cpu_seconds, fast=True)
             v1, _, _ = oracle_scores_per_sec(topo, sblobs, 1, min_seconds=args.cpu_seconds / 4, fast=True)
-            ntl = best_oracle_threads(topo, sblobs)
-            vl, dtl, _ = oracle_scores_per_sec(topo, sblobs, ntl, min_seconds=args.cpu_seconds / 2)
+            lblobs = oracle_wave_blobs(topo, sample[:max(8, min(len(sample), 128))])   # the literal oracle is ~50x slower: a smaller sample
+            ntl = best_oracle_threads(topo, lblobs)
+            vl, dtl, _ = oracle_scores_per_sec(topo, lblobs, ntl, min_seconds=args.cpu_seconds / 2)
             cpu = {"value": v, "unit": UNIT, "cores": nt, "kind": "port",
                    "sample": f"{len(sample)} of the {len(specs)} RBGs x {reps} passes, same {n_nodes}-node topology, "
                              f"{dt:.1f} s of wall time on {nt} OpenMP threads (the fastest of "
@@ -728,15 +729,15 @@ def run_reference(args):
     for _ in range(min(args.warmup, 1)):
         oracle_scores_per_sec(topo, blobs, nt, min_seconds=0.0, max_reps=1, fast=True)
     v, dt, reps = oracle_scores_per_sec(topo, blobs, nt, min_seconds=0.0, max_reps=args.steps, fast=True)
-    ntl = best_oracle_threads(topo, blobs)
-    vl, _, _ = oracle_scores_per_sec(topo, blobs, ntl, min_seconds=0.0, max_reps=max(1, args.steps // 10))
+    lblobs = oracle_wave_blobs(topo, sample[:max(8, min(len(sample), 128))])   # the literal oracle is ~50x slower: a smaller sample
+    ntl = best_oracle_threads(topo, lblobs)
+    vl, _, _ = oracle_scores_per_sec(topo, lblobs, ntl, min_seconds=0.0, max_reps=max(1, args.steps // 4))
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": cfg["scaling"],
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config}: {cfg['what']} x {n_nodes}-node topology; each step = a bounded sample of "
-                               f"{len(sample)} of the {groups} RBGs (the rate is per score, so the sample size does "
-                               "not enter the comparison)", "groups": groups, "nodes": n_nodes},
+        "config": {"workload": f"{args.config}: {cfg['what']} x {n_nodes}-node topology; each step = "
+                               f"{len(sample)} of the {groups} RBGs", "groups": groups, "nodes": n_nodes},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": nt, "kind": "port",
                          "sample": f"{len(sample)} RBGs per step x {args.steps} steps on {nt} OpenMP threads "
                                    f"(the fastest of {host_thread_candidates()})",
@@ -763,9 +764,9 @@ def main():
     ap.add_argument("--nodes", type=int, default=10000, help="cfg3: nodes per GPU")
     ap.add_argument("--parity-groups", type=int, default=64, help="groups the oracle re-places before timing")
     ap.add_argument("--keep-going", action="store_true", help="report a parity failure in the line instead of aborting")
-    ap.add_argument("--cpu-groups", type=int, default=256)
+    ap.add_argument("--cpu-groups", type=int, default=1024, help="groups per pass of the cpu_baseline leg (the whole fleet)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--ref-groups", type=int, default=256)
+    ap.add_argument("--ref-groups", type=int, default=1024, help="groups per step of the reference arm (the whole fleet: same config as ours)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--shard-mode", default="replicated", choices=["replicated", "allgather", "p2p"],
                     help="N > 1: 'replicated' = dense matrix column-sharded, selection replicated on every rank, "

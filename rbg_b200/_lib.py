@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "librbgtopo.so")
+# RBGTOPO_LIB selects another build of the library (profiling builds such as -DRBGTOPO_PHASE_CLOCKS)
+LIB_PATH = os.environ.get("RBGTOPO_LIB") or os.path.join(_HERE, "csrc", "librbgtopo.so")
 
 i32p = C.POINTER(C.c_int32)
 u64p = C.POINTER(C.c_uint64)
