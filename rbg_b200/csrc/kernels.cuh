@@ -90,6 +90,13 @@ __host__ __device__ __forceinline__ int emit_pack_role(int count, int demand, in
   return count | (need << 6) | ((flags & RBGTOPO_ROLE_EXCLUSIVE) << 11) | (demand << 12);
 }
 
+// ---- row table of a multi-wave plan (emit_rows.cuh): per dense row {need | exclusive << 5 | demand << 6, gid}
+// (need <= RBGTOPO_NEED_CAP < 32).  `exclusive` = the step and the role are exclusive: only then does a
+// background row depend on the group (nodes of domains another group owns are infeasible).
+__host__ __device__ __forceinline__ int emit_pack_row(int demand, int need, bool rexcl) {
+  return need | ((rexcl ? 1 : 0) << 5) | (demand << 6);
+}
+
 // ---------------------------------------------------------------- helpers
 __device__ __forceinline__ uint32_t orderable_u32(float x) {
   uint32_t b = __float_as_uint(x);

@@ -75,8 +75,12 @@ __device__ __forceinline__ void plan_wave_at(PlanScratch* S, int q, int w) {
 // k_expand_plan writes into the step blob later; the first dense row of a step is the group's offset in
 // the batch (assign_off - row_base) plus the replicas of the group's earlier waves — GROUP order, no
 // prefix over steps needed.  Runs right after the first H2D of rbgtopo_place_groups.
+//
+// rtab (emit_rows.cuh) is the same information per DENSE ROW: {need | exclusive << 5 | demand << 6, gid} for every
+// replica row of the step, `exclusive` set only when the step AND the role are exclusive (the one case in
+// which the row depends on the group) — k_emit_rows walks rows, not steps.
 __global__ void __launch_bounds__(32 * PLAN_WARPS) k_plan_etab(const int* __restrict__ grp, const int* __restrict__ sgw, int ns,
-                                                               int row_base, int* __restrict__ etab) {
+                                                               int row_base, int* __restrict__ etab, int2* __restrict__ rtab) {
   __shared__ PlanScratch scratch[PLAN_WARPS];
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.x * PLAN_WARPS + (threadIdx.x >> 5);
@@ -102,7 +106,13 @@ __global__ void __launch_bounds__(32 * PLAN_WARPS) k_plan_etab(const int* __rest
       int need = 0;
       for (int j = 0; j < q; ++j)
         if (S->pair[ri * q + j] > 0) need += S->roles[4 * j + 1] - S->placed[j];
-      packed = emit_pack_role(S->count[lane], S->roles[4 * ri + 2], min(need, RBGTOPO_NEED_CAP), S->roles[4 * ri + 3]);
+      need = min(need, RBGTOPO_NEED_CAP);
+      packed = emit_pack_role(S->count[lane], S->roles[4 * ri + 2], need, S->roles[4 * ri + 3]);
+      int r0 = S->rec[8] - row_base + S->cum[RBGTOPO_MAX_GROUP_ROLES];  // first dense row of the step
+      for (int k = 0; k < lane; ++k) r0 += S->count[k];
+      const bool rexcl = (S->rec[1] & RBGTOPO_STEP_EXCLUSIVE) && (S->roles[4 * ri + 3] & RBGTOPO_ROLE_EXCLUSIVE);
+      const int2 rr = make_int2(emit_pack_row(S->roles[4 * ri + 2], need, rexcl), S->rec[0]);
+      for (int k = 0; k < S->count[lane]; ++k) rtab[r0 + k] = rr;
     }
     e[4 + lane] = packed;
   } else if (lane == 8) {

@@ -78,6 +78,9 @@ __device__ __forceinline__ float gtab_delta(const GroupTab& T, const float* pair
 #ifdef RBGTOPO_PHASE_CLOCKS  // one-off instrumentation (profiles/README.md): per-CTA phase timestamps
 __device__ long long g_phase_clk[2048 * 32];
 __device__ int g_dbg_skip;  // timing experiments only: bit 0 = no corrections, bit 1 = no patched-slot pass
+__device__ long long g_cta_ns[2048 * 4];  // globaltimer at CTA start / end, table entries, SM id
+__device__ __forceinline__ long long pg_gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ int pg_smid() { int v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
 #define PCLK(k) do { if (tid == 0 && blockIdx.x < 2048 && (k) < 32) g_phase_clk[blockIdx.x * 32 + (k)] = clock64(); } while (0)
 #define PCLKL(k) do { if ((k) >= 0 && (threadIdx.x & 31) == 0 && blockIdx.x < 2048 && (k) < 32) g_phase_clk[blockIdx.x * 32 + (k)] = clock64(); } while (0)
 #else
@@ -261,6 +264,9 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
   float* sPair = reinterpret_cast<float*>(sRole + MAXP);  // [MAXP][RBGTOPO_MAX_GROUP_ROLES]
 
   PCLK(30);
+#ifdef RBGTOPO_PHASE_CLOCKS
+  if (tid == 0 && blockIdx.x < 2048) { g_cta_ns[blockIdx.x * 4] = pg_gtime(); g_cta_ns[blockIdx.x * 4 + 3] = pg_smid(); }
+#endif
   int wave_i = 0;
   int step = blockIdx.x;
   StepHdr h = load_hdr(b, step);  // in flight while the table is cleared
@@ -517,6 +523,9 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
     h = load_hdr(b, step);
   }
   PCLK(31);
+#ifdef RBGTOPO_PHASE_CLOCKS
+  if (tid == 0 && blockIdx.x < 2048) { g_cta_ns[blockIdx.x * 4 + 1] = pg_gtime(); g_cta_ns[blockIdx.x * 4 + 2] = sCnt; }
+#endif
 }
 
 // Applies the correction records k_plan_group(record = 1) left: one warp per step, one lane per

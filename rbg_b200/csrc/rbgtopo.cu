@@ -26,6 +26,7 @@
 #include "plan.cuh"
 #include "score.cuh"
 #include "emit_tma.cuh"
+#include "emit_rows.cuh"
 #include "select.cuh"
 #include "select_fast.cuh"
 #include "plan_group.cuh"
@@ -179,6 +180,8 @@ struct Batch {
   DevBuf<int> cand;  // patched-node scratch of the selection kernels
   DevBuf<long long> emit_clk;  // RBGTOPO_EMIT_CLOCKS
   DevBuf<int> etab, emit_ctr;  // emit table of a plan (emit_tma.cuh) and the item queue of k_emit_tma
+  DevBuf<int2> rtab;           // row table of a plan (emit_rows.cuh)
+  bool any_excl = false;       // a group of the plan is exclusive: k_emit_rows<true>
   DevBuf<int> corr, corr_cnt;  // correction records of a plan: k_plan_group(record) -> k_plan_correct
   // device-resident multi-wave plan (rbgtopo_stage_groups / place_groups): steps are
   // wave-major; wave w = steps [wave_begin[w], wave_begin[w + 1])
@@ -264,6 +267,10 @@ const int kSelectSmemKB = getenv("RBGTOPO_SELECT_SMEM_KB") ? std::max(0, atoi(ge
 // selects k_emit_tma (TMA bulk stores from shared memory, 8 warps per SM): bit-identical, a quarter of the
 // footprint, but 58-64 us against 54 us on cfg3 (per-warp latency bound), see profiles/README.md round 2.
 const bool kEmitSt = getenv("RBGTOPO_EMIT_TMA") == nullptr;
+// Default among the streaming-store kernels: k_emit_rows (emit_rows.cuh, row-major walk of the plan's row
+// table, ~1/3 of the instructions per store); RBGTOPO_EMIT_STEPS=1 selects the step-major k_score_emit<false, ETAB>.
+const bool kEmitRows = getenv("RBGTOPO_EMIT_STEPS") == nullptr;
+const int kEmitRowsBlock = getenv("RBGTOPO_EMIT_ROWS") ? std::min(EMIT_ROWS_MAX, std::max(1, atoi(getenv("RBGTOPO_EMIT_ROWS")))) : 8;
 const int kEmitTmaBlock = getenv("RBGTOPO_EMIT_TMA_BLOCK")
                               ? std::min(EMIT_MAX_BSTEPS, std::max(1, atoi(getenv("RBGTOPO_EMIT_TMA_BLOCK")))) : 4;
 const int kEmitCtasPerSm = getenv("RBGTOPO_EMIT_CTAS") ? std::max(1, atoi(getenv("RBGTOPO_EMIT_CTAS"))) : 1;
@@ -757,14 +764,23 @@ BatchDev batch_dev(rbgtopo_ctx* c, Batch* b) {
 
 // Dense rows of a multi-wave plan from its emit table (b->etab): needs neither the expanded plan blob nor
 // b->m, so plan_stage can launch it while the host still computes the rest of the geometry.
-int launch_emit_plan(rbgtopo_ctx* c, Batch* b, cudaStream_t s, int ns) {
+int launch_emit_plan(rbgtopo_ctx* c, Batch* b, cudaStream_t s, int ns, long long n_rows) {
   if (ns <= 0) return RBGTOPO_OK;
   BatchDev d{};
   d.n_steps = ns;
   d.lc = c->lc;
   d.chunk = c->chunk;
   d.matrix = b->matrix.p;
-  if (kEmitSt) {
+  if (kEmitSt && kEmitRows) {
+    const long long segs = ((n_rows + kEmitRowsBlock - 1) / kEmitRowsBlock) * c->lc;
+    if (segs > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "rows x chunks exceed 2^31 segments");
+    if (segs > 0) {
+      if (b->any_excl)
+        k_emit_rows<true><<<(unsigned)segs, SCORE_THREADS, 0, s>>>(topo_dev(c), b->matrix.p, b->rtab.p, (int)n_rows, c->lc, c->chunk, kEmitRowsBlock);
+      else
+        k_emit_rows<false><<<(unsigned)segs, SCORE_THREADS, 0, s>>>(topo_dev(c), b->matrix.p, b->rtab.p, (int)n_rows, c->lc, c->chunk, kEmitRowsBlock);
+    }
+  } else if (kEmitSt) {
     d.bsteps = kEmitBlockSteps;
     const int items = (int)emit_items(ns, c->lc);
     k_score_emit<false, true><<<items / kEmitBlockSteps, SCORE_THREADS, 0, s>>>(topo_dev(c), d, items, b->etab.p);
@@ -786,7 +802,7 @@ int launch_emit_plan(rbgtopo_ctx* c, Batch* b, cudaStream_t s, int ns) {
 int launch_score(rbgtopo_ctx* c, Batch* b, cudaStream_t s) {
   const BatchMeta& m = b->m;
   if (m.n_steps == 0) return RBGTOPO_OK;
-  if (!b->wave_begin.empty()) return launch_emit_plan(c, b, s, m.n_steps);  // multi-wave plan: background rows from the emit table
+  if (!b->wave_begin.empty()) return launch_emit_plan(c, b, s, m.n_steps, m.total_r);  // multi-wave plan: background rows from the emit table
   const int items = (int)emit_items(m.n_steps, c->lc);
   const int grid = items / kEmitBlockSteps;  // one CTA per (block of steps, chunk of nodes)
   k_score_emit<true, false><<<grid, SCORE_THREADS, 0, s>>>(topo_dev(c), batch_dev(c, b), items, nullptr);  // step batch: rows + sparse corrections
@@ -982,6 +998,17 @@ int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int3
       long long t0min = LLONG_MAX, t1max = 0;
       for (int g = 0; g < n0; ++g) { tot += (double)(clk[g * 32 + 31] - clk[g * 32 + 30]); t0min = std::min(t0min, clk[g * 32 + 30]); t1max = std::max(t1max, clk[g * 32 + 31]); }
       fprintf(stderr, "[phase clocks] CTA lifetime avg %.0f cycles; first start -> last end %lld cycles\n", tot / n0, t1max - t0min);
+      std::vector<long long> ns((size_t)2048 * 4);
+      if (cudaMemcpyFromSymbol(ns.data(), g_cta_ns, ns.size() * 8) == cudaSuccess) {  // global-timer timeline of the launch
+        long long g0 = LLONG_MAX, g1 = 0;
+        for (int g = 0; g < n0; ++g) { g0 = std::min(g0, ns[g * 4]); g1 = std::max(g1, ns[g * 4 + 1]); }
+        std::vector<long long> st, life, cn;
+        for (int g = 0; g < n0; ++g) { st.push_back(ns[g * 4] - g0); life.push_back(ns[g * 4 + 1] - ns[g * 4]); cn.push_back(ns[g * 4 + 2]); }
+        std::sort(st.begin(), st.end()); std::sort(life.begin(), life.end()); std::sort(cn.begin(), cn.end());
+        auto q = [&](const std::vector<long long>& v, double f) { return v[std::min(v.size() - 1, (size_t)(f * v.size()))]; };
+        fprintf(stderr, "[cta timeline] first start -> last end %lld ns; start offset ns p50 %lld p90 %lld max %lld; lifetime ns min %lld p50 %lld p90 %lld max %lld; table entries min %lld p50 %lld p90 %lld max %lld\n",
+                g1 - g0, q(st, .5), q(st, .9), st.back(), life.front(), q(life, .5), q(life, .9), life.back(), cn.front(), q(cn, .5), q(cn, .9), cn.back());
+      }
       for (int w = 0; w < 3; ++w) {
         double d[6] = {0};
         for (int g = 0; g < n0; ++g) {
@@ -2263,6 +2290,9 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, bool 
     CK(b->gsrc.reserve(P.src_words));
     CK(b->matrix.reserve((size_t)std::max<long long>(1, P.racc) * c->slab_stride));
     CK(b->etab.reserve((size_t)P.ns * EMIT_TAB_WORDS + 4));
+    CK(b->rtab.reserve((size_t)std::max<long long>(1, P.racc)));
+    b->any_excl = false;
+    for (int gf : b->grp_flags) b->any_excl |= (gf & RBGTOPO_STEP_EXCLUSIVE) != 0;
     if (!b->emit_ctr.p) {
       CK(b->emit_ctr.reserve(4));
       CK(cudaMemset(b->emit_ctr.p, 0, b->emit_ctr.cap * 4));
@@ -2274,7 +2304,7 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, bool 
     if (dev_groups && dev_groups_ready) CK(cudaStreamWaitEvent(s, dev_groups_ready, 0));
     if (P.ns > 0) {
       k_plan_etab<<<(P.ns + PLAN_WARPS - 1) / PLAN_WARPS, 32 * PLAN_WARPS, 0, s>>>(dev_groups ? dev_groups : b->gsrc.p, b->gsrc.p + P.sgw_off, P.ns,
-                                                                                 (int)pacc0, b->etab.p);
+                                                                                 (int)pacc0, b->etab.p, b->rtab.p);
       CK(cudaMemsetAsync(b->emit_ctr.p, 0, 8, s));  // re-arm the TMA item queue (a failed launch may have left it mid-way)
       CK(cudaGetLastError());
       b->pend_launches += 1;
@@ -2284,7 +2314,7 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, bool 
         if (erc) return erc;
         CK(cudaStreamWaitEvent(s, c->base_ready, 0));  // base / free / node_owner of a pending refresh
         CK(cudaEventRecord(b->it_ev[3 * b->passes], s));
-        erc = launch_emit_plan(c, b, s, P.ns);
+        erc = launch_emit_plan(c, b, s, P.ns, P.racc);
         if (erc) return erc;
         CK(cudaEventRecord(b->it_ev[3 * b->passes + 1], s));
         CK(cudaGetLastError());
@@ -2372,6 +2402,25 @@ int verify_plan(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words) {
     }
     if (!ok) return fail(RBGTOPO_ECUDA, "verify_plan: emit table of step %d differs from the plan", st);
   }
+  // ... and so must the row table (emit_rows.cuh): every dense row of every step
+  std::vector<int2> rtab((size_t)m.total_r);
+  if (m.total_r) CK(cudaMemcpy(rtab.data(), b->rtab.p, rtab.size() * sizeof(int2), cudaMemcpyDeviceToHost));
+  std::vector<char> seen((size_t)m.total_r, 0);
+  for (int st = 0; st < m.n_steps; ++st) {
+    const int32_t* h = ref.h_in.p + RBGTOPO_HDR_WORDS + (size_t)st * RBGTOPO_STEP_WORDS;
+    int row = h[12];
+    for (int p2 = 0; p2 < h[3]; ++p2) {
+      const int32_t* r = ref.h_in.p + h[4] + 4 * p2;
+      const bool rexcl = (h[1] & RBGTOPO_STEP_EXCLUSIVE) && (r[3] & RBGTOPO_ROLE_EXCLUSIVE);
+      for (int k = 0; k < r[0]; ++k, ++row) {
+        if (row < 0 || row >= m.total_r || seen[row] || rtab[row].x != emit_pack_row(r[1], r[2], rexcl) || rtab[row].y != h[0])
+          return fail(RBGTOPO_ECUDA, "verify_plan: row table entry %d (step %d role %d) differs from the plan", row, st, p2);
+        seen[row] = 1;
+      }
+    }
+  }
+  for (int r = 0; r < m.total_r; ++r)
+    if (!seen[r]) return fail(RBGTOPO_ECUDA, "verify_plan: dense row %d belongs to no step", r);
   return RBGTOPO_OK;
 }
 
