@@ -329,6 +329,13 @@ int32_t rbgtopo_p2p_stats(rbgtopo_ctx* ctx, int64_t* peer_bytes_last_pass, int32
  * cudaStreamLegacy, (void*)0x1, to select the legacy default stream). */
 int32_t rbgtopo_set_stream(rbgtopo_ctx* ctx, void* cuda_stream);
 
+/* Per-kernel CUDA events inside a pass.  Off (default): a pass is timed as a whole and the selection
+ * kernel of a plan is launched as a programmatic dependent of the dense-matrix kernel (its CTAs become
+ * resident while the last dense-matrix CTAs drain).  On: an event is recorded between the two kernels —
+ * rbgtopo_last_timing / rbgtopo_last_pass_times then report each kernel, and the two kernels serialise
+ * (what bench.py's roofline leg measures).  Initial value: environment RBGTOPO_KERNEL_TIMING. */
+int32_t rbgtopo_set_kernel_timing(rbgtopo_ctx* ctx, int32_t on);
+
 /* ---- stats (SURVEY.md §5 metrics row) ----------------------------------- */
 int32_t rbgtopo_last_timing(rbgtopo_ctx* ctx, rbgtopo_timing* out);
 /* Per-pass CUDA-event durations (ms) of the dense-matrix kernel (k_score_emit) and of the

@@ -29,6 +29,9 @@ __global__ void __launch_bounds__(SCORE_THREADS, EMIT_ROWS_MIN_CTAS)
 k_emit_rows(TopoDev t, float* __restrict__ matrix, const int2* __restrict__ rtab, int n_rows, int lc, int T, int rb) {
   __shared__ int2 sRow[EMIT_ROWS_MAX];  // {need as fp32 bits, demand (bit 31: exclusive row)}
   __shared__ int sGid[EMIT_ROWS_MAX];
+  // every segment is scheduled before the dependents may start: k_plan_group's CTAs (launched as a programmatic
+  // dependent) fill the SMs as the last segments drain, and wait before they touch the matrix
+  pdl_launch_dependents();
   const int tid = threadIdx.x;
   const int seg = blockIdx.x;
   const int blk = seg / lc, ch = seg - blk * lc;

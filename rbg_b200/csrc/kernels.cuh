@@ -128,6 +128,12 @@ __device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
                : "memory");
 }
 
+// ---- programmatic dependent launch (griddepcontrol, sm_90+): the primary grid lets its dependents become
+// resident early; a dependent blocks in pdl_wait() until the primary grid has completed and its writes are visible.
+// Both are no-ops for a kernel launched without the programmatic attribute / with no dependents.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- mbarrier + TMA 1-D bulk copy (cp.async.bulk), sm_90+/sm_100a ----------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -427,6 +427,9 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
         }
       }
     } else if (warp != 0) {
+      // first touch of the matrix: as a programmatic dependent of the dense-matrix kernel, everything up to
+      // here (table, selection of wave 0) ran while that kernel was draining; warp 0 (greedy) never waits
+      if (wave_i == 0) pdl_wait();
       float* const mrow0 = b.matrix + (size_t)h.rep_off * stride - t.slab_lo;  // mrow0[node]
       for (int d = tid - 32; d < cnt; d += nthreads - 32) {
         const int slot = T.dSlot[d];

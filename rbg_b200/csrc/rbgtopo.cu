@@ -182,6 +182,7 @@ struct Batch {
   DevBuf<int> etab, emit_ctr;  // emit table of a plan (emit_tma.cuh) and the item queue of k_emit_tma
   DevBuf<int2> rtab;           // row table of a plan (emit_rows.cuh)
   bool any_excl = false;       // a group of the plan is exclusive: k_emit_rows<true>
+  std::vector<char> pass_mid;  // per pending pass: was the event between the two kernels recorded?
   DevBuf<int> corr, corr_cnt;  // correction records of a plan: k_plan_group(record) -> k_plan_correct
   // device-resident multi-wave plan (rbgtopo_stage_groups / place_groups): steps are
   // wave-major; wave w = steps [wave_begin[w], wave_begin[w + 1])
@@ -216,6 +217,11 @@ struct rbgtopo_ctx {
   std::vector<std::unique_ptr<Batch>> batches;
   cudaStream_t ext_stream = nullptr;
   bool use_ext_stream = false;
+  // Per-kernel CUDA events inside a pass (rbgtopo_set_kernel_timing).  Off (default): a pass records only its
+  // start / end, and k_plan_group is launched as a PROGRAMMATIC DEPENDENT of the dense-matrix kernel — its CTAs
+  // become resident while the last dense-matrix CTAs drain and wait (griddepcontrol.wait) before they touch the
+  // matrix.  On: an event sits between the two kernels, which serialises them (that is what it measures).
+  std::atomic<bool> kernel_timing{false};
   // snapshot refresh pipeline: update_nodes enqueues on topo_stream and returns; every batch
   // stream waits on topo_ready before it touches the snapshot
   cudaStream_t topo_stream = nullptr;
@@ -257,6 +263,8 @@ const bool kPerWavePlan = getenv("RBGTOPO_PER_WAVE_PLAN") != nullptr;  // one la
 // B200 in every configuration tried (profiles/README.md round 2: the write stream inflates the latency of
 // the selection's dependent loads 3-4x and the two kernels fight for registers), so it is opt-in.
 const bool kSerialPlan = getenv("RBGTOPO_CONCURRENT_PLAN") == nullptr;
+const bool kNoPdl = getenv("RBGTOPO_NO_PDL") != nullptr;                // plain stream order between the two plan kernels
+const bool kKernelTimingEnv = getenv("RBGTOPO_KERNEL_TIMING") != nullptr;  // initial value of rbgtopo_set_kernel_timing
 const bool kSelectHighPriority = getenv("RBGTOPO_SELECT_LOW_PRIO") == nullptr;
 const bool kSelectFirst = getenv("RBGTOPO_SELECT_FIRST") != nullptr;  // launch order of the two concurrent kernels
 // Residency cap of k_plan_group beside the dense-matrix kernel: its CTAs REQUEST this much dynamic shared
@@ -824,7 +832,7 @@ bool plan_group_cfg(const Batch* b, PlanGroupCfg* o) {
 }
 
 // world == 1: one fused kernel (select + exclusive domain + greedy), one CTA per step
-int launch_select_assign(rbgtopo_ctx* c, Batch* b, cudaStream_t s, const BatchDev& d, int* launches) {
+int launch_select_assign(rbgtopo_ctx* c, Batch* b, cudaStream_t s, const BatchDev& d, int* launches, bool pdl = false) {
   const int ns = b->m.n_steps;
   if (ns == 0) return RBGTOPO_OK;
   // shared-memory hash table for the patched nodes of a step: power of two >= 1.5 x the
@@ -854,7 +862,21 @@ int launch_select_assign(rbgtopo_ctx* c, Batch* b, cudaStream_t s, const BatchDe
   PlanGroupCfg pg;
   if (plan_group_cfg(b, &pg)) {
     if (pg.n0 > 0) {
-      k_plan_group<<<pg.n0, pg.nth, pg.smem, s>>>(topo_dev(c), d, b->m.max_q, pg.HT, pg.CAP, 0);
+      if (pdl) {  // programmatic dependent of the dense-matrix kernel just launched on s
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)pg.n0);
+        cfg.blockDim = dim3((unsigned)pg.nth);
+        cfg.dynamicSmemBytes = pg.smem;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, k_plan_group, topo_dev(c), d, (int)b->m.max_q, pg.HT, pg.CAP, 0));
+      } else {
+        k_plan_group<<<pg.n0, pg.nth, pg.smem, s>>>(topo_dev(c), d, b->m.max_q, pg.HT, pg.CAP, 0);
+      }
       ++*launches;
     }
     return RBGTOPO_OK;
@@ -910,6 +932,7 @@ int run_batch(rbgtopo_ctx* c, Batch* b, int iters) {
     }
     int rc;
     PlanGroupCfg pg;
+    bool has_mid = true;
     if (it == 0) {  // a pending snapshot refresh: the dense-matrix kernel needs base / free, selection also the order
       if (!early) CK(cudaStreamWaitEvent(s, c->base_ready, 0));
       if (!kSerialPlan || b->wave_begin.empty()) CK(cudaStreamWaitEvent(s, c->topo_ready, 0));
@@ -934,18 +957,26 @@ int run_batch(rbgtopo_ctx* c, Batch* b, int iters) {
         launches += 2;
       }
     } else {
+      // no event (and no wait) between the two kernels unless asked for: k_plan_group is then a programmatic
+      // dependent of the dense-matrix kernel
+      const bool mid = early || c->kernel_timing.load(std::memory_order_relaxed);
+      const bool pdl = !mid && !kNoPdl && !b->wave_begin.empty();
+      has_mid = mid;
+      if (it == 0 && !mid) CK(cudaStreamWaitEvent(s, c->topo_ready, 0));  // the background order of the refresh
       if (!early) {
         rc = launch_score(c, b, s);
         if (rc) return rc;
-        if (timed) CK(cudaEventRecord(b->it_ev[e0 + 1], s));
+        if (timed && mid) CK(cudaEventRecord(b->it_ev[e0 + 1], s));
       }
       ++launches;
-      if (it == 0) CK(cudaStreamWaitEvent(s, c->topo_ready, 0));  // the background order of the refresh
-      rc = launch_select_assign(c, b, s, d, &launches);
+      if (it == 0 && mid) CK(cudaStreamWaitEvent(s, c->topo_ready, 0));
+      rc = launch_select_assign(c, b, s, d, &launches, pdl);
       if (rc) return rc;
     }
     if (timed) {
       CK(cudaEventRecord(b->it_ev[e0 + 2], s));
+      if ((int)b->pass_mid.size() <= b->passes) b->pass_mid.resize(b->passes + 1, 1);
+      b->pass_mid[b->passes] = has_mid;
       b->passes += 1;
     }
     b->untimed_or_timed_passes += 1;
@@ -1057,16 +1088,22 @@ int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int3
   if (cudaEventElapsedTime(&x, b->ev[0], b->ev[1]) == cudaSuccess) tm.h2d_ms = x;
   float score = 0.f, sel = 0.f;
   std::vector<float> pass_score, pass_sel;
+  int mids = 0;
   for (int it = 0; it < b->passes; ++it) {
+    if (it < (int)b->pass_mid.size() && !b->pass_mid[it]) continue;  // pass without the event between its kernels
+    ++mids;
     if (cudaEventElapsedTime(&x, b->it_ev[3 * it], b->it_ev[3 * it + 1]) == cudaSuccess) { score += x; pass_score.push_back(x); }
     if (cudaEventElapsedTime(&x, b->it_ev[3 * it + 1], b->it_ev[3 * it + 2]) == cudaSuccess) { sel += x; pass_sel.push_back(x); }
   }
-  if (b->passes > 0) {
-    tm.score_ms = score / b->passes;
-    tm.select_ms = sel / b->passes;
+  if (mids > 0) {
+    tm.score_ms = score / mids;
+    tm.select_ms = sel / mids;
   }
   if (cudaEventElapsedTime(&x, b->ev[4], b->ev[5]) == cudaSuccess) tm.d2h_ms = x;
-  tm.total_ms = tm.h2d_ms + score + sel + tm.d2h_ms;
+  float whole = 0.f;  // passes timed as a whole (kernel timing off)
+  for (int it = 0; it < b->passes; ++it)
+    if (it < (int)b->pass_mid.size() && !b->pass_mid[it] && cudaEventElapsedTime(&x, b->it_ev[3 * it], b->it_ev[3 * it + 2]) == cudaSuccess) whole += x;
+  tm.total_ms = tm.h2d_ms + score + sel + whole + tm.d2h_ms;
   harvest_base_ms(c);
   tm.base_ms = c->topo.base_ms;
   tm.scores = m.scores;
@@ -1076,6 +1113,7 @@ int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int3
   (void)cudaGetLastError();  // events recorded under stream capture have no timestamps: not an error here
   const int total_passes = b->untimed_or_timed_passes;
   b->passes = 0;
+  b->pass_mid.clear();
   b->pend_launches = 0;
   b->untimed_or_timed_passes = 0;
   std::lock_guard<std::mutex> g(c->stat_mu);
@@ -1172,6 +1210,7 @@ int32_t rbgtopo_create(const rbgtopo_config* cfg, rbgtopo_ctx** out) {
   c->cfg = *cfg;
   c->cfg.emit_matrix = 1;  // the dense matrix is always materialised (it is the product; rbgtopo_read_scores)
   c->sm_count = prop.multiProcessorCount;
+  c->kernel_timing.store(kKernelTimingEnv);
   CK(cudaStreamCreateWithFlags(&c->topo_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&c->topo_ready, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->base_ready, cudaEventDisableTiming));
@@ -3079,6 +3118,12 @@ int32_t rbgtopo_p2p_stats(rbgtopo_ctx* c, int64_t* peer_bytes_last_pass, int32_t
       *timed_out = v;
     }
   }
+  return RBGTOPO_OK;
+}
+
+int32_t rbgtopo_set_kernel_timing(rbgtopo_ctx* c, int32_t on) {
+  if (!c) return RBGTOPO_EINVAL;
+  c->kernel_timing.store(on != 0, std::memory_order_relaxed);
   return RBGTOPO_OK;
 }
 

@@ -247,6 +247,11 @@ class TopoPlacer:
         else:
             self._check(self.lib.rbgtopo_set_stream(self._h, C.c_void_p(cuda_stream if cuda_stream else 1)))
 
+    def set_kernel_timing(self, on: bool) -> None:
+        """Per-kernel CUDA events inside a pass (serialises the two plan kernels); off = a pass is timed as a
+        whole and the selection kernel is a programmatic dependent of the dense-matrix kernel."""
+        self._check(self.lib.rbgtopo_set_kernel_timing(self._h, 1 if on else 0))
+
     # -- stats
     def last_timing(self) -> dict:
         t = _lib.Timing()
