@@ -333,7 +333,10 @@ int32_t rbgtopo_set_stream(rbgtopo_ctx* ctx, void* cuda_stream);
  * kernel of a plan is launched as a programmatic dependent of the dense-matrix kernel (its CTAs become
  * resident while the last dense-matrix CTAs drain).  On: an event is recorded between the two kernels —
  * rbgtopo_last_timing / rbgtopo_last_pass_times then report each kernel, and the two kernels serialise
- * (what bench.py's roofline leg measures).  Initial value: environment RBGTOPO_KERNEL_TIMING. */
+ * (what bench.py's roofline leg measures).  With timing off the passes of the resident entry points
+ * (rbgtopo_run_staged) record no events at all (an event record between two kernels costs ~3 us of stream
+ * time): rbgtopo_last_timing then reports the staging and the D2H only.  Initial value: environment
+ * RBGTOPO_KERNEL_TIMING. */
 int32_t rbgtopo_set_kernel_timing(rbgtopo_ctx* ctx, int32_t on);
 
 /* ---- stats (SURVEY.md §5 metrics row) ----------------------------------- */

@@ -278,7 +278,7 @@ const bool kEmitSt = getenv("RBGTOPO_EMIT_TMA") == nullptr;
 // Default among the streaming-store kernels: k_emit_rows (emit_rows.cuh, row-major walk of the plan's row
 // table, ~1/3 of the instructions per store); RBGTOPO_EMIT_STEPS=1 selects the step-major k_score_emit<false, ETAB>.
 const bool kEmitRows = getenv("RBGTOPO_EMIT_STEPS") == nullptr;
-const int kEmitRowsBlock = getenv("RBGTOPO_EMIT_ROWS") ? std::min(EMIT_ROWS_MAX, std::max(1, atoi(getenv("RBGTOPO_EMIT_ROWS")))) : 8;
+const int kEmitRowsBlock = getenv("RBGTOPO_EMIT_ROWS") ? std::min(EMIT_ROWS_MAX, std::max(1, atoi(getenv("RBGTOPO_EMIT_ROWS")))) : 6;
 const int kEmitTmaBlock = getenv("RBGTOPO_EMIT_TMA_BLOCK")
                               ? std::min(EMIT_MAX_BSTEPS, std::max(1, atoi(getenv("RBGTOPO_EMIT_TMA_BLOCK")))) : 4;
 const int kEmitCtasPerSm = getenv("RBGTOPO_EMIT_CTAS") ? std::max(1, atoi(getenv("RBGTOPO_EMIT_CTAS"))) : 1;
@@ -923,7 +923,9 @@ int run_batch(rbgtopo_ctx* c, Batch* b, int iters) {
   for (int it = 0; it < iters; ++it) {
     const bool early = b->early_emit;  // the staging enqueued this pass's dense-matrix kernel and its events already
     b->early_emit = false;
-    const bool timed = early || b->passes < kMaxTimedPasses;
+    // per-pass events only with kernel timing on (or for the pass the staging started): an event record between two
+    // kernels costs ~3 us of stream time on this stack, as much as it measures
+    const bool timed = early || (b->passes < kMaxTimedPasses && c->kernel_timing.load(std::memory_order_relaxed));
     const int e0 = 3 * b->passes;
     if (timed && !early) {
       int rc = ensure_pass_events(b, b->passes + 1);
