@@ -630,6 +630,11 @@ def roofline_of(r, peak, peak_src):
             "peak_source": peak_src, "algo_bytes_per_step": r["algo_bytes"], "kernel_ms_per_step": r["score_ms"],
             "kernel_launch_us": r.get("emit_launch_us"), "select_launch_us": r.get("select_launch_us"),
             "frac_of_nominal_8000": achieved / 8000.0,
+            "frac_note": "the peak is the measured COPY bandwidth (reads + writes); a write-only stream can exceed it, and at the "
+                         "end of a launch part of the stream is still dirty in the 126 MB L2 (see traffic): "
+                         "dram_frac_in_kernel = traffic / kernel time / peak is the HBM rate inside the launch itself",
+            "dram_frac_in_kernel": (traffic / 1e9) / (r["score_ms"] * 1e-3) / peak if (traffic and r.get("score_ms") and peak
+                                                                                     and r.get("config_name") == "cfg3") else None,
             "whole_step_frac": step_frac,
             "whole_step_note": "the same algorithmic bytes over ms_per_step (dense-matrix kernel + selection/greedy kernel)"}
 
