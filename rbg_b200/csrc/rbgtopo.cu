@@ -183,6 +183,7 @@ struct Batch {
   DevBuf<int2> rtab;           // row table of a plan (emit_rows.cuh)
   bool any_excl = false;       // a group of the plan is exclusive: k_emit_rows<true>
   std::vector<char> pass_mid;  // per pending pass: was the event between the two kernels recorded?
+  bool tev = false;            // timing events (ev[0], ev[1], ev[4], ev[5], the early emit's) recorded since the staging
   DevBuf<int> corr, corr_cnt;  // correction records of a plan: k_plan_group(record) -> k_plan_correct
   // device-resident multi-wave plan (rbgtopo_stage_groups / place_groups): steps are
   // wave-major; wave w = steps [wave_begin[w], wave_begin[w + 1])
@@ -265,6 +266,7 @@ const bool kPerWavePlan = getenv("RBGTOPO_PER_WAVE_PLAN") != nullptr;  // one la
 const bool kSerialPlan = getenv("RBGTOPO_CONCURRENT_PLAN") == nullptr;
 const bool kNoPdl = getenv("RBGTOPO_NO_PDL") != nullptr;                // plain stream order between the two plan kernels
 const bool kKernelTimingEnv = getenv("RBGTOPO_KERNEL_TIMING") != nullptr;  // initial value of rbgtopo_set_kernel_timing
+const bool kProfileHost = getenv("RBGTOPO_PROFILE_HOST") != nullptr;
 const bool kSelectHighPriority = getenv("RBGTOPO_SELECT_LOW_PRIO") == nullptr;
 const bool kSelectFirst = getenv("RBGTOPO_SELECT_FIRST") != nullptr;  // launch order of the two concurrent kernels
 // Residency cap of k_plan_group beside the dense-matrix kernel: its CTAs REQUEST this much dynamic shared
@@ -307,6 +309,10 @@ const bool kRefreshGraph = getenv("RBGTOPO_NO_REFRESH_GRAPH") == nullptr;
 const bool kSmallSort = getenv("RBGTOPO_SMALL_SORT") != nullptr;
 const bool kVerifyPlan = getenv("RBGTOPO_VERIFY_PLAN") != nullptr;  // self-check: device-expanded plan == host-built plan
 const int kHostThreads = getenv("RBGTOPO_HOST_THREADS") ? std::max(1, atoi(getenv("RBGTOPO_HOST_THREADS"))) : 4;
+
+// Events that only measure (staging, early emit, D2H, refresh) are recorded with kernel timing on or under
+// RBGTOPO_PROFILE_HOST: each costs stream time, and the host-buffer entry points are latency-bound.
+inline bool timing_events(const rbgtopo_ctx* c) { return kProfileHost || c->kernel_timing.load(std::memory_order_relaxed); }
 
 void compute_slab(rbgtopo_ctx* c, int n) {
   const int W = c->cfg.world, r = c->cfg.rank;
@@ -508,7 +514,8 @@ int run_base(rbgtopo_ctx* c, cudaStream_t s, bool sync) {
     }
     T.refresh_ready = true;
   }
-  CK(cudaEventRecord(c->ev_base_a, s));
+  const bool tev = timing_events(c);
+  if (tev) CK(cudaEventRecord(c->ev_base_a, s));
   if (T.refresh_exec) {
     CK(cudaGraphLaunch(T.refresh_exec, s));
     CK(cudaEventRecord(c->base_ready, s));
@@ -517,10 +524,10 @@ int run_base(rbgtopo_ctx* c, cudaStream_t s, bool sync) {
     int rc = enqueue_refresh(c, s, 3);
     if (rc) return rc;
   }
-  CK(cudaEventRecord(c->ev_base_b, s));
+  if (tev) CK(cudaEventRecord(c->ev_base_b, s));
   CK(cudaEventRecord(c->topo_ready, s));
   T.pos_valid = c->cfg.world == 1;
-  c->base_timing_pending = true;
+  c->base_timing_pending = tev;
   CK(cudaGetLastError());
   if (sync) {
     CK(cudaStreamSynchronize(s));
@@ -728,11 +735,12 @@ int stage_into(rbgtopo_ctx* c, Batch* b, const int32_t* blob, int64_t words) {
   if (rc) return rc;
   b->m.h2d_words = (long long)in_words;
   b->epoch = c->topo_epoch;
-  CK(cudaEventRecord(b->ev[0], s));  // staging touches the batch's own buffers only; run_batch waits for a pending refresh
+  b->tev = timing_events(c);
+  if (b->tev) CK(cudaEventRecord(b->ev[0], s));  // staging touches the batch's own buffers only; run_batch waits for a pending refresh
   if (!in_place) memcpy(b->h_in.p, blob, (size_t)words * 4);
   memcpy(b->h_in.p + words, m.poff.data(), ((size_t)m.n_steps + 1) * 4);
   CK(cudaMemcpyAsync(b->blob.p, b->h_in.p, in_words * 4, cudaMemcpyHostToDevice, s));
-  CK(cudaEventRecord(b->ev[1], s));
+  if (b->tev) CK(cudaEventRecord(b->ev[1], s));
   b->staged = true;
   b->ran = false;
   return RBGTOPO_OK;
@@ -925,7 +933,7 @@ int run_batch(rbgtopo_ctx* c, Batch* b, int iters) {
     b->early_emit = false;
     // per-pass events only with kernel timing on (or for the pass the staging started): an event record between two
     // kernels costs ~3 us of stream time on this stack, as much as it measures
-    const bool timed = early || (b->passes < kMaxTimedPasses && c->kernel_timing.load(std::memory_order_relaxed));
+    const bool timed = early ? b->tev : (b->passes < kMaxTimedPasses && c->kernel_timing.load(std::memory_order_relaxed));
     const int e0 = 3 * b->passes;
     if (timed && !early) {
       int rc = ensure_pass_events(b, b->passes + 1);
@@ -998,9 +1006,9 @@ int enqueue_d2h(rbgtopo_ctx* c, Batch* b) {
   cudaStream_t s = stream_of(c, b);
   const BatchMeta& m = b->m;
   const size_t out_n = (size_t)m.total_r + 2 * (size_t)m.n_steps;
-  CK(cudaEventRecord(b->ev[4], s));
+  if (b->tev) CK(cudaEventRecord(b->ev[4], s));
   if (out_n) CK(cudaMemcpyAsync(b->h_out.p, b->out.p, out_n * 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaEventRecord(b->ev[5], s));
+  if (b->tev) CK(cudaEventRecord(b->ev[5], s));
   b->d2h_enqueued = true;
   return RBGTOPO_OK;
 }
@@ -1075,7 +1083,7 @@ int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int3
     }
   }
   static const bool prof_dev = getenv("RBGTOPO_PROFILE_HOST") != nullptr;
-  if (prof_dev && b->passes == 1 && !b->wave_begin.empty()) {  // device timeline of a place_groups call, us after the staging began
+  if (prof_dev && b->tev && b->passes == 1 && !b->wave_begin.empty()) {  // device timeline of a place_groups call, us after the staging began
     float t[6] = {0, 0, 0, 0, 0, 0};
     cudaEvent_t evs[6] = {b->it_ev[0], b->it_ev[1], b->ev[1], b->it_ev[2], b->ev[4], b->ev[5]};
     for (int i = 0; i < 6; ++i)
@@ -1087,7 +1095,7 @@ int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int3
   }
   rbgtopo_timing tm{};
   float x = 0.f;
-  if (cudaEventElapsedTime(&x, b->ev[0], b->ev[1]) == cudaSuccess) tm.h2d_ms = x;
+  if (b->tev && cudaEventElapsedTime(&x, b->ev[0], b->ev[1]) == cudaSuccess) tm.h2d_ms = x;
   float score = 0.f, sel = 0.f;
   std::vector<float> pass_score, pass_sel;
   int mids = 0;
@@ -1101,7 +1109,7 @@ int fetch_batch(rbgtopo_ctx* c, Batch* b, int32_t* assign, int32_t* status, int3
     tm.score_ms = score / mids;
     tm.select_ms = sel / mids;
   }
-  if (cudaEventElapsedTime(&x, b->ev[4], b->ev[5]) == cudaSuccess) tm.d2h_ms = x;
+  if (b->tev && cudaEventElapsedTime(&x, b->ev[4], b->ev[5]) == cudaSuccess) tm.d2h_ms = x;
   float whole = 0.f;  // passes timed as a whole (kernel timing off)
   for (int it = 0; it < b->passes; ++it)
     if (it < (int)b->pass_mid.size() && !b->pass_mid[it] && cudaEventElapsedTime(&x, b->it_ev[3 * it], b->it_ev[3 * it + 2]) == cudaSuccess) whole += x;
@@ -1468,7 +1476,8 @@ int32_t rbgtopo_update_nodes_delta(rbgtopo_ctx* c, int32_t n_changed, const int3
     CK(cudaGetLastError());
     return run_base(c, s, false);
   }
-  CK(cudaEventRecord(c->ev_base_a, s));
+  const bool tev = timing_events(c);
+  if (tev) CK(cudaEventRecord(c->ev_base_a, s));
   CK(cudaMemsetAsync(T.aff.p, 0, 4, s));
   const TopoDev td = topo_dev(c);
   k_delta_apply<<<(unsigned)((m * 32 + 255) / 256), 256, 0, s>>>(td, T.free_.p, T.fmin.p, T.base.p, T.d_changed.p, (int)m, T.flag.p, T.aff.p);
@@ -1477,9 +1486,9 @@ int32_t rbgtopo_update_nodes_delta(rbgtopo_ctx* c, int32_t n_changed, const int3
   const int n = c->slab_hi - c->slab_lo;  // == T.n (world == 1)
   k_delta_merge<<<(n + 255) / 256, 256, 0, s>>>(T.order.p, n, T.aff.p, T.new_keys.p, T.old_pos.p, T.order_alt.p, T.pos.p);
   CK(cudaMemcpyAsync(T.order.p, T.order_alt.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));  // the refresh graph holds T.order.p
-  CK(cudaEventRecord(c->ev_base_b, s));
+  if (tev) CK(cudaEventRecord(c->ev_base_b, s));
   CK(cudaEventRecord(c->topo_ready, s));
-  c->base_timing_pending = true;
+  c->base_timing_pending = tev;
   CK(cudaGetLastError());
   std::lock_guard<std::mutex> g(c->stat_mu);
   c->launches += 3;
@@ -2339,7 +2348,8 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, bool 
       CK(cudaMemset(b->emit_ctr.p, 0, b->emit_ctr.cap * 4));
     }
     b->epoch = c->topo_epoch;
-    CK(cudaEventRecord(b->ev[0], s));  // staging touches the batch's own buffers only: no wait for a pending snapshot refresh
+    b->tev = timing_events(c);
+    if (b->tev) CK(cudaEventRecord(b->ev[0], s));  // staging touches the batch's own buffers only: no wait for a pending snapshot refresh
     const size_t lo = dev_groups ? P.sgw_off : 0, hi = P.aux_off;  // blob (unless an earlier batch uploaded it) + (group, wave) table
     if (hi > lo) CK(cudaMemcpyAsync(b->gsrc.p + lo, b->h_in.p + lo, (hi - lo) * 4, cudaMemcpyHostToDevice, s));
     if (dev_groups && dev_groups_ready) CK(cudaStreamWaitEvent(s, dev_groups_ready, 0));
@@ -2351,13 +2361,13 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, bool 
       b->pend_launches += 1;
       CK(cudaEventRecord(b->ev[2], s));  // GROUPS blob + emit table are on the device: the second half of the staging may follow on stream2
       if (early_emit) {  // pass 0 of run_batch starts here
-        int erc = ensure_pass_events(b, b->passes + 1);
+        int erc = b->tev ? ensure_pass_events(b, b->passes + 1) : RBGTOPO_OK;
         if (erc) return erc;
         CK(cudaStreamWaitEvent(s, c->base_ready, 0));  // base / free / node_owner of a pending refresh
-        CK(cudaEventRecord(b->it_ev[3 * b->passes], s));
+        if (b->tev) CK(cudaEventRecord(b->it_ev[3 * b->passes], s));
         erc = launch_emit_plan(c, b, s, P.ns, P.racc);
         if (erc) return erc;
-        CK(cudaEventRecord(b->it_ev[3 * b->passes + 1], s));
+        if (b->tev) CK(cudaEventRecord(b->it_ev[3 * b->passes + 1], s));
         CK(cudaGetLastError());
         b->early_emit = true;
       }
@@ -2395,7 +2405,7 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, bool 
     CK(cudaEventRecord(b->ev[3], s_exp));
     CK(cudaStreamWaitEvent(s, b->ev[3], 0));
   }
-  CK(cudaEventRecord(b->ev[1], s));  // h2d_ms = uploads + emit table + expansion (+ the early emit when there is one)
+  if (b->tev) CK(cudaEventRecord(b->ev[1], s));  // h2d_ms = uploads + emit table + expansion (+ the early emit when there is one)
   b->pend_launches += 1;
   b->staged = true;
   b->ran = false;
