@@ -195,7 +195,9 @@ def test_plan_dense_matrix_and_lists_match_oracle_per_wave():
 
 
 @pytest.mark.parametrize("var", ["RBGTOPO_VERIFY_PLAN", "RBGTOPO_PER_WAVE_PLAN", "RBGTOPO_SPLIT_MIN_GROUPS",
-                                 "RBGTOPO_CONCURRENT_PLAN", "RBGTOPO_EMIT_TMA", "RBGTOPO_CONCURRENT_PLAN+RBGTOPO_EMIT_TMA"])
+                                 "RBGTOPO_CONCURRENT_PLAN", "RBGTOPO_EMIT_TMA", "RBGTOPO_CONCURRENT_PLAN+RBGTOPO_EMIT_TMA",
+                                 "RBGTOPO_EMIT_STEPS+RBGTOPO_VERIFY_PLAN", "RBGTOPO_KERNEL_TIMING", "RBGTOPO_NO_PDL",
+                                 "RBGTOPO_EMIT_ROWS"])
 def test_plan_variants_in_a_subprocess(var):
     """The library reads its switches when it loads, hence the subprocess.
     RBGTOPO_VERIFY_PLAN: every place_groups / stage_groups call compares the plan k_expand_plan
@@ -204,7 +206,10 @@ def test_plan_variants_in_a_subprocess(var):
     through the plan blob (what groups too large for k_plan_group's shared memory take).
     RBGTOPO_SPLIT_MIN_GROUPS=1 (-> 2): place_groups pipelines every fleet as two halves (opt-in).
     RBGTOPO_CONCURRENT_PLAN: k_plan_group in record mode on a second stream + k_plan_correct (opt-in).
-    RBGTOPO_EMIT_TMA: the dense rows of plans through k_emit_tma (TMA bulk stores) instead of k_score_emit."""
+    RBGTOPO_EMIT_TMA: the dense rows of plans through k_emit_tma (TMA bulk stores) instead of k_emit_rows.
+    RBGTOPO_EMIT_STEPS: the step-major dense-matrix kernel (k_score_emit<false, ETAB>) instead of k_emit_rows.
+    RBGTOPO_KERNEL_TIMING / RBGTOPO_NO_PDL: an event between the two plan kernels / plain stream order instead of the
+    programmatic dependent launch.  RBGTOPO_EMIT_ROWS=1: one row per segment of k_emit_rows (the smallest segment)."""
     import os
     import subprocess
     import sys
