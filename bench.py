@@ -333,6 +333,12 @@ class Dist:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(self, x: float) -> float:
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
     def min_over_ranks(self, x: float) -> float:
         t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
         if self.world > 1:
@@ -345,7 +351,7 @@ def make_device_step(D, eng, handles, n_waves, mode):
     path).  p2p: the in-library all-gather over NVLink peer memory (rbgtopo_run_staged_p2p).
     allgather: per-wave NCCL all-gather driven from here (north_star's literal scheme)."""
     torch, dist = D.torch, D.dist
-    if mode == "replicated" or D.world == 1:
+    if mode in ("replicated", "groups") or D.world == 1:
         def step():
             for h in handles:
                 eng.run_staged(h, 1)
@@ -390,14 +396,22 @@ def run_config(D, args, cfg_name, with_clocks):
     rank, world, local = D.rank, D.world, D.local
     groups = args.groups if cfg_name == "cfg3" else cfg["groups"]
     nodes = args.nodes if cfg_name == "cfg3" else cfg["nodes"]
-    n_nodes = nodes * world if cfg["scaling"] == "weak" else nodes
-    topo = synth.make_topology(n_nodes, seed=0, tiers=4, samples_per_tier=5)
-    specs = fleet_spec(cfg["shape"], groups, n_nodes)
-    rbgs = to_plugin(specs)
     mode = args.shard_mode if world > 1 else "replicated"
+    by_groups = mode == "groups"   # SURVEY.md §8(e) "alternative": the PROBLEM axis is sharded, every rank sees every node
+    n_nodes = nodes * world if (cfg["scaling"] == "weak" and not by_groups) else nodes
+    topo = synth.make_topology(n_nodes, seed=0, tiers=4, samples_per_tier=5)
+    if by_groups:
+        # weak: `groups` RBGs per GPU on the same cluster (the fleet grows with N); strong: the fleet is split
+        all_specs = fleet_spec(cfg["shape"], groups * world if cfg["scaling"] == "weak" else groups, n_nodes)
+        per = (len(all_specs) + world - 1) // world
+        specs = all_specs[rank * per:(rank + 1) * per]
+        groups = len(specs)
+    else:
+        specs = fleet_spec(cfg["shape"], groups, n_nodes)
+    rbgs = to_plugin(specs)
     churn = cfg_name == "cfg5"
 
-    eng = TopoPlacer(device=local, rank=rank, world=world)
+    eng = TopoPlacer(device=local, rank=0, world=1) if by_groups else TopoPlacer(device=local, rank=rank, world=world)
     eng.set_topology(topo.row_ptr, topo.col_idx, topo.edge_w, topo.free, topo.domain, topo.domain_owner)
     gblob, _ = B200TopoPodGroupManager(eng).groups_blob(rbgs)   # host-side marshalling, identical on every rank
     if mode == "p2p":
@@ -409,6 +423,8 @@ def run_config(D, args, cfg_name, with_clocks):
     lo, hi = eng.slab()
     scores_rank = total_r * (hi - lo)
     scores_all = total_r * n_nodes
+    if by_groups:   # every rank scores its own groups against all nodes: the job's scores are the sum over ranks
+        scores_all = int(round(D.sum_over_ranks(float(total_r * n_nodes))))
     device_step = make_device_step(D, eng, handles, n_waves, mode)
 
     # ---- parity first: a deterministic sample of the fleet, all waves, on every rank
@@ -490,7 +506,7 @@ def run_config(D, args, cfg_name, with_clocks):
         eng.set_kernel_timing(False)
         out["ms_per_step_kernel_timing"] = kt_ms / steps
         dev_ms = D.max_over_ranks(dev_ms)
-        out.update(value=scores_rank * world * steps / (dev_ms * 1e-3) if cfg["scaling"] == "weak"
+        out.update(value=scores_rank * world * steps / (dev_ms * 1e-3) if (cfg["scaling"] == "weak" and not by_groups)
                    else scores_all * steps / (dev_ms * 1e-3),
                    ms_per_step=dev_ms / steps, launches=int(launches), clocks=clocks, score_ms=score_ms,
                    algo_bytes=algo_bytes,
@@ -513,7 +529,7 @@ def run_config(D, args, cfg_name, with_clocks):
             frees.append(np.where(gone, 0, free0).astype(np.int32))
     else:
         frees = [free0]
-    if mode == "replicated" or world == 1:
+    if mode in ("replicated", "groups") or world == 1:
         def e2e_step(k):
             eng.update_nodes(frees[k % len(frees)])
             return eng.place_groups(gblob)
@@ -596,7 +612,7 @@ def run_config(D, args, cfg_name, with_clocks):
     if not churn:
         assert np.array_equal(fetched[0], res[0]), "e2e placement differs from the staged path"
     n_plan_words = eng.last_timing()["h2d_words"]          # GROUPS blob + per-step geometry words uploaded
-    out.update(e2e_value=(scores_rank * world if cfg["scaling"] == "weak" else scores_all) * steps / (e2e_ms * 1e-3),
+    out.update(e2e_value=(scores_rank * world if (cfg["scaling"] == "weak" and not by_groups) else scores_all) * steps / (e2e_ms * 1e-3),
                e2e_ms=e2e_ms / steps, h2d=int(free0.nbytes + 4 * n_plan_words), d2h=int(4 * (total_r + 2 * 3 * groups)),
                n_nodes=n_nodes, groups=groups, total_r=total_r, edges=int(topo.e), slab=(lo, hi), mode=mode,
                topo=topo, specs=specs, what=cfg["what"], scaling=cfg["scaling"])
@@ -700,14 +716,17 @@ def run_ours(args):
                 "workload": f"{args.config}: {main['groups']} {main['what']} x "
                             f"{n_nodes}-node NVLink/PCIe/RDMA/VPC topology"
                             + ("" if world == 1 else
+                               (f"; PROBLEM axis sharded over {world} GPUs: {main['groups']} RBGs per rank, every rank scores "
+                                "its groups against all nodes, no collective (SURVEY.md §8(e) alternative)") if main["mode"] == "groups" else
                                f", node axis sharded over {world} GPUs ({(hi - lo)} nodes on rank 0): "
                                + ("dense matrix column-sharded, selection replicated on every rank over all nodes "
                                   "(identical placements, no per-step collective)" if replicated else
                                   ("per-shard top-K lists all-gathered per wave by the library's own kernels over NVLink "
                                    "peer memory (no NCCL call on the step path)" if main["mode"] == "p2p" else
                                    "one NCCL all-gather of per-shard top-K lists per wave"))),
-                "parallelism": "single GPU" if world == 1 else f"node-axis x{world}, " + main["mode"],
-                "launch": "eager: k_emit_rows, then k_plan_group as its programmatic dependent (griddepcontrol), per step" if replicated else main["mode"],
+                "parallelism": "single GPU" if world == 1 else
+                               (f"problem-axis x{world}" if main["mode"] == "groups" else f"node-axis x{world}, " + main["mode"]),
+                "launch": "eager: k_emit_rows, then k_plan_group as its programmatic dependent (griddepcontrol), per step" if (replicated or main["mode"] == "groups") else main["mode"],
                 "groups": main["groups"], "nodes": n_nodes, "edges": main["edges"], "replicas_per_step": main["total_r"],
                 "emit_matrix": True,
                 "l2": "dense-matrix write stream per step "
@@ -796,7 +815,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--ref-groups", type=int, default=1024, help="groups per step of the reference arm (the whole fleet: same config as ours)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--shard-mode", default="replicated", choices=["replicated", "allgather", "p2p"],
+    ap.add_argument("--shard-mode", default="replicated", choices=["replicated", "allgather", "p2p", "groups"],
                     help="N > 1: 'replicated' = dense matrix column-sharded, selection replicated on every rank, "
                          "no per-step collective; 'p2p' = per-shard top-K lists exchanged per wave by the library's "
                          "own kernels over NVLink peer memory; 'allgather' = the same exchange as NCCL all-gathers "
