@@ -19,9 +19,13 @@ launch-bound, SURVEY.md §0.6 — batching is what makes the roofline meaningful
   e2e   : the same metric through the C-ABI plugin call with HOST buffers:
           rbgtopo_update_nodes(free) + rbgtopo_place_groups(groups blob) per
           step — H2D of the inputs and D2H of the results inside the timed region
-  roofline : k_score_emit (dominant kernel): algorithmic bytes / CUDA-event
-          duration of its launches inside the timed region vs the measured HBM
-          peak (MEASURED_PEAKS.json); per-launch min / median / max beside it
+  value : K steps with nothing recorded inside a step (k_plan_group is a programmatic
+          dependent of k_emit_rows); torch events + barrier / synchronize around them
+  roofline : k_emit_rows (dominant kernel): algorithmic bytes / CUDA-event
+          duration of its launches vs the measured HBM peak (MEASURED_PEAKS.json),
+          from a second leg of the same K steps with per-kernel events recorded inside
+          the library on the launching stream (rbgtopo_set_kernel_timing); per-launch
+          min / median / max beside it, that leg's step time as ms_per_step_kernel_timing
   cpu_baseline : a CPU port of OUR spec (kind "port": sgl-project/rbg has no such
           path and no Go toolchain exists here) on a bounded sample — the variant
           with the GPU path's algebra (oracle/placer_fast.c), the literal oracle

@@ -250,7 +250,7 @@ int32_t rbgtopo_stage(rbgtopo_ctx* ctx, const int32_t* blob, int64_t blob_words,
 /* run_staged only ENQUEUES `iters` passes on the call's stream (asynchronous);
  * rbgtopo_fetch synchronises, copies the results of the last pass (any output
  * pointer may be NULL) and harvests the timing of every pass since the
- * previous fetch (rbgtopo_last_timing: score_ms = average k_score_emit
+ * previous fetch (rbgtopo_last_timing: score_ms = average dense-matrix kernel (k_emit_rows for plans, k_score_emit for step batches)
  * duration from CUDA events recorded around each launch).  Valid for any world
  * (replicated selection); the shard calls below are the all-gather alternative. */
 int32_t rbgtopo_run_staged(rbgtopo_ctx* ctx, int32_t handle, int32_t iters);
@@ -284,7 +284,7 @@ int32_t rbgtopo_read_topk(rbgtopo_ctx* ctx, int32_t handle, int32_t rolerow,
  * (rbgtopo_stage_groups, also valid with world > 1) has W = rbgtopo_shard_waves
  * waves that must be run in order 0..W-1, each as score -> all-gather -> merge
  * [-> all-gather -> ] assign.  Wave 0's score call also enqueues the single
- * k_score_emit launch for the rows of every wave on this rank's slab; the
+ * dense-matrix launch (k_emit_rows) for the rows of every wave on this rank's slab; the
  * placements are chained into later waves on every rank identically. */
 int32_t rbgtopo_shard_waves(rbgtopo_ctx* ctx, int32_t handle, int32_t* n_waves);
 int32_t rbgtopo_shard_wave_score(rbgtopo_ctx* ctx, int32_t handle, int32_t wave,
@@ -341,7 +341,7 @@ int32_t rbgtopo_set_kernel_timing(rbgtopo_ctx* ctx, int32_t on);
 
 /* ---- stats (SURVEY.md §5 metrics row) ----------------------------------- */
 int32_t rbgtopo_last_timing(rbgtopo_ctx* ctx, rbgtopo_timing* out);
-/* Per-pass CUDA-event durations (ms) of the dense-matrix kernel (k_score_emit) and of the
+/* Per-pass CUDA-event durations (ms) of the dense-matrix kernel (k_emit_rows for plans, k_score_emit for step batches) and of the
  * selection / assignment kernel(s), for every timed pass the last rbgtopo_fetch harvested
  * (bench.py prints their min / median so that a reported average can be checked).  At most `cap`
  * entries are written; *n_passes is the number available. */
