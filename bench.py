@@ -421,7 +421,11 @@ def run_config(D, args, cfg_name, with_clocks):
     if mode == "p2p":
         eng.p2p_connect(D)
     eng.set_stream(D.stream.cuda_stream)
-    handles = [eng.stage_groups(gblob)]
+    # --slots S > 1: S staged copies of the fleet (independent batches: own matrix, plan and outputs) re-placed round
+    # robin, one batch per step — the dense-matrix kernel of a step is chained behind the selection kernel of the
+    # step before it (rbgtopo_run_staged_chain)
+    slots = args.slots if (mode in ("replicated", "groups") or world == 1) and not churn else 1
+    handles = [eng.stage_groups(gblob) for _ in range(slots)]
     total_r = int(gblob[4])
     n_waves = eng.shard_waves(handles[0])
     lo, hi = eng.slab()
@@ -429,7 +433,14 @@ def run_config(D, args, cfg_name, with_clocks):
     scores_all = total_r * n_nodes
     if by_groups:   # every rank scores its own groups against all nodes: the job's scores are the sum over ranks
         scores_all = int(round(D.sum_over_ranks(float(total_r * n_nodes))))
-    device_step = make_device_step(D, eng, handles, n_waves, mode)
+    device_step = make_device_step(D, eng, handles[:1], n_waves, mode)
+
+    def device_steps(k):   # k steps, enqueue only
+        if slots > 1:
+            eng.run_staged_chain(handles, k)
+        else:
+            for _ in range(k):
+                device_step()
 
     # ---- parity first: a deterministic sample of the fleet, all waves, on every rank
     from oracle import placer as oracle_placer
@@ -448,8 +459,7 @@ def run_config(D, args, cfg_name, with_clocks):
     steps = args.steps
     if not churn:
         # ---- value: resident inputs, CUDA events on the launching stream
-        for _ in range(max(args.warmup, 3)):
-            device_step()
+        device_steps(max(args.warmup, 3) * slots)
         for h in handles:
             eng.fetch(h)            # sync + reset the timing window
         sampler = ClockSampler(local)
@@ -460,8 +470,7 @@ def run_config(D, args, cfg_name, with_clocks):
         t_soak = time.perf_counter()
         soak_s = args.soak if with_clocks else 0.1
         while True:   # every rank runs the SAME number of steps (the sharded modes are SPMD): rank 0's clock decides
-            for _ in range(50):
-                device_step()
+            device_steps(50)
             for h in handles:
                 eng.fetch(h)
             more = 1.0 if time.perf_counter() - t_soak < soak_s else 0.0
@@ -475,38 +484,47 @@ def run_config(D, args, cfg_name, with_clocks):
         D.barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(D.stream)
-        for _ in range(steps):
-            device_step()
+        device_steps(steps)
         ev1.record(D.stream)
         D.barrier()
         dev_ms = ev0.elapsed_time(ev1)
         launches = eng.stats()["kernel_launches"] - launches0
-        for h in handles:
-            eng.fetch(h)
+        post = [eng.fetch(h) for h in handles]
+        if slots > 1:   # every slot holds the same fleet: the chained passes must leave what the checked pass left
+            rows = sorted(set(int(i) for i in np.linspace(0, total_r - 1, 16)))
+            ref_rows = [eng.read_scores(handles[0], r).copy() for r in rows]
+            for h, res in zip(handles, post):
+                ok = all(np.array_equal(x, y) for x, y in zip(res, fetched))
+                ok = ok and all(np.array_equal(eng.read_scores(h, r).view(np.uint32), x.view(np.uint32)) for r, x in zip(rows, ref_rows))
+                if not ok and not args.keep_going:
+                    raise SystemExit(f"PARITY FAILED after the chained passes ({cfg_name}, rank {rank}, slot {h})")
+                par["ok"] = bool(par["ok"] and ok)
+            par["slots_checked_after_timing"] = slots
         # per-kernel leg: the SAME K steps again with an event between the two kernels of every pass (recorded
         # inside the library on the launching stream, harvested at fetch).  The event serialises the kernels, so
         # this leg is a little slower than the timed region above (where the selection kernel is a programmatic
         # dependent of the dense-matrix kernel); its step time is reported as ms_per_step_kernel_timing.
         eng.set_kernel_timing(True)
-        device_step()
+        device_steps(slots)
         for h in handles:
             eng.fetch(h)
         D.barrier()
         kv0, kv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         kv0.record(D.stream)
-        for _ in range(steps):
-            device_step()
+        device_steps(steps)
         kv1.record(D.stream)
         D.barrier()
         kt_ms = D.max_over_ranks(kv0.elapsed_time(kv1))
         clocks = sampler.stop() if (rank == 0 and with_clocks) else None
         score_ms = algo_bytes = 0.0
-        for h in handles:
+        per_score = per_sel = np.zeros(0, dtype=np.float32)
+        for h in handles:   # a step is ONE pass over ONE batch: per-step kernel time and bytes = the average over the slots
             eng.fetch(h)
             t = eng.last_timing()
-            score_ms += t["score_ms"]
-            algo_bytes += t["algo_bytes"]
-        per_score, per_sel = eng.last_pass_times()
+            score_ms += t["score_ms"] / len(handles)
+            algo_bytes += t["algo_bytes"] / len(handles)
+            ps, pl = eng.last_pass_times()
+            per_score, per_sel = np.concatenate([per_score, ps]), np.concatenate([per_sel, pl])
         eng.set_kernel_timing(False)
         out["ms_per_step_kernel_timing"] = kt_ms / steps
         dev_ms = D.max_over_ranks(dev_ms)
@@ -620,6 +638,7 @@ def run_config(D, args, cfg_name, with_clocks):
                e2e_ms=e2e_ms / steps, h2d=int(free0.nbytes + 4 * n_plan_words), d2h=int(4 * (total_r + 2 * 3 * groups)),
                n_nodes=n_nodes, groups=groups, total_r=total_r, edges=int(topo.e), slab=(lo, hi), mode=mode,
                topo=topo, specs=specs, what=cfg["what"], scaling=cfg["scaling"])
+    out["slots"] = slots
     if churn:   # no resident-plan leg: every step re-uploads a changed snapshot, so the step IS the e2e call
         out.update(value=out["e2e_value"], ms_per_step=out["e2e_ms"], launches=0, clocks=None, score_ms=0.0, algo_bytes=0.0)
     for h in handles:
@@ -735,7 +754,12 @@ def run_ours(args):
                 "emit_matrix": True,
                 "l2": "dense-matrix write stream per step "
                       f"({main['total_r'] * (hi - lo) * 4 / 1e6:.0f} MB) exceeds the 126 MB L2; inputs are L2-resident by design",
-                "value_leg": "multi-wave plan resident in HBM (rbgtopo_stage_groups), base vector resident "
+                "slots": main.get("slots", 1),
+                "value_leg": ("" if main.get("slots", 1) == 1 else
+                              f"{main.get('slots')} staged copies of the fleet (independent batches: own matrix, plan, outputs) re-placed round "
+                              "robin, one batch per step, the dense-matrix kernel of a step chained behind the selection kernel of the step "
+                              "before it (rbgtopo_run_staged_chain); results of every slot re-checked after the timed region; ") +
+                             "multi-wave plan resident in HBM (rbgtopo_stage_groups), base vector resident "
                              "(recomputed by update_nodes, which is inside the e2e leg)",
                 "e2e_leg": "rbgtopo_update_nodes + rbgtopo_place_groups with host buffers, median of 5 rounds of "
                            "K steps; marshalling RBG objects into the groups blob is the caller's (Go shim) job "
@@ -824,6 +848,9 @@ def main():
                          "no per-step collective; 'p2p' = per-shard top-K lists exchanged per wave by the library's "
                          "own kernels over NVLink peer memory; 'allgather' = the same exchange as NCCL all-gathers "
                          "driven from Python")
+    ap.add_argument("--slots", type=int, default=1,
+                    help="staged copies of the fleet re-placed round robin in the resident leg (independent batches, one per "
+                         "step); > 1 chains the dense-matrix kernel of a step behind the selection kernel of the step before it")
     ap.add_argument("--soak", type=float, default=0.6, help="seconds of untimed identical steps before the timed region")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -254,6 +254,15 @@ int32_t rbgtopo_stage(rbgtopo_ctx* ctx, const int32_t* blob, int64_t blob_words,
  * duration from CUDA events recorded around each launch).  Valid for any world
  * (replicated selection); the shard calls below are the all-gather alternative. */
 int32_t rbgtopo_run_staged(rbgtopo_ctx* ctx, int32_t handle, int32_t iters);
+
+/* Pipeline of staged GROUPS batches (rbgtopo_stage_groups): enqueues `passes` passes, pass k over handles[k %
+ * n_handles] — the reconcile loop of a controller that re-places several independent batches round robin
+ * (rolebasedgroupset_controller.go:69-207 fans one RBGSet out into such batches).  The batches share nothing but the
+ * snapshot, so the dense-matrix kernel of pass k + 1 is chained behind the selection kernel of pass k as a programmatic
+ * dependent and fills the SMs while the slowest groups of pass k are still being placed.  Results as with
+ * rbgtopo_run_staged: rbgtopo_fetch per handle.  The handles must be distinct; with one handle, kernel timing on, or
+ * batches on different streams the passes run one after the other. */
+int32_t rbgtopo_run_staged_chain(rbgtopo_ctx* ctx, const int32_t* handles, int32_t n_handles, int32_t passes);
 int32_t rbgtopo_fetch(rbgtopo_ctx* ctx, int32_t handle, int32_t* assign,
                       int32_t* status, int32_t* domain);
 int32_t rbgtopo_release(rbgtopo_ctx* ctx, int32_t handle);

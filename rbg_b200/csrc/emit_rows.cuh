@@ -101,6 +101,10 @@ k_emit_rows(TopoDev t, float* __restrict__ matrix, const int2* __restrict__ rtab
       if (live[j]) st_stream_f4(rowp + j * (SCORE_THREADS << 2), o4);
     }
   }
+  // Chained behind the selection kernel of the PREVIOUS batch (rbgtopo_run_staged_chain) this launch never needed
+  // its results; waiting for it here, at the very end, keeps the ordering transitive: when this grid is complete so
+  // is everything before it, which the next pass over the previous batch's buffers relies on.  No-op otherwise.
+  pdl_wait();
 }
 
 }  // namespace rbgtopo

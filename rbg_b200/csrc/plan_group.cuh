@@ -263,6 +263,13 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
   GroupRole* sRole = reinterpret_cast<GroupRole*>(sPatAv + (size_t)PB * KS);
   float* sPair = reinterpret_cast<float*>(sRole + MAXP);  // [MAXP][RBGTOPO_MAX_GROUP_ROLES]
 
+  // A dense-matrix kernel of ANOTHER batch may be chained behind this launch as a programmatic dependent
+  // (rbgtopo_run_staged_chain): it touches none of this batch's buffers, and its CTAs can only become resident
+  // where this kernel leaves registers free — on SMs it does not fill, and everywhere as its CTAs retire.  The
+  // trigger comes after this CTA's own wait for the dense-matrix kernel of ITS batch (below), so that "a chained
+  // kernel has started" implies "everything up to this batch's dense matrix is complete"; in record mode nothing
+  // is waited for.
+  if (record) pdl_launch_dependents();
   PCLK(30);
 #ifdef RBGTOPO_PHASE_CLOCKS
   if (tid == 0 && blockIdx.x < 2048) { g_cta_ns[blockIdx.x * 4] = pg_gtime(); g_cta_ns[blockIdx.x * 4 + 3] = pg_smid(); }
@@ -429,7 +436,10 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
     } else if (warp != 0) {
       // first touch of the matrix: as a programmatic dependent of the dense-matrix kernel, everything up to
       // here (table, selection of wave 0) ran while that kernel was draining; warp 0 (greedy) never waits
-      if (wave_i == 0) pdl_wait();
+      if (wave_i == 0) {
+        pdl_wait();
+        pdl_launch_dependents();
+      }
       float* const mrow0 = b.matrix + (size_t)h.rep_off * stride - t.slab_lo;  // mrow0[node]
       for (int d = tid - 32; d < cnt; d += nthreads - 32) {
         const int slot = T.dSlot[d];

@@ -780,7 +780,9 @@ BatchDev batch_dev(rbgtopo_ctx* c, Batch* b) {
 
 // Dense rows of a multi-wave plan from its emit table (b->etab): needs neither the expanded plan blob nor
 // b->m, so plan_stage can launch it while the host still computes the rest of the geometry.
-int launch_emit_plan(rbgtopo_ctx* c, Batch* b, cudaStream_t s, int ns, long long n_rows) {
+// pdl: launch k_emit_rows as a programmatic dependent of the kernel before it on s (run_chain: the selection kernel of
+// another batch)
+int launch_emit_plan(rbgtopo_ctx* c, Batch* b, cudaStream_t s, int ns, long long n_rows, bool pdl = false) {
   if (ns <= 0) return RBGTOPO_OK;
   BatchDev d{};
   d.n_steps = ns;
@@ -791,10 +793,20 @@ int launch_emit_plan(rbgtopo_ctx* c, Batch* b, cudaStream_t s, int ns, long long
     const long long segs = ((n_rows + kEmitRowsBlock - 1) / kEmitRowsBlock) * c->lc;
     if (segs > 0x7FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "rows x chunks exceed 2^31 segments");
     if (segs > 0) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)segs);
+      cfg.blockDim = dim3(SCORE_THREADS);
+      cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = pdl ? 1 : 0;
+      const int2* rt = b->rtab.p;
       if (b->any_excl)
-        k_emit_rows<true><<<(unsigned)segs, SCORE_THREADS, 0, s>>>(topo_dev(c), b->matrix.p, b->rtab.p, (int)n_rows, c->lc, c->chunk, kEmitRowsBlock);
+        CK(cudaLaunchKernelEx(&cfg, k_emit_rows<true>, topo_dev(c), b->matrix.p, rt, (int)n_rows, (int)c->lc, (int)c->chunk, (int)kEmitRowsBlock));
       else
-        k_emit_rows<false><<<(unsigned)segs, SCORE_THREADS, 0, s>>>(topo_dev(c), b->matrix.p, b->rtab.p, (int)n_rows, c->lc, c->chunk, kEmitRowsBlock);
+        CK(cudaLaunchKernelEx(&cfg, k_emit_rows<false>, topo_dev(c), b->matrix.p, rt, (int)n_rows, (int)c->lc, (int)c->chunk, (int)kEmitRowsBlock));
     }
   } else if (kEmitSt) {
     d.bsteps = kEmitBlockSteps;
@@ -994,6 +1006,45 @@ int run_batch(rbgtopo_ctx* c, Batch* b, int iters) {
   CK(cudaGetLastError());
   b->ran = true;
   b->pend_launches += launches;
+  std::lock_guard<std::mutex> g(c->stat_mu);
+  c->launches += launches;
+  return RBGTOPO_OK;
+}
+
+// Pipeline of staged PLAN batches on one stream, ENQUEUE ONLY: `passes` passes, pass k over batch k % n.  Batches are
+// independent (own matrix, plan, outputs), so every dense-matrix kernel but the first is chained behind the selection
+// kernel of the batch before it as a programmatic dependent: its CTAs fill the SMs while the slowest groups of that
+// selection are still being placed (their CTA lifetimes spread over 20-30 us on cfg3), instead of after the launch gap.
+// Falls back to plain passes when the chain does not apply (kernel timing on, other dense-matrix kernels, world > 1's
+// per-wave paths, batches on different streams).
+int run_chain(rbgtopo_ctx* c, Batch** bs, int n, int passes) {
+  NvtxRange nv("rbgtopo:run_chain");
+  cudaStream_t s = stream_of(c, bs[0]);
+  bool chain = !kNoPdl && kSerialPlan && kEmitSt && kEmitRows && !c->kernel_timing.load(std::memory_order_relaxed) && n > 1;
+  PlanGroupCfg pg;
+  for (int i = 0; i < n; ++i) chain = chain && stream_of(c, bs[i]) == s && !bs[i]->early_emit && plan_group_cfg(bs[i], &pg);
+  if (!chain) {
+    for (int k = 0; k < passes; ++k) {
+      int rc = run_batch(c, bs[k % n], 1);
+      if (rc) return rc;
+    }
+    return RBGTOPO_OK;
+  }
+  CK(cudaStreamWaitEvent(s, c->base_ready, 0));  // a pending snapshot refresh: base / free, and the background order
+  CK(cudaStreamWaitEvent(s, c->topo_ready, 0));
+  int launches = 0;
+  for (int k = 0; k < passes; ++k) {
+    Batch* b = bs[k % n];
+    int rc = launch_emit_plan(c, b, s, b->m.n_steps, b->m.total_r, /*pdl=*/k > 0);
+    if (rc) return rc;
+    ++launches;
+    rc = launch_select_assign(c, b, s, batch_dev(c, b), &launches, /*pdl=*/true);
+    if (rc) return rc;
+    b->ran = true;
+    b->untimed_or_timed_passes += 1;
+  }
+  CK(cudaGetLastError());
+  for (int i = 0; i < n; ++i) bs[i]->pend_launches += 2 * ((passes - i + n - 1) / n);
   std::lock_guard<std::mutex> g(c->stat_mu);
   c->launches += launches;
   return RBGTOPO_OK;
@@ -2698,6 +2749,21 @@ int32_t rbgtopo_run_staged(rbgtopo_ctx* c, int32_t handle, int32_t iters) {
   if (!b) return fail(RBGTOPO_EINVAL, "bad or stale handle %d", handle);
   CK(cudaSetDevice(c->cfg.device));
   return run_batch(c, b, iters);
+}
+
+int32_t rbgtopo_run_staged_chain(rbgtopo_ctx* c, const int32_t* handles, int32_t n_handles, int32_t passes) {
+  if (!c || !handles) return fail(RBGTOPO_EINVAL, "null argument");
+  if (n_handles < 1 || n_handles > 64 || passes < 1 || passes > 65536) return fail(RBGTOPO_EINVAL, "n_handles / passes");
+  std::shared_lock<std::shared_mutex> lk(c->topo_mu);
+  Batch* bs[64];
+  for (int i = 0; i < n_handles; ++i) {
+    bs[i] = batch_of(c, handles[i]);
+    if (!bs[i]) return fail(RBGTOPO_EINVAL, "bad or stale handle %d", handles[i]);
+    for (int j = 0; j < i; ++j)
+      if (bs[j] == bs[i]) return fail(RBGTOPO_EINVAL, "handle %d listed twice: the batches of a chain must be distinct", handles[i]);
+  }
+  CK(cudaSetDevice(c->cfg.device));
+  return run_chain(c, bs, n_handles, passes);
 }
 
 int32_t rbgtopo_fetch(rbgtopo_ctx* c, int32_t handle, int32_t* assign, int32_t* status, int32_t* domain) {

@@ -138,6 +138,12 @@ class TopoPlacer:
     def run_staged(self, handle: int, iters: int = 1) -> None:
         self._check(self.lib.rbgtopo_run_staged(self._h, handle, iters))
 
+    def run_staged_chain(self, handles, passes: int) -> None:
+        """`passes` passes round robin over distinct staged GROUPS batches, enqueue only: the dense-matrix kernel of
+        a pass is chained behind the selection kernel of the pass before it (rbgtopo_run_staged_chain)."""
+        hs = np.ascontiguousarray(handles, dtype=np.int32)
+        self._check(self.lib.rbgtopo_run_staged_chain(self._h, _p(hs), len(hs), passes))
+
     def fetch(self, handle: int):
         ns, tr, _ = self._staged_totals[handle]
         assign = np.empty(max(tr, 1), dtype=np.int32)

@@ -194,6 +194,58 @@ def test_plan_dense_matrix_and_lists_match_oracle_per_wave():
     eng.close()
 
 
+def test_chained_batches_equal_separate_runs():
+    """rbgtopo_run_staged_chain: passes round robin over distinct staged batches, the dense-matrix kernel of a pass
+    chained behind the selection kernel of the pass before it (programmatic dependent launch).  Every batch must end
+    with exactly what a plain rbgtopo_run_staged leaves: placements, status, domains and every dense-matrix row —
+    also for tiny batches (few dense-matrix CTAs: the ordering argument must not lean on the grid size), for a single
+    handle, and with kernel timing on (the documented fallbacks)."""
+    from gpu_util import new_engine
+    n = 3000
+    topo = synth.make_topology(n, seed=11, tiers=4, owned_frac=0.2)
+    eng = new_engine(topo)
+    mgr = B200TopoPodGroupManager(eng)
+    fleets = [_fleet(n, 24, seed=5, excl_every=3, big_every=5), _fleet(n, 40, seed=9, excl_every=4, big_every=7),
+              _fleet(n, 2, seed=3, excl_every=2, big_every=0), _fleet(n, 1, seed=4, excl_every=0, big_every=0)]
+    blobs = [mgr.groups_blob(f)[0] for f in fleets]
+    want = []
+    for gb in blobs:                      # reference: each batch alone
+        h = eng.stage_groups(gb)
+        eng.run_staged(h, 1)
+        a, st, dm = eng.fetch(h)
+        rows = [eng.read_scores(h, r).copy() for r in range(int(gb[4]))]
+        want.append((a.copy(), st.copy(), dm.copy(), rows))
+        eng.release(h)
+
+    def check(hs, which):
+        for h, i in zip(hs, which):
+            a, st, dm = eng.fetch(h)
+            wa, ws, wd, wrows = want[i]
+            assert np.array_equal(a, wa) and np.array_equal(st, ws) and np.array_equal(dm, wd), i
+            for r, exp in enumerate(wrows):
+                got = eng.read_scores(h, r)
+                assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (i, r)
+
+    hs = [eng.stage_groups(gb) for gb in blobs]
+    eng.run_staged_chain(hs, 4)           # one pass each
+    check(hs, range(4))
+    eng.run_staged_chain(hs, 4 * 7 + 2)   # many rounds, ending mid-round
+    check(hs, range(4))
+    eng.run_staged_chain(hs[2:], 9)       # the two tiny batches alone (1-2 groups: a handful of CTAs per kernel)
+    check(hs[2:], [2, 3])
+    eng.run_staged_chain(hs[:1], 3)       # one handle: plain passes
+    check(hs[:1], [0])
+    eng.set_kernel_timing(True)           # per-kernel events: plain passes
+    eng.run_staged_chain(hs, 8)
+    check(hs, range(4))
+    eng.set_kernel_timing(False)
+    with pytest.raises(Exception):
+        eng.run_staged_chain([hs[0], hs[0]], 2)
+    for h in hs:
+        eng.release(h)
+    eng.close()
+
+
 @pytest.mark.parametrize("var", ["RBGTOPO_VERIFY_PLAN", "RBGTOPO_PER_WAVE_PLAN", "RBGTOPO_SPLIT_MIN_GROUPS",
                                  "RBGTOPO_CONCURRENT_PLAN", "RBGTOPO_EMIT_TMA", "RBGTOPO_CONCURRENT_PLAN+RBGTOPO_EMIT_TMA",
                                  "RBGTOPO_EMIT_STEPS+RBGTOPO_VERIFY_PLAN", "RBGTOPO_KERNEL_TIMING", "RBGTOPO_NO_PDL",
