@@ -183,6 +183,11 @@ struct Batch {
   DevBuf<int2> rtab;           // row table of a plan (emit_rows.cuh)
   bool any_excl = false;       // a group of the plan is exclusive: k_emit_rows<true>
   std::vector<char> pass_mid;  // per pending pass: was the event between the two kernels recorded?
+  // host-buffer entry point: the GROUPS blob was copied to the pinned staging and its upload enqueued BEFORE validation
+  // (bytes only; no kernel reads them unless the validation passes), valid while both buffers stay where they were
+  const int32_t* prestaged_h = nullptr;
+  const int* prestaged_d = nullptr;
+  size_t prestaged_hcap = 0, prestaged_dcap = 0;  // a re-allocation changes the capacity even when the address comes back
   bool tev = false;            // timing events (ev[0], ev[1], ev[4], ev[5], the early emit's) recorded since the staging
   DevBuf<int> corr, corr_cnt;  // correction records of a plan: k_plan_group(record) -> k_plan_correct
   // device-resident multi-wave plan (rbgtopo_stage_groups / place_groups): steps are
@@ -309,6 +314,9 @@ const bool kRefreshGraph = getenv("RBGTOPO_NO_REFRESH_GRAPH") == nullptr;
 const bool kSmallSort = getenv("RBGTOPO_SMALL_SORT") != nullptr;
 const bool kVerifyPlan = getenv("RBGTOPO_VERIFY_PLAN") != nullptr;  // self-check: device-expanded plan == host-built plan
 const int kHostThreads = getenv("RBGTOPO_HOST_THREADS") ? std::max(1, atoi(getenv("RBGTOPO_HOST_THREADS"))) : 4;
+// With the per-shape caches a group costs ~50 ns of host time: below a few thousand groups an OpenMP region costs more
+// than it saves (94 us on one thread against 114 / 143 us on 2 / 4 for the 1 024-group bench fleet).
+const int kHostParallelMinGroups = getenv("RBGTOPO_HOST_PARALLEL_MIN") ? std::max(1, atoi(getenv("RBGTOPO_HOST_PARALLEL_MIN"))) : 4096;
 
 // Events that only measure (staging, early emit, D2H, refresh) are recorded with kernel timing on or under
 // RBGTOPO_PROFILE_HOST: each costs stream time, and the host-buffer entry points are latency-bound.
@@ -2075,6 +2083,52 @@ struct TopoHost {
   int max_degp1 = 1;
   long long wsum_max = 0;
 };
+// Fleets are made of a few role templates (an RBGSet fans ONE RoleBasedGroup out into N, rolebasedgroupset_controller.go:69-207):
+// what the plan geometry derives from a group's role table and pair matrix alone — validity, pending replicas, the
+// wave structure, per-wave sizes and the shape part of the exactness bound — is computed once per run of identical
+// shapes (per host thread) and re-used; only the anchor-dependent terms are per group.  Shapes with more than
+// kShapeWaves waves are not cached.
+constexpr int kShapeWaves = 16;
+struct ShapeCache {
+  bool valid = false;
+  int q = 0, nw = 0;
+  long long pend = 0;
+  int32_t roles[4 * RBGTOPO_MAX_GROUP_ROLES];
+  int32_t pair[RBGTOPO_MAX_GROUP_ROLES * RBGTOPO_MAX_GROUP_ROLES];
+  // per wave (size_group)
+  bool sized = false;
+  int P[kShapeWaves], n[kShapeWaves], i0[kShapeWaves];
+  int role[kShapeWaves][RBGTOPO_MAX_STEP_ROLES];
+  long long bound[kShapeWaves][RBGTOPO_MAX_STEP_ROLES];  // sum_j pair[ri][j] * placed[j] + min(need, cap) * F (saturated)
+  bool match(const int32_t* r, const int32_t* p, int qq) const {
+    return valid && qq == q && memcmp(r, roles, (size_t)16 * qq) == 0 && memcmp(p, pair, (size_t)4 * qq * qq) == 0;
+  }
+  void set(const int32_t* r, const int32_t* p, int qq) {
+    q = qq;
+    memcpy(roles, r, (size_t)16 * qq);
+    memcpy(pair, p, (size_t)4 * qq * qq);
+    valid = true;
+    sized = false;
+  }
+};
+
+// A few shapes per thread (fleets interleave a handful of templates), round-robin replacement.
+struct ShapeCaches {
+  static constexpr int kWays = 4;
+  ShapeCache way[kWays];
+  int next = 0;
+  ShapeCache* find(const int32_t* r, const int32_t* p, int q) {
+    for (int i = 0; i < kWays; ++i)
+      if (way[i].match(r, p, q)) return &way[i];
+    return nullptr;
+  }
+  ShapeCache* victim() {
+    ShapeCache* v = &way[next];
+    next = (next + 1) % kWays;
+    return v;
+  }
+};
+
 struct PlanLayout {  // staging layout of one plan: GROUPS blob | pad | (group, wave) per step | geometry (8 ints per step) | poff
   size_t sgw_off = 0, aux_off = 0, tail_off = 0, tail_words = 0, src_words = 0;
   long long plan_words = 0, racc = 0, rowacc = 0;
@@ -2126,21 +2180,34 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
     if (!in(rec[4], 4LL * q) || !in(rec[5], (long long)q * q) || !in(rec[7], 3LL * rec[6]))
       GROUP_FAIL(RBGTOPO_EINVAL, "group %d: section out of bounds", g);
     const int32_t* roles = gb + rec[4];
+    static thread_local ShapeCaches sc_chk;  // the last shapes this thread validated
     long long pend = 0;
-    for (int i = 0; i < q; ++i) {
-      if (roles[4 * i + 1] < 0 || (i && roles[4 * i] < roles[4 * (i - 1)]))
-        GROUP_FAIL(RBGTOPO_EINVAL, "group %d role %d: pending < 0 or levels not ascending", g, i);
-      if (roles[4 * i + 2] < 0 || roles[4 * i + 2] > RBGTOPO_MAX_FREE)
-        GROUP_FAIL(RBGTOPO_EINVAL, "group %d role %d: demand", g, i);
-      pend += roles[4 * i + 1];
+    int nw_g = 0;
+    const ShapeCache* hit = report ? nullptr : sc_chk.find(roles, gb + rec[5], q);
+    if (hit) {  // same role table and pair matrix as an earlier group: valid, known
+      pend = hit->pend;
+      nw_g = hit->nw;
+    } else {
+      for (int i = 0; i < q; ++i) {
+        if (roles[4 * i + 1] < 0 || (i && roles[4 * i] < roles[4 * (i - 1)]))
+          GROUP_FAIL(RBGTOPO_EINVAL, "group %d role %d: pending < 0 or levels not ascending", g, i);
+        if (roles[4 * i + 2] < 0 || roles[4 * i + 2] > RBGTOPO_MAX_FREE)
+          GROUP_FAIL(RBGTOPO_EINVAL, "group %d role %d: demand", g, i);
+        pend += roles[4 * i + 1];
+      }
+      if (pend > 0x3FFFFFFFLL) GROUP_FAIL(RBGTOPO_ELIMIT, "group %d: pending replicas", g);
+      for (int i = 0; i < q; ++i)
+        if (roles[4 * i + 3] & ~RBGTOPO_ROLE_EXCLUSIVE) GROUP_FAIL(RBGTOPO_EINVAL, "group %d role %d: unknown role flags", g, i);
+      for (int i = 0; i < q * q; ++i)
+        if (gb[rec[5] + i] < 0 || gb[rec[5] + i] > kMaxExactTerm) GROUP_FAIL(RBGTOPO_EINVAL, "group %d: pair weight out of [0, 2^24]", g);
+      nw_g = gen_waves(roles, q, nullptr);
+      ShapeCache* v = sc_chk.victim();
+      v->set(roles, gb + rec[5], q);
+      v->pend = pend;
+      v->nw = nw_g;
     }
-    if (pend > 0x3FFFFFFFLL) GROUP_FAIL(RBGTOPO_ELIMIT, "group %d: pending replicas", g);
     if (rec[0] < 0 || rec[2] < -1 || rec[2] >= n_domains) GROUP_FAIL(RBGTOPO_EINVAL, "group %d: gid / fixed_domain", g);
     if (rec[1] & ~(RBGTOPO_STEP_EXCLUSIVE | RBGTOPO_STEP_GANG)) GROUP_FAIL(RBGTOPO_EINVAL, "group %d: unknown flags 0x%x", g, rec[1]);
-    for (int i = 0; i < q; ++i)
-      if (roles[4 * i + 3] & ~RBGTOPO_ROLE_EXCLUSIVE) GROUP_FAIL(RBGTOPO_EINVAL, "group %d role %d: unknown role flags", g, i);
-    for (int i = 0; i < q * q; ++i)
-      if (gb[rec[5] + i] < 0 || gb[rec[5] + i] > kMaxExactTerm) GROUP_FAIL(RBGTOPO_EINVAL, "group %d: pair weight out of [0, 2^24]", g);
     long long pc = 0;  // closed neighbourhoods of the scheduled pods
     for (int a = 0; a < rec[6]; ++a) {
       const int32_t* an = gb + rec[7] + 3 * a;
@@ -2151,11 +2218,11 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
     if (pc > 0x3FFFFFFFLL) GROUP_FAIL(RBGTOPO_ELIMIT, "group %d: patch list exceeds 2^30 entries", g);
     g_pend[g] = (int)pend;
     g_pcp[g] = (int)pc;
-    g_nw[g] = gen_waves(roles, q, nullptr);
+    g_nw[g] = nw_g;
     return RBGTOPO_OK;
   };
   int first_bad = ng;
-#pragma omp parallel for schedule(static) num_threads(kHostThreads) reduction(min : first_bad) if (ng >= 64 && kHostThreads > 1)
+#pragma omp parallel for schedule(static) num_threads(kHostThreads) reduction(min : first_bad) if (ng >= kHostParallelMinGroups && kHostThreads > 1)
   for (int g = 0; g < ng; ++g)
     if (check_group(g, false) != RBGTOPO_OK) first_bad = std::min(first_bad, g);
   if (first_bad < ng) return check_group(first_bad, true);
@@ -2204,6 +2271,7 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
   const size_t tail_words = (size_t)ns + 1;
   const size_t src_words = tail_off + tail_words;
   if (src_words > 0x7FFFFFF0ULL) return fail(RBGTOPO_ELIMIT, "plan staging exceeds 2^31 words");
+  if (b->prestaged_h && src_words > b->h_in.cap) CK(cudaDeviceSynchronize());  // the pre-validation upload reads the buffer about to be replaced
   CK(b->h_in.reserve(src_words));
   int32_t* const hin = b->h_in.p;
   int32_t* const aux = hin + aux_off;
@@ -2229,8 +2297,11 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
       }
     }
   }
-  if (with_blob) {  // the caller's blob into the pinned staging (the hook uploads it)
-    memcpy(hin, gb, (size_t)words * 4);
+  if (with_blob) {  // the caller's blob into the pinned staging (the hook uploads it) — unless plan_stage did both already
+    if (b->prestaged_h != hin || b->prestaged_hcap != b->h_in.cap) {
+      b->prestaged_h = nullptr;
+      memcpy(hin, gb, (size_t)words * 4);
+    }
     for (size_t i = (size_t)words; i < sgw_off; ++i) hin[i] = 0;
   }
   for (size_t i = sgw_off + 2 * (size_t)ns; i < aux_off; ++i) hin[i] = 0;
@@ -2250,6 +2321,7 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
   const long long row_w = T.wsum_max + RBGTOPO_SELF_W;
   const int max_degp1 = T.max_degp1;
   const int* const first_of = g_first.data();
+  const long long amax_limit = ((1LL << 24) + row_w - 1) / row_w;  // amax * row_w >= 2^24  <=>  amax >= limit
   auto size_group = [&](int g, bool report) -> int {
     const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)(g_lo + g) * RBGTOPO_GROUP_WORDS;
     const int q = rec[3], na = rec[6];
@@ -2262,29 +2334,17 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
       for (int a = 0; a < na && acc < sat; ++a) acc += (long long)pair[ri * q + gb[rec[7] + 3 * a + 1]] * gb[rec[7] + 3 * a + 2];
       anch_w[ri] = std::min(acc, sat);
     }
-    int placed[RBGTOPO_MAX_GROUP_ROLES] = {0};
-    int i0 = 0, s = -1, rc = RBGTOPO_OK;
-    // the group's steps in wave order: follow the `next` links from its first step
-    walk_waves(roles, q, [&](int w, const PlanWave& pw) {
-      if (rc) return;
-      s = (w == 0) ? first_of[g] : aux[(size_t)s * PLAN_AUX_WORDS + 6];
-      const int P = pw.size();
-      int n = 0;
+    // one step of the group: the exactness bound (anchor term of THIS group + the shape's term), sizes, capacity
+    int s = -1, rc = RBGTOPO_OK;
+    auto step_of = [&](int w, int P, int n, int i0, const int* role_of, const long long* bound) {
+      s = (w == 0) ? first_of[g] : aux[(size_t)s * PLAN_AUX_WORDS + 6];  // follow the `next` links from the group's first step
       for (int k = 0; k < P; ++k) {
-        const int ri = pw.role[k];
-        int need = 0;
-        long long amax = anch_w[ri];
-        for (int j = 0; j < q; ++j) {
-          if (pair[ri * q + j] > 0) need = (int)std::min<long long>((long long)need + roles[4 * j + 1] - placed[j], 1 << 30);
-          amax = std::min(amax + (long long)pair[ri * q + j] * placed[j], sat);  // each term < 2^24 * 2^30
-        }
-        amax += (long long)std::min(need, RBGTOPO_NEED_CAP) * RBGTOPO_F_CAP;
-        if (amax >= ((1LL << 24) + row_w - 1) / row_w) {
-          rc = report ? fail(RBGTOPO_EINEXACT, "group %d wave %d role %d: max score bound >= 2^24 (anchor weight %lld x row weight %lld)", g, w, ri, amax, row_w)
+        const long long amax = std::min(anch_w[role_of[k]] + bound[k], sat);
+        if (amax >= amax_limit) {
+          rc = report ? fail(RBGTOPO_EINEXACT, "group %d wave %d role %d: max score bound >= 2^24 (anchor weight %lld x row weight %lld)", g, w, role_of[k], amax, row_w)
                       : (int)RBGTOPO_EINEXACT;
           return;
         }
-        n += pw.count[k];
       }
       long long sz = 4LL * P + (long long)P * q + 3LL * (na + i0) + 2LL * i0;
       sz = (sz + 3) & ~3LL;  // keeps every role section 16-byte aligned
@@ -2299,13 +2359,53 @@ int plan_geometry(const TopoHost& T, int lc, Batch* b, const int32_t* gb, int64_
       a[4] = n;        // -> rep_off
       a[5] = P;        // -> row_off
       a[7] = i0;
+    };
+    static thread_local ShapeCaches sc_szs;  // the last shapes this thread sized
+    if (const ShapeCache* hit = report ? nullptr : sc_szs.find(roles, pair, q)) {
+      if (hit->sized) {
+        for (int w = 0; w < hit->nw && !rc; ++w) step_of(w, hit->P[w], hit->n[w], hit->i0[w], hit->role[w], hit->bound[w]);
+        return rc;
+      }
+    }
+    ShapeCache& sc_sz = *sc_szs.victim();
+    sc_sz.set(roles, pair, q);
+    bool cacheable = true;
+    int placed[RBGTOPO_MAX_GROUP_ROLES] = {0};
+    int i0 = 0;
+    const int nw = walk_waves(roles, q, [&](int w, const PlanWave& pw) {
+      if (rc) return;
+      const int P = pw.size();
+      int n = 0;
+      long long bound[RBGTOPO_MAX_STEP_ROLES];
+      for (int k = 0; k < P; ++k) {
+        const int ri = pw.role[k];
+        int need = 0;
+        long long bnd = 0;
+        for (int j = 0; j < q; ++j) {
+          if (pair[ri * q + j] > 0) need = (int)std::min<long long>((long long)need + roles[4 * j + 1] - placed[j], 1 << 30);
+          bnd = std::min(bnd + (long long)pair[ri * q + j] * placed[j], sat);  // each term < 2^24 * 2^30
+        }
+        bound[k] = bnd + (long long)std::min(need, RBGTOPO_NEED_CAP) * RBGTOPO_F_CAP;
+        n += pw.count[k];
+      }
+      step_of(w, P, n, i0, pw.role, bound);
+      if (w < kShapeWaves) {
+        sc_sz.P[w] = P;
+        sc_sz.n[w] = n;
+        sc_sz.i0[w] = i0;
+        for (int k = 0; k < P; ++k) { sc_sz.role[w][k] = pw.role[k]; sc_sz.bound[w][k] = bound[k]; }
+      } else {
+        cacheable = false;
+      }
       for (int k = 0; k < P; ++k) placed[pw.role[k]] += pw.count[k];
       i0 += n;
     });
+    sc_sz.nw = nw;
+    sc_sz.sized = cacheable && rc == RBGTOPO_OK && !report;
     return rc;
   };
   first_bad = ng;
-#pragma omp parallel for schedule(static) num_threads(kHostThreads) reduction(min : first_bad) if (ng >= 64 && kHostThreads > 1)
+#pragma omp parallel for schedule(static) num_threads(kHostThreads) reduction(min : first_bad) if (ng >= kHostParallelMinGroups && kHostThreads > 1)
   for (int g = 0; g < ng; ++g)
     if (size_group(g, false) != RBGTOPO_OK) first_bad = std::min(first_bad, g);
   if (first_bad < ng) return size_group(first_bad, true);
@@ -2401,7 +2501,10 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, bool 
     b->epoch = c->topo_epoch;
     b->tev = timing_events(c);
     if (b->tev) CK(cudaEventRecord(b->ev[0], s));  // staging touches the batch's own buffers only: no wait for a pending snapshot refresh
-    const size_t lo = dev_groups ? P.sgw_off : 0, hi = P.aux_off;  // blob (unless an earlier batch uploaded it) + (group, wave) table
+    const bool pre = b->prestaged_h && b->prestaged_h == b->h_in.p && b->prestaged_hcap == b->h_in.cap &&
+                     b->prestaged_d == b->gsrc.p && b->prestaged_dcap == b->gsrc.cap;  // both buffers stayed put
+    // blob (unless an earlier batch, or the pre-validation upload, brought it) + (group, wave) table
+    const size_t lo = dev_groups ? P.sgw_off : (pre ? (size_t)words : 0), hi = P.aux_off;
     if (hi > lo) CK(cudaMemcpyAsync(b->gsrc.p + lo, b->h_in.p + lo, (hi - lo) * 4, cudaMemcpyHostToDevice, s));
     if (dev_groups && dev_groups_ready) CK(cudaStreamWaitEvent(s, dev_groups_ready, 0));
     if (P.ns > 0) {
@@ -2426,7 +2529,21 @@ int plan_stage(rbgtopo_ctx* c, Batch* b, const int32_t* gb, int64_t words, bool 
     return RBGTOPO_OK;
   };
   b->early_emit = false;
+  // The upload of the GROUPS blob does not wait for its validation: ~15 us of PCIe time under the host's check + numbering
+  b->prestaged_h = nullptr;
+  b->prestaged_d = nullptr;
+  if (early_emit && !dev_groups && g_lo == 0 && words >= RBGTOPO_HDR_WORDS && !b->h_in.pageable && (size_t)words <= b->h_in.cap &&
+      (size_t)words <= b->gsrc.cap) {
+    memcpy(b->h_in.p, gb, (size_t)words * 4);
+    CK(cudaMemcpyAsync(b->gsrc.p, b->h_in.p, (size_t)words * 4, cudaMemcpyHostToDevice, s));
+    b->prestaged_h = b->h_in.p;
+    b->prestaged_d = b->gsrc.p;
+    b->prestaged_hcap = b->h_in.cap;
+    b->prestaged_dcap = b->gsrc.cap;
+  }
   int rc = plan_geometry(th, c->lc, b, gb, words, g_lo, g_hi, pacc0, dev_groups == nullptr, &L, mid);
+  b->prestaged_h = nullptr;
+  b->prestaged_d = nullptr;
   if (rc) return rc;
   BatchMeta& m = b->m;
   const long long slab = c->slab_hi - c->slab_lo;
