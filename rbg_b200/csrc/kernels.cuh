@@ -63,6 +63,7 @@ struct BatchDev {
   float* matrix;              // [total R][slab_stride]
   int* cand;                  // per-step scratch: patched slab nodes (select.cuh)
   const int* poff;            // [n_steps + 1] scratch offsets (host prefix of the caps)
+  const int* perm;            // [groups with pending replicas] first step of the group CTA i of k_plan_group places, or nullptr
   unsigned long long* lists;  // [rolerows][KS] rank-local top-K per role row
   const unsigned long long* lists_all;  // [parts][rolerows][KS]
   long long part_stride;                // u64 elements between parts

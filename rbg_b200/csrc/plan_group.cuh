@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
   if (tid == 0 && blockIdx.x < 2048) { g_cta_ns[blockIdx.x * 4] = pg_gtime(); g_cta_ns[blockIdx.x * 4 + 3] = pg_smid(); }
 #endif
   int wave_i = 0;
-  int step = blockIdx.x;
+  int step = b.perm ? b.perm[blockIdx.x] : blockIdx.x;  // launch order: heavy groups dealt across the SMs (rbgtopo.cu)
   StepHdr h = load_hdr(b, step);  // in flight while the table is cleared
   for (int i = tid; i < HT; i += nthreads) {
     T.node[i] = -1;
