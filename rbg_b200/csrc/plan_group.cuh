@@ -227,6 +227,69 @@ __device__ __forceinline__ void gtab_add_anchor(const TopoDev& t, const GroupTab
   }
 }
 
+// Next wave of a group from its role table (level, pending, demand, flags per role): the rule of walk_waves
+// (rbgtopo.cu) / plan_wave_at (plan.cuh), one wave per call with the cursor (cr, taken) carried by the caller.
+// Fills role[] / count[] and returns the number of role rows (0 = no wave left).  One thread.
+__device__ __forceinline__ int wave_next(const int* roles, int q, int& cr, int& taken, int* role, int* count) {
+  while (cr < q && roles[4 * cr + 1] - taken <= 0) { ++cr; taken = 0; }
+  if (cr >= q) return 0;
+  const int level = roles[4 * cr];
+  int n = 0, P = 0;
+  while (cr < q && roles[4 * cr] == level && n < RBGTOPO_MAX_STEP_REPLICAS && P < RBGTOPO_MAX_STEP_ROLES) {
+    const int left = roles[4 * cr + 1] - taken;
+    if (left <= 0) { ++cr; taken = 0; continue; }
+    const int take = min(left, RBGTOPO_MAX_STEP_REPLICAS - n);
+    role[P] = cr;
+    count[P] = take;
+    ++P;
+    n += take;
+    taken += take;
+    if (taken == roles[4 * cr + 1]) { ++cr; taken = 0; }
+  }
+  return P;
+}
+
+// Row table of k_emit_rows (kernels.cuh) straight from the GROUPS blob, one warp per group: the group's dense rows
+// are [assign_off, + pending) in role order within a wave, waves in order — the row of a replica is a function of its
+// group alone, so the dense matrix needs nothing the host computes per step.  rbgtopo_place_groups' direct path.
+constexpr int RTAB_WARPS = 4;
+__global__ void __launch_bounds__(32 * RTAB_WARPS) k_group_rtab(const int* __restrict__ grp, int n_groups, int2* __restrict__ rtab) {
+  __shared__ int sR[RTAB_WARPS][4 * RBGTOPO_MAX_GROUP_ROLES], sP[RTAB_WARPS][RBGTOPO_MAX_GROUP_ROLES * RBGTOPO_MAX_GROUP_ROLES];
+  __shared__ int sPl[RTAB_WARPS][RBGTOPO_MAX_GROUP_ROLES], sRole[RTAB_WARPS][RBGTOPO_MAX_STEP_ROLES], sCount[RTAB_WARPS][RBGTOPO_MAX_STEP_ROLES];
+  __shared__ int sNP[RTAB_WARPS];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int g = blockIdx.x * RTAB_WARPS + wi;
+  if (g >= n_groups) return;
+  const int* rec = grp + RBGTOPO_HDR_WORDS + (size_t)g * RBGTOPO_GROUP_WORDS;
+  const int gid = rec[0], q = rec[3];
+  const bool excl = (rec[1] & RBGTOPO_STEP_EXCLUSIVE) != 0;
+  if (rec[9] <= 0) return;  // nothing pending: no rows
+  for (int i = lane; i < 4 * q; i += 32) sR[wi][i] = grp[rec[4] + i];
+  for (int i = lane; i < q * q; i += 32) sP[wi][i] = grp[rec[5] + i];
+  if (lane < RBGTOPO_MAX_GROUP_ROLES) sPl[wi][lane] = 0;
+  __syncwarp();
+  int cr = 0, tk = 0, row = rec[8];
+  while (true) {
+    if (lane == 0) sNP[wi] = wave_next(sR[wi], q, cr, tk, sRole[wi], sCount[wi]);  // the cursor lives in lane 0
+    __syncwarp();
+    const int P = sNP[wi];
+    if (P == 0) break;
+    for (int p = 0; p < P; ++p) {
+      const int ri = sRole[wi][p], cnt = sCount[wi][p];
+      int need = 0;
+      for (int j = 0; j < q; ++j)
+        if (sP[wi][ri * q + j] > 0) need += sR[wi][4 * j + 1] - sPl[wi][j];
+      const bool rexcl = excl && (sR[wi][4 * ri + 3] & RBGTOPO_ROLE_EXCLUSIVE);
+      const int2 rr = make_int2(emit_pack_row(sR[wi][4 * ri + 2], min(need, RBGTOPO_NEED_CAP), rexcl), gid);
+      for (int k = lane; k < cnt; k += 32) rtab[row + k] = rr;
+      row += cnt;
+    }
+    __syncwarp();
+    if (lane < P) sPl[wi][sRole[wi][lane]] += sCount[wi][lane];
+    __syncwarp();
+  }
+}
+
 // grid = groups with at least one pending replica = the steps of wave 0; CTA g starts at step g.
 // QB = largest role count of a group in the batch, PB = warps per CTA (>= roles of any wave).
 // record == 0: the sparse corrections of the dense matrix are applied here (the kernel must run
@@ -235,6 +298,14 @@ __device__ __forceinline__ void gtab_add_anchor(const TopoDev& t, const GroupTab
 //   and leaves, per step, a compact list of corrections (node, one value per role row: the summed
 //   delta, or -inf) in b.corr / b.corr_cnt for k_plan_correct.  It then runs CONCURRENTLY with
 //   k_score_emit on a second stream; the step's critical path becomes max(emit, select) + correct.
+//
+// DIRECT = true (rbgtopo_place_groups, the host-buffer entry point): there is no expanded plan.  b.blob is the GROUPS
+// blob as the caller passed it, b.perm[blockIdx.x] the group this CTA places; the CTA replays the group's wave rule
+// itself (wave_next), derives every wave's role records (count, demand, predicted need) and pair rows from the
+// group's role table, and reports per GROUP: b.status[g] = worst wave status, b.domain_out[g] = the exclusive
+// domain.  The host then computes nothing per step — no step numbering, section sizes or prefixes — and launches
+// this kernel right behind the dense-matrix kernel.
+template <bool DIRECT>
 __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev b, int QB, int HT, int CAP, int record) {
   extern __shared__ __align__(16) unsigned char pg_smem[];
   __shared__ int sTakenNode[KS], sTakenAmt[KS], sTakenRole[KS], sRowB[KS], sRowN[KS];
@@ -276,17 +347,48 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
 #endif
   int wave_i = 0;
   int step = b.perm ? b.perm[blockIdx.x] : blockIdx.x;  // launch order: heavy groups dealt across the SMs (rbgtopo.cu)
-  StepHdr h = load_hdr(b, step);  // in flight while the table is cleared
+  // DIRECT: `step` is the group's index in the GROUPS blob; the header is the group record
+  __shared__ int sGR[DIRECT ? 4 * RBGTOPO_MAX_GROUP_ROLES : 1];                            // role table of the group
+  __shared__ int sGP[DIRECT ? RBGTOPO_MAX_GROUP_ROLES * RBGTOPO_MAX_GROUP_ROLES : 1];      // pair matrix
+  __shared__ int sPlaced[DIRECT ? RBGTOPO_MAX_GROUP_ROLES : 1];                            // replicas of a role in earlier waves
+  __shared__ int sWRole[DIRECT ? RBGTOPO_MAX_STEP_ROLES : 1], sWCount[DIRECT ? RBGTOPO_MAX_STEP_ROLES : 1];
+  __shared__ int sWP, sWN, sCr, sTk;
+  int g_rep0 = 0, g_pend = 0, g_i0 = 0, g_stat = 0, g_dom = -1;  // DIRECT: first dense row, pending replicas, rows of earlier waves, results
+  StepHdr h;
+  if (DIRECT) {
+    const int* rec = b.blob + RBGTOPO_HDR_WORDS + (size_t)step * RBGTOPO_GROUP_WORDS;
+    h.gid = rec[0];
+    h.flags = rec[1] & (RBGTOPO_STEP_EXCLUSIVE | RBGTOPO_STEP_GANG);
+    h.fixed_domain = (rec[1] & RBGTOPO_STEP_EXCLUSIVE) ? rec[2] : -1;
+    h.Q = rec[3];
+    h.role_off = rec[4];
+    h.pair_off = rec[5];
+    h.n_anchors = rec[6];
+    h.anchor_off = rec[7];
+    h.i0 = 0;
+    g_rep0 = rec[8];  // place_groups passes the whole fleet as one batch: assign_off is the dense row
+    g_pend = rec[9];
+    h.P = 0; h.R = 0; h.rep_off = g_rep0; h.rolerow_off = 0; h.next_step = 0; h.n_cons = 0; h.cons_off = 0;
+  } else {
+    h = load_hdr(b, step);  // in flight while the table is cleared
+  }
   for (int i = tid; i < HT; i += nthreads) {
     T.node[i] = -1;
     T.cons[i] = 0;
   }
   for (int i = tid; i < QB * HT; i += nthreads) T.aw[i] = 0.0f;
   if (tid == 0) sCnt = 0;
+  if (DIRECT) {
+    for (int i = tid; i < 4 * h.Q; i += nthreads) sGR[i] = b.blob[h.role_off + i];
+    for (int i = tid; i < h.Q * h.Q; i += nthreads) sGP[i] = b.blob[h.pair_off + i];
+    if (tid < RBGTOPO_MAX_GROUP_ROLES) sPlaced[tid] = 0;
+    if (tid == 0) { sCr = 0; sTk = 0; }
+  }
   const bool excl_step = (h.flags & RBGTOPO_STEP_EXCLUSIVE) != 0;
   const bool gang = (h.flags & RBGTOPO_STEP_GANG) != 0;
   const int gid = h.gid, Q = h.Q;
   int fixed = excl_step ? h.fixed_domain : -1;
+  g_dom = fixed;  // DIRECT: an exclusive group confirms the domain it already occupies
   const size_t stride = (size_t)t.slab_stride;
   __syncthreads();
 
@@ -303,13 +405,42 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
     // head of the background order for this warp's candidates: in flight during A (used when need > 0)
     const unsigned long long ob0 = lane < t.n ? t.order_all[lane] : 0ull;
     // ---- A. this wave's roles; consumption + CSR row bounds of the previous wave's placements
-    if (tid < h.P) {
-      const int4 r = *reinterpret_cast<const int4*>(b.blob + h.role_off + 4 * tid);
-      sRole[tid] = GroupRole{r.x, r.y, r.z, r.w};
+    if (DIRECT) {
+      // the wave itself: role rows and counts from the group's role table (one thread), then the records
+      // k_expand_plan would have written: (count, demand, predicted need, flags | group role << 8) and the pair rows
+      if (tid == 0) {
+        int cr = sCr, tk = sTk;
+        const int P = wave_next(sGR, Q, cr, tk, sWRole, sWCount);
+        int n = 0;
+        for (int k = 0; k < P; ++k) n += sWCount[k];
+        sCr = cr;
+        sTk = tk;
+        sWP = P;
+        sWN = n;
+      }
+      __syncthreads();
+      h.P = sWP;
+      h.R = sWN;
+      h.rep_off = g_rep0 + g_i0;
+      if (h.P == 0) break;  // no wave left (a group with pending replicas always has a first one)
+      if (tid < h.P) {
+        const int ri = sWRole[tid];
+        int need = 0;
+        for (int j = 0; j < Q; ++j)
+          if (sGP[ri * Q + j] > 0) need += sGR[4 * j + 1] - sPlaced[j];
+        sRole[tid] = GroupRole{sWCount[tid], sGR[4 * ri + 2], min(need, RBGTOPO_NEED_CAP), (sGR[4 * ri + 3] & 0xFF) | (ri << 8)};
+      }
+      for (int i = tid; i < h.P * Q; i += nthreads)
+        sPair[(i / Q) * RBGTOPO_MAX_GROUP_ROLES + i % Q] = (float)sGP[sWRole[i / Q] * Q + i % Q];
+    } else {
+      if (tid < h.P) {
+        const int4 r = *reinterpret_cast<const int4*>(b.blob + h.role_off + 4 * tid);
+        sRole[tid] = GroupRole{r.x, r.y, r.z, r.w};
+      }
+      for (int i = tid; i < h.P * Q; i += nthreads)
+        sPair[(i / Q) * RBGTOPO_MAX_GROUP_ROLES + i % Q] = (float)b.blob[h.pair_off + i];
     }
     if (tid == 0) sCorrN = 0;
-    for (int i = tid; i < h.P * Q; i += nthreads)
-      sPair[(i / Q) * RBGTOPO_MAX_GROUP_ROLES + i % Q] = (float)b.blob[h.pair_off + i];
     if (tid < n_new) {
       const int m = sTakenNode[tid];
       const int rb = t.row_ptr[m], re = t.row_ptr[m + 1];
@@ -393,7 +524,7 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
       select_role_group(t, gid, excl_step, sRole[p], sPair + p * RBGTOPO_MAX_GROUP_ROLES, Q, K, dom, T, cnt, true, first, warp == 0 ? wave_i * 8 + 6 : -1,
                         sAcc + p * KS, sAccAv + p * KS, sPat + p * KS, sPatAv + p * KS, sList + p * KS,
                         sListAv + p * KS);
-      b.merged[(size_t)(h.rolerow_off + p) * KS + lane] = sList[p * KS + lane];
+      if (!DIRECT) b.merged[(size_t)(h.rolerow_off + p) * KS + lane] = sList[p * KS + lane];
     }
     __syncthreads();
     PCLK(wave_i * 8 + 4);
@@ -502,18 +633,30 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
         sTakenRole[lane] = trole;
       }
       if (lane == 0) {
-        b.status[step] = status;
-        b.domain_out[step] = dstar;
-        b.dstar[step] = dstar;
+        if (!DIRECT) {
+          b.status[step] = status;
+          b.domain_out[step] = dstar;
+          b.dstar[step] = dstar;
+        }
         sNew = ntaken;
         sStatus = status;
         sAny = ntaken > 0;
       }
     }
+    if (DIRECT && tid < h.P) sPlaced[sWRole[tid]] += sWCount[tid];  // planned, as the host's wave rule counts them
     __syncthreads();
     if (record && tid == 0) b.corr_cnt[step] = sCorrN;
     PCLK(wave_i * 8 + 5);
     ++wave_i;
+    if (DIRECT) {  // per-group result (what plan_results derives from the per-step outputs of the expanded plan)
+      g_stat = max(g_stat, sStatus);
+      if (dstar >= 0) g_dom = dstar;
+      g_i0 += h.R;
+      n_new = sNew;
+      if (excl_step && dstar >= 0 && sAny) fixed = dstar;
+      if (sStatus == RBGTOPO_GANG_FAILED) break;
+      continue;  // the next wave, if the role table has one
+    }
     if (h.next_step <= 0) break;
     n_new = sNew;
     if (excl_step && dstar >= 0 && sAny) fixed = dstar;
@@ -534,6 +677,18 @@ __global__ void __launch_bounds__(32 * MAXP, 4) k_plan_group(TopoDev t, BatchDev
     }
     step = h.next_step;
     h = load_hdr(b, step);
+  }
+  if (DIRECT) {
+    // a gang group is placed completely or not at all (plan_results does this on the host for expanded plans)
+    if (g_stat == RBGTOPO_GANG_FAILED || (gang && g_stat != RBGTOPO_PLACED_ALL)) {
+      for (int i = tid; i < g_pend; i += nthreads) b.assign[g_rep0 + i] = -1;
+      g_stat = RBGTOPO_GANG_FAILED;
+      g_dom = -1;
+    }
+    if (tid == 0) {
+      b.status[step] = g_stat;
+      b.domain_out[step] = excl_step ? g_dom : -1;
+    }
   }
   PCLK(31);
 #ifdef RBGTOPO_PHASE_CLOCKS

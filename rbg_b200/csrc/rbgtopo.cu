@@ -905,9 +905,9 @@ int launch_select_assign(rbgtopo_ctx* c, Batch* b, cudaStream_t s, const BatchDe
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        CK(cudaLaunchKernelEx(&cfg, k_plan_group, topo_dev(c), d, (int)b->m.max_q, pg.HT, pg.CAP, 0));
+        CK(cudaLaunchKernelEx(&cfg, k_plan_group<false>, topo_dev(c), d, (int)b->m.max_q, pg.HT, pg.CAP, 0));
       } else {
-        k_plan_group<<<pg.n0, pg.nth, pg.smem, s>>>(topo_dev(c), d, b->m.max_q, pg.HT, pg.CAP, 0);
+        k_plan_group<false><<<pg.n0, pg.nth, pg.smem, s>>>(topo_dev(c), d, b->m.max_q, pg.HT, pg.CAP, 0);
       }
       ++*launches;
     }
@@ -978,12 +978,12 @@ int run_batch(rbgtopo_ctx* c, Batch* b, int iters) {
       CK(cudaEventRecord(b->ev[2], s));
       CK(cudaStreamWaitEvent(s2, b->ev[2], 0));  // after the staging / the previous pass's k_plan_correct
       const size_t pg_smem = std::min(kFastSmemMax, std::max(pg.smem, (size_t)kSelectSmemKB * 1024));
-      if (kSelectFirst && pg.n0 > 0) k_plan_group<<<pg.n0, pg.nth, pg_smem, s2>>>(topo_dev(c), d, b->m.max_q, pg.HT, pg.CAP, 1);
+      if (kSelectFirst && pg.n0 > 0) k_plan_group<false><<<pg.n0, pg.nth, pg_smem, s2>>>(topo_dev(c), d, b->m.max_q, pg.HT, pg.CAP, 1);
       rc = launch_score(c, b, s);
       if (rc) return rc;
       ++launches;
       if (timed) CK(cudaEventRecord(b->it_ev[e0 + 1], s));
-      if (!kSelectFirst && pg.n0 > 0) k_plan_group<<<pg.n0, pg.nth, pg_smem, s2>>>(topo_dev(c), d, b->m.max_q, pg.HT, pg.CAP, 1);
+      if (!kSelectFirst && pg.n0 > 0) k_plan_group<false><<<pg.n0, pg.nth, pg_smem, s2>>>(topo_dev(c), d, b->m.max_q, pg.HT, pg.CAP, 1);
       if (pg.n0 > 0) {
         CK(cudaEventRecord(b->ev[3], s2));
         CK(cudaStreamWaitEvent(s, b->ev[3], 0));
@@ -1322,13 +1322,15 @@ int32_t rbgtopo_create(const rbgtopo_config* cfg, rbgtopo_ctx** out) {
   for (auto& e : c->stage_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CK(cudaFuncSetAttribute(k_select_assign_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
   CK(cudaFuncSetAttribute(k_shard_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
-  CK(cudaFuncSetAttribute(k_plan_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
+  CK(cudaFuncSetAttribute(k_plan_group<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
+  CK(cudaFuncSetAttribute(k_plan_group<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemMax));
+  CK(cudaFuncSetAttribute(k_plan_group<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(emit_tma_fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_tma_smem_bytes(kEmitStages)));
   // k_emit_tma and k_plan_group are meant to share an SM: both ask for the largest shared-memory carve-out,
   // otherwise the persistent emit CTA pins the SM at the small carve-out it needs alone and the CTAs of
   // k_plan_group (28 KB each) cannot be co-scheduled until it exits
   CK(cudaFuncSetAttribute(emit_tma_fn(), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(cudaFuncSetAttribute(k_plan_group, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_plan_group<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 #ifdef RBGTOPO_PHASE_CLOCKS
   {
     const int skip = getenv("RBGTOPO_DBG_SKIP") ? atoi(getenv("RBGTOPO_DBG_SKIP")) : 0;
@@ -2768,6 +2770,348 @@ rbgtopo_timing add_timing(const rbgtopo_timing& a, const rbgtopo_timing& b) {
 }
 }  // namespace
 
+namespace {
+// ---- rbgtopo_place_groups, direct path -------------------------------------------------------------------------------
+// No expanded plan and nothing per step on the host: the GROUPS blob goes up as it came (the upload is enqueued before
+// it is validated: bytes only), the host validates every group, checks the exactness bound and collects a handful of
+// maxima (per-shape caches: a fleet repeats a few templates), k_group_rtab derives the row table, k_emit_rows writes the
+// dense matrix and k_plan_group<true> — a programmatic dependent of it — replays each group's waves from its role
+// table.  8 CUDA calls and ~50 us of host time per call instead of ~20 calls and ~115 us.
+// Used for world == 1 with the default kernels; *handled = false -> the caller takes the staged path (plan_stage).
+const bool kNoDirect = getenv("RBGTOPO_NO_DIRECT") != nullptr;
+
+struct GroupFacts {
+  int pend = 0, nw = 0, max_p = 1, max_k = 1, i0_last = 0;
+  long long pcp = 0;  // closed neighbourhoods of the scheduled pods
+};
+// per-shape part of the facts (thread-local, 4 ways): valid shapes only
+struct ShapeFacts {
+  bool valid = false;
+  int q = 0, nw = 0, max_p = 1, max_k = 1, i0_last = 0;
+  long long pend = 0;
+  int32_t roles[4 * RBGTOPO_MAX_GROUP_ROLES];
+  int32_t pair[RBGTOPO_MAX_GROUP_ROLES * RBGTOPO_MAX_GROUP_ROLES];
+  long long role_bound[RBGTOPO_MAX_GROUP_ROLES];  // max over the waves a role appears in of sum_j pair*placed + min(need, cap)*F
+  bool match(const int32_t* r, const int32_t* p, int qq) const {
+    return valid && qq == q && memcmp(r, roles, (size_t)16 * qq) == 0 && memcmp(p, pair, (size_t)4 * qq * qq) == 0;
+  }
+};
+
+// Everything about group g that the direct path needs; the checks are those of plan_geometry's check_group /
+// size_group (same messages), the exactness bound is taken per role over its worst wave.
+// phase 1: the group record, role table and pair matrix (what the row table and the dense matrix depend on);
+// phase 2: the scheduled pods (ranges, neighbourhood sizes) and the exactness bound; phase 3 = both.
+int group_facts(const TopoHost& T, const int32_t* gb, int64_t words, int g, bool report, long long amax_limit, long long row_w,
+                GroupFacts* out, int phase = 3) {
+  auto in = [&](long long off, long long cnt) { return off >= 0 && cnt >= 0 && off + cnt <= words; };
+  const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
+  const int q = rec[3];
+  if (q < 1 || q > RBGTOPO_MAX_GROUP_ROLES) GROUP_FAIL(RBGTOPO_ELIMIT, "group %d: %d roles", g, q);
+  if (!in(rec[4], 4LL * q) || !in(rec[5], (long long)q * q) || !in(rec[7], 3LL * rec[6]))
+    GROUP_FAIL(RBGTOPO_EINVAL, "group %d: section out of bounds", g);
+  const int32_t* roles = gb + rec[4];
+  const int32_t* pair = gb + rec[5];
+  static thread_local ShapeFacts ways[4];
+  static thread_local int next_way = 0;
+  const ShapeFacts* sf = nullptr;
+  if (!report)
+    for (const ShapeFacts& w : ways)
+      if (w.match(roles, pair, q)) { sf = &w; break; }
+  const long long sat = 1LL << 40;
+  if (!sf) {
+    long long pend = 0;
+    for (int i = 0; i < q; ++i) {
+      if (roles[4 * i + 1] < 0 || (i && roles[4 * i] < roles[4 * (i - 1)]))
+        GROUP_FAIL(RBGTOPO_EINVAL, "group %d role %d: pending < 0 or levels not ascending", g, i);
+      if (roles[4 * i + 2] < 0 || roles[4 * i + 2] > RBGTOPO_MAX_FREE)
+        GROUP_FAIL(RBGTOPO_EINVAL, "group %d role %d: demand", g, i);
+      pend += roles[4 * i + 1];
+    }
+    if (pend > 0x3FFFFFFFLL) GROUP_FAIL(RBGTOPO_ELIMIT, "group %d: pending replicas", g);
+    for (int i = 0; i < q; ++i)
+      if (roles[4 * i + 3] & ~RBGTOPO_ROLE_EXCLUSIVE) GROUP_FAIL(RBGTOPO_EINVAL, "group %d role %d: unknown role flags", g, i);
+    for (int i = 0; i < q * q; ++i)
+      if (pair[i] < 0 || pair[i] > kMaxExactTerm) GROUP_FAIL(RBGTOPO_EINVAL, "group %d: pair weight out of [0, 2^24]", g);
+    ShapeFacts& w = ways[next_way];
+    next_way = (next_way + 1) % 4;
+    w.valid = false;
+    w.q = q;
+    memcpy(w.roles, roles, (size_t)16 * q);
+    memcpy(w.pair, pair, (size_t)4 * q * q);
+    w.pend = pend;
+    w.max_p = 1;
+    w.max_k = 1;
+    w.i0_last = 0;
+    for (int i = 0; i < q; ++i) w.role_bound[i] = 0;
+    int placed[RBGTOPO_MAX_GROUP_ROLES] = {0};
+    int i0 = 0;
+    w.nw = walk_waves(roles, q, [&](int, const PlanWave& pw) {
+      const int P = pw.size();
+      int n = 0;
+      for (int k = 0; k < P; ++k) {
+        const int ri = pw.role[k];
+        int need = 0;
+        long long bnd = 0;
+        for (int j = 0; j < q; ++j) {
+          if (pair[ri * q + j] > 0) need = (int)std::min<long long>((long long)need + roles[4 * j + 1] - placed[j], 1 << 30);
+          bnd = std::min(bnd + (long long)pair[ri * q + j] * placed[j], sat);
+        }
+        w.role_bound[ri] = std::max(w.role_bound[ri], bnd + (long long)std::min(need, RBGTOPO_NEED_CAP) * RBGTOPO_F_CAP);
+        n += pw.count[k];
+      }
+      w.max_p = std::max(w.max_p, P);
+      w.max_k = std::max(w.max_k, n);
+      w.i0_last = i0;
+      for (int k = 0; k < P; ++k) placed[pw.role[k]] += pw.count[k];
+      i0 += n;
+    });
+    w.valid = !report;
+    sf = &w;
+  }
+  if (phase & 1) {
+    if (rec[0] < 0 || rec[2] < -1 || rec[2] >= T.n_domains) GROUP_FAIL(RBGTOPO_EINVAL, "group %d: gid / fixed_domain", g);
+    if (rec[1] & ~(RBGTOPO_STEP_EXCLUSIVE | RBGTOPO_STEP_GANG)) GROUP_FAIL(RBGTOPO_EINVAL, "group %d: unknown flags 0x%x", g, rec[1]);
+    out->pend = (int)sf->pend;
+    out->nw = sf->nw;
+    out->max_p = sf->max_p;
+    out->max_k = sf->max_k;
+    out->i0_last = sf->i0_last;
+  }
+  if (!(phase & 2)) return RBGTOPO_OK;
+  long long pc = 0;
+  long long anch_w[RBGTOPO_MAX_GROUP_ROLES] = {0};
+  const int na = rec[6];
+  for (int a = 0; a < na; ++a) {
+    const int32_t* an = gb + rec[7] + 3 * a;
+    if (an[0] < 0 || an[0] >= T.n || an[1] < 0 || an[1] >= q || an[2] < 0 || an[2] > kMaxExactTerm)
+      GROUP_FAIL(RBGTOPO_EINVAL, "group %d anchor %d out of range", g, a);
+    pc += T.degp1 ? T.degp1[an[0]] : 1;
+    for (int ri = 0; ri < q; ++ri) anch_w[ri] = std::min(anch_w[ri] + (long long)pair[ri * q + an[1]] * an[2], sat);
+  }
+  if (pc > 0x3FFFFFFFLL) GROUP_FAIL(RBGTOPO_ELIMIT, "group %d: patch list exceeds 2^30 entries", g);
+  if (sf->nw > 0)
+    for (int ri = 0; ri < q; ++ri) {
+      if (roles[4 * ri + 1] <= 0) continue;  // a role without pending replicas has no row
+      const long long amax = std::min(anch_w[ri] + sf->role_bound[ri], sat);
+      if (amax >= amax_limit)
+        GROUP_FAIL(RBGTOPO_EINEXACT, "group %d role %d: max score bound >= 2^24 (anchor weight %lld x row weight %lld)", g, ri, amax, row_w);
+    }
+  out->pcp = pc;
+  return RBGTOPO_OK;
+}
+
+int place_groups_direct(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int32_t* assign, int32_t* status, int32_t* domain,
+                        std::vector<char>* dirty, bool* handled) {
+  *handled = false;
+  if (kNoDirect || c->cfg.world != 1 || !kSerialPlan || !kEmitSt || !kEmitRows || kVerifyPlan || kPerWavePlan) return RBGTOPO_OK;
+  if (words < RBGTOPO_HDR_WORDS || gb[0] != RBGTOPO_GROUPS_MAGIC || gb[1] != RBGTOPO_ABI_VERSION || gb[3] != words ||
+      words > 0x3FFFFFFFLL)
+    return RBGTOPO_OK;  // the staged path reports what is wrong with the header
+  const int ng = gb[2];
+  if (ng < 1 || (int64_t)RBGTOPO_HDR_WORDS + (int64_t)ng * RBGTOPO_GROUP_WORDS > words || ng >= kSplitMinGroups) return RBGTOPO_OK;
+  NvtxRange nv("rbgtopo:place_groups_direct");
+  const Topology& T = c->topo;
+  static const bool prof = kProfileHost;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto us = [](auto a, auto b2) { return std::chrono::duration<double, std::micro>(b2 - a).count(); };
+  const auto t0 = now();
+  Batch* b = nullptr;
+  int rc = acquire_batch(c, &b);
+  if (rc) return rc;
+  cudaStream_t s = stream_of(c, b);
+  auto done = [&](int r) {
+    if (r || !*handled) cudaStreamSynchronize(s);  // the early upload may still read the staging buffer the staged path re-uses
+    release_batch(c, b);
+    return r;
+  };
+  // staging layout: GROUPS blob | pad | launch order (<= ng ints)
+  const size_t perm_off = ((size_t)words + 3) & ~(size_t)3;
+  const size_t src_words = perm_off + (size_t)ng;
+  rc = [&]() -> int {
+    CK(b->h_in.reserve(src_words));
+    CK(b->gsrc.reserve(src_words));
+    b->tev = false;
+    b->perm_n = 0;
+    memcpy(b->h_in.p, gb, (size_t)words * 4);
+    CK(cudaMemcpyAsync(b->gsrc.p, b->h_in.p, (size_t)words * 4, cudaMemcpyHostToDevice, s));  // before validation: bytes only
+    return RBGTOPO_OK;
+  }();
+  if (rc) return done(rc);
+  const auto t1 = now();
+
+  // ---- pass 1: group records, role tables, pair matrices (per-shape caches) — all the row table and the dense
+  // matrix depend on; the launch order of k_plan_group from (scheduled pods + pending replicas) per group
+  TopoHost th;
+  th.n = T.n;
+  th.n_domains = T.n_domains;
+  th.degp1 = T.h_degp1.data();
+  th.max_degp1 = T.max_degp1;
+  th.wsum_max = T.wsum_max;
+  const long long row_w = T.wsum_max + RBGTOPO_SELF_W;
+  const long long amax_limit = ((1LL << 24) + row_w - 1) / row_w;
+  static thread_local std::vector<GroupFacts> facts;
+  facts.resize((size_t)ng);
+  int first_bad = ng;
+#pragma omp parallel for schedule(static) num_threads(kHostThreads) reduction(min : first_bad) if (ng >= kHostParallelMinGroups && kHostThreads > 1)
+  for (int g = 0; g < ng; ++g)
+    if (group_facts(th, gb, words, g, false, amax_limit, row_w, &facts[g], 1) != RBGTOPO_OK) first_bad = std::min(first_bad, g);
+  if (first_bad < ng) return done(group_facts(th, gb, words, first_bad, true, amax_limit, row_w, &facts[first_bad], 1));
+  long long pacc = 0, wmax = 1;
+  int max_q = 1, max_p = 1, n0 = 0;
+  bool any_excl = false;
+  for (int g = 0; g < ng; ++g) {
+    const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
+    const GroupFacts& f = facts[g];
+    if (rec[8] != pacc || rec[9] != f.pend) return done(fail(RBGTOPO_EINVAL, "group %d: bad assign_off/n_pending", g));
+    pacc += f.pend;
+    if (pacc > 0x3FFFFFF0LL) return done(fail(RBGTOPO_ELIMIT, "pending replicas exceed 2^30"));
+    if (f.nw > 0) {
+      ++n0;
+      max_q = std::max(max_q, rec[3]);
+      max_p = std::max(max_p, f.max_p);
+      any_excl |= (rec[1] & RBGTOPO_STEP_EXCLUSIVE) != 0;
+      wmax = std::max(wmax, (long long)f.pend + std::max(0, rec[6]));
+    }
+  }
+  if (gb[4] != pacc) return done(fail(RBGTOPO_EINVAL, "total pending mismatch"));
+  const long long total_r = pacc;
+  const long long segs = ((total_r + kEmitRowsBlock - 1) / kEmitRowsBlock) * c->lc;
+  if (segs > 0x7FFFFFF0LL) return done(RBGTOPO_OK);
+  // launch order of k_plan_group: groups with pending replicas, heaviest expected table first (see plan_geometry); the
+  // weight is the number of closed neighbourhoods the group's table will hold (scheduled pods + replicas to place)
+  {
+    int32_t* const perm = b->h_in.p + perm_off;
+    const int nb = 1024;
+    static thread_local std::vector<int> bucket, wkey;
+    bucket.assign(nb + 1, 0);
+    wkey.resize((size_t)ng);
+    for (int g = 0; g < ng; ++g) {
+      if (facts[g].nw <= 0) continue;
+      const long long w = (long long)facts[g].pend + std::max(0, gb[RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS + 6]);
+      wkey[g] = (nb - 1) - (int)(w * (nb - 1) / wmax);
+      bucket[wkey[g] + 1] += 1;
+    }
+    for (int k = 0; k < nb; ++k) bucket[k + 1] += bucket[k];
+    for (int g = 0; g < ng; ++g)
+      if (facts[g].nw > 0) perm[bucket[wkey[g]]++] = g;
+  }
+  const auto t2 = now();
+
+  // ---- device, first half: launch order up, row table, dense matrix (it runs under pass 2)
+  const size_t out_n = (size_t)total_r + 2 * (size_t)ng;
+  rc = [&]() -> int {
+    CK(b->matrix.reserve((size_t)std::max<long long>(1, total_r) * c->slab_stride));
+    CK(b->rtab.reserve((size_t)std::max<long long>(1, total_r)));
+    CK(b->out.reserve(out_n + 4));
+    CK(b->h_out.reserve(out_n + 4));
+    b->epoch = c->topo_epoch;
+    if (n0 > 0) {
+      CK(cudaMemcpyAsync(b->gsrc.p + perm_off, b->h_in.p + perm_off, (size_t)n0 * 4, cudaMemcpyHostToDevice, s));
+      k_group_rtab<<<(ng + RTAB_WARPS - 1) / RTAB_WARPS, 32 * RTAB_WARPS, 0, s>>>(b->gsrc.p, ng, b->rtab.p);
+      CK(cudaStreamWaitEvent(s, c->base_ready, 0));  // a pending snapshot refresh: base / free ...
+      CK(cudaStreamWaitEvent(s, c->topo_ready, 0));  // ... and the background order, both in front of the dense-matrix kernel
+      b->any_excl = any_excl;
+      const int erc = launch_emit_plan(c, b, s, ng, total_r);
+      if (erc) return erc;
+    }
+    return RBGTOPO_OK;
+  }();
+  if (rc) return done(rc);
+  const auto t2b = now();
+
+  // ---- pass 2: scheduled pods (ranges, neighbourhood sizes), exactness bound, table capacity
+  first_bad = ng;
+#pragma omp parallel for schedule(static) num_threads(kHostThreads) reduction(min : first_bad) if (ng >= kHostParallelMinGroups && kHostThreads > 1)
+  for (int g = 0; g < ng; ++g)
+    if (group_facts(th, gb, words, g, false, amax_limit, row_w, &facts[g], 2) != RBGTOPO_OK) first_bad = std::min(first_bad, g);
+  if (first_bad < ng) return done(group_facts(th, gb, words, first_bad, true, amax_limit, row_w, &facts[first_bad], 2));
+  long long max_cap = 0;
+  for (int g = 0; g < ng; ++g)
+    if (facts[g].nw > 0)
+      max_cap = std::max(max_cap, (long long)facts[g].i0_last + facts[g].pcp + (long long)facts[g].i0_last * T.max_degp1);  // the last wave's table
+  // launch geometry of k_plan_group (plan_group_cfg); what does not fit a CTA's shared memory takes the staged path
+  const int nth = std::max(128, 32 * max_p);
+  const int CAP = std::max(32, round_up((int)std::min<long long>(max_cap, 0x3FFFFFFF), 32));
+  int HT = 64;
+  while (HT <= CAP && HT < (1 << 20)) HT <<= 1;
+  const size_t smem = group_smem_bytes(max_q, nth / 32, HT, CAP);
+  if (max_cap > 0x3FFFFFFFLL || smem > kFastSmemMax) return done(RBGTOPO_OK);  // *handled stays false (the dense matrix was emitted in vain)
+  const auto t2c = now();
+
+  // ---- device, second half: selection as a programmatic dependent of the dense-matrix kernel, results
+  rc = [&]() -> int {
+    if (n0 > 0) {
+      BatchDev d{};
+      d.blob = b->gsrc.p;
+      d.n_steps = ng;
+      d.lc = c->lc;
+      d.chunk = c->chunk;
+      d.parts = 1;
+      d.matrix = b->matrix.p;
+      d.assign = b->out.p;
+      d.status = b->out.p + total_r;
+      d.domain_out = d.status + ng;
+      d.dstar = d.domain_out;
+      d.perm = b->gsrc.p + perm_off;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)n0);
+      cfg.blockDim = dim3((unsigned)nth);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = kNoPdl ? 0 : 1;
+      CK(cudaLaunchKernelEx(&cfg, k_plan_group<true>, topo_dev(c), d, (int)max_q, HT, CAP, 0));
+      CK(cudaMemcpyAsync(b->h_out.p, b->out.p, out_n * 4, cudaMemcpyDeviceToHost, s));
+    }
+    const auto t3 = now();
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    const auto t4 = now();
+    const int32_t* a = b->h_out.p;
+    if (total_r > 0) memcpy(assign, a, (size_t)total_r * 4);
+    if ((int)dirty->size() < ng) dirty->resize((size_t)ng, 0);
+    for (int g = 0; g < ng; ++g) {
+      const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
+      const bool excl = (rec[1] & RBGTOPO_STEP_EXCLUSIVE) != 0;
+      int st = RBGTOPO_PLACED_ALL, dm = excl ? rec[2] : -1;  // nothing pending: placed, the domain it occupies confirmed
+      if (facts[g].nw > 0) {
+        st = a[total_r + g];
+        dm = excl ? a[total_r + ng + g] : -1;
+      }
+      (*dirty)[g] = st == RBGTOPO_PLACED_PART;  // `need` of the later waves was predicted with every replica placed
+      if (status) status[g] = st;
+      if (domain) domain[g] = dm;
+    }
+    if (prof)
+      fprintf(stderr, "[rbgtopo direct] stage %.0f us, pass 1 %.0f us, enqueue 1 %.0f us, pass 2 %.0f us, enqueue 2 %.0f us, wait %.0f us, results %.0f us\n",
+              us(t0, t1), us(t1, t2), us(t2, t2b), us(t2b, t2c), us(t2c, t3), us(t3, t4), us(t4, now()));
+    return RBGTOPO_OK;
+  }();
+  if (rc) return done(rc);
+  {
+    const long long slab = c->slab_hi - c->slab_lo;
+    rbgtopo_timing tm{};
+    tm.scores = total_r * slab;
+    tm.algo_bytes = 4LL * total_r * slab + 4LL * words + 8LL * slab;
+    tm.launches = n0 > 0 ? 3 : 0;
+    tm.h2d_words = (int32_t)((long long)words + n0);
+    std::lock_guard<std::mutex> g(c->stat_mu);
+    c->last = tm;
+    c->last_score_ms.clear();
+    c->last_select_ms.clear();
+    c->calls += 1;
+    c->scores_total += tm.scores;
+    c->launches += tm.launches;
+  }
+  *handled = true;
+  return done(RBGTOPO_OK);
+}
+
+}  // namespace
+
 int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int32_t* assign,
                              int32_t* status, int32_t* domain) {
   if (!c || !gb || !assign) return fail(RBGTOPO_EINVAL, "null argument");
@@ -2785,11 +3129,17 @@ int32_t rbgtopo_place_groups(rbgtopo_ctx* c, const int32_t* gb, int64_t words, i
     // uploaded once.
     const int ng_all = words >= RBGTOPO_HDR_WORDS ? gb[2] : 0;
     const bool split = ng_all >= kSplitMinGroups && !kVerifyPlan;
+    // the direct path (no expanded plan, nothing per step on the host) when it applies
+    bool handled = false;
+    const int drc = place_groups_direct(c, gb, words, assign, status, domain, &dirty, &handled);
+    if (drc) return drc;
     Batch* b = nullptr;
-    int rc = acquire_batch(c, &b);
+    int rc = handled ? RBGTOPO_OK : acquire_batch(c, &b);
     if (rc) return rc;
     static const bool no_early = getenv("RBGTOPO_NO_EARLY_EMIT") != nullptr;  // A/B switch (profiles/README.md)
-    if (!split) {
+    if (handled) {
+      // results and dirty groups are in place: the host loop for the latter follows below, outside the lock
+    } else if (!split) {
       auto t0 = now();
       rc = plan_stage(c, b, gb, words, kSerialPlan && !no_early);  // early emit: the dense matrix starts while the host finishes the geometry
       auto t1 = now();
