@@ -246,10 +246,70 @@ def test_chained_batches_equal_separate_runs():
     eng.close()
 
 
+def test_place_groups_rejects_bad_blobs_and_recovers():
+    """Malformed GROUPS blobs through rbgtopo_place_groups: the same error codes on the direct path (default) and on the
+    staged one (the subprocess variant RBGTOPO_NO_DIRECT runs this test too), nothing placed, and the context keeps
+    working — the direct path has enqueued the upload (and, for errors of the second validation pass, the dense matrix)
+    by the time it finds them."""
+    from gpu_util import new_engine
+    from rbg_b200.engine import RbgTopoError
+    n = 2048
+    topo = synth.make_topology(n, seed=6, tiers=3)
+    eng = new_engine(topo)
+    mgr = B200TopoPodGroupManager(eng)
+    gb, _ = mgr.groups_blob(_fleet(n, 12, seed=2, excl_every=4, gang_every=5))
+    gb = np.ascontiguousarray(gb, dtype=np.int32)
+    good = eng.place_groups(gb)
+    HDR, GW = 8, 12
+
+    def rec(g):
+        return HDR + g * GW
+
+    def mutate(f):
+        b = gb.copy()
+        f(b)
+        return b
+
+    def set_(idx, v):
+        return lambda b: b.__setitem__(idx, v)
+
+    g3 = rec(3)
+    roles3, pair3, anc_n3, anc3 = int(gb[g3 + 4]), int(gb[g3 + 5]), int(gb[g3 + 6]), int(gb[g3 + 7])
+    cases = [
+        (set_(0, 0x12345), -1),                                   # magic
+        (set_(g3 + 3, 0), -6),                                    # q = 0 roles: limit
+        (set_(g3 + 3, 17), -6),                                   # q > 16
+        (set_(roles3 + 1, -2), -1),                               # pending < 0
+        (set_(roles3 + 2, 1 << 20), -1),                          # demand out of range
+        (set_(roles3 + 3, 0x40), -1),                             # unknown role flag
+        (set_(pair3, -1), -1),                                    # pair weight < 0
+        (set_(g3 + 1, 0x100), -1),                                # unknown group flags
+        (set_(g3 + 8, int(gb[g3 + 8]) + 1), -1),                  # assign_off does not continue the prefix
+        (set_(g3 + 2, 1 << 20), -1),                              # fixed_domain out of range
+    ]
+    g_anc = next(g for g in range(12) if int(gb[rec(g) + 6]) > 0)
+    a_off = int(gb[rec(g_anc) + 7])
+    q_anc, pair_anc, role_anc = int(gb[rec(g_anc) + 3]), int(gb[rec(g_anc) + 5]), int(gb[a_off + 1])
+    cases += [
+        (set_(pair_anc + 0 * q_anc + role_anc, 1 << 23), -4),     # exactness bound: anchor weight x row weight >= 2^24
+        (set_(a_off, n + 5), -1),                                 # scheduled pod on a node that does not exist
+        (set_(a_off + 1, 99), -1),                                # ... of a role that does not exist
+        (set_(a_off + 2, (1 << 24) + 1), -1),                     # ... with an inadmissible count
+    ]
+    for f, code in cases:
+        bad = mutate(f)
+        with pytest.raises(RbgTopoError) as ei:
+            eng.place_groups(bad)
+        assert ei.value.code == code, (code, str(ei.value))
+        again = eng.place_groups(gb)                              # the context is unharmed
+        assert all(np.array_equal(x, y) for x, y in zip(again, good))
+    eng.close()
+
+
 @pytest.mark.parametrize("var", ["RBGTOPO_VERIFY_PLAN", "RBGTOPO_PER_WAVE_PLAN", "RBGTOPO_SPLIT_MIN_GROUPS",
                                  "RBGTOPO_CONCURRENT_PLAN", "RBGTOPO_EMIT_TMA", "RBGTOPO_CONCURRENT_PLAN+RBGTOPO_EMIT_TMA",
                                  "RBGTOPO_EMIT_STEPS+RBGTOPO_VERIFY_PLAN", "RBGTOPO_KERNEL_TIMING", "RBGTOPO_NO_PDL",
-                                 "RBGTOPO_EMIT_ROWS"])
+                                 "RBGTOPO_EMIT_ROWS", "RBGTOPO_NO_DIRECT"])
 def test_plan_variants_in_a_subprocess(var):
     """The library reads its switches when it loads, hence the subprocess.
     RBGTOPO_VERIFY_PLAN: every place_groups / stage_groups call compares the plan k_expand_plan
@@ -261,7 +321,8 @@ def test_plan_variants_in_a_subprocess(var):
     RBGTOPO_EMIT_TMA: the dense rows of plans through k_emit_tma (TMA bulk stores) instead of k_emit_rows.
     RBGTOPO_EMIT_STEPS: the step-major dense-matrix kernel (k_score_emit<false, ETAB>) instead of k_emit_rows.
     RBGTOPO_KERNEL_TIMING / RBGTOPO_NO_PDL: an event between the two plan kernels / plain stream order instead of the
-    programmatic dependent launch.  RBGTOPO_EMIT_ROWS=1: one row per segment of k_emit_rows (the smallest segment)."""
+    programmatic dependent launch.  RBGTOPO_EMIT_ROWS=1: one row per segment of k_emit_rows (the smallest segment).
+    RBGTOPO_NO_DIRECT: rbgtopo_place_groups through the staged path (expanded plan, early emit) that world > 1 takes."""
     import os
     import subprocess
     import sys
