@@ -638,7 +638,7 @@ def run_config(D, args, cfg_name, with_clocks):
                e2e_ms=e2e_ms / steps, h2d=int(free0.nbytes + 4 * n_plan_words),
                # results read back per step: the assignment + (status, domain) per group on the direct path of
                # rbgtopo_place_groups (world == 1), per step of the expanded plan on the staged path
-               d2h=int(4 * (total_r + 2 * groups)) if (world == 1 and not os.environ.get("RBGTOPO_NO_DIRECT"))
+               d2h=int(4 * (total_r + 2 * groups)) if (mode in ("replicated", "groups") and not os.environ.get("RBGTOPO_NO_DIRECT"))
                else int(4 * (total_r + 2 * n_waves * groups)),
                n_nodes=n_nodes, groups=groups, total_r=total_r, edges=int(topo.e), slab=(lo, hi), mode=mode,
                topo=topo, specs=specs, what=cfg["what"], scaling=cfg["scaling"])
@@ -765,7 +765,7 @@ def run_ours(args):
                               "before it (rbgtopo_run_staged_chain); results of every slot re-checked after the timed region; ") +
                              "multi-wave plan resident in HBM (rbgtopo_stage_groups), base vector resident "
                              "(recomputed by update_nodes, which is inside the e2e leg)",
-                "e2e_leg": "rbgtopo_update_nodes + rbgtopo_place_groups with host buffers (world == 1: the direct path — GROUPS blob up, "
+                "e2e_leg": "rbgtopo_update_nodes + rbgtopo_place_groups with host buffers (the direct path — GROUPS blob up, "
                            "k_group_rtab, k_emit_rows, k_plan_group<direct>, results down; no expanded plan), median of 5 rounds of "
                            "K steps; marshalling RBG objects into the groups blob is the caller's (Go shim) job "
                            "and is outside",

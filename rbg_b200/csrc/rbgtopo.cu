@@ -2777,7 +2777,8 @@ namespace {
 // maxima (per-shape caches: a fleet repeats a few templates), k_group_rtab derives the row table, k_emit_rows writes the
 // dense matrix and k_plan_group<true> — a programmatic dependent of it — replays each group's waves from its role
 // table.  8 CUDA calls and ~50 us of host time per call instead of ~20 calls and ~115 us.
-// Used for world == 1 with the default kernels; *handled = false -> the caller takes the staged path (plan_stage).
+// Used with the default kernels (any world: selection is replicated); *handled = false -> the caller takes the staged
+// path (plan_stage).
 const bool kNoDirect = getenv("RBGTOPO_NO_DIRECT") != nullptr;
 
 struct GroupFacts {
@@ -2903,7 +2904,9 @@ int group_facts(const TopoHost& T, const int32_t* gb, int64_t words, int g, bool
 int place_groups_direct(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int32_t* assign, int32_t* status, int32_t* domain,
                         std::vector<char>* dirty, bool* handled) {
   *handled = false;
-  if (kNoDirect || c->cfg.world != 1 || !kSerialPlan || !kEmitSt || !kEmitRows || kVerifyPlan || kPerWavePlan) return RBGTOPO_OK;
+  // world > 1: replicated selection (every rank places every group over all nodes; the dense matrix and its corrections
+  // are limited to the rank's column slab by the kernels themselves), exactly as on the staged path
+  if (kNoDirect || !kSerialPlan || !kEmitSt || !kEmitRows || kVerifyPlan || kPerWavePlan) return RBGTOPO_OK;
   if (words < RBGTOPO_HDR_WORDS || gb[0] != RBGTOPO_GROUPS_MAGIC || gb[1] != RBGTOPO_ABI_VERSION || gb[3] != words ||
       words > 0x3FFFFFFFLL)
     return RBGTOPO_OK;  // the staged path reports what is wrong with the header
