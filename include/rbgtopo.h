@@ -204,12 +204,17 @@ int32_t rbgtopo_score_assign(rbgtopo_ctx* ctx, const int32_t* blob,
  * exceeded — feeds the placements of wave w back as anchors / consumed
  * capacity / fixed exclusive domain of wave w+1 (levels see earlier levels:
  * rolebasedgroup_controller.go:448-476), and applies gang all-or-nothing over
- * the whole group (k8s-scheduler-plugin/manager.go:131).  On the device this is
- * a multi-wave plan: the GROUPS blob is expanded into one step blob in HBM, one
- * launch scores the dense rows of every wave — it is started from inside the
- * staging, from an emit table built on the device, while the host still computes
- * the rest of the plan geometry — and one launch runs every group's waves back to
- * back.  The dense rows of a plan are in GROUP order: row i is the
+ * the whole group (k8s-scheduler-plugin/manager.go:131).  On the device the
+ * GROUPS blob itself is the plan: it is uploaded while the host still validates it,
+ * one small launch derives the row table of the dense matrix from it, one launch
+ * writes the dense rows of every wave, and one launch — a programmatic dependent
+ * of the former — replays every group's waves from its role table in one CTA
+ * (the direct path).  Groups whose table of patched nodes does not
+ * fit a CTA's shared memory, RBGTOPO_VERIFY_PLAN and the opt-in pipelines take
+ * the staged path instead: the blob is expanded into one step blob in HBM
+ * (rbgtopo_stage_groups below) with the dense-matrix launch started from inside the
+ * staging.  Same results, same error codes either way.
+ * The dense rows of a plan are in GROUP order: row i is the
  * i-th pending replica of the blob (assign[] order).  With world > 1 every rank calls it with
  * the same blob and gets the same result (replicated selection).  need_rho of a wave is
  * min(RBGTOPO_NEED_CAP, still-unplaced replicas of the roles q with
