@@ -474,6 +474,18 @@ int32_t rbgtopo_plan_describe(const int32_t* groups, int64_t groups_words,
                               int32_t* n_steps, int32_t* n_waves,
                               int64_t* plan_words);
 
+/* What the DIRECT path of rbgtopo_place_groups derives on the host (the code path the call uses, without a device):
+ * both validation passes — a malformed blob returns the code rbgtopo_place_groups returns — and
+ *   geom[0] pending replicas (dense rows)   [1] groups with pending replicas (= CTAs of the selection kernel)
+ *   geom[2] / [3] largest role count of a group / of a wave
+ *   geom[4] largest table capacity (closed neighbourhoods of the scheduled pods and of the replicas placed before the last
+ *           wave, + those replicas)   [5] threads per CTA   [6] / [7] hash-table and dense-view sizes of the selection kernel
+ * order[0 .. geom[1]) = the groups in the launch order of the selection kernel: descending (pending replicas + scheduled
+ * pods), ties in group order — CTA i runs on SM (i mod #SMs) for the whole kernel, so the heavy groups are dealt across
+ * the SMs.  deg_plus1 / wsum_max as for rbgtopo_plan_describe. */
+int32_t rbgtopo_place_describe(const int32_t* groups, int64_t groups_words, int32_t n_nodes, int32_t n_domains,
+                               const int32_t* deg_plus1, int64_t wsum_max, int32_t* order, int64_t order_cap, int32_t* geom);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,7 @@ SIGNATURES = {
     "rbgtopo_set_stream": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "rbgtopo_set_kernel_timing": (C.c_int32, [C.c_void_p, C.c_int32]),
     "rbgtopo_run_staged_chain": (C.c_int32, [C.c_void_p, i32p, C.c_int32, C.c_int32]),
+    "rbgtopo_place_describe": (C.c_int32, [i32p, C.c_int64, C.c_int32, C.c_int32, i32p, C.c_int64, i32p, C.c_int64, i32p]),
     "rbgtopo_last_timing": (C.c_int32, [C.c_void_p, C.POINTER(Timing)]),
     "rbgtopo_last_pass_times": (C.c_int32, [C.c_void_p, f32p, f32p, C.c_int32, i32p]),
     "rbgtopo_stats": (C.c_int32, [C.c_void_p, u64p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),

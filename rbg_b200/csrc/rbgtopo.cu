@@ -2901,6 +2901,76 @@ int group_facts(const TopoHost& T, const int32_t* gb, int64_t words, int g, bool
   return RBGTOPO_OK;
 }
 
+// What the direct path derives on the host, in two passes (pure host code: rbgtopo_place_describe runs it without a device).
+struct DirectGeom {
+  long long total_r = 0, max_cap = 0;
+  int n0 = 0, max_q = 1, max_p = 1, nth = 128, HT = 64, CAP = 32;
+  size_t smem = 0;
+  bool any_excl = false;
+};
+// pass 1: group records, role tables, pair matrices (per-shape caches), the prefix of the assignment offsets, and the
+// launch order of k_plan_group (perm[0 .. n0): groups with pending replicas, heaviest expected table first — the
+// weight is the number of closed neighbourhoods the table will hold: scheduled pods + replicas to place)
+int direct_pass1(const TopoHost& th, const int32_t* gb, int64_t words, int ng, long long amax_limit, long long row_w,
+                 std::vector<GroupFacts>& facts, int32_t* perm, DirectGeom* G) {
+  facts.resize((size_t)ng);
+  int first_bad = ng;
+#pragma omp parallel for schedule(static) num_threads(kHostThreads) reduction(min : first_bad) if (ng >= kHostParallelMinGroups && kHostThreads > 1)
+  for (int g = 0; g < ng; ++g)
+    if (group_facts(th, gb, words, g, false, amax_limit, row_w, &facts[g], 1) != RBGTOPO_OK) first_bad = std::min(first_bad, g);
+  if (first_bad < ng) return group_facts(th, gb, words, first_bad, true, amax_limit, row_w, &facts[first_bad], 1);
+  long long pacc = 0, wmax = 1;
+  for (int g = 0; g < ng; ++g) {
+    const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
+    const GroupFacts& f = facts[g];
+    if (rec[8] != pacc || rec[9] != f.pend) return fail(RBGTOPO_EINVAL, "group %d: bad assign_off/n_pending", g);
+    pacc += f.pend;
+    if (pacc > 0x3FFFFFF0LL) return fail(RBGTOPO_ELIMIT, "pending replicas exceed 2^30");
+    if (f.nw > 0) {
+      G->n0 += 1;
+      G->max_q = std::max(G->max_q, rec[3]);
+      G->max_p = std::max(G->max_p, f.max_p);
+      G->any_excl |= (rec[1] & RBGTOPO_STEP_EXCLUSIVE) != 0;
+      wmax = std::max(wmax, (long long)f.pend + std::max(0, rec[6]));
+    }
+  }
+  if (gb[4] != pacc) return fail(RBGTOPO_EINVAL, "total pending mismatch");
+  G->total_r = pacc;
+  const int nb = 1024;
+  static thread_local std::vector<int> bucket, wkey;
+  bucket.assign(nb + 1, 0);
+  wkey.resize((size_t)ng);
+  for (int g = 0; g < ng; ++g) {
+    if (facts[g].nw <= 0) continue;
+    const long long w = (long long)facts[g].pend + std::max(0, gb[RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS + 6]);
+    wkey[g] = (nb - 1) - (int)(w * (nb - 1) / wmax);
+    bucket[wkey[g] + 1] += 1;
+  }
+  for (int k = 0; k < nb; ++k) bucket[k + 1] += bucket[k];
+  for (int g = 0; g < ng; ++g)
+    if (facts[g].nw > 0) perm[bucket[wkey[g]]++] = g;  // stable: equal weights keep group order
+  return RBGTOPO_OK;
+}
+// pass 2: scheduled pods (ranges, neighbourhood sizes), the exactness bound, the table capacity and with it the launch
+// geometry of k_plan_group (as plan_group_cfg)
+int direct_pass2(const TopoHost& th, const int32_t* gb, int64_t words, int ng, long long amax_limit, long long row_w,
+                 std::vector<GroupFacts>& facts, DirectGeom* G) {
+  int first_bad = ng;
+#pragma omp parallel for schedule(static) num_threads(kHostThreads) reduction(min : first_bad) if (ng >= kHostParallelMinGroups && kHostThreads > 1)
+  for (int g = 0; g < ng; ++g)
+    if (group_facts(th, gb, words, g, false, amax_limit, row_w, &facts[g], 2) != RBGTOPO_OK) first_bad = std::min(first_bad, g);
+  if (first_bad < ng) return group_facts(th, gb, words, first_bad, true, amax_limit, row_w, &facts[first_bad], 2);
+  for (int g = 0; g < ng; ++g)
+    if (facts[g].nw > 0)
+      G->max_cap = std::max(G->max_cap, (long long)facts[g].i0_last + facts[g].pcp + (long long)facts[g].i0_last * th.max_degp1);  // the last wave's table
+  G->nth = std::max(128, 32 * G->max_p);
+  G->CAP = std::max(32, round_up((int)std::min<long long>(G->max_cap, 0x3FFFFFFF), 32));
+  G->HT = 64;
+  while (G->HT <= G->CAP && G->HT < (1 << 20)) G->HT <<= 1;
+  G->smem = group_smem_bytes(G->max_q, G->nth / 32, G->HT, G->CAP);
+  return RBGTOPO_OK;
+}
+
 int place_groups_direct(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int32_t* assign, int32_t* status, int32_t* domain,
                         std::vector<char>* dirty, bool* handled) {
   *handled = false;
@@ -2953,51 +3023,14 @@ int place_groups_direct(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int32_
   const long long row_w = T.wsum_max + RBGTOPO_SELF_W;
   const long long amax_limit = ((1LL << 24) + row_w - 1) / row_w;
   static thread_local std::vector<GroupFacts> facts;
-  facts.resize((size_t)ng);
-  int first_bad = ng;
-#pragma omp parallel for schedule(static) num_threads(kHostThreads) reduction(min : first_bad) if (ng >= kHostParallelMinGroups && kHostThreads > 1)
-  for (int g = 0; g < ng; ++g)
-    if (group_facts(th, gb, words, g, false, amax_limit, row_w, &facts[g], 1) != RBGTOPO_OK) first_bad = std::min(first_bad, g);
-  if (first_bad < ng) return done(group_facts(th, gb, words, first_bad, true, amax_limit, row_w, &facts[first_bad], 1));
-  long long pacc = 0, wmax = 1;
-  int max_q = 1, max_p = 1, n0 = 0;
-  bool any_excl = false;
-  for (int g = 0; g < ng; ++g) {
-    const int32_t* rec = gb + RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS;
-    const GroupFacts& f = facts[g];
-    if (rec[8] != pacc || rec[9] != f.pend) return done(fail(RBGTOPO_EINVAL, "group %d: bad assign_off/n_pending", g));
-    pacc += f.pend;
-    if (pacc > 0x3FFFFFF0LL) return done(fail(RBGTOPO_ELIMIT, "pending replicas exceed 2^30"));
-    if (f.nw > 0) {
-      ++n0;
-      max_q = std::max(max_q, rec[3]);
-      max_p = std::max(max_p, f.max_p);
-      any_excl |= (rec[1] & RBGTOPO_STEP_EXCLUSIVE) != 0;
-      wmax = std::max(wmax, (long long)f.pend + std::max(0, rec[6]));
-    }
-  }
-  if (gb[4] != pacc) return done(fail(RBGTOPO_EINVAL, "total pending mismatch"));
-  const long long total_r = pacc;
+  DirectGeom G;
+  rc = direct_pass1(th, gb, words, ng, amax_limit, row_w, facts, b->h_in.p + perm_off, &G);
+  if (rc) return done(rc);
+  const long long total_r = G.total_r;
+  const int n0 = G.n0, max_q = G.max_q;
+  const bool any_excl = G.any_excl;
   const long long segs = ((total_r + kEmitRowsBlock - 1) / kEmitRowsBlock) * c->lc;
   if (segs > 0x7FFFFFF0LL) return done(RBGTOPO_OK);
-  // launch order of k_plan_group: groups with pending replicas, heaviest expected table first (see plan_geometry); the
-  // weight is the number of closed neighbourhoods the group's table will hold (scheduled pods + replicas to place)
-  {
-    int32_t* const perm = b->h_in.p + perm_off;
-    const int nb = 1024;
-    static thread_local std::vector<int> bucket, wkey;
-    bucket.assign(nb + 1, 0);
-    wkey.resize((size_t)ng);
-    for (int g = 0; g < ng; ++g) {
-      if (facts[g].nw <= 0) continue;
-      const long long w = (long long)facts[g].pend + std::max(0, gb[RBGTOPO_HDR_WORDS + (int64_t)g * RBGTOPO_GROUP_WORDS + 6]);
-      wkey[g] = (nb - 1) - (int)(w * (nb - 1) / wmax);
-      bucket[wkey[g] + 1] += 1;
-    }
-    for (int k = 0; k < nb; ++k) bucket[k + 1] += bucket[k];
-    for (int g = 0; g < ng; ++g)
-      if (facts[g].nw > 0) perm[bucket[wkey[g]]++] = g;
-  }
   const auto t2 = now();
 
   // ---- device, first half: launch order up, row table, dense matrix (it runs under pass 2)
@@ -3023,22 +3056,12 @@ int place_groups_direct(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int32_
   const auto t2b = now();
 
   // ---- pass 2: scheduled pods (ranges, neighbourhood sizes), exactness bound, table capacity
-  first_bad = ng;
-#pragma omp parallel for schedule(static) num_threads(kHostThreads) reduction(min : first_bad) if (ng >= kHostParallelMinGroups && kHostThreads > 1)
-  for (int g = 0; g < ng; ++g)
-    if (group_facts(th, gb, words, g, false, amax_limit, row_w, &facts[g], 2) != RBGTOPO_OK) first_bad = std::min(first_bad, g);
-  if (first_bad < ng) return done(group_facts(th, gb, words, first_bad, true, amax_limit, row_w, &facts[first_bad], 2));
-  long long max_cap = 0;
-  for (int g = 0; g < ng; ++g)
-    if (facts[g].nw > 0)
-      max_cap = std::max(max_cap, (long long)facts[g].i0_last + facts[g].pcp + (long long)facts[g].i0_last * T.max_degp1);  // the last wave's table
-  // launch geometry of k_plan_group (plan_group_cfg); what does not fit a CTA's shared memory takes the staged path
-  const int nth = std::max(128, 32 * max_p);
-  const int CAP = std::max(32, round_up((int)std::min<long long>(max_cap, 0x3FFFFFFF), 32));
-  int HT = 64;
-  while (HT <= CAP && HT < (1 << 20)) HT <<= 1;
-  const size_t smem = group_smem_bytes(max_q, nth / 32, HT, CAP);
-  if (max_cap > 0x3FFFFFFFLL || smem > kFastSmemMax) return done(RBGTOPO_OK);  // *handled stays false (the dense matrix was emitted in vain)
+  rc = direct_pass2(th, gb, words, ng, amax_limit, row_w, facts, &G);
+  if (rc) return done(rc);
+  const int nth = G.nth, HT = G.HT, CAP = G.CAP;
+  const size_t smem = G.smem;
+  // what does not fit a CTA's shared memory takes the staged path (*handled stays false; the dense matrix was emitted in vain)
+  if (G.max_cap > 0x3FFFFFFFLL || smem > kFastSmemMax) return done(RBGTOPO_OK);
   const auto t2c = now();
 
   // ---- device, second half: selection as a programmatic dependent of the dense-matrix kernel, results
@@ -3242,6 +3265,46 @@ int32_t rbgtopo_plan_describe(const int32_t* gb, int64_t words, int32_t n_nodes,
   if (out_steps && out_cap_steps > 0)
     memcpy(out_steps, scratch->h_in.p + L.aux_off,
            (size_t)std::min<int64_t>(out_cap_steps, L.ns) * RBGTOPO_PLAN_STEP_WORDS * 4);
+  return RBGTOPO_OK;
+}
+
+int32_t rbgtopo_place_describe(const int32_t* gb, int64_t words, int32_t n_nodes, int32_t n_domains, const int32_t* deg_plus1,
+                               int64_t wsum_max, int32_t* order, int64_t order_cap, int32_t* geom) {
+  if (!gb || !geom) return fail(RBGTOPO_EINVAL, "null argument");
+  if (n_nodes < 1 || n_domains < 1 || wsum_max < 0) return fail(RBGTOPO_EINVAL, "n_nodes / n_domains / wsum_max");
+  if (words < RBGTOPO_HDR_WORDS || gb[0] != RBGTOPO_GROUPS_MAGIC || gb[1] != RBGTOPO_ABI_VERSION || gb[3] != words || words > 0x3FFFFFFFLL)
+    return fail(RBGTOPO_EINVAL, "bad groups blob header");
+  const int ng = gb[2];
+  if (ng < 0 || (int64_t)RBGTOPO_HDR_WORDS + (int64_t)ng * RBGTOPO_GROUP_WORDS > words) return fail(RBGTOPO_EINVAL, "group table exceeds blob");
+  TopoHost th;
+  th.n = n_nodes;
+  th.n_domains = n_domains;
+  th.degp1 = deg_plus1;
+  th.max_degp1 = 1;
+  if (deg_plus1)
+    for (int i = 0; i < n_nodes; ++i) {
+      if (deg_plus1[i] < 1) return fail(RBGTOPO_EINVAL, "deg_plus1[%d]", i);
+      th.max_degp1 = std::max(th.max_degp1, deg_plus1[i]);
+    }
+  th.wsum_max = wsum_max;
+  const long long row_w = wsum_max + RBGTOPO_SELF_W;
+  const long long amax_limit = ((1LL << 24) + row_w - 1) / row_w;
+  static thread_local std::vector<GroupFacts> facts;
+  static thread_local std::vector<int32_t> perm;
+  perm.assign((size_t)std::max(1, ng), 0);
+  DirectGeom G;
+  int rc = direct_pass1(th, gb, words, ng, amax_limit, row_w, facts, perm.data(), &G);
+  if (!rc) rc = direct_pass2(th, gb, words, ng, amax_limit, row_w, facts, &G);
+  if (rc) return rc;
+  geom[0] = (int32_t)G.total_r;
+  geom[1] = G.n0;
+  geom[2] = G.max_q;
+  geom[3] = G.max_p;
+  geom[4] = (int32_t)std::min<long long>(G.max_cap, 0x7FFFFFFF);
+  geom[5] = G.nth;
+  geom[6] = G.HT;
+  geom[7] = G.CAP;
+  if (order && order_cap > 0) memcpy(order, perm.data(), (size_t)std::min<int64_t>(order_cap, G.n0) * 4);
   return RBGTOPO_OK;
 }
 
