@@ -134,3 +134,17 @@ def test_shape_caches_do_not_leak_between_blobs(world):
     for _ in range(3):                                               # alternate: hits and misses interleave
         assert describe(mk(3), topo, degp1, wsum)[0] == 0
         assert describe(b, topo, degp1, wsum)[0] == -1
+
+
+def test_the_parallel_host_loops_in_a_subprocess():
+    """From RBGTOPO_HOST_PARALLEL_MIN groups on (default 4 096) the validation loops run under OpenMP with per-thread shape
+    caches; the switch is read when the library loads, hence the subprocess: the same tests with every loop parallel."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RBGTOPO_HOST_PARALLEL_MIN="1", RBGTOPO_HOST_THREADS="4")
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_place_describe.py", "tests/test_plan_describe.py", "-q", "-x",
+                        "-k", "not subprocess"], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout
