@@ -632,7 +632,8 @@ def run_config(D, args, cfg_name, with_clocks):
         rounds.append((time.perf_counter() - t0) * 1e3)
     e2e_ms = D.max_over_ranks(sorted(rounds)[len(rounds) // 2])
     if not churn:
-        assert np.array_equal(fetched[0], res[0]), "e2e placement differs from the staged path"
+        # the host-buffer entry point (direct path) against the staged plan the oracle checked above: assignment, status, domain
+        assert all(np.array_equal(x, y) for x, y in zip(fetched, res)), "e2e placement differs from the staged path"
     n_plan_words = eng.last_timing()["h2d_words"]          # GROUPS blob + per-step geometry words uploaded
     out.update(e2e_value=(scores_rank * world if (cfg["scaling"] == "weak" and not by_groups) else scores_all) * steps / (e2e_ms * 1e-3),
                e2e_ms=e2e_ms / steps, h2d=int(free0.nbytes + 4 * n_plan_words),
