@@ -1256,6 +1256,10 @@ int fence_batches(rbgtopo_ctx* c, bool sync) {
       CK(cudaStreamSynchronize(b->stream));
       CK(cudaStreamSynchronize(b->stream2));
     } else {
+      // an idle batch (staged and fetched, nothing enqueued since) has nothing in flight that could read the old snapshot
+      const bool idle = cudaStreamQuery(b->stream) == cudaSuccess && (!b->stream2 || cudaStreamQuery(b->stream2) == cudaSuccess);
+      (void)cudaGetLastError();  // cudaErrorNotReady is the answer, not an error
+      if (idle) continue;
       CK(cudaEventRecord(b->ev[6], b->stream));
       CK(cudaStreamWaitEvent(c->topo_stream, b->ev[6], 0));
     }
