@@ -251,40 +251,53 @@ __device__ __forceinline__ int wave_next(const int* roles, int q, int& cr, int& 
 
 // Row table of k_emit_rows (kernels.cuh) straight from the GROUPS blob, one warp per group: the group's dense rows
 // are [assign_off, + pending) in role order within a wave, waves in order — the row of a replica is a function of its
-// group alone, so the dense matrix needs nothing the host computes per step.  rbgtopo_place_groups' direct path.
+// group alone, so the dense matrix needs nothing the host computes per step.  rbgtopo_place_groups' direct path
+// launches it right behind the upload of the blob, i.e. BEFORE the host has validated the blob (the validation runs
+// meanwhile and the result is only used if it passes): every offset and count read from the blob is range-checked
+// against `words` / `n_rows` here, a group that fails a check writes nothing, and the wave loop ends when the rows run
+// out — garbage in, bounded garbage out, no out-of-range access.
 constexpr int RTAB_WARPS = 4;
-__global__ void __launch_bounds__(32 * RTAB_WARPS) k_group_rtab(const int* __restrict__ grp, int n_groups, int2* __restrict__ rtab) {
+__global__ void __launch_bounds__(32 * RTAB_WARPS) k_group_rtab(const int* __restrict__ grp, int words, int n_groups, int n_rows,
+                                                              int2* __restrict__ rtab) {
   __shared__ int sR[RTAB_WARPS][4 * RBGTOPO_MAX_GROUP_ROLES], sP[RTAB_WARPS][RBGTOPO_MAX_GROUP_ROLES * RBGTOPO_MAX_GROUP_ROLES];
   __shared__ int sPl[RTAB_WARPS][RBGTOPO_MAX_GROUP_ROLES], sRole[RTAB_WARPS][RBGTOPO_MAX_STEP_ROLES], sCount[RTAB_WARPS][RBGTOPO_MAX_STEP_ROLES];
-  __shared__ int sNP[RTAB_WARPS];
+  __shared__ int sRec[RTAB_WARPS][RBGTOPO_MAX_STEP_ROLES], sNP[RTAB_WARPS];
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const int g = blockIdx.x * RTAB_WARPS + wi;
   if (g >= n_groups) return;
-  const int* rec = grp + RBGTOPO_HDR_WORDS + (size_t)g * RBGTOPO_GROUP_WORDS;
+  const int* rec = grp + RBGTOPO_HDR_WORDS + (size_t)g * RBGTOPO_GROUP_WORDS;  // the host checked that the group table fits the blob
   const int gid = rec[0], q = rec[3];
+  const long long roff = rec[4], poff = rec[5];
   const bool excl = (rec[1] & RBGTOPO_STEP_EXCLUSIVE) != 0;
+  if (q < 1 || q > RBGTOPO_MAX_GROUP_ROLES || roff < 0 || roff + 4 * q > words || poff < 0 || poff + q * q > words) return;
   if (rec[9] <= 0) return;  // nothing pending: no rows
-  for (int i = lane; i < 4 * q; i += 32) sR[wi][i] = grp[rec[4] + i];
-  for (int i = lane; i < q * q; i += 32) sP[wi][i] = grp[rec[5] + i];
+  for (int i = lane; i < 4 * q; i += 32) sR[wi][i] = grp[roff + i];
+  for (int i = lane; i < q * q; i += 32) sP[wi][i] = grp[poff + i];
   if (lane < RBGTOPO_MAX_GROUP_ROLES) sPl[wi][lane] = 0;
   __syncwarp();
-  int cr = 0, tk = 0, row = rec[8];
-  while (true) {
+  int cr = 0, tk = 0;
+  long long row = rec[8];
+  if (row < 0) return;
+  while (row < n_rows) {
     if (lane == 0) sNP[wi] = wave_next(sR[wi], q, cr, tk, sRole[wi], sCount[wi]);  // the cursor lives in lane 0
     __syncwarp();
     const int P = sNP[wi];
     if (P == 0) break;
-    for (int p = 0; p < P; ++p) {
-      const int ri = sRole[wi][p], cnt = sCount[wi][p];
+    if (lane < P) {  // one role row per lane: its record
+      const int ri = sRole[wi][lane];
       int need = 0;
       for (int j = 0; j < q; ++j)
         if (sP[wi][ri * q + j] > 0) need += sR[wi][4 * j + 1] - sPl[wi][j];
       const bool rexcl = excl && (sR[wi][4 * ri + 3] & RBGTOPO_ROLE_EXCLUSIVE);
-      const int2 rr = make_int2(emit_pack_row(sR[wi][4 * ri + 2], min(need, RBGTOPO_NEED_CAP), rexcl), gid);
-      for (int k = lane; k < cnt; k += 32) rtab[row + k] = rr;
-      row += cnt;
+      sRec[wi][lane] = emit_pack_row(sR[wi][4 * ri + 2], max(0, min(need, RBGTOPO_NEED_CAP)), rexcl);
     }
     __syncwarp();
+    for (int p = 0; p < P; ++p) {
+      const int cnt = sCount[wi][p];  // 1 .. 32 by construction of the wave rule
+      const int2 rr = make_int2(sRec[wi][p], gid);
+      if (lane < cnt && row + lane < n_rows) rtab[row + lane] = rr;
+      row += cnt;
+    }
     if (lane < P) sPl[wi][sRole[wi][lane]] += sCount[wi][lane];
     __syncwarp();
   }

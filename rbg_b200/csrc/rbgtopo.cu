@@ -3004,6 +3004,7 @@ int place_groups_direct(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int32_
   // staging layout: GROUPS blob | pad | launch order (<= ng ints)
   const size_t perm_off = ((size_t)words + 3) & ~(size_t)3;
   const size_t src_words = perm_off + (size_t)ng;
+  bool rtab_early = false;
   rc = [&]() -> int {
     CK(b->h_in.reserve(src_words));
     CK(b->gsrc.reserve(src_words));
@@ -3011,6 +3012,12 @@ int place_groups_direct(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int32_
     b->perm_n = 0;
     memcpy(b->h_in.p, gb, (size_t)words * 4);
     CK(cudaMemcpyAsync(b->gsrc.p, b->h_in.p, (size_t)words * 4, cudaMemcpyHostToDevice, s));  // before validation: bytes only
+    // ... and the row table behind it, from the not yet validated blob (k_group_rtab range-checks what it reads), when the
+    // buffer of an earlier call is large enough: it is ready by the time pass 1 is through
+    if (gb[4] > 0 && (size_t)gb[4] <= b->rtab.cap) {
+      k_group_rtab<<<(ng + RTAB_WARPS - 1) / RTAB_WARPS, 32 * RTAB_WARPS, 0, s>>>(b->gsrc.p, (int)words, ng, gb[4], b->rtab.p);
+      rtab_early = true;
+    }
     return RBGTOPO_OK;
   }();
   if (rc) return done(rc);
@@ -3047,7 +3054,8 @@ int place_groups_direct(rbgtopo_ctx* c, const int32_t* gb, int64_t words, int32_
     b->epoch = c->topo_epoch;
     if (n0 > 0) {
       CK(cudaMemcpyAsync(b->gsrc.p + perm_off, b->h_in.p + perm_off, (size_t)n0 * 4, cudaMemcpyHostToDevice, s));
-      k_group_rtab<<<(ng + RTAB_WARPS - 1) / RTAB_WARPS, 32 * RTAB_WARPS, 0, s>>>(b->gsrc.p, ng, b->rtab.p);
+      if (!rtab_early)  // (pass 1 found gb[4] == total_r, which is what the early launch was given)
+        k_group_rtab<<<(ng + RTAB_WARPS - 1) / RTAB_WARPS, 32 * RTAB_WARPS, 0, s>>>(b->gsrc.p, (int)words, ng, (int)total_r, b->rtab.p);
       CK(cudaStreamWaitEvent(s, c->base_ready, 0));  // a pending snapshot refresh: base / free ...
       CK(cudaStreamWaitEvent(s, c->topo_ready, 0));  // ... and the background order, both in front of the dense-matrix kernel
       b->any_excl = any_excl;
